@@ -1,0 +1,214 @@
+/* rpe_c_api.h — C-ABI of the B200-native robust absolute-pose hot path.
+ *
+ * This is the drop-in boundary. The reference (ShudaLi/rgbd_pose_estimation) is a
+ * header-only C++ template library; the host side of this project keeps its class and function
+ * names in include/rpe/ (PoseAdapterBase.hpp, PnPPoseAdapter.hpp, AOPoseAdapter.hpp,
+ * NormalAOPoseAdapter.hpp, AOOnlyPoseAdapter.hpp, AbsoluteOrientation.hpp, P3P.hpp,
+ * AbsoluteOrientationNormal.hpp) and every estimator body marshals into the entry points
+ * declared here. Plain pointers and sizes only; no C++/torch/Eigen types cross this line.
+ *
+ * Reference interface each entry point replaces (paths into /root/reference):
+ *   rpe_upload            adapters' const-reference 3xN matrices         PnPPoseAdapter.hpp:96-99, AOPoseAdapter.hpp:88,
+ *                                                                        NormalAOPoseAdapter.hpp:83-84, AOOnlyPoseAdapter.hpp:94-95
+ *   rpe_ransac            shinji_ransac / shinji_ransac2                  AbsoluteOrientation.hpp:101-213
+ *                         shinji_prosac / shinji_kneip_ransac / _prosac  AbsoluteOrientation.hpp:215-271, 367-515
+ *                         kneip_ransac / kneip_prosac                    P3P.hpp:320-469
+ *                         nl_kneip_ransac / nl_shinji_ransac / nl_shinji_kneip_ransac
+ *                                                                        AbsoluteOrientationNormal.hpp:215-445
+ *                         (result -> setRcw/sett/setMaxVotes/setInlier: PoseAdapterBase.hpp:109-122,
+ *                          PnPPoseAdapter.hpp:196-202, AOPoseAdapter.hpp:171-184, NormalAOPoseAdapter.hpp:179-195)
+ *   rpe_refit             shinji_ls / shinji_ls1 / shinji_ls2            AbsoluteOrientation.hpp:273-342
+ *                         nl_shinji_kneip_ls                             AbsoluteOrientationNormal.hpp:447-552
+ *                         Gauss-Newton/LM on SE3 (north-star addition; no reference code)
+ *   rpe_update_num_iters  RANSACUpdateNumIters                           P3P.hpp:296-318
+ *   rpe_sample_table      RandomElements<int>::run                       Utility.hpp:125-156
+ *   rpe_prosac_table      ProsacSampler::sample + getSortedIdx           Utility.hpp:161-250, PnPPoseAdapter.hpp:239-255
+ *   rpe_sim_*             Simulator.hpp generators                       Simulator.hpp:158-367
+ *   rpe_ao / rpe_ao_ransac  extern "C" ao() / ao_ransac()                Library.cpp:17-75
+ *
+ * Error behaviour: the reference returns void, asserts in debug builds and std::abort()s inside
+ * SOPHUS_ENSURE (sophus/common.hpp:115-132). Every function here returns an int status instead
+ * (0 = RPE_OK, negative = error, text via rpe_last_error); a hypothesis whose rotation would have
+ * tripped SOPHUS_ENSURE is dropped (its vote slot is -1), nothing aborts.
+ *
+ * There is NO CPU fallback: rpe_create fails with RPE_ERR_NO_DEVICE when no CUDA device is
+ * usable, and every compute entry point requires a context.
+ */
+#ifndef RPE_C_API_H_
+#define RPE_C_API_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RPE_API_VERSION 1
+
+/* status codes */
+#define RPE_OK 0
+#define RPE_ERR_ARG (-1)
+#define RPE_ERR_CUDA (-2)
+#define RPE_ERR_STATE (-3)
+#define RPE_ERR_NO_DEVICE (-4)
+#define RPE_ERR_COMM (-5)
+#define RPE_ERR_NOMEM (-6)
+
+/* estimator families; numbering shared with the oracle (oracle/ransac.hpp) */
+#define RPE_SHINJI 0          /* 3-D/3-D only, 3-point sample            shinji_ransac(2)            */
+#define RPE_KNEIP 1           /* 2-D/3-D only, matrix-form rotation      kneip_ransac (P3P.hpp:365)  */
+#define RPE_SHINJI_KNEIP 2    /* 3-D + 2-D votes, slots {AO, P3P}        shinji_kneip_ransac         */
+#define RPE_NL_KNEIP 3        /* normal + 2-D votes, slot {P3P}          nl_kneip_ransac             */
+#define RPE_NL_SHINJI 4       /* normal + 3-D votes, slots {AO, nl_2p}   nl_shinji_ransac            */
+#define RPE_NL_SHINJI_KNEIP 5 /* all three votes, slots {AO, P3P, nl_2p} nl_shinji_kneip_ransac      */
+#define RPE_KNEIP_QUAT 6      /* 2-D only, quaternion-form rotation      kneip_prosac (P3P.hpp:442)  */
+
+/* refit kinds for rpe_refit */
+#define RPE_REFIT_KABSCH_INLIERS 0 /* shinji_ls / shinji_ls1: Kabsch over 3-D inliers of the last RANSAC  */
+#define RPE_REFIT_KABSCH_ALL 1     /* shinji_ls2: Kabsch over all correspondences                          */
+#define RPE_REFIT_GN 2             /* LM/Gauss-Newton on SE3 over the inliers of every modality            */
+#define RPE_REFIT_NL_SK_LS 3       /* nl_shinji_kneip_ls (3 weighted Kabsch + ray-intersection passes)     */
+
+typedef struct rpe_ctx rpe_ctx; /* opaque: one per (host thread, GPU, stream) */
+
+typedef struct rpe_result {
+  float R[9];       /* R_cw, row-major (same convention Library.cpp:66-69 writes out) */
+  float q[4];       /* unit quaternion x,y,z,w (Sophus/Eigen coefficient order)       */
+  float t[3];       /* t_w: x_c = R_cw x_w + t                                        */
+  int32_t max_votes;   /* adapter.getMaxVotes()                                       */
+  int32_t iter_final;  /* the in/out `Iter` after adaptive shrinking                  */
+  int32_t winner;      /* iteration*slots + slot of the accepted hypothesis, -1 none  */
+  int32_t n_slots;     /* hypothesis slots generated and scored (H * slots)           */
+  int32_t n_borderline;/* evaluations resolved by the exact-order path                */
+  int32_t flags;       /* bit0: worklist overflow -> whole frame rescored exactly     */
+  int32_t n_inliers[3];/* per modality column (2-D, 3-D, normal) of the winner        */
+  int32_t refit_ok;    /* 1 if the last rpe_refit produced a valid rotation           */
+  double  refit_cost;  /* GN: final weighted sum of squared residuals                  */
+  int32_t refit_evals; /* GN: cost/Jacobian evaluations executed                      */
+  int32_t reserved;
+} rpe_result;
+
+/* ---- library / device ---------------------------------------------------------------- */
+int rpe_version(void);
+const char* rpe_status_string(int status);
+int rpe_device_count(int* count);
+
+int rpe_create(int device, rpe_ctx** ctx);                          /* owns a non-blocking stream */
+int rpe_create_on_stream(int device, void* cuda_stream, rpe_ctx** ctx); /* borrows caller's stream */
+int rpe_destroy(rpe_ctx* ctx);
+const char* rpe_last_error(const rpe_ctx* ctx);
+void* rpe_stream(rpe_ctx* ctx);
+int rpe_sync(rpe_ctx* ctx);
+/* Number of kernels this context has launched since creation (bench.py's gpu_launches). */
+long long rpe_launch_count(const rpe_ctx* ctx);
+
+/* page-locked host memory for callers that want overlap of H2D with compute */
+int rpe_host_alloc(size_t bytes, void** ptr);
+int rpe_host_free(void* ptr);
+
+/* ---- correspondences -------------------------------------------------------------------
+ * Every array is column-major 3 x n float (n contiguous xyz triples: the memory layout of the
+ * Eigen::Matrix<float,Dynamic,Dynamic> the reference adapters hold). NULL = modality absent.
+ *   bv: bearing vectors (camera)   xc: points (camera)   nc: normals (camera)
+ *   xw: points (world)             nw: normals (world)
+ * rpe_upload copies from host memory (pinned or pageable) and repacks on the device;
+ * rpe_upload_device takes device pointers (no PCIe traffic). Both are asynchronous on the
+ * context's stream. `focal` is adapter.getFocal() (PoseAdapterBase.hpp:126).            */
+int rpe_upload(rpe_ctx* ctx, const float* bv, const float* xc, const float* nc, const float* xw, const float* nw, int n);
+int rpe_upload_device(rpe_ctx* ctx, const float* bv, const float* xc, const float* nc, const float* xw, const float* nw,
+                      int n);
+int rpe_num_correspondences(const rpe_ctx* ctx);
+
+/* ---- robust estimation ------------------------------------------------------------------
+ * samples: host int32 [H x 4] rows of correspondence indices (3 used by RPE_SHINJI), exactly the
+ *          draws RandomElements::run / ProsacSampler::sample would produce (see rpe_sample_table).
+ * H      : the caller's `Iter` on entry. All H iterations are generated and scored on the GPU;
+ *          the reference's sequential rule (strict `votes > max`, Iter = RANSACUpdateNumIters(..))
+ *          is then replayed on the device, so winner / max_votes / iter_final / mask are exactly
+ *          what the early-stopping CPU loop returns.
+ * thr3d  : dist_thre_3d_ (metres). cos_thr2d: cos(atan(thre_2d_/focal)) (P3P.hpp:323).
+ * cos_thrN: cos(nl_thre) (AbsoluteOrientationNormal.hpp:223). Unused ones are ignored.
+ * mask   : host int16 [n x cols] column-major, cols = 1 (KNEIP*), 2 (SHINJI, SHINJI_KNEIP), 3 (NL_*);
+ *          col 0 = 2-D, col 1 = 3-D, col 2 = normal flags — the matrix the reference hands to
+ *          setInlier(). May be NULL.
+ * rpe_ransac blocks until the result is on the host; rpe_ransac_async only enqueues (out/mask must
+ * then be page-locked and stay alive until rpe_sync).                                       */
+int rpe_ransac(rpe_ctx* ctx, int method, const int32_t* samples, int H, float thr3d, float cos_thr2d, float cos_thrN,
+               float confidence, rpe_result* out, int16_t* mask);
+int rpe_ransac_async(rpe_ctx* ctx, int method, const int32_t* samples, int H, float thr3d, float cos_thr2d,
+                     float cos_thrN, float confidence, rpe_result* out_pinned, int16_t* mask_pinned);
+
+/* Refit / refinement starting from the pose and inlier mask of the last rpe_ransac on ctx.
+ * weights: modality weights {w2d, w3d, wN} for RPE_REFIT_GN (NULL = {1,1,1}); per-correspondence
+ * n x 3 column-major weights for RPE_REFIT_NL_SK_LS (NULL = the adapters' default 1).
+ * max_iters: LM evaluations for RPE_REFIT_GN (<=0 -> 6).                                   */
+int rpe_refit(rpe_ctx* ctx, int kind, const float* weights, int max_iters, rpe_result* out);
+int rpe_refit_async(rpe_ctx* ctx, int kind, const float* weights, int max_iters, rpe_result* out_pinned);
+/* Override the pose/mask a refit starts from (setRcw/sett + setInlier on the adapter). */
+int rpe_set_pose(rpe_ctx* ctx, const float q_xyzw[4], const float t[3], int max_votes);
+int rpe_set_mask(rpe_ctx* ctx, const int16_t* mask, int cols);
+
+/* ---- stage access (parity tests, profiling, hypothesis-sharded multi-GPU) ---------------- */
+/* Generate hypotheses for iterations [0,H) from `samples`; nothing is scored. */
+int rpe_generate(rpe_ctx* ctx, int method, const int32_t* samples, int H);
+/* Copy back generated hypotheses: hyps [n_slots x 7] = qx,qy,qz,qw,tx,ty,tz ; valid [n_slots]. */
+int rpe_get_hypotheses(rpe_ctx* ctx, float* hyps, int32_t* valid, int n_slots);
+/* Replace the hypothesis set (scoring arbitrary poses). */
+int rpe_set_hypotheses(rpe_ctx* ctx, int method, const float* hyps, const int32_t* valid, int n_slots);
+/* Score slots [slot_begin, slot_end) of the current hypothesis set; votes stay on the device. */
+int rpe_score(rpe_ctx* ctx, int method, int slot_begin, int slot_end, float thr3d, float cos_thr2d, float cos_thrN);
+/* votes [n_slots] int32, -1 = empty slot. */
+int rpe_get_votes(rpe_ctx* ctx, int32_t* votes, int n_slots);
+int rpe_set_votes(rpe_ctx* ctx, const int32_t* votes, int n_slots);
+/* Device pointer of the votes array (for NCCL all-gather by the caller in sharded mode). */
+int32_t* rpe_votes_device_ptr(rpe_ctx* ctx);
+/* Replay the adaptive rule over the current votes, build the winner's mask. */
+int rpe_finish(rpe_ctx* ctx, int method, int H, float thr3d, float cos_thr2d, float cos_thrN, float confidence,
+               rpe_result* out, int16_t* mask);
+
+/* ---- host-side helpers that the reference computes on the CPU too ------------------------- */
+/* RANSACUpdateNumIters<float> with the bit-reproducible log of include/rpe/det_math.h. */
+int rpe_update_num_iters(float p, float ep, int model_points, int max_iters);
+/* H consecutive RandomElements<int>::run(m) draws. The generator restates glibc's rand()
+ * (TYPE_3, what the reference's ::rand() is) from `seed`; seed 1 == a process that never
+ * called srand(). Rows are padded to 4 with -1. */
+int rpe_sample_table(uint32_t seed, int n, int m, int H, int32_t* samples);
+/* H consecutive ProsacSampler draws mapped through the descending-weight order. */
+int rpe_prosac_table(uint32_t seed, int n, int m, int H, const float* weights, int32_t* samples);
+
+/* ---- synthetic correspondences (Simulator.hpp) -------------------------------------------- */
+/* pose: R = Rz*Ry*Rx from uniform angles (Simulator.hpp:23-83, use_gaussian=false), t = size*U(-1,1)^3 (:16-21) */
+int rpe_sim_pose(uint64_t seed, float max_angle_rad, float t_size, float q_xyzw[4], float t[3]);
+/* simulate_3d_3d_correspondences (Simulator.hpp:268-314). Q = noisy/outlier world points, P = clean camera points. */
+int rpe_sim_3d_3d(uint64_t seed, const float q_xyzw[4], const float t[3], int n, float noise, float outlier_ratio,
+                  float min_depth, float max_depth, float f, int use_gaussian, float* Q_xw, float* P_xc, float* weights3);
+/* simulate_2d_3d_correspondences (:175-233). U = unit bearing vectors. */
+int rpe_sim_2d_3d(uint64_t seed, const float q_xyzw[4], const float t[3], int n, float noise_px, float outlier_ratio,
+                  float min_depth, float max_depth, float f, int use_gaussian, float* Q_xw, float* U_bv, float* P_gt,
+                  float* weights3);
+/* simulate_2d_3d_nl_correspondences (:316-367). */
+int rpe_sim_2d_3d_nl(uint64_t seed, const float q_xyzw[4], const float t[3], int n, float n2d, float or2d, float n3d,
+                     float or3d, float nnl, float ornl, float min_depth, float max_depth, float f, int use_gaussian,
+                     float* Q_xw, float* M_nw, float* P_xc, float* N_nc, float* U_bv, float* weights3);
+
+/* ---- the reference's own C shim (Library.cpp:17-75), same argument meaning ------------------ */
+/* x_w, x_c: 3 x n column-major; R_cw out row-major 9; t out 3. ao = shinji_ls2; ao_ransac =
+ * shinji_ransac2(thr 0.1, 1000 iterations, confidence 0.99999) + shinji_ls1. */
+int rpe_ao(const float* x_w, const float* x_c, int n, float* R_cw, float* t);
+int rpe_ao_ransac(const float* x_w, const float* x_c, int n, float* R_cw, float* t);
+
+/* ---- microbenchmarks used by bench.py for the roofline denominators ------------------------ */
+/* Sustained FP32 FFMA throughput of the device in TFLOP/s (2 flop per FMA), measured with CUDA
+ * events over `ms_target` milliseconds of dependent-chain-free FFMA work. */
+int rpe_measure_ffma_tflops(rpe_ctx* ctx, int ms_target, double* tflops_scalar, double* tflops_packed);
+/* Device time in ms of the last call's stages, measured with CUDA events on the context's stream:
+ * [0] upload+pack [1] generate [2] score (fast + exact fix-up) [3] replay [4] mask+refit [5] GN [6] total */
+int rpe_last_stage_ms(rpe_ctx* ctx, float ms[8]);
+int rpe_enable_stage_timing(rpe_ctx* ctx, int enable);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* RPE_C_API_H_ */

@@ -1,0 +1,368 @@
+"""ctypes binding of include/rpe_c_api.h.
+
+Everything here is plumbing: argument marshalling into the C-ABI of ``librpe_b200.so``.
+No arithmetic of the hot path is done in Python, and nothing under ``oracle/`` is imported.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+lib_path = os.path.join(_HERE, "librpe_b200.so")
+
+METHODS = {
+    "shinji": 0,            # shinji_ransac / shinji_ransac2     AbsoluteOrientation.hpp:101-213
+    "kneip": 1,             # kneip_ransac                       P3P.hpp:320-392
+    "shinji_kneip": 2,      # shinji_kneip_ransac                AbsoluteOrientation.hpp:367-438
+    "nl_kneip": 3,          # nl_kneip_ransac                    AbsoluteOrientationNormal.hpp:215-284
+    "nl_shinji": 4,         # nl_shinji_ransac                   AbsoluteOrientationNormal.hpp:286-354
+    "nl_shinji_kneip": 5,   # nl_shinji_kneip_ransac             AbsoluteOrientationNormal.hpp:356-445
+    "kneip_quat": 6,        # kneip_prosac's scoring form        P3P.hpp:439-453
+}
+REFITS = {"kabsch_inliers": 0, "kabsch_all": 1, "gn": 2, "nl_sk_ls": 3}
+
+
+def method_slots(m: int) -> int:
+    return 2 if m in (2, 4) else (3 if m == 5 else 1)
+
+
+def method_mask_cols(m: int) -> int:
+    return 1 if m in (1, 6) else (2 if m in (0, 2) else 3)
+
+
+def method_sample_size(m: int) -> int:
+    return 3 if m == 0 else 4
+
+
+class RpeError(RuntimeError):
+    pass
+
+
+class _Result(C.Structure):
+    _fields_ = [
+        ("R", C.c_float * 9), ("q", C.c_float * 4), ("t", C.c_float * 3),
+        ("max_votes", C.c_int32), ("iter_final", C.c_int32), ("winner", C.c_int32), ("n_slots", C.c_int32),
+        ("n_borderline", C.c_int32), ("flags", C.c_int32), ("n_inliers", C.c_int32 * 3), ("refit_ok", C.c_int32),
+        ("refit_cost", C.c_double), ("refit_evals", C.c_int32), ("reserved", C.c_int32),
+    ]
+
+    def to_dict(self):
+        return {
+            "R": np.array(self.R, dtype=np.float32).reshape(3, 3), "q": np.array(self.q, dtype=np.float32),
+            "t": np.array(self.t, dtype=np.float32), "max_votes": int(self.max_votes),
+            "iter_final": int(self.iter_final), "winner": int(self.winner), "n_slots": int(self.n_slots),
+            "n_borderline": int(self.n_borderline), "flags": int(self.flags),
+            "n_inliers": [int(v) for v in self.n_inliers], "refit_ok": int(self.refit_ok),
+            "refit_cost": float(self.refit_cost), "refit_evals": int(self.refit_evals),
+        }
+
+
+def _load():
+    if not os.path.exists(lib_path):
+        raise RpeError(
+            f"{lib_path} is missing: the CUDA library has not been built. There is no CPU fallback; "
+            "run `python -c 'import __graft_entry__ as g; g.build()'` (or `make -C rgbd_pose_estimation_b200/csrc`).")
+    return C.CDLL(lib_path)
+
+
+lib = _load()
+
+_fp = C.POINTER(C.c_float)
+_ip = C.POINTER(C.c_int32)
+_sp = C.POINTER(C.c_int16)
+_vp = C.c_void_p
+
+
+def _sig(name, restype, argtypes):
+    fn = getattr(lib, name)
+    fn.restype = restype
+    fn.argtypes = argtypes
+    return fn
+
+
+_sig("rpe_version", C.c_int, [])
+_sig("rpe_status_string", C.c_char_p, [C.c_int])
+_sig("rpe_device_count", C.c_int, [C.POINTER(C.c_int)])
+_sig("rpe_create", C.c_int, [C.c_int, C.POINTER(_vp)])
+_sig("rpe_create_on_stream", C.c_int, [C.c_int, _vp, C.POINTER(_vp)])
+_sig("rpe_destroy", C.c_int, [_vp])
+_sig("rpe_last_error", C.c_char_p, [_vp])
+_sig("rpe_stream", _vp, [_vp])
+_sig("rpe_sync", C.c_int, [_vp])
+_sig("rpe_launch_count", C.c_longlong, [_vp])
+_sig("rpe_host_alloc", C.c_int, [C.c_size_t, C.POINTER(_vp)])
+_sig("rpe_host_free", C.c_int, [_vp])
+_sig("rpe_upload", C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, C.c_int])
+_sig("rpe_upload_device", C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, C.c_int])
+_sig("rpe_num_correspondences", C.c_int, [_vp])
+_sig("rpe_ransac", C.c_int, [_vp, C.c_int, _vp, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float,
+                             C.POINTER(_Result), _vp])
+_sig("rpe_ransac_async", C.c_int, [_vp, C.c_int, _vp, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float,
+                                   C.POINTER(_Result), _vp])
+_sig("rpe_refit", C.c_int, [_vp, C.c_int, _vp, C.c_int, C.POINTER(_Result)])
+_sig("rpe_refit_async", C.c_int, [_vp, C.c_int, _vp, C.c_int, C.POINTER(_Result)])
+_sig("rpe_set_pose", C.c_int, [_vp, _vp, _vp, C.c_int])
+_sig("rpe_set_mask", C.c_int, [_vp, _vp, C.c_int])
+_sig("rpe_generate", C.c_int, [_vp, C.c_int, _vp, C.c_int])
+_sig("rpe_get_hypotheses", C.c_int, [_vp, _vp, _vp, C.c_int])
+_sig("rpe_set_hypotheses", C.c_int, [_vp, C.c_int, _vp, _vp, C.c_int])
+_sig("rpe_score", C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float])
+_sig("rpe_get_votes", C.c_int, [_vp, _vp, C.c_int])
+_sig("rpe_set_votes", C.c_int, [_vp, _vp, C.c_int])
+_sig("rpe_votes_device_ptr", _vp, [_vp])
+_sig("rpe_finish", C.c_int, [_vp, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.POINTER(_Result), _vp])
+_sig("rpe_update_num_iters", C.c_int, [C.c_float, C.c_float, C.c_int, C.c_int])
+_sig("rpe_sample_table", C.c_int, [C.c_uint32, C.c_int, C.c_int, C.c_int, _vp])
+_sig("rpe_prosac_table", C.c_int, [C.c_uint32, C.c_int, C.c_int, C.c_int, _vp, _vp])
+_sig("rpe_sim_pose", C.c_int, [C.c_uint64, C.c_float, C.c_float, _vp, _vp])
+_sig("rpe_sim_3d_3d", C.c_int, [C.c_uint64, _vp, _vp, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
+                                C.c_int, _vp, _vp, _vp])
+_sig("rpe_sim_2d_3d", C.c_int, [C.c_uint64, _vp, _vp, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
+                                C.c_int, _vp, _vp, _vp, _vp])
+_sig("rpe_sim_2d_3d_nl", C.c_int, [C.c_uint64, _vp, _vp, C.c_int] + [C.c_float] * 9 + [C.c_int] + [_vp] * 6)
+_sig("rpe_ao", C.c_int, [_vp, _vp, C.c_int, _vp, _vp])
+_sig("rpe_ao_ransac", C.c_int, [_vp, _vp, C.c_int, _vp, _vp])
+_sig("rpe_measure_ffma_tflops", C.c_int, [_vp, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)])
+_sig("rpe_last_stage_ms", C.c_int, [_vp, _vp])
+_sig("rpe_enable_stage_timing", C.c_int, [_vp, C.c_int])
+_sig("rpe_debug_set_packed", C.c_int, [C.c_int])
+
+# every symbol include/rpe_c_api.h declares (tests check the header against this list and the .so)
+DECLARED_SYMBOLS = [
+    "rpe_version", "rpe_status_string", "rpe_device_count", "rpe_create", "rpe_create_on_stream", "rpe_destroy",
+    "rpe_last_error", "rpe_stream", "rpe_sync", "rpe_launch_count", "rpe_host_alloc", "rpe_host_free", "rpe_upload",
+    "rpe_upload_device", "rpe_num_correspondences", "rpe_ransac", "rpe_ransac_async", "rpe_refit", "rpe_refit_async",
+    "rpe_set_pose", "rpe_set_mask", "rpe_generate", "rpe_get_hypotheses", "rpe_set_hypotheses", "rpe_score",
+    "rpe_get_votes", "rpe_set_votes", "rpe_votes_device_ptr", "rpe_finish", "rpe_update_num_iters", "rpe_sample_table",
+    "rpe_prosac_table", "rpe_sim_pose", "rpe_sim_3d_3d", "rpe_sim_2d_3d", "rpe_sim_2d_3d_nl", "rpe_ao", "rpe_ao_ransac",
+    "rpe_measure_ffma_tflops", "rpe_last_stage_ms", "rpe_enable_stage_timing",
+]
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return C.c_void_p(a)
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _f32(a):
+    if a is None:
+        return None
+    a = np.asarray(a)
+    if a.dtype != np.float32 or not a.flags["C_CONTIGUOUS"]:
+        a = np.ascontiguousarray(a, dtype=np.float32)
+    return a
+
+
+def _check(rc, ctx=None):
+    if rc != 0:
+        msg = lib.rpe_status_string(rc).decode()
+        if ctx is not None:
+            msg += ": " + lib.rpe_last_error(ctx).decode()
+        raise RpeError(f"rpe error {rc}: {msg}")
+
+
+# ---- host helpers ------------------------------------------------------------------------------
+def sample_table(seed: int, n: int, m: int, H: int) -> np.ndarray:
+    out = np.empty((H, 4), dtype=np.int32)
+    _check(lib.rpe_sample_table(seed, n, m, H, _ptr(out)))
+    return out
+
+
+def prosac_table(seed: int, n: int, m: int, H: int, weights=None) -> np.ndarray:
+    out = np.empty((H, 4), dtype=np.int32)
+    w = _f32(weights)
+    _check(lib.rpe_prosac_table(seed, n, m, H, _ptr(w), _ptr(out)))
+    return out
+
+
+def update_num_iters(p: float, ep: float, model_points: int, max_iters: int) -> int:
+    return int(lib.rpe_update_num_iters(p, ep, model_points, max_iters))
+
+
+def sim_pose(seed: int, max_angle: float = np.pi / 2, t_size: float = 5.0):
+    q = np.empty(4, np.float32)
+    t = np.empty(3, np.float32)
+    _check(lib.rpe_sim_pose(seed, max_angle, t_size, _ptr(q), _ptr(t)))
+    return q, t
+
+
+def sim_3d_3d(seed, q, t, n, noise=0.1, outlier_ratio=0.5, min_depth=0.4, max_depth=8.0, f=585.0, gaussian=True):
+    """Points are returned as (n, 3) float32 arrays == column-major 3 x n in memory."""
+    Q = np.empty((n, 3), np.float32)
+    P = np.empty((n, 3), np.float32)
+    W = np.zeros((3, n), np.float32)  # n x 3 column-major
+    _check(lib.rpe_sim_3d_3d(seed, _ptr(_f32(q)), _ptr(_f32(t)), n, noise, outlier_ratio, min_depth, max_depth, f,
+                             1 if gaussian else 0, _ptr(Q), _ptr(P), _ptr(W)))
+    return Q, P, W
+
+
+def sim_2d_3d(seed, q, t, n, noise_px=1.0, outlier_ratio=0.7, min_depth=0.4, max_depth=8.0, f=585.0, gaussian=True):
+    Q = np.empty((n, 3), np.float32)
+    U = np.empty((n, 3), np.float32)
+    P = np.empty((n, 3), np.float32)
+    W = np.zeros((3, n), np.float32)
+    _check(lib.rpe_sim_2d_3d(seed, _ptr(_f32(q)), _ptr(_f32(t)), n, noise_px, outlier_ratio, min_depth, max_depth, f,
+                             1 if gaussian else 0, _ptr(Q), _ptr(U), _ptr(P), _ptr(W)))
+    return Q, U, P, W
+
+
+def sim_2d_3d_nl(seed, q, t, n, n2d=1.0, or2d=0.3, n3d=0.05, or3d=0.3, nnl=np.deg2rad(2.0), ornl=0.3, min_depth=0.4,
+                 max_depth=8.0, f=585.0, gaussian=True):
+    Q = np.empty((n, 3), np.float32)
+    M = np.empty((n, 3), np.float32)
+    P = np.empty((n, 3), np.float32)
+    N = np.empty((n, 3), np.float32)
+    U = np.empty((n, 3), np.float32)
+    W = np.zeros((3, n), np.float32)
+    _check(lib.rpe_sim_2d_3d_nl(seed, _ptr(_f32(q)), _ptr(_f32(t)), n, n2d, or2d, n3d, or3d, nnl, ornl, min_depth,
+                                max_depth, f, 1 if gaussian else 0, _ptr(Q), _ptr(M), _ptr(P), _ptr(N), _ptr(U),
+                                _ptr(W)))
+    return {"xw": Q, "nw": M, "xc": P, "nc": N, "bv": U, "weights": W}
+
+
+# ---- device context ---------------------------------------------------------------------------
+class Context:
+    """One rpe_ctx (one GPU, one stream). Arrays are (n, 3) float32 == the reference's 3 x n column-major."""
+
+    def __init__(self, device: int = 0, stream: int | None = None):
+        self._h = C.c_void_p()
+        if stream is None:
+            _check(lib.rpe_create(device, C.byref(self._h)))
+        else:
+            _check(lib.rpe_create_on_stream(device, C.c_void_p(stream), C.byref(self._h)))
+        self._keep = []
+        self.n = 0
+
+    def close(self):
+        if self._h:
+            lib.rpe_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    @property
+    def handle(self):
+        return self._h
+
+    def upload(self, bv=None, xc=None, nc=None, xw=None, nw=None):
+        arrs = [_f32(a) for a in (bv, xc, nc, xw, nw)]
+        n = next(a.shape[0] for a in arrs if a is not None)
+        for a in arrs:
+            if a is not None and a.shape != (n, 3):
+                raise ValueError("correspondence arrays must be (n, 3)")
+        self._keep = arrs  # host buffers must outlive the asynchronous copy
+        self.n = n
+        _check(lib.rpe_upload(self._h, *[_ptr(a) for a in arrs], n), self._h)
+
+    def upload_device(self, n, bv=None, xc=None, nc=None, xw=None, nw=None):
+        """Device pointers (ints), e.g. torch tensor.data_ptr()."""
+        self.n = n
+        _check(lib.rpe_upload_device(self._h, *[_ptr(a) for a in (bv, xc, nc, xw, nw)], n), self._h)
+
+    def ransac(self, method, samples, thr3d=0.0, cos_thr2d=0.0, cos_thrN=0.0, confidence=0.99, want_mask=True):
+        m = METHODS[method] if isinstance(method, str) else method
+        samples = np.ascontiguousarray(samples, dtype=np.int32)
+        H = samples.shape[0]
+        res = _Result()
+        mask = np.empty((method_mask_cols(m), self.n), np.int16) if want_mask else None
+        _check(lib.rpe_ransac(self._h, m, _ptr(samples), H, thr3d, cos_thr2d, cos_thrN, confidence, C.byref(res),
+                              _ptr(mask)), self._h)
+        d = res.to_dict()
+        d["mask"] = mask  # (cols, n): row k == column k of the reference's n x cols matrix
+        return d
+
+    def refit(self, kind, weights=None, max_iters=0):
+        k = REFITS[kind] if isinstance(kind, str) else kind
+        res = _Result()
+        w = _f32(weights)
+        _check(lib.rpe_refit(self._h, k, _ptr(w), max_iters, C.byref(res)), self._h)
+        return res.to_dict()
+
+    def set_pose(self, q, t, max_votes=0):
+        _check(lib.rpe_set_pose(self._h, _ptr(_f32(q)), _ptr(_f32(t)), max_votes), self._h)
+
+    def set_mask(self, mask):
+        mask = np.ascontiguousarray(mask, dtype=np.int16)
+        _check(lib.rpe_set_mask(self._h, _ptr(mask), mask.shape[0]), self._h)
+
+    def generate(self, method, samples):
+        m = METHODS[method] if isinstance(method, str) else method
+        samples = np.ascontiguousarray(samples, dtype=np.int32)
+        _check(lib.rpe_generate(self._h, m, _ptr(samples), samples.shape[0]), self._h)
+        return samples.shape[0] * method_slots(m)
+
+    def get_hypotheses(self, n_slots):
+        hyps = np.empty((n_slots, 7), np.float32)
+        valid = np.empty(n_slots, np.int32)
+        _check(lib.rpe_get_hypotheses(self._h, _ptr(hyps), _ptr(valid), n_slots), self._h)
+        return hyps, valid
+
+    def set_hypotheses(self, method, hyps, valid=None):
+        m = METHODS[method] if isinstance(method, str) else method
+        hyps = _f32(hyps)
+        v = None if valid is None else np.ascontiguousarray(valid, dtype=np.int32)
+        _check(lib.rpe_set_hypotheses(self._h, m, _ptr(hyps), _ptr(v), hyps.shape[0]), self._h)
+
+    def score(self, method, slot_begin, slot_end, thr3d=0.0, cos_thr2d=0.0, cos_thrN=0.0):
+        m = METHODS[method] if isinstance(method, str) else method
+        _check(lib.rpe_score(self._h, m, slot_begin, slot_end, thr3d, cos_thr2d, cos_thrN), self._h)
+
+    def get_votes(self, n_slots):
+        v = np.empty(n_slots, np.int32)
+        _check(lib.rpe_get_votes(self._h, _ptr(v), n_slots), self._h)
+        return v
+
+    def set_votes(self, votes):
+        v = np.ascontiguousarray(votes, dtype=np.int32)
+        _check(lib.rpe_set_votes(self._h, _ptr(v), v.shape[0]), self._h)
+
+    def votes_device_ptr(self):
+        return int(lib.rpe_votes_device_ptr(self._h) or 0)
+
+    def finish(self, method, H, thr3d=0.0, cos_thr2d=0.0, cos_thrN=0.0, confidence=0.99, want_mask=True):
+        m = METHODS[method] if isinstance(method, str) else method
+        res = _Result()
+        mask = np.empty((method_mask_cols(m), self.n), np.int16) if want_mask else None
+        _check(lib.rpe_finish(self._h, m, H, thr3d, cos_thr2d, cos_thrN, confidence, C.byref(res), _ptr(mask)), self._h)
+        d = res.to_dict()
+        d["mask"] = mask
+        return d
+
+    def sync(self):
+        _check(lib.rpe_sync(self._h), self._h)
+
+    def launch_count(self):
+        return int(lib.rpe_launch_count(self._h))
+
+    def stream(self):
+        return int(lib.rpe_stream(self._h) or 0)
+
+    def enable_stage_timing(self, on=True):
+        _check(lib.rpe_enable_stage_timing(self._h, 1 if on else 0), self._h)
+
+    def last_stage_ms(self):
+        ms = np.zeros(8, np.float32)
+        _check(lib.rpe_last_stage_ms(self._h, _ptr(ms)), self._h)
+        names = ["upload_pack", "generate", "score", "replay", "mask_refit", "gn", "total"]
+        return {k: float(v) for k, v in zip(names, ms)}
+
+    def measure_ffma_tflops(self, ms_target=50):
+        a, b = C.c_double(0), C.c_double(0)
+        _check(lib.rpe_measure_ffma_tflops(self._h, ms_target, C.byref(a), C.byref(b)), self._h)
+        return a.value, b.value

@@ -1,0 +1,837 @@
+// capi.cu — implementation of include/rpe_c_api.h: contexts, device memory, and the per-frame
+// launch sequence  reset -> pack -> generate -> score (fast + exact fix-up) -> replay -> mask(+Kabsch)
+// [-> LM iterations], all asynchronous on one stream with a single synchronisation at the end.
+//
+// There is no CPU fallback in this file: every compute entry point needs a live CUDA context and
+// returns RPE_ERR_NO_DEVICE / RPE_ERR_CUDA otherwise.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "kernels.cuh"
+
+namespace rpe {
+void set_use_packed(bool v);
+}
+
+using namespace rpe;
+
+namespace {
+
+enum { A_BV = 0, A_XC = 1, A_NC = 2, A_XW = 3, A_NW = 4 };
+constexpr int kNumStaging = 4;
+enum { ST_UPLOAD = 0, ST_GEN = 1, ST_SCORE = 2, ST_REPLAY = 3, ST_MASK = 4, ST_GN = 5, ST_TOTAL = 6, ST_COUNT = 8 };
+
+}  // namespace
+
+struct rpe_ctx {
+  int device = 0;
+  int num_sms = 148;
+  cudaStream_t stream = nullptr;
+  bool own_stream = true;
+  std::string err;
+  long long launches = 0;
+
+  // correspondences
+  int n = 0;
+  size_t cap_n = 0;
+  float* d_raw[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  const float* view[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // what kernels read (own copy or caller's)
+  float4* d_pk = nullptr;
+  size_t pk_cap_bytes = 0;
+  int pk_kind = -1;  // modalities currently packed, -1 = stale
+  int npairs_pad = 0;
+
+  // hypotheses
+  int cap_slots = 0;
+  int cap_H = 0;
+  int n_slots = 0;
+  int cur_method = -1;
+  HypGen* d_gen = nullptr;
+  HypFast* d_fast = nullptr;
+  int32_t* d_votes = nullptr;
+  int32_t* d_samples = nullptr;
+  int32_t* h_samples = nullptr;  // pinned staging
+  size_t h_samples_cap = 0;
+
+  FrameStats* d_stats = nullptr;
+  ReplayOut* d_pose = nullptr;    // current pose = the adapter's (R_cw, t_w, max_votes) state
+  ReplayOut* d_kabsch = nullptr;  // Kabsch refit computed by the mask kernel's last CTA
+  ReplayOut* h_pose = nullptr;    // pinned, kNumStaging slots; [0] doubles as scratch for set_pose
+  bool kabsch_valid = false;
+  Worklist wl = {nullptr, 0};
+  int16_t* d_mask = nullptr;
+  size_t mask_cap = 0;
+  int mask_cols = 0;
+  RefitBuffers rb = {nullptr, nullptr, 0};
+  GnState* d_gn = nullptr;
+  double* d_gn_cost = nullptr;
+  int32_t* d_gn_evals = nullptr;
+  double* h_gn_cost = nullptr;  // pinned (cost + evals packed)
+  int32_t* h_gn_evals = nullptr;
+
+  // results of enqueued-but-not-yet-synchronised calls, in stream order
+  struct Pending {
+    rpe_result* out;
+    int slot;
+    bool is_refit, gn;
+  };
+  std::vector<Pending> pending;
+  Thresh last_th = {0.f, 0.f, 0.f};
+
+  // stage timing
+  bool timing = false;
+  cudaEvent_t ev[ST_COUNT + 1] = {};
+  bool ev_ok = false;
+  bool ev_recorded[ST_COUNT + 1] = {};
+  float stage_ms[ST_COUNT] = {};
+};
+
+namespace {
+
+int fail(rpe_ctx* c, int code, const char* what, cudaError_t e = cudaSuccess) {
+  if (c) {
+    c->err = what;
+    if (e != cudaSuccess) {
+      c->err += ": ";
+      c->err += cudaGetErrorString(e);
+    }
+  }
+  return code;
+}
+#define CK(call)                                                        \
+  do {                                                                  \
+    cudaError_t e__ = (call);                                           \
+    if (e__ != cudaSuccess) return fail(ctx, RPE_ERR_CUDA, #call, e__); \
+  } while (0)
+
+int kind_for_method(int method) {
+  return (method_uses_2d(method) ? 1 : 0) | (method_uses_3d(method) ? 2 : 0) | (method_uses_nl(method) ? 4 : 0);
+}
+int f4_per_pair(int kind) {
+  int arrays = 1 + ((kind & 1) ? 1 : 0) + ((kind & 2) ? 1 : 0) + ((kind & 4) ? 2 : 0);
+  return (arrays * 6 + 3) / 4;
+}
+bool method_ok(int m) { return m >= RPE_SHINJI && m <= RPE_KNEIP_QUAT; }
+
+int check_arrays(rpe_ctx* ctx, int method) {
+  if (ctx->n <= 0) return fail(ctx, RPE_ERR_STATE, "no correspondences uploaded");
+  if (!ctx->view[A_XW]) return fail(ctx, RPE_ERR_STATE, "world points missing");
+  if (method_uses_2d(method) && !ctx->view[A_BV]) return fail(ctx, RPE_ERR_STATE, "bearing vectors missing for this method");
+  if ((method_uses_3d(method) || method_uses_nl(method)) && !ctx->view[A_XC])
+    return fail(ctx, RPE_ERR_STATE, "camera points missing for this method");
+  if (method_uses_nl(method) && (!ctx->view[A_NC] || !ctx->view[A_NW]))
+    return fail(ctx, RPE_ERR_STATE, "normals missing for this method");
+  return RPE_OK;
+}
+
+FrameView make_view(const rpe_ctx* c) {
+  FrameView f;
+  f.bv = c->view[A_BV];
+  f.xc = c->view[A_XC];
+  f.nc = c->view[A_NC];
+  f.xw = c->view[A_XW];
+  f.nw = c->view[A_NW];
+  f.n = c->n;
+  f.npairs_pad = c->npairs_pad;
+  f.pk = c->d_pk;
+  f.pk_kind = c->pk_kind;
+  f.pk_f4_per_pair = c->pk_kind >= 0 ? f4_per_pair(c->pk_kind) : 0;
+  return f;
+}
+
+int ensure_corr_capacity(rpe_ctx* ctx, int n, bool own_copy) {
+  if (own_copy && (size_t)n > ctx->cap_n) {
+    for (int k = 0; k < 5; ++k) {
+      if (ctx->d_raw[k]) cudaFree(ctx->d_raw[k]);
+      ctx->d_raw[k] = nullptr;
+    }
+    const size_t cap = (size_t)n + (size_t)n / 8 + 64;
+    for (int k = 0; k < 5; ++k) CK(cudaMalloc(&ctx->d_raw[k], cap * 3 * sizeof(float)));
+    ctx->cap_n = cap;
+  }
+  const size_t mask_need = (size_t)n * 3;
+  if (mask_need > ctx->mask_cap) {
+    if (ctx->d_mask) cudaFree(ctx->d_mask);
+    CK(cudaMalloc(&ctx->d_mask, mask_need * sizeof(int16_t)));
+    ctx->mask_cap = mask_need;
+  }
+  const int blocks = (n + 255) / 256;
+  if (blocks > ctx->rb.max_blocks) {
+    if (ctx->rb.partials) cudaFree(ctx->rb.partials);
+    CK(cudaMalloc(&ctx->rb.partials, (size_t)blocks * kMomentCount * sizeof(double)));
+    ctx->rb.max_blocks = blocks;
+  }
+  return RPE_OK;
+}
+
+int ensure_hyp_capacity(rpe_ctx* ctx, int H, int slots) {
+  if (slots > ctx->cap_slots) {
+    if (ctx->d_gen) cudaFree(ctx->d_gen);
+    if (ctx->d_fast) cudaFree(ctx->d_fast);
+    if (ctx->d_votes) cudaFree(ctx->d_votes);
+    const int cap = slots + slots / 4 + 256;
+    CK(cudaMalloc(&ctx->d_gen, (size_t)cap * sizeof(HypGen)));
+    CK(cudaMalloc(&ctx->d_fast, (size_t)cap * sizeof(HypFast)));
+    CK(cudaMalloc(&ctx->d_votes, (size_t)cap * sizeof(int32_t)));
+    ctx->cap_slots = cap;
+  }
+  if (H > ctx->cap_H) {
+    if (ctx->d_samples) cudaFree(ctx->d_samples);
+    const int cap = H + H / 4 + 256;
+    CK(cudaMalloc(&ctx->d_samples, (size_t)cap * 4 * sizeof(int32_t)));
+    ctx->cap_H = cap;
+  }
+  return RPE_OK;
+}
+
+int ensure_packed(rpe_ctx* ctx, int kind) {
+  if (ctx->pk_kind == kind) return RPE_OK;
+  const int npairs = (ctx->n + 1) / 2;
+  const int npad = ((npairs + kSubPairs - 1) / kSubPairs) * kSubPairs;
+  const size_t bytes = (size_t)npad * f4_per_pair(kind) * sizeof(float4);
+  if (bytes > ctx->pk_cap_bytes) {
+    if (ctx->d_pk) cudaFree(ctx->d_pk);
+    CK(cudaMalloc(&ctx->d_pk, bytes + bytes / 8));
+    ctx->pk_cap_bytes = bytes + bytes / 8;
+  }
+  ctx->npairs_pad = npad;
+  ctx->pk_kind = kind;
+  FrameView f = make_view(ctx);
+  launch_reset_corr_bound(ctx->d_stats, ctx->stream);
+  launch_pack(f, kind, ctx->d_pk, ctx->d_stats, ctx->stream);
+  ctx->launches += 2;
+  return RPE_OK;
+}
+
+void stamp(rpe_ctx* ctx, int which) {
+  if (ctx->timing && ctx->ev_ok) {
+    cudaEventRecord(ctx->ev[which], ctx->stream);
+    ctx->ev_recorded[which] = true;
+  }
+}
+
+void quat_to_R_rowmajor(const float q[4], float R[9]) {
+  const float x = q[0], y = q[1], z = q[2], w = q[3];
+  const float tx = 2.f * x, ty = 2.f * y, tz = 2.f * z;
+  const float twx = tx * w, twy = ty * w, twz = tz * w;
+  const float txx = tx * x, txy = ty * x, txz = tz * x;
+  const float tyy = ty * y, tyz = tz * y, tzz = tz * z;
+  R[0] = 1.f - (tyy + tzz);
+  R[1] = txy - twz;
+  R[2] = txz + twy;
+  R[3] = txy + twz;
+  R[4] = 1.f - (txx + tzz);
+  R[5] = tyz - twx;
+  R[6] = txz - twy;
+  R[7] = tyz + twx;
+  R[8] = 1.f - (txx + tyy);
+}
+
+void fill_result(const rpe_ctx* ctx, rpe_result* out, int slot, bool is_refit, bool gn) {
+  const ReplayOut& p = ctx->h_pose[slot];
+  memset(out, 0, sizeof(*out));
+  for (int k = 0; k < 4; ++k) out->q[k] = p.q[k];
+  for (int k = 0; k < 3; ++k) out->t[k] = p.t[k];
+  quat_to_R_rowmajor(p.q, out->R);
+  out->max_votes = p.max_votes;
+  out->iter_final = p.iter_final;
+  out->winner = p.winner;
+  out->n_slots = p.n_slots;
+  out->n_borderline = p.n_borderline;
+  out->flags = p.flags;
+  for (int k = 0; k < 3; ++k) out->n_inliers[k] = p.n_inliers[k];
+  out->refit_ok = is_refit ? p.refit_ok : 0;
+  if (gn) {
+    out->refit_cost = ctx->h_gn_cost[slot];
+    out->refit_evals = ctx->h_gn_evals[slot];
+  }
+}
+
+int finish_pending(rpe_ctx* ctx) {
+  for (const rpe_ctx::Pending& p : ctx->pending) fill_result(ctx, p.out, p.slot, p.is_refit, p.gn);
+  ctx->pending.clear();
+  if (ctx->timing && ctx->ev_ok) {
+    for (int k = 0; k < ST_COUNT; ++k) ctx->stage_ms[k] = 0.f;
+    for (int k = 0; k < ST_TOTAL; ++k)
+      if (ctx->ev_recorded[k] && ctx->ev_recorded[k + 1]) cudaEventElapsedTime(&ctx->stage_ms[k], ctx->ev[k], ctx->ev[k + 1]);
+    if (ctx->ev_recorded[0]) {
+      int last = 0;
+      for (int k = 0; k <= ST_TOTAL; ++k)
+        if (ctx->ev_recorded[k]) last = k;
+      if (last > 0) cudaEventElapsedTime(&ctx->stage_ms[ST_TOTAL], ctx->ev[0], ctx->ev[last]);
+    }
+    for (int k = 0; k <= ST_COUNT; ++k) ctx->ev_recorded[k] = false;
+  }
+  return RPE_OK;
+}
+
+// claim a pinned staging slot for an enqueued result; drains the queue first when it is full
+int claim_slot(rpe_ctx* ctx, int* slot) {
+  if ((int)ctx->pending.size() >= kNumStaging) {
+    CK(cudaStreamSynchronize(ctx->stream));
+    finish_pending(ctx);
+  }
+  *slot = (int)ctx->pending.size();
+  return RPE_OK;
+}
+
+// score the slot range with the best available kernel, including the exact fix-up
+int score_range(rpe_ctx* ctx, int method, int slot_begin, int slot_end, Thresh th) {
+  FrameView f = make_view(ctx);
+  if (method == RPE_SHINJI) {
+    launch_score_fast(method, f, ctx->d_gen, ctx->d_fast, slot_begin, slot_end, th, ctx->d_votes, ctx->d_stats, ctx->wl,
+                      ctx->num_sms, ctx->stream);
+    launch_fixup(method, f, ctx->d_gen, th, ctx->d_votes, ctx->d_stats, ctx->wl, ctx->num_sms, ctx->stream);
+    launch_score_exact(method, f, ctx->d_gen, slot_begin, slot_end, th, ctx->d_votes, ctx->d_stats, true, ctx->num_sms,
+                       ctx->stream);
+    ctx->launches += 4;
+  } else {
+    launch_score_exact(method, f, ctx->d_gen, slot_begin, slot_end, th, ctx->d_votes, ctx->d_stats, false, ctx->num_sms,
+                       ctx->stream);
+    ctx->launches += 2;
+  }
+  return RPE_OK;
+}
+
+int do_finish(rpe_ctx* ctx, int method, int H, Thresh th, float confidence, rpe_result* out, int16_t* mask, bool blocking) {
+  FrameView f = make_view(ctx);
+  launch_replay(method, ctx->d_gen, ctx->d_votes, H, ctx->n, confidence, ctx->d_stats, ctx->d_pose, ctx->stream);
+  stamp(ctx, ST_MASK);
+  ctx->mask_cols = method_mask_cols(method);
+  launch_mask(method, f, ctx->d_pose, th, ctx->d_mask, ctx->d_kabsch, ctx->rb, ctx->d_stats, ctx->stream);
+  ctx->launches += 2;
+  ctx->kabsch_valid = method_uses_3d(method);
+  ctx->last_th = th;
+  stamp(ctx, ST_GN);
+  int slot = 0;
+  int rc = claim_slot(ctx, &slot);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(&ctx->h_pose[slot], ctx->d_pose, sizeof(ReplayOut), cudaMemcpyDeviceToHost, ctx->stream));
+  if (mask)
+    CK(cudaMemcpyAsync(mask, ctx->d_mask, (size_t)ctx->n * ctx->mask_cols * sizeof(int16_t), cudaMemcpyDeviceToHost,
+                       ctx->stream));
+  ctx->pending.push_back(rpe_ctx::Pending{out, slot, false, false});
+  if (blocking) {
+    CK(cudaStreamSynchronize(ctx->stream));
+    finish_pending(ctx);
+  }
+  return RPE_OK;
+}
+
+int do_ransac(rpe_ctx* ctx, int method, const int32_t* samples, int H, float thr3d, float cos_thr2d, float cos_thrN,
+              float confidence, rpe_result* out, int16_t* mask, bool blocking) {
+  if (!ctx) return RPE_ERR_ARG;
+  if (!method_ok(method) || !samples || H <= 0 || !out) return fail(ctx, RPE_ERR_ARG, "bad argument to rpe_ransac");
+  int rc = check_arrays(ctx, method);
+  if (rc) return rc;
+  CK(cudaSetDevice(ctx->device));
+  const int S = method_slots(method);
+  rc = ensure_hyp_capacity(ctx, H, H * S);
+  if (rc) return rc;
+  const Thresh th = {thr3d, cos_thr2d, cos_thrN};
+  if (!ctx->ev_recorded[ST_UPLOAD]) stamp(ctx, ST_UPLOAD);
+  // sample table: stage through pinned memory so the copy is truly asynchronous
+  const size_t sbytes = (size_t)H * 4 * sizeof(int32_t);
+  if (sbytes > ctx->h_samples_cap) {
+    if (ctx->h_samples) cudaFreeHost(ctx->h_samples);
+    CK(cudaMallocHost(&ctx->h_samples, sbytes + sbytes / 4));
+    ctx->h_samples_cap = sbytes + sbytes / 4;
+  }
+  memcpy(ctx->h_samples, samples, sbytes);
+  CK(cudaMemcpyAsync(ctx->d_samples, ctx->h_samples, sbytes, cudaMemcpyHostToDevice, ctx->stream));
+  launch_reset_stats(ctx->d_stats, ctx->stream);
+  ctx->launches++;
+  if (method == RPE_SHINJI) {
+    rc = ensure_packed(ctx, kind_for_method(method));
+    if (rc) return rc;
+  }
+  stamp(ctx, ST_GEN);
+  FrameView f = make_view(ctx);
+  launch_hypgen(method, f, ctx->d_samples, H, ctx->d_gen, ctx->d_fast, ctx->d_votes, ctx->d_stats, ctx->stream);
+  ctx->launches++;
+  ctx->n_slots = H * S;
+  ctx->cur_method = method;
+  stamp(ctx, ST_SCORE);
+  rc = score_range(ctx, method, 0, H * S, th);
+  if (rc) return rc;
+  stamp(ctx, ST_REPLAY);
+  return do_finish(ctx, method, H, th, confidence, out, mask, blocking);
+}
+
+}  // namespace
+
+extern "C" {
+
+int rpe_version(void) { return RPE_API_VERSION; }
+
+const char* rpe_status_string(int status) {
+  switch (status) {
+    case RPE_OK: return "ok";
+    case RPE_ERR_ARG: return "invalid argument";
+    case RPE_ERR_CUDA: return "CUDA error";
+    case RPE_ERR_STATE: return "invalid state";
+    case RPE_ERR_NO_DEVICE: return "no usable CUDA device (this library has no CPU fallback)";
+    case RPE_ERR_COMM: return "communication error";
+    case RPE_ERR_NOMEM: return "out of memory";
+    default: return "unknown status";
+  }
+}
+
+int rpe_device_count(int* count) {
+  if (!count) return RPE_ERR_ARG;
+  int n = 0;
+  const cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) {
+    *count = 0;
+    (void)cudaGetLastError();
+    return RPE_ERR_NO_DEVICE;
+  }
+  *count = n;
+  return RPE_OK;
+}
+
+static int create_common(int device, void* stream, bool own, rpe_ctx** out) {
+  if (!out) return RPE_ERR_ARG;
+  *out = nullptr;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) {
+    (void)cudaGetLastError();
+    return RPE_ERR_NO_DEVICE;
+  }
+  if (device < 0 || device >= n) return RPE_ERR_ARG;
+  if (cudaSetDevice(device) != cudaSuccess) return RPE_ERR_CUDA;
+  rpe_ctx* ctx = new rpe_ctx();
+  ctx->device = device;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->num_sms = prop.multiProcessorCount;
+  if (prop.major < 10) {
+    delete ctx;
+    return RPE_ERR_NO_DEVICE;  // kernels are built for sm_100a only
+  }
+  if (own) {
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+      delete ctx;
+      return RPE_ERR_CUDA;
+    }
+  } else {
+    ctx->stream = (cudaStream_t)stream;
+  }
+  ctx->own_stream = own;
+  bool ok = true;
+  ok = ok && cudaMalloc(&ctx->d_stats, sizeof(FrameStats)) == cudaSuccess;
+  ok = ok && cudaMalloc(&ctx->d_pose, sizeof(ReplayOut)) == cudaSuccess;
+  ok = ok && cudaMalloc(&ctx->d_kabsch, sizeof(ReplayOut)) == cudaSuccess;
+  ok = ok && cudaMallocHost(&ctx->h_pose, kNumStaging * sizeof(ReplayOut)) == cudaSuccess;
+  ok = ok && cudaMalloc(&ctx->rb.moments, kMomentCount * sizeof(double)) == cudaSuccess;
+  ok = ok && cudaMalloc(&ctx->d_gn, sizeof(GnState)) == cudaSuccess;
+  ok = ok && cudaMalloc(&ctx->d_gn_cost, sizeof(double)) == cudaSuccess;
+  ok = ok && cudaMalloc(&ctx->d_gn_evals, sizeof(int32_t)) == cudaSuccess;
+  ok = ok && cudaMallocHost(&ctx->h_gn_cost, kNumStaging * sizeof(double)) == cudaSuccess;
+  ok = ok && cudaMallocHost(&ctx->h_gn_evals, kNumStaging * sizeof(int32_t)) == cudaSuccess;
+  ctx->wl.capacity = 1u << 21;  // 2 Mi borderline evaluations (16 MiB)
+  ok = ok && cudaMalloc(&ctx->wl.entries, (size_t)ctx->wl.capacity * sizeof(uint2)) == cudaSuccess;
+  if (ok) {
+    ok = ok && cudaMemsetAsync(ctx->d_stats, 0, sizeof(FrameStats), ctx->stream) == cudaSuccess;
+    ok = ok && cudaMemsetAsync(ctx->d_pose, 0, sizeof(ReplayOut), ctx->stream) == cudaSuccess;
+    ok = ok && cudaMemsetAsync(ctx->d_kabsch, 0, sizeof(ReplayOut), ctx->stream) == cudaSuccess;
+  }
+  for (int k = 0; k <= ST_COUNT && ok; ++k) ok = ok && cudaEventCreate(&ctx->ev[k]) == cudaSuccess;
+  ctx->ev_ok = ok;
+  if (!ok) {
+    rpe_destroy(ctx);
+    return RPE_ERR_CUDA;
+  }
+  memset(ctx->h_pose, 0, kNumStaging * sizeof(ReplayOut));
+  ctx->h_pose->q[3] = 1.f;
+  ctx->h_pose->winner = -1;
+  ctx->h_pose->max_votes = -1;
+  cudaMemcpyAsync(ctx->d_pose, ctx->h_pose, sizeof(ReplayOut), cudaMemcpyHostToDevice, ctx->stream);
+  cudaStreamSynchronize(ctx->stream);
+  *out = ctx;
+  return RPE_OK;
+}
+
+int rpe_create(int device, rpe_ctx** ctx) { return create_common(device, nullptr, true, ctx); }
+int rpe_create_on_stream(int device, void* cuda_stream, rpe_ctx** ctx) {
+  return create_common(device, cuda_stream, false, ctx);
+}
+
+int rpe_destroy(rpe_ctx* ctx) {
+  if (!ctx) return RPE_OK;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  for (int k = 0; k < 5; ++k)
+    if (ctx->d_raw[k]) cudaFree(ctx->d_raw[k]);
+  cudaFree(ctx->d_pk);
+  cudaFree(ctx->d_gen);
+  cudaFree(ctx->d_fast);
+  cudaFree(ctx->d_votes);
+  cudaFree(ctx->d_samples);
+  if (ctx->h_samples) cudaFreeHost(ctx->h_samples);
+  cudaFree(ctx->d_stats);
+  cudaFree(ctx->d_pose);
+  cudaFree(ctx->d_kabsch);
+  if (ctx->h_pose) cudaFreeHost(ctx->h_pose);
+  cudaFree(ctx->wl.entries);
+  cudaFree(ctx->d_mask);
+  cudaFree(ctx->rb.partials);
+  cudaFree(ctx->rb.moments);
+  cudaFree(ctx->d_gn);
+  cudaFree(ctx->d_gn_cost);
+  cudaFree(ctx->d_gn_evals);
+  if (ctx->h_gn_cost) cudaFreeHost(ctx->h_gn_cost);
+  if (ctx->h_gn_evals) cudaFreeHost(ctx->h_gn_evals);
+  for (int k = 0; k <= ST_COUNT; ++k)
+    if (ctx->ev[k]) cudaEventDestroy(ctx->ev[k]);
+  if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+  (void)cudaGetLastError();
+  delete ctx;
+  return RPE_OK;
+}
+
+const char* rpe_last_error(const rpe_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+void* rpe_stream(rpe_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+long long rpe_launch_count(const rpe_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int rpe_sync(rpe_ctx* ctx) {
+  if (!ctx) return RPE_ERR_ARG;
+  CK(cudaStreamSynchronize(ctx->stream));
+  return finish_pending(ctx);
+}
+
+int rpe_host_alloc(size_t bytes, void** ptr) {
+  if (!ptr) return RPE_ERR_ARG;
+  const cudaError_t e = cudaMallocHost(ptr, bytes);
+  if (e != cudaSuccess) {
+    (void)cudaGetLastError();
+    return RPE_ERR_NOMEM;
+  }
+  return RPE_OK;
+}
+int rpe_host_free(void* ptr) {
+  if (ptr) cudaFreeHost(ptr);
+  return RPE_OK;
+}
+
+static int upload_common(rpe_ctx* ctx, const float* const src[5], int n, bool from_device) {
+  if (!ctx) return RPE_ERR_ARG;
+  if (n <= 0 || !src[A_XW]) return fail(ctx, RPE_ERR_ARG, "rpe_upload needs n > 0 and world points");
+  CK(cudaSetDevice(ctx->device));
+  int rc = ensure_corr_capacity(ctx, n, !from_device);
+  if (rc) return rc;
+  ctx->n = n;
+  for (int k = 0; k < 5; ++k) {
+    if (!src[k]) {
+      ctx->view[k] = nullptr;
+      continue;
+    }
+    if (from_device) {
+      ctx->view[k] = src[k];
+    } else {
+      CK(cudaMemcpyAsync(ctx->d_raw[k], src[k], (size_t)n * 3 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+      ctx->view[k] = ctx->d_raw[k];
+    }
+  }
+  ctx->pk_kind = -1;
+  ctx->kabsch_valid = false;
+  ctx->n_slots = 0;
+  return RPE_OK;
+}
+
+int rpe_upload(rpe_ctx* ctx, const float* bv, const float* xc, const float* nc, const float* xw, const float* nw, int n) {
+  const float* src[5] = {bv, xc, nc, xw, nw};
+  if (ctx) stamp(ctx, ST_UPLOAD);
+  return upload_common(ctx, src, n, false);
+}
+int rpe_upload_device(rpe_ctx* ctx, const float* bv, const float* xc, const float* nc, const float* xw, const float* nw,
+                      int n) {
+  const float* src[5] = {bv, xc, nc, xw, nw};
+  return upload_common(ctx, src, n, true);
+}
+int rpe_num_correspondences(const rpe_ctx* ctx) { return ctx ? ctx->n : 0; }
+
+int rpe_ransac(rpe_ctx* ctx, int method, const int32_t* samples, int H, float thr3d, float cos_thr2d, float cos_thrN,
+               float confidence, rpe_result* out, int16_t* mask) {
+  return do_ransac(ctx, method, samples, H, thr3d, cos_thr2d, cos_thrN, confidence, out, mask, true);
+}
+int rpe_ransac_async(rpe_ctx* ctx, int method, const int32_t* samples, int H, float thr3d, float cos_thr2d,
+                     float cos_thrN, float confidence, rpe_result* out, int16_t* mask) {
+  return do_ransac(ctx, method, samples, H, thr3d, cos_thr2d, cos_thrN, confidence, out, mask, false);
+}
+
+static int do_refit(rpe_ctx* ctx, int kind, const float* weights, int max_iters, rpe_result* out, bool blocking) {
+  if (!ctx || !out) return RPE_ERR_ARG;
+  if (ctx->n <= 0) return fail(ctx, RPE_ERR_STATE, "no correspondences uploaded");
+  CK(cudaSetDevice(ctx->device));
+  int slot = 0;
+  int rcs = claim_slot(ctx, &slot);
+  if (rcs) return rcs;
+  FrameView f = make_view(ctx);
+  bool gn = false;
+  if (kind == RPE_REFIT_KABSCH_INLIERS || kind == RPE_REFIT_KABSCH_ALL) {
+    if (!f.xc) return fail(ctx, RPE_ERR_STATE, "Kabsch refit needs camera points");
+    if (kind == RPE_REFIT_KABSCH_INLIERS && ctx->kabsch_valid) {
+      // already computed by the mask kernel's last CTA; adopt it as the current pose
+      CK(cudaMemcpyAsync(ctx->d_pose, ctx->d_kabsch, sizeof(ReplayOut), cudaMemcpyDeviceToDevice, ctx->stream));
+    } else {
+      if (kind == RPE_REFIT_KABSCH_INLIERS && ctx->mask_cols < 2)
+        return fail(ctx, RPE_ERR_STATE, "no 3-D inlier column available");
+      const int16_t* flags = kind == RPE_REFIT_KABSCH_INLIERS ? ctx->d_mask + ctx->n : nullptr;
+      launch_kabsch_moments(f, flags, ctx->rb, ctx->d_stats, ctx->stream);
+      launch_kabsch_solve(ctx->rb, (ctx->n + 255) / 256, ctx->d_pose, nullptr, ctx->stream);
+      ctx->launches += 2;
+    }
+  } else if (kind == RPE_REFIT_GN) {
+    if (ctx->mask_cols <= 0) return fail(ctx, RPE_ERR_STATE, "no inlier mask: run rpe_ransac or rpe_set_mask first");
+    const float w2 = weights ? weights[0] : 1.f, w3 = weights ? weights[1] : 1.f, wn = weights ? weights[2] : 1.f;
+    const int iters = max_iters > 0 ? max_iters : 6;
+    stamp(ctx, ST_GN);
+    launch_gn_init(ctx->d_pose, ctx->d_gn, ctx->stream);
+    for (int it = 0; it < iters; ++it)
+      launch_gn_iteration(f, ctx->d_mask, ctx->mask_cols, w2, w3, wn, ctx->rb, ctx->d_gn, ctx->d_stats, ctx->stream);
+    launch_gn_finish(ctx->d_gn, ctx->d_pose, ctx->d_gn_cost, ctx->d_gn_evals, ctx->stream);
+    ctx->launches += iters + 2;
+    CK(cudaMemcpyAsync(&ctx->h_gn_cost[slot], ctx->d_gn_cost, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(&ctx->h_gn_evals[slot], ctx->d_gn_evals, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    stamp(ctx, ST_TOTAL);
+    gn = true;
+  } else {
+    return fail(ctx, RPE_ERR_ARG, "unknown or unimplemented refit kind");
+  }
+  ctx->kabsch_valid = false;
+  CK(cudaMemcpyAsync(&ctx->h_pose[slot], ctx->d_pose, sizeof(ReplayOut), cudaMemcpyDeviceToHost, ctx->stream));
+  ctx->pending.push_back(rpe_ctx::Pending{out, slot, true, gn});
+  if (blocking) {
+    CK(cudaStreamSynchronize(ctx->stream));
+    finish_pending(ctx);
+  }
+  return RPE_OK;
+}
+
+int rpe_refit(rpe_ctx* ctx, int kind, const float* weights, int max_iters, rpe_result* out) {
+  return do_refit(ctx, kind, weights, max_iters, out, true);
+}
+int rpe_refit_async(rpe_ctx* ctx, int kind, const float* weights, int max_iters, rpe_result* out) {
+  return do_refit(ctx, kind, weights, max_iters, out, false);
+}
+
+int rpe_set_pose(rpe_ctx* ctx, const float q_xyzw[4], const float t[3], int max_votes) {
+  if (!ctx || !q_xyzw || !t) return RPE_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  finish_pending(ctx);
+  ReplayOut p;
+  memset(&p, 0, sizeof(p));
+  for (int k = 0; k < 4; ++k) p.q[k] = q_xyzw[k];
+  for (int k = 0; k < 3; ++k) p.t[k] = t[k];
+  p.max_votes = max_votes;
+  p.winner = 0;
+  *ctx->h_pose = p;
+  CK(cudaMemcpyAsync(ctx->d_pose, ctx->h_pose, sizeof(ReplayOut), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->kabsch_valid = false;
+  return RPE_OK;
+}
+
+int rpe_set_mask(rpe_ctx* ctx, const int16_t* mask, int cols) {
+  if (!ctx || !mask || cols < 1 || cols > 3) return RPE_ERR_ARG;
+  if (ctx->n <= 0) return fail(ctx, RPE_ERR_STATE, "no correspondences uploaded");
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaMemcpyAsync(ctx->d_mask, mask, (size_t)ctx->n * cols * sizeof(int16_t), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->mask_cols = cols;
+  ctx->kabsch_valid = false;
+  return RPE_OK;
+}
+
+// ---- stage access ----------------------------------------------------------------------------------
+int rpe_generate(rpe_ctx* ctx, int method, const int32_t* samples, int H) {
+  if (!ctx) return RPE_ERR_ARG;
+  if (!method_ok(method) || !samples || H <= 0) return fail(ctx, RPE_ERR_ARG, "bad argument to rpe_generate");
+  int rc = check_arrays(ctx, method);
+  if (rc) return rc;
+  CK(cudaSetDevice(ctx->device));
+  const int S = method_slots(method);
+  rc = ensure_hyp_capacity(ctx, H, H * S);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(ctx->d_samples, samples, (size_t)H * 4 * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+  launch_reset_stats(ctx->d_stats, ctx->stream);
+  FrameView f = make_view(ctx);
+  launch_hypgen(method, f, ctx->d_samples, H, ctx->d_gen, ctx->d_fast, ctx->d_votes, ctx->d_stats, ctx->stream);
+  ctx->launches += 2;
+  ctx->n_slots = H * S;
+  ctx->cur_method = method;
+  CK(cudaStreamSynchronize(ctx->stream));
+  return RPE_OK;
+}
+
+int rpe_get_hypotheses(rpe_ctx* ctx, float* hyps, int32_t* valid, int n_slots) {
+  if (!ctx || n_slots <= 0 || n_slots > ctx->n_slots) return ctx ? fail(ctx, RPE_ERR_ARG, "bad slot count") : RPE_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  std::vector<HypGen> h(n_slots);
+  CK(cudaMemcpyAsync(h.data(), ctx->d_gen, (size_t)n_slots * sizeof(HypGen), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  for (int i = 0; i < n_slots; ++i) {
+    if (hyps) {
+      for (int k = 0; k < 4; ++k) hyps[7 * i + k] = h[i].q[k];
+      for (int k = 0; k < 3; ++k) hyps[7 * i + 4 + k] = h[i].t[k];
+    }
+    if (valid) valid[i] = h[i].valid;
+  }
+  return RPE_OK;
+}
+
+int rpe_set_hypotheses(rpe_ctx* ctx, int method, const float* hyps, const int32_t* valid, int n_slots) {
+  if (!ctx) return RPE_ERR_ARG;
+  if (!method_ok(method) || !hyps || n_slots <= 0) return fail(ctx, RPE_ERR_ARG, "bad argument to rpe_set_hypotheses");
+  CK(cudaSetDevice(ctx->device));
+  int rc = ensure_hyp_capacity(ctx, 1, n_slots);
+  if (rc) return rc;
+  std::vector<HypGen> h(n_slots);
+  for (int i = 0; i < n_slots; ++i) {
+    for (int k = 0; k < 4; ++k) h[i].q[k] = hyps[7 * i + k];
+    for (int k = 0; k < 3; ++k) h[i].t[k] = hyps[7 * i + 4 + k];
+    h[i].valid = valid ? valid[i] : 1;
+  }
+  CK(cudaMemcpyAsync(ctx->d_gen, h.data(), (size_t)n_slots * sizeof(HypGen), cudaMemcpyHostToDevice, ctx->stream));
+  launch_reset_stats(ctx->d_stats, ctx->stream);
+  launch_derive_fast(ctx->d_gen, ctx->d_fast, ctx->d_votes, n_slots, ctx->d_stats, ctx->stream);
+  ctx->launches += 2;
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->n_slots = n_slots;
+  ctx->cur_method = method;
+  return RPE_OK;
+}
+
+int rpe_score(rpe_ctx* ctx, int method, int slot_begin, int slot_end, float thr3d, float cos_thr2d, float cos_thrN) {
+  if (!ctx) return RPE_ERR_ARG;
+  if (!method_ok(method) || slot_begin < 0 || slot_end > ctx->n_slots || slot_begin > slot_end)
+    return fail(ctx, RPE_ERR_ARG, "bad slot range");
+  int rc = check_arrays(ctx, method);
+  if (rc) return rc;
+  CK(cudaSetDevice(ctx->device));
+  if (method == RPE_SHINJI) {
+    rc = ensure_packed(ctx, kind_for_method(method));
+    if (rc) return rc;
+  }
+  const Thresh th = {thr3d, cos_thr2d, cos_thrN};
+  stamp(ctx, ST_SCORE);
+  rc = score_range(ctx, method, slot_begin, slot_end, th);
+  stamp(ctx, ST_REPLAY);
+  return rc;
+}
+
+int rpe_get_votes(rpe_ctx* ctx, int32_t* votes, int n_slots) {
+  if (!ctx || !votes || n_slots <= 0 || n_slots > ctx->n_slots) return RPE_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaMemcpyAsync(votes, ctx->d_votes, (size_t)n_slots * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return RPE_OK;
+}
+int rpe_set_votes(rpe_ctx* ctx, const int32_t* votes, int n_slots) {
+  if (!ctx || !votes || n_slots <= 0 || n_slots > ctx->n_slots) return RPE_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaMemcpyAsync(ctx->d_votes, votes, (size_t)n_slots * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return RPE_OK;
+}
+int32_t* rpe_votes_device_ptr(rpe_ctx* ctx) { return ctx ? ctx->d_votes : nullptr; }
+
+int rpe_finish(rpe_ctx* ctx, int method, int H, float thr3d, float cos_thr2d, float cos_thrN, float confidence,
+               rpe_result* out, int16_t* mask) {
+  if (!ctx) return RPE_ERR_ARG;
+  if (!method_ok(method) || H <= 0 || H * method_slots(method) > ctx->n_slots || !out)
+    return fail(ctx, RPE_ERR_ARG, "bad argument to rpe_finish");
+  CK(cudaSetDevice(ctx->device));
+  const Thresh th = {thr3d, cos_thr2d, cos_thrN};
+  return do_finish(ctx, method, H, th, confidence, out, mask, true);
+}
+
+// ---- Library.cpp shim -----------------------------------------------------------------------------
+static int ao_common(const float* x_w, const float* x_c, int n, float* R_cw, float* t, bool ransac) {
+  if (!x_w || !x_c || n < 3 || !R_cw || !t) return RPE_ERR_ARG;
+  rpe_ctx* ctx = nullptr;
+  int rc = rpe_create(0, &ctx);
+  if (rc) return rc;
+  rpe_result res;
+  rc = rpe_upload(ctx, nullptr, x_c, nullptr, x_w, nullptr, n);
+  if (!rc && ransac) {
+    // Library.cpp:54-64: thr 0.1, 1000 iterations, confidence 0.99999, unseeded rand() (seed 1)
+    const int H = 1000;
+    std::vector<int32_t> samples((size_t)H * 4);
+    rc = rpe_sample_table(1u, n, 3, H, samples.data());
+    if (!rc) rc = rpe_ransac(ctx, RPE_SHINJI, samples.data(), H, 0.1f, 0.f, 0.f, 0.99999f, &res, nullptr);
+    if (!rc) rc = rpe_refit(ctx, RPE_REFIT_KABSCH_INLIERS, nullptr, 0, &res);
+  } else if (!rc) {
+    rc = rpe_refit(ctx, RPE_REFIT_KABSCH_ALL, nullptr, 0, &res);  // shinji_ls2 (Library.cpp:35)
+  }
+  if (!rc) {
+    for (int i = 0; i < 9; ++i) R_cw[i] = res.R[i];
+    for (int i = 0; i < 3; ++i) t[i] = res.t[i];
+  }
+  rpe_destroy(ctx);
+  return rc;
+}
+int rpe_ao(const float* x_w, const float* x_c, int n, float* R_cw, float* t) { return ao_common(x_w, x_c, n, R_cw, t, false); }
+int rpe_ao_ransac(const float* x_w, const float* x_c, int n, float* R_cw, float* t) {
+  return ao_common(x_w, x_c, n, R_cw, t, true);
+}
+
+// ---- microbenchmark / timing -------------------------------------------------------------------------
+int rpe_measure_ffma_tflops(rpe_ctx* ctx, int ms_target, double* tflops_scalar, double* tflops_packed) {
+  if (!ctx) return RPE_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  float* sink = nullptr;
+  CK(cudaMalloc(&sink, 64));
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  const int blocks = ctx->num_sms * 8;
+  double* outs[2] = {tflops_scalar, tflops_packed};
+  for (int mode = 0; mode < 2; ++mode) {
+    int iters = 2048;
+    float ms = 0.f;
+    for (int rep = 0; rep < 6; ++rep) {
+      launch_ffma_bench(sink, iters, mode == 1, blocks, ctx->stream);  // warm / calibrate
+      CK(cudaEventRecord(e0, ctx->stream));
+      launch_ffma_bench(sink, iters, mode == 1, blocks, ctx->stream);
+      CK(cudaEventRecord(e1, ctx->stream));
+      CK(cudaEventSynchronize(e1));
+      CK(cudaEventElapsedTime(&ms, e0, e1));
+      ctx->launches += 2;
+      if (ms >= (float)ms_target || iters > (1 << 24)) break;
+      const double scale = ms > 0.01f ? (double)ms_target / ms * 1.2 : 8.0;
+      iters = (int)(iters * (scale > 8.0 ? 8.0 : (scale < 1.5 ? 1.5 : scale)));
+    }
+    // per thread per iteration: 4 rounds x 8 accumulators x 2 lanes FMAs
+    const double fma = (double)blocks * 256.0 * (double)iters * 4.0 * 8.0 * 2.0;
+    if (outs[mode]) *outs[mode] = 2.0 * fma / (ms * 1e-3) / 1e12;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(sink);
+  return RPE_OK;
+}
+
+int rpe_enable_stage_timing(rpe_ctx* ctx, int enable) {
+  if (!ctx) return RPE_ERR_ARG;
+  ctx->timing = enable != 0;
+  return RPE_OK;
+}
+int rpe_last_stage_ms(rpe_ctx* ctx, float ms[8]) {
+  if (!ctx || !ms) return RPE_ERR_ARG;
+  for (int k = 0; k < ST_COUNT; ++k) ms[k] = ctx->stage_ms[k];
+  return RPE_OK;
+}
+
+// test hook: choose the packed (FFMA2) or scalar (FFMA) fast kernel
+int rpe_debug_set_packed(int packed) {
+  rpe::set_use_packed(packed != 0);
+  return RPE_OK;
+}
+
+}  // extern "C"

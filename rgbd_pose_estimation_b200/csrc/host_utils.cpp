@@ -1,0 +1,98 @@
+// host_utils.cpp — the C-ABI entry points that the reference also computes on the CPU:
+// sample tables (Utility.hpp:125-250), the adaptive stopping rule (P3P.hpp:296-318) and the
+// synthetic generators (Simulator.hpp). No device code here.
+#include <string.h>
+
+#include <vector>
+
+#include "../../include/rpe/Utility.hpp"
+#include "../../include/rpe/ransac_rule.h"
+#include "../../include/rpe/sim_core.hpp"
+#include "../../include/rpe_c_api.h"
+
+extern "C" {
+
+int rpe_update_num_iters(float p, float ep, int model_points, int max_iters) {
+  return rpe::update_num_iters(p, ep, model_points, max_iters);
+}
+
+int rpe_sample_table(uint32_t seed, int n, int m, int H, int32_t* samples) {
+  if (!samples || n <= 0 || m <= 0 || m > 4 || m > n || H < 0) return RPE_ERR_ARG;
+  rpe::GlibcRandom src(seed);
+  RandomElements<int> re(n, &src);
+  std::vector<int> sel;
+  for (int h = 0; h < H; ++h) {
+    re.run(m, &sel);
+    for (int k = 0; k < 4; ++k) samples[4 * h + k] = k < m ? sel[k] : -1;
+  }
+  return RPE_OK;
+}
+
+int rpe_prosac_table(uint32_t seed, int n, int m, int H, const float* weights, int32_t* samples) {
+  if (!samples || n <= 0 || m <= 1 || m > 4 || m > n || H < 0) return RPE_ERR_ARG;
+  rpe::GlibcRandom src(seed);
+  ProsacSampler<float> ps(m, n, &src);
+  std::vector<int> order;
+  if (weights) {
+    std::vector<float> w(weights, weights + n);
+    order = sortIndexes<float>(w);  // adapter.sortIdx() (PnPPoseAdapter.hpp:239-244)
+  }
+  for (int h = 0; h < H; ++h) {
+    std::vector<int> sel;
+    ps.sample(&sel);
+    for (int k = 0; k < 4; ++k) {
+      int j = k < m ? sel[k] : -1;
+      // getSortedIdx (PnPPoseAdapter.hpp:246-255): indices beyond the table are left untouched
+      if (j >= 0 && weights && j < (int)order.size()) j = order[j];
+      samples[4 * h + k] = j;
+    }
+  }
+  return RPE_OK;
+}
+
+int rpe_sim_pose(uint64_t seed, float max_angle_rad, float t_size, float q_xyzw[4], float t[3]) {
+  if (!q_xyzw || !t) return RPE_ERR_ARG;
+  rpe::sim::Rng rng(seed);
+  const rpe::sim::Pose<float> p = rpe::sim::random_pose<float>(rng, max_angle_rad, t_size);
+  memcpy(q_xyzw, p.q, sizeof(p.q));
+  memcpy(t, p.t, sizeof(p.t));
+  return RPE_OK;
+}
+
+static rpe::sim::Pose<float> make_pose(const float q[4], const float t[3]) {
+  rpe::sim::Pose<float> p;
+  memcpy(p.q, q, sizeof(p.q));
+  memcpy(p.t, t, sizeof(p.t));
+  return p;
+}
+
+int rpe_sim_3d_3d(uint64_t seed, const float q_xyzw[4], const float t[3], int n, float noise, float outlier_ratio,
+                  float min_depth, float max_depth, float f, int use_gaussian, float* Q_xw, float* P_xc, float* weights3) {
+  if (!q_xyzw || !t || n <= 0 || !Q_xw || !P_xc) return RPE_ERR_ARG;
+  rpe::sim::Rng rng(seed);
+  rpe::sim::simulate_3d_3d<float>(rng, make_pose(q_xyzw, t), n, noise, outlier_ratio, min_depth, max_depth, f,
+                                  use_gaussian != 0, Q_xw, P_xc, weights3);
+  return RPE_OK;
+}
+
+int rpe_sim_2d_3d(uint64_t seed, const float q_xyzw[4], const float t[3], int n, float noise_px, float outlier_ratio,
+                  float min_depth, float max_depth, float f, int use_gaussian, float* Q_xw, float* U_bv, float* P_gt,
+                  float* weights3) {
+  if (!q_xyzw || !t || n <= 0 || !Q_xw || !U_bv) return RPE_ERR_ARG;
+  rpe::sim::Rng rng(seed);
+  rpe::sim::simulate_2d_3d<float>(rng, make_pose(q_xyzw, t), n, noise_px, outlier_ratio, min_depth, max_depth, f,
+                                  use_gaussian != 0, Q_xw, U_bv, P_gt, weights3);
+  return RPE_OK;
+}
+
+int rpe_sim_2d_3d_nl(uint64_t seed, const float q_xyzw[4], const float t[3], int n, float n2d, float or2d, float n3d,
+                     float or3d, float nnl, float ornl, float min_depth, float max_depth, float f, int use_gaussian,
+                     float* Q_xw, float* M_nw, float* P_xc, float* N_nc, float* U_bv, float* weights3) {
+  if (!q_xyzw || !t || n <= 0 || !Q_xw || !M_nw || !P_xc || !N_nc || !U_bv) return RPE_ERR_ARG;
+  rpe::sim::Rng rng(seed);
+  rpe::sim::simulate_2d_3d_nl<float>(rng, make_pose(q_xyzw, t), n, n2d, or2d, n3d, or3d, nnl, ornl, min_depth, max_depth,
+                                     f, use_gaussian != 0, Q_xw, M_nw, P_xc, N_nc, U_bv, weights3);
+  return RPE_OK;
+}
+
+}  // extern "C"

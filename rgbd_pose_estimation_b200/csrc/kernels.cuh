@@ -1,0 +1,100 @@
+// kernels.cuh — launch interface between the C-ABI layer (capi.cu) and the kernel TUs.
+#ifndef RPE_KERNELS_CUH_
+#define RPE_KERNELS_CUH_
+
+#include "rpe_device.cuh"
+
+namespace rpe {
+
+// Device view of one frame's correspondences. Raw arrays are the caller's column-major 3 x n
+// layout (n contiguous xyz triples); `pk_*` are the pair-interleaved copies the tiled scorer streams
+// through shared memory.
+struct FrameView {
+  const float* bv;
+  const float* xc;
+  const float* nc;
+  const float* xw;
+  const float* nw;
+  int n;
+  int npairs_pad;      // pairs, padded to a multiple of kSubPairs with NaN correspondences
+  const float4* pk;    // packed pair records, `pk_f4_per_pair` float4 per pair
+  int pk_f4_per_pair;  // 3 (AO) ...
+  int pk_kind;         // which modalities are packed (bit0 2-D, bit1 3-D, bit2 normal)
+};
+
+struct Thresh {
+  float thr3d, cos_thr, cos_nl;
+};
+
+struct Worklist {
+  uint2* entries;  // (slot, correspondence)
+  unsigned int capacity;
+};
+
+constexpr int kSubPairs = 8;       // correspondences are rescanned in groups of 16
+constexpr int kTilePairs = 256;    // pairs per shared-memory stage
+constexpr int kScoreThreads = 256; // threads per scoring CTA
+constexpr int kHypPerThread = 2;   // hypotheses held in registers by one thread
+
+// -- prep ---------------------------------------------------------------------------------------
+void launch_reset_stats(FrameStats* st, cudaStream_t s);
+void launch_pack(const FrameView& f, int kind, float4* pk_out, FrameStats* st, cudaStream_t s);
+
+// -- generation ----------------------------------------------------------------------------------
+void launch_hypgen(int method, const FrameView& f, const int32_t* samples_dev, int H, HypGen* gen, HypFast* fast,
+                   int32_t* votes, FrameStats* st, cudaStream_t s);
+void launch_derive_fast(const HypGen* gen, HypFast* fast, int32_t* votes, int n_slots, FrameStats* st, cudaStream_t s);
+
+// -- scoring -------------------------------------------------------------------------------------
+void launch_score_fast(int method, const FrameView& f, const HypGen* gen, const HypFast* fast, int slot_begin,
+                       int slot_end, Thresh th, int32_t* votes, FrameStats* st, Worklist wl, int num_sms, cudaStream_t s);
+void launch_fixup(int method, const FrameView& f, const HypGen* gen, Thresh th, int32_t* votes, FrameStats* st,
+                  Worklist wl, int num_sms, cudaStream_t s);
+// exact-order scoring of every (slot, correspondence); `only_if_overflow` makes it a no-op unless
+// the fast pass overflowed its worklist.
+void launch_score_exact(int method, const FrameView& f, const HypGen* gen, int slot_begin, int slot_end, Thresh th,
+                        int32_t* votes, FrameStats* st, bool only_if_overflow, int num_sms, cudaStream_t s);
+
+// -- replay / mask / refit --------------------------------------------------------------------------
+void launch_replay(int method, const HypGen* gen, const int32_t* votes, int H, int n, float confidence,
+                   const FrameStats* st, ReplayOut* out, cudaStream_t s);
+
+struct RefitBuffers {
+  double* partials;   // [blocks x kMomentCount]
+  double* moments;    // [kMomentCount] reduced
+  int max_blocks;
+};
+constexpr int kMomentCount = 32;  // 16 Kabsch moments / 28 GN entries, padded
+
+// pose_rw: the ReplayOut written by the replay kernel (read for the pose, per-column inlier counts are
+// added to it); kabsch_out receives pose_rw with (q,t) replaced by the Kabsch refit over the 3-D inliers.
+void launch_mask(int method, const FrameView& f, ReplayOut* pose_rw, Thresh th, int16_t* mask, ReplayOut* kabsch_out,
+                 RefitBuffers rb, FrameStats* st, cudaStream_t s);
+void launch_reset_corr_bound(FrameStats* st, cudaStream_t s);
+// Kabsch from the moments left by launch_mask (or by launch_kabsch_moments); writes pose_out.
+void launch_kabsch_moments(const FrameView& f, const int16_t* flags3d /*null: all points*/, RefitBuffers rb,
+                           FrameStats* st, cudaStream_t s);
+void launch_kabsch_solve(RefitBuffers rb, int blocks_used, ReplayOut* pose_inout, int32_t* refit_ok, cudaStream_t s);
+
+struct GnState {  // device-resident LM state (mirrors oracle/refine.hpp refine_gn)
+  double Rp[9], tp[3];  // proposal
+  double Ra[9], ta[3];  // accepted
+  double H[21], g[6];   // accepted normal equations
+  double cost_acc;
+  double mu;
+  long long rows;
+  int have, done, evals, accepted;
+};
+void launch_gn_init(const ReplayOut* pose, GnState* st, cudaStream_t s);
+void launch_gn_iteration(const FrameView& f, const int16_t* mask, int mask_cols, float w2d, float w3d, float wnl,
+                         RefitBuffers rb, GnState* gs, FrameStats* st, cudaStream_t s);
+void launch_gn_finish(const GnState* gs, ReplayOut* pose_out, double* cost_out, int32_t* evals_out, cudaStream_t s);
+
+// -- microbenchmark -----------------------------------------------------------------------------------
+void launch_ffma_bench(float* sink, int iters, bool packed, int blocks, cudaStream_t s);
+
+int grid_blocks_for(int n, int threads);
+
+}  // namespace rpe
+
+#endif  // RPE_KERNELS_CUH_

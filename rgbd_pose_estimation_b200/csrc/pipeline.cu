@@ -1,0 +1,720 @@
+// pipeline.cu — everything around the scorer: hypothesis generation, the replay of the reference's
+// sequential keep-best / adaptive-stop rule, the winner's inlier mask, and the refits.
+//
+// Reference code replaced (paths into /root/reference/pose):
+//   generation   shinji (AbsoluteOrientation.hpp:47-99) on RandomElements samples (:113-130, :170-187)
+//   replay       `if (votes > max) {...; Iter = RANSACUpdateNumIters(...)}` AbsoluteOrientation.hpp:145-151,
+//                P3P.hpp:378-385, AbsoluteOrientationNormal.hpp:267-277,339-347,426-436
+//   mask         setInlier(inliers) of the accepted hypothesis, PnPPoseAdapter.hpp:196-202 etc.
+//   refit        shinji_ls / _ls1 / _ls2 (AbsoluteOrientation.hpp:273-342); LM on SE3 (north-star
+//                addition, twin in oracle/refine.hpp)
+//
+// Compiled with -fmad=false like every TU of this library.
+#include <cuda_runtime.h>
+#include <math_constants.h>
+
+#include "../../include/rpe/ransac_rule.h"
+#include "kernels.cuh"
+#include "solvers.cuh"
+#include "solvers_p3p.cuh"
+
+namespace rpe {
+
+// ================================================================================================
+// generation
+// ================================================================================================
+// -R and -t for the fast scorer. R is the quaternion polynomial evaluated in binary64 and rounded
+// once, so each entry is within one float rounding of the exact polynomial value.
+__device__ __forceinline__ void derive_fast(const HypGen& g, HypFast* f) {
+  const double x = g.q[0], y = g.q[1], z = g.q[2], w = g.q[3];
+  const double tx = 2.0 * x, ty = 2.0 * y, tz = 2.0 * z;
+  const double twx = tx * w, twy = ty * w, twz = tz * w;
+  const double txx = tx * x, txy = ty * x, txz = tz * x;
+  const double tyy = ty * y, tyz = tz * y, tzz = tz * z;
+  f->nR[0] = -(float)(1.0 - (tyy + tzz));
+  f->nR[1] = -(float)(txy - twz);
+  f->nR[2] = -(float)(txz + twy);
+  f->nR[3] = -(float)(txy + twz);
+  f->nR[4] = -(float)(1.0 - (txx + tzz));
+  f->nR[5] = -(float)(tyz - twx);
+  f->nR[6] = -(float)(txz - twy);
+  f->nR[7] = -(float)(tyz + twx);
+  f->nR[8] = -(float)(1.0 - (txx + tyy));
+  f->nt[0] = -g.t[0];
+  f->nt[1] = -g.t[1];
+  f->nt[2] = -g.t[2];
+}
+
+__device__ __forceinline__ void publish_hypothesis(const HypGen& g, int slot, HypGen* gen, HypFast* fast, int32_t* votes,
+                                                   FrameStats* st) {
+  gen[slot] = g;
+  HypFast f;
+  derive_fast(g, &f);
+  fast[slot] = f;
+  votes[slot] = g.valid ? 0 : -1;
+  if (g.valid) {
+    const float tn = sqrtf(g.t[0] * g.t[0] + g.t[1] * g.t[1] + g.t[2] * g.t[2]) * 1.000001f;
+    atomic_max_nonneg(&st->t_max_bits, tn);
+  }
+}
+
+// grid.x over iterations, grid.y = slot within the iteration (so a CTA runs one solver only).
+__global__ void __launch_bounds__(128)
+hypgen_kernel(int method, FrameView f, const int32_t* __restrict__ samples, int H, HypGen* __restrict__ gen,
+              HypFast* __restrict__ fast, int32_t* __restrict__ votes, FrameStats* __restrict__ st) {
+  const int ii = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ii >= H) return;
+  const int S = method_slots(method);
+  const int s = blockIdx.y;
+  const int solver = method_slot_solver(method, s);
+  const int32_t* sel = samples + 4 * ii;
+  HypGen g;
+  g.q[0] = g.q[1] = g.q[2] = 0.f;
+  g.q[3] = 1.f;
+  g.t[0] = g.t[1] = g.t[2] = 0.f;
+  g.valid = 0;
+  if (solver == SOLVER_AO) {
+    float Xw[9], Xc[9];
+    bool all_valid = true;
+    for (int k = 0; k < 3; ++k) {
+      const int c = sel[k];
+      const F3 pw = load_col(f.xw, c), pc = load_col(f.xc, c);
+      Xw[3 * k] = pw.x;
+      Xw[3 * k + 1] = pw.y;
+      Xw[3 * k + 2] = pw.z;
+      Xc[3 * k] = pc.x;
+      Xc[3 * k + 1] = pc.y;
+      Xc[3 * k + 2] = pc.z;
+      all_valid = all_valid && ex_is_valid(pc);
+    }
+    if (all_valid) {
+      const bool ok = shinji3<float>(Xw, Xc, method == RPE_SHINJI ? 3 : 4, g.q, g.t);
+      g.valid = ok ? 1 : 0;
+    }
+  } else if (solver == SOLVER_P3P) {
+    float Xw[12], bv[12];
+    for (int k = 0; k < 4; ++k) {
+      const int c = sel[k];
+      const F3 pw = load_col(f.xw, c), b = load_col(f.bv, c);
+      Xw[3 * k] = pw.x;
+      Xw[3 * k + 1] = pw.y;
+      Xw[3 * k + 2] = pw.z;
+      bv[3 * k] = b.x;
+      bv[3 * k + 1] = b.y;
+      bv[3 * k + 2] = b.z;
+    }
+    // kneip_ransac/prosac start the 4th-point search from 1000000.0 (P3P.hpp:338,415); the
+    // matrix-argument overload used by the hybrids starts from numeric_limits::max() (P3P.hpp:258)
+    const float start = (method == RPE_KNEIP || method == RPE_KNEIP_QUAT) ? 1000000.0f : 3.402823466e+38f;
+    g.valid = kneip_select<float>(Xw, bv, start, g.q, g.t) ? 1 : 0;
+  } else {
+    float pc0[3], nc0[3], pc1[3], pw0[3], nw0[3], pw1[3];
+    const int c0 = sel[0], c1 = sel[1];
+    for (int r = 0; r < 3; ++r) {
+      pc0[r] = f.xc[3 * c0 + r];
+      nc0[r] = f.nc[3 * c0 + r];
+      pc1[r] = f.xc[3 * c1 + r];
+      pw0[r] = f.xw[3 * c0 + r];
+      nw0[r] = f.nw[3 * c0 + r];
+      pw1[r] = f.xw[3 * c1 + r];
+    }
+    // An invalid (all-NaN) camera point simply propagates NaN into the translation (the reference
+    // would read a stale column of its hoisted sample buffer there: AbsoluteOrientationNormal.hpp:61-65).
+    nl_2p<float>(pc0, nc0, pc1, pw0, nw0, pw1, g.q, g.t);
+    g.valid = 1;
+  }
+  publish_hypothesis(g, ii * S + s, gen, fast, votes, st);
+}
+
+void launch_hypgen(int method, const FrameView& f, const int32_t* samples_dev, int H, HypGen* gen, HypFast* fast,
+                   int32_t* votes, FrameStats* st, cudaStream_t s) {
+  if (H <= 0) return;
+  dim3 grid((H + 127) / 128, method_slots(method));
+  hypgen_kernel<<<grid, 128, 0, s>>>(method, f, samples_dev, H, gen, fast, votes, st);
+}
+
+__global__ void derive_fast_kernel(const HypGen* __restrict__ gen, HypFast* __restrict__ fast, int32_t* __restrict__ votes,
+                                   int n_slots, FrameStats* __restrict__ st) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_slots) return;
+  HypGen g = gen[i];
+  HypFast f;
+  derive_fast(g, &f);
+  fast[i] = f;
+  votes[i] = g.valid ? 0 : -1;
+  if (g.valid) {
+    const float tn = sqrtf(g.t[0] * g.t[0] + g.t[1] * g.t[1] + g.t[2] * g.t[2]) * 1.000001f;
+    atomic_max_nonneg(&st->t_max_bits, tn);
+  }
+}
+void launch_derive_fast(const HypGen* gen, HypFast* fast, int32_t* votes, int n_slots, FrameStats* st, cudaStream_t s) {
+  if (n_slots <= 0) return;
+  derive_fast_kernel<<<(n_slots + 127) / 128, 128, 0, s>>>(gen, fast, votes, n_slots, st);
+}
+
+// ================================================================================================
+// replay of the sequential rule (one warp; all lanes run the scalar part redundantly)
+// ================================================================================================
+__global__ void replay_kernel(int method, const HypGen* __restrict__ gen, const int32_t* __restrict__ votes, int H, int n,
+                              float confidence, const FrameStats* __restrict__ st, ReplayOut* __restrict__ out) {
+  const int lane = threadIdx.x;
+  const int S = method_slots(method);
+  const int K = method_model_points(method);
+  const int mod = method_modalities(method);
+  const int E = H * S;
+  int best = -1, Iter = H, win = -1, cur_iter = -1;
+  bool stop = false;
+  for (int base = 0; base < E && !stop; base += 32) {
+    const int i = base + lane;
+    const int v = i < E ? votes[i] : -1;
+    int pm = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int tv = __shfl_up_sync(0xffffffffu, pm, o);
+      if (lane >= o) pm = max(pm, tv);
+    }
+    int excl = __shfl_up_sync(0xffffffffu, pm, 1);
+    if (lane == 0) excl = -2147483647;
+    const bool rec = v >= 0 && v > max(excl, best);
+    unsigned int m = __ballot_sync(0xffffffffu, rec);
+    while (m) {
+      const int b = __ffs(m) - 1;
+      m &= m - 1;
+      const int idx = base + b;
+      const int it = idx / S;
+      const int vb = __shfl_sync(0xffffffffu, v, b);
+      if (it != cur_iter) {
+        if (it >= Iter) {  // `for (ii = 0; ii < Iter; ii++)` would not have reached this iteration
+          stop = true;
+          break;
+        }
+        cur_iter = it;
+      }
+      best = vb;
+      win = idx;
+      Iter = update_num_iters(confidence, outlier_ratio(mod, n, vb), K, Iter);
+    }
+    if ((long long)(base + 32) >= (long long)Iter * S) stop = true;  // nothing below the loop bound is left
+  }
+  if (lane == 0) {
+    if (win >= 0) {
+      const HypGen g = gen[win];
+      for (int k = 0; k < 4; ++k) out->q[k] = g.q[k];
+      for (int k = 0; k < 3; ++k) out->t[k] = g.t[k];
+    } else {
+      out->q[0] = out->q[1] = out->q[2] = 0.f;
+      out->q[3] = 1.f;
+      out->t[0] = out->t[1] = out->t[2] = 0.f;
+    }
+    out->max_votes = best;
+    out->iter_final = Iter;
+    out->winner = win;
+    out->n_slots = E;
+    out->n_borderline = (int)st->wl_count;
+    out->flags = st->wl_overflow ? 1 : 0;
+    out->n_inliers[0] = out->n_inliers[1] = out->n_inliers[2] = 0;
+    out->refit_ok = 0;
+  }
+}
+
+void launch_replay(int method, const HypGen* gen, const int32_t* votes, int H, int n, float confidence,
+                   const FrameStats* st, ReplayOut* out, cudaStream_t s) {
+  replay_kernel<<<1, 32, 0, s>>>(method, gen, votes, H, n, confidence, st, out);
+}
+
+// ================================================================================================
+// block-level deterministic reduction of NV doubles -> partials[blockIdx][NV]
+// ================================================================================================
+template <int NV>
+__device__ __forceinline__ void block_reduce_store(double* v, double* __restrict__ partials, double* smem /*[8*NV]*/) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    double x = v[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+    if (lane == 0) smem[warp * NV + k] = x;
+  }
+  __syncthreads();
+  const int nw = blockDim.x >> 5;
+  if (threadIdx.x < NV) {
+    double x = 0.0;
+    for (int w = 0; w < nw; ++w) x += smem[w * NV + threadIdx.x];
+    partials[(size_t)blockIdx.x * kMomentCount + threadIdx.x] = x;
+  }
+}
+// Sum partials over blocks in a fixed order (lane-strided, then a shuffle tree): one warp.
+__device__ __forceinline__ double reduce_partials(const double* __restrict__ partials, int nblocks, int comp) {
+  const int lane = threadIdx.x & 31;
+  double x = 0.0;
+  for (int b = lane; b < nblocks; b += 32) x += partials[(size_t)b * kMomentCount + comp];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+  return __shfl_sync(0xffffffffu, x, 0);
+}
+
+// Kabsch from moments m[0]=K, m[1..3]=sum x_w, m[4..6]=sum x_c, m[7..15]=sum x_c x_w^T (row-major).
+// Same closed form as shinji (centroids, cross-covariance / K, SVD, det fix, t = c_c - R c_w), evaluated in binary64.
+__device__ bool kabsch_from_moments(const double* m, float* q_out, float* t_out) {
+  const double K = m[0];
+  if (!(K >= 3.0)) return false;  // reference asserts 3 <= K (AbsoluteOrientation.hpp:53)
+  double cw[3], cc[3];
+  for (int r = 0; r < 3; ++r) {
+    cw[r] = m[1 + r] / K;
+    cc[r] = m[4 + r] / K;
+  }
+  double M[9];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) M[3 * i + j] = (m[7 + 3 * i + j] - K * cc[i] * cw[j]) / K;
+  double q[4];
+  const bool ok = rotation_from_covariance<double>(M, q);
+  double rc[3];
+  quat_rotate<double>(q, cw, rc);
+  for (int k = 0; k < 4; ++k) q_out[k] = (float)q[k];
+  for (int r = 0; r < 3; ++r) t_out[r] = (float)(cc[r] - rc[r]);
+  return ok;
+}
+
+// ================================================================================================
+// winner's mask (+ Kabsch moments of the 3-D inliers, + the Kabsch solve in the last CTA)
+// ================================================================================================
+__global__ void __launch_bounds__(256)
+mask_kernel(int method, FrameView f, ReplayOut* pose_rw, Thresh th, int16_t* __restrict__ mask, RefitBuffers rb,
+            ReplayOut* kabsch_out, FrameStats* st) {
+  const ReplayOut* pose = pose_rw;
+  __shared__ double red[8 * 16];
+  __shared__ int cnts[3];
+  __shared__ bool is_last;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = f.n;
+  const int cols = method_mask_cols(method);
+  if (threadIdx.x < 3) cnts[threadIdx.x] = 0;
+  __syncthreads();
+  HypGen h;
+  for (int k = 0; k < 4; ++k) h.q[k] = pose->q[k];
+  for (int k = 0; k < 3; ++k) h.t[k] = pose->t[k];
+  const bool have = pose->winner >= 0;
+  float Rm[9];
+  ex_quat_to_matrix(h.q, Rm);
+  const bool u2 = method_uses_2d(method), u3 = method_uses_3d(method), un = method_uses_nl(method);
+  double mom[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) mom[k] = 0.0;
+  bool f2 = false, f3d = false, fn = false;
+  if (c < n) {
+    if (have) {
+      const F3 xw = load_col(f.xw, c);
+      bool valid = false;
+      F3 xc = f3(0.f, 0.f, 0.f);
+      if (u3 || un) {
+        xc = load_col(f.xc, c);
+        valid = ex_is_valid(xc);
+      }
+      if (un && valid) fn = ex_test_nl(h.q, load_col(f.nw, c), load_col(f.nc, c), th.cos_nl);
+      if (u3 && valid) f3d = ex_test_3d(h.q, h.t, xw, xc, th.thr3d);
+      if (u2) f2 = ex_test_2d(h.q, h.t, method == RPE_KNEIP ? Rm : nullptr, xw, load_col(f.bv, c), th.cos_thr);
+      if (f3d) {
+        mom[0] = 1.0;
+        const double w3[3] = {xw.x, xw.y, xw.z}, c3[3] = {xc.x, xc.y, xc.z};
+        for (int r = 0; r < 3; ++r) {
+          mom[1 + r] = w3[r];
+          mom[4 + r] = c3[r];
+          for (int q = 0; q < 3; ++q) mom[7 + 3 * r + q] = c3[r] * w3[q];
+        }
+      }
+    } else {
+      f2 = f3d = fn = true;  // adapters start with setOnes() and setInlier is never called
+    }
+    mask[c] = (int16_t)((cols == 1 || u2) ? (f2 ? 1 : 0) : 0);
+    if (cols >= 2) mask[n + c] = (int16_t)(u3 ? (f3d ? 1 : 0) : (have ? 0 : 1));
+    if (cols >= 3) mask[2 * n + c] = (int16_t)(fn ? 1 : 0);
+  }
+  // per-column counts
+  const unsigned b2 = __ballot_sync(0xffffffffu, f2 && have), b3 = __ballot_sync(0xffffffffu, f3d && have),
+                 bn = __ballot_sync(0xffffffffu, fn && have);
+  if ((threadIdx.x & 31) == 0) {
+    if (b2) atomicAdd(&cnts[0], __popc(b2));
+    if (b3) atomicAdd(&cnts[1], __popc(b3));
+    if (bn) atomicAdd(&cnts[2], __popc(bn));
+  }
+  block_reduce_store<16>(mom, rb.partials, red);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int k = 0; k < 3; ++k)
+      if (cnts[k]) atomicAdd(&pose_rw->n_inliers[k], cnts[k]);
+    __threadfence();
+    const unsigned int t = atomicAdd(&st->ticket, 1u);
+    is_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (is_last && threadIdx.x < 32) {
+    __threadfence();
+    double m[16];
+    for (int k = 0; k < 16; ++k) m[k] = reduce_partials(rb.partials, gridDim.x, k);
+    if (threadIdx.x == 0) {
+      for (int k = 0; k < 16; ++k) rb.moments[k] = m[k];
+      ReplayOut o = *pose_rw;
+      float q[4], t[3];
+      bool ok = false;
+      if (u3 && have) ok = kabsch_from_moments(m, q, t);
+      if (ok) {
+        for (int k = 0; k < 4; ++k) o.q[k] = q[k];
+        for (int k = 0; k < 3; ++k) o.t[k] = t[k];
+      }
+      o.refit_ok = ok ? 1 : 0;
+      *kabsch_out = o;
+      st->ticket = 0;
+    }
+  }
+}
+
+void launch_mask(int method, const FrameView& f, ReplayOut* pose_rw, Thresh th, int16_t* mask, ReplayOut* kabsch_out,
+                 RefitBuffers rb, FrameStats* st, cudaStream_t s) {
+  const int threads = 256;
+  const int blocks = (f.n + threads - 1) / threads;
+  mask_kernel<<<blocks, threads, 0, s>>>(method, f, pose_rw, th, mask, rb, kabsch_out, st);
+}
+
+// Stand-alone moments over an explicit flag column (after rpe_set_mask) or over all points (shinji_ls2).
+__global__ void __launch_bounds__(256)
+kabsch_moments_kernel(FrameView f, const int16_t* __restrict__ flags3d, RefitBuffers rb) {
+  __shared__ double red[8 * 16];
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  double mom[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) mom[k] = 0.0;
+  if (c < f.n && (!flags3d || flags3d[c] == 1)) {
+    const F3 xw = load_col(f.xw, c), xc = load_col(f.xc, c);
+    mom[0] = 1.0;
+    const double w3[3] = {xw.x, xw.y, xw.z}, c3[3] = {xc.x, xc.y, xc.z};
+    for (int r = 0; r < 3; ++r) {
+      mom[1 + r] = w3[r];
+      mom[4 + r] = c3[r];
+      for (int q = 0; q < 3; ++q) mom[7 + 3 * r + q] = c3[r] * w3[q];
+    }
+  }
+  block_reduce_store<16>(mom, rb.partials, red);
+}
+void launch_kabsch_moments(const FrameView& f, const int16_t* flags3d, RefitBuffers rb, FrameStats* st, cudaStream_t s) {
+  (void)st;
+  const int threads = 256;
+  kabsch_moments_kernel<<<(f.n + threads - 1) / threads, threads, 0, s>>>(f, flags3d, rb);
+}
+__global__ void kabsch_solve_kernel(RefitBuffers rb, int blocks_used, ReplayOut* __restrict__ pose, int32_t* refit_ok) {
+  double m[16];
+  for (int k = 0; k < 16; ++k) m[k] = reduce_partials(rb.partials, blocks_used, k);
+  if (threadIdx.x == 0) {
+    for (int k = 0; k < 16; ++k) rb.moments[k] = m[k];
+    float q[4], t[3];
+    const bool ok = kabsch_from_moments(m, q, t);
+    if (ok) {
+      for (int k = 0; k < 4; ++k) pose->q[k] = q[k];
+      for (int k = 0; k < 3; ++k) pose->t[k] = t[k];
+    }
+    pose->refit_ok = ok ? 1 : 0;
+    if (refit_ok) *refit_ok = ok ? 1 : 0;
+  }
+}
+void launch_kabsch_solve(RefitBuffers rb, int blocks_used, ReplayOut* pose_inout, int32_t* refit_ok, cudaStream_t s) {
+  kabsch_solve_kernel<<<1, 32, 0, s>>>(rb, blocks_used, pose_inout, refit_ok);
+}
+
+// ================================================================================================
+// LM / Gauss-Newton on SE(3): fused residual + Jacobian + normal equations, FP64 reductions,
+// 6x6 Cholesky and the SE3 exponential in the last CTA. Twin of oracle/refine.hpp::refine_gn.
+// ================================================================================================
+__global__ void gn_init_kernel(const ReplayOut* __restrict__ pose, GnState* __restrict__ gs) {
+  if (threadIdx.x != 0) return;
+  double q[4] = {pose->q[0], pose->q[1], pose->q[2], pose->q[3]};
+  const double qn = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+  for (int k = 0; k < 4; ++k) q[k] /= qn;
+  const double x = q[0], y = q[1], z = q[2], w = q[3];
+  const double tx = 2.0 * x, ty = 2.0 * y, tz = 2.0 * z;
+  const double twx = tx * w, twy = ty * w, twz = tz * w;
+  const double txx = tx * x, txy = ty * x, txz = tz * x;
+  const double tyy = ty * y, tyz = tz * y, tzz = tz * z;
+  double* R = gs->Rp;
+  R[0] = 1.0 - (tyy + tzz);
+  R[1] = txy - twz;
+  R[2] = txz + twy;
+  R[3] = txy + twz;
+  R[4] = 1.0 - (txx + tzz);
+  R[5] = tyz - twx;
+  R[6] = txz - twy;
+  R[7] = tyz + twx;
+  R[8] = 1.0 - (txx + tyy);
+  for (int k = 0; k < 3; ++k) gs->tp[k] = pose->t[k];
+  for (int k = 0; k < 9; ++k) gs->Ra[k] = R[k];
+  for (int k = 0; k < 3; ++k) gs->ta[k] = gs->tp[k];
+  gs->cost_acc = 0.0;
+  gs->mu = 1e-4;
+  gs->rows = 0;
+  gs->have = 0;
+  gs->done = 0;
+  gs->evals = 0;
+  gs->accepted = 0;
+}
+void launch_gn_init(const ReplayOut* pose, GnState* st, cudaStream_t s) { gn_init_kernel<<<1, 32, 0, s>>>(pose, st); }
+
+// acc layout: [0..20] upper triangle of J^T J, [21..26] J^T r, [27] cost, [28] rows
+__device__ __forceinline__ void gn_add_row(double* acc, const double J[6], double r, double w) {
+  int k = 0;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+#pragma unroll
+    for (int j = i; j < 6; ++j) acc[k++] += w * J[i] * J[j];
+    acc[21 + i] += w * J[i] * r;
+  }
+  acc[27] += w * r * r;
+  acc[28] += 1.0;
+}
+__device__ __forceinline__ void gn_point_rows(const double y[3], double J[3][6]) {
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int c = 0; c < 6; ++c) J[r][c] = 0.0;
+  J[0][0] = J[1][1] = J[2][2] = 1.0;
+  J[0][4] = y[2];
+  J[0][5] = -y[1];
+  J[1][3] = -y[2];
+  J[1][5] = y[0];
+  J[2][3] = y[1];
+  J[2][4] = -y[0];
+}
+
+__device__ bool gn_solve(const double* Hu, const double* g, double mu, double* delta) {
+  double A[6][6], L[6][6];
+  int k = 0;
+  for (int i = 0; i < 6; ++i)
+    for (int j = i; j < 6; ++j) {
+      A[i][j] = A[j][i] = Hu[k++];
+    }
+  for (int i = 0; i < 6; ++i) A[i][i] += mu * A[i][i];
+  for (int i = 0; i < 6; ++i)
+    for (int j = 0; j < 6; ++j) L[i][j] = 0.0;
+  for (int j = 0; j < 6; ++j) {
+    double s = A[j][j];
+    for (int p = 0; p < j; ++p) s -= L[j][p] * L[j][p];
+    if (!(s > 0.0)) return false;
+    L[j][j] = sqrt(s);
+    for (int i = j + 1; i < 6; ++i) {
+      double v = A[i][j];
+      for (int p = 0; p < j; ++p) v -= L[i][p] * L[j][p];
+      L[i][j] = v / L[j][j];
+    }
+  }
+  double z[6];
+  for (int i = 0; i < 6; ++i) {
+    double v = -g[i];
+    for (int p = 0; p < i; ++p) v -= L[i][p] * z[p];
+    z[i] = v / L[i][i];
+  }
+  for (int i = 5; i >= 0; --i) {
+    double v = z[i];
+    for (int p = i + 1; p < 6; ++p) v -= L[p][i] * delta[p];
+    delta[i] = v / L[i][i];
+  }
+  return true;
+}
+
+// T <- exp(delta) T (sophus/se3.hpp:321-342)
+__device__ void se3_exp_left(const double* delta, double* R, double* t) {
+  const double v[3] = {delta[0], delta[1], delta[2]};
+  const double w[3] = {delta[3], delta[4], delta[5]};
+  const double th2 = w[0] * w[0] + w[1] * w[1] + w[2] * w[2];
+  const double th = sqrt(th2);
+  double A, B, C;
+  if (th < 1e-6) {
+    A = 1.0 - th2 / 6.0;
+    B = 0.5 - th2 / 24.0;
+    C = 1.0 / 6.0 - th2 / 120.0;
+  } else {
+    A = sin(th) / th;
+    B = (1.0 - cos(th)) / th2;
+    C = (th - sin(th)) / (th2 * th);
+  }
+  const double W[9] = {0, -w[2], w[1], w[2], 0, -w[0], -w[1], w[0], 0};
+  double W2[9];
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) W2[3 * r + c] = W[3 * r] * W[c] + W[3 * r + 1] * W[3 + c] + W[3 * r + 2] * W[6 + c];
+  double Rd[9], V[9];
+  for (int i = 0; i < 9; ++i) {
+    const double I = (i == 0 || i == 4 || i == 8) ? 1.0 : 0.0;
+    Rd[i] = I + A * W[i] + B * W2[i];
+    V[i] = I + B * W[i] + C * W2[i];
+  }
+  double Rn[9], tn[3];
+  for (int r = 0; r < 3; ++r) {
+    for (int c = 0; c < 3; ++c) Rn[3 * r + c] = Rd[3 * r] * R[c] + Rd[3 * r + 1] * R[3 + c] + Rd[3 * r + 2] * R[6 + c];
+    tn[r] = Rd[3 * r] * t[0] + Rd[3 * r + 1] * t[1] + Rd[3 * r + 2] * t[2] + V[3 * r] * v[0] + V[3 * r + 1] * v[1] +
+            V[3 * r + 2] * v[2];
+  }
+  for (int i = 0; i < 9; ++i) R[i] = Rn[i];
+  for (int i = 0; i < 3; ++i) t[i] = tn[i];
+}
+
+__global__ void __launch_bounds__(256)
+gn_iteration_kernel(FrameView f, const int16_t* __restrict__ mask, int mask_cols, float w2d, float w3d, float wnl,
+                    RefitBuffers rb, GnState* __restrict__ gs, FrameStats* __restrict__ st) {
+  if (gs->done) return;
+  __shared__ double red[8 * 29];
+  __shared__ bool is_last;
+  const int n = f.n;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  double acc[29];
+#pragma unroll
+  for (int k = 0; k < 29; ++k) acc[k] = 0.0;
+  if (c < n) {
+    const bool u2 = mask_cols >= 1 && f.bv && w2d > 0.f && mask[c] == 1;
+    const bool u3 = mask_cols >= 2 && f.xc && w3d > 0.f && mask[n + c] == 1;
+    const bool un = mask_cols >= 3 && f.nc && wnl > 0.f && mask[2 * n + c] == 1;
+    if (u2 || u3 || un) {
+      // FP32 residuals / Jacobian entries from the FP32 copy of the current proposal, FP64 accumulation
+      float R[9], t[3];
+#pragma unroll
+      for (int k = 0; k < 9; ++k) R[k] = (float)gs->Rp[k];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) t[k] = (float)gs->tp[k];
+      const F3 x = load_col(f.xw, c);
+      float yf[3];
+#pragma unroll
+      for (int r = 0; r < 3; ++r) yf[r] = fmaf(R[3 * r], x.x, fmaf(R[3 * r + 1], x.y, fmaf(R[3 * r + 2], x.z, t[r])));
+      const double y[3] = {yf[0], yf[1], yf[2]};
+      double Jy[3][6];
+      gn_point_rows(y, Jy);
+      if (u3) {
+        const F3 p = load_col(f.xc, c);
+        const float rf[3] = {yf[0] - p.x, yf[1] - p.y, yf[2] - p.z};
+#pragma unroll
+        for (int r = 0; r < 3; ++r) gn_add_row(acc, Jy[r], (double)rf[r], (double)w3d);
+      }
+      if (u2) {
+        const F3 b = load_col(f.bv, c);
+        const float nyf = sqrtf(yf[0] * yf[0] + yf[1] * yf[1] + yf[2] * yf[2]);
+        const float uf[3] = {yf[0] / nyf, yf[1] / nyf, yf[2] / nyf};
+        const float resf[3] = {b.y * uf[2] - b.z * uf[1], b.z * uf[0] - b.x * uf[2], b.x * uf[1] - b.y * uf[0]};
+        const double u[3] = {uf[0], uf[1], uf[2]}, ny = nyf, bd[3] = {b.x, b.y, b.z};
+        double Ju[3][6];
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+          for (int cc = 0; cc < 6; ++cc) {
+            double s = 0.0;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) s += (((r == k) ? 1.0 : 0.0) - u[r] * u[k]) / ny * Jy[k][cc];
+            Ju[r][cc] = s;
+          }
+        double Jr[3][6];
+#pragma unroll
+        for (int cc = 0; cc < 6; ++cc) {
+          Jr[0][cc] = bd[1] * Ju[2][cc] - bd[2] * Ju[1][cc];
+          Jr[1][cc] = bd[2] * Ju[0][cc] - bd[0] * Ju[2][cc];
+          Jr[2][cc] = bd[0] * Ju[1][cc] - bd[1] * Ju[0][cc];
+        }
+#pragma unroll
+        for (int r = 0; r < 3; ++r) gn_add_row(acc, Jr[r], (double)resf[r], (double)w2d);
+      }
+      if (un) {
+        const F3 nw = load_col(f.nw, c), nc = load_col(f.nc, c);
+        float mf[3];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) mf[r] = fmaf(R[3 * r], nw.x, fmaf(R[3 * r + 1], nw.y, R[3 * r + 2] * nw.z));
+        const double m[3] = {mf[0], mf[1], mf[2]};
+        double Jn[3][6];
+        gn_point_rows(m, Jn);
+        const float rf[3] = {mf[0] - nc.x, mf[1] - nc.y, mf[2] - nc.z};
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+          Jn[r][0] = Jn[r][1] = Jn[r][2] = 0.0;
+          gn_add_row(acc, Jn[r], (double)rf[r], (double)wnl);
+        }
+      }
+    }
+  }
+  block_reduce_store<29>(acc, rb.partials, red);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned int tk = atomicAdd(&st->ticket2, 1u);
+    is_last = (tk == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!(is_last && threadIdx.x < 32)) return;
+  __threadfence();
+  double tot[29];
+  for (int k = 0; k < 29; ++k) tot[k] = reduce_partials(rb.partials, gridDim.x, k);
+  if (threadIdx.x != 0) return;
+  st->ticket2 = 0;
+  // ---- LM tail (oracle/refine.hpp::refine_gn, one evaluation) ----
+  gs->evals += 1;
+  const double cost = tot[27];
+  if (!gs->have || cost < gs->cost_acc) {
+    for (int k = 0; k < 9; ++k) gs->Ra[k] = gs->Rp[k];
+    for (int k = 0; k < 3; ++k) gs->ta[k] = gs->tp[k];
+    for (int k = 0; k < 21; ++k) gs->H[k] = tot[k];
+    for (int k = 0; k < 6; ++k) gs->g[k] = tot[21 + k];
+    gs->cost_acc = cost;
+    gs->rows = (long long)tot[28];
+    if (gs->have) {
+      double mu = gs->mu * 0.1;
+      gs->mu = mu < 1e-12 ? 1e-12 : mu;
+      gs->accepted += 1;
+    }
+    gs->have = 1;
+  } else {
+    gs->mu = gs->mu * 10.0;
+  }
+  if (gs->rows < 6) {
+    gs->done = 1;
+    return;
+  }
+  double delta[6];
+  int tries = 0;
+  double mu = gs->mu;
+  while (!gn_solve(gs->H, gs->g, mu, delta) && tries < 8) {
+    mu *= 10.0;
+    ++tries;
+  }
+  gs->mu = mu;
+  if (tries == 8) {
+    gs->done = 1;
+    return;
+  }
+  double mx = 0.0;
+  for (int k = 0; k < 6; ++k) mx = fabs(delta[k]) > mx ? fabs(delta[k]) : mx;
+  if (mx < 1e-10) {
+    gs->done = 1;
+    return;
+  }
+  for (int k = 0; k < 9; ++k) gs->Rp[k] = gs->Ra[k];
+  for (int k = 0; k < 3; ++k) gs->tp[k] = gs->ta[k];
+  se3_exp_left(delta, gs->Rp, gs->tp);
+}
+
+void launch_gn_iteration(const FrameView& f, const int16_t* mask, int mask_cols, float w2d, float w3d, float wnl,
+                         RefitBuffers rb, GnState* gs, FrameStats* st, cudaStream_t s) {
+  const int threads = 256;
+  gn_iteration_kernel<<<(f.n + threads - 1) / threads, threads, 0, s>>>(f, mask, mask_cols, w2d, w3d, wnl, rb, gs, st);
+}
+
+__global__ void gn_finish_kernel(const GnState* __restrict__ gs, ReplayOut* __restrict__ pose, double* cost_out,
+                                 int32_t* evals_out) {
+  if (threadIdx.x != 0) return;
+  if (gs->have) {
+    double q[4];
+    so3_from_matrix<double>(gs->Ra, q);
+    const double nn = sqrt((q[0] * q[0] + q[1] * q[1]) + (q[2] * q[2] + q[3] * q[3]));
+    for (int k = 0; k < 4; ++k) pose->q[k] = (float)(q[k] / nn);
+    for (int k = 0; k < 3; ++k) pose->t[k] = (float)gs->ta[k];
+    pose->refit_ok = 1;
+  } else {
+    pose->refit_ok = 0;
+  }
+  *cost_out = gs->cost_acc;
+  *evals_out = gs->evals;
+}
+void launch_gn_finish(const GnState* gs, ReplayOut* pose_out, double* cost_out, int32_t* evals_out, cudaStream_t s) {
+  gn_finish_kernel<<<1, 32, 0, s>>>(gs, pose_out, cost_out, evals_out);
+}
+
+}  // namespace rpe

@@ -1,0 +1,488 @@
+// score.cu — hypothesis x correspondence scoring for sm_100a.
+//
+// Replaces the reference's inner `for c` loops (the ~100 % hot spot of the CPU path):
+//   3-D test   pose/AbsoluteOrientation.hpp:135-143 (=:192-200, :250-258, :403-411)
+//   2-D test   pose/P3P.hpp:362-376 / :439-453, AbsoluteOrientation.hpp:413-421
+//   normal     pose/AbsoluteOrientationNormal.hpp:245-253, :322-329, :397-404
+//
+// Design: one thread owns kHypPerThread hypotheses in registers (-R, -t, each value
+// duplicated into an f32x2 register pair); a CTA streams its slice of the correspondences through a
+// double-buffered shared-memory ring filled by 1-D bulk TMA (cp.async.bulk + mbarrier); every lane
+// reads the same pair record (LDS.128 broadcast) so one record feeds 32 x kHypPerThread x 2
+// evaluations. Votes accumulate in per-thread registers — no cross-thread reduction per evaluation —
+// and are added to the global vote table once per CTA.
+//
+// Exactness: the fast path evaluates  s = |x_c - t - R x_w|^2 - thr^2  with 12 (packed) FMA + 3 ADD.
+// sign(s) decides, unless |s| <= band, where `band` rigorously covers the rounding error of BOTH
+// this path and the reference's quaternion-sandwich/sqrt path. Borderline
+// evaluations are removed from the fast count and appended to a worklist which fixup_kernel
+// re-evaluates in the reference's exact operation order. Inlier counts are therefore identical to the
+// CPU path's, evaluation by evaluation.
+#include <cuda_runtime.h>
+#include <math_constants.h>
+
+#include "kernels.cuh"
+
+namespace rpe {
+
+// ================================================================================================
+// small PTX helpers: mbarrier + 1-D bulk TMA
+// ================================================================================================
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok = 0;
+  const uint32_t addr = smem_u32(bar);
+  while (!ok) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  }
+}
+
+// ================================================================================================
+// reset / pack
+// ================================================================================================
+__global__ void reset_stats_kernel(FrameStats* st) {
+  if (threadIdx.x == 0) {  // m_corr_bits belongs to the packed frame and is reset by the pack only
+    st->t_max_bits = 0;
+    st->wl_count = 0;
+    st->wl_overflow = 0;
+    st->ticket = 0;
+    st->ticket2 = 0;
+  }
+}
+void launch_reset_stats(FrameStats* st, cudaStream_t s) { reset_stats_kernel<<<1, 32, 0, s>>>(st); }
+__global__ void reset_corr_bound_kernel(FrameStats* st) {
+  if (threadIdx.x == 0) {
+    st->m_corr_bits = 0;
+    st->m_bv_bits = 0;
+  }
+}
+void launch_reset_corr_bound(FrameStats* st, cudaStream_t s) { reset_corr_bound_kernel<<<1, 32, 0, s>>>(st); }
+
+struct PackSrc {
+  const float* a[5];
+  int count;
+};
+
+// One thread per PAIR of correspondences (2j, 2j+1). For every source array in order, writes
+// x(2j) x(2j+1) y(2j) y(2j+1) z(2j) z(2j+1): each 64-bit half is a ready-made f32x2 operand.
+// Also reduces max_i(|x_w| + |x_c|) over finite points for the guard band.
+__global__ void pack_kernel(PackSrc src, int n, int npairs_pad, int f4_per_pair, float* __restrict__ out,
+                            const float* __restrict__ xw, const float* __restrict__ xc, FrameStats* st) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  float mloc = 0.f;
+  if (j < npairs_pad) {
+    float* o = out + (size_t)j * f4_per_pair * 4;
+    const int c0 = 2 * j, c1 = 2 * j + 1;
+    int w = 0;
+    for (int k = 0; k < src.count; ++k) {
+      const float* a = src.a[k];
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        o[w++] = c0 < n ? a[3 * c0 + r] : CUDART_NAN_F;
+        o[w++] = c1 < n ? a[3 * c1 + r] : CUDART_NAN_F;
+      }
+    }
+    for (; w < f4_per_pair * 4; ++w) o[w] = 0.f;
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int c = 2 * j + u;
+      if (c < n) {
+        float m = 0.f;
+        const float a0 = xw[3 * c], a1 = xw[3 * c + 1], a2 = xw[3 * c + 2];
+        m = sqrtf(a0 * a0 + a1 * a1 + a2 * a2);
+        if (xc) {
+          const float b0 = xc[3 * c], b1 = xc[3 * c + 1], b2 = xc[3 * c + 2];
+          const float mc = sqrtf(b0 * b0 + b1 * b1 + b2 * b2);
+          if (mc == mc && mc < CUDART_INF_F) m += mc;
+        }
+        if (m == m && m < CUDART_INF_F) mloc = fmaxf(mloc, m);
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mloc = fmaxf(mloc, __shfl_xor_sync(0xffffffffu, mloc, o));
+  if ((threadIdx.x & 31) == 0 && mloc > 0.f) atomic_max_nonneg(&st->m_corr_bits, mloc);
+}
+
+void launch_pack(const FrameView& f, int kind, float4* pk_out, FrameStats* st, cudaStream_t s) {
+  PackSrc src;
+  src.count = 0;
+  src.a[src.count++] = f.xw;
+  if (kind & 2) src.a[src.count++] = f.xc;
+  if (kind & 1) src.a[src.count++] = f.bv;
+  if (kind & 4) {
+    src.a[src.count++] = f.nw;
+    src.a[src.count++] = f.nc;
+  }
+  const int threads = 256;
+  const int blocks = (f.npairs_pad + threads - 1) / threads;
+  pack_kernel<<<blocks, threads, 0, s>>>(src, f.n, f.npairs_pad, f.pk_f4_per_pair, (float*)pk_out, f.xw,
+                                         (kind & 2) ? f.xc : nullptr, st);
+}
+
+// ================================================================================================
+// fast tiled scorer — 3-D modality (RPE_SHINJI)
+// ================================================================================================
+// Guard band on s = r^2 - thr^2:  band = thr * u * (64 M + 16 thr),  u = 2^-24,
+// M >= |x_w| + |x_c| + |t| for every (correspondence, hypothesis) of the frame.
+__device__ __forceinline__ float guard_band_3d(const FrameStats* st, float thr) {
+  const float M = __uint_as_float(st->m_corr_bits) + __uint_as_float(st->t_max_bits);
+  const float u = 5.9604644775390625e-08f;
+  return thr * u * (64.f * M * 1.0001f + 16.f * thr);
+}
+
+template <bool PACKED>
+struct HypRegs;
+
+template <>
+struct HypRegs<true> {
+  float2 nR[9];
+  float2 nt[3];
+  __device__ __forceinline__ void load(const HypFast* h, bool live) {
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+      const float v = live ? h->nR[i] : CUDART_NAN_F;
+      nR[i] = make_float2(v, v);
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const float v = live ? h->nt[i] : CUDART_NAN_F;
+      nt[i] = make_float2(v, v);
+    }
+  }
+  // s for both correspondences of the pair
+  __device__ __forceinline__ float2 eval(const float4& a, const float4& b, const float4& c, float2 nlo) const {
+    const float2 X0 = make_float2(a.x, a.y), X1 = make_float2(a.z, a.w), X2 = make_float2(b.x, b.y);
+    const float2 P0 = make_float2(b.z, b.w), P1 = make_float2(c.x, c.y), P2 = make_float2(c.z, c.w);
+    float2 e0 = __fadd2_rn(P0, nt[0]);
+    float2 e1 = __fadd2_rn(P1, nt[1]);
+    float2 e2 = __fadd2_rn(P2, nt[2]);
+    e0 = __ffma2_rn(nR[0], X0, e0);
+    e1 = __ffma2_rn(nR[3], X0, e1);
+    e2 = __ffma2_rn(nR[6], X0, e2);
+    e0 = __ffma2_rn(nR[1], X1, e0);
+    e1 = __ffma2_rn(nR[4], X1, e1);
+    e2 = __ffma2_rn(nR[7], X1, e2);
+    e0 = __ffma2_rn(nR[2], X2, e0);
+    e1 = __ffma2_rn(nR[5], X2, e1);
+    e2 = __ffma2_rn(nR[8], X2, e2);
+    float2 s = __ffma2_rn(e0, e0, nlo);
+    s = __ffma2_rn(e1, e1, s);
+    s = __ffma2_rn(e2, e2, s);
+    return s;
+  }
+};
+
+template <>
+struct HypRegs<false> {
+  float nR[9];
+  float nt[3];
+  __device__ __forceinline__ void load(const HypFast* h, bool live) {
+#pragma unroll
+    for (int i = 0; i < 9; ++i) nR[i] = live ? h->nR[i] : CUDART_NAN_F;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) nt[i] = live ? h->nt[i] : CUDART_NAN_F;
+  }
+  __device__ __forceinline__ float one(float x0, float x1, float x2, float p0, float p1, float p2, float nlo) const {
+    float e0 = p0 + nt[0], e1 = p1 + nt[1], e2 = p2 + nt[2];
+    e0 = fmaf(nR[0], x0, e0);
+    e1 = fmaf(nR[3], x0, e1);
+    e2 = fmaf(nR[6], x0, e2);
+    e0 = fmaf(nR[1], x1, e0);
+    e1 = fmaf(nR[4], x1, e1);
+    e2 = fmaf(nR[7], x1, e2);
+    e0 = fmaf(nR[2], x2, e0);
+    e1 = fmaf(nR[5], x2, e1);
+    e2 = fmaf(nR[8], x2, e2);
+    float s = fmaf(e0, e0, nlo);
+    s = fmaf(e1, e1, s);
+    s = fmaf(e2, e2, s);
+    return s;
+  }
+  __device__ __forceinline__ float2 eval(const float4& a, const float4& b, const float4& c, float2 nlo) const {
+    return make_float2(one(a.x, a.z, b.x, b.z, c.x, c.z, nlo.x), one(a.y, a.w, b.y, b.w, c.y, c.w, nlo.y));
+  }
+};
+
+template <bool PACKED>
+__global__ void __launch_bounds__(kScoreThreads, 2)
+score3d_fast_kernel(const float4* __restrict__ pk, int npairs_pad, int pairs_per_cta, const HypFast* __restrict__ fast,
+                    const HypGen* __restrict__ gen, int slot_begin, int slot_end, float thr, int32_t* __restrict__ votes,
+                    FrameStats* __restrict__ st, Worklist wl) {
+  __shared__ __align__(128) float4 tile[2][kTilePairs * 3];
+  __shared__ __align__(8) uint64_t bars[2];
+
+  const int tid = threadIdx.x;
+  const int p_begin = blockIdx.x * pairs_per_cta;
+  const int p_end = min(p_begin + pairs_per_cta, npairs_pad);
+  const int npairs = p_end - p_begin;
+  const int ntiles = (npairs + kTilePairs - 1) / kTilePairs;
+
+  // hypotheses of this thread
+  HypRegs<PACKED> hyp[kHypPerThread];
+  int slot[kHypPerThread];
+  int cnt[kHypPerThread];
+#pragma unroll
+  for (int k = 0; k < kHypPerThread; ++k) {
+    slot[k] = slot_begin + (blockIdx.y * kHypPerThread + k) * kScoreThreads + tid;
+    const bool live = slot[k] < slot_end && gen[slot[k]].valid != 0;
+    hyp[k].load(&fast[live ? slot[k] : slot_begin], live);
+    if (!live) slot[k] = -1;
+    cnt[k] = 0;
+  }
+  const float band = guard_band_3d(st, thr);
+  const float thr2 = __fmul_rn(thr, thr);
+  const float2 nlo = make_float2(-thr2, -thr2);
+
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  if (tid == 0) {
+    for (int t = 0; t < 2 && t < ntiles; ++t) {
+      const int tp = min(kTilePairs, npairs - t * kTilePairs);
+      const uint32_t bytes = (uint32_t)tp * 48u;
+      mbar_expect_tx(&bars[t], bytes);
+      tma_load_1d(&tile[t][0], pk + (size_t)(p_begin + t * kTilePairs) * 3, bytes, &bars[t]);
+    }
+  }
+
+  for (int t = 0; t < ntiles; ++t) {
+    const int buf = t & 1;
+    mbar_wait(&bars[buf], (uint32_t)((t >> 1) & 1));
+    const int tp = min(kTilePairs, npairs - t * kTilePairs);
+    const float4* sp = &tile[buf][0];
+    for (int sub = 0; sub < tp; sub += kSubPairs) {
+      bool flag = false;
+#pragma unroll
+      for (int pp = 0; pp < kSubPairs; ++pp) {
+        const float4 a = sp[(sub + pp) * 3 + 0];
+        const float4 b = sp[(sub + pp) * 3 + 1];
+        const float4 c = sp[(sub + pp) * 3 + 2];
+#pragma unroll
+        for (int k = 0; k < kHypPerThread; ++k) {
+          const float2 s = hyp[k].eval(a, b, c, nlo);
+          cnt[k] += (int)(__float_as_uint(s.x) >> 31) + (int)(__float_as_uint(s.y) >> 31);
+          flag = flag || (fabsf(s.x) <= band) || (fabsf(s.y) <= band);
+        }
+      }
+      if (flag) {
+        // Rare: some evaluation of this 16-correspondence group sits inside the guard band.
+        // Re-walk the group, take the borderline evaluations OUT of the fast count and queue them.
+        for (int pp = 0; pp < kSubPairs; ++pp) {
+          const float4 a = sp[(sub + pp) * 3 + 0];
+          const float4 b = sp[(sub + pp) * 3 + 1];
+          const float4 c = sp[(sub + pp) * 3 + 2];
+#pragma unroll
+          for (int k = 0; k < kHypPerThread; ++k) {
+            const float2 s = hyp[k].eval(a, b, c, nlo);
+            const float sv[2] = {s.x, s.y};
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              if (fabsf(sv[u]) <= band) {
+                cnt[k] -= (int)(__float_as_uint(sv[u]) >> 31);
+                const unsigned int corr = (unsigned int)(2 * (p_begin + t * kTilePairs + sub + pp) + u);
+                const unsigned int idx = atomicAdd(&st->wl_count, 1u);
+                if (idx < wl.capacity)
+                  wl.entries[idx] = make_uint2((unsigned int)slot[k], corr | (1u << 30));
+                else
+                  st->wl_overflow = 1u;
+              }
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();
+    if (tid == 0 && t + 2 < ntiles) {
+      const int tn = t + 2;
+      const int tpn = min(kTilePairs, npairs - tn * kTilePairs);
+      const uint32_t bytes = (uint32_t)tpn * 48u;
+      mbar_expect_tx(&bars[buf], bytes);
+      tma_load_1d(&tile[buf][0], pk + (size_t)(p_begin + tn * kTilePairs) * 3, bytes, &bars[buf]);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < kHypPerThread; ++k)
+    if (slot[k] >= 0 && cnt[k] != 0) atomicAdd(&votes[slot[k]], cnt[k]);
+}
+
+static bool g_use_packed = true;
+void set_use_packed(bool v) { g_use_packed = v; }
+
+void launch_score_fast(int method, const FrameView& f, const HypGen* gen, const HypFast* fast, int slot_begin,
+                       int slot_end, Thresh th, int32_t* votes, FrameStats* st, Worklist wl, int num_sms,
+                       cudaStream_t s) {
+  (void)method;
+  const int nslots = slot_end - slot_begin;
+  if (nslots <= 0 || f.n <= 0) return;
+  const int hyp_per_cta = kScoreThreads * kHypPerThread;
+  const int gy = (nslots + hyp_per_cta - 1) / hyp_per_cta;
+  const int groups = f.npairs_pad / kSubPairs;
+  int gx = (2 * num_sms + gy - 1) / gy;  // aim at 2 resident CTAs per SM in total
+  if (gx < 1) gx = 1;
+  if (gx > groups) gx = groups;
+  int groups_per_cta = (groups + gx - 1) / gx;
+  const int pairs_per_cta = groups_per_cta * kSubPairs;
+  gx = (f.npairs_pad + pairs_per_cta - 1) / pairs_per_cta;
+  dim3 grid(gx, gy);
+  if (g_use_packed)
+    score3d_fast_kernel<true><<<grid, kScoreThreads, 0, s>>>(f.pk, f.npairs_pad, pairs_per_cta, fast, gen, slot_begin,
+                                                            slot_end, th.thr3d, votes, st, wl);
+  else
+    score3d_fast_kernel<false><<<grid, kScoreThreads, 0, s>>>(f.pk, f.npairs_pad, pairs_per_cta, fast, gen, slot_begin,
+                                                             slot_end, th.thr3d, votes, st, wl);
+}
+
+// ================================================================================================
+// exact-order evaluation: worklist fix-up and whole-frame fallback
+// ================================================================================================
+// modality codes carried in bits 30..31 of a worklist entry: 0 = 2-D, 1 = 3-D, 2 = normal
+__device__ __forceinline__ bool exact_eval(int method, int modality, const FrameView& f, const HypGen& h, const float* Rm,
+                                           int c, const Thresh& th) {
+  if (modality == 1) {
+    const F3 xc = load_col(f.xc, c);
+    if (!ex_is_valid(xc)) return false;
+    return ex_test_3d(h.q, h.t, load_col(f.xw, c), xc, th.thr3d);
+  }
+  if (modality == 2) {
+    if (!ex_is_valid(load_col(f.xc, c))) return false;
+    return ex_test_nl(h.q, load_col(f.nw, c), load_col(f.nc, c), th.cos_nl);
+  }
+  return ex_test_2d(h.q, h.t, method == RPE_KNEIP ? Rm : nullptr, load_col(f.xw, c), load_col(f.bv, c), th.cos_thr);
+}
+
+__global__ void fixup_kernel(int method, FrameView f, const HypGen* __restrict__ gen, Thresh th,
+                             int32_t* __restrict__ votes, const FrameStats* __restrict__ st, Worklist wl) {
+  if (st->wl_overflow) return;  // the whole frame is rescored exactly instead
+  const unsigned int count = min(st->wl_count, wl.capacity);
+  for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
+    const uint2 e = wl.entries[i];
+    const int slot = (int)e.x;
+    const int modality = (int)(e.y >> 30);
+    const int c = (int)(e.y & 0x3fffffffu);
+    const HypGen h = gen[slot];
+    float Rm[9];
+    if (method == RPE_KNEIP) ex_quat_to_matrix(h.q, Rm);
+    if (exact_eval(method, modality, f, h, Rm, c, th)) atomicAdd(&votes[slot], 1);
+  }
+}
+
+void launch_fixup(int method, const FrameView& f, const HypGen* gen, Thresh th, int32_t* votes, FrameStats* st,
+                  Worklist wl, int num_sms, cudaStream_t s) {
+  fixup_kernel<<<num_sms, 256, 0, s>>>(method, f, gen, th, votes, st, wl);
+}
+
+// Whole-frame exact scoring. Thread <-> slot, CTA column <-> correspondence slice; every lane reads the
+// same correspondence (uniform, L1-broadcast loads).
+__global__ void __launch_bounds__(128)
+score_exact_kernel(int method, FrameView f, const HypGen* __restrict__ gen, int slot_begin, int slot_end, Thresh th,
+                   int32_t* __restrict__ votes, const FrameStats* __restrict__ st, int only_if_overflow, int corr_per_cta) {
+  if (only_if_overflow && !st->wl_overflow) return;
+  const int slot = slot_begin + blockIdx.y * blockDim.x + threadIdx.x;
+  const bool live = slot < slot_end && gen[slot].valid != 0;
+  HypGen h;
+  if (live) h = gen[slot];
+  else {
+    h.q[0] = h.q[1] = h.q[2] = h.q[3] = CUDART_NAN_F;
+    h.t[0] = h.t[1] = h.t[2] = CUDART_NAN_F;
+  }
+  float Rm[9];
+  ex_quat_to_matrix(h.q, Rm);
+  const bool u2 = method_uses_2d(method), u3 = method_uses_3d(method), un = method_uses_nl(method);
+  const int c0 = blockIdx.x * corr_per_cta;
+  const int c1 = min(c0 + corr_per_cta, f.n);
+  int cnt = 0;
+  for (int c = c0; c < c1; ++c) {
+    if (un) cnt += exact_eval(method, 2, f, h, Rm, c, th) ? 1 : 0;
+    if (u3) cnt += exact_eval(method, 1, f, h, Rm, c, th) ? 1 : 0;
+    if (u2) cnt += exact_eval(method, 0, f, h, Rm, c, th) ? 1 : 0;
+  }
+  if (live && cnt) atomicAdd(&votes[slot], cnt);
+}
+
+__global__ void zero_votes_if_overflow_kernel(const HypGen* __restrict__ gen, int slot_begin, int slot_end,
+                                              int32_t* __restrict__ votes, const FrameStats* __restrict__ st,
+                                              int only_if_overflow) {
+  if (only_if_overflow && !st->wl_overflow) return;
+  for (int sidx = slot_begin + blockIdx.x * blockDim.x + threadIdx.x; sidx < slot_end; sidx += gridDim.x * blockDim.x)
+    votes[sidx] = gen[sidx].valid ? 0 : -1;
+}
+
+void launch_score_exact(int method, const FrameView& f, const HypGen* gen, int slot_begin, int slot_end, Thresh th,
+                        int32_t* votes, FrameStats* st, bool only_if_overflow, int num_sms, cudaStream_t s) {
+  const int nslots = slot_end - slot_begin;
+  if (nslots <= 0 || f.n <= 0) return;
+  zero_votes_if_overflow_kernel<<<4, 256, 0, s>>>(gen, slot_begin, slot_end, votes, st, only_if_overflow ? 1 : 0);
+  const int threads = 128;
+  const int gy = (nslots + threads - 1) / threads;
+  int gx = (4 * num_sms + gy - 1) / gy;
+  if (gx < 1) gx = 1;
+  if (gx > f.n) gx = f.n;
+  const int corr_per_cta = (f.n + gx - 1) / gx;
+  gx = (f.n + corr_per_cta - 1) / corr_per_cta;
+  score_exact_kernel<<<dim3(gx, gy), threads, 0, s>>>(method, f, gen, slot_begin, slot_end, th, votes, st,
+                                                      only_if_overflow ? 1 : 0, corr_per_cta);
+}
+
+// ================================================================================================
+// FP32 FFMA peak microbenchmark (roofline denominator measured on the same device and run)
+// ================================================================================================
+template <bool PACKED>
+__global__ void __launch_bounds__(256) ffma_bench_kernel(float* sink, int iters) {
+  float2 acc[8];
+  const float seed = 1.0f + 1e-7f * (float)(threadIdx.x + blockIdx.x);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = make_float2(seed + i, seed - i);
+  const float2 m = make_float2(0.999999f, 1.000001f);
+  const float2 a = make_float2(1e-6f, -1e-6f);
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (PACKED) {
+          acc[i] = __ffma2_rn(acc[i], m, a);
+        } else {
+          acc[i].x = fmaf(acc[i].x, m.x, a.x);
+          acc[i].y = fmaf(acc[i].y, m.y, a.y);
+        }
+      }
+    }
+  }
+  float r = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) r += acc[i].x + acc[i].y;
+  if (r == 123.456f) sink[0] = r;
+}
+void launch_ffma_bench(float* sink, int iters, bool packed, int blocks, cudaStream_t s) {
+  if (packed)
+    ffma_bench_kernel<true><<<blocks, 256, 0, s>>>(sink, iters);
+  else
+    ffma_bench_kernel<false><<<blocks, 256, 0, s>>>(sink, iters);
+}
+
+int grid_blocks_for(int n, int threads) { return (n + threads - 1) / threads; }
+
+}  // namespace rpe

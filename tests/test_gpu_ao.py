@@ -1,0 +1,172 @@
+"""GPU parity: AO (3-D/3-D) RANSAC through the C-ABI vs the CPU oracle.
+
+Reference path: shinji_ransac2 + shinji_ls1 (AbsoluteOrientation.hpp:158-213, 298-320) on
+simulate_3d_3d_correspondences inputs (Simulator.hpp:268-314). Bars: hypotheses,
+votes[H], winner, final Iter, masks and counts BIT-IDENTICAL (oracle in DET math mode, see
+oracle/README.md); refit rotation within 1e-6 rad and translation within 1e-6 x scene scale against the
+oracle evaluated in binary64.
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+SHINJI = 0
+
+
+def _frame(rpe, seed, n, outlier=0.5, noise=0.1):
+    q, t = rpe.sim_pose(seed)
+    Q, P, _ = rpe.sim_3d_3d(seed + 1, q, t, n, noise=noise, outlier_ratio=outlier)
+    return q, t, Q, P
+
+
+def _angle(qa, qb):
+    qa = np.asarray(qa, np.float64) / np.linalg.norm(qa)
+    qb = np.asarray(qb, np.float64) / np.linalg.norm(qb)
+    d = abs(float(np.dot(qa, qb)))
+    return 2.0 * np.arccos(min(1.0, d))
+
+
+@pytest.mark.parametrize("n,H,seed", [(1000, 1024, 3), (1001, 300, 5), (37, 64, 7), (10000, 2048, 9)])
+def test_generation_bit_exact(rpe, orc, gpu_ctx, n, H, seed):
+    orc.set_math_mode(orc.DET)
+    q, t, Q, P = _frame(rpe, seed, n)
+    S = rpe.sample_table(seed, n, 3, H)
+    ref = orc.ransac(SHINJI, S, thr3d=0.25, confidence=0.9999, full=True, xc=P, xw=Q)
+    gpu_ctx.upload(xc=P, xw=Q)
+    ns = gpu_ctx.generate(SHINJI, S)
+    hyps, valid = gpu_ctx.get_hypotheses(ns)
+    ref_valid = (ref["votes"] >= 0).astype(np.int32)
+    assert np.array_equal(valid, ref_valid)
+    sel = valid == 1
+    assert np.array_equal(hyps[sel].view(np.uint32), ref["hyps"][sel].view(np.uint32)), "hypotheses differ in some bit"
+
+
+@pytest.mark.parametrize("packed", [1, 0])
+@pytest.mark.parametrize("n,H,seed,outlier,noise,thr", [
+    (1000, 1024, 3, 0.5, 0.1, 0.25),
+    (1001, 300, 5, 0.2, 0.05, 0.1),
+    (37, 64, 7, 0.0, 0.01, 0.05),
+    (20000, 1024, 9, 0.5, 0.1, 0.25),
+    (4097, 513, 11, 0.7, 0.2, 0.5),
+])
+def test_ransac_votes_winner_iter_mask_identical(rpe, orc, gpu_ctx, packed, n, H, seed, outlier, noise, thr):
+    orc.set_math_mode(orc.DET)
+    rpe.lib.rpe_debug_set_packed(packed)
+    q, t, Q, P = _frame(rpe, seed, n, outlier, noise)
+    S = rpe.sample_table(seed, n, 3, H)
+    ref = orc.ransac(SHINJI, S, thr3d=thr, confidence=0.9999, full=True, xc=P, xw=Q)
+    gpu_ctx.upload(xc=P, xw=Q)
+    got = gpu_ctx.ransac(SHINJI, S, thr3d=thr, confidence=0.9999)
+    votes = gpu_ctx.get_votes(H)
+    rpe.lib.rpe_debug_set_packed(1)
+    assert got["flags"] == 0
+    assert np.array_equal(votes, ref["votes"]), f"votes differ at {np.nonzero(votes != ref['votes'])[0][:10]}"
+    assert got["winner"] == ref["winner"]
+    assert got["max_votes"] == ref["max_votes"]
+    assert got["iter_final"] == ref["iter_final"]
+    assert np.array_equal(got["q"].view(np.uint32), ref["q"].view(np.uint32))
+    assert np.array_equal(got["t"].view(np.uint32), ref["t"].view(np.uint32))
+    assert np.array_equal(got["mask"], ref["mask"])
+    assert got["n_inliers"][1] == int(ref["mask"][1].sum()) == ref["max_votes"]
+
+
+def test_early_stop_loop_equals_full_replay(rpe, orc):
+    """The oracle's literal early-stopping loop and its score-everything-then-replay form agree."""
+    orc.set_math_mode(orc.DET)
+    for seed in range(20, 30):
+        q, t = rpe.sim_pose(seed)
+        Q, P, _ = rpe.sim_3d_3d(seed + 1, q, t, 500, noise=0.1, outlier_ratio=0.5)
+        S = rpe.sample_table(seed, 500, 3, 2000)
+        a = orc.ransac(SHINJI, S, thr3d=0.25, confidence=0.9999, full=True, xc=P, xw=Q)
+        b = orc.ransac(SHINJI, S, thr3d=0.25, confidence=0.9999, full=False, xc=P, xw=Q)
+        for k in ("winner", "max_votes", "iter_final"):
+            assert a[k] == b[k]
+        assert np.array_equal(a["mask"], b["mask"])
+
+
+def test_kabsch_refit_within_tolerance(rpe, orc, gpu_ctx):
+    orc.set_math_mode(orc.DET)
+    n, H = 20000, 512
+    q, t, Q, P = _frame(rpe, 31, n)
+    S = rpe.sample_table(31, n, 3, H)
+    gpu_ctx.upload(xc=P, xw=Q)
+    got = gpu_ctx.ransac(SHINJI, S, thr3d=0.25, confidence=0.9999)
+    ref_q, ref_t, ok = orc.shinji_ls(P, Q, got["mask"][1], dt=np.float64)
+    assert ok
+    fit = gpu_ctx.refit("kabsch_inliers")
+    assert fit["refit_ok"] == 1
+    scale = float(np.abs(P).max())
+    assert _angle(fit["q"], ref_q) < 1e-6  # rad
+    assert np.abs(fit["t"].astype(np.float64) - ref_t).max() < 1e-6 * scale
+    # shinji_ls2 (all points)
+    ref_q2, ref_t2, _ = orc.shinji_ls(P, Q, None, dt=np.float64)
+    fit2 = gpu_ctx.refit("kabsch_all")
+    assert _angle(fit2["q"], ref_q2) < 1e-6
+    assert np.abs(fit2["t"].astype(np.float64) - ref_t2).max() < 1e-6 * scale
+    # and the refit is close to ground truth (Simulator's known answer)
+    assert _angle(fit["q"], q) < 5e-3
+
+
+def test_gn_refinement_matches_twin_and_closed_form(rpe, orc, gpu_ctx):
+    orc.set_math_mode(orc.DET)
+    n, H = 5000, 256
+    q, t, Q, P = _frame(rpe, 41, n)
+    S = rpe.sample_table(41, n, 3, H)
+    gpu_ctx.upload(xc=P, xw=Q)
+    got = gpu_ctx.ransac(SHINJI, S, thr3d=0.25, confidence=0.9999)
+    twin_q, twin_t, info = orc.refine_gn(got["q"], got["t"], got["mask"], max_iters=8, xc=P, xw=Q)
+    fit = gpu_ctx.refit("gn", max_iters=8)
+    assert fit["refit_ok"] == 1 and fit["refit_evals"] >= 2
+    scale = float(np.abs(P).max())
+    assert _angle(fit["q"], twin_q) < 1e-6
+    assert np.abs(fit["t"].astype(np.float64) - twin_t.astype(np.float64)).max() < 1e-6 * scale * 4
+    # same least-squares objective as Kabsch on pure 3-D data: converges to the closed form
+    ls_q, ls_t, _ = orc.shinji_ls(P, Q, got["mask"][1], dt=np.float64)
+    assert _angle(fit["q"], ls_q) < 2e-6
+    assert np.abs(fit["t"].astype(np.float64) - ls_t).max() < 1e-5
+
+
+def test_nan_points_and_invalid_samples(rpe, orc, gpu_ctx):
+    """isValid semantics (AOOnlyPoseAdapter.hpp:161-166): all-NaN camera points never vote; a sample that
+    hits one consumes the iteration without a hypothesis (AbsoluteOrientation.hpp:185)."""
+    orc.set_math_mode(orc.DET)
+    n, H = 3000, 512
+    q, t, Q, P = _frame(rpe, 51, n)
+    rng = np.random.default_rng(0)
+    bad = rng.choice(n, n // 5, replace=False)
+    P = P.copy()
+    P[bad] = np.nan
+    P[bad[:50], 1] = 1.0  # partially-NaN points are "valid" for isValid but can never be inliers
+    S = rpe.sample_table(51, n, 3, H)
+    ref = orc.ransac(SHINJI, S, thr3d=0.25, confidence=0.9999, full=True, xc=P, xw=Q)
+    gpu_ctx.upload(xc=P, xw=Q)
+    got = gpu_ctx.ransac(SHINJI, S, thr3d=0.25, confidence=0.9999)
+    votes = gpu_ctx.get_votes(H)
+    assert (ref["votes"] == -1).sum() > 0
+    assert np.array_equal(votes, ref["votes"])
+    assert got["winner"] == ref["winner"] and got["iter_final"] == ref["iter_final"]
+    assert np.array_equal(got["mask"], ref["mask"])
+
+
+def test_borderline_band_forces_exact_path(rpe, orc, gpu_ctx):
+    """Put many residuals exactly around the threshold: the fast path must hand them to the exact fix-up."""
+    orc.set_math_mode(orc.DET)
+    n = 4096
+    q, t = rpe.sim_pose(61)
+    Q, P, _ = rpe.sim_3d_3d(62, q, t, n, noise=0.0, outlier_ratio=0.0)
+    # displace camera points by exactly thr along random directions (+- a few ulps)
+    rng = np.random.default_rng(1)
+    d = rng.normal(size=(n, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    thr = 0.25
+    P2 = (P.astype(np.float64) + d * thr * (1.0 + rng.integers(-3, 4, size=(n, 1)) * 1e-7)).astype(np.float32)
+    P2[:8] = P[:8]  # a few clean points for the sampler below
+    S = np.tile(np.array([[0, 1, 2, -1], [3, 4, 5, -1], [1, 5, 7, -1]], np.int32), (11, 1))
+    ref = orc.ransac(SHINJI, S, thr3d=thr, confidence=0.99, full=True, xc=P2, xw=Q)
+    gpu_ctx.upload(xc=P2, xw=Q)
+    got = gpu_ctx.ransac(SHINJI, S, thr3d=thr, confidence=0.99)
+    votes = gpu_ctx.get_votes(S.shape[0])
+    assert got["n_borderline"] > 1000
+    assert np.array_equal(votes, ref["votes"])
+    assert np.array_equal(got["mask"], ref["mask"])
