@@ -121,7 +121,7 @@ int rpe_upload_device(rpe_ctx* ctx, const float* bv, const float* xc, const floa
 int rpe_num_correspondences(const rpe_ctx* ctx);
 
 /* ---- robust estimation ------------------------------------------------------------------
- * samples: host int32 [H x 4] rows of correspondence indices (3 used by RPE_SHINJI), exactly the
+ * samples: int32 [H x 4] (host, page-locked host, or device memory) rows of correspondence indices (3 used by RPE_SHINJI), exactly the
  *          draws RandomElements::run / ProsacSampler::sample would produce (see rpe_sample_table).
  * H      : the caller's `Iter` on entry. All H iterations are generated and scored on the GPU;
  *          the reference's sequential rule (strict `votes > max`, Iter = RANSACUpdateNumIters(..))
@@ -203,7 +203,8 @@ int rpe_ao_ransac(const float* x_w, const float* x_c, int n, float* R_cw, float*
  * events over `ms_target` milliseconds of dependent-chain-free FFMA work. */
 int rpe_measure_ffma_tflops(rpe_ctx* ctx, int ms_target, double* tflops_scalar, double* tflops_packed);
 /* Device time in ms of the last call's stages, measured with CUDA events on the context's stream:
- * [0] upload+pack [1] generate [2] score (fast + exact fix-up) [3] replay [4] mask+refit [5] GN [6] total */
+ * [0] upload+pack [1] generate [2] score (fast + exact fix-up) [3] replay [4] mask+refit [5] GN [6] total
+ * [7] the tiled fast scoring kernel alone (the roofline kernel) */
 int rpe_last_stage_ms(rpe_ctx* ctx, float ms[8]);
 int rpe_enable_stage_timing(rpe_ctx* ctx, int enable);
 

@@ -23,10 +23,11 @@ from .capi import (  # noqa: F401
     method_slots,
     method_mask_cols,
     method_sample_size,
+    pinned_empty,
 )
 
 __all__ = [
     "Context", "RpeError", "lib", "lib_path", "METHODS", "REFITS", "sample_table", "prosac_table",
     "update_num_iters", "sim_pose", "sim_3d_3d", "sim_2d_3d", "sim_2d_3d_nl", "method_slots",
-    "method_mask_cols", "method_sample_size",
+    "method_mask_cols", "method_sample_size", "pinned_empty",
 ]

@@ -226,6 +226,21 @@ def sim_2d_3d_nl(seed, q, t, n, n2d=1.0, or2d=0.3, n3d=0.05, or3d=0.3, nnl=np.de
     return {"xw": Q, "nw": M, "xc": P, "nc": N, "bv": U, "weights": W}
 
 
+def pinned_empty(shape, dtype=np.float32) -> np.ndarray:
+    """numpy array backed by page-locked host memory from rpe_host_alloc (freed with the array's base)."""
+    dtype = np.dtype(dtype)
+    nbytes = int(np.prod(shape)) * dtype.itemsize
+    p = C.c_void_p()
+    _check(lib.rpe_host_alloc(max(nbytes, 1), C.byref(p)))
+    buf = (C.c_byte * max(nbytes, 1)).from_address(p.value)
+    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+    _PINNED.append((p, buf))
+    return arr
+
+
+_PINNED = []
+
+
 # ---- device context ---------------------------------------------------------------------------
 class Context:
     """One rpe_ctx (one GPU, one stream). Arrays are (n, 3) float32 == the reference's 3 x n column-major."""
@@ -286,6 +301,38 @@ class Context:
         d = res.to_dict()
         d["mask"] = mask  # (cols, n): row k == column k of the reference's n x cols matrix
         return d
+
+    def ransac_async(self, method, samples, H=None, thr3d=0.0, cos_thr2d=0.0, cos_thrN=0.0, confidence=0.99, mask=None):
+        """Enqueue only. `samples` may be a numpy int32 array (kept alive until sync) or a device pointer (int)
+        with H given. Returns the ctypes result struct, valid after :meth:`sync`."""
+        m = METHODS[method] if isinstance(method, str) else method
+        if isinstance(samples, int):
+            sp = C.c_void_p(samples)
+        else:
+            samples = np.ascontiguousarray(samples, dtype=np.int32)
+            H = samples.shape[0]
+            self._keep.append(samples)
+            sp = _ptr(samples)
+        res = _Result()
+        _check(lib.rpe_ransac_async(self._h, m, sp, H, thr3d, cos_thr2d, cos_thrN, confidence, C.byref(res),
+                                    _ptr(mask)), self._h)
+        return res
+
+    def refit_async(self, kind, weights=None, max_iters=0):
+        k = REFITS[kind] if isinstance(kind, str) else kind
+        res = _Result()
+        w = _f32(weights)
+        if w is not None:
+            self._keep.append(w)
+        _check(lib.rpe_refit_async(self._h, k, _ptr(w), max_iters, C.byref(res)), self._h)
+        return res
+
+    def upload_async(self, bv=None, xc=None, nc=None, xw=None, nw=None):
+        """Like upload() but does not retain references (caller keeps page-locked arrays alive)."""
+        arrs = [bv, xc, nc, xw, nw]
+        n = next(a.shape[0] for a in arrs if a is not None)
+        self.n = n
+        _check(lib.rpe_upload(self._h, *[_ptr(a) for a in arrs], n), self._h)
 
     def refit(self, kind, weights=None, max_iters=0):
         k = REFITS[kind] if isinstance(kind, str) else kind
@@ -359,7 +406,7 @@ class Context:
     def last_stage_ms(self):
         ms = np.zeros(8, np.float32)
         _check(lib.rpe_last_stage_ms(self._h, _ptr(ms)), self._h)
-        names = ["upload_pack", "generate", "score", "replay", "mask_refit", "gn", "total"]
+        names = ["upload_pack", "generate", "score", "replay", "mask_refit", "gn", "total", "score_fast"]
         return {k: float(v) for k, v in zip(names, ms)}
 
     def measure_ffma_tflops(self, ms_target=50):

@@ -22,8 +22,8 @@ using namespace rpe;
 namespace {
 
 enum { A_BV = 0, A_XC = 1, A_NC = 2, A_XW = 3, A_NW = 4 };
-constexpr int kNumStaging = 4;
-enum { ST_UPLOAD = 0, ST_GEN = 1, ST_SCORE = 2, ST_REPLAY = 3, ST_MASK = 4, ST_GN = 5, ST_TOTAL = 6, ST_COUNT = 8 };
+constexpr int kNumStaging = 96;  // results that may be in flight before an implicit drain
+enum { ST_UPLOAD = 0, ST_GEN = 1, ST_SCORE = 2, ST_REPLAY = 3, ST_MASK = 4, ST_GN = 5, ST_TOTAL = 6, ST_FAST = 7, ST_COUNT = 8 };
 
 }  // namespace
 
@@ -54,8 +54,6 @@ struct rpe_ctx {
   HypFast* d_fast = nullptr;
   int32_t* d_votes = nullptr;
   int32_t* d_samples = nullptr;
-  int32_t* h_samples = nullptr;  // pinned staging
-  size_t h_samples_cap = 0;
 
   FrameStats* d_stats = nullptr;
   ReplayOut* d_pose = nullptr;    // current pose = the adapter's (R_cw, t_w, max_votes) state
@@ -85,6 +83,8 @@ struct rpe_ctx {
   // stage timing
   bool timing = false;
   cudaEvent_t ev[ST_COUNT + 1] = {};
+  cudaEvent_t ev_fast[2] = {};
+  bool ev_fast_recorded = false;
   bool ev_ok = false;
   bool ev_recorded[ST_COUNT + 1] = {};
   float stage_ms[ST_COUNT] = {};
@@ -264,6 +264,8 @@ int finish_pending(rpe_ctx* ctx) {
         if (ctx->ev_recorded[k]) last = k;
       if (last > 0) cudaEventElapsedTime(&ctx->stage_ms[ST_TOTAL], ctx->ev[0], ctx->ev[last]);
     }
+    if (ctx->ev_fast_recorded) cudaEventElapsedTime(&ctx->stage_ms[ST_FAST], ctx->ev_fast[0], ctx->ev_fast[1]);
+    ctx->ev_fast_recorded = false;
     for (int k = 0; k <= ST_COUNT; ++k) ctx->ev_recorded[k] = false;
   }
   return RPE_OK;
@@ -283,8 +285,14 @@ int claim_slot(rpe_ctx* ctx, int* slot) {
 int score_range(rpe_ctx* ctx, int method, int slot_begin, int slot_end, Thresh th) {
   FrameView f = make_view(ctx);
   if (method == RPE_SHINJI) {
+    const bool tm = ctx->timing && ctx->ev_ok;
+    if (tm) cudaEventRecord(ctx->ev_fast[0], ctx->stream);
     launch_score_fast(method, f, ctx->d_gen, ctx->d_fast, slot_begin, slot_end, th, ctx->d_votes, ctx->d_stats, ctx->wl,
                       ctx->num_sms, ctx->stream);
+    if (tm) {
+      cudaEventRecord(ctx->ev_fast[1], ctx->stream);
+      ctx->ev_fast_recorded = true;
+    }
     launch_fixup(method, f, ctx->d_gen, th, ctx->d_votes, ctx->d_stats, ctx->wl, ctx->num_sms, ctx->stream);
     launch_score_exact(method, f, ctx->d_gen, slot_begin, slot_end, th, ctx->d_votes, ctx->d_stats, true, ctx->num_sms,
                        ctx->stream);
@@ -334,15 +342,19 @@ int do_ransac(rpe_ctx* ctx, int method, const int32_t* samples, int H, float thr
   if (rc) return rc;
   const Thresh th = {thr3d, cos_thr2d, cos_thrN};
   if (!ctx->ev_recorded[ST_UPLOAD]) stamp(ctx, ST_UPLOAD);
-  // sample table: stage through pinned memory so the copy is truly asynchronous
-  const size_t sbytes = (size_t)H * 4 * sizeof(int32_t);
-  if (sbytes > ctx->h_samples_cap) {
-    if (ctx->h_samples) cudaFreeHost(ctx->h_samples);
-    CK(cudaMallocHost(&ctx->h_samples, sbytes + sbytes / 4));
-    ctx->h_samples_cap = sbytes + sbytes / 4;
+  // sample table: device pointers are used in place; host memory is copied on the stream (pageable
+  // memory is staged by the driver before the call returns, page-locked memory must stay alive until rpe_sync)
+  const int32_t* samples_dev = ctx->d_samples;
+  {
+    cudaPointerAttributes attr;
+    const cudaError_t pe = cudaPointerGetAttributes(&attr, samples);
+    if (pe != cudaSuccess) (void)cudaGetLastError();
+    if (pe == cudaSuccess && (attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged)) {
+      samples_dev = samples;
+    } else {
+      CK(cudaMemcpyAsync(ctx->d_samples, samples, (size_t)H * 4 * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    }
   }
-  memcpy(ctx->h_samples, samples, sbytes);
-  CK(cudaMemcpyAsync(ctx->d_samples, ctx->h_samples, sbytes, cudaMemcpyHostToDevice, ctx->stream));
   launch_reset_stats(ctx->d_stats, ctx->stream);
   ctx->launches++;
   if (method == RPE_SHINJI) {
@@ -351,7 +363,7 @@ int do_ransac(rpe_ctx* ctx, int method, const int32_t* samples, int H, float thr
   }
   stamp(ctx, ST_GEN);
   FrameView f = make_view(ctx);
-  launch_hypgen(method, f, ctx->d_samples, H, ctx->d_gen, ctx->d_fast, ctx->d_votes, ctx->d_stats, ctx->stream);
+  launch_hypgen(method, f, samples_dev, H, ctx->d_gen, ctx->d_fast, ctx->d_votes, ctx->d_stats, ctx->stream);
   ctx->launches++;
   ctx->n_slots = H * S;
   ctx->cur_method = method;
@@ -440,6 +452,7 @@ static int create_common(int device, void* stream, bool own, rpe_ctx** out) {
     ok = ok && cudaMemsetAsync(ctx->d_kabsch, 0, sizeof(ReplayOut), ctx->stream) == cudaSuccess;
   }
   for (int k = 0; k <= ST_COUNT && ok; ++k) ok = ok && cudaEventCreate(&ctx->ev[k]) == cudaSuccess;
+  for (int k = 0; k < 2 && ok; ++k) ok = ok && cudaEventCreate(&ctx->ev_fast[k]) == cudaSuccess;
   ctx->ev_ok = ok;
   if (!ok) {
     rpe_destroy(ctx);
@@ -471,7 +484,6 @@ int rpe_destroy(rpe_ctx* ctx) {
   cudaFree(ctx->d_fast);
   cudaFree(ctx->d_votes);
   cudaFree(ctx->d_samples);
-  if (ctx->h_samples) cudaFreeHost(ctx->h_samples);
   cudaFree(ctx->d_stats);
   cudaFree(ctx->d_pose);
   cudaFree(ctx->d_kabsch);
@@ -487,6 +499,8 @@ int rpe_destroy(rpe_ctx* ctx) {
   if (ctx->h_gn_evals) cudaFreeHost(ctx->h_gn_evals);
   for (int k = 0; k <= ST_COUNT; ++k)
     if (ctx->ev[k]) cudaEventDestroy(ctx->ev[k]);
+  for (int k = 0; k < 2; ++k)
+    if (ctx->ev_fast[k]) cudaEventDestroy(ctx->ev_fast[k]);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
   (void)cudaGetLastError();
   delete ctx;
@@ -665,8 +679,7 @@ int rpe_generate(rpe_ctx* ctx, int method, const int32_t* samples, int H) {
   ctx->launches += 2;
   ctx->n_slots = H * S;
   ctx->cur_method = method;
-  CK(cudaStreamSynchronize(ctx->stream));
-  return RPE_OK;
+  return RPE_OK;  // asynchronous; rpe_get_hypotheses / rpe_get_votes / rpe_finish synchronise
 }
 
 int rpe_get_hypotheses(rpe_ctx* ctx, float* hyps, int32_t* valid, int n_slots) {

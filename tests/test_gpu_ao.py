@@ -21,10 +21,14 @@ def _frame(rpe, seed, n, outlier=0.5, noise=0.1):
 
 
 def _angle(qa, qb):
-    qa = np.asarray(qa, np.float64) / np.linalg.norm(qa)
-    qb = np.asarray(qb, np.float64) / np.linalg.norm(qb)
-    d = abs(float(np.dot(qa, qb)))
-    return 2.0 * np.arccos(min(1.0, d))
+    """Geodesic angle between two rotations given as (x,y,z,w) quaternions, accurate near zero."""
+    a = np.asarray(qa, np.float64) / np.linalg.norm(np.asarray(qa, np.float64))
+    b = np.asarray(qb, np.float64) / np.linalg.norm(np.asarray(qb, np.float64))
+    # relative rotation a * conj(b)
+    av, aw, bv, bw = a[:3], a[3], -b[:3], b[3]
+    w = aw * bw - np.dot(av, bv)
+    v = aw * bv + bw * av + np.cross(av, bv)
+    return 2.0 * np.arctan2(np.linalg.norm(v), abs(w))
 
 
 @pytest.mark.parametrize("n,H,seed", [(1000, 1024, 3), (1001, 300, 5), (37, 64, 7), (10000, 2048, 9)])
