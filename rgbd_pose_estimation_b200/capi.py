@@ -314,6 +314,7 @@ class Context:
             self._keep.append(samples)
             sp = _ptr(samples)
         res = _Result()
+        self._keep.append(res)  # the library writes into it at sync time
         _check(lib.rpe_ransac_async(self._h, m, sp, H, thr3d, cos_thr2d, cos_thrN, confidence, C.byref(res),
                                     _ptr(mask)), self._h)
         return res
@@ -324,6 +325,7 @@ class Context:
         w = _f32(weights)
         if w is not None:
             self._keep.append(w)
+        self._keep.append(res)
         _check(lib.rpe_refit_async(self._h, k, _ptr(w), max_iters, C.byref(res)), self._h)
         return res
 
@@ -393,6 +395,7 @@ class Context:
 
     def sync(self):
         _check(lib.rpe_sync(self._h), self._h)
+        self._keep = []
 
     def launch_count(self):
         return int(lib.rpe_launch_count(self._h))

@@ -85,6 +85,7 @@ struct rpe_ctx {
   cudaEvent_t ev[ST_COUNT + 1] = {};
   cudaEvent_t ev_fast[2] = {};
   bool ev_fast_recorded = false;
+  bool upload_stamped = false;
   bool ev_ok = false;
   bool ev_recorded[ST_COUNT + 1] = {};
   float stage_ms[ST_COUNT] = {};
@@ -341,7 +342,8 @@ int do_ransac(rpe_ctx* ctx, int method, const int32_t* samples, int H, float thr
   rc = ensure_hyp_capacity(ctx, H, H * S);
   if (rc) return rc;
   const Thresh th = {thr3d, cos_thr2d, cos_thrN};
-  if (!ctx->ev_recorded[ST_UPLOAD]) stamp(ctx, ST_UPLOAD);
+  if (!ctx->upload_stamped) stamp(ctx, ST_UPLOAD);
+  ctx->upload_stamped = false;
   // sample table: device pointers are used in place; host memory is copied on the stream (pageable
   // memory is staged by the driver before the call returns, page-locked memory must stay alive until rpe_sync)
   const int32_t* samples_dev = ctx->d_samples;
@@ -558,7 +560,10 @@ static int upload_common(rpe_ctx* ctx, const float* const src[5], int n, bool fr
 
 int rpe_upload(rpe_ctx* ctx, const float* bv, const float* xc, const float* nc, const float* xw, const float* nw, int n) {
   const float* src[5] = {bv, xc, nc, xw, nw};
-  if (ctx) stamp(ctx, ST_UPLOAD);
+  if (ctx) {
+    stamp(ctx, ST_UPLOAD);
+    ctx->upload_stamped = ctx->timing;
+  }
   return upload_common(ctx, src, n, false);
 }
 int rpe_upload_device(rpe_ctx* ctx, const float* bv, const float* xc, const float* nc, const float* xw, const float* nw,

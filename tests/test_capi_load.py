@@ -1,0 +1,98 @@
+"""CPU-only checks of the drop-in boundary: the C-ABI library loads, exports every symbol that
+include/rpe_c_api.h declares, fails loudly without a GPU, and its host-side helpers work."""
+import ctypes
+import os
+import re
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_in_header():
+    src = open(os.path.join(ROOT, "include", "rpe_c_api.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(rpe_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_are_exported(rpe):
+    names = _declared_in_header()
+    assert len(names) >= 40
+    lib = ctypes.CDLL(rpe.lib_path)
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, f"declared in include/rpe_c_api.h but not exported: {missing}"
+    from rgbd_pose_estimation_b200 import capi
+    assert sorted(capi.DECLARED_SYMBOLS) == names
+
+
+def test_no_torch_or_cxx_types_in_signatures():
+    src = open(os.path.join(ROOT, "include", "rpe_c_api.h")).read()
+    assert 'extern "C"' in src
+    for banned in ("torch", "at::", "std::", "Eigen", "template"):
+        body = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+        assert banned not in body
+
+
+def test_library_is_cuda_and_sm100a(rpe):
+    """The shipped .so carries sm_100a SASS (cuobjdump) — it is the thing the GPU tests load."""
+    import shutil
+    import subprocess
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        return
+    out = subprocess.run([cuobjdump, "-lelf", rpe.lib_path], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+
+
+def test_fails_loudly_without_gpu_or_reports_devices(rpe):
+    n = ctypes.c_int(-1)
+    rc = rpe.lib.rpe_device_count(ctypes.byref(n))
+    if rc != 0 or n.value == 0:
+        try:
+            rpe.Context(0)
+        except rpe.RpeError as e:
+            assert "no CPU fallback" in str(e) or "CUDA" in str(e)
+        else:
+            raise AssertionError("Context() must not succeed without a CUDA device")
+    assert rpe.lib.rpe_status_string(-4).decode().startswith("no usable CUDA device")
+
+
+def test_product_does_not_import_oracle():
+    """The product path never loads, links, includes or imports anything under oracle/ (comments may cite it)."""
+    bad = re.compile(r'liboracle|tests\.orc|from\s+tests|import\s+oracle|from\s+oracle|#\s*include\s*"[^"]*oracle/|dlopen')
+    roots = [os.path.join(ROOT, "rgbd_pose_estimation_b200"), os.path.join(ROOT, "include")]
+    for root in roots:
+        for dirpath, _, files in os.walk(root):
+            for f in files:
+                if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".hpp", "Makefile")):
+                    txt = open(os.path.join(dirpath, f), errors="ignore").read()
+                    assert not bad.search(txt), os.path.join(dirpath, f)
+
+
+def test_simulator_statistics(rpe):
+    q, t = rpe.sim_pose(3)
+    assert abs(np.linalg.norm(q) - 1) < 1e-6 and np.abs(t).max() <= 5.0
+    n = 20000
+    Q, P, W = rpe.sim_3d_3d(4, q, t, n, noise=0.1, outlier_ratio=0.5)
+    f = 585.0
+    assert (np.abs(P[:, 0] / P[:, 2]) < 320 / f).all() and (np.abs(P[:, 1] / P[:, 2]) < 240 / f).all()
+    assert P[:, 2].min() >= 0.4 and P[:, 2].max() <= 8.0
+    x, y, z, w = [float(v) for v in q]
+    R = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                  [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                  [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+    e = np.linalg.norm(P - (Q @ R.T + t), axis=1)
+    inl = e < 0.5
+    assert abs(inl.mean() - 0.5) < 0.02                 # 50 % outliers
+    assert abs(np.std((P - (Q @ R.T + t))[inl], axis=0).mean() - 0.1) < 0.01   # sigma = 0.1 m per axis
+    d = rpe.sim_2d_3d_nl(5, q, t, 5000)
+    assert np.abs(np.linalg.norm(d["bv"], axis=1) - 1).max() < 1e-5
+    assert np.abs(np.linalg.norm(d["nc"], axis=1) - 1).max() < 1e-5
+    assert (d["nc"][:, 2] <= 0).all()                   # normals face the camera (Simulator.hpp:106)
+
+
+def test_update_num_iters_host(rpe):
+    assert rpe.update_num_iters(0.99, 0.5, 3, 100000) == 34
+    assert rpe.update_num_iters(0.9999, 0.5, 3, 100000) == 69
+    assert rpe.update_num_iters(0.99, 0.0, 3, 100) == 0
+    assert rpe.update_num_iters(0.99, 1.0, 3, 100) == 100
