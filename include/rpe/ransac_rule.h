@@ -37,23 +37,51 @@ RPE_HD float rule_fdiv(float a, float b) {
 #endif
 }
 
-RPE_HD int update_num_iters(float p, float ep, const int model_points, const int max_iters) {
+// The rule split into its three data dependencies, so that a device replay can evaluate the expensive
+// part (the logarithm of the denominator, a function of the vote count only) for many candidates in
+// parallel and keep only the cheap clamp/divide sequential. update_num_iters() composes them.
+struct RuleDenominator {
+  int state;        // 0: "1 - (1-ep)^K < eps" -> the rule returns 0;  1: log_denom valid
+  float log_denom;  // log(1 - (1-ep)^K)
+};
+
+RPE_HD float rule_log_numerator(float p) {
   const float feps = 1.1920928955078125e-07f;  // std::numeric_limits<float>::epsilon()
   p = p > 0.f ? p : 0.f;
   p = p < 1.f ? p : 1.f;
-  ep = ep > 0.f ? ep : 0.f;
-  ep = ep < 1.f ? ep : 1.f;
   float num = (float)det::dsub(1.0, (double)p);
   num = num > feps ? num : feps;
+  return det::log_f(num);
+}
+
+RPE_HD RuleDenominator rule_denominator(float ep, const int model_points) {
+  const float feps = 1.1920928955078125e-07f;
+  ep = ep > 0.f ? ep : 0.f;
+  ep = ep < 1.f ? ep : 1.f;
   const double base = (double)((float)det::dsub(1.0, (double)ep));
   double pw = 1.0;
   for (int i = 0; i < model_points; ++i) pw = det::dmul(pw, base);
-  float denom = (float)det::dsub(1.0, pw);
-  if (denom < feps) return 0;
-  num = det::log_f(num);
-  denom = det::log_f(denom);
+  const float denom = (float)det::dsub(1.0, pw);
+  RuleDenominator r;
+  if (denom < feps) {
+    r.state = 0;
+    r.log_denom = 0.f;
+  } else {
+    r.state = 1;
+    r.log_denom = det::log_f(denom);
+  }
+  return r;
+}
+
+RPE_HD int rule_finish(float log_num, RuleDenominator d, const int max_iters) {
+  if (d.state == 0) return 0;
+  const float num = log_num, denom = d.log_denom;
   if (denom >= 0.f || -num >= rule_fmul((float)max_iters, -denom)) return max_iters;
   return (int)rule_fadd(rule_fdiv(num, denom), 0.5f);
+}
+
+RPE_HD int update_num_iters(float p, float ep, const int model_points, const int max_iters) {
+  return rule_finish(rule_log_numerator(p), rule_denominator(ep, model_points), max_iters);
 }
 
 RPE_HD float outlier_ratio(int modalities, int n, int votes) {

@@ -15,6 +15,8 @@
 
 namespace rpe {
 void set_use_packed(bool v);
+void set_score_variant(int v);
+void set_nosync(int v);
 }
 
 using namespace rpe;
@@ -64,7 +66,7 @@ struct rpe_ctx {
   int16_t* d_mask = nullptr;
   size_t mask_cap = 0;
   int mask_cols = 0;
-  RefitBuffers rb = {nullptr, nullptr, 0};
+  RefitBuffers rb = {nullptr, nullptr, 0, 148};
   GnState* d_gn = nullptr;
   double* d_gn_cost = nullptr;
   int32_t* d_gn_evals = nullptr;
@@ -422,6 +424,7 @@ static int create_common(int device, void* stream, bool own, rpe_ctx** out) {
   ctx->device = device;
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->num_sms = prop.multiProcessorCount;
+  ctx->rb.num_sms = ctx->num_sms;
   if (prop.major < 10) {
     delete ctx;
     return RPE_ERR_NO_DEVICE;  // kernels are built for sm_100a only
@@ -600,8 +603,8 @@ static int do_refit(rpe_ctx* ctx, int kind, const float* weights, int max_iters,
       if (kind == RPE_REFIT_KABSCH_INLIERS && ctx->mask_cols < 2)
         return fail(ctx, RPE_ERR_STATE, "no 3-D inlier column available");
       const int16_t* flags = kind == RPE_REFIT_KABSCH_INLIERS ? ctx->d_mask + ctx->n : nullptr;
-      launch_kabsch_moments(f, flags, ctx->rb, ctx->d_stats, ctx->stream);
-      launch_kabsch_solve(ctx->rb, (ctx->n + 255) / 256, ctx->d_pose, nullptr, ctx->stream);
+      const int used = launch_kabsch_moments(f, flags, ctx->rb, ctx->d_stats, ctx->stream);
+      launch_kabsch_solve(ctx->rb, used, ctx->d_pose, nullptr, ctx->stream);
       ctx->launches += 2;
     }
   } else if (kind == RPE_REFIT_GN) {
@@ -611,9 +614,9 @@ static int do_refit(rpe_ctx* ctx, int kind, const float* weights, int max_iters,
     stamp(ctx, ST_GN);
     launch_gn_init(ctx->d_pose, ctx->d_gn, ctx->stream);
     for (int it = 0; it < iters; ++it)
-      launch_gn_iteration(f, ctx->d_mask, ctx->mask_cols, w2, w3, wn, ctx->rb, ctx->d_gn, ctx->d_stats, ctx->stream);
-    launch_gn_finish(ctx->d_gn, ctx->d_pose, ctx->d_gn_cost, ctx->d_gn_evals, ctx->stream);
-    ctx->launches += iters + 2;
+      launch_gn_iteration(f, ctx->d_mask, ctx->mask_cols, w2, w3, wn, ctx->rb, ctx->d_gn, ctx->d_stats, ctx->d_pose,
+                          ctx->d_gn_cost, ctx->d_gn_evals, ctx->stream);
+    ctx->launches += iters + 1;
     CK(cudaMemcpyAsync(&ctx->h_gn_cost[slot], ctx->d_gn_cost, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemcpyAsync(&ctx->h_gn_evals[slot], ctx->d_gn_evals, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
     stamp(ctx, ST_TOTAL);
@@ -849,6 +852,14 @@ int rpe_last_stage_ms(rpe_ctx* ctx, float ms[8]) {
 // test hook: choose the packed (FFMA2) or scalar (FFMA) fast kernel
 int rpe_debug_set_packed(int packed) {
   rpe::set_use_packed(packed != 0);
+  return RPE_OK;
+}
+int rpe_debug_set_nosync(int v) {
+  rpe::set_nosync(v);
+  return RPE_OK;
+}
+int rpe_debug_set_score_variant(int v) {
+  rpe::set_score_variant(v);
   return RPE_OK;
 }
 

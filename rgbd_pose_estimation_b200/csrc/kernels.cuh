@@ -63,6 +63,7 @@ struct RefitBuffers {
   double* partials;   // [blocks x kMomentCount]
   double* moments;    // [kMomentCount] reduced
   int max_blocks;
+  int num_sms;        // refit kernels use at most 2 CTAs per SM and stride over the correspondences
 };
 constexpr int kMomentCount = 32;  // 16 Kabsch moments / 28 GN entries, padded
 
@@ -72,8 +73,9 @@ void launch_mask(int method, const FrameView& f, ReplayOut* pose_rw, Thresh th, 
                  RefitBuffers rb, FrameStats* st, cudaStream_t s);
 void launch_reset_corr_bound(FrameStats* st, cudaStream_t s);
 // Kabsch from the moments left by launch_mask (or by launch_kabsch_moments); writes pose_out.
-void launch_kabsch_moments(const FrameView& f, const int16_t* flags3d /*null: all points*/, RefitBuffers rb,
-                           FrameStats* st, cudaStream_t s);
+// returns the number of CTAs launched (= rows of rb.partials to reduce)
+int launch_kabsch_moments(const FrameView& f, const int16_t* flags3d /*null: all points*/, RefitBuffers rb,
+                          FrameStats* st, cudaStream_t s);
 void launch_kabsch_solve(RefitBuffers rb, int blocks_used, ReplayOut* pose_inout, int32_t* refit_ok, cudaStream_t s);
 
 struct GnState {  // device-resident LM state (mirrors oracle/refine.hpp refine_gn)
@@ -86,9 +88,11 @@ struct GnState {  // device-resident LM state (mirrors oracle/refine.hpp refine_
   int have, done, evals, accepted;
 };
 void launch_gn_init(const ReplayOut* pose, GnState* st, cudaStream_t s);
+// One LM evaluation; its last CTA solves, updates the state and refreshes pose_out/cost_out/evals_out with
+// the best pose accepted so far.
 void launch_gn_iteration(const FrameView& f, const int16_t* mask, int mask_cols, float w2d, float w3d, float wnl,
-                         RefitBuffers rb, GnState* gs, FrameStats* st, cudaStream_t s);
-void launch_gn_finish(const GnState* gs, ReplayOut* pose_out, double* cost_out, int32_t* evals_out, cudaStream_t s);
+                         RefitBuffers rb, GnState* gs, FrameStats* st, ReplayOut* pose_out, double* cost_out,
+                         int32_t* evals_out, cudaStream_t s);
 
 // -- microbenchmark -----------------------------------------------------------------------------------
 void launch_ffma_bench(float* sink, int iters, bool packed, int blocks, cudaStream_t s);

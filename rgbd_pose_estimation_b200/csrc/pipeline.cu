@@ -155,48 +155,86 @@ void launch_derive_fast(const HypGen* gen, HypFast* fast, int32_t* votes, int n_
 // ================================================================================================
 // replay of the sequential rule (one warp; all lanes run the scalar part redundantly)
 // ================================================================================================
-__global__ void replay_kernel(int method, const HypGen* __restrict__ gen, const int32_t* __restrict__ votes, int H, int n,
-                              float confidence, const FrameStats* __restrict__ st, ReplayOut* __restrict__ out) {
-  const int lane = threadIdx.x;
+constexpr int kReplayChunk = 4096;  // vote-table entries staged in shared memory per pass
+__global__ void __launch_bounds__(256)
+replay_kernel(int method, const HypGen* __restrict__ gen, const int32_t* __restrict__ votes, int H, int n,
+              float confidence, const FrameStats* __restrict__ st, ReplayOut* __restrict__ out) {
+  __shared__ int32_t sv[kReplayChunk];
+  __shared__ int s_state[5];  // best, Iter, win, cur_iter, stop
+  const int lane = threadIdx.x & 31;
   const int S = method_slots(method);
   const int K = method_model_points(method);
   const int mod = method_modalities(method);
   const int E = H * S;
-  int best = -1, Iter = H, win = -1, cur_iter = -1;
-  bool stop = false;
-  for (int base = 0; base < E && !stop; base += 32) {
-    const int i = base + lane;
-    const int v = i < E ? votes[i] : -1;
-    int pm = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int tv = __shfl_up_sync(0xffffffffu, pm, o);
-      if (lane >= o) pm = max(pm, tv);
-    }
-    int excl = __shfl_up_sync(0xffffffffu, pm, 1);
-    if (lane == 0) excl = -2147483647;
-    const bool rec = v >= 0 && v > max(excl, best);
-    unsigned int m = __ballot_sync(0xffffffffu, rec);
-    while (m) {
-      const int b = __ffs(m) - 1;
-      m &= m - 1;
-      const int idx = base + b;
-      const int it = idx / S;
-      const int vb = __shfl_sync(0xffffffffu, v, b);
-      if (it != cur_iter) {
-        if (it >= Iter) {  // `for (ii = 0; ii < Iter; ii++)` would not have reached this iteration
-          stop = true;
-          break;
-        }
-        cur_iter = it;
-      }
-      best = vb;
-      win = idx;
-      Iter = update_num_iters(confidence, outlier_ratio(mod, n, vb), K, Iter);
-    }
-    if ((long long)(base + 32) >= (long long)Iter * S) stop = true;  // nothing below the loop bound is left
+  if (threadIdx.x == 0) {
+    s_state[0] = -1;
+    s_state[1] = H;
+    s_state[2] = -1;
+    s_state[3] = -1;
+    s_state[4] = 0;
   }
-  if (lane == 0) {
+  __syncthreads();
+  for (int cbase = 0; cbase < E; cbase += kReplayChunk) {
+    if (s_state[4]) break;
+    const int cn = min(kReplayChunk, E - cbase);
+    for (int i = threadIdx.x; i < cn; i += blockDim.x) sv[i] = votes[cbase + i];  // all loads in flight at once
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      const float log_num = rule_log_numerator(confidence);
+      int best = s_state[0], Iter = s_state[1], win = s_state[2], cur_iter = s_state[3];
+      bool stop = false;
+      for (int base = 0; base < cn && !stop; base += 32) {
+        const int i = base + lane;
+        const int v = i < cn ? sv[i] : -1;
+        int pm = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int tv = __shfl_up_sync(0xffffffffu, pm, o);
+          if (lane >= o) pm = max(pm, tv);
+        }
+        int excl = __shfl_up_sync(0xffffffffu, pm, 1);
+        if (lane == 0) excl = -2147483647;
+        const bool rec = v >= 0 && v > max(excl, best);
+        unsigned int m = __ballot_sync(0xffffffffu, rec);
+        // every candidate's log-denominator depends on its own vote count only: all lanes evaluate theirs at once
+        RuleDenominator rd;
+        rd.state = 0;
+        rd.log_denom = 0.f;
+        if (rec) rd = rule_denominator(outlier_ratio(mod, n, v), K);
+        while (m) {
+          const int b = __ffs(m) - 1;
+          m &= m - 1;
+          const int idx = cbase + base + b;
+          const int it = idx / S;
+          const int vb = __shfl_sync(0xffffffffu, v, b);
+          if (it != cur_iter) {
+            if (it >= Iter) {  // `for (ii = 0; ii < Iter; ii++)` would not have reached this iteration
+              stop = true;
+              break;
+            }
+            cur_iter = it;
+          }
+          best = vb;
+          win = idx;
+          RuleDenominator rb_;
+          rb_.state = __shfl_sync(0xffffffffu, rd.state, b);
+          rb_.log_denom = __shfl_sync(0xffffffffu, rd.log_denom, b);
+          Iter = rule_finish(log_num, rb_, Iter);
+        }
+        if ((long long)(cbase + base + 32) >= (long long)Iter * S) stop = true;  // nothing below the loop bound is left
+      }
+      if (lane == 0) {
+        s_state[0] = best;
+        s_state[1] = Iter;
+        s_state[2] = win;
+        s_state[3] = cur_iter;
+        s_state[4] = stop ? 1 : 0;
+      }
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const int best = s_state[0], Iter = s_state[1], win = s_state[2];
     if (win >= 0) {
       const HypGen g = gen[win];
       for (int k = 0; k < 4; ++k) out->q[k] = g.q[k];
@@ -219,7 +257,7 @@ __global__ void replay_kernel(int method, const HypGen* __restrict__ gen, const 
 
 void launch_replay(int method, const HypGen* gen, const int32_t* votes, int H, int n, float confidence,
                    const FrameStats* st, ReplayOut* out, cudaStream_t s) {
-  replay_kernel<<<1, 32, 0, s>>>(method, gen, votes, H, n, confidence, st, out);
+  replay_kernel<<<1, 256, 0, s>>>(method, gen, votes, H, n, confidence, st, out);
 }
 
 // ================================================================================================
@@ -237,20 +275,30 @@ __device__ __forceinline__ void block_reduce_store(double* v, double* __restrict
   }
   __syncthreads();
   const int nw = blockDim.x >> 5;
-  if (threadIdx.x < NV) {
+  if (threadIdx.x < kMomentCount) {
     double x = 0.0;
-    for (int w = 0; w < nw; ++w) x += smem[w * NV + threadIdx.x];
+    if (threadIdx.x < NV)
+      for (int w = 0; w < nw; ++w) x += smem[w * NV + threadIdx.x];
     partials[(size_t)blockIdx.x * kMomentCount + threadIdx.x] = x;
   }
 }
-// Sum partials over blocks in a fixed order (lane-strided, then a shuffle tree): one warp.
-__device__ __forceinline__ double reduce_partials(const double* __restrict__ partials, int nblocks, int comp) {
-  const int lane = threadIdx.x & 31;
+// Final reduction by the LAST CTA (256 threads): thread (g = tid/32, k = tid%32) sums component k over the CTAs
+// b = g, g+8, ... (independent loads, all in flight together), then the 8 groups are added in a fixed order.
+// Deterministic for a given grid size. Result in smem_out[0..kMomentCount).
+__device__ __forceinline__ void final_reduce_partials(const double* __restrict__ partials, int nblocks,
+                                                      double* smem_scratch /*[8*32]*/, double* smem_out /*[32]*/) {
+  const int k = threadIdx.x & 31, g = threadIdx.x >> 5;
   double x = 0.0;
-  for (int b = lane; b < nblocks; b += 32) x += partials[(size_t)b * kMomentCount + comp];
+  for (int b = g; b < nblocks; b += 8) x += partials[(size_t)b * kMomentCount + k];
+  smem_scratch[g * 32 + k] = x;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double t = 0.0;
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
-  return __shfl_sync(0xffffffffu, x, 0);
+    for (int gg = 0; gg < 8; ++gg) t += smem_scratch[gg * 32 + threadIdx.x];
+    smem_out[threadIdx.x] = t;
+  }
+  __syncthreads();
 }
 
 // Kabsch from moments m[0]=K, m[1..3]=sum x_w, m[4..6]=sum x_c, m[7..15]=sum x_c x_w^T (row-major).
@@ -278,14 +326,13 @@ __device__ bool kabsch_from_moments(const double* m, float* q_out, float* t_out)
 // ================================================================================================
 // winner's mask (+ Kabsch moments of the 3-D inliers, + the Kabsch solve in the last CTA)
 // ================================================================================================
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 mask_kernel(int method, FrameView f, ReplayOut* pose_rw, Thresh th, int16_t* __restrict__ mask, RefitBuffers rb,
             ReplayOut* kabsch_out, FrameStats* st) {
   const ReplayOut* pose = pose_rw;
   __shared__ double red[8 * 16];
   __shared__ int cnts[3];
   __shared__ bool is_last;
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
   const int n = f.n;
   const int cols = method_mask_cols(method);
   if (threadIdx.x < 3) cnts[threadIdx.x] = 0;
@@ -300,8 +347,9 @@ mask_kernel(int method, FrameView f, ReplayOut* pose_rw, Thresh th, int16_t* __r
   double mom[16];
 #pragma unroll
   for (int k = 0; k < 16; ++k) mom[k] = 0.0;
-  bool f2 = false, f3d = false, fn = false;
-  if (c < n) {
+  int c2 = 0, c3 = 0, cn = 0;
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < n; c += gridDim.x * blockDim.x) {
+    bool f2 = false, f3d = false, fn = false;
     if (have) {
       const F3 xw = load_col(f.xw, c);
       bool valid = false;
@@ -314,14 +362,19 @@ mask_kernel(int method, FrameView f, ReplayOut* pose_rw, Thresh th, int16_t* __r
       if (u3 && valid) f3d = ex_test_3d(h.q, h.t, xw, xc, th.thr3d);
       if (u2) f2 = ex_test_2d(h.q, h.t, method == RPE_KNEIP ? Rm : nullptr, xw, load_col(f.bv, c), th.cos_thr);
       if (f3d) {
-        mom[0] = 1.0;
-        const double w3[3] = {xw.x, xw.y, xw.z}, c3[3] = {xc.x, xc.y, xc.z};
+        mom[0] += 1.0;
+        const double w3[3] = {xw.x, xw.y, xw.z}, c3v[3] = {xc.x, xc.y, xc.z};
+#pragma unroll
         for (int r = 0; r < 3; ++r) {
-          mom[1 + r] = w3[r];
-          mom[4 + r] = c3[r];
-          for (int q = 0; q < 3; ++q) mom[7 + 3 * r + q] = c3[r] * w3[q];
+          mom[1 + r] += w3[r];
+          mom[4 + r] += c3v[r];
+#pragma unroll
+          for (int q = 0; q < 3; ++q) mom[7 + 3 * r + q] += c3v[r] * w3[q];
         }
       }
+      c2 += f2 ? 1 : 0;
+      c3 += f3d ? 1 : 0;
+      cn += fn ? 1 : 0;
     } else {
       f2 = f3d = fn = true;  // adapters start with setOnes() and setInlier is never called
     }
@@ -330,12 +383,16 @@ mask_kernel(int method, FrameView f, ReplayOut* pose_rw, Thresh th, int16_t* __r
     if (cols >= 3) mask[2 * n + c] = (int16_t)(fn ? 1 : 0);
   }
   // per-column counts
-  const unsigned b2 = __ballot_sync(0xffffffffu, f2 && have), b3 = __ballot_sync(0xffffffffu, f3d && have),
-                 bn = __ballot_sync(0xffffffffu, fn && have);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    c2 += __shfl_xor_sync(0xffffffffu, c2, o);
+    c3 += __shfl_xor_sync(0xffffffffu, c3, o);
+    cn += __shfl_xor_sync(0xffffffffu, cn, o);
+  }
   if ((threadIdx.x & 31) == 0) {
-    if (b2) atomicAdd(&cnts[0], __popc(b2));
-    if (b3) atomicAdd(&cnts[1], __popc(b3));
-    if (bn) atomicAdd(&cnts[2], __popc(bn));
+    if (c2) atomicAdd(&cnts[0], c2);
+    if (c3) atomicAdd(&cnts[1], c3);
+    if (cn) atomicAdd(&cnts[2], cn);
   }
   block_reduce_store<16>(mom, rb.partials, red);
   __syncthreads();
@@ -347,11 +404,14 @@ mask_kernel(int method, FrameView f, ReplayOut* pose_rw, Thresh th, int16_t* __r
     is_last = (t == gridDim.x - 1);
   }
   __syncthreads();
-  if (is_last && threadIdx.x < 32) {
+  if (is_last) {
     __threadfence();
-    double m[16];
-    for (int k = 0; k < 16; ++k) m[k] = reduce_partials(rb.partials, gridDim.x, k);
+    __shared__ double fin_scratch[8 * 32];
+    __shared__ double fin[32];
+    final_reduce_partials(rb.partials, gridDim.x, fin_scratch, fin);
     if (threadIdx.x == 0) {
+      double m[16];
+      for (int k = 0; k < 16; ++k) m[k] = fin[k];
       for (int k = 0; k < 16; ++k) rb.moments[k] = m[k];
       ReplayOut o = *pose_rw;
       float q[4], t[3];
@@ -368,42 +428,52 @@ mask_kernel(int method, FrameView f, ReplayOut* pose_rw, Thresh th, int16_t* __r
   }
 }
 
+static int refit_grid(int n, int num_sms_hint) {
+  const int full = (n + 255) / 256;
+  const int cap = 2 * (num_sms_hint > 0 ? num_sms_hint : 148);
+  return full < cap ? full : cap;
+}
 void launch_mask(int method, const FrameView& f, ReplayOut* pose_rw, Thresh th, int16_t* mask, ReplayOut* kabsch_out,
                  RefitBuffers rb, FrameStats* st, cudaStream_t s) {
-  const int threads = 256;
-  const int blocks = (f.n + threads - 1) / threads;
-  mask_kernel<<<blocks, threads, 0, s>>>(method, f, pose_rw, th, mask, rb, kabsch_out, st);
+  mask_kernel<<<refit_grid(f.n, rb.num_sms), 256, 0, s>>>(method, f, pose_rw, th, mask, rb, kabsch_out, st);
 }
 
 // Stand-alone moments over an explicit flag column (after rpe_set_mask) or over all points (shinji_ls2).
 __global__ void __launch_bounds__(256)
 kabsch_moments_kernel(FrameView f, const int16_t* __restrict__ flags3d, RefitBuffers rb) {
   __shared__ double red[8 * 16];
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
   double mom[16];
 #pragma unroll
   for (int k = 0; k < 16; ++k) mom[k] = 0.0;
-  if (c < f.n && (!flags3d || flags3d[c] == 1)) {
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < f.n; c += gridDim.x * blockDim.x) {
+    if (flags3d && flags3d[c] != 1) continue;
     const F3 xw = load_col(f.xw, c), xc = load_col(f.xc, c);
-    mom[0] = 1.0;
+    mom[0] += 1.0;
     const double w3[3] = {xw.x, xw.y, xw.z}, c3[3] = {xc.x, xc.y, xc.z};
+#pragma unroll
     for (int r = 0; r < 3; ++r) {
-      mom[1 + r] = w3[r];
-      mom[4 + r] = c3[r];
-      for (int q = 0; q < 3; ++q) mom[7 + 3 * r + q] = c3[r] * w3[q];
+      mom[1 + r] += w3[r];
+      mom[4 + r] += c3[r];
+#pragma unroll
+      for (int q = 0; q < 3; ++q) mom[7 + 3 * r + q] += c3[r] * w3[q];
     }
   }
   block_reduce_store<16>(mom, rb.partials, red);
 }
-void launch_kabsch_moments(const FrameView& f, const int16_t* flags3d, RefitBuffers rb, FrameStats* st, cudaStream_t s) {
+int launch_kabsch_moments(const FrameView& f, const int16_t* flags3d, RefitBuffers rb, FrameStats* st, cudaStream_t s) {
   (void)st;
-  const int threads = 256;
-  kabsch_moments_kernel<<<(f.n + threads - 1) / threads, threads, 0, s>>>(f, flags3d, rb);
+  const int blocks = refit_grid(f.n, rb.num_sms);
+  kabsch_moments_kernel<<<blocks, 256, 0, s>>>(f, flags3d, rb);
+  return blocks;
 }
-__global__ void kabsch_solve_kernel(RefitBuffers rb, int blocks_used, ReplayOut* __restrict__ pose, int32_t* refit_ok) {
-  double m[16];
-  for (int k = 0; k < 16; ++k) m[k] = reduce_partials(rb.partials, blocks_used, k);
+__global__ void __launch_bounds__(256)
+kabsch_solve_kernel(RefitBuffers rb, int blocks_used, ReplayOut* __restrict__ pose, int32_t* refit_ok) {
+  __shared__ double fin_scratch[8 * 32];
+  __shared__ double fin[32];
+  final_reduce_partials(rb.partials, blocks_used, fin_scratch, fin);
   if (threadIdx.x == 0) {
+    double m[16];
+    for (int k = 0; k < 16; ++k) m[k] = fin[k];
     for (int k = 0; k < 16; ++k) rb.moments[k] = m[k];
     float q[4], t[3];
     const bool ok = kabsch_from_moments(m, q, t);
@@ -416,7 +486,7 @@ __global__ void kabsch_solve_kernel(RefitBuffers rb, int blocks_used, ReplayOut*
   }
 }
 void launch_kabsch_solve(RefitBuffers rb, int blocks_used, ReplayOut* pose_inout, int32_t* refit_ok, cudaStream_t s) {
-  kabsch_solve_kernel<<<1, 32, 0, s>>>(rb, blocks_used, pose_inout, refit_ok);
+  kabsch_solve_kernel<<<1, 256, 0, s>>>(rb, blocks_used, pose_inout, refit_ok);
 }
 
 // ================================================================================================
@@ -553,33 +623,81 @@ __device__ void se3_exp_left(const double* delta, double* R, double* t) {
   for (int i = 0; i < 3; ++i) t[i] = tn[i];
 }
 
+// Accumulator layouts (per thread, FP64):
+//   GENERIC (any modality, needed for the 2-D rows): [0..20] upper triangle of J^T J, [21..26] J^T r,
+//            [27] cost, [28] rows
+//   MOMENTS (3-D and normal rows only; their normal equations are polynomial in y = R x + t, m = R n):
+//            [0] sum w3, [1..3] sum w3 y, [4..9] sum w3 y y^T (xx,xy,xz,yy,yz,zz), [10..12] sum w3 r,
+//            [13..15] sum w3 (y x r), [16..21] sum wn m m^T, [22..24] sum wn (m x rn), [25] cost, [26] rows
+//   J^T J = [[S I, -[Sy]x], [., (tr Syy) I - Syy + (tr Smm) I - Smm]],  J^T r = [Sr ; Syxr + Smxr]
+constexpr int kGnAcc = 29;
+
+__device__ __forceinline__ void gn_moments_to_normal_eq(const double* a, double* H21, double* g6, double* cost,
+                                                        double* rows) {
+  double H[6][6];
+  for (int i = 0; i < 6; ++i)
+    for (int j = 0; j < 6; ++j) H[i][j] = 0.0;
+  H[0][0] = H[1][1] = H[2][2] = a[0];
+  const double sx = a[1], sy = a[2], sz = a[3];
+  H[0][4] = sz;
+  H[0][5] = -sy;
+  H[1][3] = -sz;
+  H[1][5] = sx;
+  H[2][3] = sy;
+  H[2][4] = -sx;
+  const double yy[6] = {a[4] + a[16], a[5] + a[17], a[6] + a[18], a[7] + a[19], a[8] + a[20], a[9] + a[21]};
+  const double tr = yy[0] + yy[3] + yy[5];
+  H[3][3] = tr - yy[0];
+  H[3][4] = -yy[1];
+  H[3][5] = -yy[2];
+  H[4][4] = tr - yy[3];
+  H[4][5] = -yy[4];
+  H[5][5] = tr - yy[5];
+  int k = 0;
+  for (int i = 0; i < 6; ++i)
+    for (int j = i; j < 6; ++j) H21[k++] = H[i][j];
+  g6[0] = a[10];
+  g6[1] = a[11];
+  g6[2] = a[12];
+  g6[3] = a[13] + a[22];
+  g6[4] = a[14] + a[23];
+  g6[5] = a[15] + a[24];
+  *cost = a[25];
+  *rows = a[26];
+}
+
+template <bool GENERIC>
 __global__ void __launch_bounds__(256)
 gn_iteration_kernel(FrameView f, const int16_t* __restrict__ mask, int mask_cols, float w2d, float w3d, float wnl,
-                    RefitBuffers rb, GnState* __restrict__ gs, FrameStats* __restrict__ st) {
+                    RefitBuffers rb, GnState* __restrict__ gs, FrameStats* __restrict__ st, ReplayOut* __restrict__ pose_out,
+                    double* __restrict__ cost_out, int32_t* __restrict__ evals_out) {
   if (gs->done) return;
-  __shared__ double red[8 * 29];
+  __shared__ double red[8 * kGnAcc];
   __shared__ bool is_last;
   const int n = f.n;
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  double acc[29];
+  double acc[kGnAcc];
 #pragma unroll
-  for (int k = 0; k < 29; ++k) acc[k] = 0.0;
-  if (c < n) {
-    const bool u2 = mask_cols >= 1 && f.bv && w2d > 0.f && mask[c] == 1;
-    const bool u3 = mask_cols >= 2 && f.xc && w3d > 0.f && mask[n + c] == 1;
-    const bool un = mask_cols >= 3 && f.nc && wnl > 0.f && mask[2 * n + c] == 1;
-    if (u2 || u3 || un) {
-      // FP32 residuals / Jacobian entries from the FP32 copy of the current proposal, FP64 accumulation
-      float R[9], t[3];
+  for (int k = 0; k < kGnAcc; ++k) acc[k] = 0.0;
+  // FP32 residuals / Jacobian entries from the FP32 copy of the current proposal, FP64 accumulation
+  float R[9], t[3];
 #pragma unroll
-      for (int k = 0; k < 9; ++k) R[k] = (float)gs->Rp[k];
+  for (int k = 0; k < 9; ++k) R[k] = (float)gs->Rp[k];
 #pragma unroll
-      for (int k = 0; k < 3; ++k) t[k] = (float)gs->tp[k];
-      const F3 x = load_col(f.xw, c);
-      float yf[3];
+  for (int k = 0; k < 3; ++k) t[k] = (float)gs->tp[k];
+  const bool m2 = mask_cols >= 1 && f.bv && w2d > 0.f;
+  const bool m3 = mask_cols >= 2 && f.xc && w3d > 0.f;
+  const bool mn = mask_cols >= 3 && f.nc && wnl > 0.f;
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < n; c += gridDim.x * blockDim.x) {
+    const bool u2 = GENERIC && m2 && mask[c] == 1;
+    const bool u3 = m3 && mask[n + c] == 1;
+    const bool un = mn && mask[2 * n + c] == 1;
+    if (!(u2 || u3 || un)) continue;
+    const F3 x = load_col(f.xw, c);
+    float yf[3];
 #pragma unroll
-      for (int r = 0; r < 3; ++r) yf[r] = fmaf(R[3 * r], x.x, fmaf(R[3 * r + 1], x.y, fmaf(R[3 * r + 2], x.z, t[r])));
-      const double y[3] = {yf[0], yf[1], yf[2]};
+    for (int r = 0; r < 3; ++r) yf[r] = fmaf(R[3 * r], x.x, fmaf(R[3 * r + 1], x.y, fmaf(R[3 * r + 2], x.z, t[r])));
+    const double y[3] = {yf[0], yf[1], yf[2]};
+    if (GENERIC) {
       double Jy[3][6];
       gn_point_rows(y, Jy);
       if (u3) {
@@ -599,10 +717,10 @@ gn_iteration_kernel(FrameView f, const int16_t* __restrict__ mask, int mask_cols
         for (int r = 0; r < 3; ++r)
 #pragma unroll
           for (int cc = 0; cc < 6; ++cc) {
-            double s = 0.0;
+            double sacc = 0.0;
 #pragma unroll
-            for (int k = 0; k < 3; ++k) s += (((r == k) ? 1.0 : 0.0) - u[r] * u[k]) / ny * Jy[k][cc];
-            Ju[r][cc] = s;
+            for (int k = 0; k < 3; ++k) sacc += (((r == k) ? 1.0 : 0.0) - u[r] * u[k]) / ny * Jy[k][cc];
+            Ju[r][cc] = sacc;
           }
         double Jr[3][6];
 #pragma unroll
@@ -629,9 +747,53 @@ gn_iteration_kernel(FrameView f, const int16_t* __restrict__ mask, int mask_cols
           gn_add_row(acc, Jn[r], (double)rf[r], (double)wnl);
         }
       }
+    } else {
+      if (u3) {
+        const F3 p = load_col(f.xc, c);
+        const double w = (double)w3d;
+        const double r[3] = {(double)(yf[0] - p.x), (double)(yf[1] - p.y), (double)(yf[2] - p.z)};
+        acc[0] += w;
+        acc[1] += w * y[0];
+        acc[2] += w * y[1];
+        acc[3] += w * y[2];
+        acc[4] += w * y[0] * y[0];
+        acc[5] += w * y[0] * y[1];
+        acc[6] += w * y[0] * y[2];
+        acc[7] += w * y[1] * y[1];
+        acc[8] += w * y[1] * y[2];
+        acc[9] += w * y[2] * y[2];
+        acc[10] += w * r[0];
+        acc[11] += w * r[1];
+        acc[12] += w * r[2];
+        acc[13] += w * (y[1] * r[2] - y[2] * r[1]);
+        acc[14] += w * (y[2] * r[0] - y[0] * r[2]);
+        acc[15] += w * (y[0] * r[1] - y[1] * r[0]);
+        acc[25] += w * (r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
+        acc[26] += 3.0;
+      }
+      if (un) {
+        const F3 nw = load_col(f.nw, c), nc = load_col(f.nc, c);
+        float mf[3];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) mf[r] = fmaf(R[3 * r], nw.x, fmaf(R[3 * r + 1], nw.y, R[3 * r + 2] * nw.z));
+        const double m[3] = {mf[0], mf[1], mf[2]};
+        const double w = (double)wnl;
+        const double r[3] = {(double)(mf[0] - nc.x), (double)(mf[1] - nc.y), (double)(mf[2] - nc.z)};
+        acc[16] += w * m[0] * m[0];
+        acc[17] += w * m[0] * m[1];
+        acc[18] += w * m[0] * m[2];
+        acc[19] += w * m[1] * m[1];
+        acc[20] += w * m[1] * m[2];
+        acc[21] += w * m[2] * m[2];
+        acc[22] += w * (m[1] * r[2] - m[2] * r[1]);
+        acc[23] += w * (m[2] * r[0] - m[0] * r[2]);
+        acc[24] += w * (m[0] * r[1] - m[1] * r[0]);
+        acc[25] += w * (r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
+        acc[26] += 3.0;
+      }
     }
   }
-  block_reduce_store<29>(acc, rb.partials, red);
+  block_reduce_store<kGnAcc>(acc, rb.partials, red);
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence();
@@ -639,24 +801,36 @@ gn_iteration_kernel(FrameView f, const int16_t* __restrict__ mask, int mask_cols
     is_last = (tk == gridDim.x - 1);
   }
   __syncthreads();
-  if (!(is_last && threadIdx.x < 32)) return;
+  if (!is_last) return;
   __threadfence();
-  double tot[29];
-  for (int k = 0; k < 29; ++k) tot[k] = reduce_partials(rb.partials, gridDim.x, k);
+  __shared__ double fin_scratch[8 * 32];
+  __shared__ double fin[32];
+  final_reduce_partials(rb.partials, gridDim.x, fin_scratch, fin);
   if (threadIdx.x != 0) return;
+  double tot[kGnAcc];
+  for (int k = 0; k < kGnAcc; ++k) tot[k] = fin[k];
   st->ticket2 = 0;
+  double Hn[21], gn[6], cost, rows;
+  if (GENERIC) {
+    for (int k = 0; k < 21; ++k) Hn[k] = tot[k];
+    for (int k = 0; k < 6; ++k) gn[k] = tot[21 + k];
+    cost = tot[27];
+    rows = tot[28];
+  } else {
+    gn_moments_to_normal_eq(tot, Hn, gn, &cost, &rows);
+  }
   // ---- LM tail (oracle/refine.hpp::refine_gn, one evaluation) ----
   gs->evals += 1;
-  const double cost = tot[27];
+  bool finished = false;
   if (!gs->have || cost < gs->cost_acc) {
     for (int k = 0; k < 9; ++k) gs->Ra[k] = gs->Rp[k];
     for (int k = 0; k < 3; ++k) gs->ta[k] = gs->tp[k];
-    for (int k = 0; k < 21; ++k) gs->H[k] = tot[k];
-    for (int k = 0; k < 6; ++k) gs->g[k] = tot[21 + k];
+    for (int k = 0; k < 21; ++k) gs->H[k] = Hn[k];
+    for (int k = 0; k < 6; ++k) gs->g[k] = gn[k];
     gs->cost_acc = cost;
-    gs->rows = (long long)tot[28];
+    gs->rows = (long long)rows;
     if (gs->have) {
-      double mu = gs->mu * 0.1;
+      const double mu = gs->mu * 0.1;
       gs->mu = mu < 1e-12 ? 1e-12 : mu;
       gs->accepted += 1;
     }
@@ -664,57 +838,55 @@ gn_iteration_kernel(FrameView f, const int16_t* __restrict__ mask, int mask_cols
   } else {
     gs->mu = gs->mu * 10.0;
   }
-  if (gs->rows < 6) {
-    gs->done = 1;
-    return;
+  if (gs->rows < 6) finished = true;
+  if (!finished) {
+    double delta[6];
+    int tries = 0;
+    double mu = gs->mu;
+    while (!gn_solve(gs->H, gs->g, mu, delta) && tries < 8) {
+      mu *= 10.0;
+      ++tries;
+    }
+    gs->mu = mu;
+    if (tries == 8) {
+      finished = true;
+    } else {
+      double mx = 0.0;
+      for (int k = 0; k < 6; ++k) mx = fabs(delta[k]) > mx ? fabs(delta[k]) : mx;
+      if (mx < 1e-10) {
+        finished = true;
+      } else {
+        for (int k = 0; k < 9; ++k) gs->Rp[k] = gs->Ra[k];
+        for (int k = 0; k < 3; ++k) gs->tp[k] = gs->ta[k];
+        se3_exp_left(delta, gs->Rp, gs->tp);
+      }
+    }
   }
-  double delta[6];
-  int tries = 0;
-  double mu = gs->mu;
-  while (!gn_solve(gs->H, gs->g, mu, delta) && tries < 8) {
-    mu *= 10.0;
-    ++tries;
-  }
-  gs->mu = mu;
-  if (tries == 8) {
-    gs->done = 1;
-    return;
-  }
-  double mx = 0.0;
-  for (int k = 0; k < 6; ++k) mx = fabs(delta[k]) > mx ? fabs(delta[k]) : mx;
-  if (mx < 1e-10) {
-    gs->done = 1;
-    return;
-  }
-  for (int k = 0; k < 9; ++k) gs->Rp[k] = gs->Ra[k];
-  for (int k = 0; k < 3; ++k) gs->tp[k] = gs->ta[k];
-  se3_exp_left(delta, gs->Rp, gs->tp);
-}
-
-void launch_gn_iteration(const FrameView& f, const int16_t* mask, int mask_cols, float w2d, float w3d, float wnl,
-                         RefitBuffers rb, GnState* gs, FrameStats* st, cudaStream_t s) {
-  const int threads = 256;
-  gn_iteration_kernel<<<(f.n + threads - 1) / threads, threads, 0, s>>>(f, mask, mask_cols, w2d, w3d, wnl, rb, gs, st);
-}
-
-__global__ void gn_finish_kernel(const GnState* __restrict__ gs, ReplayOut* __restrict__ pose, double* cost_out,
-                                 int32_t* evals_out) {
-  if (threadIdx.x != 0) return;
-  if (gs->have) {
+  if (finished) gs->done = 1;
+  // publish the best pose accepted so far (the final answer if no later evaluation improves on it)
+  {
     double q[4];
     so3_from_matrix<double>(gs->Ra, q);
     const double nn = sqrt((q[0] * q[0] + q[1] * q[1]) + (q[2] * q[2] + q[3] * q[3]));
-    for (int k = 0; k < 4; ++k) pose->q[k] = (float)(q[k] / nn);
-    for (int k = 0; k < 3; ++k) pose->t[k] = (float)gs->ta[k];
-    pose->refit_ok = 1;
-  } else {
-    pose->refit_ok = 0;
+    for (int k = 0; k < 4; ++k) pose_out->q[k] = (float)(q[k] / nn);
+    for (int k = 0; k < 3; ++k) pose_out->t[k] = (float)gs->ta[k];
+    pose_out->refit_ok = 1;
+    *cost_out = gs->cost_acc;
+    *evals_out = gs->evals;
   }
-  *cost_out = gs->cost_acc;
-  *evals_out = gs->evals;
 }
-void launch_gn_finish(const GnState* gs, ReplayOut* pose_out, double* cost_out, int32_t* evals_out, cudaStream_t s) {
-  gn_finish_kernel<<<1, 32, 0, s>>>(gs, pose_out, cost_out, evals_out);
+
+void launch_gn_iteration(const FrameView& f, const int16_t* mask, int mask_cols, float w2d, float w3d, float wnl,
+                         RefitBuffers rb, GnState* gs, FrameStats* st, ReplayOut* pose_out, double* cost_out,
+                         int32_t* evals_out, cudaStream_t s) {
+  const int blocks = refit_grid(f.n, rb.num_sms);
+  const bool generic = mask_cols >= 1 && f.bv != nullptr && w2d > 0.f;
+  if (generic)
+    gn_iteration_kernel<true><<<blocks, 256, 0, s>>>(f, mask, mask_cols, w2d, w3d, wnl, rb, gs, st, pose_out, cost_out,
+                                                     evals_out);
+  else
+    gn_iteration_kernel<false><<<blocks, 256, 0, s>>>(f, mask, mask_cols, w2d, w3d, wnl, rb, gs, st, pose_out, cost_out,
+                                                      evals_out);
 }
 
 }  // namespace rpe

@@ -82,36 +82,57 @@ struct PackSrc {
   int count;
 };
 
-// One thread per PAIR of correspondences (2j, 2j+1). For every source array in order, writes
-// x(2j) x(2j+1) y(2j) y(2j+1) z(2j) z(2j+1): each 64-bit half is a ready-made f32x2 operand.
+// A CTA packs kPackPairs pairs of correspondences (2j, 2j+1). The raw xyz triples of the CTA's slice are
+// first staged in shared memory with fully coalesced loads, then every thread emits whole float4 records at
+// consecutive addresses. Record layout per pair, for every source array in order:
+//   x(2j) x(2j+1) y(2j) y(2j+1) z(2j) z(2j+1)   — each 64-bit half is a ready-made f32x2 operand.
 // Also reduces max_i(|x_w| + |x_c|) over finite points for the guard band.
-__global__ void pack_kernel(PackSrc src, int n, int npairs_pad, int f4_per_pair, float* __restrict__ out,
-                            const float* __restrict__ xw, const float* __restrict__ xc, FrameStats* st) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  float mloc = 0.f;
-  if (j < npairs_pad) {
-    float* o = out + (size_t)j * f4_per_pair * 4;
-    const int c0 = 2 * j, c1 = 2 * j + 1;
-    int w = 0;
-    for (int k = 0; k < src.count; ++k) {
-      const float* a = src.a[k];
-#pragma unroll
-      for (int r = 0; r < 3; ++r) {
-        o[w++] = c0 < n ? a[3 * c0 + r] : CUDART_NAN_F;
-        o[w++] = c1 < n ? a[3 * c1 + r] : CUDART_NAN_F;
-      }
+constexpr int kPackPairs = 256;
+__global__ void __launch_bounds__(256)
+pack_kernel(PackSrc src, int n, int npairs_pad, int f4_per_pair, float4* __restrict__ out, int has_xc,
+            FrameStats* st) {
+  extern __shared__ float sm_raw[];  // [count][kPackPairs * 6]
+  const int pair0 = blockIdx.x * kPackPairs;
+  const int c_base = 2 * pair0;
+  const int floats = kPackPairs * 6;
+  for (int k = 0; k < src.count; ++k) {
+    const float* a = src.a[k];
+    for (int i = threadIdx.x; i < floats; i += blockDim.x) {
+      const long long g = (long long)c_base * 3 + i;
+      sm_raw[k * floats + i] = (g < (long long)n * 3) ? a[g] : CUDART_NAN_F;
     }
-    for (; w < f4_per_pair * 4; ++w) o[w] = 0.f;
+  }
+  __syncthreads();
+  const int pairs_here = min(kPackPairs, npairs_pad - pair0);
+  const int total_f4 = pairs_here * f4_per_pair;
+  const int fpp = f4_per_pair * 4;
+  for (int o = threadIdx.x; o < total_f4; o += blockDim.x) {
+    const int j = o / f4_per_pair;
+    const int part = o - j * f4_per_pair;
+    float v[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int w = part * 4 + e;  // float index inside the pair record
+      const int k = w / 6;
+      const int r = (w - k * 6) >> 1;
+      const int u = w & 1;
+      v[e] = (k < src.count) ? sm_raw[k * floats + (2 * j + u) * 3 + r] : 0.f;
+    }
+    (void)fpp;
+    out[(size_t)pair0 * f4_per_pair + o] = make_float4(v[0], v[1], v[2], v[3]);
+  }
+  // magnitude bound: thread <-> pair, source 0 is x_w, source 1 is x_c when present
+  float mloc = 0.f;
+  if (threadIdx.x < pairs_here) {
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
-      const int c = 2 * j + u;
+      const int c = c_base + 2 * threadIdx.x + u;
       if (c < n) {
-        float m = 0.f;
-        const float a0 = xw[3 * c], a1 = xw[3 * c + 1], a2 = xw[3 * c + 2];
-        m = sqrtf(a0 * a0 + a1 * a1 + a2 * a2);
-        if (xc) {
-          const float b0 = xc[3 * c], b1 = xc[3 * c + 1], b2 = xc[3 * c + 2];
-          const float mc = sqrtf(b0 * b0 + b1 * b1 + b2 * b2);
+        const float* pw = &sm_raw[(2 * threadIdx.x + u) * 3];
+        float m = sqrtf(pw[0] * pw[0] + pw[1] * pw[1] + pw[2] * pw[2]);
+        if (has_xc) {
+          const float* pc = &sm_raw[floats + (2 * threadIdx.x + u) * 3];
+          const float mc = sqrtf(pc[0] * pc[0] + pc[1] * pc[1] + pc[2] * pc[2]);
           if (mc == mc && mc < CUDART_INF_F) m += mc;
         }
         if (m == m && m < CUDART_INF_F) mloc = fmaxf(mloc, m);
@@ -133,10 +154,9 @@ void launch_pack(const FrameView& f, int kind, float4* pk_out, FrameStats* st, c
     src.a[src.count++] = f.nw;
     src.a[src.count++] = f.nc;
   }
-  const int threads = 256;
-  const int blocks = (f.npairs_pad + threads - 1) / threads;
-  pack_kernel<<<blocks, threads, 0, s>>>(src, f.n, f.npairs_pad, f.pk_f4_per_pair, (float*)pk_out, f.xw,
-                                         (kind & 2) ? f.xc : nullptr, st);
+  const int blocks = (f.npairs_pad + kPackPairs - 1) / kPackPairs;
+  const size_t smem = (size_t)src.count * kPackPairs * 6 * sizeof(float);
+  pack_kernel<<<blocks, 256, smem, s>>>(src, f.n, f.npairs_pad, f.pk_f4_per_pair, pk_out, (kind & 2) ? 1 : 0, st);
 }
 
 // ================================================================================================
@@ -223,13 +243,18 @@ struct HypRegs<false> {
   }
 };
 
-template <bool PACKED>
-__global__ void __launch_bounds__(kScoreThreads, 2)
+template <bool PACKED, int HPT, int TILE, int THREADS, int MINB, int SUB>
+__global__ void __launch_bounds__(THREADS, MINB)
 score3d_fast_kernel(const float4* __restrict__ pk, int npairs_pad, int pairs_per_cta, const HypFast* __restrict__ fast,
                     const HypGen* __restrict__ gen, int slot_begin, int slot_end, float thr, int32_t* __restrict__ votes,
-                    FrameStats* __restrict__ st, Worklist wl) {
-  __shared__ __align__(128) float4 tile[2][kTilePairs * 3];
-  __shared__ __align__(8) uint64_t bars[2];
+                    FrameStats* __restrict__ st, Worklist wl, int nosync) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float4(*tile)[TILE * 3] = reinterpret_cast<float4(*)[TILE * 3]>(smem_raw);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + 2 * TILE * 3 * sizeof(float4));
+  constexpr int kTilePairs = TILE;
+  constexpr int kHypPerThread = HPT;
+  constexpr int kScoreThreads = THREADS;
+  constexpr int kSubPairs = SUB;
 
   const int tid = threadIdx.x;
   const int p_begin = blockIdx.x * pairs_per_cta;
@@ -260,7 +285,7 @@ score3d_fast_kernel(const float4* __restrict__ pk, int npairs_pad, int pairs_per
   }
   __syncthreads();
   if (tid == 0) {
-    for (int t = 0; t < 2 && t < ntiles; ++t) {
+    for (int t = 0; t < (nosync ? 1 : 2) && t < ntiles; ++t) {
       const int tp = min(kTilePairs, npairs - t * kTilePairs);
       const uint32_t bytes = (uint32_t)tp * 48u;
       mbar_expect_tx(&bars[t], bytes);
@@ -269,8 +294,8 @@ score3d_fast_kernel(const float4* __restrict__ pk, int npairs_pad, int pairs_per
   }
 
   for (int t = 0; t < ntiles; ++t) {
-    const int buf = t & 1;
-    mbar_wait(&bars[buf], (uint32_t)((t >> 1) & 1));
+    const int buf = nosync ? 0 : (t & 1);
+    if (!nosync || t == 0) mbar_wait(&bars[buf], (uint32_t)((t >> 1) & 1));
     const int tp = min(kTilePairs, npairs - t * kTilePairs);
     const float4* sp = &tile[buf][0];
     for (int sub = 0; sub < tp; sub += kSubPairs) {
@@ -314,6 +339,7 @@ score3d_fast_kernel(const float4* __restrict__ pk, int npairs_pad, int pairs_per
         }
       }
     }
+    if (nosync) continue;
     __syncthreads();
     if (tid == 0 && t + 2 < ntiles) {
       const int tn = t + 2;
@@ -329,30 +355,67 @@ score3d_fast_kernel(const float4* __restrict__ pk, int npairs_pad, int pairs_per
 }
 
 static bool g_use_packed = true;
+static int g_nosync = 0;
+void set_nosync(int v) { g_nosync = v; }
+static int g_variant = 14;  // HPT=2, 1024-pair stages, 512 threads, 1 CTA per SM (best of the sweep in profiles/r01_variant_sweep.md)
 void set_use_packed(bool v) { g_use_packed = v; }
+void set_score_variant(int v) { g_variant = v; }
+
+template <bool PACKED, int HPT, int TILE, int THREADS, int MINB, int SUB>
+static void launch_variant(const FrameView& f, const HypGen* gen, const HypFast* fast, int slot_begin, int slot_end,
+                           Thresh th, int32_t* votes, FrameStats* st, Worklist wl, int num_sms, cudaStream_t s) {
+  const int nslots = slot_end - slot_begin;
+  const int hyp_per_cta = THREADS * HPT;
+  const int gy = (nslots + hyp_per_cta - 1) / hyp_per_cta;
+  // correspondences are handed out in groups of kSubPairs pairs (the pack pads to that), SUB divides into it
+  const int groups = f.npairs_pad / SUB;
+  int gx = (MINB * num_sms + gy - 1) / gy;  // aim at MINB resident CTAs per SM in total
+  if (gx < 1) gx = 1;
+  if (gx > groups) gx = groups;
+  const int groups_per_cta = (groups + gx - 1) / gx;
+  const int pairs_per_cta = groups_per_cta * SUB;
+  gx = (f.npairs_pad + pairs_per_cta - 1) / pairs_per_cta;
+  const size_t smem = 2 * (size_t)TILE * 3 * sizeof(float4) + 2 * sizeof(uint64_t);
+  auto kern = score3d_fast_kernel<PACKED, HPT, TILE, THREADS, MINB, SUB>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr_set = true;
+  }
+  kern<<<dim3(gx, gy), THREADS, smem, s>>>(f.pk, f.npairs_pad, pairs_per_cta, fast, gen, slot_begin, slot_end, th.thr3d,
+                                            votes, st, wl, g_nosync);
+}
 
 void launch_score_fast(int method, const FrameView& f, const HypGen* gen, const HypFast* fast, int slot_begin,
                        int slot_end, Thresh th, int32_t* votes, FrameStats* st, Worklist wl, int num_sms,
                        cudaStream_t s) {
   (void)method;
-  const int nslots = slot_end - slot_begin;
-  if (nslots <= 0 || f.n <= 0) return;
-  const int hyp_per_cta = kScoreThreads * kHypPerThread;
-  const int gy = (nslots + hyp_per_cta - 1) / hyp_per_cta;
-  const int groups = f.npairs_pad / kSubPairs;
-  int gx = (2 * num_sms + gy - 1) / gy;  // aim at 2 resident CTAs per SM in total
-  if (gx < 1) gx = 1;
-  if (gx > groups) gx = groups;
-  int groups_per_cta = (groups + gx - 1) / gx;
-  const int pairs_per_cta = groups_per_cta * kSubPairs;
-  gx = (f.npairs_pad + pairs_per_cta - 1) / pairs_per_cta;
-  dim3 grid(gx, gy);
-  if (g_use_packed)
-    score3d_fast_kernel<true><<<grid, kScoreThreads, 0, s>>>(f.pk, f.npairs_pad, pairs_per_cta, fast, gen, slot_begin,
-                                                            slot_end, th.thr3d, votes, st, wl);
-  else
-    score3d_fast_kernel<false><<<grid, kScoreThreads, 0, s>>>(f.pk, f.npairs_pad, pairs_per_cta, fast, gen, slot_begin,
-                                                             slot_end, th.thr3d, votes, st, wl);
+  if (slot_end - slot_begin <= 0 || f.n <= 0) return;
+#define RPE_V(P, H, T, TH, MB, SB) launch_variant<P, H, T, TH, MB, SB>(f, gen, fast, slot_begin, slot_end, th, votes, st, wl, num_sms, s)
+  if (!g_use_packed) {
+    RPE_V(false, 2, 256, 256, 2, 8);
+    return;
+  }
+  switch (g_variant) {
+    default:
+    case 0: RPE_V(true, 2, 256, 256, 2, 8); break;
+    case 1: RPE_V(true, 2, 512, 256, 2, 8); break;
+    case 2: RPE_V(true, 2, 256, 256, 3, 8); break;
+    case 3: RPE_V(true, 4, 256, 128, 3, 8); break;
+    case 4: RPE_V(true, 1, 256, 256, 4, 8); break;
+    case 5: RPE_V(true, 2, 512, 512, 1, 8); break;
+    case 6: RPE_V(true, 4, 256, 256, 1, 8); break;
+    case 7: RPE_V(true, 2, 256, 128, 4, 8); break;
+    case 8: RPE_V(true, 2, 256, 256, 2, 4); break;
+    case 9: RPE_V(true, 4, 256, 128, 4, 8); break;
+    case 10: RPE_V(true, 4, 256, 256, 2, 8); break;
+    case 11: RPE_V(true, 3, 256, 128, 4, 8); break;
+    case 12: RPE_V(true, 4, 512, 256, 2, 8); break;
+    case 13: RPE_V(true, 1, 512, 1024, 1, 8); break;
+    case 14: RPE_V(true, 2, 1024, 512, 1, 8); break;
+    case 15: RPE_V(true, 2, 512, 512, 1, 16); break;
+  }
+#undef RPE_V
 }
 
 // ================================================================================================

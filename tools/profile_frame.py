@@ -16,9 +16,13 @@ ap.add_argument("--n", type=int, default=307200)
 ap.add_argument("--hyp", type=int, default=1024)
 ap.add_argument("--packed", type=int, default=1)
 ap.add_argument("--gn-iters", type=int, default=3)
+ap.add_argument("--variant", type=int, default=14)
+ap.add_argument("--nosync", type=int, default=0)
 args = ap.parse_args()
 
 rpe.lib.rpe_debug_set_packed(args.packed)
+rpe.lib.rpe_debug_set_score_variant(args.variant)
+rpe.lib.rpe_debug_set_nosync(args.nosync)
 q, t = rpe.sim_pose(1000)
 Q, P, _ = rpe.sim_3d_3d(1001, q, t, args.n, noise=0.1, outlier_ratio=0.5)
 S = rpe.sample_table(1, args.n, 3, args.hyp)

@@ -1,0 +1,192 @@
+// Micro-benchmarks of the instruction forms the tiled scorer issues (sm_100a). Build:
+//   nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -o tools/ubench tools/ubench.cu
+#include <cstdio>
+#include <cuda_runtime.h>
+
+#define ITERS 4096
+
+template <int MODE>
+__global__ void __launch_bounds__(256) k(float* sink, const float* src, int iters) {
+  // hypothesis-like scalars and pair-like vectors, all in registers
+  float r[12];
+  for (int i = 0; i < 12; ++i) r[i] = src[i] + 1e-6f * threadIdx.x;
+  float2 X0 = make_float2(src[12], src[13]), X1 = make_float2(src[14], src[15]), X2 = make_float2(src[16], src[17]);
+  float2 P0 = make_float2(src[18], src[19]), P1 = make_float2(src[20], src[21]), P2 = make_float2(src[22], src[23]);
+  const float2 nlo = make_float2(-src[24], -src[24]);
+  const float band = src[25];
+  int cnt = 0;
+  bool flag = false;
+  float2 acc[8];
+  for (int i = 0; i < 8; ++i) acc[i] = make_float2(src[i], src[i + 1]);
+  for (int it = 0; it < iters; ++it) {
+    if (MODE == 0) {  // pure vector FFMA2, 8 independent chains, reused multiplicands
+#pragma unroll
+      for (int u = 0; u < 2; ++u)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = __ffma2_rn(acc[i], X0, P0);
+    } else if (MODE == 1) {  // scalar-broadcast multiplicand form, distinct scalars
+#pragma unroll
+      for (int u = 0; u < 2; ++u)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = __ffma2_rn(make_float2(r[i], r[i]), X0, acc[i]);
+    } else if (MODE == 2) {  // FADD2 only
+#pragma unroll
+      for (int u = 0; u < 2; ++u)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = __fadd2_rn(acc[i], make_float2(r[i], r[i]));
+    } else {  // MODE 3/4/5: the scorer's mix for 2 "pairs", FP only (3) / + LEA.HI count (4) / + FSETP flag too (5)
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        float2 e0 = __fadd2_rn(P0, make_float2(r[9], r[9]));
+        float2 e1 = __fadd2_rn(P1, make_float2(r[10], r[10]));
+        float2 e2 = __fadd2_rn(P2, make_float2(r[11], r[11]));
+        e0 = __ffma2_rn(make_float2(r[0], r[0]), X0, e0);
+        e1 = __ffma2_rn(make_float2(r[3], r[3]), X0, e1);
+        e2 = __ffma2_rn(make_float2(r[6], r[6]), X0, e2);
+        e0 = __ffma2_rn(make_float2(r[1], r[1]), X1, e0);
+        e1 = __ffma2_rn(make_float2(r[4], r[4]), X1, e1);
+        e2 = __ffma2_rn(make_float2(r[7], r[7]), X1, e2);
+        e0 = __ffma2_rn(make_float2(r[2], r[2]), X2, e0);
+        e1 = __ffma2_rn(make_float2(r[5], r[5]), X2, e1);
+        e2 = __ffma2_rn(make_float2(r[8], r[8]), X2, e2);
+        float2 s = __ffma2_rn(e0, e0, nlo);
+        s = __ffma2_rn(e1, e1, s);
+        s = __ffma2_rn(e2, e2, s);
+        if (MODE >= 4) cnt += (int)(__float_as_uint(s.x) >> 31) + (int)(__float_as_uint(s.y) >> 31);
+        if (MODE >= 5) flag = flag || (fabsf(s.x) <= band) || (fabsf(s.y) <= band);
+        // perturb the pair data so iterations are not loop-invariant (2 extra FADD2 per 15)
+        X0 = __fadd2_rn(X0, s);
+        P0 = __fadd2_rn(P0, e1);
+        if (MODE == 3) acc[0] = __fadd2_rn(acc[0], s);
+      }
+    }
+  }
+  float o = 0.f;
+  for (int i = 0; i < 8; ++i) o += acc[i].x + acc[i].y;
+  o += X0.x + P0.y + (float)cnt + (flag ? 1.f : 0.f);
+  if (o == 123.456f) sink[0] = o;
+}
+
+// MODE 6: the real data path — 3 broadcast LDS.128 per pair feeding two hypotheses held in registers
+__global__ void __launch_bounds__(256) k6(float* sink, const float* src, int iters) {
+  extern __shared__ float4 tile[];
+  for (int i = threadIdx.x; i < 256 * 3; i += blockDim.x) tile[i] = make_float4(src[i & 31], src[(i + 1) & 31], src[(i + 2) & 31], src[(i + 3) & 31]);
+  __syncthreads();
+  float r[2][12];
+  for (int h = 0; h < 2; ++h)
+    for (int i = 0; i < 12; ++i) r[h][i] = src[i + h] + 1e-6f * threadIdx.x;
+  const float2 nlo = make_float2(-src[24], -src[24]);
+  const float band = -src[25];  // never borderline in this experiment
+  int cnt[2] = {0, 0};
+  bool flag = false;
+  for (int it = 0; it < iters; ++it) {
+    const float4* sp = tile + (it & 31) * 8 * 3;
+#pragma unroll
+    for (int pp = 0; pp < 8; ++pp) {
+      const float4 a = sp[pp * 3], b = sp[pp * 3 + 1], c = sp[pp * 3 + 2];
+      const float2 X0 = make_float2(a.x, a.y), X1 = make_float2(a.z, a.w), X2 = make_float2(b.x, b.y);
+      const float2 P0 = make_float2(b.z, b.w), P1 = make_float2(c.x, c.y), P2 = make_float2(c.z, c.w);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        float2 e0 = __fadd2_rn(P0, make_float2(r[h][9], r[h][9]));
+        float2 e1 = __fadd2_rn(P1, make_float2(r[h][10], r[h][10]));
+        float2 e2 = __fadd2_rn(P2, make_float2(r[h][11], r[h][11]));
+        e0 = __ffma2_rn(make_float2(r[h][0], r[h][0]), X0, e0);
+        e1 = __ffma2_rn(make_float2(r[h][3], r[h][3]), X0, e1);
+        e2 = __ffma2_rn(make_float2(r[h][6], r[h][6]), X0, e2);
+        e0 = __ffma2_rn(make_float2(r[h][1], r[h][1]), X1, e0);
+        e1 = __ffma2_rn(make_float2(r[h][4], r[h][4]), X1, e1);
+        e2 = __ffma2_rn(make_float2(r[h][7], r[h][7]), X1, e2);
+        e0 = __ffma2_rn(make_float2(r[h][2], r[h][2]), X2, e0);
+        e1 = __ffma2_rn(make_float2(r[h][5], r[h][5]), X2, e1);
+        e2 = __ffma2_rn(make_float2(r[h][8], r[h][8]), X2, e2);
+        float2 s = __ffma2_rn(e0, e0, nlo);
+        s = __ffma2_rn(e1, e1, s);
+        s = __ffma2_rn(e2, e2, s);
+        cnt[h] += (int)(__float_as_uint(s.x) >> 31) + (int)(__float_as_uint(s.y) >> 31);
+        flag = flag || (fabsf(s.x) <= band) || (fabsf(s.y) <= band);
+      }
+    }
+    if (flag) {
+      sink[1] = 1.f;
+      flag = false;
+    }
+  }
+  if (cnt[0] + cnt[1] == 123456789) sink[0] = 1.f;
+}
+void run6(float* sink, float* src, int ctas_per_sm) {
+  cudaEvent_t a, b;
+  cudaEventCreate(&a);
+  cudaEventCreate(&b);
+  const size_t smem = (size_t)(220 * 1024 / ctas_per_sm) & ~(size_t)1023;
+  cudaFuncSetAttribute(k6, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const int blocks = 148 * ctas_per_sm, iters = 256;
+  k6<<<blocks, 256, smem>>>(sink, src, iters);
+  cudaEventRecord(a);
+  k6<<<blocks, 256, smem>>>(sink, src, iters);
+  cudaEventRecord(b);
+  cudaEventSynchronize(b);
+  float ms;
+  cudaEventElapsedTime(&ms, a, b);
+  const double inst = (double)blocks * 256 * iters * 8 * 2 * 15;
+  printf("%-32s %d CTA/SM (%2d warps/SM) %8.3f ms = %6.2f T lane-ops/s (%.0f%% of 37.2)\n", "smem-fed scorer loop (15 FP2/unit)", ctas_per_sm,
+         8 * ctas_per_sm, ms, 2 * inst / ms / 1e9, 2 * inst / ms / 1e9 / 37.22 * 100);
+}
+
+template <int MODE>
+void run_occ(const char* name, double fp2_per_iter, float* sink, float* src, int ctas_per_sm) {
+  cudaEvent_t a, b;
+  cudaEventCreate(&a);
+  cudaEventCreate(&b);
+  const size_t smem = (size_t)(220 * 1024 / ctas_per_sm) & ~(size_t)1023;  // forces <= ctas_per_sm resident CTAs
+  cudaFuncSetAttribute(k<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const int blocks = 148 * ctas_per_sm;
+  k<MODE><<<blocks, 256, smem>>>(sink, src, ITERS);
+  cudaEventRecord(a);
+  k<MODE><<<blocks, 256, smem>>>(sink, src, ITERS);
+  cudaEventRecord(b);
+  cudaEventSynchronize(b);
+  float ms;
+  cudaEventElapsedTime(&ms, a, b);
+  const double inst = (double)blocks * 256 * ITERS * fp2_per_iter;
+  printf("%-32s %d CTA/SM (%2d warps/SM) %8.3f ms = %6.2f T lane-ops/s (%.0f%% of 37.2)\n", name, ctas_per_sm, 8 * ctas_per_sm, ms,
+         2 * inst / ms / 1e9, 2 * inst / ms / 1e9 / 37.22 * 100);
+}
+
+template <int MODE>
+void run(const char* name, double fp2_per_iter, float* sink, float* src) {
+  cudaEvent_t a, b;
+  cudaEventCreate(&a);
+  cudaEventCreate(&b);
+  const int blocks = 148 * 8;
+  k<MODE><<<blocks, 256>>>(sink, src, ITERS);
+  cudaEventRecord(a);
+  k<MODE><<<blocks, 256>>>(sink, src, ITERS);
+  cudaEventRecord(b);
+  cudaEventSynchronize(b);
+  float ms;
+  cudaEventElapsedTime(&ms, a, b);
+  const double inst = (double)blocks * 256 * ITERS * fp2_per_iter;  // thread-level FP2 instructions
+  // one FP2 thread-instruction = 2 lane-ops; peak = 148 SM * 128 lanes * clk
+  printf("%-40s %8.3f ms  %7.2f G FP2-thread-inst/s  = %6.2f T lane-ops/s\n", name, ms, inst / ms / 1e6, 2 * inst / ms / 1e9);
+}
+
+int main() {
+  float *sink, *src;
+  cudaMalloc(&sink, 64);
+  cudaMalloc(&src, 256);
+  float h[64];
+  for (int i = 0; i < 64; ++i) h[i] = 0.001f * (i + 1);
+  cudaMemcpy(src, h, sizeof(h), cudaMemcpyHostToDevice);
+  run<0>("FFMA2 vector, reused operands", 16, sink, src);
+  run<1>("FFMA2 scalar-broadcast multiplicand", 16, sink, src);
+  run<2>("FADD2 scalar-broadcast addend", 16, sink, src);
+  run<3>("scorer mix FP only (17 FP2/unit)", 2 * 18, sink, src);
+  run<4>("scorer mix + sign-bit count", 2 * 17, sink, src);
+  run<5>("scorer mix + count + band flag", 2 * 17, sink, src);
+  for (int c : {1, 2, 3, 4, 6, 8}) run_occ<5>("scorer mix + count + flag", 2 * 17, sink, src, c);
+  for (int c : {1, 2, 4, 8}) run_occ<0>("FFMA2 vector reused", 16, sink, src, c);
+  for (int c : {1, 2, 4}) run6(sink, src, c);
+  printf("peak lane-ops/s at 1.965 GHz: %.2f T\n", 148 * 128 * 1.965e9 / 1e12);
+  return 0;
+}
