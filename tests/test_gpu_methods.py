@@ -1,0 +1,155 @@
+"""GPU parity for the 2-D / hybrid / normal-aware estimator families through the C-ABI.
+
+Reference paths: kneip_ransac (P3P.hpp:320-392), kneip_prosac's scoring form (:439-453),
+shinji_kneip_ransac (AbsoluteOrientation.hpp:367-438), nl_kneip_ransac / nl_shinji_ransac /
+nl_shinji_kneip_ransac (AbsoluteOrientationNormal.hpp:215-445), on Simulator.hpp:316-367 inputs.
+Bars: generated hypotheses (Kneip P3P + Ferrari quartic, shinji, nl_2p) BIT-IDENTICAL to the oracle in DET
+math mode; vote tables, winner, final Iter, masks and per-column counts identical; LM refinement within
+1e-6 rad / 1e-6 x scale of its CPU twin.
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+NAMES = {1: "kneip", 2: "shinji_kneip", 3: "nl_kneip", 4: "nl_shinji", 5: "nl_shinji_kneip", 6: "kneip_quat"}
+F = 585.0
+
+
+def _data(rpe, seed, n, **kw):
+    q, t = rpe.sim_pose(seed)
+    d = rpe.sim_2d_3d_nl(seed + 1, q, t, n, **kw)
+    return q, t, {k: d[k] for k in ("bv", "xc", "nc", "xw", "nw")}, d["weights"]
+
+
+def _thr(thr2d_px=8.0, thrn=0.1, thr3d=0.2):
+    return dict(thr3d=thr3d, cos_thr=float(np.cos(np.arctan(np.float32(thr2d_px) / np.float32(F)))),
+                cos_nl=float(np.cos(np.float32(thrn))))
+
+
+def _angle(qa, qb):
+    a = np.asarray(qa, np.float64) / np.linalg.norm(np.asarray(qa, np.float64))
+    b = np.asarray(qb, np.float64) / np.linalg.norm(np.asarray(qb, np.float64))
+    av, aw, bv, bw = a[:3], a[3], -b[:3], b[3]
+    w = aw * bw - np.dot(av, bv)
+    v = aw * bv + bw * av + np.cross(av, bv)
+    return 2.0 * np.arctan2(np.linalg.norm(v), abs(w))
+
+
+@pytest.mark.parametrize("method", [1, 2, 3, 4, 5, 6])
+@pytest.mark.parametrize("n,H,seed", [(800, 512, 3), (5001, 300, 5)])
+def test_generation_bit_exact(rpe, orc, gpu_ctx, method, n, H, seed):
+    orc.set_math_mode(orc.DET)
+    q, t, arrs, _ = _data(rpe, seed + 10 * method, n)
+    S = rpe.sample_table(seed, n, 4, H)
+    th = _thr()
+    ref = orc.ransac(method, S, confidence=0.99, full=True, **th, **arrs)
+    gpu_ctx.upload(**arrs)
+    ns = gpu_ctx.generate(method, S)
+    hyps, valid = gpu_ctx.get_hypotheses(ns)
+    assert np.array_equal(valid, (ref["votes"] >= 0).astype(np.int32))
+    sel = valid == 1
+    assert sel.sum() > H // 2
+    same = hyps[sel].view(np.uint32) == ref["hyps"][sel].view(np.uint32)
+    assert same.all(), f"{(~same.all(axis=1)).sum()} of {sel.sum()} hypotheses differ in some bit"
+
+
+@pytest.mark.parametrize("method", [1, 2, 3, 4, 5, 6])
+@pytest.mark.parametrize("n,H,seed,kw", [
+    (800, 512, 3, {}),
+    (5001, 300, 5, dict(n2d=2.0, or2d=0.5, n3d=0.1, or3d=0.5, nnl=float(np.deg2rad(4.0)), ornl=0.5)),
+    (64, 100, 7, dict(or2d=0.0, or3d=0.0, ornl=0.0)),
+])
+def test_ransac_identical_to_oracle(rpe, orc, gpu_ctx, method, n, H, seed, kw):
+    orc.set_math_mode(orc.DET)
+    q, t, arrs, _ = _data(rpe, seed + 10 * method, n, **kw)
+    S = rpe.sample_table(seed, n, 4, H)
+    th = _thr()
+    ref = orc.ransac(method, S, confidence=0.99, full=True, **th, **arrs)
+    gpu_ctx.upload(**arrs)
+    got = gpu_ctx.ransac(method, S, thr3d=th["thr3d"], cos_thr2d=th["cos_thr"], cos_thrN=th["cos_nl"], confidence=0.99)
+    votes = gpu_ctx.get_votes(ref["votes"].shape[0])
+    assert np.array_equal(votes, ref["votes"]), f"votes differ at {np.nonzero(votes != ref['votes'])[0][:10]}"
+    for k in ("winner", "max_votes", "iter_final"):
+        assert got[k] == ref[k], k
+    assert np.array_equal(got["q"].view(np.uint32), ref["q"].view(np.uint32))
+    assert np.array_equal(got["t"].view(np.uint32), ref["t"].view(np.uint32))
+    assert np.array_equal(got["mask"], ref["mask"])
+    assert got["n_inliers"][:got["mask"].shape[0]] == [int(v) for v in ref["mask"].sum(axis=1)]
+    assert sum(got["n_inliers"]) == ref["max_votes"]
+
+
+def test_config2_pnp_10k_70pct_outliers(rpe, orc, gpu_ctx):
+    """BASELINE.json config #2: P3P RANSAC on 10k 2-D/3-D correspondences, 70 % outliers, then LM refinement."""
+    orc.set_math_mode(orc.DET)
+    n, H = 10000, 1024
+    q, t = rpe.sim_pose(101)
+    Q, U, P, _ = rpe.sim_2d_3d(102, q, t, n, noise_px=1.0, outlier_ratio=0.7)
+    S = rpe.sample_table(1, n, 4, H)
+    th = _thr(thr2d_px=8.0)
+    ref = orc.ransac(1, S, confidence=0.99, full=True, cos_thr=th["cos_thr"], bv=U, xw=Q)
+    gpu_ctx.upload(bv=U, xw=Q)
+    got = gpu_ctx.ransac("kneip", S, cos_thr2d=th["cos_thr"], confidence=0.99)
+    assert np.array_equal(gpu_ctx.get_votes(H), ref["votes"])
+    assert got["winner"] == ref["winner"] and got["iter_final"] == ref["iter_final"] and got["max_votes"] == ref["max_votes"]
+    assert np.array_equal(got["mask"], ref["mask"])
+    assert 0.25 * n < got["max_votes"] < 0.35 * n
+    twin_q, twin_t, info = orc.refine_gn(got["q"], got["t"], got["mask"], max_iters=8, bv=U, xw=Q)
+    fit = gpu_ctx.refit("gn", max_iters=8)
+    assert fit["refit_ok"] == 1
+    assert _angle(fit["q"], twin_q) < 1e-6
+    assert np.abs(fit["t"].astype(np.float64) - twin_t.astype(np.float64)).max() < 1e-6 * 10.0
+    assert _angle(fit["q"], q) < _angle(got["q"], q) + 1e-4  # refinement does not move away from ground truth
+    assert _angle(fit["q"], q) < 5e-3
+
+
+def test_config3_normal_ao_50k_int32_indices(rpe, orc, gpu_ctx):
+    """BASELINE.json config #3: 50 000 correspondences with 2-D/3-D/normal residuals. The reference's `short` index
+    loops break above 32 767 (PnPPoseAdapter.hpp:232); masks here cover all 50 000 rows."""
+    orc.set_math_mode(orc.DET)
+    n, H = 50000, 256
+    q, t, arrs, _ = _data(rpe, 201, n, n2d=1.0, or2d=0.3, n3d=0.05, or3d=0.3, nnl=float(np.deg2rad(2.0)), ornl=0.3)
+    S = rpe.sample_table(1, n, 4, H)
+    th = _thr()
+    ref = orc.ransac(5, S, confidence=0.99, full=True, **th, **arrs)
+    gpu_ctx.upload(**arrs)
+    got = gpu_ctx.ransac("nl_shinji_kneip", S, thr3d=th["thr3d"], cos_thr2d=th["cos_thr"], cos_thrN=th["cos_nl"],
+                         confidence=0.99)
+    assert np.array_equal(gpu_ctx.get_votes(3 * H), ref["votes"])
+    assert got["winner"] == ref["winner"] and got["iter_final"] == ref["iter_final"]
+    assert np.array_equal(got["mask"], ref["mask"])
+    assert got["mask"][:, 40000:].sum() > 1000  # rows beyond the reference's short range carry inliers
+    twin_q, twin_t, info = orc.refine_gn(got["q"], got["t"], got["mask"], max_iters=8, **arrs)
+    fit = gpu_ctx.refit("gn", max_iters=8)
+    assert _angle(fit["q"], twin_q) < 1e-6
+    assert np.abs(fit["t"].astype(np.float64) - twin_t.astype(np.float64)).max() < 1e-6 * 10.0
+    assert _angle(fit["q"], q) < 2e-3
+
+
+def test_prosac_tables_feed_the_same_kernels(rpe, orc, gpu_ctx):
+    """kneip_prosac / shinji_kneip_prosac differ from the RANSAC variants only by the sample table
+    (Utility.hpp:161-250) — and, for kneip_prosac, by the quaternion-form rotation in scoring (P3P.hpp:442)."""
+    orc.set_math_mode(orc.DET)
+    n, H = 2000, 400
+    q, t, arrs, W = _data(rpe, 301, n)
+    th = _thr()
+    S = rpe.prosac_table(1, n, 4, H, W[0])
+    S = np.minimum(S, n - 1)  # the reference's sampler can emit index n (Utility.hpp:238): clamp for the test
+    for method in (6, 2):
+        ref = orc.ransac(method, S, confidence=0.99, full=True, **th, **arrs)
+        gpu_ctx.upload(**arrs)
+        got = gpu_ctx.ransac(method, S, thr3d=th["thr3d"], cos_thr2d=th["cos_thr"], cos_thrN=th["cos_nl"], confidence=0.99)
+        assert np.array_equal(gpu_ctx.get_votes(ref["votes"].shape[0]), ref["votes"])
+        assert got["winner"] == ref["winner"] and got["iter_final"] == ref["iter_final"]
+        assert np.array_equal(got["mask"], ref["mask"])
+
+
+def test_missing_modality_is_an_error(rpe, gpu_ctx):
+    q, t = rpe.sim_pose(1)
+    Q, P, _ = rpe.sim_3d_3d(2, q, t, 100)
+    gpu_ctx.upload(xc=P, xw=Q)
+    S = rpe.sample_table(1, 100, 4, 10)
+    with pytest.raises(rpe.RpeError):
+        gpu_ctx.ransac("kneip", S, cos_thr2d=0.999)
+    with pytest.raises(rpe.RpeError):
+        gpu_ctx.ransac("nl_shinji", S, thr3d=0.1, cos_thrN=0.99)
