@@ -58,6 +58,9 @@ struct rpe_ctx {
   int32_t* d_samples = nullptr;
 
   FrameStats* d_stats = nullptr;
+  bool stats_clean = true;       // per-pass counters are zero (the replay kernel leaves them so)
+  ReplayState* d_rs = nullptr;
+  ReplayState* h_rs = nullptr;   // pinned
   ReplayOut* d_pose = nullptr;    // current pose = the adapter's (R_cw, t_w, max_votes) state
   ReplayOut* d_kabsch = nullptr;  // Kabsch refit computed by the mask kernel's last CTA
   ReplayOut* h_pose = nullptr;    // pinned, kNumStaging slots; [0] doubles as scratch for set_pose
@@ -308,13 +311,13 @@ int score_range(rpe_ctx* ctx, int method, int slot_begin, int slot_end, Thresh t
   return RPE_OK;
 }
 
-int do_finish(rpe_ctx* ctx, int method, int H, Thresh th, float confidence, rpe_result* out, int16_t* mask, bool blocking) {
+// mask of the accepted hypothesis (+ fused Kabsch), result and mask copies. The replay must already be enqueued.
+int do_finish(rpe_ctx* ctx, int method, Thresh th, rpe_result* out, int16_t* mask, bool blocking) {
   FrameView f = make_view(ctx);
-  launch_replay(method, ctx->d_gen, ctx->d_votes, H, ctx->n, confidence, ctx->d_stats, ctx->d_pose, ctx->stream);
   stamp(ctx, ST_MASK);
   ctx->mask_cols = method_mask_cols(method);
   launch_mask(method, f, ctx->d_pose, th, ctx->d_mask, ctx->d_kabsch, ctx->rb, ctx->d_stats, ctx->stream);
-  ctx->launches += 2;
+  ctx->launches += 1;
   ctx->kabsch_valid = method_uses_3d(method);
   ctx->last_th = th;
   stamp(ctx, ST_GN);
@@ -333,6 +336,8 @@ int do_finish(rpe_ctx* ctx, int method, int H, Thresh th, float confidence, rpe_
   return RPE_OK;
 }
 
+constexpr int kMaxPassIters = 8192;  // iterations generated + scored per device pass
+
 int do_ransac(rpe_ctx* ctx, int method, const int32_t* samples, int H, float thr3d, float cos_thr2d, float cos_thrN,
               float confidence, rpe_result* out, int16_t* mask, bool blocking) {
   if (!ctx) return RPE_ERR_ARG;
@@ -341,41 +346,68 @@ int do_ransac(rpe_ctx* ctx, int method, const int32_t* samples, int H, float thr
   if (rc) return rc;
   CK(cudaSetDevice(ctx->device));
   const int S = method_slots(method);
-  rc = ensure_hyp_capacity(ctx, H, H * S);
-  if (rc) return rc;
   const Thresh th = {thr3d, cos_thr2d, cos_thrN};
   if (!ctx->upload_stamped) stamp(ctx, ST_UPLOAD);
   ctx->upload_stamped = false;
-  // sample table: device pointers are used in place; host memory is copied on the stream (pageable
-  // memory is staged by the driver before the call returns, page-locked memory must stay alive until rpe_sync)
-  const int32_t* samples_dev = ctx->d_samples;
+  const int pass = H < kMaxPassIters ? H : kMaxPassIters;
+  rc = ensure_hyp_capacity(ctx, pass, pass * S);
+  if (rc) return rc;
+  // sample table: device pointers are used in place; host memory is copied on the stream (pageable memory is
+  // staged by the driver before the call returns, page-locked memory must stay alive until rpe_sync)
+  bool samples_on_device = false;
   {
     cudaPointerAttributes attr;
     const cudaError_t pe = cudaPointerGetAttributes(&attr, samples);
     if (pe != cudaSuccess) (void)cudaGetLastError();
-    if (pe == cudaSuccess && (attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged)) {
-      samples_dev = samples;
-    } else {
-      CK(cudaMemcpyAsync(ctx->d_samples, samples, (size_t)H * 4 * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
-    }
+    samples_on_device = pe == cudaSuccess && (attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged);
   }
-  launch_reset_stats(ctx->d_stats, ctx->stream);
+  if (!ctx->stats_clean) {
+    launch_reset_stats(ctx->d_stats, ctx->stream);
+    ctx->launches++;
+  }
+  launch_replay_begin(ctx->d_rs, H, ctx->stream);
   ctx->launches++;
   if (method == RPE_SHINJI) {
     rc = ensure_packed(ctx, kind_for_method(method));
     if (rc) return rc;
   }
-  stamp(ctx, ST_GEN);
-  FrameView f = make_view(ctx);
-  launch_hypgen(method, f, samples_dev, H, ctx->d_gen, ctx->d_fast, ctx->d_votes, ctx->d_stats, ctx->stream);
-  ctx->launches++;
-  ctx->n_slots = H * S;
-  ctx->cur_method = method;
-  stamp(ctx, ST_SCORE);
-  rc = score_range(ctx, method, 0, H * S, th);
-  if (rc) return rc;
-  stamp(ctx, ST_REPLAY);
-  return do_finish(ctx, method, H, th, confidence, out, mask, blocking);
+  const bool single = H <= pass;
+  for (int base = 0; base < H; base += pass) {
+    const int hc = (H - base) < pass ? (H - base) : pass;
+    const int32_t* chunk = samples + (size_t)base * 4;
+    const int32_t* samples_dev = chunk;
+    if (!samples_on_device) {
+      CK(cudaMemcpyAsync(ctx->d_samples, chunk, (size_t)hc * 4 * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+      samples_dev = ctx->d_samples;
+    }
+    if (base == 0) stamp(ctx, ST_GEN);
+    FrameView f = make_view(ctx);
+    launch_hypgen(method, f, samples_dev, hc, ctx->d_gen, ctx->d_fast, ctx->d_votes, ctx->d_stats, ctx->stream);
+    ctx->launches++;
+    ctx->n_slots = hc * S;
+    ctx->cur_method = method;
+    if (base == 0) stamp(ctx, ST_SCORE);
+    rc = score_range(ctx, method, 0, hc * S, th);
+    if (rc) return rc;
+    if (base == 0) stamp(ctx, ST_REPLAY);
+    launch_replay(method, ctx->d_gen, ctx->d_votes, hc, base, ctx->n, confidence, ctx->d_stats, ctx->d_rs, ctx->d_pose,
+                  single, ctx->stream);
+    ctx->launches++;
+    ctx->stats_clean = true;
+    if (!single) {
+      // the caller's Iter exceeds one pass: look at the adaptive bound before generating more hypotheses
+      CK(cudaMemcpyAsync(ctx->h_rs, ctx->d_rs, sizeof(ReplayState), cudaMemcpyDeviceToHost, ctx->stream));
+      CK(cudaStreamSynchronize(ctx->stream));
+      const bool last = ctx->h_rs->stop != 0 || base + hc >= H;
+      if (last) {
+        launch_replay(method, ctx->d_gen, ctx->d_votes, 0, base + hc, ctx->n, confidence, ctx->d_stats, ctx->d_rs,
+                      ctx->d_pose, true, ctx->stream);
+        ctx->launches++;
+        break;
+      }
+    }
+  }
+  return do_finish(ctx, method, th, out, mask, blocking);
 }
 
 }  // namespace
@@ -441,6 +473,8 @@ static int create_common(int device, void* stream, bool own, rpe_ctx** out) {
   bool ok = true;
   ok = ok && cudaMalloc(&ctx->d_stats, sizeof(FrameStats)) == cudaSuccess;
   ok = ok && cudaMalloc(&ctx->d_pose, sizeof(ReplayOut)) == cudaSuccess;
+  ok = ok && cudaMalloc(&ctx->d_rs, sizeof(ReplayState)) == cudaSuccess;
+  ok = ok && cudaMallocHost(&ctx->h_rs, sizeof(ReplayState)) == cudaSuccess;
   ok = ok && cudaMalloc(&ctx->d_kabsch, sizeof(ReplayOut)) == cudaSuccess;
   ok = ok && cudaMallocHost(&ctx->h_pose, kNumStaging * sizeof(ReplayOut)) == cudaSuccess;
   ok = ok && cudaMalloc(&ctx->rb.moments, kMomentCount * sizeof(double)) == cudaSuccess;
@@ -491,6 +525,8 @@ int rpe_destroy(rpe_ctx* ctx) {
   cudaFree(ctx->d_samples);
   cudaFree(ctx->d_stats);
   cudaFree(ctx->d_pose);
+  cudaFree(ctx->d_rs);
+  if (ctx->h_rs) cudaFreeHost(ctx->h_rs);
   cudaFree(ctx->d_kabsch);
   if (ctx->h_pose) cudaFreeHost(ctx->h_pose);
   cudaFree(ctx->wl.entries);
@@ -687,6 +723,7 @@ int rpe_generate(rpe_ctx* ctx, int method, const int32_t* samples, int H) {
   ctx->launches += 2;
   ctx->n_slots = H * S;
   ctx->cur_method = method;
+  ctx->stats_clean = false;
   return RPE_OK;  // asynchronous; rpe_get_hypotheses / rpe_get_votes / rpe_finish synchronise
 }
 
@@ -725,6 +762,7 @@ int rpe_set_hypotheses(rpe_ctx* ctx, int method, const float* hyps, const int32_
   CK(cudaStreamSynchronize(ctx->stream));
   ctx->n_slots = n_slots;
   ctx->cur_method = method;
+  ctx->stats_clean = false;
   return RPE_OK;
 }
 
@@ -743,6 +781,7 @@ int rpe_score(rpe_ctx* ctx, int method, int slot_begin, int slot_end, float thr3
   stamp(ctx, ST_SCORE);
   rc = score_range(ctx, method, slot_begin, slot_end, th);
   stamp(ctx, ST_REPLAY);
+  ctx->stats_clean = false;
   return rc;
 }
 
@@ -769,7 +808,12 @@ int rpe_finish(rpe_ctx* ctx, int method, int H, float thr3d, float cos_thr2d, fl
     return fail(ctx, RPE_ERR_ARG, "bad argument to rpe_finish");
   CK(cudaSetDevice(ctx->device));
   const Thresh th = {thr3d, cos_thr2d, cos_thrN};
-  return do_finish(ctx, method, H, th, confidence, out, mask, true);
+  launch_replay_begin(ctx->d_rs, H, ctx->stream);
+  launch_replay(method, ctx->d_gen, ctx->d_votes, H, 0, ctx->n, confidence, ctx->d_stats, ctx->d_rs, ctx->d_pose, true,
+                ctx->stream);
+  ctx->launches += 2;
+  ctx->stats_clean = true;
+  return do_finish(ctx, method, th, out, mask, true);
 }
 
 // ---- Library.cpp shim -----------------------------------------------------------------------------

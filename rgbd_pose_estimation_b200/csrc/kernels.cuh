@@ -56,8 +56,11 @@ void launch_score_exact(int method, const FrameView& f, const HypGen* gen, int s
                         int32_t* votes, FrameStats* st, bool only_if_overflow, int num_sms, cudaStream_t s);
 
 // -- replay / mask / refit --------------------------------------------------------------------------
-void launch_replay(int method, const HypGen* gen, const int32_t* votes, int H, int n, float confidence,
-                   const FrameStats* st, ReplayOut* out, cudaStream_t s);
+// Replay of the sequential rule over the iterations [iter_base, iter_base+H) held in gen/votes; the state is
+// carried in `rs` (launch_replay_begin resets it). The kernel also clears the per-pass FrameStats counters.
+void launch_replay_begin(ReplayState* rs, int iter_max, cudaStream_t s);
+void launch_replay(int method, const HypGen* gen, const int32_t* votes, int H, int iter_base, int n, float confidence,
+                   FrameStats* st, ReplayState* rs, ReplayOut* out, bool finalize, cudaStream_t s);
 
 struct RefitBuffers {
   double* partials;   // [blocks x kMomentCount]

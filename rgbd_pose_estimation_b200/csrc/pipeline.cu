@@ -156,9 +156,12 @@ void launch_derive_fast(const HypGen* gen, HypFast* fast, int32_t* votes, int n_
 // replay of the sequential rule (one warp; all lanes run the scalar part redundantly)
 // ================================================================================================
 constexpr int kReplayChunk = 4096;  // vote-table entries staged in shared memory per pass
+// votes/gen hold the H iterations [iter_base, iter_base + H) of this device pass; `rs` carries the sequential
+// state between passes. With `finalize` the accepted hypothesis is published to `out`.
 __global__ void __launch_bounds__(256)
-replay_kernel(int method, const HypGen* __restrict__ gen, const int32_t* __restrict__ votes, int H, int n,
-              float confidence, const FrameStats* __restrict__ st, ReplayOut* __restrict__ out) {
+replay_kernel(int method, const HypGen* __restrict__ gen, const int32_t* __restrict__ votes, int H, int iter_base, int n,
+              float confidence, FrameStats* __restrict__ st, ReplayState* __restrict__ rs, ReplayOut* __restrict__ out,
+              int finalize) {
   __shared__ int32_t sv[kReplayChunk];
   __shared__ int s_state[5];  // best, Iter, win, cur_iter, stop
   const int lane = threadIdx.x & 31;
@@ -166,12 +169,13 @@ replay_kernel(int method, const HypGen* __restrict__ gen, const int32_t* __restr
   const int K = method_model_points(method);
   const int mod = method_modalities(method);
   const int E = H * S;
+  const int slot_base = iter_base * S;
   if (threadIdx.x == 0) {
-    s_state[0] = -1;
-    s_state[1] = H;
-    s_state[2] = -1;
-    s_state[3] = -1;
-    s_state[4] = 0;
+    s_state[0] = rs->best;
+    s_state[1] = rs->iter;
+    s_state[2] = rs->win;
+    s_state[3] = rs->cur_iter;
+    s_state[4] = rs->stop;
   }
   __syncthreads();
   for (int cbase = 0; cbase < E; cbase += kReplayChunk) {
@@ -204,7 +208,7 @@ replay_kernel(int method, const HypGen* __restrict__ gen, const int32_t* __restr
         while (m) {
           const int b = __ffs(m) - 1;
           m &= m - 1;
-          const int idx = cbase + base + b;
+          const int idx = slot_base + cbase + base + b;  // global slot index
           const int it = idx / S;
           const int vb = __shfl_sync(0xffffffffu, v, b);
           if (it != cur_iter) {
@@ -221,7 +225,8 @@ replay_kernel(int method, const HypGen* __restrict__ gen, const int32_t* __restr
           rb_.log_denom = __shfl_sync(0xffffffffu, rd.log_denom, b);
           Iter = rule_finish(log_num, rb_, Iter);
         }
-        if ((long long)(cbase + base + 32) >= (long long)Iter * S) stop = true;  // nothing below the loop bound is left
+        // nothing below the loop bound is left in (or after) this pass
+        if ((long long)(slot_base + cbase + base + 32) >= (long long)Iter * S) stop = true;
       }
       if (lane == 0) {
         s_state[0] = best;
@@ -234,30 +239,66 @@ replay_kernel(int method, const HypGen* __restrict__ gen, const int32_t* __restr
     __syncthreads();
   }
   if (threadIdx.x == 0) {
-    const int best = s_state[0], Iter = s_state[1], win = s_state[2];
-    if (win >= 0) {
-      const HypGen g = gen[win];
-      for (int k = 0; k < 4; ++k) out->q[k] = g.q[k];
-      for (int k = 0; k < 3; ++k) out->t[k] = g.t[k];
-    } else {
-      out->q[0] = out->q[1] = out->q[2] = 0.f;
-      out->q[3] = 1.f;
-      out->t[0] = out->t[1] = out->t[2] = 0.f;
+    const int win = s_state[2];
+    if (win >= slot_base && win != rs->win) {  // accepted in this pass: keep its pose
+      const HypGen g = gen[win - slot_base];
+      for (int k = 0; k < 4; ++k) rs->q[k] = g.q[k];
+      for (int k = 0; k < 3; ++k) rs->t[k] = g.t[k];
     }
-    out->max_votes = best;
-    out->iter_final = Iter;
-    out->winner = win;
-    out->n_slots = E;
-    out->n_borderline = (int)st->wl_count;
-    out->flags = st->wl_overflow ? 1 : 0;
-    out->n_inliers[0] = out->n_inliers[1] = out->n_inliers[2] = 0;
-    out->refit_ok = 0;
+    rs->best = s_state[0];
+    rs->iter = s_state[1];
+    rs->win = win;
+    rs->cur_iter = s_state[3];
+    rs->stop = s_state[4] || ((long long)(slot_base + E) >= (long long)s_state[1] * S) ? 1 : 0;
+    rs->slots_done += E;
+    rs->borderline += (int)st->wl_count;
+    rs->overflow |= st->wl_overflow ? 1 : 0;
+    // per-pass counters are consumed: leave them clean for the next pass / frame
+    st->t_max_bits = 0;
+    st->wl_count = 0;
+    st->wl_overflow = 0;
+    st->ticket = 0;
+    st->ticket2 = 0;
+    if (finalize) {
+      if (win >= 0) {
+        for (int k = 0; k < 4; ++k) out->q[k] = rs->q[k];
+        for (int k = 0; k < 3; ++k) out->t[k] = rs->t[k];
+      } else {
+        out->q[0] = out->q[1] = out->q[2] = 0.f;
+        out->q[3] = 1.f;
+        out->t[0] = out->t[1] = out->t[2] = 0.f;
+      }
+      out->max_votes = rs->best;
+      out->iter_final = rs->iter;
+      out->winner = win;
+      out->n_slots = rs->slots_done;
+      out->n_borderline = rs->borderline;
+      out->flags = rs->overflow ? 1 : 0;
+      out->n_inliers[0] = out->n_inliers[1] = out->n_inliers[2] = 0;
+      out->refit_ok = 0;
+    }
   }
 }
 
-void launch_replay(int method, const HypGen* gen, const int32_t* votes, int H, int n, float confidence,
-                   const FrameStats* st, ReplayOut* out, cudaStream_t s) {
-  replay_kernel<<<1, 256, 0, s>>>(method, gen, votes, H, n, confidence, st, out);
+__global__ void replay_begin_kernel(ReplayState* rs, int iter_max) {
+  if (threadIdx.x != 0) return;
+  rs->best = -1;  // setMaxVotes(-1)
+  rs->iter = iter_max;
+  rs->win = -1;
+  rs->cur_iter = -1;
+  rs->stop = 0;
+  rs->slots_done = 0;
+  rs->borderline = 0;
+  rs->overflow = 0;
+  rs->q[0] = rs->q[1] = rs->q[2] = 0.f;
+  rs->q[3] = 1.f;
+  rs->t[0] = rs->t[1] = rs->t[2] = 0.f;
+}
+void launch_replay_begin(ReplayState* rs, int iter_max, cudaStream_t s) { replay_begin_kernel<<<1, 32, 0, s>>>(rs, iter_max); }
+
+void launch_replay(int method, const HypGen* gen, const int32_t* votes, int H, int iter_base, int n, float confidence,
+                   FrameStats* st, ReplayState* rs, ReplayOut* out, bool finalize, cudaStream_t s) {
+  replay_kernel<<<1, 256, 0, s>>>(method, gen, votes, H, iter_base, n, confidence, st, rs, out, finalize ? 1 : 0);
 }
 
 // ================================================================================================

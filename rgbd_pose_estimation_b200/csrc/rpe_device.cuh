@@ -101,6 +101,22 @@ struct ReplayOut {  // written by the replay kernel, read by mask/refit kernels 
   int32_t refit_ok;
 };
 
+// Sequential state of the keep-best / adaptive-stop rule, carried across chunks of iterations when the
+// caller's Iter is larger than one device pass (e.g. SimpleMain.cpp's 100 000).
+struct ReplayState {
+  int32_t best;      // adapter.getMaxVotes()
+  int32_t iter;      // current `Iter`
+  int32_t win;       // global slot index of the accepted hypothesis
+  int32_t cur_iter;  // iteration of the last accepted record
+  int32_t stop;      // the `ii < Iter` loop has ended
+  int32_t slots_done;
+  int32_t borderline;
+  int32_t overflow;
+  float q[4];
+  float t[3];
+  int32_t pad;
+};
+
 // ---- exact-order primitives ------------------------------------------------------------------
 struct F3 {
   float x, y, z;
