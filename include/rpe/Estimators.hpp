@@ -1,0 +1,157 @@
+// rpe/Estimators.hpp — the marshalling layer shared by every estimator template: adapter -> C-ABI -> adapter.
+//
+// What the reference does inside each *_ransac loop on the CPU (sample, minimal solve, score all N, keep
+// best, shrink Iter: e.g. AbsoluteOrientation.hpp:101-156) happens on the GPU behind rpe_ransac(); this file
+// only (1) draws the same sample stream the reference would draw (RandomElements / ProsacSampler on ::rand()),
+// (2) moves the adapter's arrays to the device, (3) writes the result back through the adapter's own setters
+// (setMaxVotes / setRcw / sett / setInlier / cvtInlier), exactly the observable state the reference leaves.
+#ifndef RPE_ESTIMATORS_HPP_
+#define RPE_ESTIMATORS_HPP_
+
+#include <stdint.h>
+
+#include <cmath>
+#include <vector>
+
+#include "../rpe_c_api.h"
+#include "PoseAdapterBase.hpp"
+#include "Utility.hpp"
+#include "session.hpp"
+
+namespace rpe {
+namespace detail {
+
+inline int mask_cols(int method) {
+  return (method == RPE_KNEIP || method == RPE_KNEIP_QUAT) ? 1 : ((method == RPE_SHINJI || method == RPE_SHINJI_KNEIP) ? 2 : 3);
+}
+
+// H rows of `m` distinct indices, the draws of `RandomElements<int> re(n); re.run(m, &sel)` per iteration.
+inline void draw_ransac_table(int n, int m, int H, std::vector<int32_t>* table, RandSource* src = nullptr) {
+  table->assign((size_t)H * 4, -1);
+  RandomElements<int> re(n, src);
+  std::vector<int> sel;
+  for (int h = 0; h < H; ++h) {
+    re.run(m, &sel);
+    for (int k = 0; k < m; ++k) (*table)[(size_t)4 * h + k] = sel[k];
+  }
+}
+
+// H rows of ProsacSampler draws mapped through adapter.getSortedIdx (e.g. AbsoluteOrientation.hpp:221-229).
+// The reference's sampler can emit the index n == N (Utility.hpp:238), one past the last correspondence; it is
+// clamped to N-1 here instead of being read out of bounds.
+template <class Tp, class Adapter>
+inline void draw_prosac_table(Adapter& adapter, int m, int H, std::vector<int32_t>* table, RandSource* src = nullptr) {
+  const int n = adapter.getNumberCorrespondences();
+  table->assign((size_t)H * 4, -1);
+  adapter.sortIdx();
+  ProsacSampler<Tp> ps(m, n, src);
+  for (int h = 0; h < H; ++h) {
+    std::vector<int> sel;
+    ps.sample(&sel);
+    adapter.getSortedIdx(sel);
+    for (int k = 0; k < m; ++k) (*table)[(size_t)4 * h + k] = sel[k] < n ? sel[k] : n - 1;
+  }
+}
+
+template <class Tp>
+inline void upload(Session& s, const PoseAdapterBase<Tp>& adapter) {
+  const Tp *bv, *xc, *nc, *xw, *nw;
+  adapter.rpeArrays(&bv, &xc, &nc, &xw, &nw);
+  s.upload<Tp>(bv, xc, nc, xw, nw, adapter.getNumberCorrespondences());
+}
+
+template <class Tp>
+inline void pose_from_result(const rpe_result& r, SO3<Tp>* R, Vec3<Tp>* t) {
+  const Tp q[4] = {(Tp)r.q[0], (Tp)r.q[1], (Tp)r.q[2], (Tp)r.q[3]};
+  *R = SO3<Tp>::fromRawQuaternion(q);
+  *t = Vec3<Tp>((Tp)r.t[0], (Tp)r.t[1], (Tp)r.t[2]);
+}
+
+// The common body of every *_ransac / *_prosac template.
+template <class Tp, class Adapter>
+inline rpe_result run_ransac(Adapter& adapter, int method, const std::vector<int32_t>& table, Tp thr3d, Tp cos_thr2d,
+                             Tp cos_thrN, int& Iter, Tp confidence) {
+  Session& s = Session::local();
+  upload<Tp>(s, adapter);
+  const int n = adapter.getNumberCorrespondences();
+  const int cols = mask_cols(method);
+  std::vector<int16_t> mask((size_t)n * cols);
+  rpe_result res;
+  adapter.setMaxVotes(-1);
+  s.check(rpe_ransac(s.ctx(), method, table.data(), Iter, (float)thr3d, (float)cos_thr2d, (float)cos_thrN,
+                     (float)confidence, &res, mask.data()),
+          "rpe_ransac");
+  if (res.winner >= 0) {
+    adapter.setMaxVotes(res.max_votes);
+    SO3<Tp> R;
+    Vec3<Tp> t;
+    pose_from_result<Tp>(res, &R, &t);
+    adapter.setRcw(R);
+    adapter.sett(t);
+    MaskX m(n, cols);
+    for (size_t i = 0; i < mask.size(); ++i) m(i) = mask[i];
+    adapter.setInlier(m);
+  }
+  Iter = res.iter_final;
+  adapter.rpeSetStateToken(s.bump());  // the device now mirrors this adapter's pose and flags
+  return res;
+}
+
+// Make sure the device holds the adapter's arrays, pose and inlier flags (after user-side setInlier/setRcw the
+// token no longer matches and everything is sent again).
+template <class Tp, class Adapter>
+inline void sync_state(Session& s, Adapter& adapter) {
+  if (adapter.rpeStateToken() != 0 && adapter.rpeStateToken() == s.token()) return;
+  upload<Tp>(s, adapter);
+  std::vector<short> flags;
+  const int cols = adapter.rpeMask(&flags);
+  if (cols > 0) s.check(rpe_set_mask(s.ctx(), flags.data(), cols), "rpe_set_mask");
+  const Quaternion<Tp>& q = adapter.getRcw().unit_quaternion();
+  const float qf[4] = {(float)q.x(), (float)q.y(), (float)q.z(), (float)q.w()};
+  const Vec3<Tp> t = adapter.gettw();
+  const float tf[3] = {(float)t[0], (float)t[1], (float)t[2]};
+  s.check(rpe_set_pose(s.ctx(), qf, tf, 0), "rpe_set_pose");
+}
+
+template <class Tp, class Adapter>
+inline rpe_result run_refit(Adapter& adapter, int kind, const float* weights, int max_iters) {
+  Session& s = Session::local();
+  sync_state<Tp>(s, adapter);
+  rpe_result res;
+  s.check(rpe_refit(s.ctx(), kind, weights, max_iters, &res), "rpe_refit");
+  if (res.refit_ok) {
+    SO3<Tp> R;
+    Vec3<Tp> t;
+    pose_from_result<Tp>(res, &R, &t);
+    adapter.setRcw(R);
+    adapter.sett(t);
+  }
+  adapter.rpeSetStateToken(s.bump());
+  return res;
+}
+
+}  // namespace detail
+}  // namespace rpe
+
+// RANSACUpdateNumIters — /root/reference/pose/P3P.hpp:296-318 (same name, same arguments). For float it is the
+// bit-reproducible rule the device replays (rpe/ransac_rule.h); other scalar types use libm like the reference.
+#include "ransac_rule.h"
+template <typename T>
+int RANSACUpdateNumIters(T p, T ep, const int modelPoints, const int maxIters) {
+  p = std::max(p, T(0.));
+  p = std::min(p, T(1.));
+  ep = std::max(ep, T(0.));
+  ep = std::min(ep, T(1.));
+  T num = std::max(T(1. - p), std::numeric_limits<T>::epsilon());
+  T denom = T(1.) - std::pow(T(1. - ep), modelPoints);
+  if (denom < std::numeric_limits<T>::epsilon()) return 0;
+  num = std::log(num);
+  denom = std::log(denom);
+  return denom >= 0 || -num >= maxIters * (-denom) ? maxIters : int(num / denom + 0.5f);
+}
+template <>
+inline int RANSACUpdateNumIters<float>(float p, float ep, const int modelPoints, const int maxIters) {
+  return rpe::update_num_iters(p, ep, modelPoints, maxIters);
+}
+
+#endif  // RPE_ESTIMATORS_HPP_

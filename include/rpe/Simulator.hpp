@@ -1,0 +1,124 @@
+// rpe/Simulator.hpp — mirrors /root/reference/pose/Simulator.hpp (same function names and argument order) on top
+// of rpe/sim_core.hpp. The reference draws from hidden global state (::rand(), a global std::default_random_engine,
+// :13-14); here the single global stream is rpe::sim::global_rng(), reseedable with rpe::sim::seed(s).
+#ifndef RPE_SIMULATOR_HPP_
+#define RPE_SIMULATOR_HPP_
+
+#include "sim_core.hpp"
+#include "so3.hpp"
+#include "types.hpp"
+
+namespace rpe {
+namespace sim {
+inline Rng& global_rng() {
+  static Rng g(1);
+  return g;
+}
+inline void seed(uint64_t s) { global_rng() = Rng(s); }
+template <class T>
+inline Pose<T> make_pose(const rpe::SO3<T>& R, const rpe::Vec3<T>& t) {
+  Pose<T> p;
+  for (int k = 0; k < 4; ++k) p.q[k] = R.unit_quaternion().c[k];
+  for (int k = 0; k < 3; ++k) p.t[k] = t[k];
+  return p;
+}
+}  // namespace sim
+}  // namespace rpe
+
+template <typename T>
+rpe::Vec3<T> generate_random_translation_uniform(T size) {  // [reference :16-21]
+  rpe::sim::Rng& g = rpe::sim::global_rng();
+  return rpe::Vec3<T>(size * (T)g.uniform_pm1(), size * (T)g.uniform_pm1(), size * (T)g.uniform_pm1());
+}
+
+template <typename T>
+rpe::SO3<T> generate_random_rotation(T max_angle_radian_, bool use_guassian_ = true) {  // [reference :23-83]
+  rpe::Mat3<T> R;
+  rpe::sim::random_rotation<T>(rpe::sim::global_rng(), max_angle_radian_, use_guassian_, R.m);
+  T q[4];
+  rpe::sim::R_to_quat<T>(R.m, q);
+  return rpe::SO3<T>::fromRawQuaternion(q);
+}
+
+template <typename T>
+rpe::MatrixX<T> simulate_rand_point_cloud_in_frustum(int number_, T f_, T min_depth_, T max_depth_) {  // [:158-173]
+  rpe::MatrixX<T> P(3, number_);
+  rpe::sim::frustum_cloud<T>(rpe::sim::global_rng(), number_, f_, min_depth_, max_depth_, P.data());
+  return P;
+}
+
+template <typename T>
+void simulate_3d_3d_correspondences(const rpe::SO3<T>& R_cw_, const rpe::Vec3<T>& t_w_, int number_, T noise_,
+                                    T outlier_ratio_, T min_depth_, T max_depth_, T f_, bool use_guassian_,
+                                    rpe::MatrixX<T>* pQ_, rpe::MatrixX<T>* pP_gt = NULL,
+                                    rpe::MatrixX<T>* p_all_weights_ = NULL) {  // [reference :268-314]
+  pQ_->resize(3, number_);
+  rpe::MatrixX<T> P(3, number_);
+  rpe::sim::simulate_3d_3d<T>(rpe::sim::global_rng(), rpe::sim::make_pose(R_cw_, t_w_), number_, noise_, outlier_ratio_,
+                              min_depth_, max_depth_, f_, use_guassian_, pQ_->data(), P.data(),
+                              p_all_weights_ ? p_all_weights_->data() : (T*)0);
+  if (pP_gt) *pP_gt = P;
+}
+
+template <typename T>
+void simulate_2d_3d_correspondences(const rpe::SO3<T>& R_cw_, const rpe::Vec3<T>& t_w_, int number_, T noise_,
+                                    T outlier_ratio_, T min_depth_, T max_depth_, T f_, bool use_guassian_,
+                                    rpe::MatrixX<T>* pQ_, rpe::MatrixX<T>* pU_, rpe::MatrixX<T>* pP_gt = NULL,
+                                    rpe::MatrixX<T>* p_all_weights_ = NULL) {  // [reference :175-233]
+  pQ_->resize(3, number_);
+  pU_->resize(3, number_);
+  rpe::MatrixX<T> P(3, number_);
+  rpe::sim::simulate_2d_3d<T>(rpe::sim::global_rng(), rpe::sim::make_pose(R_cw_, t_w_), number_, noise_, outlier_ratio_,
+                              min_depth_, max_depth_, f_, use_guassian_, pQ_->data(), pU_->data(), P.data(),
+                              p_all_weights_ ? p_all_weights_->data() : (T*)0);
+  if (pP_gt) *pP_gt = P;
+}
+
+template <typename T>
+void simulate_2d_3d_3d_correspondences(const rpe::SO3<T>& R_cw_, const rpe::Vec3<T>& t_w_, int number_, T noise_2d_,
+                                       T noise_3d_, T outlier_ratio_, T min_depth_, T max_depth_, T f_, bool use_guassian_,
+                                       rpe::MatrixX<T>* pQ_, rpe::MatrixX<T>* pU_, rpe::MatrixX<T>* pP_gt = NULL,
+                                       rpe::MatrixX<T>* p_all_weights_ = NULL) {  // [reference :235-265]
+  simulate_2d_3d_correspondences<T>(R_cw_, t_w_, number_, noise_2d_, outlier_ratio_, min_depth_, max_depth_, f_,
+                                    use_guassian_, pQ_, pU_, pP_gt, p_all_weights_);
+  rpe::sim::Rng& g = rpe::sim::global_rng();
+  for (int i = 0; i < number_; i++) {
+    T rv[3];
+    rpe::sim::noise_vec<T>(g, use_guassian_, 3, rv);
+    if (p_all_weights_) (*p_all_weights_)(i, 1) = T(1.) / std::sqrt(rv[0] * rv[0] + rv[1] * rv[1] + rv[2] * rv[2]);
+    for (int r = 0; r < 3; ++r) (*pQ_)(r, i) += noise_3d_ * rv[r];
+  }
+}
+
+template <typename T>
+void simulate_nl_nl_correspondences(const rpe::SO3<T>& R_cw_, int number_, T noise_nl_, T outlier_ratio_nl_,
+                                    bool use_guassian_, rpe::MatrixX<T>* pM_, rpe::MatrixX<T>* pN_,
+                                    rpe::MatrixX<T>* pN_gt = NULL, rpe::MatrixX<T>* p_all_weights_ = NULL) {  // [:85-130]
+  pM_->resize(3, number_);
+  pN_->resize(3, number_);
+  rpe::MatrixX<T> Ngt(3, number_);
+  rpe::sim::simulate_nl_nl<T>(rpe::sim::global_rng(), rpe::sim::make_pose(R_cw_, rpe::Vec3<T>()), number_, noise_nl_,
+                              outlier_ratio_nl_, use_guassian_, pM_->data(), pN_->data(), Ngt.data(),
+                              p_all_weights_ ? p_all_weights_->data() : (T*)0);
+  if (pN_gt) *pN_gt = Ngt;
+}
+
+template <typename T>
+void simulate_2d_3d_nl_correspondences(const rpe::SO3<T>& R_cw_, const rpe::Vec3<T>& t_w_, int number_, T n2D_, T or_2D_,
+                                       T n3D_, T or_3D_, T nNl_, T or_Nl_, T min_depth_, T max_depth_, T f_,
+                                       bool use_guassian_, rpe::MatrixX<T>* pQ_, rpe::MatrixX<T>* pM_, rpe::MatrixX<T>* pP_,
+                                       rpe::MatrixX<T>* pN_, rpe::MatrixX<T>* pU_,
+                                       rpe::MatrixX<T>* p_all_weights_ = NULL) {  // [reference :316-367]
+  pQ_->resize(3, number_);
+  pM_->resize(3, number_);
+  pP_->resize(3, number_);
+  pN_->resize(3, number_);
+  pU_->resize(3, number_);
+  rpe::MatrixX<T> w(number_, 3);
+  rpe::sim::simulate_2d_3d_nl<T>(rpe::sim::global_rng(), rpe::sim::make_pose(R_cw_, t_w_), number_, n2D_, or_2D_, n3D_,
+                                 or_3D_, nNl_, or_Nl_, min_depth_, max_depth_, f_, use_guassian_, pQ_->data(), pM_->data(),
+                                 pP_->data(), pN_->data(), pU_->data(), w.data());
+  if (p_all_weights_) *p_all_weights_ = w;
+}
+
+#endif  // RPE_SIMULATOR_HPP_

@@ -1,21 +1,30 @@
-// solvers.cuh — device minimal solvers, one hypothesis per thread.
+// rpe/solvers.h — minimal solvers, host + device, one hypothesis per thread on the GPU.
 //
-// MUST be compiled with -fmad=false (csrc/Makefile does): every `a*b + c` below has to stay two
-// IEEE roundings so that the results are bit-identical to the reference's non-FMA x86-64 build
-// (CMakeLists.txt:13-15 sets only -Wall -std=c++11). Division and sqrt are IEEE (nvcc defaults
-// -prec-div=true -prec-sqrt=true, -ftz=false).
+// Device TUs MUST be compiled with -fmad=false (csrc/Makefile does) and host TUs with -ffp-contract=off
+// (or for a target without FMA): every `a*b + c` below has to stay two IEEE roundings so that the results
+// are bit-identical to the reference's non-FMA x86-64 build (CMakeLists.txt:13-15 sets only -Wall
+// -std=c++11). Division and sqrt are IEEE (nvcc defaults -prec-div=true -prec-sqrt=true, -ftz=false).
 //
 // Reference routines implemented here (paths into /root/reference/pose):
 //   svd3_jacobi      Eigen::JacobiSVD as used at AbsoluteOrientation.hpp:79 (two-sided Jacobi, square input)
 //   so3_from_matrix  Sophus::SO3(Matrix3) sophus/so3.hpp:561-566 (Eigen Quaternion(Matrix3) + ENSURE checks)
 //   shinji3          shinji<Tp>(X_w, X_c, K=3) AbsoluteOrientation.hpp:47-99
 //   kabsch_from_moments  the same closed form from accumulated moments (shinji_ls*, :273-342)
-#ifndef RPE_SOLVERS_CUH_
-#define RPE_SOLVERS_CUH_
+#ifndef RPE_SOLVERS_H_
+#define RPE_SOLVERS_H_
 
 #include <float.h>
+#include <math.h>
 
-#include "rpe_device.cuh"
+#include "det_math.h"
+
+#if defined(__CUDACC__)
+#define RPE_FN __host__ __device__ __forceinline__
+#define RPE_UNROLL _Pragma("unroll")
+#else
+#define RPE_FN inline
+#define RPE_UNROLL
+#endif
 
 namespace rpe {
 
@@ -23,33 +32,33 @@ template <class T>
 struct Lim;
 template <>
 struct Lim<float> {
-  __device__ static float eps() { return FLT_EPSILON; }
-  __device__ static float tiny() { return FLT_MIN; }
-  __device__ static float sophus_eps() { return 1e-5f; }  // sophus/common.hpp:143-151
+  RPE_FN static float eps() { return FLT_EPSILON; }
+  RPE_FN static float tiny() { return FLT_MIN; }
+  RPE_FN static float sophus_eps() { return 1e-5f; }  // sophus/common.hpp:143-151
 };
 template <>
 struct Lim<double> {
-  __device__ static double eps() { return DBL_EPSILON; }
-  __device__ static double tiny() { return DBL_MIN; }
-  __device__ static double sophus_eps() { return 1e-10; }  // sophus/common.hpp:137-141
+  RPE_FN static double eps() { return DBL_EPSILON; }
+  RPE_FN static double tiny() { return DBL_MIN; }
+  RPE_FN static double sophus_eps() { return 1e-10; }  // sophus/common.hpp:137-141
 };
 
 template <class T>
-__device__ __forceinline__ T t_abs(T a) {
+RPE_FN T t_abs(T a) {
   return a < T(0) ? -a : (a == T(0) ? T(0) : a);  // clears -0 like fabs
 }
-__device__ __forceinline__ float t_sqrt(float a) { return sqrtf(a); }
-__device__ __forceinline__ double t_sqrt(double a) { return sqrt(a); }
+RPE_FN float t_sqrt(float a) { return sqrtf(a); }
+RPE_FN double t_sqrt(double a) { return sqrt(a); }
 template <class T>
-__device__ __forceinline__ T sum3(T a, T b, T c) {
+RPE_FN T sum3(T a, T b, T c) {
   return a + (b + c);
 }
 
 // Plane rotation (c,s) applied to rows p,q: x' = c x + s y ; y' = -s x + c y
 template <class T>
-__device__ __forceinline__ void rot_rows(T* W, int p, int q, T c, T s) {
+RPE_FN void rot_rows(T* W, int p, int q, T c, T s) {
   if (c == T(1) && s == T(0)) return;
-#pragma unroll
+RPE_UNROLL
   for (int i = 0; i < 3; ++i) {
     const T xi = W[3 * p + i], yi = W[3 * q + i];
     W[3 * p + i] = c * xi + s * yi;
@@ -58,10 +67,10 @@ __device__ __forceinline__ void rot_rows(T* W, int p, int q, T c, T s) {
 }
 // applyOnTheRight(p,q,j): columns p,q rotated by j.transpose() = (c,-s)
 template <class T>
-__device__ __forceinline__ void rot_cols(T* W, int p, int q, T c, T s) {
+RPE_FN void rot_cols(T* W, int p, int q, T c, T s) {
   const T sc = -s;
   if (c == T(1) && sc == T(0)) return;
-#pragma unroll
+RPE_UNROLL
   for (int i = 0; i < 3; ++i) {
     const T xi = W[3 * i + p], yi = W[3 * i + q];
     W[3 * i + p] = c * xi + sc * yi;
@@ -71,18 +80,18 @@ __device__ __forceinline__ void rot_cols(T* W, int p, int q, T c, T s) {
 
 // Two-sided Jacobi SVD of a 3x3 (row-major). U, V row-major, s descending.
 template <class T>
-__device__ void svd3_jacobi(const T* A, T* U, T* V, T* s) {
+RPE_FN void svd3_jacobi(const T* A, T* U, T* V, T* s) {
   const T precision = T(2) * Lim<T>::eps();
   const T tiny = Lim<T>::tiny();
   T scale = T(0);
-#pragma unroll
+RPE_UNROLL
   for (int i = 0; i < 9; ++i) {
     const T v = t_abs(A[i]);
     if (v > scale) scale = v;
   }
   if (scale == T(0)) scale = T(1);
   T W[9];
-#pragma unroll
+RPE_UNROLL
   for (int i = 0; i < 9; ++i) {
     W[i] = A[i] / scale;
     U[i] = (i == 0 || i == 4 || i == 8) ? T(1) : T(0);
@@ -155,7 +164,7 @@ __device__ void svd3_jacobi(const T* A, T* U, T* V, T* s) {
       }
     }
   }
-#pragma unroll
+RPE_UNROLL
   for (int i = 0; i < 3; ++i) {
     const T aii = W[4 * i];
     s[i] = t_abs(aii);
@@ -165,7 +174,7 @@ __device__ void svd3_jacobi(const T* A, T* U, T* V, T* s) {
       U[6 + i] = -U[6 + i];
     }
   }
-#pragma unroll
+RPE_UNROLL
   for (int i = 0; i < 3; ++i) s[i] *= scale;
   for (int i = 0; i < 3; ++i) {
     int pos = i;
@@ -194,22 +203,22 @@ __device__ void svd3_jacobi(const T* A, T* U, T* V, T* s) {
 
 // C = A * B^T? No: plain C = A*B with redux-tree coefficients (Eigen lazy product, small fixed size).
 template <class T>
-__device__ __forceinline__ void mat_mul(const T* A, const T* B, T* C) {
-#pragma unroll
+RPE_FN void mat_mul(const T* A, const T* B, T* C) {
+RPE_UNROLL
   for (int i = 0; i < 3; ++i)
-#pragma unroll
+RPE_UNROLL
     for (int j = 0; j < 3; ++j) C[3 * i + j] = sum3(A[3 * i] * B[j], A[3 * i + 1] * B[3 + j], A[3 * i + 2] * B[6 + j]);
 }
 template <class T>
-__device__ __forceinline__ void mat_transpose(const T* A, T* At) {
-#pragma unroll
+RPE_FN void mat_transpose(const T* A, T* At) {
+RPE_UNROLL
   for (int i = 0; i < 3; ++i)
-#pragma unroll
+RPE_UNROLL
     for (int j = 0; j < 3; ++j) At[3 * i + j] = A[3 * j + i];
 }
 // Eigen determinant_impl<3>: h(0,1,2) - h(1,0,2) + h(2,0,1), h(a,b,c) = m(0,a)*(m(1,b)*m(2,c) - m(1,c)*m(2,b))
 template <class T>
-__device__ __forceinline__ T mat_det(const T* m) {
+RPE_FN T mat_det(const T* m) {
   const T h0 = m[0] * (m[4] * m[8] - m[5] * m[7]);
   const T h1 = m[1] * (m[3] * m[8] - m[5] * m[6]);
   const T h2 = m[2] * (m[3] * m[7] - m[4] * m[6]);
@@ -219,7 +228,7 @@ __device__ __forceinline__ T mat_det(const T* m) {
 // Sophus::SO3(Matrix3): Shoemake quaternion WITHOUT renormalisation; returns false where the
 // reference would abort (||R R^T - I||_F >= eps or det <= 0).
 template <class T>
-__device__ bool so3_from_matrix(const T* R, T* q /*x,y,z,w*/) {
+RPE_FN bool so3_from_matrix(const T* R, T* q /*x,y,z,w*/) {
   T t = sum3(R[0], R[4], R[8]);
   if (t > T(0)) {
     t = t_sqrt(t + T(1.0));
@@ -263,7 +272,7 @@ __device__ bool so3_from_matrix(const T* R, T* q /*x,y,z,w*/) {
 
 // v + w*uv + qv x uv (plain operators; this TU is compiled with -fmad=false)
 template <class T>
-__device__ __forceinline__ void quat_rotate(const T* q, const T* v, T* out) {
+RPE_FN void quat_rotate(const T* q, const T* v, T* out) {
   T uv[3] = {q[1] * v[2] - q[2] * v[1], q[2] * v[0] - q[0] * v[2], q[0] * v[1] - q[1] * v[0]};
   uv[0] = uv[0] + uv[0];
   uv[1] = uv[1] + uv[1];
@@ -276,7 +285,7 @@ __device__ __forceinline__ void quat_rotate(const T* q, const T* v, T* out) {
 
 // Rotation from the cross-covariance M (row-major): R = U diag(1,1,sign det(U V^T)) V^T.
 template <class T>
-__device__ bool rotation_from_covariance(const T* M, T* q) {
+RPE_FN bool rotation_from_covariance(const T* M, T* q) {
   T U[9], V[9], s[3];
   svd3_jacobi(M, U, V, s);
   T Vt[9], Tmp[9];
@@ -297,7 +306,7 @@ __device__ bool rotation_from_covariance(const T* M, T* q) {
 
 // shinji with K = 3 sample columns; `cols` is the divisor X_w_.cols() (3 in shinji_ransac*, 4 in the hybrids).
 template <class T>
-__device__ bool shinji3(const T Xw[9], const T Xc[9], int cols, T* q, T* t) {
+RPE_FN bool shinji3(const T Xw[9], const T Xc[9], int cols, T* q, T* t) {
   T Cw[3] = {T(0), T(0), T(0)}, Cc[3] = {T(0), T(0), T(0)};
   for (int n = 0; n < 3; ++n)
     for (int r = 0; r < 3; ++r) {
@@ -331,4 +340,4 @@ __device__ bool shinji3(const T Xw[9], const T Xc[9], int cols, T* q, T* t) {
 
 }  // namespace rpe
 
-#endif  // RPE_SOLVERS_CUH_
+#endif  // RPE_SOLVERS_H_

@@ -1,6 +1,6 @@
-// solvers_p3p.cuh — device P3P (Kneip) with the Ferrari quartic, and the point+normal solver.
+// rpe/solvers_p3p.h — P3P (Kneip) with the Ferrari quartic, and the point+normal solver; host + device.
 //
-// One hypothesis per thread; -fmad=false TU (see solvers.cuh). Transcendentals go through
+// One hypothesis per thread on the GPU; -fmad=false / -ffp-contract=off TUs (see solvers.h). Transcendentals go through
 // include/rpe/det_math.h so that the CPU oracle in DET mode produces the same bits.
 //
 // Reference routines (paths into /root/reference/pose):
@@ -9,10 +9,10 @@
 //   kneip_main    P3P.hpp:63-232
 //   kneip (4th-point disambiguation)  P3P.hpp:250-294 and the inline copy in kneip_ransac :338-354
 //   nl_2p         AbsoluteOrientationNormal.hpp:77-142
-#ifndef RPE_SOLVERS_P3P_CUH_
-#define RPE_SOLVERS_P3P_CUH_
+#ifndef RPE_SOLVERS_P3P_H_
+#define RPE_SOLVERS_P3P_H_
 
-#include "solvers.cuh"
+#include "solvers.h"
 
 namespace rpe {
 
@@ -21,14 +21,14 @@ struct Cplx {
   T re, im;
 };
 template <class T>
-__device__ __forceinline__ Cplx<T> c_mul(Cplx<T> a, Cplx<T> b) {
+RPE_FN Cplx<T> c_mul(Cplx<T> a, Cplx<T> b) {
   Cplx<T> r;
   r.re = a.re * b.re - a.im * b.im;
   r.im = a.re * b.im + a.im * b.re;
   return r;
 }
 template <class T>
-__device__ __forceinline__ Cplx<T> c_div(Cplx<T> a, Cplx<T> b) {  // Smith
+RPE_FN Cplx<T> c_div(Cplx<T> a, Cplx<T> b) {  // Smith
   Cplx<T> r;
   if (t_abs(b.re) < t_abs(b.im)) {
     const T ratio = b.re / b.im;
@@ -44,7 +44,7 @@ __device__ __forceinline__ Cplx<T> c_div(Cplx<T> a, Cplx<T> b) {  // Smith
   return r;
 }
 template <class T>
-__device__ __forceinline__ Cplx<T> c_sqrt(Cplx<T> z) {
+RPE_FN Cplx<T> c_sqrt(Cplx<T> z) {
   Cplx<T> r;
   if (z.re == T(0) && z.im == T(0)) {
     r.re = T(0);
@@ -63,7 +63,7 @@ __device__ __forceinline__ Cplx<T> c_sqrt(Cplx<T> z) {
   return r;
 }
 template <class T>
-__device__ __forceinline__ Cplx<T> c_cbrt(Cplx<T> z) {
+RPE_FN Cplx<T> c_cbrt(Cplx<T> z) {
   Cplx<T> r;
   if (z.re == T(0) && z.im == T(0)) {
     r.re = T(0);
@@ -81,7 +81,7 @@ __device__ __forceinline__ Cplx<T> c_cbrt(Cplx<T> z) {
 }
 
 template <class T>
-__device__ void o4_roots_dev(const T* f, T* roots) {
+RPE_FN void o4_roots_dev(const T* f, T* roots) {
   const T A = f[0], B = f[1], C = f[2], D = f[3], E = f[4];
   const T A_pw2 = A * A, B_pw2 = B * B;
   const T A_pw3 = A_pw2 * A, B_pw3 = B_pw2 * B;
@@ -149,27 +149,27 @@ __device__ void o4_roots_dev(const T* f, T* roots) {
 }
 
 template <class T>
-__device__ __forceinline__ void v_cross(const T* a, const T* b, T* c) {
+RPE_FN void v_cross(const T* a, const T* b, T* c) {
   c[0] = a[1] * b[2] - a[2] * b[1];
   c[1] = a[2] * b[0] - a[0] * b[2];
   c[2] = a[0] * b[1] - a[1] * b[0];
 }
 template <class T>
-__device__ __forceinline__ T v_dot(const T* a, const T* b) {
+RPE_FN T v_dot(const T* a, const T* b) {
   return sum3(a[0] * b[0], a[1] * b[1], a[2] * b[2]);
 }
 template <class T>
-__device__ __forceinline__ T v_norm(const T* a) {
+RPE_FN T v_norm(const T* a) {
   return t_sqrt(v_dot(a, a));
 }
 template <class T>
-__device__ __forceinline__ void mat_vec(const T* M, const T* x, T* y) {
+RPE_FN void mat_vec(const T* M, const T* x, T* y) {
   y[0] = sum3(M[0] * x[0], M[1] * x[1], M[2] * x[2]);
   y[1] = sum3(M[3] * x[0], M[4] * x[1], M[5] * x[2]);
   y[2] = sum3(M[6] * x[0], M[7] * x[1], M[8] * x[2]);
 }
 template <class T>
-__device__ __forceinline__ void quat_to_matrix_t(const T* q, T* R) {
+RPE_FN void quat_to_matrix_t(const T* q, T* R) {
   const T tx = T(2) * q[0], ty = T(2) * q[1], tz = T(2) * q[2];
   const T twx = tx * q[3], twy = ty * q[3], twz = tz * q[3];
   const T txx = tx * q[0], txy = ty * q[0], txz = tz * q[0];
@@ -187,7 +187,7 @@ __device__ __forceinline__ void quat_to_matrix_t(const T* q, T* R) {
 
 // Up to 4 solutions (quaternion x,y,z,w + translation) in root order; returns their number.
 template <class T>
-__device__ int kneip_main_dev(const T* Xw, const T* bv, T (*qs)[4], T (*ts)[3]) {
+RPE_FN int kneip_main_dev(const T* Xw, const T* bv, T (*qs)[4], T (*ts)[3]) {
   T P1[3], P2[3], P3[3];
   for (int r = 0; r < 3; ++r) {
     P1[r] = Xw[r];
@@ -349,7 +349,7 @@ __device__ int kneip_main_dev(const T* Xw, const T* bv, T (*qs)[4], T (*ts)[3]) 
 
 // P3P + 4th-point disambiguation. Xw, bv: 3 x 4 column-major. `start` is the initial minScore.
 template <class T>
-__device__ bool kneip_select(const T* Xw, const T* bv, T start, T* q_out, T* t_out) {
+RPE_FN bool kneip_select(const T* Xw, const T* bv, T start, T* q_out, T* t_out) {
   T qs[4][4], ts[4][3];
   const int ns = kneip_main_dev<T>(Xw, bv, qs, ts);
   T minScore = start;
@@ -375,12 +375,12 @@ __device__ bool kneip_select(const T* Xw, const T* bv, T start, T* q_out, T* t_o
 
 // ---- nl_2p ---------------------------------------------------------------------------------------
 template <class T>
-__device__ __forceinline__ void quat_normalized(const T* qin, T* q) {  // Sophus explicit-quaternion ctor
+RPE_FN void quat_normalized(const T* qin, T* q) {  // Sophus explicit-quaternion ctor
   const T len = t_sqrt((qin[0] * qin[0] + qin[1] * qin[1]) + (qin[2] * qin[2] + qin[3] * qin[3]));
   for (int k = 0; k < 4; ++k) q[k] = qin[k] / len;
 }
 template <class T>
-__device__ __forceinline__ void quat_from_angle_axis(T angle, const T* axis, T* q) {
+RPE_FN void quat_from_angle_axis(T angle, const T* axis, T* q) {
   const T ha = T(0.5) * angle;
   T s, c;
   det::sincos_t(ha, &s, &c);
@@ -388,7 +388,7 @@ __device__ __forceinline__ void quat_from_angle_axis(T angle, const T* axis, T* 
   quat_normalized(raw, q);
 }
 template <class T>
-__device__ __forceinline__ void v_normalize(T* a) {
+RPE_FN void v_normalize(T* a) {
   const T z = v_dot(a, a);
   if (z > T(0)) {
     const T n = t_sqrt(z);
@@ -399,7 +399,7 @@ __device__ __forceinline__ void v_normalize(T* a) {
 }
 // Hamilton product + Sophus' first-order renormalisation (so3.hpp:255-272); coefficient order x,y,z,w
 template <class T>
-__device__ __forceinline__ void so3_mul(const T* a, const T* b, T* r) {
+RPE_FN void so3_mul(const T* a, const T* b, T* r) {
   const T w = a[3] * b[3] - a[0] * b[0] - a[1] * b[1] - a[2] * b[2];
   const T x = a[3] * b[0] + a[0] * b[3] + a[1] * b[2] - a[2] * b[1];
   const T y = a[3] * b[1] + a[1] * b[3] + a[2] * b[0] - a[0] * b[2];
@@ -419,7 +419,7 @@ __device__ __forceinline__ void so3_mul(const T* a, const T* b, T* r) {
 }
 
 template <class T>
-__device__ void nl_2p(const T* pt1_c, const T* nl1_c, const T* pt2_c, const T* pt1_w, const T* nl1_w, const T* pt2_w,
+RPE_FN void nl_2p(const T* pt1_c, const T* nl1_c, const T* pt2_c, const T* pt1_w, const T* nl1_w, const T* pt2_w,
                       T* q_out, T* t_out) {
   const T alpha = det::acos_t(nl1_w[0]);
   T axis[3] = {T(0), nl1_w[2], -nl1_w[1]};
@@ -460,4 +460,4 @@ __device__ void nl_2p(const T* pt1_c, const T* nl1_c, const T* pt2_c, const T* p
 
 }  // namespace rpe
 
-#endif  // RPE_SOLVERS_P3P_CUH_
+#endif  // RPE_SOLVERS_P3P_H_

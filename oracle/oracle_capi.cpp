@@ -144,6 +144,17 @@ void orc_sample_table(unsigned seed, int n_corr, int m, int H, int32_t* out) {
     for (int k = 0; k < 4; ++k) out[4 * h + k] = k < m ? sel[k] : -1;
   }
 }
+// Same, after discarding `skip` rand() draws (a program that already ran other samplers on the same stream).
+void orc_sample_table_skip(unsigned seed, long long skip, int n_corr, int m, int H, int32_t* out) {
+  GlibcRand g(seed);
+  for (long long i = 0; i < skip; ++i) (void)g.next();
+  RandomElementsModel re(n_corr, &g);
+  std::vector<int> sel;
+  for (int h = 0; h < H; ++h) {
+    re.run(m, &sel);
+    for (int k = 0; k < 4; ++k) out[4 * h + k] = k < m ? sel[k] : -1;
+  }
+}
 // H consecutive ProsacSampler::sample draws mapped through the weight-sorted index
 // (Utility.hpp:183-243, PnPPoseAdapter.hpp:239-255); weights may be null (identity order).
 void orc_prosac_table_f(unsigned seed, int n_corr, int m, int H, const float* weights, int32_t* out) {

@@ -71,6 +71,9 @@ struct rpe_ctx {
   int mask_cols = 0;
   RefitBuffers rb = {nullptr, nullptr, 0, 148};
   GnState* d_gn = nullptr;
+  NlskState* d_nlsk = nullptr;
+  float* d_weights3 = nullptr;
+  size_t weights_cap = 0;
   double* d_gn_cost = nullptr;
   int32_t* d_gn_evals = nullptr;
   double* h_gn_cost = nullptr;  // pinned (cost + evals packed)
@@ -479,6 +482,7 @@ static int create_common(int device, void* stream, bool own, rpe_ctx** out) {
   ok = ok && cudaMallocHost(&ctx->h_pose, kNumStaging * sizeof(ReplayOut)) == cudaSuccess;
   ok = ok && cudaMalloc(&ctx->rb.moments, kMomentCount * sizeof(double)) == cudaSuccess;
   ok = ok && cudaMalloc(&ctx->d_gn, sizeof(GnState)) == cudaSuccess;
+  ok = ok && cudaMalloc(&ctx->d_nlsk, sizeof(NlskState)) == cudaSuccess;
   ok = ok && cudaMalloc(&ctx->d_gn_cost, sizeof(double)) == cudaSuccess;
   ok = ok && cudaMalloc(&ctx->d_gn_evals, sizeof(int32_t)) == cudaSuccess;
   ok = ok && cudaMallocHost(&ctx->h_gn_cost, kNumStaging * sizeof(double)) == cudaSuccess;
@@ -534,6 +538,8 @@ int rpe_destroy(rpe_ctx* ctx) {
   cudaFree(ctx->rb.partials);
   cudaFree(ctx->rb.moments);
   cudaFree(ctx->d_gn);
+  cudaFree(ctx->d_nlsk);
+  cudaFree(ctx->d_weights3);
   cudaFree(ctx->d_gn_cost);
   cudaFree(ctx->d_gn_evals);
   if (ctx->h_gn_cost) cudaFreeHost(ctx->h_gn_cost);
@@ -657,8 +663,26 @@ static int do_refit(rpe_ctx* ctx, int kind, const float* weights, int max_iters,
     CK(cudaMemcpyAsync(&ctx->h_gn_evals[slot], ctx->d_gn_evals, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
     stamp(ctx, ST_TOTAL);
     gn = true;
+  } else if (kind == RPE_REFIT_NL_SK_LS) {
+    if (!f.bv || !f.xc || !f.nc || !f.nw) return fail(ctx, RPE_ERR_STATE, "nl_shinji_kneip_ls needs all five arrays");
+    if (ctx->mask_cols < 3) return fail(ctx, RPE_ERR_STATE, "nl_shinji_kneip_ls needs the three inlier columns");
+    const float* w3 = nullptr;
+    if (weights) {
+      const size_t need = (size_t)ctx->n * 3;
+      if (need > ctx->weights_cap) {
+        if (ctx->d_weights3) cudaFree(ctx->d_weights3);
+        CK(cudaMalloc(&ctx->d_weights3, need * sizeof(float)));
+        ctx->weights_cap = need;
+      }
+      CK(cudaMemcpyAsync(ctx->d_weights3, weights, need * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+      w3 = ctx->d_weights3;
+    }
+    launch_nlsk_prepass(f, ctx->d_mask, w3, ctx->d_pose, ctx->rb, ctx->d_nlsk, ctx->d_stats, ctx->stream);
+    for (int it = 0; it < 3; ++it)
+      launch_nlsk_iteration(f, ctx->d_mask, w3, ctx->rb, ctx->d_nlsk, ctx->d_stats, ctx->d_pose, ctx->stream);
+    ctx->launches += 4;
   } else {
-    return fail(ctx, RPE_ERR_ARG, "unknown or unimplemented refit kind");
+    return fail(ctx, RPE_ERR_ARG, "unknown refit kind");
   }
   ctx->kabsch_valid = false;
   CK(cudaMemcpyAsync(&ctx->h_pose[slot], ctx->d_pose, sizeof(ReplayOut), cudaMemcpyDeviceToHost, ctx->stream));

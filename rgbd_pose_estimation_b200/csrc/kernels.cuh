@@ -68,7 +68,7 @@ struct RefitBuffers {
   int max_blocks;
   int num_sms;        // refit kernels use at most 2 CTAs per SM and stride over the correspondences
 };
-constexpr int kMomentCount = 32;  // 16 Kabsch moments / 28 GN entries, padded
+constexpr int kMomentCount = 48;  // 16 Kabsch moments / 29 LM entries / 40 nl_shinji_kneip_ls sums, padded
 
 // pose_rw: the ReplayOut written by the replay kernel (read for the pose, per-column inlier counts are
 // added to it); kabsch_out receives pose_rw with (q,t) replaced by the Kabsch refit over the 3-D inliers.
@@ -96,6 +96,22 @@ void launch_gn_init(const ReplayOut* pose, GnState* st, cudaStream_t s);
 void launch_gn_iteration(const FrameView& f, const int16_t* mask, int mask_cols, float w2d, float w3d, float wnl,
                          RefitBuffers rb, GnState* gs, FrameStats* st, ReplayOut* pose_out, double* cost_out,
                          int32_t* evals_out, cudaStream_t s);
+
+// nl_shinji_kneip_ls (AbsoluteOrientationNormal.hpp:447-552) as one pose-independent reduction pass plus three
+// passes for the only sum that depends on the running camera centre (M23); the 3x3 SVDs, find_opt_cc's
+// ray-intersection solve and the blending run in the last CTA of each pass, in binary64.
+struct NlskState {
+  double Cw[3], Cc[3], TV;
+  double S33[9], sig, SNN[9], tl, tw;
+  double M23[9], M33[9], MNN[9], TW, TL;
+  double cp[3], c_opt[3], q_opt[4];
+  double q0[4], t0[3];
+  int N, k23, mnn, K, M, cp_ok, stopped, iter;
+};
+void launch_nlsk_prepass(const FrameView& f, const int16_t* mask3, const float* weights3, const ReplayOut* pose,
+                         RefitBuffers rb, NlskState* ns, FrameStats* st, cudaStream_t s);
+void launch_nlsk_iteration(const FrameView& f, const int16_t* mask3, const float* weights3, RefitBuffers rb, NlskState* ns,
+                           FrameStats* st, ReplayOut* pose_out, cudaStream_t s);
 
 // -- microbenchmark -----------------------------------------------------------------------------------
 void launch_ffma_bench(float* sink, int iters, bool packed, int blocks, cudaStream_t s);

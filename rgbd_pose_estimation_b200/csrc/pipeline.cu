@@ -15,8 +15,8 @@
 
 #include "../../include/rpe/ransac_rule.h"
 #include "kernels.cuh"
-#include "solvers.cuh"
-#include "solvers_p3p.cuh"
+#include "../../include/rpe/solvers.h"
+#include "../../include/rpe/solvers_p3p.h"
 
 namespace rpe {
 
@@ -327,19 +327,23 @@ __device__ __forceinline__ void block_reduce_store(double* v, double* __restrict
 // b = g, g+8, ... (independent loads, all in flight together), then the 8 groups are added in a fixed order.
 // Deterministic for a given grid size. Result in smem_out[0..kMomentCount).
 __device__ __forceinline__ void final_reduce_partials(const double* __restrict__ partials, int nblocks,
-                                                      double* smem_scratch /*[8*32]*/, double* smem_out /*[32]*/) {
-  const int k = threadIdx.x & 31, g = threadIdx.x >> 5;
-  double x = 0.0;
-  for (int b = g; b < nblocks; b += 8) x += partials[(size_t)b * kMomentCount + k];
-  smem_scratch[g * 32 + k] = x;
-  __syncthreads();
-  if (threadIdx.x < 32) {
-    double t = 0.0;
+                                                      double* smem_scratch /*[8*32]*/, double* smem_out /*[kMomentCount]*/) {
+  const int lane = threadIdx.x & 31, g = threadIdx.x >> 5;
+  for (int k0 = 0; k0 < kMomentCount; k0 += 32) {
+    const int k = k0 + lane;
+    double x = 0.0;
+    if (k < kMomentCount)
+      for (int b = g; b < nblocks; b += 8) x += partials[(size_t)b * kMomentCount + k];
+    smem_scratch[g * 32 + lane] = x;
+    __syncthreads();
+    if (threadIdx.x < 32 && k < kMomentCount) {
+      double t = 0.0;
 #pragma unroll
-    for (int gg = 0; gg < 8; ++gg) t += smem_scratch[gg * 32 + threadIdx.x];
-    smem_out[threadIdx.x] = t;
+      for (int gg = 0; gg < 8; ++gg) t += smem_scratch[gg * 32 + threadIdx.x];
+      smem_out[k] = t;
+    }
+    __syncthreads();
   }
-  __syncthreads();
 }
 
 // Kabsch from moments m[0]=K, m[1..3]=sum x_w, m[4..6]=sum x_c, m[7..15]=sum x_c x_w^T (row-major).
@@ -448,7 +452,7 @@ mask_kernel(int method, FrameView f, ReplayOut* pose_rw, Thresh th, int16_t* __r
   if (is_last) {
     __threadfence();
     __shared__ double fin_scratch[8 * 32];
-    __shared__ double fin[32];
+    __shared__ double fin[kMomentCount];
     final_reduce_partials(rb.partials, gridDim.x, fin_scratch, fin);
     if (threadIdx.x == 0) {
       double m[16];
@@ -510,7 +514,7 @@ int launch_kabsch_moments(const FrameView& f, const int16_t* flags3d, RefitBuffe
 __global__ void __launch_bounds__(256)
 kabsch_solve_kernel(RefitBuffers rb, int blocks_used, ReplayOut* __restrict__ pose, int32_t* refit_ok) {
   __shared__ double fin_scratch[8 * 32];
-  __shared__ double fin[32];
+  __shared__ double fin[kMomentCount];
   final_reduce_partials(rb.partials, blocks_used, fin_scratch, fin);
   if (threadIdx.x == 0) {
     double m[16];
@@ -845,7 +849,7 @@ gn_iteration_kernel(FrameView f, const int16_t* __restrict__ mask, int mask_cols
   if (!is_last) return;
   __threadfence();
   __shared__ double fin_scratch[8 * 32];
-  __shared__ double fin[32];
+  __shared__ double fin[kMomentCount];
   final_reduce_partials(rb.partials, gridDim.x, fin_scratch, fin);
   if (threadIdx.x != 0) return;
   double tot[kGnAcc];
@@ -928,6 +932,276 @@ void launch_gn_iteration(const FrameView& f, const int16_t* mask, int mask_cols,
   else
     gn_iteration_kernel<false><<<blocks, 256, 0, s>>>(f, mask, mask_cols, w2d, w3d, wnl, rb, gs, st, pose_out, cost_out,
                                                       evals_out);
+}
+
+// ================================================================================================
+// nl_shinji_kneip_ls — the reference's multi-modal refinement (AbsoluteOrientationNormal.hpp:447-552 with
+// find_opt_cc :13-46), quirks included: the 3-3 / N-N weights are divided by 32767 (AOPoseAdapter.hpp:167,
+// NormalAOPoseAdapter.hpp:159) and M23 / M33 / MNN / K / TW / M / TL are NOT reset between the three passes.
+// ================================================================================================
+constexpr int kNlskAcc = 40;
+// prepass accumulator layout: [0] TV [1] N [2..4] sum v xw [5..7] sum v xc [8..16] sum v xc xw^T [17] sum v |xc|^2
+// [18..26] sum l nc nw^T [27] tl [28] mnn [29] tw [30] k23 [31..36] AA (00,01,02,11,12,22) [37..39] bb
+__global__ void __launch_bounds__(256)
+nlsk_prepass_kernel(FrameView f, const int16_t* __restrict__ mask3, const float* __restrict__ w3, const ReplayOut* pose,
+                    RefitBuffers rb, NlskState* ns, FrameStats* st) {
+  __shared__ double red[8 * kNlskAcc];
+  __shared__ bool is_last;
+  const int n = f.n;
+  double acc[kNlskAcc];
+#pragma unroll
+  for (int k = 0; k < kNlskAcc; ++k) acc[k] = 0.0;
+  // R_wc = R_cw^-1 as a matrix, from the adapter's current rotation (find_opt_cc :21)
+  double q[4] = {pose->q[0], pose->q[1], pose->q[2], pose->q[3]};
+  {
+    const double len = sqrt((q[0] * q[0] + q[1] * q[1]) + (q[2] * q[2] + q[3] * q[3]));
+    for (int k = 0; k < 4; ++k) q[k] /= len;  // inverse() goes through the normalising constructor
+  }
+  const double qi[4] = {-q[0], -q[1], -q[2], q[3]};
+  double Rwc[9];
+  quat_to_matrix_t<double>(qi, Rwc);
+  const double inv_short = 1.0 / 32767.0;
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < n; c += gridDim.x * blockDim.x) {
+    const bool i23 = mask3[c] == 1, i33 = mask3[n + c] == 1, inn = mask3[2 * n + c] == 1;
+    if (!(i23 || i33 || inn)) continue;
+    const F3 xwf = load_col(f.xw, c);
+    const double xw[3] = {xwf.x, xwf.y, xwf.z};
+    if (i33) {
+      const double v = w3 ? (double)w3[n + c] * inv_short : 1.0;
+      const F3 xcf = load_col(f.xc, c);
+      const double xc[3] = {xcf.x, xcf.y, xcf.z};
+      acc[0] += v;
+      acc[1] += 1.0;
+      for (int r = 0; r < 3; ++r) {
+        acc[2 + r] += v * xw[r];
+        acc[5 + r] += v * xc[r];
+        for (int k = 0; k < 3; ++k) acc[8 + 3 * r + k] += v * xc[r] * xw[k];
+      }
+      acc[17] += v * (xc[0] * xc[0] + xc[1] * xc[1] + xc[2] * xc[2]);
+    }
+    if (inn) {
+      const double l = w3 ? (double)w3[2 * n + c] * inv_short : 1.0;
+      const F3 ncf = load_col(f.nc, c), nwf = load_col(f.nw, c);
+      const double nc[3] = {ncf.x, ncf.y, ncf.z}, nw[3] = {nwf.x, nwf.y, nwf.z};
+      for (int r = 0; r < 3; ++r)
+        for (int k = 0; k < 3; ++k) acc[18 + 3 * r + k] += l * nc[r] * nw[k];
+      acc[27] += l;
+      acc[28] += 1.0;
+    }
+    if (i23) {
+      const double w = w3 ? (double)w3[c] : 1.0;
+      acc[29] += w;
+      acc[30] += 1.0;
+      const F3 bf = load_col(f.bv, c);
+      const double b[3] = {bf.x, bf.y, bf.z};
+      double vr[3];
+      for (int r = 0; r < 3; ++r) vr[r] = Rwc[3 * r] * b[0] + Rwc[3 * r + 1] * b[1] + Rwc[3 * r + 2] * b[2];
+      const double A00 = 1 - vr[0] * vr[0], A01 = -vr[0] * vr[1], A02 = -vr[0] * vr[2], A11 = 1 - vr[1] * vr[1],
+                   A12 = -vr[1] * vr[2], A22 = 1 - vr[2] * vr[2];
+      acc[31] += A00;
+      acc[32] += A01;
+      acc[33] += A02;
+      acc[34] += A11;
+      acc[35] += A12;
+      acc[36] += A22;
+      acc[37] += A00 * xw[0] + A01 * xw[1] + A02 * xw[2];
+      acc[38] += A01 * xw[0] + A11 * xw[1] + A12 * xw[2];
+      acc[39] += A02 * xw[0] + A12 * xw[1] + A22 * xw[2];
+    }
+  }
+  block_reduce_store<kNlskAcc>(acc, rb.partials, red);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned int tk = atomicAdd(&st->ticket2, 1u);
+    is_last = (tk == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  __shared__ double fin_scratch[8 * 32];
+  __shared__ double fin[kMomentCount];
+  final_reduce_partials(rb.partials, gridDim.x, fin_scratch, fin);
+  if (threadIdx.x != 0) return;
+  st->ticket2 = 0;
+  const double* a = fin;
+  ns->TV = a[0];
+  ns->N = (int)a[1];
+  for (int r = 0; r < 3; ++r) {
+    ns->Cw[r] = a[2 + r];
+    ns->Cc[r] = a[5 + r];
+  }
+  if (ns->N > 2)
+    for (int r = 0; r < 3; ++r) {  // :466-469 (with N <= 2 the raw weighted sums are kept, as in the reference)
+      ns->Cw[r] /= ns->TV;
+      ns->Cc[r] /= ns->TV;
+    }
+  // centred sums from the raw moments: sum v (xc-Cc)(xw-Cw)^T = sum v xc xw^T - Cc (sum v xw)^T - (sum v xc) Cw^T + TV Cc Cw^T
+  for (int r = 0; r < 3; ++r)
+    for (int k = 0; k < 3; ++k)
+      ns->S33[3 * r + k] = a[8 + 3 * r + k] - ns->Cc[r] * a[2 + k] - a[5 + r] * ns->Cw[k] + a[0] * ns->Cc[r] * ns->Cw[k];
+  ns->sig = a[17] - 2.0 * (ns->Cc[0] * a[5] + ns->Cc[1] * a[6] + ns->Cc[2] * a[7]) +
+            a[0] * (ns->Cc[0] * ns->Cc[0] + ns->Cc[1] * ns->Cc[1] + ns->Cc[2] * ns->Cc[2]);
+  for (int k = 0; k < 9; ++k) ns->SNN[k] = a[18 + k];
+  ns->tl = a[27];
+  ns->mnn = (int)a[28];
+  ns->tw = a[29];
+  ns->k23 = (int)a[30];
+  // find_opt_cc: solve AA x = bb through the SVD with Eigen's rank threshold, NaN when |det AA| < 1e-4 (:41-44)
+  const double AA[9] = {a[31], a[32], a[33], a[32], a[34], a[35], a[33], a[35], a[36]};
+  ns->cp_ok = 0;
+  if (fabs(mat_det<double>(AA)) >= 0.0001) {
+    double U[9], V[9], sv[3];
+    svd3_jacobi<double>(AA, U, V, sv);
+    const double thr0 = sv[0] * (3.0 * DBL_EPSILON);
+    const double thr = thr0 > DBL_MIN ? thr0 : DBL_MIN;
+    int rank = 0;
+    while (rank < 3 && sv[rank] > thr) ++rank;
+    double tmp[3] = {0, 0, 0};
+    for (int k = 0; k < rank; ++k) tmp[k] = (U[k] * a[37] + U[3 + k] * a[38] + U[6 + k] * a[39]) / sv[k];
+    for (int r = 0; r < 3; ++r) {
+      double x = 0.0;
+      for (int k = 0; k < rank; ++k) x += V[3 * r + k] * tmp[k];
+      ns->cp[r] = x;
+    }
+    ns->cp_ok = 1;
+  }
+  for (int k = 0; k < 9; ++k) ns->M23[k] = ns->M33[k] = ns->MNN[k] = 0.0;
+  ns->TW = ns->TL = 0.0;
+  ns->K = ns->M = 0;
+  ns->stopped = 0;
+  ns->iter = 0;
+  for (int k = 0; k < 4; ++k) {
+    ns->q0[k] = q[k];
+    ns->q_opt[k] = k == 3 ? 1.0 : 0.0;  // Sophus::SO3 default = identity (:480)
+  }
+  for (int k = 0; k < 3; ++k) ns->t0[k] = pose->t[k];
+  // c_opt = R_cw^-1 * (-t_w)  (:479)
+  const double nt[3] = {-ns->t0[0], -ns->t0[1], -ns->t0[2]};
+  quat_rotate<double>(qi, nt, ns->c_opt);
+}
+
+__global__ void __launch_bounds__(256)
+nlsk_iteration_kernel(FrameView f, const int16_t* __restrict__ mask3, const float* __restrict__ w3, RefitBuffers rb,
+                      NlskState* ns, FrameStats* st, ReplayOut* pose_out) {
+  if (ns->stopped) return;
+  __shared__ double red[8 * 9];
+  __shared__ bool is_last;
+  const int n = f.n;
+  double acc[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) acc[k] = 0.0;
+  const double co[3] = {ns->c_opt[0], ns->c_opt[1], ns->c_opt[2]};
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < n; c += gridDim.x * blockDim.x) {
+    if (mask3[c] != 1) continue;
+    const double w = w3 ? (double)w3[c] : 1.0;
+    const F3 xwf = load_col(f.xw, c), bf = load_col(f.bv, c);
+    double Aw[3] = {xwf.x - co[0], xwf.y - co[1], xwf.z - co[2]};
+    const double z = Aw[0] * Aw[0] + Aw[1] * Aw[1] + Aw[2] * Aw[2];
+    if (z > 0.0) {
+      const double nn = sqrt(z);
+      Aw[0] /= nn;
+      Aw[1] /= nn;
+      Aw[2] /= nn;
+    }
+    const double b[3] = {bf.x, bf.y, bf.z};
+    for (int r = 0; r < 3; ++r)
+      for (int k = 0; k < 3; ++k) acc[3 * r + k] += (w * b[r]) * Aw[k];
+  }
+  block_reduce_store<9>(acc, rb.partials, red);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned int tk = atomicAdd(&st->ticket2, 1u);
+    is_last = (tk == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  __shared__ double fin_scratch[8 * 32];
+  __shared__ double fin[kMomentCount];
+  final_reduce_partials(rb.partials, gridDim.x, fin_scratch, fin);
+  if (threadIdx.x != 0) return;
+  st->ticket2 = 0;
+  // ---- one pass of the reference's loop body (:483-543), accumulators carried over as in the reference ----
+  for (int k = 0; k < 9; ++k) {
+    ns->M23[k] += fin[k];
+    ns->M33[k] += ns->S33[k];
+    ns->MNN[k] += ns->SNN[k];
+  }
+  ns->TW += ns->tw;
+  ns->K += ns->k23;
+  ns->TL += ns->tl;
+  ns->M += ns->mnn;
+  double sigma = ns->sig;
+  if (ns->N > 2) {
+    for (int k = 0; k < 9; ++k) ns->M33[k] /= ns->TV;
+    sigma /= ns->TV;
+  } else {
+    for (int k = 0; k < 9; ++k) ns->M33[k] = 0.0;
+    sigma = 1.0;
+  }
+  if (ns->M > 0) {
+    for (int k = 0; k < 9; ++k) ns->MNN[k] /= ns->TL;
+  } else {
+    for (int k = 0; k < 9; ++k) ns->MNN[k] = 0.0;
+  }
+  if (ns->K > 0) {
+    for (int k = 0; k < 9; ++k) ns->M23[k] /= ns->TW;
+  } else {
+    for (int k = 0; k < 9; ++k) ns->M23[k] = 0.0;
+  }
+  for (int k = 0; k < 9; ++k) ns->M33[k] += sigma * (ns->M23[k] + ns->MNN[k]);
+  double qo[4];
+  rotation_from_covariance<double>(ns->M33, qo);
+  for (int k = 0; k < 4; ++k) ns->q_opt[k] = qo[k];
+  // c = Cw - R_opt^-1 * Cc
+  double qn[4];
+  {
+    const double len = sqrt((qo[0] * qo[0] + qo[1] * qo[1]) + (qo[2] * qo[2] + qo[3] * qo[3]));
+    qn[0] = -qo[0] / len;
+    qn[1] = -qo[1] / len;
+    qn[2] = -qo[2] / len;
+    qn[3] = qo[3] / len;
+  }
+  double rc[3];
+  quat_rotate<double>(qn, ns->Cc, rc);
+  const double cvec[3] = {ns->Cw[0] - rc[0], ns->Cw[1] - rc[1], ns->Cw[2] - rc[2]};
+  bool brk = false;
+  if (ns->N > 2) {
+    if (ns->cp_ok) {
+      const double fk = (double)ns->K / (double)(ns->K + ns->N), fn = (double)ns->N / (double)(ns->K + ns->N);
+      for (int r = 0; r < 3; ++r) ns->c_opt[r] = fk * ns->cp[r] + fn * cvec[r];
+    } else {
+      for (int r = 0; r < 3; ++r) ns->c_opt[r] = cvec[r];
+    }
+  } else {
+    if (ns->cp_ok) {
+      for (int r = 0; r < 3; ++r) ns->c_opt[r] = ns->cp[r];
+    } else {
+      brk = true;
+    }
+  }
+  ns->iter += 1;
+  if (brk || ns->iter >= 3) {
+    ns->stopped = 1;
+    // setRcw(R_opt); sett(R_opt * (-c_opt))  (:545-546)
+    const double nc[3] = {-ns->c_opt[0], -ns->c_opt[1], -ns->c_opt[2]};
+    double tt[3];
+    quat_rotate<double>(qo, nc, tt);
+    for (int k = 0; k < 4; ++k) pose_out->q[k] = (float)qo[k];
+    for (int k = 0; k < 3; ++k) pose_out->t[k] = (float)tt[k];
+    pose_out->refit_ok = 1;
+  }
+}
+
+void launch_nlsk_prepass(const FrameView& f, const int16_t* mask3, const float* weights3, const ReplayOut* pose,
+                         RefitBuffers rb, NlskState* ns, FrameStats* st, cudaStream_t s) {
+  nlsk_prepass_kernel<<<refit_grid(f.n, rb.num_sms), 256, 0, s>>>(f, mask3, weights3, pose, rb, ns, st);
+}
+void launch_nlsk_iteration(const FrameView& f, const int16_t* mask3, const float* weights3, RefitBuffers rb, NlskState* ns,
+                           FrameStats* st, ReplayOut* pose_out, cudaStream_t s) {
+  nlsk_iteration_kernel<<<refit_grid(f.n, rb.num_sms), 256, 0, s>>>(f, mask3, weights3, rb, ns, st, pose_out);
 }
 
 }  // namespace rpe

@@ -52,6 +52,12 @@ def sample_table(seed, n_corr, m, H):
     return out
 
 
+def sample_table_skip(seed, skip, n_corr, m, H):
+    out = np.empty((H, 4), np.int32)
+    lib.orc_sample_table_skip(C.c_uint(seed), C.c_longlong(skip), n_corr, m, H, _p(out))
+    return out
+
+
 def prosac_table(seed, n_corr, m, H, weights=None):
     out = np.empty((H, 4), np.int32)
     w = _arr(weights, np.float32)
