@@ -62,9 +62,11 @@ def make_frames(rpe, count, n, seed0=1000):
 
 
 class ClockSampler:
-    """nvidia-smi clock / throttle sampling DURING the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clock / throttle sampling DURING the timed region (B200_PROFILING.md recipe). The sampler is
+    started early (nvidia-smi needs ~0.5 s to produce its first line); only samples whose timestamp falls inside
+    a window [t0, t1] of time.time() are summarised."""
 
-    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+    FIELDS = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
               "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
               "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -78,37 +80,42 @@ class ClockSampler:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100",
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "50",
                  "-i", str(self.gpu)], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
     def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         if self.proc is None:
-            return out
+            return
         try:
             self.proc.terminate()
             self.proc.wait(timeout=5)
         except Exception:
             pass
+
+    def summarise(self, t0, t1):
+        import datetime
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         sm, mx, pw = [], [], []
         reasons = set()
         try:
             for line in open(self.path):
                 p = [x.strip() for x in line.split(",")]
-                if len(p) < 9:
+                if len(p) < 10:
                     continue
                 try:
-                    sm.append(float(p[1]))
-                    mx.append(float(p[2]))
-                    pw.append(float(p[3]))
+                    ts = datetime.datetime.strptime(p[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                    if ts < t0 - 0.05 or ts > t1 + 0.05:
+                        continue
+                    sm.append(float(p[2]))
+                    mx.append(float(p[3]))
+                    pw.append(float(p[4]))
                 except ValueError:
                     continue
-                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[5:9]):
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[6:10]):
                     if val.lower().startswith("active"):
                         reasons.add(name)
-            os.unlink(self.path)
         except Exception:
             pass
         if sm:
@@ -116,6 +123,12 @@ class ClockSampler:
                         "power_w_max": float(max(pw)) if pw else None})
         out["reasons"] = sorted(reasons)
         return out
+
+    def cleanup(self):
+        try:
+            os.unlink(self.path)
+        except Exception:
+            pass
 
 
 def load_measured_peaks():
@@ -276,7 +289,7 @@ def run_gpu(args, rank, world, local_rank):
             for _f in range(args.frames_per_step):
                 last = step_fn(k % args.contexts, k % args.ring)
                 k += 1
-            if stage_acc is not None:
+            if stage_acc is not None and (_s % 4 == 3 or _s == steps - 1):
                 sync_all()
                 for c in ctxs:
                     stage_acc.append(c.last_stage_ms())
@@ -291,6 +304,8 @@ def run_gpu(args, rank, world, local_rank):
         barrier()
         return ms, last
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     # --- FFMA peak of this device, same process/run (roofline denominator)
     ffma_scalar, ffma_packed = ctxs[0].measure_ffma_tflops(100)
 
@@ -302,17 +317,19 @@ def run_gpu(args, rank, world, local_rank):
 
     # --- `value`: inputs resident in HBM
     launches0 = sum(c.launch_count() for c in ctxs)
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     stage_acc = []
+    w0 = time.time()
     ms_dev, last_dev = timed(frame_device, args.steps, stage_acc)
-    clocks = sampler.stop()
+    w1 = time.time()
     launches = sum(c.launch_count() for c in ctxs) - launches0
     # --- `e2e`: host buffers, H2D + D2H inside the timed region
-    sampler2 = ClockSampler(local_rank)
-    sampler2.start()
+    w2 = time.time()
     ms_e2e, last_e2e = timed(frame_host, args.steps)
-    clocks_e2e = sampler2.stop()
+    w3 = time.time()
+    sampler.stop()
+    clocks = sampler.summarise(w0, w1)
+    clocks_e2e = sampler.summarise(w2, w3)
+    sampler.cleanup()
 
     # --- single blocking frame latency through the C-ABI with host buffers (one context)
     lat = []
@@ -438,7 +455,10 @@ def run_single_frame_sharded(args, torch, dist, rpe, ctx, stream, frames, tables
     # identical frame on every rank: regenerate rank 0's frame 0
     f0 = make_frames(rpe, 1, N_CORR, seed0=1000)[0]
     tab = rpe.sample_table(1, N_CORR, 3, N_HYP)
-    chunk = N_HYP // world
+    from rgbd_pose_estimation_b200 import sharding
+    b0, e0 = sharding.slot_range(rank, world, N_HYP)
+    if N_HYP % world:
+        return {"skipped": "N_HYP not divisible by world size (in-place all-gather needs equal chunks)"}
     with torch.cuda.stream(stream):
         xw = torch.from_numpy(f0["xw"]).to(dev)
         xc = torch.from_numpy(f0["xc"]).to(dev)
@@ -454,8 +474,8 @@ def run_single_frame_sharded(args, torch, dist, rpe, ctx, stream, frames, tables
             e1 = torch.cuda.Event(enable_timing=True)
             e0.record(stream)
             ctx.generate(METHOD_SHINJI, tab)  # resets the vote table; generation is replicated (cheap)
-            ctx.score(METHOD_SHINJI, rank * chunk, (rank + 1) * chunk, thr3d=THR3D)
-            dist.all_gather_into_tensor(votes, votes[rank * chunk:(rank + 1) * chunk].clone())
+            ctx.score(METHOD_SHINJI, b0, e0, thr3d=THR3D)
+            dist.all_gather_into_tensor(votes, votes[b0:e0].clone())
             res = ctx.finish(METHOD_SHINJI, N_HYP, thr3d=THR3D, confidence=CONF, want_mask=False)
             e1.record(stream)
             torch.cuda.synchronize()
@@ -474,7 +494,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--frames-per-step", type=int, default=24)
+    ap.add_argument("--frames-per-step", type=int, default=96)
     ap.add_argument("--ring", type=int, default=24, help="distinct frames resident per GPU (>L2 in total)")
     ap.add_argument("--contexts", type=int, default=3, help="rpe contexts (streams) per GPU, frames round-robin")
     ap.add_argument("--gn-iters", type=int, default=3)

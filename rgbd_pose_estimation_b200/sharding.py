@@ -1,0 +1,67 @@
+"""Host-side partitioning for the two multi-GPU modes and the sequential rule on a vote table.
+
+* frames sharded (config #5): rank r takes frames r, r+G, r+2G, ... — no data-path collective;
+* hypotheses sharded (config #4): rank r scores the slot range ``slot_range(r, G, n_slots)``; the int32 vote
+  table is all-gathered (4 KB at H = 1024) and every rank replays the reference's keep-best / adaptive-stop rule
+  (AbsoluteOrientation.hpp:145-151, P3P.hpp:296-318) redundantly, so all ranks agree on the winner.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import capi
+
+_MODEL_POINTS = {0: 3, 1: 4, 2: 3, 3: 3, 4: 3, 5: 3, 6: 4}
+_MODALITIES = {0: 1, 1: 1, 2: 2, 3: 2, 4: 2, 5: 3, 6: 1}
+
+
+def frame_indices(rank: int, world: int, n_frames: int) -> list[int]:
+    return list(range(rank, n_frames, world))
+
+
+def slot_range(rank: int, world: int, n_slots: int) -> tuple[int, int]:
+    """Contiguous, balanced ranges covering [0, n_slots) exactly once."""
+    base, rem = divmod(n_slots, world)
+    begin = rank * base + min(rank, rem)
+    return begin, begin + base + (1 if rank < rem else 0)
+
+
+def gather_votes(dist, votes_local: np.ndarray, rank: int, world: int, n_slots: int) -> np.ndarray:
+    """All-gather ragged slot ranges with any torch.distributed backend (gloo on CPU, NCCL on GPU tensors)."""
+    import torch
+    sizes = [slot_range(r, world, n_slots) for r in range(world)]
+    width = max(e - b for b, e in sizes)
+    mine = torch.full((width,), -1, dtype=torch.int32)
+    mine[: votes_local.shape[0]] = torch.from_numpy(np.ascontiguousarray(votes_local, dtype=np.int32))
+    parts = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(parts, mine)
+    out = np.empty(n_slots, np.int32)
+    for r, (b, e) in enumerate(sizes):
+        out[b:e] = parts[r][: e - b].numpy()
+    return out
+
+
+def replay(votes: np.ndarray, method: int, n_corr: int, confidence: float, iter_in: int | None = None):
+    """The reference's sequential rule over a complete vote table (slot = iteration*slots + slot, -1 = empty).
+    Returns (winner, max_votes, iter_final). Uses the same bit-reproducible rule as the device replay kernel."""
+    S = capi.method_slots(method)
+    K = _MODEL_POINTS[method]
+    m = _MODALITIES[method]
+    H = votes.shape[0] // S if iter_in is None else iter_in
+    best, win, it = -1, -1, H
+    ii = 0
+    nf = np.float32(n_corr)
+    while ii < it and ii < votes.shape[0] // S:
+        for s in range(S):
+            v = int(votes[ii * S + s])
+            if v < 0:
+                continue
+            if v > best:
+                best, win = v, ii * S + s
+                if m == 1:
+                    ep = np.float32(n_corr - v) / nf
+                else:
+                    ep = np.float32(np.float32(n_corr * m - v) / nf) / np.float32(m)
+                it = capi.update_num_iters(float(np.float32(confidence)), float(ep), K, it)
+        ii += 1
+    return win, best, it
