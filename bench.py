@@ -456,7 +456,7 @@ def run_single_frame_sharded(args, torch, dist, rpe, ctx, stream, frames, tables
     f0 = make_frames(rpe, 1, N_CORR, seed0=1000)[0]
     tab = rpe.sample_table(1, N_CORR, 3, N_HYP)
     from rgbd_pose_estimation_b200 import sharding
-    b0, e0 = sharding.slot_range(rank, world, N_HYP)
+    sb, se = sharding.slot_range(rank, world, N_HYP)
     if N_HYP % world:
         return {"skipped": "N_HYP not divisible by world size (in-place all-gather needs equal chunks)"}
     with torch.cuda.stream(stream):
@@ -474,8 +474,8 @@ def run_single_frame_sharded(args, torch, dist, rpe, ctx, stream, frames, tables
             e1 = torch.cuda.Event(enable_timing=True)
             e0.record(stream)
             ctx.generate(METHOD_SHINJI, tab)  # resets the vote table; generation is replicated (cheap)
-            ctx.score(METHOD_SHINJI, b0, e0, thr3d=THR3D)
-            dist.all_gather_into_tensor(votes, votes[b0:e0].clone())
+            ctx.score(METHOD_SHINJI, sb, se, thr3d=THR3D)
+            dist.all_gather_into_tensor(votes, votes[sb:se].clone())
             res = ctx.finish(METHOD_SHINJI, N_HYP, thr3d=THR3D, confidence=CONF, want_mask=False)
             e1.record(stream)
             torch.cuda.synchronize()

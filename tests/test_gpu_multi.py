@@ -1,0 +1,58 @@
+"""GPU (needs >= 2 devices, skipped otherwise): hypothesis-sharded single frame across two contexts on two
+GPUs, vote ranges exchanged on the host (the NCCL path is exercised by bench.py under torchrun), and frame sharding."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _ngpu(rpe):
+    import ctypes
+    n = ctypes.c_int(0)
+    rpe.lib.rpe_device_count(ctypes.byref(n))
+    return n.value
+
+
+def test_hypothesis_sharded_frame_two_gpus(rpe, orc):
+    if _ngpu(rpe) < 2:
+        pytest.skip("needs 2 GPUs")
+    from rgbd_pose_estimation_b200 import sharding
+    orc.set_math_mode(orc.DET)
+    n, H = 20000, 1024
+    q, t = rpe.sim_pose(3)
+    Q, P, _ = rpe.sim_3d_3d(4, q, t, n)
+    S = rpe.sample_table(1, n, 3, H)
+    ref = orc.ransac(0, S, thr3d=0.25, confidence=0.9999, full=True, xc=P, xw=Q)
+    ctxs = [rpe.Context(0), rpe.Context(1)]
+    votes = np.empty(H, np.int32)
+    for r, c in enumerate(ctxs):
+        c.upload(xc=P, xw=Q)
+        c.generate("shinji", S)
+        b, e = sharding.slot_range(r, 2, H)
+        c.score("shinji", b, e, thr3d=0.25)
+        votes[b:e] = c.get_votes(H)[b:e]
+    assert np.array_equal(votes, ref["votes"])
+    for c in ctxs:
+        c.set_votes(votes)
+        out = c.finish("shinji", H, thr3d=0.25, confidence=0.9999)
+        assert (out["winner"], out["max_votes"], out["iter_final"]) == (ref["winner"], ref["max_votes"], ref["iter_final"])
+        assert np.array_equal(out["mask"], ref["mask"])
+        c.close()
+
+
+def test_partial_range_scoring_single_gpu(rpe, orc, gpu_ctx):
+    """rpe_score over two disjoint slot ranges on one device == one full pass (the per-rank work of config #4)."""
+    orc.set_math_mode(orc.DET)
+    n, H = 5000, 700
+    q, t = rpe.sim_pose(5)
+    Q, P, _ = rpe.sim_3d_3d(6, q, t, n)
+    S = rpe.sample_table(1, n, 3, H)
+    ref = orc.ransac(0, S, thr3d=0.25, confidence=0.9999, full=True, xc=P, xw=Q)
+    gpu_ctx.upload(xc=P, xw=Q)
+    gpu_ctx.generate("shinji", S)
+    gpu_ctx.score("shinji", 0, 300, thr3d=0.25)
+    gpu_ctx.score("shinji", 300, H, thr3d=0.25)
+    assert np.array_equal(gpu_ctx.get_votes(H), ref["votes"])
+    out = gpu_ctx.finish("shinji", H, thr3d=0.25, confidence=0.9999)
+    assert (out["winner"], out["iter_final"]) == (ref["winner"], ref["iter_final"])
+    assert np.array_equal(out["mask"], ref["mask"])
