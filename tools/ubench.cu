@@ -68,22 +68,98 @@ __global__ void __launch_bounds__(256) k(float* sink, const float* src, int iter
 }
 
 // MODE 6: the real data path — 3 broadcast LDS.128 per pair feeding two hypotheses held in registers
+template <int HPT>
 __global__ void __launch_bounds__(256) k6(float* sink, const float* src, int iters) {
   extern __shared__ float4 tile[];
   for (int i = threadIdx.x; i < 256 * 3; i += blockDim.x) tile[i] = make_float4(src[i & 31], src[(i + 1) & 31], src[(i + 2) & 31], src[(i + 3) & 31]);
   __syncthreads();
-  float r[2][12];
-  for (int h = 0; h < 2; ++h)
+  float r[HPT][12];
+  for (int h = 0; h < HPT; ++h)
     for (int i = 0; i < 12; ++i) r[h][i] = src[i + h] + 1e-6f * threadIdx.x;
   const float2 nlo = make_float2(-src[24], -src[24]);
   const float band = -src[25];  // never borderline in this experiment
-  int cnt[2] = {0, 0};
+  int cnt[HPT];
+  for (int h = 0; h < HPT; ++h) cnt[h] = 0;
   bool flag = false;
   for (int it = 0; it < iters; ++it) {
     const float4* sp = tile + (it & 31) * 8 * 3;
 #pragma unroll
     for (int pp = 0; pp < 8; ++pp) {
       const float4 a = sp[pp * 3], b = sp[pp * 3 + 1], c = sp[pp * 3 + 2];
+      const float2 X0 = make_float2(a.x, a.y), X1 = make_float2(a.z, a.w), X2 = make_float2(b.x, b.y);
+      const float2 P0 = make_float2(b.z, b.w), P1 = make_float2(c.x, c.y), P2 = make_float2(c.z, c.w);
+#pragma unroll
+      for (int h = 0; h < HPT; ++h) {
+        float2 e0 = __fadd2_rn(P0, make_float2(r[h][9], r[h][9]));
+        float2 e1 = __fadd2_rn(P1, make_float2(r[h][10], r[h][10]));
+        float2 e2 = __fadd2_rn(P2, make_float2(r[h][11], r[h][11]));
+        e0 = __ffma2_rn(make_float2(r[h][0], r[h][0]), X0, e0);
+        e1 = __ffma2_rn(make_float2(r[h][3], r[h][3]), X0, e1);
+        e2 = __ffma2_rn(make_float2(r[h][6], r[h][6]), X0, e2);
+        e0 = __ffma2_rn(make_float2(r[h][1], r[h][1]), X1, e0);
+        e1 = __ffma2_rn(make_float2(r[h][4], r[h][4]), X1, e1);
+        e2 = __ffma2_rn(make_float2(r[h][7], r[h][7]), X1, e2);
+        e0 = __ffma2_rn(make_float2(r[h][2], r[h][2]), X2, e0);
+        e1 = __ffma2_rn(make_float2(r[h][5], r[h][5]), X2, e1);
+        e2 = __ffma2_rn(make_float2(r[h][8], r[h][8]), X2, e2);
+        float2 s = __ffma2_rn(e0, e0, nlo);
+        s = __ffma2_rn(e1, e1, s);
+        s = __ffma2_rn(e2, e2, s);
+        cnt[h] += (int)(__float_as_uint(s.x) >> 31) + (int)(__float_as_uint(s.y) >> 31);
+        flag = flag || (fabsf(s.x) <= band) || (fabsf(s.y) <= band);
+      }
+    }
+    if (flag) {
+      sink[1] = 1.f;
+      flag = false;
+    }
+  }
+  int tot = 0;
+  for (int h = 0; h < HPT; ++h) tot += cnt[h];
+  if (tot == 123456789) sink[0] = 1.f;
+}
+template <int HPT>
+void run6(float* sink, float* src, int ctas_per_sm) {
+  cudaEvent_t a, b;
+  cudaEventCreate(&a);
+  cudaEventCreate(&b);
+  const size_t smem = (size_t)(220 * 1024 / ctas_per_sm) & ~(size_t)1023;
+  cudaFuncSetAttribute(k6<HPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const int blocks = 148 * ctas_per_sm, iters = 256;
+  k6<HPT><<<blocks, 256, smem>>>(sink, src, iters);
+  cudaEventRecord(a);
+  k6<HPT><<<blocks, 256, smem>>>(sink, src, iters);
+  cudaEventRecord(b);
+  cudaEventSynchronize(b);
+  float ms;
+  cudaEventElapsedTime(&ms, a, b);
+  const double inst = (double)blocks * 256 * iters * 8 * HPT * 15;
+  printf("%-32s %d CTA/SM (%2d warps/SM) %8.3f ms = %6.2f T lane-ops/s (%.0f%% of 37.2)\n", (HPT == 1 ? "smem-fed, 1 hyp/thread" : HPT == 2 ? "smem-fed, 2 hyp/thread" : HPT == 4 ? "smem-fed, 4 hyp/thread" : "smem-fed, 8 hyp/thread"), ctas_per_sm,
+         8 * ctas_per_sm, ms, 2 * inst / ms / 1e9, 2 * inst / ms / 1e9 / 37.22 * 100);
+}
+
+
+// MODE 7: like k6<2> but the next pair's three float4 are loaded explicitly one pair ahead
+__global__ void __launch_bounds__(256) k7(float* sink, const float* src, int iters) {
+  extern __shared__ float4 tile[];
+  for (int i = threadIdx.x; i < 256 * 3 + 8; i += blockDim.x) tile[i] = make_float4(src[i & 31], src[(i + 1) & 31], src[(i + 2) & 31], src[(i + 3) & 31]);
+  __syncthreads();
+  float r[2][12];
+  for (int h = 0; h < 2; ++h)
+    for (int i = 0; i < 12; ++i) r[h][i] = src[i + h] + 1e-6f * threadIdx.x;
+  const float2 nlo = make_float2(-src[24], -src[24]);
+  const float band = -src[25];
+  int cnt[2] = {0, 0};
+  bool flag = false;
+  float4 na = tile[0], nb = tile[1], nc = tile[2];
+  for (int it = 0; it < iters; ++it) {
+    const float4* sp = tile + (it & 31) * 8 * 3;
+#pragma unroll
+    for (int pp = 0; pp < 8; ++pp) {
+      const float4 a = na, b = nb, c = nc;
+      na = sp[(pp + 1) * 3];
+      nb = sp[(pp + 1) * 3 + 1];
+      nc = sp[(pp + 1) * 3 + 2];
       const float2 X0 = make_float2(a.x, a.y), X1 = make_float2(a.z, a.w), X2 = make_float2(b.x, b.y);
       const float2 P0 = make_float2(b.z, b.w), P1 = make_float2(c.x, c.y), P2 = make_float2(c.z, c.w);
 #pragma unroll
@@ -114,23 +190,63 @@ __global__ void __launch_bounds__(256) k6(float* sink, const float* src, int ite
   }
   if (cnt[0] + cnt[1] == 123456789) sink[0] = 1.f;
 }
-void run6(float* sink, float* src, int ctas_per_sm) {
+// MODE 8: no count / flag at all (pure FP2 + LDS)
+__global__ void __launch_bounds__(256) k8(float* sink, const float* src, int iters) {
+  extern __shared__ float4 tile[];
+  for (int i = threadIdx.x; i < 256 * 3 + 8; i += blockDim.x) tile[i] = make_float4(src[i & 31], src[(i + 1) & 31], src[(i + 2) & 31], src[(i + 3) & 31]);
+  __syncthreads();
+  float r[2][12];
+  for (int h = 0; h < 2; ++h)
+    for (int i = 0; i < 12; ++i) r[h][i] = src[i + h] + 1e-6f * threadIdx.x;
+  const float2 nlo = make_float2(-src[24], -src[24]);
+  float2 tot[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+  for (int it = 0; it < iters; ++it) {
+    const float4* sp = tile + (it & 31) * 8 * 3;
+#pragma unroll
+    for (int pp = 0; pp < 8; ++pp) {
+      const float4 a = sp[pp * 3], b = sp[pp * 3 + 1], c = sp[pp * 3 + 2];
+      const float2 X0 = make_float2(a.x, a.y), X1 = make_float2(a.z, a.w), X2 = make_float2(b.x, b.y);
+      const float2 P0 = make_float2(b.z, b.w), P1 = make_float2(c.x, c.y), P2 = make_float2(c.z, c.w);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        float2 e0 = __fadd2_rn(P0, make_float2(r[h][9], r[h][9]));
+        float2 e1 = __fadd2_rn(P1, make_float2(r[h][10], r[h][10]));
+        float2 e2 = __fadd2_rn(P2, make_float2(r[h][11], r[h][11]));
+        e0 = __ffma2_rn(make_float2(r[h][0], r[h][0]), X0, e0);
+        e1 = __ffma2_rn(make_float2(r[h][3], r[h][3]), X0, e1);
+        e2 = __ffma2_rn(make_float2(r[h][6], r[h][6]), X0, e2);
+        e0 = __ffma2_rn(make_float2(r[h][1], r[h][1]), X1, e0);
+        e1 = __ffma2_rn(make_float2(r[h][4], r[h][4]), X1, e1);
+        e2 = __ffma2_rn(make_float2(r[h][7], r[h][7]), X1, e2);
+        e0 = __ffma2_rn(make_float2(r[h][2], r[h][2]), X2, e0);
+        e1 = __ffma2_rn(make_float2(r[h][5], r[h][5]), X2, e1);
+        e2 = __ffma2_rn(make_float2(r[h][8], r[h][8]), X2, e2);
+        float2 s = __ffma2_rn(e0, e0, tot[h]);
+        s = __ffma2_rn(e1, e1, s);
+        tot[h] = __ffma2_rn(e2, e2, s);
+      }
+    }
+  }
+  if (tot[0].x + tot[1].y + nlo.x == 123456789.f) sink[0] = 1.f;
+}
+template <class K>
+void run_k(const char* name, K kern, float* sink, float* src, int ctas_per_sm) {
   cudaEvent_t a, b;
   cudaEventCreate(&a);
   cudaEventCreate(&b);
   const size_t smem = (size_t)(220 * 1024 / ctas_per_sm) & ~(size_t)1023;
-  cudaFuncSetAttribute(k6, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   const int blocks = 148 * ctas_per_sm, iters = 256;
-  k6<<<blocks, 256, smem>>>(sink, src, iters);
+  kern<<<blocks, 256, smem>>>(sink, src, iters);
   cudaEventRecord(a);
-  k6<<<blocks, 256, smem>>>(sink, src, iters);
+  kern<<<blocks, 256, smem>>>(sink, src, iters);
   cudaEventRecord(b);
   cudaEventSynchronize(b);
   float ms;
   cudaEventElapsedTime(&ms, a, b);
   const double inst = (double)blocks * 256 * iters * 8 * 2 * 15;
-  printf("%-32s %d CTA/SM (%2d warps/SM) %8.3f ms = %6.2f T lane-ops/s (%.0f%% of 37.2)\n", "smem-fed scorer loop (15 FP2/unit)", ctas_per_sm,
-         8 * ctas_per_sm, ms, 2 * inst / ms / 1e9, 2 * inst / ms / 1e9 / 37.22 * 100);
+  printf("%-32s %d CTA/SM (%2d warps/SM) %8.3f ms = %6.2f T lane-ops/s (%.0f%% of 37.2)\n", name, ctas_per_sm, 8 * ctas_per_sm, ms,
+         2 * inst / ms / 1e9, 2 * inst / ms / 1e9 / 37.22 * 100);
 }
 
 template <int MODE>
@@ -186,7 +302,12 @@ int main() {
   run<5>("scorer mix + count + band flag", 2 * 17, sink, src);
   for (int c : {1, 2, 3, 4, 6, 8}) run_occ<5>("scorer mix + count + flag", 2 * 17, sink, src, c);
   for (int c : {1, 2, 4, 8}) run_occ<0>("FFMA2 vector reused", 16, sink, src, c);
-  for (int c : {1, 2, 4}) run6(sink, src, c);
+  for (int c : {2, 4}) run_k("smem-fed prefetch 1 pair ahead", k7, sink, src, c);
+  for (int c : {2, 4}) run_k("smem-fed, no count/flag", k8, sink, src, c);
+  for (int c : {1, 2, 4}) run6<1>(sink, src, c);
+  for (int c : {1, 2, 4}) run6<2>(sink, src, c);
+  for (int c : {1, 2}) run6<4>(sink, src, c);
+  for (int c : {1}) run6<8>(sink, src, c);
   printf("peak lane-ops/s at 1.965 GHz: %.2f T\n", 148 * 128 * 1.965e9 / 1e12);
   return 0;
 }
