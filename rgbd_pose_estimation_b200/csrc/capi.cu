@@ -290,10 +290,12 @@ int claim_slot(rpe_ctx* ctx, int* slot) {
   return RPE_OK;
 }
 
+bool g_force_exact_multi = false;  // test hook: run the exact-order kernel for the non-AO families
+
 // score the slot range with the best available kernel, including the exact fix-up
 int score_range(rpe_ctx* ctx, int method, int slot_begin, int slot_end, Thresh th) {
   FrameView f = make_view(ctx);
-  if (method == RPE_SHINJI) {
+  if (method == RPE_SHINJI || !g_force_exact_multi) {
     const bool tm = ctx->timing && ctx->ev_ok;
     if (tm) cudaEventRecord(ctx->ev_fast[0], ctx->stream);
     launch_score_fast(method, f, ctx->d_gen, ctx->d_fast, slot_begin, slot_end, th, ctx->d_votes, ctx->d_stats, ctx->wl,
@@ -370,7 +372,7 @@ int do_ransac(rpe_ctx* ctx, int method, const int32_t* samples, int H, float thr
   }
   launch_replay_begin(ctx->d_rs, H, ctx->stream);
   ctx->launches++;
-  if (method == RPE_SHINJI) {
+  if (method == RPE_SHINJI || !g_force_exact_multi) {
     rc = ensure_packed(ctx, kind_for_method(method));
     if (rc) return rc;
   }
@@ -797,7 +799,7 @@ int rpe_score(rpe_ctx* ctx, int method, int slot_begin, int slot_end, float thr3
   int rc = check_arrays(ctx, method);
   if (rc) return rc;
   CK(cudaSetDevice(ctx->device));
-  if (method == RPE_SHINJI) {
+  if (method == RPE_SHINJI || !g_force_exact_multi) {
     rc = ensure_packed(ctx, kind_for_method(method));
     if (rc) return rc;
   }
@@ -920,6 +922,10 @@ int rpe_last_stage_ms(rpe_ctx* ctx, float ms[8]) {
 // test hook: choose the packed (FFMA2) or scalar (FFMA) fast kernel
 int rpe_debug_set_packed(int packed) {
   rpe::set_use_packed(packed != 0);
+  return RPE_OK;
+}
+int rpe_debug_force_exact_multi(int v) {
+  g_force_exact_multi = v != 0;
   return RPE_OK;
 }
 int rpe_debug_set_nosync(int v) {

@@ -79,7 +79,7 @@ struct __align__(16) HypFast {
 
 struct FrameStats {
   unsigned int m_corr_bits;  // max_i (|x_w,i| + |x_c,i|) over finite points, float bits
-  unsigned int m_bv_bits;    // reserved
+  unsigned int m_bv_bits;    // max_i max(|n_w,i|, |n_c,i|) over finite normals, float bits (normal-test guard band)
   unsigned int t_max_bits;   // max_h |t_h| over valid hypotheses, float bits
   unsigned int wl_count;     // borderline worklist length
   unsigned int wl_overflow;  // 1 if the worklist overflowed -> exact rescoring of the frame

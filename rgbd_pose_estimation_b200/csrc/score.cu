@@ -80,6 +80,8 @@ void launch_reset_corr_bound(FrameStats* st, cudaStream_t s) { reset_corr_bound_
 struct PackSrc {
   const float* a[5];
   int count;
+  int idx_nw, idx_nc;     // positions of the normal arrays among the sources, -1 if absent
+  const float* valid_xc;  // raw camera points: an all-NaN point makes its packed camera normal NaN (isValid gate)
 };
 
 // A CTA packs kPackPairs pairs of correspondences (2j, 2j+1). The raw xyz triples of the CTA's slice are
@@ -104,6 +106,25 @@ pack_kernel(PackSrc src, int n, int npairs_pad, int f4_per_pair, float4* __restr
   }
   __syncthreads();
   const int pairs_here = min(kPackPairs, npairs_pad - pair0);
+  // The normal test sits inside `if (adapter.isValid(c))` (AbsoluteOrientationNormal.hpp:246,323,398): a correspondence
+  // whose camera point is all-NaN must never cast a normal vote -> poison its packed camera normal.
+  float nloc = 0.f;
+  if (src.idx_nc >= 0) {
+    for (int i = threadIdx.x; i < 2 * pairs_here; i += blockDim.x) {
+      const int c = c_base + i;
+      float* pn = &sm_raw[src.idx_nc * floats + i * 3];
+      if (c < n) {
+        const float* pw = &sm_raw[src.idx_nw * floats + i * 3];
+        const float a = sqrtf(pn[0] * pn[0] + pn[1] * pn[1] + pn[2] * pn[2]);
+        const float b = sqrtf(pw[0] * pw[0] + pw[1] * pw[1] + pw[2] * pw[2]);
+        if (a == a && a < CUDART_INF_F) nloc = fmaxf(nloc, a);
+        if (b == b && b < CUDART_INF_F) nloc = fmaxf(nloc, b);
+        const float v0 = src.valid_xc[3 * (size_t)c], v1 = src.valid_xc[3 * (size_t)c + 1], v2 = src.valid_xc[3 * (size_t)c + 2];
+        if (!(v0 == v0 || v1 == v1 || v2 == v2)) pn[0] = pn[1] = pn[2] = CUDART_NAN_F;
+      }
+    }
+    __syncthreads();
+  }
   const int total_f4 = pairs_here * f4_per_pair;
   const int fpp = f4_per_pair * 4;
   for (int o = threadIdx.x; o < total_f4; o += blockDim.x) {
@@ -142,16 +163,23 @@ pack_kernel(PackSrc src, int n, int npairs_pad, int f4_per_pair, float4* __restr
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) mloc = fmaxf(mloc, __shfl_xor_sync(0xffffffffu, mloc, o));
   if ((threadIdx.x & 31) == 0 && mloc > 0.f) atomic_max_nonneg(&st->m_corr_bits, mloc);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) nloc = fmaxf(nloc, __shfl_xor_sync(0xffffffffu, nloc, o));
+  if ((threadIdx.x & 31) == 0 && nloc > 0.f) atomic_max_nonneg(&st->m_bv_bits, nloc);
 }
 
 void launch_pack(const FrameView& f, int kind, float4* pk_out, FrameStats* st, cudaStream_t s) {
   PackSrc src;
   src.count = 0;
+  src.idx_nw = src.idx_nc = -1;
+  src.valid_xc = f.xc;
   src.a[src.count++] = f.xw;
   if (kind & 2) src.a[src.count++] = f.xc;
   if (kind & 1) src.a[src.count++] = f.bv;
   if (kind & 4) {
+    src.idx_nw = src.count;
     src.a[src.count++] = f.nw;
+    src.idx_nc = src.count;
     src.a[src.count++] = f.nc;
   }
   const int blocks = (f.npairs_pad + kPackPairs - 1) / kPackPairs;
@@ -354,6 +382,261 @@ score3d_fast_kernel(const float4* __restrict__ pk, int npairs_pad, int pairs_per
     if (slot[k] >= 0 && cnt[k] != 0) atomicAdd(&votes[slot[k]], cnt[k]);
 }
 
+// ================================================================================================
+// fast tiled scorer — 2-D, 3-D and normal modalities in any combination (all other estimator families)
+// ================================================================================================
+// Shared per (pair, hypothesis): ny = -(R x_w + t) = nR x_w + nt (9 FFMA2). Then
+//   3-D   : e = x_c + ny, s3 = |e|^2 - thr^2                      (3 FADD2 + 3 FFMA2)    inlier <=> s3 < 0
+//   2-D   : d' = ny.b, n2 = |ny|^2, F' = d'|d'| + cos_thr^2 n2     (6 FP2 + 2x(FMUL,FFMA))  inlier <=> F' < 0
+//           (F' < 0 <=> y.b > 0 and (y.b)^2 > cos_thr^2 |y|^2 <=> normalize(y).b > cos_thr, cos_thr > 0 always: P3P.hpp:323)
+//   normal: g' = cos_nl - n_c.(R n_w) = n_c.(nR n_w) + cos_nl     (3 FMUL2 + 6 FFMA2 + 3 FFMA2)  inlier <=> g' < 0
+// Guard bands (same rigorous scheme as §4.2 of DESIGN.md; u = 2^-24, M2 >= |x_w| + |t|, Nn >= |n_c||n_w|):
+//   2-D   : |F'| <= cos_thr * u * 1.1 * (32 M2 (1 + n2) + 26 n2)   (reference error 19.1u M2/|y| + 7u, fast 12.5u M2/|y| + 5.5u in
+//           cosine units, times 2 cos_thr |y|^2, |y| <= (1 + n2)/2)
+//   normal: |g'| <= u * 1.1 * (29 Nn + 2)                          (reference 19.1u Nn, fast 9.2u Nn + u)
+// Packed layout per pair: x_w, [x_c], [b], [n_w, n_c], 6 floats each (see pack_kernel), padded to whole float4.
+template <int KIND>
+struct KindTraits {
+  static constexpr bool k2 = (KIND & 1) != 0, k3 = (KIND & 2) != 0, kn = (KIND & 4) != 0;
+  static constexpr int arrays = 1 + (k2 ? 1 : 0) + (k3 ? 1 : 0) + (kn ? 2 : 0);
+  static constexpr int f4pp = (arrays * 6 + 3) / 4;
+  static constexpr int off_xc = 6;                       // floats
+  static constexpr int off_bv = 6 + (k3 ? 6 : 0);
+  static constexpr int off_nw = 6 + (k3 ? 6 : 0) + (k2 ? 6 : 0);
+  static constexpr int off_nc = off_nw + 6;
+};
+
+struct BandConsts {
+  float band3;        // on s3
+  float a0_2d, a1_2d; // band2 = a0 + a1 * n2
+  float band_n;       // on g'
+};
+
+template <int KIND, int TILE, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1)
+score_multi_fast_kernel(const float4* __restrict__ pk, int npairs_pad, int pairs_per_cta, const HypFast* __restrict__ fast,
+                        const HypGen* __restrict__ gen, int slot_begin, int slot_end, Thresh th,
+                        int32_t* __restrict__ votes, FrameStats* __restrict__ st, Worklist wl) {
+  typedef KindTraits<KIND> KT;
+  constexpr int HPT = 2;
+  constexpr int SUB = kSubPairs;
+  constexpr int F4 = KT::f4pp;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float4(*tile)[TILE * F4] = reinterpret_cast<float4(*)[TILE * F4]>(smem_raw);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + 2 * TILE * F4 * sizeof(float4));
+
+  const int tid = threadIdx.x;
+  const int p_begin = blockIdx.x * pairs_per_cta;
+  const int p_end = min(p_begin + pairs_per_cta, npairs_pad);
+  const int npairs = p_end - p_begin;
+  const int ntiles = (npairs + TILE - 1) / TILE;
+
+  float nR[HPT][9], nt[HPT][3];
+  int slot[HPT], cnt[HPT];
+#pragma unroll
+  for (int k = 0; k < HPT; ++k) {
+    slot[k] = slot_begin + (blockIdx.y * HPT + k) * THREADS + tid;
+    const bool live = slot[k] < slot_end && gen[slot[k]].valid != 0;
+    const HypFast* h = &fast[live ? slot[k] : slot_begin];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) nR[k][i] = live ? h->nR[i] : CUDART_NAN_F;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) nt[k][i] = live ? h->nt[i] : CUDART_NAN_F;
+    if (!live) slot[k] = -1;
+    cnt[k] = 0;
+  }
+  // guard bands from the per-frame magnitude bounds
+  BandConsts bc;
+  {
+    const float u = 5.9604644775390625e-08f;
+    const float mcorr = __uint_as_float(st->m_corr_bits), tmax = __uint_as_float(st->t_max_bits);
+    const float M = (mcorr + tmax) * 1.0001f;  // >= |x_w| + |x_c| + |t| (and >= |x_w| + |t|)
+    bc.band3 = th.thr3d * u * (64.f * M + 16.f * th.thr3d);
+    bc.a0_2d = th.cos_thr * u * 1.1f * (32.f * M);
+    bc.a1_2d = th.cos_thr * u * 1.1f * (32.f * M + 26.f);
+    const float nmax = __uint_as_float(st->m_bv_bits) * 1.0001f;
+    bc.band_n = u * 1.1f * (29.f * nmax * nmax + 2.f);
+  }
+  const float thr2 = __fmul_rn(th.thr3d, th.thr3d);
+  const float2 nlo = make_float2(-thr2, -thr2);
+  const float c2 = (float)((double)th.cos_thr * (double)th.cos_thr);
+  const float2 cnl2 = make_float2(th.cos_nl, th.cos_nl);
+
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  if (tid == 0) {
+    for (int t = 0; t < 2 && t < ntiles; ++t) {
+      const int tp = min(TILE, npairs - t * TILE);
+      const uint32_t bytes = (uint32_t)tp * F4 * 16u;
+      mbar_expect_tx(&bars[t], bytes);
+      tma_load_1d(&tile[t][0], pk + (size_t)(p_begin + t * TILE) * F4, bytes, &bars[t]);
+    }
+  }
+
+  // One (pair, hypothesis) unit. rescan == false: count sign bits and OR the band flags;
+  // rescan == true : take borderline evaluations out of the count and queue them for the exact fix-up.
+  auto unit = [&](const float* rec, int k, bool rescan, bool& flag, int corr0) {
+    const float2 X0 = make_float2(rec[0], rec[1]), X1 = make_float2(rec[2], rec[3]), X2 = make_float2(rec[4], rec[5]);
+    float2 ny0 = make_float2(nt[k][0], nt[k][0]), ny1 = make_float2(nt[k][1], nt[k][1]), ny2 = make_float2(nt[k][2], nt[k][2]);
+    ny0 = __ffma2_rn(make_float2(nR[k][2], nR[k][2]), X2, ny0);
+    ny1 = __ffma2_rn(make_float2(nR[k][5], nR[k][5]), X2, ny1);
+    ny2 = __ffma2_rn(make_float2(nR[k][8], nR[k][8]), X2, ny2);
+    ny0 = __ffma2_rn(make_float2(nR[k][1], nR[k][1]), X1, ny0);
+    ny1 = __ffma2_rn(make_float2(nR[k][4], nR[k][4]), X1, ny1);
+    ny2 = __ffma2_rn(make_float2(nR[k][7], nR[k][7]), X1, ny2);
+    ny0 = __ffma2_rn(make_float2(nR[k][0], nR[k][0]), X0, ny0);
+    ny1 = __ffma2_rn(make_float2(nR[k][3], nR[k][3]), X0, ny1);
+    ny2 = __ffma2_rn(make_float2(nR[k][6], nR[k][6]), X0, ny2);
+    float val[3][2];   // per modality (2-D, 3-D, normal) the decision value of both correspondences
+    float bnd[3][2];
+    if (KT::k3) {
+      const float* p = rec + KT::off_xc;
+      const float2 e0 = __fadd2_rn(make_float2(p[0], p[1]), ny0);
+      const float2 e1 = __fadd2_rn(make_float2(p[2], p[3]), ny1);
+      const float2 e2 = __fadd2_rn(make_float2(p[4], p[5]), ny2);
+      float2 s = __ffma2_rn(e0, e0, nlo);
+      s = __ffma2_rn(e1, e1, s);
+      s = __ffma2_rn(e2, e2, s);
+      val[1][0] = s.x;
+      val[1][1] = s.y;
+      bnd[1][0] = bnd[1][1] = bc.band3;
+    }
+    if (KT::k2) {
+      const float* b = rec + KT::off_bv;
+      float2 d = __fmul2_rn(ny0, make_float2(b[0], b[1]));
+      d = __ffma2_rn(ny1, make_float2(b[2], b[3]), d);
+      d = __ffma2_rn(ny2, make_float2(b[4], b[5]), d);
+      float2 n2 = __fmul2_rn(ny0, ny0);
+      n2 = __ffma2_rn(ny1, ny1, n2);
+      n2 = __ffma2_rn(ny2, ny2, n2);
+      const float2 band2 = __ffma2_rn(make_float2(bc.a1_2d, bc.a1_2d), n2, make_float2(bc.a0_2d, bc.a0_2d));
+      val[0][0] = fmaf(c2, n2.x, d.x * fabsf(d.x));
+      val[0][1] = fmaf(c2, n2.y, d.y * fabsf(d.y));
+      bnd[0][0] = band2.x;
+      bnd[0][1] = band2.y;
+    }
+    if (KT::kn) {
+      const float* w = rec + KT::off_nw;
+      const float* c = rec + KT::off_nc;
+      const float2 W0 = make_float2(w[0], w[1]), W1 = make_float2(w[2], w[3]), W2 = make_float2(w[4], w[5]);
+      float2 m0 = __fmul2_rn(make_float2(nR[k][0], nR[k][0]), W0);
+      float2 m1 = __fmul2_rn(make_float2(nR[k][3], nR[k][3]), W0);
+      float2 m2 = __fmul2_rn(make_float2(nR[k][6], nR[k][6]), W0);
+      m0 = __ffma2_rn(make_float2(nR[k][1], nR[k][1]), W1, m0);
+      m1 = __ffma2_rn(make_float2(nR[k][4], nR[k][4]), W1, m1);
+      m2 = __ffma2_rn(make_float2(nR[k][7], nR[k][7]), W1, m2);
+      m0 = __ffma2_rn(make_float2(nR[k][2], nR[k][2]), W2, m0);
+      m1 = __ffma2_rn(make_float2(nR[k][5], nR[k][5]), W2, m1);
+      m2 = __ffma2_rn(make_float2(nR[k][8], nR[k][8]), W2, m2);
+      float2 g = __ffma2_rn(make_float2(c[0], c[1]), m0, cnl2);
+      g = __ffma2_rn(make_float2(c[2], c[3]), m1, g);
+      g = __ffma2_rn(make_float2(c[4], c[5]), m2, g);
+      val[2][0] = g.x;
+      val[2][1] = g.y;
+      bnd[2][0] = bnd[2][1] = bc.band_n;
+    }
+#pragma unroll
+    for (int mod = 0; mod < 3; ++mod) {
+      if ((mod == 0 && !KT::k2) || (mod == 1 && !KT::k3) || (mod == 2 && !KT::kn)) continue;
+#pragma unroll
+      for (int uu = 0; uu < 2; ++uu) {
+        const float v = val[mod][uu];
+        if (!rescan) {
+          cnt[k] += (int)(__float_as_uint(v) >> 31);
+          flag = flag || (fabsf(v) <= bnd[mod][uu]);
+        } else if (fabsf(v) <= bnd[mod][uu]) {
+          cnt[k] -= (int)(__float_as_uint(v) >> 31);
+          const unsigned int idx = atomicAdd(&st->wl_count, 1u);
+          if (idx < wl.capacity)
+            wl.entries[idx] = make_uint2((unsigned int)slot[k], (unsigned int)(corr0 + uu) | ((unsigned int)mod << 30));
+          else
+            st->wl_overflow = 1u;
+        }
+      }
+    }
+  };
+
+  for (int t = 0; t < ntiles; ++t) {
+    const int buf = t & 1;
+    mbar_wait(&bars[buf], (uint32_t)((t >> 1) & 1));
+    const int tp = min(TILE, npairs - t * TILE);
+    const float* sp = reinterpret_cast<const float*>(&tile[buf][0]);
+    for (int sub = 0; sub < tp; sub += SUB) {
+      bool flag = false;
+#pragma unroll 2
+      for (int pp = 0; pp < SUB; ++pp) {
+        float rec[F4 * 4];
+#pragma unroll
+        for (int i = 0; i < F4; ++i) {
+          const float4 v = reinterpret_cast<const float4*>(sp)[(sub + pp) * F4 + i];
+          rec[4 * i] = v.x;
+          rec[4 * i + 1] = v.y;
+          rec[4 * i + 2] = v.z;
+          rec[4 * i + 3] = v.w;
+        }
+#pragma unroll
+        for (int k = 0; k < HPT; ++k) unit(rec, k, false, flag, 0);
+      }
+      if (flag) {
+        for (int pp = 0; pp < SUB; ++pp) {
+          float rec[F4 * 4];
+#pragma unroll
+          for (int i = 0; i < F4; ++i) {
+            const float4 v = reinterpret_cast<const float4*>(sp)[(sub + pp) * F4 + i];
+            rec[4 * i] = v.x;
+            rec[4 * i + 1] = v.y;
+            rec[4 * i + 2] = v.z;
+            rec[4 * i + 3] = v.w;
+          }
+          bool dummy = false;
+#pragma unroll
+          for (int k = 0; k < HPT; ++k) unit(rec, k, true, dummy, 2 * (p_begin + t * TILE + sub + pp));
+        }
+      }
+    }
+    __syncthreads();
+    if (tid == 0 && t + 2 < ntiles) {
+      const int tn = t + 2;
+      const int tpn = min(TILE, npairs - tn * TILE);
+      const uint32_t bytes = (uint32_t)tpn * F4 * 16u;
+      mbar_expect_tx(&bars[buf], bytes);
+      tma_load_1d(&tile[buf][0], pk + (size_t)(p_begin + tn * TILE) * F4, bytes, &bars[buf]);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < HPT; ++k)
+    if (slot[k] >= 0 && cnt[k] != 0) atomicAdd(&votes[slot[k]], cnt[k]);
+}
+
+template <int KIND>
+static void launch_multi(const FrameView& f, const HypGen* gen, const HypFast* fast, int slot_begin, int slot_end, Thresh th,
+                         int32_t* votes, FrameStats* st, Worklist wl, int num_sms, cudaStream_t s) {
+  constexpr int THREADS = 256, HPT = 2;
+  constexpr int F4 = KindTraits<KIND>::f4pp;
+  constexpr int TILE = F4 <= 3 ? 1024 : 512;
+  const int nslots = slot_end - slot_begin;
+  const int gy = (nslots + THREADS * HPT - 1) / (THREADS * HPT);
+  const int groups = f.npairs_pad / kSubPairs;
+  int gx = (2 * num_sms + gy - 1) / gy;
+  if (gx < 1) gx = 1;
+  if (gx > groups) gx = groups;
+  const int groups_per_cta = (groups + gx - 1) / gx;
+  const int pairs_per_cta = groups_per_cta * kSubPairs;
+  gx = (f.npairs_pad + pairs_per_cta - 1) / pairs_per_cta;
+  const size_t smem = 2 * (size_t)TILE * F4 * sizeof(float4) + 2 * sizeof(uint64_t);
+  auto kern = score_multi_fast_kernel<KIND, TILE, THREADS>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr_set = true;
+  }
+  kern<<<dim3(gx, gy), THREADS, smem, s>>>(f.pk, f.npairs_pad, pairs_per_cta, fast, gen, slot_begin, slot_end, th, votes, st, wl);
+}
+
 static bool g_use_packed = true;
 static int g_nosync = 0;
 void set_nosync(int v) { g_nosync = v; }
@@ -389,8 +672,18 @@ static void launch_variant(const FrameView& f, const HypGen* gen, const HypFast*
 void launch_score_fast(int method, const FrameView& f, const HypGen* gen, const HypFast* fast, int slot_begin,
                        int slot_end, Thresh th, int32_t* votes, FrameStats* st, Worklist wl, int num_sms,
                        cudaStream_t s) {
-  (void)method;
   if (slot_end - slot_begin <= 0 || f.n <= 0) return;
+  if (method != RPE_SHINJI) {
+    switch (f.pk_kind) {
+      case 1: launch_multi<1>(f, gen, fast, slot_begin, slot_end, th, votes, st, wl, num_sms, s); break;
+      case 3: launch_multi<3>(f, gen, fast, slot_begin, slot_end, th, votes, st, wl, num_sms, s); break;
+      case 5: launch_multi<5>(f, gen, fast, slot_begin, slot_end, th, votes, st, wl, num_sms, s); break;
+      case 6: launch_multi<6>(f, gen, fast, slot_begin, slot_end, th, votes, st, wl, num_sms, s); break;
+      case 7: launch_multi<7>(f, gen, fast, slot_begin, slot_end, th, votes, st, wl, num_sms, s); break;
+      default: break;
+    }
+    return;
+  }
 #define RPE_V(P, H, T, TH, MB, SB) launch_variant<P, H, T, TH, MB, SB>(f, gen, fast, slot_begin, slot_end, th, votes, st, wl, num_sms, s)
   if (!g_use_packed) {
     RPE_V(false, 2, 256, 256, 2, 8);

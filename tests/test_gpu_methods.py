@@ -153,3 +153,59 @@ def test_missing_modality_is_an_error(rpe, gpu_ctx):
         gpu_ctx.ransac("kneip", S, cos_thr2d=0.999)
     with pytest.raises(rpe.RpeError):
         gpu_ctx.ransac("nl_shinji", S, thr3d=0.1, cos_thrN=0.99)
+
+
+@pytest.mark.parametrize("method", [1, 2, 3, 4, 5, 6])
+def test_fast_tiled_scorer_equals_exact_kernel(rpe, orc, gpu_ctx, method):
+    """The FFMA2 tiled scorer (+ guard band + exact fix-up) and the exact-order kernel give the same vote table,
+    and the fast path really is the one that ran (borderline evaluations were queued)."""
+    n, H = 20000, 512
+    q, t, arrs, _ = _data(rpe, 400 + method, n, n2d=2.0, or2d=0.4, n3d=0.08, or3d=0.4, nnl=float(np.deg2rad(3.0)), ornl=0.4)
+    S = rpe.sample_table(3, n, 4, H)
+    th = _thr()
+    gpu_ctx.upload(**arrs)
+    rpe.lib.rpe_debug_force_exact_multi(1)
+    a = gpu_ctx.ransac(method, S, thr3d=th["thr3d"], cos_thr2d=th["cos_thr"], cos_thrN=th["cos_nl"], confidence=0.99)
+    va = gpu_ctx.get_votes(a["n_slots"])
+    rpe.lib.rpe_debug_force_exact_multi(0)
+    b = gpu_ctx.ransac(method, S, thr3d=th["thr3d"], cos_thr2d=th["cos_thr"], cos_thrN=th["cos_nl"], confidence=0.99)
+    vb = gpu_ctx.get_votes(b["n_slots"])
+    assert a["n_borderline"] == 0 and b["flags"] == 0
+    assert np.array_equal(va, vb)
+    assert np.array_equal(a["mask"], b["mask"]) and a["winner"] == b["winner"] and a["iter_final"] == b["iter_final"]
+
+
+def test_borderline_2d_and_normal_residuals_go_to_the_exact_path(rpe, orc, gpu_ctx):
+    """Adversarial data: bearing vectors at exactly the threshold angle and normals at exactly the threshold angle
+    (+- a few ulps) from the ground-truth pose, scored with hypotheses that reproduce that pose."""
+    orc.set_math_mode(orc.DET)
+    n = 4096
+    q, t = rpe.sim_pose(71)
+    d = rpe.sim_2d_3d_nl(72, q, t, n, n2d=0.0, or2d=0.0, n3d=0.0, or3d=0.0, nnl=0.0, ornl=0.0)
+    rng = np.random.default_rng(5)
+    th = _thr()
+    ang2 = np.arccos(np.float64(th["cos_thr"]))
+    angn = np.arccos(np.float64(th["cos_nl"]))
+
+    def tilt(v, ang):
+        v = v.astype(np.float64)
+        r = rng.normal(size=v.shape)
+        r -= np.sum(r * v, axis=1, keepdims=True) * v
+        r /= np.linalg.norm(r, axis=1, keepdims=True)
+        a = ang * (1.0 + rng.integers(-4, 5, size=(v.shape[0], 1)) * 2e-8)
+        return (np.cos(a) * v + np.sin(a) * r).astype(np.float32)
+
+    bv = tilt(d["bv"], ang2)
+    nc = tilt(d["nc"], angn)
+    bv[:16], nc[:16] = d["bv"][:16], d["nc"][:16]  # clean rows for the minimal samples
+    arrs = dict(bv=bv, xc=d["xc"], nc=nc, xw=d["xw"], nw=d["nw"])
+    S = np.tile(np.array([[0, 1, 2, 3], [4, 5, 6, 7], [8, 9, 10, 11], [12, 13, 14, 15]], np.int32), (8, 1))
+    for method in (5, 3, 1):
+        ref = orc.ransac(method, S, confidence=0.99, full=True, **th, **arrs)
+        gpu_ctx.upload(**arrs)
+        got = gpu_ctx.ransac(method, S, thr3d=th["thr3d"], cos_thr2d=th["cos_thr"], cos_thrN=th["cos_nl"], confidence=0.99)
+        votes = gpu_ctx.get_votes(ref["votes"].shape[0])
+        assert got["n_borderline"] > 1000, method
+        assert np.array_equal(votes, ref["votes"]), method
+        assert np.array_equal(got["mask"], ref["mask"]), method
+    orc.set_math_mode(orc.LIBM)
