@@ -924,6 +924,12 @@ int rpe_debug_set_packed(int packed) {
   rpe::set_use_packed(packed != 0);
   return RPE_OK;
 }
+// test hook: shrink the borderline worklist so that the overflow -> whole-frame exact rescoring path can be exercised
+int rpe_debug_set_worklist_capacity(rpe_ctx* ctx, unsigned int cap) {
+  if (!ctx) return RPE_ERR_ARG;
+  ctx->wl.capacity = cap < (1u << 21) ? cap : (1u << 21);
+  return RPE_OK;
+}
 int rpe_debug_force_exact_multi(int v) {
   g_force_exact_multi = v != 0;
   return RPE_OK;

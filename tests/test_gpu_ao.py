@@ -194,3 +194,28 @@ def test_config1_iter_100000_runs_in_passes(rpe, orc, gpu_ctx):
         assert got["n_slots"] >= min(H, ref["iter_final"])
     # with 90 % outliers the bound stays above one pass: several passes were needed
     assert got["n_slots"] > 8192
+
+
+def test_worklist_overflow_falls_back_to_exact_rescoring(rpe, orc):
+    """If more evaluations are borderline than the worklist holds, the frame is rescored in exact order on the device
+    (flags bit 0 is set) and the result is still identical to the CPU path."""
+    import ctypes
+    orc.set_math_mode(orc.DET)
+    n, H = 6000, 300
+    q, t, Q, P = _frame(rpe, 91, n)
+    S = rpe.sample_table(91, n, 3, H)
+    ref = orc.ransac(SHINJI, S, thr3d=0.25, confidence=0.9999, full=True, xc=P, xw=Q)
+    with rpe.Context(0) as ctx:
+        rpe.lib.rpe_debug_set_worklist_capacity.argtypes = [ctypes.c_void_p, ctypes.c_uint]
+        rpe.lib.rpe_debug_set_worklist_capacity(ctx.handle, 3)
+        ctx.upload(xc=P, xw=Q)
+        got = ctx.ransac(SHINJI, S, thr3d=0.25, confidence=0.9999)
+        votes = ctx.get_votes(H)
+        assert got["flags"] & 1
+        assert np.array_equal(votes, ref["votes"])
+        assert got["winner"] == ref["winner"] and got["iter_final"] == ref["iter_final"]
+        assert np.array_equal(got["mask"], ref["mask"])
+        # and the next frame on the same context is clean again
+        rpe.lib.rpe_debug_set_worklist_capacity(ctx.handle, 1 << 21)
+        got2 = ctx.ransac(SHINJI, S, thr3d=0.25, confidence=0.9999)
+        assert got2["flags"] == 0 and np.array_equal(ctx.get_votes(H), ref["votes"])
