@@ -192,6 +192,17 @@ int rpe_sim_2d_3d_nl(uint64_t seed, const float q_xyzw[4], const float t[3], int
                      float or3d, float nnl, float ornl, float min_depth, float max_depth, float f, int use_gaussian,
                      float* Q_xw, float* M_nw, float* P_xc, float* N_nc, float* U_bv, float* weights3);
 
+/* Device-side generators: the same distributions produced straight into the context's device arrays (no PCIe
+ * traffic; counter-based random stream, so the values differ from the host generators for the same seed).
+ * After the call the context holds n correspondences exactly as after rpe_upload. */
+int rpe_sim_3d_3d_device(rpe_ctx* ctx, uint64_t seed, const float q_xyzw[4], const float t[3], int n, float noise,
+                         float outlier_ratio, float min_depth, float max_depth, float f, int use_gaussian);
+int rpe_sim_2d_3d_nl_device(rpe_ctx* ctx, uint64_t seed, const float q_xyzw[4], const float t[3], int n, float n2d,
+                            float or2d, float n3d, float or3d, float nnl, float ornl, float min_depth, float max_depth,
+                            float f, int use_gaussian);
+/* Copy the context's current correspondence arrays back to host memory (NULL = skip). */
+int rpe_download(rpe_ctx* ctx, float* bv, float* xc, float* nc, float* xw, float* nw);
+
 /* ---- the reference's own C shim (Library.cpp:17-75), same argument meaning ------------------ */
 /* x_w, x_c: 3 x n column-major; R_cw out row-major 9; t out 3. ao = shinji_ls2; ao_ransac =
  * shinji_ransac2(thr 0.1, 1000 iterations, confidence 0.99999) + shinji_ls1. */

@@ -123,6 +123,9 @@ _sig("rpe_sim_3d_3d", C.c_int, [C.c_uint64, _vp, _vp, C.c_int, C.c_float, C.c_fl
 _sig("rpe_sim_2d_3d", C.c_int, [C.c_uint64, _vp, _vp, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
                                 C.c_int, _vp, _vp, _vp, _vp])
 _sig("rpe_sim_2d_3d_nl", C.c_int, [C.c_uint64, _vp, _vp, C.c_int] + [C.c_float] * 9 + [C.c_int] + [_vp] * 6)
+_sig("rpe_sim_3d_3d_device", C.c_int, [_vp, C.c_uint64, _vp, _vp, C.c_int] + [C.c_float] * 5 + [C.c_int])
+_sig("rpe_sim_2d_3d_nl_device", C.c_int, [_vp, C.c_uint64, _vp, _vp, C.c_int] + [C.c_float] * 9 + [C.c_int])
+_sig("rpe_download", C.c_int, [_vp] * 6)
 _sig("rpe_ao", C.c_int, [_vp, _vp, C.c_int, _vp, _vp])
 _sig("rpe_ao_ransac", C.c_int, [_vp, _vp, C.c_int, _vp, _vp])
 _sig("rpe_measure_ffma_tflops", C.c_int, [_vp, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)])
@@ -137,7 +140,8 @@ DECLARED_SYMBOLS = [
     "rpe_upload_device", "rpe_num_correspondences", "rpe_ransac", "rpe_ransac_async", "rpe_refit", "rpe_refit_async",
     "rpe_set_pose", "rpe_set_mask", "rpe_generate", "rpe_get_hypotheses", "rpe_set_hypotheses", "rpe_score",
     "rpe_get_votes", "rpe_set_votes", "rpe_votes_device_ptr", "rpe_finish", "rpe_update_num_iters", "rpe_sample_table",
-    "rpe_prosac_table", "rpe_sim_pose", "rpe_sim_3d_3d", "rpe_sim_2d_3d", "rpe_sim_2d_3d_nl", "rpe_ao", "rpe_ao_ransac",
+    "rpe_prosac_table", "rpe_sim_pose", "rpe_sim_3d_3d", "rpe_sim_2d_3d", "rpe_sim_2d_3d_nl", "rpe_sim_3d_3d_device",
+    "rpe_sim_2d_3d_nl_device", "rpe_download", "rpe_ao", "rpe_ao_ransac",
     "rpe_measure_ffma_tflops", "rpe_last_stage_ms", "rpe_enable_stage_timing",
 ]
 
@@ -301,6 +305,24 @@ class Context:
         d = res.to_dict()
         d["mask"] = mask  # (cols, n): row k == column k of the reference's n x cols matrix
         return d
+
+    def sim_3d_3d_device(self, seed, q, t, n, noise=0.1, outlier_ratio=0.5, min_depth=0.4, max_depth=8.0, f=585.0,
+                         gaussian=True):
+        self.n = n
+        _check(lib.rpe_sim_3d_3d_device(self._h, seed, _ptr(_f32(q)), _ptr(_f32(t)), n, noise, outlier_ratio, min_depth,
+                                        max_depth, f, 1 if gaussian else 0), self._h)
+
+    def sim_2d_3d_nl_device(self, seed, q, t, n, n2d=1.0, or2d=0.3, n3d=0.05, or3d=0.3, nnl=np.deg2rad(2.0), ornl=0.3,
+                            min_depth=0.4, max_depth=8.0, f=585.0, gaussian=True):
+        self.n = n
+        _check(lib.rpe_sim_2d_3d_nl_device(self._h, seed, _ptr(_f32(q)), _ptr(_f32(t)), n, n2d, or2d, n3d, or3d, nnl, ornl,
+                                           min_depth, max_depth, f, 1 if gaussian else 0), self._h)
+
+    def download(self, names=("xc", "xw")):
+        order = ("bv", "xc", "nc", "xw", "nw")
+        out = {k: (np.empty((self.n, 3), np.float32) if k in names else None) for k in order}
+        _check(lib.rpe_download(self._h, *[_ptr(out[k]) for k in order]), self._h)
+        return {k: v for k, v in out.items() if v is not None}
 
     def ransac_async(self, method, samples, H=None, thr3d=0.0, cos_thr2d=0.0, cos_thrN=0.0, confidence=0.99, mask=None):
         """Enqueue only. `samples` may be a numpy int32 array (kept alive until sync) or a device pointer (int)

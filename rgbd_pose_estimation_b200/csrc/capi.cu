@@ -14,6 +14,18 @@
 #include "kernels.cuh"
 
 namespace rpe {
+struct SimParams {
+  float R[9];
+  float t[3];
+  int n;
+  float noise2d, noise3d, noise_nl;
+  int out2d, out3d, outnl;
+  unsigned int ainv[3], b[3];
+  float min_depth, max_depth, f;
+  int gaussian;
+  unsigned long long seed;
+};
+void launch_simulate(const SimParams& p, float* xw, float* xc, float* bv, float* nw, float* nc, int mode_3d3d, cudaStream_t s);
 void set_use_packed(bool v);
 void set_score_variant(int v);
 void set_nosync(int v);
@@ -840,6 +852,109 @@ int rpe_finish(rpe_ctx* ctx, int method, int H, float thr3d, float cos_thr2d, fl
   ctx->launches += 2;
   ctx->stats_clean = true;
   return do_finish(ctx, method, th, out, mask, true);
+}
+
+// ---- device-side Simulator (frames are generated straight into the context's own device arrays) ------------
+static unsigned long long host_mix64(unsigned long long x) {
+  x += 0x9e3779b97f4a7c15ULL;
+  x = (x ^ (x >> 30)) * 0xbf58476d1ce4e5b9ULL;
+  x = (x ^ (x >> 27)) * 0x94d049bb133111ebULL;
+  return x ^ (x >> 31);
+}
+static unsigned int gcd_u(unsigned int a, unsigned int b) {
+  while (b) {
+    const unsigned int t = a % b;
+    a = b;
+    b = t;
+  }
+  return a;
+}
+static unsigned int modinv_u(unsigned int a, unsigned int n) {  // a^-1 mod n, gcd(a,n) = 1
+  long long t = 0, nt = 1, r = n, nr = a % n;
+  while (nr != 0) {
+    const long long q = r / nr;
+    long long tmp = t - q * nt;
+    t = nt;
+    nt = tmp;
+    tmp = r - q * nr;
+    r = nr;
+    nr = tmp;
+  }
+  if (t < 0) t += n;
+  return (unsigned int)t;
+}
+
+static int sim_device_common(rpe_ctx* ctx, uint64_t seed, const float q[4], const float t[3], int n, float n2d, float or2d,
+                             float n3d, float or3d, float nnl, float ornl, float min_depth, float max_depth, float f,
+                             int use_gaussian, int mode_3d3d) {
+  if (!ctx || !q || !t || n <= 0) return RPE_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  int rc = ensure_corr_capacity(ctx, n, true);
+  if (rc) return rc;
+  SimParams p;
+  quat_to_R_rowmajor(q, p.R);
+  for (int k = 0; k < 3; ++k) p.t[k] = t[k];
+  p.n = n;
+  p.noise2d = n2d;
+  p.noise3d = n3d;
+  p.noise_nl = nnl;
+  p.out2d = (int)(or2d * n + .5);
+  p.out3d = (int)(or3d * n + .5);
+  p.outnl = (int)(ornl * n + .5f);
+  for (int k = 0; k < 3; ++k) {
+    unsigned int a = (unsigned int)(host_mix64(seed * 3 + k) % (unsigned long long)n);
+    if (a < 2) a = 2;
+    while (gcd_u(a, (unsigned int)n) != 1) ++a;
+    a %= (unsigned int)n;
+    if (a == 0) a = 1;
+    p.ainv[k] = n > 1 ? modinv_u(a, (unsigned int)n) : 0;
+    p.b[k] = (unsigned int)(host_mix64(seed * 7 + k + 11) % (unsigned long long)n);
+  }
+  p.min_depth = min_depth;
+  p.max_depth = max_depth;
+  p.f = f;
+  p.gaussian = use_gaussian;
+  p.seed = seed;
+  ctx->n = n;
+  for (int k = 0; k < 5; ++k) ctx->view[k] = nullptr;
+  ctx->view[A_XW] = ctx->d_raw[A_XW];
+  ctx->view[A_XC] = ctx->d_raw[A_XC];
+  if (!mode_3d3d) {
+    ctx->view[A_BV] = ctx->d_raw[A_BV];
+    ctx->view[A_NW] = ctx->d_raw[A_NW];
+    ctx->view[A_NC] = ctx->d_raw[A_NC];
+  }
+  launch_simulate(p, ctx->d_raw[A_XW], ctx->d_raw[A_XC], mode_3d3d ? nullptr : ctx->d_raw[A_BV],
+                  mode_3d3d ? nullptr : ctx->d_raw[A_NW], mode_3d3d ? nullptr : ctx->d_raw[A_NC], mode_3d3d, ctx->stream);
+  ctx->launches++;
+  ctx->pk_kind = -1;
+  ctx->kabsch_valid = false;
+  ctx->n_slots = 0;
+  return RPE_OK;
+}
+
+int rpe_sim_3d_3d_device(rpe_ctx* ctx, uint64_t seed, const float q_xyzw[4], const float t[3], int n, float noise,
+                         float outlier_ratio, float min_depth, float max_depth, float f, int use_gaussian) {
+  return sim_device_common(ctx, seed, q_xyzw, t, n, 0.f, 0.f, noise, outlier_ratio, 0.f, 0.f, min_depth, max_depth, f,
+                           use_gaussian, 1);
+}
+int rpe_sim_2d_3d_nl_device(rpe_ctx* ctx, uint64_t seed, const float q_xyzw[4], const float t[3], int n, float n2d,
+                            float or2d, float n3d, float or3d, float nnl, float ornl, float min_depth, float max_depth,
+                            float f, int use_gaussian) {
+  return sim_device_common(ctx, seed, q_xyzw, t, n, n2d, or2d, n3d, or3d, nnl, ornl, min_depth, max_depth, f, use_gaussian, 0);
+}
+// Copy the context's current correspondence arrays back to the host (NULL = skip). For tests / inspection.
+int rpe_download(rpe_ctx* ctx, float* bv, float* xc, float* nc, float* xw, float* nw) {
+  if (!ctx || ctx->n <= 0) return RPE_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  float* dst[5] = {bv, xc, nc, xw, nw};
+  for (int k = 0; k < 5; ++k)
+    if (dst[k]) {
+      if (!ctx->view[k]) return fail(ctx, RPE_ERR_STATE, "array not present on the device");
+      CK(cudaMemcpyAsync(dst[k], ctx->view[k], (size_t)ctx->n * 3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+  CK(cudaStreamSynchronize(ctx->stream));
+  return RPE_OK;
 }
 
 // ---- Library.cpp shim -----------------------------------------------------------------------------

@@ -116,3 +116,26 @@ def test_nl_shinji_kneip_ls_through_c_abi(rpe, orc, gpu_ctx):
     assert _angle(fit["q"], ref_q) < 1e-6 and np.abs(fit["t"].astype(np.float64) - ref_t).max() < 1e-5
     assert _angle(fit["q"], q) <= _angle(r["q"], q) + 1e-4
     orc.set_math_mode(orc.LIBM)
+
+
+def test_library_cpp_shim_ao_and_ao_ransac(rpe, orc):
+    """rpe_ao / rpe_ao_ransac: same arguments and conventions as the reference's extern "C" ao() / ao_ransac()
+    (Library.cpp:17-75): x_w, x_c 3 x n column-major in, R_cw row-major 9 floats + t out; ao = shinji_ls2,
+    ao_ransac = shinji_ransac2(thr 0.1, 1000 iterations, confidence 0.99999, unseeded rand()) + shinji_ls1."""
+    orc.set_math_mode(orc.DET)
+    n = 3000
+    q, t = rpe.sim_pose(21)
+    Q, P, _ = rpe.sim_3d_3d(22, q, t, n, noise=0.02, outlier_ratio=0.3)
+    R = np.empty(9, np.float32)
+    tt = np.empty(3, np.float32)
+    assert rpe.lib.rpe_ao_ransac(Q.ctypes.data, P.ctypes.data, n, R.ctypes.data, tt.ctypes.data) == 0
+    S = orc.sample_table(1, n, 3, 1000)
+    ref = orc.ransac(0, S, thr3d=np.float32(0.1), confidence=np.float32(0.99999), full=False, xc=P, xw=Q, want_arrays=False)
+    ls_q, ls_t, _ = orc.shinji_ls(P, Q, ref["mask"][1], dt=np.float64)
+    Rref = orc.quat_to_matrix(ls_q, np.float64)
+    assert np.abs(R.reshape(3, 3) - Rref).max() < 2e-6 and np.abs(tt - ls_t).max() < 2e-5
+    # ao(): least squares over all points, so the 30 % outliers bias it — compare with the oracle's shinji_ls2
+    assert rpe.lib.rpe_ao(Q.ctypes.data, P.ctypes.data, n, R.ctypes.data, tt.ctypes.data) == 0
+    ls_q, ls_t, _ = orc.shinji_ls(P, Q, None, dt=np.float64)
+    assert np.abs(R.reshape(3, 3) - orc.quat_to_matrix(ls_q, np.float64)).max() < 2e-6 and np.abs(tt - ls_t).max() < 2e-5
+    orc.set_math_mode(orc.LIBM)
