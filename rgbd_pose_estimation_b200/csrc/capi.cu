@@ -818,6 +818,8 @@ int rpe_score(rpe_ctx* ctx, int method, int slot_begin, int slot_end, float thr3
   const Thresh th = {thr3d, cos_thr2d, cos_thrN};
   stamp(ctx, ST_SCORE);
   rc = score_range(ctx, method, slot_begin, slot_end, th);
+  launch_consume_worklist(ctx->d_stats, ctx->stream);
+  ctx->launches++;
   stamp(ctx, ST_REPLAY);
   ctx->stats_clean = false;
   return rc;

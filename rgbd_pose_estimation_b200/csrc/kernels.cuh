@@ -50,6 +50,7 @@ void launch_score_fast(int method, const FrameView& f, const HypGen* gen, const 
                        int slot_end, Thresh th, int32_t* votes, FrameStats* st, Worklist wl, int num_sms, cudaStream_t s);
 void launch_fixup(int method, const FrameView& f, const HypGen* gen, Thresh th, int32_t* votes, FrameStats* st,
                   Worklist wl, int num_sms, cudaStream_t s);
+void launch_consume_worklist(FrameStats* st, cudaStream_t s);
 // exact-order scoring of every (slot, correspondence); `only_if_overflow` makes it a no-op unless
 // the fast pass overflowed its worklist.
 void launch_score_exact(int method, const FrameView& f, const HypGen* gen, int slot_begin, int slot_end, Thresh th,

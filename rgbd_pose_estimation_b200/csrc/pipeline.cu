@@ -251,11 +251,12 @@ replay_kernel(int method, const HypGen* __restrict__ gen, const int32_t* __restr
     rs->cur_iter = s_state[3];
     rs->stop = s_state[4] || ((long long)(slot_base + E) >= (long long)s_state[1] * S) ? 1 : 0;
     rs->slots_done += E;
-    rs->borderline += (int)st->wl_count;
+    rs->borderline += (int)(st->wl_count + st->wl_consumed);
     rs->overflow |= st->wl_overflow ? 1 : 0;
     // per-pass counters are consumed: leave them clean for the next pass / frame
     st->t_max_bits = 0;
     st->wl_count = 0;
+    st->wl_consumed = 0;
     st->wl_overflow = 0;
     st->ticket = 0;
     st->ticket2 = 0;

@@ -85,7 +85,7 @@ struct FrameStats {
   unsigned int wl_overflow;  // 1 if the worklist overflowed -> exact rescoring of the frame
   unsigned int ticket;       // last-block-done counter (refit kernels)
   unsigned int ticket2;
-  unsigned int pad;
+  unsigned int wl_consumed;  // borderline evaluations already resolved by earlier rpe_score calls of this frame
 };
 
 struct ReplayOut {  // written by the replay kernel, read by mask/refit kernels and copied to rpe_result

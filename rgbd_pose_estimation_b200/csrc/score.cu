@@ -66,6 +66,7 @@ __global__ void reset_stats_kernel(FrameStats* st) {
     st->wl_overflow = 0;
     st->ticket = 0;
     st->ticket2 = 0;
+    st->wl_consumed = 0;
   }
 }
 void launch_reset_stats(FrameStats* st, cudaStream_t s) { reset_stats_kernel<<<1, 32, 0, s>>>(st); }
@@ -744,6 +745,16 @@ __global__ void fixup_kernel(int method, FrameView f, const HypGen* __restrict__
     if (exact_eval(method, modality, f, h, Rm, c, th)) atomicAdd(&votes[slot], 1);
   }
 }
+
+// Stage API (rpe_score called several times per frame): mark the queued evaluations as resolved so that the next
+// call's fix-up does not add them again.
+__global__ void consume_worklist_kernel(FrameStats* st) {
+  if (threadIdx.x == 0) {
+    st->wl_consumed += st->wl_count < 0xffffffffu ? st->wl_count : 0u;
+    st->wl_count = 0;
+  }
+}
+void launch_consume_worklist(FrameStats* st, cudaStream_t s) { consume_worklist_kernel<<<1, 32, 0, s>>>(st); }
 
 void launch_fixup(int method, const FrameView& f, const HypGen* gen, Thresh th, int32_t* votes, FrameStats* st,
                   Worklist wl, int num_sms, cudaStream_t s) {
