@@ -77,11 +77,12 @@ struct rpe_ctx {
   ReplayOut* d_kabsch = nullptr;  // Kabsch refit computed by the mask kernel's last CTA
   ReplayOut* h_pose = nullptr;    // pinned, kNumStaging slots; [0] doubles as scratch for set_pose
   bool kabsch_valid = false;
+  bool suff_valid = false;  // rb.suff matches the inlier columns in d_mask
   Worklist wl = {nullptr, 0};
   int16_t* d_mask = nullptr;
   size_t mask_cap = 0;
   int mask_cols = 0;
-  RefitBuffers rb = {nullptr, nullptr, 0, 148};
+  RefitBuffers rb;
   GnState* d_gn = nullptr;
   NlskState* d_nlsk = nullptr;
   float* d_weights3 = nullptr;
@@ -336,6 +337,7 @@ int do_finish(rpe_ctx* ctx, int method, Thresh th, rpe_result* out, int16_t* mas
   launch_mask(method, f, ctx->d_pose, th, ctx->d_mask, ctx->d_kabsch, ctx->rb, ctx->d_stats, ctx->stream);
   ctx->launches += 1;
   ctx->kabsch_valid = method_uses_3d(method);
+  ctx->suff_valid = true;
   ctx->last_th = th;
   stamp(ctx, ST_GN);
   int slot = 0;
@@ -495,6 +497,7 @@ static int create_common(int device, void* stream, bool own, rpe_ctx** out) {
   ok = ok && cudaMalloc(&ctx->d_kabsch, sizeof(ReplayOut)) == cudaSuccess;
   ok = ok && cudaMallocHost(&ctx->h_pose, kNumStaging * sizeof(ReplayOut)) == cudaSuccess;
   ok = ok && cudaMalloc(&ctx->rb.moments, kMomentCount * sizeof(double)) == cudaSuccess;
+  ok = ok && cudaMalloc(&ctx->rb.suff, kMomentCount * sizeof(double)) == cudaSuccess;
   ok = ok && cudaMalloc(&ctx->d_gn, sizeof(GnState)) == cudaSuccess;
   ok = ok && cudaMalloc(&ctx->d_nlsk, sizeof(NlskState)) == cudaSuccess;
   ok = ok && cudaMalloc(&ctx->d_gn_cost, sizeof(double)) == cudaSuccess;
@@ -551,6 +554,7 @@ int rpe_destroy(rpe_ctx* ctx) {
   cudaFree(ctx->d_mask);
   cudaFree(ctx->rb.partials);
   cudaFree(ctx->rb.moments);
+  cudaFree(ctx->rb.suff);
   cudaFree(ctx->d_gn);
   cudaFree(ctx->d_nlsk);
   cudaFree(ctx->d_weights3);
@@ -613,6 +617,7 @@ static int upload_common(rpe_ctx* ctx, const float* const src[5], int n, bool fr
   }
   ctx->pk_kind = -1;
   ctx->kabsch_valid = false;
+  ctx->suff_valid = false;
   ctx->n_slots = 0;
   return RPE_OK;
 }
@@ -668,11 +673,27 @@ static int do_refit(rpe_ctx* ctx, int kind, const float* weights, int max_iters,
     const float w2 = weights ? weights[0] : 1.f, w3 = weights ? weights[1] : 1.f, wn = weights ? weights[2] : 1.f;
     const int iters = max_iters > 0 ? max_iters : 6;
     stamp(ctx, ST_GN);
-    launch_gn_init(ctx->d_pose, ctx->d_gn, ctx->stream);
-    for (int it = 0; it < iters; ++it)
-      launch_gn_iteration(f, ctx->d_mask, ctx->mask_cols, w2, w3, wn, ctx->rb, ctx->d_gn, ctx->d_stats, ctx->d_pose,
-                          ctx->d_gn_cost, ctx->d_gn_evals, ctx->stream);
-    ctx->launches += iters + 1;
+    const bool generic = ctx->mask_cols >= 1 && f.bv != nullptr && w2 > 0.f;
+    if (generic) {  // 2-D rows are not polynomial in the pose: one pass over the correspondences per evaluation
+      launch_gn_init(ctx->d_pose, ctx->d_gn, ctx->stream);
+      for (int it = 0; it < iters; ++it)
+        launch_gn_iteration(f, ctx->d_mask, ctx->mask_cols, w2, w3, wn, ctx->rb, ctx->d_gn, ctx->d_stats, ctx->d_pose,
+                            ctx->d_gn_cost, ctx->d_gn_evals, ctx->stream);
+      ctx->launches += iters + 1;
+    } else {
+      const bool m3 = ctx->mask_cols >= 2 && f.xc && w3 > 0.f;
+      const bool mn = ctx->mask_cols >= 3 && f.nc && f.nw && wn > 0.f;
+      int used = 0;
+      if (!ctx->suff_valid) {
+        used = launch_suffstats(f, m3 ? ctx->d_mask + ctx->n : nullptr, false, mn ? ctx->d_mask + 2 * (size_t)ctx->n : nullptr,
+                                ctx->rb, ctx->stream);
+        ctx->launches += 1;
+        ctx->suff_valid = m3 == (ctx->mask_cols >= 2 && f.xc != nullptr) && mn == (ctx->mask_cols >= 3 && f.nc && f.nw);
+      }
+      launch_gn_from_stats(ctx->rb, used, m3 ? w3 : 0.f, mn ? wn : 0.f, iters, ctx->d_pose, ctx->d_gn, ctx->d_gn_cost,
+                           ctx->d_gn_evals, ctx->stream);
+      ctx->launches += 1;
+    }
     CK(cudaMemcpyAsync(&ctx->h_gn_cost[slot], ctx->d_gn_cost, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemcpyAsync(&ctx->h_gn_evals[slot], ctx->d_gn_evals, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
     stamp(ctx, ST_TOTAL);
@@ -741,6 +762,7 @@ int rpe_set_mask(rpe_ctx* ctx, const int16_t* mask, int cols) {
   CK(cudaStreamSynchronize(ctx->stream));
   ctx->mask_cols = cols;
   ctx->kabsch_valid = false;
+  ctx->suff_valid = false;
   return RPE_OK;
 }
 
@@ -931,6 +953,7 @@ static int sim_device_common(rpe_ctx* ctx, uint64_t seed, const float q[4], cons
   ctx->launches++;
   ctx->pk_kind = -1;
   ctx->kabsch_valid = false;
+  ctx->suff_valid = false;
   ctx->n_slots = 0;
   return RPE_OK;
 }

@@ -64,10 +64,11 @@ void launch_replay(int method, const HypGen* gen, const int32_t* votes, int H, i
                    FrameStats* st, ReplayState* rs, ReplayOut* out, bool finalize, cudaStream_t s);
 
 struct RefitBuffers {
-  double* partials;   // [blocks x kMomentCount]
-  double* moments;    // [kMomentCount] reduced
-  int max_blocks;
-  int num_sms;        // refit kernels use at most 2 CTAs per SM and stride over the correspondences
+  double* partials = nullptr;   // [blocks x kMomentCount]
+  double* moments = nullptr;    // [kMomentCount] reduced
+  double* suff = nullptr;       // [kMomentCount] sufficient statistics of the current inlier columns (suff_add_3d / suff_add_nl)
+  int max_blocks = 0;
+  int num_sms = 148;        // refit kernels use at most 2 CTAs per SM and stride over the correspondences
 };
 constexpr int kMomentCount = 48;  // 16 Kabsch moments / 29 LM entries / 40 nl_shinji_kneip_ls sums, padded
 
@@ -80,6 +81,9 @@ void launch_reset_corr_bound(FrameStats* st, cudaStream_t s);
 // returns the number of CTAs launched (= rows of rb.partials to reduce)
 int launch_kabsch_moments(const FrameView& f, const int16_t* flags3d /*null: all points*/, RefitBuffers rb,
                           FrameStats* st, cudaStream_t s);
+// statistics of explicit flag columns -> rb.partials; returns the CTAs launched
+int launch_suffstats(const FrameView& f, const int16_t* flags3d, bool all3d, const int16_t* flagsN, RefitBuffers rb,
+                     cudaStream_t s);
 void launch_kabsch_solve(RefitBuffers rb, int blocks_used, ReplayOut* pose_inout, int32_t* refit_ok, cudaStream_t s);
 
 struct GnState {  // device-resident LM state (mirrors oracle/refine.hpp refine_gn)
@@ -97,6 +101,11 @@ void launch_gn_init(const ReplayOut* pose, GnState* st, cudaStream_t s);
 void launch_gn_iteration(const FrameView& f, const int16_t* mask, int mask_cols, float w2d, float w3d, float wnl,
                          RefitBuffers rb, GnState* gs, FrameStats* st, ReplayOut* pose_out, double* cost_out,
                          int32_t* evals_out, cudaStream_t s);
+
+// The complete LM loop for 3-D / normal rows from the sufficient statistics (blocks_used > 0: reduce rb.partials
+// first; 0: use rb.suff as left by the mask kernel). One launch, no pass over the correspondences.
+void launch_gn_from_stats(RefitBuffers rb, int blocks_used, float w3d, float wnl, int max_iters, ReplayOut* pose_io,
+                          GnState* gs, double* cost_out, int32_t* evals_out, cudaStream_t s);
 
 // nl_shinji_kneip_ls (AbsoluteOrientationNormal.hpp:447-552) as one pose-independent reduction pass plus three
 // passes for the only sum that depends on the running camera centre (M23); the 3x3 SVDs, find_opt_cc's

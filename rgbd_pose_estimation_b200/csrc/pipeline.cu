@@ -369,14 +369,55 @@ __device__ bool kabsch_from_moments(const double* m, float* q_out, float* t_out)
   return ok;
 }
 
+// Sufficient statistics of the 3-D and normal rows (binary64 sums of binary32 inputs). Every quantity the Kabsch refit
+// and the LM normal equations of those rows need is a polynomial in (R, t) with these coefficients:
+//   [0] n3  [1..3] sum x_w  [4..6] sum x_c  [7..15] sum x_c x_w^T (row-major)  [16..21] sum x_w x_w^T (xx,xy,xz,yy,yz,zz)
+//   [22] sum |x_c|^2        [23] nn  [24..29] sum n_w n_w^T  [30..38] sum n_c n_w^T (row-major)  [39] sum |n_c|^2
+constexpr int kSuff3 = 23, kSuffAll = 40;
+__device__ __forceinline__ void suff_add_3d(double* m, const F3& xw, const F3& xc) {
+  const double w[3] = {xw.x, xw.y, xw.z}, c[3] = {xc.x, xc.y, xc.z};
+  m[0] += 1.0;
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    m[1 + r] += w[r];
+    m[4 + r] += c[r];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) m[7 + 3 * r + q] += c[r] * w[q];
+  }
+  m[16] += w[0] * w[0];
+  m[17] += w[0] * w[1];
+  m[18] += w[0] * w[2];
+  m[19] += w[1] * w[1];
+  m[20] += w[1] * w[2];
+  m[21] += w[2] * w[2];
+  m[22] += c[0] * c[0] + c[1] * c[1] + c[2] * c[2];
+}
+__device__ __forceinline__ void suff_add_nl(double* m, const F3& nw, const F3& nc) {
+  const double w[3] = {nw.x, nw.y, nw.z}, c[3] = {nc.x, nc.y, nc.z};
+  m[23] += 1.0;
+  m[24] += w[0] * w[0];
+  m[25] += w[0] * w[1];
+  m[26] += w[0] * w[2];
+  m[27] += w[1] * w[1];
+  m[28] += w[1] * w[2];
+  m[29] += w[2] * w[2];
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int q = 0; q < 3; ++q) m[30 + 3 * r + q] += c[r] * w[q];
+  m[39] += c[0] * c[0] + c[1] * c[1] + c[2] * c[2];
+}
+
 // ================================================================================================
 // winner's mask (+ Kabsch moments of the 3-D inliers, + the Kabsch solve in the last CTA)
 // ================================================================================================
+template <bool UN>
 __global__ void __launch_bounds__(256, 2)
 mask_kernel(int method, FrameView f, ReplayOut* pose_rw, Thresh th, int16_t* __restrict__ mask, RefitBuffers rb,
             ReplayOut* kabsch_out, FrameStats* st) {
   const ReplayOut* pose = pose_rw;
-  __shared__ double red[8 * 16];
+  constexpr int NV = UN ? kSuffAll : kSuff3;
+  __shared__ double red[8 * NV];
   __shared__ int cnts[3];
   __shared__ bool is_last;
   const int n = f.n;
@@ -389,10 +430,10 @@ mask_kernel(int method, FrameView f, ReplayOut* pose_rw, Thresh th, int16_t* __r
   const bool have = pose->winner >= 0;
   float Rm[9];
   ex_quat_to_matrix(h.q, Rm);
-  const bool u2 = method_uses_2d(method), u3 = method_uses_3d(method), un = method_uses_nl(method);
-  double mom[16];
+  const bool u2 = method_uses_2d(method), u3 = method_uses_3d(method), un = UN;
+  double mom[NV];
 #pragma unroll
-  for (int k = 0; k < 16; ++k) mom[k] = 0.0;
+  for (int k = 0; k < NV; ++k) mom[k] = 0.0;
   int c2 = 0, c3 = 0, cn = 0;
   for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < n; c += gridDim.x * blockDim.x) {
     bool f2 = false, f3d = false, fn = false;
@@ -404,25 +445,22 @@ mask_kernel(int method, FrameView f, ReplayOut* pose_rw, Thresh th, int16_t* __r
         xc = load_col(f.xc, c);
         valid = ex_is_valid(xc);
       }
-      if (un && valid) fn = ex_test_nl(h.q, load_col(f.nw, c), load_col(f.nc, c), th.cos_nl);
+      if (UN && valid) {
+        const F3 nw = load_col(f.nw, c), nc = load_col(f.nc, c);
+        fn = ex_test_nl(h.q, nw, nc, th.cos_nl);
+        if (fn) suff_add_nl(mom, nw, nc);
+      }
       if (u3 && valid) f3d = ex_test_3d(h.q, h.t, xw, xc, th.thr3d);
       if (u2) f2 = ex_test_2d(h.q, h.t, method == RPE_KNEIP ? Rm : nullptr, xw, load_col(f.bv, c), th.cos_thr);
-      if (f3d) {
-        mom[0] += 1.0;
-        const double w3[3] = {xw.x, xw.y, xw.z}, c3v[3] = {xc.x, xc.y, xc.z};
-#pragma unroll
-        for (int r = 0; r < 3; ++r) {
-          mom[1 + r] += w3[r];
-          mom[4 + r] += c3v[r];
-#pragma unroll
-          for (int q = 0; q < 3; ++q) mom[7 + 3 * r + q] += c3v[r] * w3[q];
-        }
-      }
+      if (f3d) suff_add_3d(mom, xw, xc);
       c2 += f2 ? 1 : 0;
       c3 += f3d ? 1 : 0;
       cn += fn ? 1 : 0;
     } else {
       f2 = f3d = fn = true;  // adapters start with setOnes() and setInlier is never called
+      // keep the statistics consistent with the all-ones columns a later refinement would read
+      if (cols >= 2 && f.xc) suff_add_3d(mom, load_col(f.xw, c), load_col(f.xc, c));
+      if (UN && f.nw && f.nc) suff_add_nl(mom, load_col(f.nw, c), load_col(f.nc, c));
     }
     mask[c] = (int16_t)((cols == 1 || u2) ? (f2 ? 1 : 0) : 0);
     if (cols >= 2) mask[n + c] = (int16_t)(u3 ? (f3d ? 1 : 0) : (have ? 0 : 1));
@@ -440,7 +478,7 @@ mask_kernel(int method, FrameView f, ReplayOut* pose_rw, Thresh th, int16_t* __r
     if (c3) atomicAdd(&cnts[1], c3);
     if (cn) atomicAdd(&cnts[2], cn);
   }
-  block_reduce_store<16>(mom, rb.partials, red);
+  block_reduce_store<NV>(mom, rb.partials, red);
   __syncthreads();
   if (threadIdx.x == 0) {
     for (int k = 0; k < 3; ++k)
@@ -455,6 +493,7 @@ mask_kernel(int method, FrameView f, ReplayOut* pose_rw, Thresh th, int16_t* __r
     __shared__ double fin_scratch[8 * 32];
     __shared__ double fin[kMomentCount];
     final_reduce_partials(rb.partials, gridDim.x, fin_scratch, fin);
+    if (threadIdx.x < kSuffAll) rb.suff[threadIdx.x] = fin[threadIdx.x];
     if (threadIdx.x == 0) {
       double m[16];
       for (int k = 0; k < 16; ++k) m[k] = fin[k];
@@ -481,36 +520,35 @@ static int refit_grid(int n, int num_sms_hint) {
 }
 void launch_mask(int method, const FrameView& f, ReplayOut* pose_rw, Thresh th, int16_t* mask, ReplayOut* kabsch_out,
                  RefitBuffers rb, FrameStats* st, cudaStream_t s) {
-  mask_kernel<<<refit_grid(f.n, rb.num_sms), 256, 0, s>>>(method, f, pose_rw, th, mask, rb, kabsch_out, st);
+  if (method_uses_nl(method))
+    mask_kernel<true><<<refit_grid(f.n, rb.num_sms), 256, 0, s>>>(method, f, pose_rw, th, mask, rb, kabsch_out, st);
+  else
+    mask_kernel<false><<<refit_grid(f.n, rb.num_sms), 256, 0, s>>>(method, f, pose_rw, th, mask, rb, kabsch_out, st);
 }
 
-// Stand-alone moments over an explicit flag column (after rpe_set_mask) or over all points (shinji_ls2).
+// Stand-alone statistics over explicit flag columns (after rpe_set_mask) or over all points (shinji_ls2).
 __global__ void __launch_bounds__(256)
-kabsch_moments_kernel(FrameView f, const int16_t* __restrict__ flags3d, RefitBuffers rb) {
-  __shared__ double red[8 * 16];
-  double mom[16];
+suffstat_kernel(FrameView f, const int16_t* __restrict__ flags3d, int all3d, const int16_t* __restrict__ flagsN,
+                RefitBuffers rb) {
+  __shared__ double red[8 * kSuffAll];
+  double mom[kSuffAll];
 #pragma unroll
-  for (int k = 0; k < 16; ++k) mom[k] = 0.0;
+  for (int k = 0; k < kSuffAll; ++k) mom[k] = 0.0;
   for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < f.n; c += gridDim.x * blockDim.x) {
-    if (flags3d && flags3d[c] != 1) continue;
-    const F3 xw = load_col(f.xw, c), xc = load_col(f.xc, c);
-    mom[0] += 1.0;
-    const double w3[3] = {xw.x, xw.y, xw.z}, c3[3] = {xc.x, xc.y, xc.z};
-#pragma unroll
-    for (int r = 0; r < 3; ++r) {
-      mom[1 + r] += w3[r];
-      mom[4 + r] += c3[r];
-#pragma unroll
-      for (int q = 0; q < 3; ++q) mom[7 + 3 * r + q] += c3[r] * w3[q];
-    }
+    if (all3d || (flags3d && flags3d[c] == 1)) suff_add_3d(mom, load_col(f.xw, c), load_col(f.xc, c));
+    if (flagsN && flagsN[c] == 1) suff_add_nl(mom, load_col(f.nw, c), load_col(f.nc, c));
   }
-  block_reduce_store<16>(mom, rb.partials, red);
+  block_reduce_store<kSuffAll>(mom, rb.partials, red);
+}
+int launch_suffstats(const FrameView& f, const int16_t* flags3d, bool all3d, const int16_t* flagsN, RefitBuffers rb,
+                     cudaStream_t s) {
+  const int blocks = refit_grid(f.n, rb.num_sms);
+  suffstat_kernel<<<blocks, 256, 0, s>>>(f, flags3d, all3d ? 1 : 0, flagsN, rb);
+  return blocks;
 }
 int launch_kabsch_moments(const FrameView& f, const int16_t* flags3d, RefitBuffers rb, FrameStats* st, cudaStream_t s) {
   (void)st;
-  const int blocks = refit_grid(f.n, rb.num_sms);
-  kabsch_moments_kernel<<<blocks, 256, 0, s>>>(f, flags3d, rb);
-  return blocks;
+  return launch_suffstats(f, flags3d, flags3d == nullptr, nullptr, rb, s);
 }
 __global__ void __launch_bounds__(256)
 kabsch_solve_kernel(RefitBuffers rb, int blocks_used, ReplayOut* __restrict__ pose, int32_t* refit_ok) {
@@ -539,8 +577,7 @@ void launch_kabsch_solve(RefitBuffers rb, int blocks_used, ReplayOut* pose_inout
 // LM / Gauss-Newton on SE(3): fused residual + Jacobian + normal equations, FP64 reductions,
 // 6x6 Cholesky and the SE3 exponential in the last CTA. Twin of oracle/refine.hpp::refine_gn.
 // ================================================================================================
-__global__ void gn_init_kernel(const ReplayOut* __restrict__ pose, GnState* __restrict__ gs) {
-  if (threadIdx.x != 0) return;
+__device__ void gn_state_init(const ReplayOut* __restrict__ pose, GnState* __restrict__ gs) {
   double q[4] = {pose->q[0], pose->q[1], pose->q[2], pose->q[3]};
   const double qn = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
   for (int k = 0; k < 4; ++k) q[k] /= qn;
@@ -569,6 +606,9 @@ __global__ void gn_init_kernel(const ReplayOut* __restrict__ pose, GnState* __re
   gs->done = 0;
   gs->evals = 0;
   gs->accepted = 0;
+}
+__global__ void gn_init_kernel(const ReplayOut* __restrict__ pose, GnState* __restrict__ gs) {
+  if (threadIdx.x == 0) gn_state_init(pose, gs);
 }
 void launch_gn_init(const ReplayOut* pose, GnState* st, cudaStream_t s) { gn_init_kernel<<<1, 32, 0, s>>>(pose, st); }
 
@@ -710,6 +750,67 @@ __device__ __forceinline__ void gn_moments_to_normal_eq(const double* a, double*
   g6[5] = a[15] + a[24];
   *cost = a[25];
   *rows = a[26];
+}
+
+// One LM evaluation's bookkeeping (oracle/refine.hpp::refine_gn): accept / reject the proposal whose normal
+// equations are (Hn, gn, cost, rows), then solve for the next proposal.
+__device__ void gn_lm_update(GnState* gs, const double* Hn, const double* gn, double cost, double rows) {
+  gs->evals += 1;
+  bool finished = false;
+  if (!gs->have || cost < gs->cost_acc) {
+    for (int k = 0; k < 9; ++k) gs->Ra[k] = gs->Rp[k];
+    for (int k = 0; k < 3; ++k) gs->ta[k] = gs->tp[k];
+    for (int k = 0; k < 21; ++k) gs->H[k] = Hn[k];
+    for (int k = 0; k < 6; ++k) gs->g[k] = gn[k];
+    gs->cost_acc = cost;
+    gs->rows = (long long)rows;
+    if (gs->have) {
+      const double mu = gs->mu * 0.1;
+      gs->mu = mu < 1e-12 ? 1e-12 : mu;
+      gs->accepted += 1;
+    }
+    gs->have = 1;
+  } else {
+    gs->mu = gs->mu * 10.0;
+  }
+  if (gs->rows < 6) finished = true;
+  if (!finished) {
+    double delta[6];
+    int tries = 0;
+    double mu = gs->mu;
+    while (!gn_solve(gs->H, gs->g, mu, delta) && tries < 8) {
+      mu *= 10.0;
+      ++tries;
+    }
+    gs->mu = mu;
+    if (tries == 8) {
+      finished = true;
+    } else {
+      double mx = 0.0;
+      for (int k = 0; k < 6; ++k) mx = fabs(delta[k]) > mx ? fabs(delta[k]) : mx;
+      if (mx < 1e-10) {
+        finished = true;
+      } else {
+        for (int k = 0; k < 9; ++k) gs->Rp[k] = gs->Ra[k];
+        for (int k = 0; k < 3; ++k) gs->tp[k] = gs->ta[k];
+        se3_exp_left(delta, gs->Rp, gs->tp);
+      }
+    }
+  }
+  if (finished) gs->done = 1;
+}
+__device__ void gn_publish(const GnState* gs, ReplayOut* pose_out, double* cost_out, int32_t* evals_out) {
+  // publish the best pose accepted so far (the final answer if no later evaluation improves on it)
+  {
+    double q[4];
+    so3_from_matrix<double>(gs->Ra, q);
+    const double nn = sqrt((q[0] * q[0] + q[1] * q[1]) + (q[2] * q[2] + q[3] * q[3]));
+    for (int k = 0; k < 4; ++k) pose_out->q[k] = (float)(q[k] / nn);
+    for (int k = 0; k < 3; ++k) pose_out->t[k] = (float)gs->ta[k];
+    pose_out->refit_ok = 1;
+    *cost_out = gs->cost_acc;
+    *evals_out = gs->evals;
+  }
 }
 
 template <bool GENERIC>
@@ -865,61 +966,116 @@ gn_iteration_kernel(FrameView f, const int16_t* __restrict__ mask, int mask_cols
   } else {
     gn_moments_to_normal_eq(tot, Hn, gn, &cost, &rows);
   }
-  // ---- LM tail (oracle/refine.hpp::refine_gn, one evaluation) ----
-  gs->evals += 1;
-  bool finished = false;
-  if (!gs->have || cost < gs->cost_acc) {
-    for (int k = 0; k < 9; ++k) gs->Ra[k] = gs->Rp[k];
-    for (int k = 0; k < 3; ++k) gs->ta[k] = gs->tp[k];
-    for (int k = 0; k < 21; ++k) gs->H[k] = Hn[k];
-    for (int k = 0; k < 6; ++k) gs->g[k] = gn[k];
-    gs->cost_acc = cost;
-    gs->rows = (long long)rows;
-    if (gs->have) {
-      const double mu = gs->mu * 0.1;
-      gs->mu = mu < 1e-12 ? 1e-12 : mu;
-      gs->accepted += 1;
+  gn_lm_update(gs, Hn, gn, cost, rows);
+  gn_publish(gs, pose_out, cost_out, evals_out);
+}
+
+// ---- 3-D / normal rows only: the whole LM loop from the sufficient statistics, no further pass over the data ----
+// With y = R x + t, r = y - p (3-D) and m = R n_w, r = m - n_c (normals) every entry of the MOMENTS layout above is a
+// polynomial in (R, t) whose coefficients are the statistics S (suff_add_3d / suff_add_nl):
+//   sum y = R sx + n t              sum y y^T = R Sxx R^T + (R sx) t^T + t (R sx)^T + n t t^T
+//   sum r = sum y - sp              sum y x r = -sum y x p = axial(C - C^T), C = Spx R^T + sp t^T (C_jk = sum p_j y_k)
+//   cost  = tr(sum y y^T) - 2 tr C + spp          (normals: the same with t = 0 and Snn, Scn, scc)
+// The residuals are evaluated in binary64 here (the per-row kernel rounds them to binary32 first); the two
+// agree to the rounding of the rows, far inside the 1e-6 refinement tolerance.
+__device__ void gn_eval_from_stats(const double* S, double w3, double wn, const double* R, const double* t, double* a) {
+  for (int k = 0; k < kGnAcc; ++k) a[k] = 0.0;
+  auto sym = [](const double* u, int i, int j) -> double {  // (xx,xy,xz,yy,yz,zz) -> entry (i,j)
+    const int lo = i < j ? i : j, hi = i < j ? j : i;
+    return u[lo == 0 ? hi : (lo == 1 ? 2 + hi : 5)];
+  };
+  if (w3 > 0.0) {
+    const double n = S[0];
+    const double* sx = S + 1;
+    const double* sp = S + 4;
+    const double* Spx = S + 7;
+    const double* Sxx = S + 16;
+    double Rsx[3], Sy[3];
+    for (int i = 0; i < 3; ++i) {
+      Rsx[i] = R[3 * i] * sx[0] + R[3 * i + 1] * sx[1] + R[3 * i + 2] * sx[2];
+      Sy[i] = Rsx[i] + n * t[i];
     }
-    gs->have = 1;
-  } else {
-    gs->mu = gs->mu * 10.0;
-  }
-  if (gs->rows < 6) finished = true;
-  if (!finished) {
-    double delta[6];
-    int tries = 0;
-    double mu = gs->mu;
-    while (!gn_solve(gs->H, gs->g, mu, delta) && tries < 8) {
-      mu *= 10.0;
-      ++tries;
-    }
-    gs->mu = mu;
-    if (tries == 8) {
-      finished = true;
-    } else {
-      double mx = 0.0;
-      for (int k = 0; k < 6; ++k) mx = fabs(delta[k]) > mx ? fabs(delta[k]) : mx;
-      if (mx < 1e-10) {
-        finished = true;
-      } else {
-        for (int k = 0; k < 9; ++k) gs->Rp[k] = gs->Ra[k];
-        for (int k = 0; k < 3; ++k) gs->tp[k] = gs->ta[k];
-        se3_exp_left(delta, gs->Rp, gs->tp);
+    double RS[9];
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j)
+        RS[3 * i + j] = R[3 * i] * sym(Sxx, 0, j) + R[3 * i + 1] * sym(Sxx, 1, j) + R[3 * i + 2] * sym(Sxx, 2, j);
+    double Syy[9], C[9];
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) {
+        Syy[3 * i + j] = RS[3 * i] * R[3 * j] + RS[3 * i + 1] * R[3 * j + 1] + RS[3 * i + 2] * R[3 * j + 2] +
+                         Rsx[i] * t[j] + t[i] * Rsx[j] + n * t[i] * t[j];
+        C[3 * i + j] = Spx[3 * i] * R[3 * j] + Spx[3 * i + 1] * R[3 * j + 1] + Spx[3 * i + 2] * R[3 * j + 2] + sp[i] * t[j];
       }
-    }
+    a[0] = w3 * n;
+    for (int i = 0; i < 3; ++i) a[1 + i] = w3 * Sy[i];
+    a[4] = w3 * Syy[0];
+    a[5] = w3 * Syy[1];
+    a[6] = w3 * Syy[2];
+    a[7] = w3 * Syy[4];
+    a[8] = w3 * Syy[5];
+    a[9] = w3 * Syy[8];
+    for (int i = 0; i < 3; ++i) a[10 + i] = w3 * (Sy[i] - sp[i]);
+    a[13] = w3 * (C[3 * 1 + 2] - C[3 * 2 + 1]);
+    a[14] = w3 * (C[3 * 2 + 0] - C[3 * 0 + 2]);
+    a[15] = w3 * (C[3 * 0 + 1] - C[3 * 1 + 0]);
+    a[25] += w3 * ((Syy[0] + Syy[4] + Syy[8]) - 2.0 * (C[0] + C[4] + C[8]) + S[22]);
+    a[26] += 3.0 * n;
   }
-  if (finished) gs->done = 1;
-  // publish the best pose accepted so far (the final answer if no later evaluation improves on it)
-  {
-    double q[4];
-    so3_from_matrix<double>(gs->Ra, q);
-    const double nn = sqrt((q[0] * q[0] + q[1] * q[1]) + (q[2] * q[2] + q[3] * q[3]));
-    for (int k = 0; k < 4; ++k) pose_out->q[k] = (float)(q[k] / nn);
-    for (int k = 0; k < 3; ++k) pose_out->t[k] = (float)gs->ta[k];
-    pose_out->refit_ok = 1;
-    *cost_out = gs->cost_acc;
-    *evals_out = gs->evals;
+  if (wn > 0.0) {
+    const double nn = S[23];
+    const double* Snn = S + 24;
+    const double* Scn = S + 30;
+    double RS[9];
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j)
+        RS[3 * i + j] = R[3 * i] * sym(Snn, 0, j) + R[3 * i + 1] * sym(Snn, 1, j) + R[3 * i + 2] * sym(Snn, 2, j);
+    double Smm[9], D[9];
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) {
+        Smm[3 * i + j] = RS[3 * i] * R[3 * j] + RS[3 * i + 1] * R[3 * j + 1] + RS[3 * i + 2] * R[3 * j + 2];
+        D[3 * i + j] = Scn[3 * i] * R[3 * j] + Scn[3 * i + 1] * R[3 * j + 1] + Scn[3 * i + 2] * R[3 * j + 2];
+      }
+    a[16] = wn * Smm[0];
+    a[17] = wn * Smm[1];
+    a[18] = wn * Smm[2];
+    a[19] = wn * Smm[4];
+    a[20] = wn * Smm[5];
+    a[21] = wn * Smm[8];
+    a[22] = wn * (D[3 * 1 + 2] - D[3 * 2 + 1]);
+    a[23] = wn * (D[3 * 2 + 0] - D[3 * 0 + 2]);
+    a[24] = wn * (D[3 * 0 + 1] - D[3 * 1 + 0]);
+    a[25] += wn * ((Smm[0] + Smm[4] + Smm[8]) - 2.0 * (D[0] + D[4] + D[8]) + S[39]);
+    a[26] += 3.0 * nn;
   }
+}
+
+__global__ void __launch_bounds__(256)
+gn_from_stats_kernel(RefitBuffers rb, int blocks_used, float w3d, float wnl, int max_iters, ReplayOut* __restrict__ pose_io,
+                     GnState* __restrict__ gs_out, double* __restrict__ cost_out, int32_t* __restrict__ evals_out) {
+  __shared__ double fin_scratch[8 * 32];
+  __shared__ double fin[kMomentCount];
+  if (blocks_used > 0) {
+    final_reduce_partials(rb.partials, blocks_used, fin_scratch, fin);
+    if (threadIdx.x < kSuffAll) rb.suff[threadIdx.x] = fin[threadIdx.x];
+  } else {
+    if (threadIdx.x < kSuffAll) fin[threadIdx.x] = rb.suff[threadIdx.x];
+  }
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  GnState gs;
+  gn_state_init(pose_io, &gs);
+  for (int it = 0; it < max_iters && !gs.done; ++it) {
+    double a[kGnAcc], Hn[21], gn[6], cost, rows;
+    gn_eval_from_stats(fin, (double)w3d, (double)wnl, gs.Rp, gs.tp, a);
+    gn_moments_to_normal_eq(a, Hn, gn, &cost, &rows);
+    gn_lm_update(&gs, Hn, gn, cost, rows);
+  }
+  if (gs.evals > 0) gn_publish(&gs, pose_io, cost_out, evals_out);
+  *gs_out = gs;
+}
+void launch_gn_from_stats(RefitBuffers rb, int blocks_used, float w3d, float wnl, int max_iters, ReplayOut* pose_io,
+                          GnState* gs, double* cost_out, int32_t* evals_out, cudaStream_t s) {
+  gn_from_stats_kernel<<<1, 256, 0, s>>>(rb, blocks_used, w3d, wnl, max_iters, pose_io, gs, cost_out, evals_out);
 }
 
 void launch_gn_iteration(const FrameView& f, const int16_t* mask, int mask_cols, float w2d, float w3d, float wnl,

@@ -209,3 +209,39 @@ def test_borderline_2d_and_normal_residuals_go_to_the_exact_path(rpe, orc, gpu_c
         assert np.array_equal(votes, ref["votes"]), method
         assert np.array_equal(got["mask"], ref["mask"]), method
     orc.set_math_mode(orc.LIBM)
+
+
+def test_gn_from_statistics_3d_and_normal_rows(rpe, orc, gpu_ctx):
+    """Without 2-D rows the LM loop runs from the sufficient statistics (one launch, no pass over the data):
+    (a) statistics left by the mask kernel, (b) recomputed after rpe_set_mask, both against the per-row twin."""
+    orc.set_math_mode(orc.DET)
+    n, H = 20000, 128
+    q, t, arrs, _ = _data(rpe, 211, n, n2d=1.0, or2d=0.3, n3d=0.05, or3d=0.3, nnl=float(np.deg2rad(2.0)), ornl=0.3)
+    S = rpe.sample_table(2, n, 4, H)
+    th = _thr()
+    gpu_ctx.upload(**arrs)
+    got = gpu_ctx.ransac("nl_shinji_kneip", S, thr3d=th["thr3d"], cos_thr2d=th["cos_thr"], cos_thrN=th["cos_nl"],
+                         confidence=0.99)
+    for w in [(0.0, 1.0, 1.0), (0.0, 1.0, 0.0), (0.0, 0.0, 1.0), (0.0, 0.5, 2.0)]:
+        twin_q, twin_t, info = orc.refine_gn(got["q"], got["t"], got["mask"], w=w, max_iters=8, **arrs)
+        gpu_ctx.set_pose(got["q"], got["t"])
+        fit = gpu_ctx.refit("gn", weights=w, max_iters=8)
+        # normal rows alone leave the translation unobservable: both sides stop after the first evaluation
+        assert fit["refit_ok"] == 1 and abs(fit["refit_evals"] - info["evals"]) <= 1
+        assert _angle(fit["q"], twin_q) < 1e-6, w
+        assert np.abs(fit["t"].astype(np.float64) - twin_t.astype(np.float64)).max() < 1e-6 * 10.0, w
+        assert abs(fit["refit_cost"] - info["cost"]) <= 1e-5 * max(1.0, abs(info["cost"])), w
+    # (b) an explicit mask invalidates the cached statistics
+    rng = np.random.default_rng(5)
+    mask = got["mask"].copy()
+    mask[1, rng.random(n) < 0.3] = 0
+    mask[2, rng.random(n) < 0.3] = 0
+    gpu_ctx.set_mask(mask)
+    gpu_ctx.set_pose(got["q"], got["t"])
+    w = (0.0, 1.0, 1.0)
+    twin_q, twin_t, info = orc.refine_gn(got["q"], got["t"], mask, w=w, max_iters=8, **arrs)
+    fit = gpu_ctx.refit("gn", weights=w, max_iters=8)
+    assert _angle(fit["q"], twin_q) < 1e-6
+    assert np.abs(fit["t"].astype(np.float64) - twin_t.astype(np.float64)).max() < 1e-6 * 10.0
+    fit2 = gpu_ctx.refit("gn", weights=w, max_iters=8)  # second call: statistics now cached, starts from the refined pose
+    assert _angle(fit2["q"], twin_q) < 1e-6
