@@ -328,7 +328,9 @@ score3d_fast_kernel(const float4* __restrict__ pk, int npairs_pad, int pairs_per
     const int tp = min(kTilePairs, npairs - t * kTilePairs);
     const float4* sp = &tile[buf][0];
     for (int sub = 0; sub < tp; sub += kSubPairs) {
-      bool flag = false;
+      // smallest |s| of the group: one 3-input FMNMX3 per pair and hypothesis (NaN operands are ignored, and a NaN
+      // evaluation is never an inlier, so it never needs the exact path)
+      float smin = CUDART_INF_F;
 #pragma unroll
       for (int pp = 0; pp < kSubPairs; ++pp) {
         const float4 a = sp[(sub + pp) * 3 + 0];
@@ -338,10 +340,10 @@ score3d_fast_kernel(const float4* __restrict__ pk, int npairs_pad, int pairs_per
         for (int k = 0; k < kHypPerThread; ++k) {
           const float2 s = hyp[k].eval(a, b, c, nlo);
           cnt[k] += (int)(__float_as_uint(s.x) >> 31) + (int)(__float_as_uint(s.y) >> 31);
-          flag = flag || (fabsf(s.x) <= band) || (fabsf(s.y) <= band);
+          smin = fminf(fminf(smin, fabsf(s.x)), fabsf(s.y));
         }
       }
-      if (flag) {
+      if (smin <= band) {
         // Rare: some evaluation of this 16-correspondence group sits inside the guard band.
         // Re-walk the group, take the borderline evaluations OUT of the fast count and queue them.
         for (int pp = 0; pp < kSubPairs; ++pp) {
