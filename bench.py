@@ -240,7 +240,7 @@ def run_gpu(args, rank, world, local_rank):
     ctxs = [rpe.Context(local_rank, stream=s.cuda_stream) for s in streams]
     h_mask = [rpe.pinned_empty((2, N_CORR), np.int16) for _ in ctxs]
     for c in ctxs:
-        c.enable_stage_timing(True)
+        c.enable_stage_timing(2)  # timed legs: only the two events around the tiled scoring kernel (roofline)
 
     def frame_device(ci, fi):
         c = ctxs[ci]
@@ -278,6 +278,8 @@ def run_gpu(args, rank, world, local_rank):
                 k += 1
         return last
 
+    host_issue_ms = [0.0]  # wall time the host spends enqueueing one frame (no GPU wait unless a queue fills up)
+
     def timed(step_fn, steps, stage_acc=None):
         barrier()
         e0 = torch.cuda.Event(enable_timing=True)
@@ -285,6 +287,7 @@ def run_gpu(args, rank, world, local_rank):
         e0.record()
         k = 0
         last = None
+        t_issue = time.perf_counter()
         for _s in range(steps):
             for _f in range(args.frames_per_step):
                 last = step_fn(k % args.contexts, k % args.ring)
@@ -293,6 +296,7 @@ def run_gpu(args, rank, world, local_rank):
                 sync_all()
                 for c in ctxs:
                     stage_acc.append(c.last_stage_ms())
+        host_issue_ms[0] = (time.perf_counter() - t_issue) * 1e3 / max(1, steps * args.frames_per_step)
         sync_all()
         e1.record()
         torch.cuda.synchronize()
@@ -320,16 +324,29 @@ def run_gpu(args, rank, world, local_rank):
     stage_acc = []
     w0 = time.time()
     ms_dev, last_dev = timed(frame_device, args.steps, stage_acc)
+    issue_dev = host_issue_ms[0]
     w1 = time.time()
     launches = sum(c.launch_count() for c in ctxs) - launches0
     # --- `e2e`: host buffers, H2D + D2H inside the timed region
     w2 = time.time()
     ms_e2e, last_e2e = timed(frame_host, args.steps)
+    issue_e2e = host_issue_ms[0]
     w3 = time.time()
     sampler.stop()
     clocks = sampler.summarise(w0, w1)
     clocks_e2e = sampler.summarise(w2, w3)
     sampler.cleanup()
+
+    # --- per-stage device times of one frame running alone (all stage events on, one context, inputs in HBM)
+    ctxs[0].enable_stage_timing(1)
+    stage_alone = []
+    for i in range(6):
+        frame_device(0, i % args.ring)
+        ctxs[0].sync()
+        ctxs[0]._keep = []
+        if i > 0:
+            stage_alone.append(ctxs[0].last_stage_ms())
+    ctxs[0].enable_stage_timing(2)
 
     # --- single blocking frame latency through the C-ABI with host buffers (one context)
     lat = []
@@ -355,7 +372,7 @@ def run_gpu(args, rank, world, local_rank):
 
     # --- roofline of the dominant kernel (tiled scorer), live CUDA-event timing of that kernel alone
     fast_ms = [s["score_fast"] for s in stage_acc if s["score_fast"] > 0]
-    stage_mean = {k: float(np.mean([s[k] for s in stage_acc])) for k in stage_acc[0]} if stage_acc else {}
+    stage_mean = {k: float(np.mean([s[k] for s in stage_alone])) for k in stage_alone[0]} if stage_alone else {}
     roofline = None
     if fast_ms:
         k_ms = float(np.mean(fast_ms))
@@ -371,6 +388,12 @@ def run_gpu(args, rank, world, local_rank):
             "frac_of_nominal": achieved / NOMINAL_FP32_TFLOPS, "nominal_peak": NOMINAL_FP32_TFLOPS,
             "ffma_scalar_tflops": ffma_scalar, "ffma2_packed_tflops": ffma_packed,
             "kernel_ms": k_ms, "flop_per_eval": FLOP_PER_EVAL, "evals_per_launch": N_CORR * N_HYP,
+            "kernel_ms_note": f"mean over the timed region while {args.contexts} contexts share the GPU (the kernel "
+                              "co-runs with other frames' small kernels); kernel_alone_ms is the same kernel with one "
+                              "context",
+            "kernel_alone_ms": stage_mean.get("score_fast"),
+            "frac_alone": (FLOP_PER_EVAL * N_CORR * N_HYP / (stage_mean["score_fast"] * 1e-3) / 1e12 / peak
+                           if stage_mean.get("score_fast") and peak > 0 else None),
             "traffic": load_profile_traffic(),
             "hbm": {"algorithmic_bytes_per_launch": alg_bytes, "achieved_gbs": alg_bytes / (k_ms * 1e-3) / 1e9,
                     "peak_gbs": hbm_peak, "peak_source": "MEASURED_PEAKS.json (of measured)" if peaks else "fallback 6.65 TB/s",
@@ -420,10 +443,12 @@ def run_gpu(args, rank, world, local_rank):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, world),
             "frames_per_s": frames_total / (ms_dev * 1e-3),
             "ms_per_frame_per_gpu": ms_dev / (args.steps * args.frames_per_step),
+            "host_issue_ms_per_frame": issue_dev,
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "frames_per_s": frames_total / (ms_e2e * 1e-3), "ms_per_step": ms_e2e / args.steps,
                     "single_frame_latency_ms": {"median": float(np.median(lat)), "min": float(min(lat))},
+                    "host_issue_ms_per_frame": issue_e2e,
                     "clocks": clocks_e2e,
                     "path": "rpe_upload(host pinned) + rpe_ransac_async + rpe_refit_async x2 + mask/pose D2H, "
                             f"{args.contexts} contexts round-robin"},
@@ -496,7 +521,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--frames-per-step", type=int, default=96)
     ap.add_argument("--ring", type=int, default=24, help="distinct frames resident per GPU (>L2 in total)")
-    ap.add_argument("--contexts", type=int, default=3, help="rpe contexts (streams) per GPU, frames round-robin")
+    ap.add_argument("--contexts", type=int, default=4, help="rpe contexts (streams) per GPU, frames round-robin")
     ap.add_argument("--gn-iters", type=int, default=3)
     ap.add_argument("--ref-hyp", type=int, default=128, help="hypotheses per step of the CPU arm (bounded sample)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")

@@ -215,7 +215,9 @@ int rpe_ao_ransac(const float* x_w, const float* x_c, int n, float* R_cw, float*
 int rpe_measure_ffma_tflops(rpe_ctx* ctx, int ms_target, double* tflops_scalar, double* tflops_packed);
 /* Device time in ms of the last call's stages, measured with CUDA events on the context's stream:
  * [0] upload+pack [1] generate [2] score (fast + exact fix-up) [3] replay [4] mask+refit [5] GN [6] total
- * [7] the tiled fast scoring kernel alone (the roofline kernel) */
+ * [7] the tiled fast scoring kernel alone (the roofline kernel)
+ * rpe_enable_stage_timing: 0 = off, 1 = every stage (ten event records per frame; they cost a few percent of
+ * throughput when several contexts overlap), 2 = only the two events around the tiled scoring kernel ([7]). */
 int rpe_last_stage_ms(rpe_ctx* ctx, float ms[8]);
 int rpe_enable_stage_timing(rpe_ctx* ctx, int enable);
 

@@ -426,7 +426,8 @@ class Context:
         return int(lib.rpe_stream(self._h) or 0)
 
     def enable_stage_timing(self, on=True):
-        _check(lib.rpe_enable_stage_timing(self._h, 1 if on else 0), self._h)
+        """False/0: off; True/1: every stage; 2: only the events around the tiled scoring kernel."""
+        _check(lib.rpe_enable_stage_timing(self._h, int(on)), self._h)
 
     def last_stage_ms(self):
         ms = np.zeros(8, np.float32)

@@ -102,7 +102,8 @@ struct rpe_ctx {
   Thresh last_th = {0.f, 0.f, 0.f};
 
   // stage timing
-  bool timing = false;
+  bool timing = false;       // record the per-stage events
+  bool timing_fast = false;  // record the two events around the tiled scoring kernel
   cudaEvent_t ev[ST_COUNT + 1] = {};
   cudaEvent_t ev_fast[2] = {};
   bool ev_fast_recorded = false;
@@ -276,7 +277,7 @@ void fill_result(const rpe_ctx* ctx, rpe_result* out, int slot, bool is_refit, b
 int finish_pending(rpe_ctx* ctx) {
   for (const rpe_ctx::Pending& p : ctx->pending) fill_result(ctx, p.out, p.slot, p.is_refit, p.gn);
   ctx->pending.clear();
-  if (ctx->timing && ctx->ev_ok) {
+  if ((ctx->timing || ctx->timing_fast) && ctx->ev_ok) {
     for (int k = 0; k < ST_COUNT; ++k) ctx->stage_ms[k] = 0.f;
     for (int k = 0; k < ST_TOTAL; ++k)
       if (ctx->ev_recorded[k] && ctx->ev_recorded[k + 1]) cudaEventElapsedTime(&ctx->stage_ms[k], ctx->ev[k], ctx->ev[k + 1]);
@@ -309,7 +310,7 @@ bool g_force_exact_multi = false;  // test hook: run the exact-order kernel for 
 int score_range(rpe_ctx* ctx, int method, int slot_begin, int slot_end, Thresh th) {
   FrameView f = make_view(ctx);
   if (method == RPE_SHINJI || !g_force_exact_multi) {
-    const bool tm = ctx->timing && ctx->ev_ok;
+    const bool tm = ctx->timing_fast && ctx->ev_ok;
     if (tm) cudaEventRecord(ctx->ev_fast[0], ctx->stream);
     launch_score_fast(method, f, ctx->d_gen, ctx->d_fast, slot_begin, slot_end, th, ctx->d_votes, ctx->d_stats, ctx->wl,
                       ctx->num_sms, ctx->stream);
@@ -1050,7 +1051,8 @@ int rpe_measure_ffma_tflops(rpe_ctx* ctx, int ms_target, double* tflops_scalar, 
 
 int rpe_enable_stage_timing(rpe_ctx* ctx, int enable) {
   if (!ctx) return RPE_ERR_ARG;
-  ctx->timing = enable != 0;
+  ctx->timing = enable == 1;
+  ctx->timing_fast = enable != 0;
   return RPE_OK;
 }
 int rpe_last_stage_ms(rpe_ctx* ctx, float ms[8]) {

@@ -18,6 +18,7 @@
 // evaluations are removed from the fast count and appended to a worklist which fixup_kernel
 // re-evaluates in the reference's exact operation order. Inlier counts are therefore identical to the
 // CPU path's, evaluation by evaluation.
+#include <cstdlib>
 #include <cuda_runtime.h>
 #include <math_constants.h>
 
@@ -647,6 +648,9 @@ static int g_variant = 14;  // HPT=2, 1024-pair stages, 512 threads, 1 CTA per S
 void set_use_packed(bool v) { g_use_packed = v; }
 void set_score_variant(int v) { g_variant = v; }
 
+// RPE_SCORER_SHARED_SM=1 in the environment lets two scorer CTAs share an SM (measurement aid)
+static int g_exclusive_sm = getenv("RPE_SCORER_SHARED_SM") ? 0 : 1;
+
 template <bool PACKED, int HPT, int TILE, int THREADS, int MINB, int SUB>
 static void launch_variant(const FrameView& f, const HypGen* gen, const HypFast* fast, int slot_begin, int slot_end,
                            Thresh th, int32_t* votes, FrameStats* st, Worklist wl, int num_sms, cudaStream_t s) {
@@ -661,11 +665,15 @@ static void launch_variant(const FrameView& f, const HypGen* gen, const HypFast*
   const int groups_per_cta = (groups + gx - 1) / gx;
   const int pairs_per_cta = groups_per_cta * SUB;
   gx = (f.npairs_pad + pairs_per_cta - 1) / pairs_per_cta;
-  const size_t smem = 2 * (size_t)TILE * 3 * sizeof(float4) + 2 * sizeof(uint64_t);
+  size_t smem = 2 * (size_t)TILE * 3 * sizeof(float4) + 2 * sizeof(uint64_t);
+  // One scorer CTA per SM is the design point (MINB = 1): ask for more than half of the SM's shared memory so that a
+  // second context's scorer queues behind this one instead of time-slicing the same FMA pipe (same throughput,
+  // twice the latency per launch); the small kernels of other frames still co-run in the remaining space.
+  if (MINB == 1 && g_exclusive_sm && smem < (size_t)116 * 1024) smem = (size_t)116 * 1024;
   auto kern = score3d_fast_kernel<PACKED, HPT, TILE, THREADS, MINB, SUB>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem > (size_t)116 * 1024 ? smem : (size_t)116 * 1024));
     attr_set = true;
   }
   kern<<<dim3(gx, gy), THREADS, smem, s>>>(f.pk, f.npairs_pad, pairs_per_cta, fast, gen, slot_begin, slot_end, th.thr3d,
