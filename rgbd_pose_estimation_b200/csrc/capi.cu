@@ -9,6 +9,9 @@
 #include <string.h>
 
 #include <string>
+#include <cstdlib>
+#include <deque>
+#include <mutex>
 #include <vector>
 
 #include "kernels.cuh"
@@ -36,7 +39,7 @@ using namespace rpe;
 namespace {
 
 enum { A_BV = 0, A_XC = 1, A_NC = 2, A_XW = 3, A_NW = 4 };
-constexpr int kNumStaging = 96;  // results that may be in flight before an implicit drain
+constexpr int kNumStaging = 256;  // results that may be in flight; when full only the oldest one is waited for
 enum { ST_UPLOAD = 0, ST_GEN = 1, ST_SCORE = 2, ST_REPLAY = 3, ST_MASK = 4, ST_GN = 5, ST_TOTAL = 6, ST_FAST = 7, ST_COUNT = 8 };
 
 }  // namespace
@@ -98,7 +101,10 @@ struct rpe_ctx {
     int slot;
     bool is_refit, gn;
   };
-  std::vector<Pending> pending;
+  std::deque<Pending> pending;
+  int next_slot = 0;                      // staging slots are handed out round-robin
+  cudaEvent_t ev_lane[2] = {};            // fences between this context's stream and the device's scorer lane
+  cudaEvent_t ev_slot[kNumStaging] = {};  // recorded behind each result's device-to-host copies
   Thresh last_th = {0.f, 0.f, 0.f};
 
   // stage timing
@@ -294,30 +300,80 @@ int finish_pending(rpe_ctx* ctx) {
   return RPE_OK;
 }
 
-// claim a pinned staging slot for an enqueued result; drains the queue first when it is full
+// claim a pinned staging slot for an enqueued result; when all are in flight, wait for the OLDEST result only
+// (its event) and deliver it, so that a long asynchronous stream of frames never drains the GPU queue
 int claim_slot(rpe_ctx* ctx, int* slot) {
   if ((int)ctx->pending.size() >= kNumStaging) {
-    CK(cudaStreamSynchronize(ctx->stream));
-    finish_pending(ctx);
+    const rpe_ctx::Pending p = ctx->pending.front();
+    CK(cudaEventSynchronize(ctx->ev_slot[p.slot]));
+    fill_result(ctx, p.out, p.slot, p.is_refit, p.gn);
+    ctx->pending.pop_front();
   }
-  *slot = (int)ctx->pending.size();
+  *slot = ctx->next_slot;
+  ctx->next_slot = (ctx->next_slot + 1) % kNumStaging;
+  return RPE_OK;
+}
+// the result whose copies were just enqueued becomes pending
+int push_pending(rpe_ctx* ctx, rpe_result* out, int slot, bool is_refit, bool gn) {
+  CK(cudaEventRecord(ctx->ev_slot[slot], ctx->stream));
+  ctx->pending.push_back(rpe_ctx::Pending{out, slot, is_refit, gn});
   return RPE_OK;
 }
 
 bool g_force_exact_multi = false;  // test hook: run the exact-order kernel for the non-AO families
+
+// ---- the scorer lane -----------------------------------------------------------------------------------
+// The tiled scorer fills every SM (one 512-thread CTA with > half of the shared memory per SM), so two of them never
+// run side by side: when several contexts (streams) are in flight their scorers are launched into ONE per-device
+// stream, in submission order, fenced against the owning context's stream by events. Other frames' small kernels
+// (pack, generation, replay, mask, refinement) keep overlapping the running scorer from their own streams, and the
+// CUDA events recorded around a scorer launch bracket its execution instead of its wait for the SMs.
+// RPE_SCORER_LANE=0 in the environment launches scorers on the context's own stream instead.
+struct ScorerLane {
+  std::mutex mu;
+  cudaStream_t stream = nullptr;
+  bool tried = false;
+};
+ScorerLane g_lane[64];
+const bool g_lane_enabled = !(getenv("RPE_SCORER_LANE") && getenv("RPE_SCORER_LANE")[0] == '0');
+
+ScorerLane* lane_for(rpe_ctx* ctx) {
+  if (!g_lane_enabled || ctx->device < 0 || ctx->device >= 64 || !ctx->ev_ok) return nullptr;
+  ScorerLane* L = &g_lane[ctx->device];
+  std::lock_guard<std::mutex> g(L->mu);
+  if (!L->tried) {
+    L->tried = true;
+    if (cudaStreamCreateWithFlags(&L->stream, cudaStreamNonBlocking) != cudaSuccess) {
+      (void)cudaGetLastError();
+      L->stream = nullptr;
+    }
+  }
+  return L->stream ? L : nullptr;
+}
 
 // score the slot range with the best available kernel, including the exact fix-up
 int score_range(rpe_ctx* ctx, int method, int slot_begin, int slot_end, Thresh th) {
   FrameView f = make_view(ctx);
   if (method == RPE_SHINJI || !g_force_exact_multi) {
     const bool tm = ctx->timing_fast && ctx->ev_ok;
-    if (tm) cudaEventRecord(ctx->ev_fast[0], ctx->stream);
-    launch_score_fast(method, f, ctx->d_gen, ctx->d_fast, slot_begin, slot_end, th, ctx->d_votes, ctx->d_stats, ctx->wl,
-                      ctx->num_sms, ctx->stream);
-    if (tm) {
-      cudaEventRecord(ctx->ev_fast[1], ctx->stream);
-      ctx->ev_fast_recorded = true;
+    ScorerLane* lane = lane_for(ctx);
+    if (lane) {
+      CK(cudaEventRecord(ctx->ev_lane[0], ctx->stream));  // everything the scorer reads has been enqueued before this
+      std::lock_guard<std::mutex> g(lane->mu);
+      CK(cudaStreamWaitEvent(lane->stream, ctx->ev_lane[0], 0));
+      if (tm) cudaEventRecord(ctx->ev_fast[0], lane->stream);
+      launch_score_fast(method, f, ctx->d_gen, ctx->d_fast, slot_begin, slot_end, th, ctx->d_votes, ctx->d_stats, ctx->wl,
+                        ctx->num_sms, lane->stream);
+      if (tm) cudaEventRecord(ctx->ev_fast[1], lane->stream);
+      CK(cudaEventRecord(ctx->ev_lane[1], lane->stream));
+      CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_lane[1], 0));
+    } else {
+      if (tm) cudaEventRecord(ctx->ev_fast[0], ctx->stream);
+      launch_score_fast(method, f, ctx->d_gen, ctx->d_fast, slot_begin, slot_end, th, ctx->d_votes, ctx->d_stats, ctx->wl,
+                        ctx->num_sms, ctx->stream);
+      if (tm) cudaEventRecord(ctx->ev_fast[1], ctx->stream);
     }
+    if (tm) ctx->ev_fast_recorded = true;
     launch_fixup(method, f, ctx->d_gen, th, ctx->d_votes, ctx->d_stats, ctx->wl, ctx->num_sms, ctx->stream);
     launch_score_exact(method, f, ctx->d_gen, slot_begin, slot_end, th, ctx->d_votes, ctx->d_stats, true, ctx->num_sms,
                        ctx->stream);
@@ -348,7 +404,7 @@ int do_finish(rpe_ctx* ctx, int method, Thresh th, rpe_result* out, int16_t* mas
   if (mask)
     CK(cudaMemcpyAsync(mask, ctx->d_mask, (size_t)ctx->n * ctx->mask_cols * sizeof(int16_t), cudaMemcpyDeviceToHost,
                        ctx->stream));
-  ctx->pending.push_back(rpe_ctx::Pending{out, slot, false, false});
+  if (int rcp = push_pending(ctx, out, slot, false, false)) return rcp;
   if (blocking) {
     CK(cudaStreamSynchronize(ctx->stream));
     finish_pending(ctx);
@@ -514,6 +570,10 @@ static int create_common(int device, void* stream, bool own, rpe_ctx** out) {
   }
   for (int k = 0; k <= ST_COUNT && ok; ++k) ok = ok && cudaEventCreate(&ctx->ev[k]) == cudaSuccess;
   for (int k = 0; k < 2 && ok; ++k) ok = ok && cudaEventCreate(&ctx->ev_fast[k]) == cudaSuccess;
+  for (int k = 0; k < kNumStaging && ok; ++k)
+    ok = ok && cudaEventCreateWithFlags(&ctx->ev_slot[k], cudaEventDisableTiming) == cudaSuccess;
+  for (int k = 0; k < 2 && ok; ++k)
+    ok = ok && cudaEventCreateWithFlags(&ctx->ev_lane[k], cudaEventDisableTiming) == cudaSuccess;
   ctx->ev_ok = ok;
   if (!ok) {
     rpe_destroy(ctx);
@@ -567,6 +627,10 @@ int rpe_destroy(rpe_ctx* ctx) {
     if (ctx->ev[k]) cudaEventDestroy(ctx->ev[k]);
   for (int k = 0; k < 2; ++k)
     if (ctx->ev_fast[k]) cudaEventDestroy(ctx->ev_fast[k]);
+  for (int k = 0; k < kNumStaging; ++k)
+    if (ctx->ev_slot[k]) cudaEventDestroy(ctx->ev_slot[k]);
+  for (int k = 0; k < 2; ++k)
+    if (ctx->ev_lane[k]) cudaEventDestroy(ctx->ev_lane[k]);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
   (void)cudaGetLastError();
   delete ctx;
@@ -722,7 +786,7 @@ static int do_refit(rpe_ctx* ctx, int kind, const float* weights, int max_iters,
   }
   ctx->kabsch_valid = false;
   CK(cudaMemcpyAsync(&ctx->h_pose[slot], ctx->d_pose, sizeof(ReplayOut), cudaMemcpyDeviceToHost, ctx->stream));
-  ctx->pending.push_back(rpe_ctx::Pending{out, slot, true, gn});
+  if (int rcp = push_pending(ctx, out, slot, true, gn)) return rcp;
   if (blocking) {
     CK(cudaStreamSynchronize(ctx->stream));
     finish_pending(ctx);

@@ -219,3 +219,24 @@ def test_worklist_overflow_falls_back_to_exact_rescoring(rpe, orc):
         rpe.lib.rpe_debug_set_worklist_capacity(ctx.handle, 1 << 21)
         got2 = ctx.ransac(SHINJI, S, thr3d=0.25, confidence=0.9999)
         assert got2["flags"] == 0 and np.array_equal(ctx.get_votes(H), ref["votes"])
+
+
+def test_async_queue_longer_than_the_staging_ring(rpe, orc, gpu_ctx):
+    """More results in flight than pinned staging slots (256): the oldest are delivered early, none is lost."""
+    n, H = 600, 32
+    q, t, Q, P = _frame(rpe, 77, n)
+    gpu_ctx.upload(xc=P, xw=Q)
+    tables = [rpe.sample_table(1000 + i, n, 3, H) for i in range(8)]
+    want = [gpu_ctx.ransac(SHINJI, S, thr3d=0.25, confidence=0.9999, want_mask=False) for S in tables]
+    pend = []
+    for i in range(300):
+        pend.append((i % 8, gpu_ctx.ransac_async(SHINJI, tables[i % 8], thr3d=0.25, confidence=0.9999)))
+        pend.append((-1, gpu_ctx.refit_async("kabsch_inliers")))
+    gpu_ctx.sync()
+    for k, r in pend:
+        if k >= 0:
+            assert r.max_votes == want[k]["max_votes"] and r.winner == want[k]["winner"]
+            assert r.iter_final == want[k]["iter_final"]
+        else:
+            assert r.refit_ok == 1
+    gpu_ctx._keep = []
