@@ -81,7 +81,10 @@ struct rpe_ctx {
   ReplayOut* h_pose = nullptr;    // pinned, kNumStaging slots; [0] doubles as scratch for set_pose
   bool kabsch_valid = false;
   bool suff_valid = false;  // rb.suff matches the inlier columns in d_mask
-  Worklist wl = {nullptr, 0};
+  Worklist wl = {nullptr, nullptr, 0};
+  unsigned int wl_allocated = 0;  // entries allocated (wl.capacity may be lowered by the test hook)
+  unsigned int wl_want = 0;       // grow to this many entries before the next scoring call (set after an overflow)
+  bool wl_fixed = false;          // test hook in force: no automatic growth
   int16_t* d_mask = nullptr;
   size_t mask_cap = 0;
   int mask_cols = 0;
@@ -280,8 +283,19 @@ void fill_result(const rpe_ctx* ctx, rpe_result* out, int slot, bool is_refit, b
   }
 }
 
+// a delivered result that reports a worklist overflow asks for a larger list
+void note_overflow(rpe_ctx* ctx, int slot) {
+  if ((ctx->h_pose[slot].flags & 1) && !ctx->wl_fixed && ctx->wl_allocated < (1u << 26)) {
+    const unsigned int want = ctx->wl_allocated * 4u;
+    if (want > ctx->wl_want) ctx->wl_want = want;
+  }
+}
+
 int finish_pending(rpe_ctx* ctx) {
-  for (const rpe_ctx::Pending& p : ctx->pending) fill_result(ctx, p.out, p.slot, p.is_refit, p.gn);
+  for (const rpe_ctx::Pending& p : ctx->pending) {
+    fill_result(ctx, p.out, p.slot, p.is_refit, p.gn);
+    note_overflow(ctx, p.slot);
+  }
   ctx->pending.clear();
   if ((ctx->timing || ctx->timing_fast) && ctx->ev_ok) {
     for (int k = 0; k < ST_COUNT; ++k) ctx->stage_ms[k] = 0.f;
@@ -307,6 +321,7 @@ int claim_slot(rpe_ctx* ctx, int* slot) {
     const rpe_ctx::Pending p = ctx->pending.front();
     CK(cudaEventSynchronize(ctx->ev_slot[p.slot]));
     fill_result(ctx, p.out, p.slot, p.is_refit, p.gn);
+    note_overflow(ctx, p.slot);
     ctx->pending.pop_front();
   }
   *slot = ctx->next_slot;
@@ -321,6 +336,25 @@ int push_pending(rpe_ctx* ctx, rpe_result* out, int slot, bool is_refit, bool gn
 }
 
 bool g_force_exact_multi = false;  // test hook: run the exact-order kernel for the non-AO families
+
+// The borderline worklist starts at 4 Mi entries (32 MiB). A frame that overflows it is still answered exactly (the
+// whole frame is rescored in the reference's operation order), and the list is grown x4 (up to 64 Mi entries) before
+// the next scoring call so that dense frames with many near-threshold 2-D evaluations stay on the fast path.
+constexpr unsigned int kWorklistInitial = 1u << 22, kWorklistMax = 1u << 26;
+int alloc_worklist(rpe_ctx* ctx, unsigned int entries) {
+  if (ctx->wl.entries) cudaFree(ctx->wl.entries);
+  ctx->wl.entries = nullptr;
+  CK(cudaMalloc(&ctx->wl.entries, (size_t)entries * sizeof(uint2)));
+  ctx->wl_allocated = entries;
+  ctx->wl.capacity = entries;
+  return RPE_OK;
+}
+int grow_worklist(rpe_ctx* ctx) {
+  if (ctx->wl_fixed || ctx->wl_want <= ctx->wl_allocated) return RPE_OK;
+  CK(cudaStreamSynchronize(ctx->stream));  // kernels in flight may still read the old list
+  finish_pending(ctx);
+  return alloc_worklist(ctx, ctx->wl_want);
+}
 
 // ---- the scorer lane -----------------------------------------------------------------------------------
 // The tiled scorer fills every SM (one 512-thread CTA with > half of the shared memory per SM), so two of them never
@@ -357,24 +391,26 @@ int score_range(rpe_ctx* ctx, int method, int slot_begin, int slot_end, Thresh t
   if (method == RPE_SHINJI || !g_force_exact_multi) {
     const bool tm = ctx->timing_fast && ctx->ev_ok;
     ScorerLane* lane = lane_for(ctx);
+    int nseg = 0;
+    if (int rcw = grow_worklist(ctx)) return rcw;
     if (lane) {
       CK(cudaEventRecord(ctx->ev_lane[0], ctx->stream));  // everything the scorer reads has been enqueued before this
       std::lock_guard<std::mutex> g(lane->mu);
       CK(cudaStreamWaitEvent(lane->stream, ctx->ev_lane[0], 0));
       if (tm) cudaEventRecord(ctx->ev_fast[0], lane->stream);
-      launch_score_fast(method, f, ctx->d_gen, ctx->d_fast, slot_begin, slot_end, th, ctx->d_votes, ctx->d_stats, ctx->wl,
-                        ctx->num_sms, lane->stream);
+      nseg = launch_score_fast(method, f, ctx->d_gen, ctx->d_fast, slot_begin, slot_end, th, ctx->d_votes, ctx->d_stats,
+                               ctx->wl, ctx->num_sms, lane->stream);
       if (tm) cudaEventRecord(ctx->ev_fast[1], lane->stream);
       CK(cudaEventRecord(ctx->ev_lane[1], lane->stream));
       CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_lane[1], 0));
     } else {
       if (tm) cudaEventRecord(ctx->ev_fast[0], ctx->stream);
-      launch_score_fast(method, f, ctx->d_gen, ctx->d_fast, slot_begin, slot_end, th, ctx->d_votes, ctx->d_stats, ctx->wl,
-                        ctx->num_sms, ctx->stream);
+      nseg = launch_score_fast(method, f, ctx->d_gen, ctx->d_fast, slot_begin, slot_end, th, ctx->d_votes, ctx->d_stats,
+                               ctx->wl, ctx->num_sms, ctx->stream);
       if (tm) cudaEventRecord(ctx->ev_fast[1], ctx->stream);
     }
     if (tm) ctx->ev_fast_recorded = true;
-    launch_fixup(method, f, ctx->d_gen, th, ctx->d_votes, ctx->d_stats, ctx->wl, ctx->num_sms, ctx->stream);
+    launch_fixup(method, f, ctx->d_gen, th, ctx->d_votes, ctx->d_stats, ctx->wl, nseg, ctx->num_sms, ctx->stream);
     launch_score_exact(method, f, ctx->d_gen, slot_begin, slot_end, th, ctx->d_votes, ctx->d_stats, true, ctx->num_sms,
                        ctx->stream);
     ctx->launches += 4;
@@ -561,8 +597,9 @@ static int create_common(int device, void* stream, bool own, rpe_ctx** out) {
   ok = ok && cudaMalloc(&ctx->d_gn_evals, sizeof(int32_t)) == cudaSuccess;
   ok = ok && cudaMallocHost(&ctx->h_gn_cost, kNumStaging * sizeof(double)) == cudaSuccess;
   ok = ok && cudaMallocHost(&ctx->h_gn_evals, kNumStaging * sizeof(int32_t)) == cudaSuccess;
-  ctx->wl.capacity = 1u << 21;  // 2 Mi borderline evaluations (16 MiB)
-  ok = ok && cudaMalloc(&ctx->wl.entries, (size_t)ctx->wl.capacity * sizeof(uint2)) == cudaSuccess;
+  ok = ok && alloc_worklist(ctx, kWorklistInitial) == RPE_OK;
+  ok = ok && cudaMalloc(&ctx->wl.counts, kMaxWorklistSegments * sizeof(unsigned int)) == cudaSuccess;
+  ok = ok && cudaMemsetAsync(ctx->wl.counts, 0, kMaxWorklistSegments * sizeof(unsigned int), ctx->stream) == cudaSuccess;
   if (ok) {
     ok = ok && cudaMemsetAsync(ctx->d_stats, 0, sizeof(FrameStats), ctx->stream) == cudaSuccess;
     ok = ok && cudaMemsetAsync(ctx->d_pose, 0, sizeof(ReplayOut), ctx->stream) == cudaSuccess;
@@ -612,6 +649,7 @@ int rpe_destroy(rpe_ctx* ctx) {
   cudaFree(ctx->d_kabsch);
   if (ctx->h_pose) cudaFreeHost(ctx->h_pose);
   cudaFree(ctx->wl.entries);
+  cudaFree(ctx->wl.counts);
   cudaFree(ctx->d_mask);
   cudaFree(ctx->rb.partials);
   cudaFree(ctx->rb.moments);
@@ -1133,7 +1171,8 @@ int rpe_debug_set_packed(int packed) {
 // test hook: shrink the borderline worklist so that the overflow -> whole-frame exact rescoring path can be exercised
 int rpe_debug_set_worklist_capacity(rpe_ctx* ctx, unsigned int cap) {
   if (!ctx) return RPE_ERR_ARG;
-  ctx->wl.capacity = cap < (1u << 21) ? cap : (1u << 21);
+  ctx->wl.capacity = cap < ctx->wl_allocated ? cap : ctx->wl_allocated;
+  ctx->wl_fixed = cap < ctx->wl_allocated;
   return RPE_OK;
 }
 int rpe_debug_force_exact_multi(int v) {

@@ -26,10 +26,15 @@ struct Thresh {
   float thr3d, cos_thr, cos_nl;
 };
 
+// Borderline evaluations queued for the exact fix-up. The list is segmented: CTA k of a scoring launch (k =
+// blockIdx.y * gridDim.x + blockIdx.x, nseg CTAs in all) owns entries [k * seg, (k + 1) * seg) with seg = capacity / nseg,
+// counts them in shared memory and publishes counts[k] when it ends — no global same-address atomics in the scorer.
 struct Worklist {
-  uint2* entries;  // (slot, correspondence)
+  uint2* entries;        // (slot, modality << 30 | correspondence)
+  unsigned int* counts;  // [kMaxWorklistSegments]
   unsigned int capacity;
 };
+constexpr int kMaxWorklistSegments = 8192;
 
 constexpr int kSubPairs = 8;       // correspondences are rescanned in groups of 16
 constexpr int kTilePairs = 256;    // pairs per shared-memory stage
@@ -46,10 +51,10 @@ void launch_hypgen(int method, const FrameView& f, const int32_t* samples_dev, i
 void launch_derive_fast(const HypGen* gen, HypFast* fast, int32_t* votes, int n_slots, FrameStats* st, cudaStream_t s);
 
 // -- scoring -------------------------------------------------------------------------------------
-void launch_score_fast(int method, const FrameView& f, const HypGen* gen, const HypFast* fast, int slot_begin,
+int launch_score_fast(int method, const FrameView& f, const HypGen* gen, const HypFast* fast, int slot_begin,
                        int slot_end, Thresh th, int32_t* votes, FrameStats* st, Worklist wl, int num_sms, cudaStream_t s);
 void launch_fixup(int method, const FrameView& f, const HypGen* gen, Thresh th, int32_t* votes, FrameStats* st,
-                  Worklist wl, int num_sms, cudaStream_t s);
+                  Worklist wl, int nseg, int num_sms, cudaStream_t s);
 void launch_consume_worklist(FrameStats* st, cudaStream_t s);
 // exact-order scoring of every (slot, correspondence); `only_if_overflow` makes it a no-op unless
 // the fast pass overflowed its worklist.

@@ -190,14 +190,51 @@ void launch_pack(const FrameView& f, int kind, float4* pk_out, FrameStats* st, c
 }
 
 // ================================================================================================
+// this CTA's segment of the borderline worklist (see struct Worklist)
+// ================================================================================================
+struct WlSegment {
+  uint2* base;
+  unsigned int cap;
+  unsigned int* n;  // shared-memory counter
+  __device__ __forceinline__ explicit WlSegment(const Worklist& wl) {
+    __shared__ unsigned int counter;
+    n = &counter;
+    const unsigned int nseg = gridDim.x * gridDim.y, cta = blockIdx.y * gridDim.x + blockIdx.x;
+    cap = wl.capacity / nseg;
+    base = wl.entries + (size_t)cta * cap;
+    if (threadIdx.x == 0) counter = 0;  // ordered before the first push by the __syncthreads after the mbarrier init
+  }
+  __device__ __forceinline__ void push(uint2 e, FrameStats* st) {
+    const unsigned int i = atomicAdd(n, 1u);
+    if (i < cap)
+      base[i] = e;
+    else
+      st->wl_overflow = 1u;
+  }
+  // every thread of the CTA calls this once, after its last push
+  __device__ __forceinline__ void publish(const Worklist& wl, FrameStats* st) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const unsigned int cnt = *n;
+      wl.counts[blockIdx.y * gridDim.x + blockIdx.x] = cnt < cap ? cnt : cap;
+      if (cnt) atomicAdd(&st->wl_count, cnt);
+    }
+  }
+};
+
+// ================================================================================================
 // fast tiled scorer — 3-D modality (RPE_SHINJI)
 // ================================================================================================
 // Guard band on s = r^2 - thr^2:  band = thr * u * (64 M + 16 thr),  u = 2^-24,
-// M >= |x_w| + |x_c| + |t| for every (correspondence, hypothesis) of the frame.
-__device__ __forceinline__ float guard_band_3d(const FrameStats* st, float thr) {
-  const float M = __uint_as_float(st->m_corr_bits) + __uint_as_float(st->t_max_bits);
+// M >= |x_w| + |x_c| + |t| for every correspondence of the frame and THIS hypothesis (per-hypothesis |t|: one wild
+// hypothesis must not widen the band of the others).
+__device__ __forceinline__ float hyp_magnitude(const FrameStats* st, float nt0, float nt1, float nt2) {
+  const float tn = sqrtf(nt0 * nt0 + nt1 * nt1 + nt2 * nt2);
+  return (__uint_as_float(st->m_corr_bits) + tn) * 1.0001f;
+}
+__device__ __forceinline__ float guard_band_3d(float M, float thr) {
   const float u = 5.9604644775390625e-08f;
-  return thr * u * (64.f * M * 1.0001f + 16.f * thr);
+  return thr * u * (64.f * M + 16.f * thr);
 }
 
 template <bool PACKED>
@@ -219,6 +256,7 @@ struct HypRegs<true> {
       nt[i] = make_float2(v, v);
     }
   }
+  __device__ __forceinline__ float magnitude(const FrameStats* st) const { return hyp_magnitude(st, nt[0].x, nt[1].x, nt[2].x); }
   // s for both correspondences of the pair
   __device__ __forceinline__ float2 eval(const float4& a, const float4& b, const float4& c, float2 nlo) const {
     const float2 X0 = make_float2(a.x, a.y), X1 = make_float2(a.z, a.w), X2 = make_float2(b.x, b.y);
@@ -252,6 +290,7 @@ struct HypRegs<false> {
 #pragma unroll
     for (int i = 0; i < 3; ++i) nt[i] = live ? h->nt[i] : CUDART_NAN_F;
   }
+  __device__ __forceinline__ float magnitude(const FrameStats* st) const { return hyp_magnitude(st, nt[0], nt[1], nt[2]); }
   __device__ __forceinline__ float one(float x0, float x1, float x2, float p0, float p1, float p2, float nlo) const {
     float e0 = p0 + nt[0], e1 = p1 + nt[1], e2 = p2 + nt[2];
     e0 = fmaf(nR[0], x0, e0);
@@ -291,6 +330,7 @@ score3d_fast_kernel(const float4* __restrict__ pk, int npairs_pad, int pairs_per
   const int p_end = min(p_begin + pairs_per_cta, npairs_pad);
   const int npairs = p_end - p_begin;
   const int ntiles = (npairs + kTilePairs - 1) / kTilePairs;
+  WlSegment seg(wl);
 
   // hypotheses of this thread
   HypRegs<PACKED> hyp[kHypPerThread];
@@ -304,7 +344,9 @@ score3d_fast_kernel(const float4* __restrict__ pk, int npairs_pad, int pairs_per
     if (!live) slot[k] = -1;
     cnt[k] = 0;
   }
-  const float band = guard_band_3d(st, thr);
+  float band[kHypPerThread];
+#pragma unroll
+  for (int k = 0; k < kHypPerThread; ++k) band[k] = guard_band_3d(hyp[k].magnitude(st), thr);  // NaN for a dead slot
   const float thr2 = __fmul_rn(thr, thr);
   const float2 nlo = make_float2(-thr2, -thr2);
 
@@ -331,7 +373,9 @@ score3d_fast_kernel(const float4* __restrict__ pk, int npairs_pad, int pairs_per
     for (int sub = 0; sub < tp; sub += kSubPairs) {
       // smallest |s| of the group: one 3-input FMNMX3 per pair and hypothesis (NaN operands are ignored, and a NaN
       // evaluation is never an inlier, so it never needs the exact path)
-      float smin = CUDART_INF_F;
+      float smin[kHypPerThread];
+#pragma unroll
+      for (int k = 0; k < kHypPerThread; ++k) smin[k] = CUDART_INF_F;
 #pragma unroll
       for (int pp = 0; pp < kSubPairs; ++pp) {
         const float4 a = sp[(sub + pp) * 3 + 0];
@@ -341,10 +385,13 @@ score3d_fast_kernel(const float4* __restrict__ pk, int npairs_pad, int pairs_per
         for (int k = 0; k < kHypPerThread; ++k) {
           const float2 s = hyp[k].eval(a, b, c, nlo);
           cnt[k] += (int)(__float_as_uint(s.x) >> 31) + (int)(__float_as_uint(s.y) >> 31);
-          smin = fminf(fminf(smin, fabsf(s.x)), fabsf(s.y));
+          smin[k] = fminf(fminf(smin[k], fabsf(s.x)), fabsf(s.y));
         }
       }
-      if (smin <= band) {
+      bool any = false;
+#pragma unroll
+      for (int k = 0; k < kHypPerThread; ++k) any = any || (smin[k] <= band[k]);
+      if (any) {
         // Rare: some evaluation of this 16-correspondence group sits inside the guard band.
         // Re-walk the group, take the borderline evaluations OUT of the fast count and queue them.
         for (int pp = 0; pp < kSubPairs; ++pp) {
@@ -357,14 +404,10 @@ score3d_fast_kernel(const float4* __restrict__ pk, int npairs_pad, int pairs_per
             const float sv[2] = {s.x, s.y};
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
-              if (fabsf(sv[u]) <= band) {
+              if (fabsf(sv[u]) <= band[k]) {
                 cnt[k] -= (int)(__float_as_uint(sv[u]) >> 31);
                 const unsigned int corr = (unsigned int)(2 * (p_begin + t * kTilePairs + sub + pp) + u);
-                const unsigned int idx = atomicAdd(&st->wl_count, 1u);
-                if (idx < wl.capacity)
-                  wl.entries[idx] = make_uint2((unsigned int)slot[k], corr | (1u << 30));
-                else
-                  st->wl_overflow = 1u;
+                seg.push(make_uint2((unsigned int)slot[k], corr | (1u << 30)), st);
               }
             }
           }
@@ -384,6 +427,7 @@ score3d_fast_kernel(const float4* __restrict__ pk, int npairs_pad, int pairs_per
 #pragma unroll
   for (int k = 0; k < kHypPerThread; ++k)
     if (slot[k] >= 0 && cnt[k] != 0) atomicAdd(&votes[slot[k]], cnt[k]);
+  seg.publish(wl, st);
 }
 
 // ================================================================================================
@@ -410,13 +454,13 @@ struct KindTraits {
   static constexpr int off_nc = off_nw + 6;
 };
 
-struct BandConsts {
-  float band3;        // on s3
-  float a0_2d, a1_2d; // band2 = a0 + a1 * n2
-  float band_n;       // on g'
+struct BandConsts {   // per hypothesis
+  float band3;            // on s3
+  float k1_2d, k2_2d, c0_2d;  // band2 = k1 |d'| + k2 n2 + c0
+  float band_n;           // on g'
 };
 
-template <int KIND, int TILE, int THREADS>
+template <int KIND, int TILE, int THREADS, bool DIRECT>
 __global__ void __launch_bounds__(THREADS, 1)
 score_multi_fast_kernel(const float4* __restrict__ pk, int npairs_pad, int pairs_per_cta, const HypFast* __restrict__ fast,
                         const HypGen* __restrict__ gen, int slot_begin, int slot_end, Thresh th,
@@ -434,6 +478,7 @@ score_multi_fast_kernel(const float4* __restrict__ pk, int npairs_pad, int pairs
   const int p_end = min(p_begin + pairs_per_cta, npairs_pad);
   const int npairs = p_end - p_begin;
   const int ntiles = (npairs + TILE - 1) / TILE;
+  WlSegment seg(wl);
 
   float nR[HPT][9], nt[HPT][3];
   int slot[HPT], cnt[HPT];
@@ -449,17 +494,24 @@ score_multi_fast_kernel(const float4* __restrict__ pk, int npairs_pad, int pairs
     if (!live) slot[k] = -1;
     cnt[k] = 0;
   }
-  // guard bands from the per-frame magnitude bounds
-  BandConsts bc;
-  {
+  // Guard bands from the frame's magnitude bound and THIS hypothesis' |t| (M >= |x_w| + |x_c| + |t|).
+  // 2-D: the rigorous band is beta(|y|) = c u 1.1 (64 M |y| + 26 |y|^2). |y| needs no square root:
+  //   * if |F'| <= beta <= 0.19 c^2 n2 then d'^2 >= 0.81 c^2 n2, i.e. |y| <= 1.112 |d'| / c, hence
+  //     beta <= u 1.1 (71.2 M |d'| + 26 c n2);
+  //   * otherwise |y| < y0 = 375 u M / c (a point within ~1e-5 M of the camera centre) and beta <= beta(y0) =: c0.
+  // band2 = k1 |d'| + k2 n2 + c0 therefore covers beta in both regimes.
+  BandConsts bc[HPT];
+#pragma unroll
+  for (int k = 0; k < HPT; ++k) {
     const float u = 5.9604644775390625e-08f;
-    const float mcorr = __uint_as_float(st->m_corr_bits), tmax = __uint_as_float(st->t_max_bits);
-    const float M = (mcorr + tmax) * 1.0001f;  // >= |x_w| + |x_c| + |t| (and >= |x_w| + |t|)
-    bc.band3 = th.thr3d * u * (64.f * M + 16.f * th.thr3d);
-    bc.a0_2d = th.cos_thr * u * 1.1f * (32.f * M);
-    bc.a1_2d = th.cos_thr * u * 1.1f * (32.f * M + 26.f);
+    const float M = hyp_magnitude(st, nt[k][0], nt[k][1], nt[k][2]);  // NaN for a dead slot: never borderline
+    bc[k].band3 = guard_band_3d(M, th.thr3d);
+    bc[k].k1_2d = u * 1.1f * 71.2f * M;
+    bc[k].k2_2d = u * 1.1f * 26.f * th.cos_thr;
+    const float y0 = 375.f * u * M / th.cos_thr;
+    bc[k].c0_2d = th.cos_thr * u * 1.1f * (64.f * M * y0 + 26.f * y0 * y0);
     const float nmax = __uint_as_float(st->m_bv_bits) * 1.0001f;
-    bc.band_n = u * 1.1f * (29.f * nmax * nmax + 2.f);
+    bc[k].band_n = u * 1.1f * (29.f * nmax * nmax + 2.f);
   }
   const float thr2 = __fmul_rn(th.thr3d, th.thr3d);
   const float2 nlo = make_float2(-thr2, -thr2);
@@ -481,8 +533,12 @@ score_multi_fast_kernel(const float4* __restrict__ pk, int npairs_pad, int pairs
     }
   }
 
-  // One (pair, hypothesis) unit. rescan == false: count sign bits and OR the band flags;
-  // rescan == true : take borderline evaluations out of the count and queue them for the exact fix-up.
+  // One (pair, hypothesis) unit.
+  // DIRECT (default): a borderline evaluation is queued for the exact fix-up on the spot instead of being counted —
+  //   frames with many near-threshold evaluations (dense frames, low outlier ratios, pixel-level 2-D thresholds) would
+  //   otherwise re-walk almost every group;
+  // otherwise: rescan == false counts sign bits and ORs the band flags of a 16-correspondence group, rescan == true
+  //   re-walks a flagged group, takes the borderline evaluations out of the count and queues them.
   auto unit = [&](const float* rec, int k, bool rescan, bool& flag, int corr0) {
     const float2 X0 = make_float2(rec[0], rec[1]), X1 = make_float2(rec[2], rec[3]), X2 = make_float2(rec[4], rec[5]);
     float2 ny0 = make_float2(nt[k][0], nt[k][0]), ny1 = make_float2(nt[k][1], nt[k][1]), ny2 = make_float2(nt[k][2], nt[k][2]);
@@ -507,7 +563,7 @@ score_multi_fast_kernel(const float4* __restrict__ pk, int npairs_pad, int pairs
       s = __ffma2_rn(e2, e2, s);
       val[1][0] = s.x;
       val[1][1] = s.y;
-      bnd[1][0] = bnd[1][1] = bc.band3;
+      bnd[1][0] = bnd[1][1] = bc[k].band3;
     }
     if (KT::k2) {
       const float* b = rec + KT::off_bv;
@@ -517,7 +573,8 @@ score_multi_fast_kernel(const float4* __restrict__ pk, int npairs_pad, int pairs
       float2 n2 = __fmul2_rn(ny0, ny0);
       n2 = __ffma2_rn(ny1, ny1, n2);
       n2 = __ffma2_rn(ny2, ny2, n2);
-      const float2 band2 = __ffma2_rn(make_float2(bc.a1_2d, bc.a1_2d), n2, make_float2(bc.a0_2d, bc.a0_2d));
+      float2 band2 = __ffma2_rn(make_float2(bc[k].k2_2d, bc[k].k2_2d), n2, make_float2(bc[k].c0_2d, bc[k].c0_2d));
+      band2 = __ffma2_rn(make_float2(bc[k].k1_2d, bc[k].k1_2d), make_float2(fabsf(d.x), fabsf(d.y)), band2);
       val[0][0] = fmaf(c2, n2.x, d.x * fabsf(d.x));
       val[0][1] = fmaf(c2, n2.y, d.y * fabsf(d.y));
       bnd[0][0] = band2.x;
@@ -541,7 +598,7 @@ score_multi_fast_kernel(const float4* __restrict__ pk, int npairs_pad, int pairs
       g = __ffma2_rn(make_float2(c[4], c[5]), m2, g);
       val[2][0] = g.x;
       val[2][1] = g.y;
-      bnd[2][0] = bnd[2][1] = bc.band_n;
+      bnd[2][0] = bnd[2][1] = bc[k].band_n;
     }
 #pragma unroll
     for (int mod = 0; mod < 3; ++mod) {
@@ -549,16 +606,17 @@ score_multi_fast_kernel(const float4* __restrict__ pk, int npairs_pad, int pairs
 #pragma unroll
       for (int uu = 0; uu < 2; ++uu) {
         const float v = val[mod][uu];
-        if (!rescan) {
+        if (DIRECT) {
+          if (fabsf(v) <= bnd[mod][uu])
+            seg.push(make_uint2((unsigned int)slot[k], (unsigned int)(corr0 + uu) | ((unsigned int)mod << 30)), st);
+          else
+            cnt[k] += (int)(__float_as_uint(v) >> 31);
+        } else if (!rescan) {
           cnt[k] += (int)(__float_as_uint(v) >> 31);
           flag = flag || (fabsf(v) <= bnd[mod][uu]);
         } else if (fabsf(v) <= bnd[mod][uu]) {
           cnt[k] -= (int)(__float_as_uint(v) >> 31);
-          const unsigned int idx = atomicAdd(&st->wl_count, 1u);
-          if (idx < wl.capacity)
-            wl.entries[idx] = make_uint2((unsigned int)slot[k], (unsigned int)(corr0 + uu) | ((unsigned int)mod << 30));
-          else
-            st->wl_overflow = 1u;
+          seg.push(make_uint2((unsigned int)slot[k], (unsigned int)(corr0 + uu) | ((unsigned int)mod << 30)), st);
         }
       }
     }
@@ -583,9 +641,9 @@ score_multi_fast_kernel(const float4* __restrict__ pk, int npairs_pad, int pairs
           rec[4 * i + 3] = v.w;
         }
 #pragma unroll
-        for (int k = 0; k < HPT; ++k) unit(rec, k, false, flag, 0);
+        for (int k = 0; k < HPT; ++k) unit(rec, k, false, flag, 2 * (p_begin + t * TILE + sub + pp));
       }
-      if (flag) {
+      if (!DIRECT && flag) {
         for (int pp = 0; pp < SUB; ++pp) {
           float rec[F4 * 4];
 #pragma unroll
@@ -614,31 +672,42 @@ score_multi_fast_kernel(const float4* __restrict__ pk, int npairs_pad, int pairs
 #pragma unroll
   for (int k = 0; k < HPT; ++k)
     if (slot[k] >= 0 && cnt[k] != 0) atomicAdd(&votes[slot[k]], cnt[k]);
+  seg.publish(wl, st);
 }
 
 template <int KIND>
-static void launch_multi(const FrameView& f, const HypGen* gen, const HypFast* fast, int slot_begin, int slot_end, Thresh th,
+static int launch_multi(const FrameView& f, const HypGen* gen, const HypFast* fast, int slot_begin, int slot_end, Thresh th,
                          int32_t* votes, FrameStats* st, Worklist wl, int num_sms, cudaStream_t s) {
   constexpr int THREADS = 256, HPT = 2;
   constexpr int F4 = KindTraits<KIND>::f4pp;
-  constexpr int TILE = F4 <= 3 ? 1024 : 512;
+  // two stages of TILE pairs; sized so that at least two 256-thread CTAs (16 warps) fit on an SM for every kind
+  constexpr int TILE = F4 <= 3 ? 1024 : (F4 <= 6 ? 512 : 256);
   const int nslots = slot_end - slot_begin;
   const int gy = (nslots + THREADS * HPT - 1) / (THREADS * HPT);
   const int groups = f.npairs_pad / kSubPairs;
-  int gx = (2 * num_sms + gy - 1) / gy;
+  int gx = (2 * num_sms) / gy;  // never more CTAs than the 2-per-SM resident slots: a partial second wave doubles the time
   if (gx < 1) gx = 1;
   if (gx > groups) gx = groups;
   const int groups_per_cta = (groups + gx - 1) / gx;
   const int pairs_per_cta = groups_per_cta * kSubPairs;
   gx = (f.npairs_pad + pairs_per_cta - 1) / pairs_per_cta;
   const size_t smem = 2 * (size_t)TILE * F4 * sizeof(float4) + 2 * sizeof(uint64_t);
-  auto kern = score_multi_fast_kernel<KIND, TILE, THREADS>;
+  // kinds with the 2-D test queue borderline evaluations on the spot (pixel-level thresholds put a percent of a good
+  // hypothesis' evaluations inside the band); without it the group flag + rare re-walk is cheaper
+  static const bool direct = getenv("RPE_MULTI_DIRECT") ? getenv("RPE_MULTI_DIRECT")[0] != '0' : KindTraits<KIND>::k2;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(score_multi_fast_kernel<KIND, TILE, THREADS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(score_multi_fast_kernel<KIND, TILE, THREADS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     attr_set = true;
   }
-  kern<<<dim3(gx, gy), THREADS, smem, s>>>(f.pk, f.npairs_pad, pairs_per_cta, fast, gen, slot_begin, slot_end, th, votes, st, wl);
+  if (direct)
+    score_multi_fast_kernel<KIND, TILE, THREADS, true><<<dim3(gx, gy), THREADS, smem, s>>>(
+        f.pk, f.npairs_pad, pairs_per_cta, fast, gen, slot_begin, slot_end, th, votes, st, wl);
+  else
+    score_multi_fast_kernel<KIND, TILE, THREADS, false><<<dim3(gx, gy), THREADS, smem, s>>>(
+        f.pk, f.npairs_pad, pairs_per_cta, fast, gen, slot_begin, slot_end, th, votes, st, wl);
+  return gx * gy;
 }
 
 static bool g_use_packed = true;
@@ -652,14 +721,14 @@ void set_score_variant(int v) { g_variant = v; }
 static int g_exclusive_sm = getenv("RPE_SCORER_SHARED_SM") ? 0 : 1;
 
 template <bool PACKED, int HPT, int TILE, int THREADS, int MINB, int SUB>
-static void launch_variant(const FrameView& f, const HypGen* gen, const HypFast* fast, int slot_begin, int slot_end,
+static int launch_variant(const FrameView& f, const HypGen* gen, const HypFast* fast, int slot_begin, int slot_end,
                            Thresh th, int32_t* votes, FrameStats* st, Worklist wl, int num_sms, cudaStream_t s) {
   const int nslots = slot_end - slot_begin;
   const int hyp_per_cta = THREADS * HPT;
   const int gy = (nslots + hyp_per_cta - 1) / hyp_per_cta;
   // correspondences are handed out in groups of kSubPairs pairs (the pack pads to that), SUB divides into it
   const int groups = f.npairs_pad / SUB;
-  int gx = (MINB * num_sms + gy - 1) / gy;  // aim at MINB resident CTAs per SM in total
+  int gx = (MINB * num_sms) / gy;  // at most MINB resident CTAs per SM in total (no partial second wave)
   if (gx < 1) gx = 1;
   if (gx > groups) gx = groups;
   const int groups_per_cta = (groups + gx - 1) / gx;
@@ -678,45 +747,44 @@ static void launch_variant(const FrameView& f, const HypGen* gen, const HypFast*
   }
   kern<<<dim3(gx, gy), THREADS, smem, s>>>(f.pk, f.npairs_pad, pairs_per_cta, fast, gen, slot_begin, slot_end, th.thr3d,
                                             votes, st, wl, g_nosync);
+  return gx * gy;
 }
 
-void launch_score_fast(int method, const FrameView& f, const HypGen* gen, const HypFast* fast, int slot_begin,
-                       int slot_end, Thresh th, int32_t* votes, FrameStats* st, Worklist wl, int num_sms,
-                       cudaStream_t s) {
-  if (slot_end - slot_begin <= 0 || f.n <= 0) return;
+int launch_score_fast(int method, const FrameView& f, const HypGen* gen, const HypFast* fast, int slot_begin,
+                      int slot_end, Thresh th, int32_t* votes, FrameStats* st, Worklist wl, int num_sms,
+                      cudaStream_t s) {
+  if (slot_end - slot_begin <= 0 || f.n <= 0) return 0;
   if (method != RPE_SHINJI) {
     switch (f.pk_kind) {
-      case 1: launch_multi<1>(f, gen, fast, slot_begin, slot_end, th, votes, st, wl, num_sms, s); break;
-      case 3: launch_multi<3>(f, gen, fast, slot_begin, slot_end, th, votes, st, wl, num_sms, s); break;
-      case 5: launch_multi<5>(f, gen, fast, slot_begin, slot_end, th, votes, st, wl, num_sms, s); break;
-      case 6: launch_multi<6>(f, gen, fast, slot_begin, slot_end, th, votes, st, wl, num_sms, s); break;
-      case 7: launch_multi<7>(f, gen, fast, slot_begin, slot_end, th, votes, st, wl, num_sms, s); break;
-      default: break;
+      case 1: return launch_multi<1>(f, gen, fast, slot_begin, slot_end, th, votes, st, wl, num_sms, s);
+      case 3: return launch_multi<3>(f, gen, fast, slot_begin, slot_end, th, votes, st, wl, num_sms, s);
+      case 5: return launch_multi<5>(f, gen, fast, slot_begin, slot_end, th, votes, st, wl, num_sms, s);
+      case 6: return launch_multi<6>(f, gen, fast, slot_begin, slot_end, th, votes, st, wl, num_sms, s);
+      case 7: return launch_multi<7>(f, gen, fast, slot_begin, slot_end, th, votes, st, wl, num_sms, s);
+      default: return 0;
     }
-    return;
   }
-#define RPE_V(P, H, T, TH, MB, SB) launch_variant<P, H, T, TH, MB, SB>(f, gen, fast, slot_begin, slot_end, th, votes, st, wl, num_sms, s)
+#define RPE_V(P, H, T, TH, MB, SB) return launch_variant<P, H, T, TH, MB, SB>(f, gen, fast, slot_begin, slot_end, th, votes, st, wl, num_sms, s)
   if (!g_use_packed) {
     RPE_V(false, 2, 256, 256, 2, 8);
-    return;
   }
   switch (g_variant) {
     default:
-    case 0: RPE_V(true, 2, 256, 256, 2, 8); break;
-    case 1: RPE_V(true, 2, 512, 256, 2, 8); break;
-    case 2: RPE_V(true, 2, 256, 256, 3, 8); break;
-    case 3: RPE_V(true, 4, 256, 128, 3, 8); break;
-    case 4: RPE_V(true, 1, 256, 256, 4, 8); break;
-    case 5: RPE_V(true, 2, 512, 512, 1, 8); break;
-    case 6: RPE_V(true, 4, 256, 256, 1, 8); break;
-    case 7: RPE_V(true, 2, 256, 128, 4, 8); break;
-    case 8: RPE_V(true, 2, 256, 256, 2, 4); break;
-    case 9: RPE_V(true, 4, 256, 128, 4, 8); break;
-    case 10: RPE_V(true, 4, 256, 256, 2, 8); break;
-    case 11: RPE_V(true, 3, 256, 128, 4, 8); break;
-    case 12: RPE_V(true, 4, 512, 256, 2, 8); break;
-    case 13: RPE_V(true, 1, 512, 1024, 1, 8); break;
-    case 14: RPE_V(true, 2, 1024, 512, 1, 8); break;
+    case 0: RPE_V(true, 2, 256, 256, 2, 8); 
+    case 1: RPE_V(true, 2, 512, 256, 2, 8); 
+    case 2: RPE_V(true, 2, 256, 256, 3, 8); 
+    case 3: RPE_V(true, 4, 256, 128, 3, 8); 
+    case 4: RPE_V(true, 1, 256, 256, 4, 8); 
+    case 5: RPE_V(true, 2, 512, 512, 1, 8); 
+    case 6: RPE_V(true, 4, 256, 256, 1, 8); 
+    case 7: RPE_V(true, 2, 256, 128, 4, 8); 
+    case 8: RPE_V(true, 2, 256, 256, 2, 4); 
+    case 9: RPE_V(true, 4, 256, 128, 4, 8); 
+    case 10: RPE_V(true, 4, 256, 256, 2, 8); 
+    case 11: RPE_V(true, 3, 256, 128, 4, 8); 
+    case 12: RPE_V(true, 4, 512, 256, 2, 8); 
+    case 13: RPE_V(true, 1, 512, 1024, 1, 8); 
+    case 14: RPE_V(true, 2, 1024, 512, 1, 8); 
     case 15: RPE_V(true, 2, 512, 512, 1, 16); break;
   }
 #undef RPE_V
@@ -740,12 +808,16 @@ __device__ __forceinline__ bool exact_eval(int method, int modality, const Frame
   return ex_test_2d(h.q, h.t, method == RPE_KNEIP ? Rm : nullptr, load_col(f.xw, c), load_col(f.bv, c), th.cos_thr);
 }
 
-__global__ void fixup_kernel(int method, FrameView f, const HypGen* __restrict__ gen, Thresh th,
-                             int32_t* __restrict__ votes, const FrameStats* __restrict__ st, Worklist wl) {
+constexpr int kFixupChunks = 4;  // CTAs per worklist segment
+__global__ void __launch_bounds__(256)
+fixup_kernel(int method, FrameView f, const HypGen* __restrict__ gen, Thresh th, int32_t* __restrict__ votes,
+             const FrameStats* __restrict__ st, Worklist wl, int nseg) {
   if (st->wl_overflow) return;  // the whole frame is rescored exactly instead
-  const unsigned int count = min(st->wl_count, wl.capacity);
-  for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
-    const uint2 e = wl.entries[i];
+  const unsigned int cap = wl.capacity / (unsigned int)nseg;
+  const unsigned int count = min(wl.counts[blockIdx.x], cap);
+  const uint2* seg = wl.entries + (size_t)blockIdx.x * cap;
+  for (unsigned int i = blockIdx.y * blockDim.x + threadIdx.x; i < count; i += gridDim.y * blockDim.x) {
+    const uint2 e = seg[i];
     const int slot = (int)e.x;
     const int modality = (int)(e.y >> 30);
     const int c = (int)(e.y & 0x3fffffffu);
@@ -767,8 +839,10 @@ __global__ void consume_worklist_kernel(FrameStats* st) {
 void launch_consume_worklist(FrameStats* st, cudaStream_t s) { consume_worklist_kernel<<<1, 32, 0, s>>>(st); }
 
 void launch_fixup(int method, const FrameView& f, const HypGen* gen, Thresh th, int32_t* votes, FrameStats* st,
-                  Worklist wl, int num_sms, cudaStream_t s) {
-  fixup_kernel<<<num_sms, 256, 0, s>>>(method, f, gen, th, votes, st, wl);
+                  Worklist wl, int nseg, int num_sms, cudaStream_t s) {
+  (void)num_sms;
+  if (nseg <= 0) return;
+  fixup_kernel<<<dim3(nseg, kFixupChunks), 256, 0, s>>>(method, f, gen, th, votes, st, wl, nseg);
 }
 
 // Whole-frame exact scoring. Thread <-> slot, CTA column <-> correspondence slice; every lane reads the

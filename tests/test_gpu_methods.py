@@ -245,3 +245,25 @@ def test_gn_from_statistics_3d_and_normal_rows(rpe, orc, gpu_ctx):
     assert np.abs(fit["t"].astype(np.float64) - twin_t.astype(np.float64)).max() < 1e-6 * 10.0
     fit2 = gpu_ctx.refit("gn", weights=w, max_iters=8)  # second call: statistics now cached, starts from the refined pose
     assert _angle(fit2["q"], twin_q) < 1e-6
+
+
+def test_many_borderline_2d_evaluations_stay_exact(rpe, orc):
+    """Low outlier ratio + pixel-level 2-D threshold: about a percent of a good hypothesis' evaluations fall inside the
+    rigorous guard band. They are queued on the spot (segmented worklist), the list grows after an overflow, and the
+    votes stay bit-identical to the CPU path."""
+    orc.set_math_mode(orc.DET)
+    n, H = 40000, 256
+    q, t, arrs, _ = _data(rpe, 401, n, n2d=1.0, or2d=0.1, n3d=0.05, or3d=0.1, nnl=float(np.deg2rad(2.0)), ornl=0.1)
+    S = rpe.sample_table(4, n, 4, H)
+    th = _thr()
+    ref = orc.ransac(5, S, confidence=0.99, full=True, nthreads=8, **th, **arrs)
+    with rpe.Context(0) as ctx:
+        ctx.upload(**arrs)
+        for rep in range(3):
+            got = ctx.ransac("nl_shinji_kneip", S, thr3d=th["thr3d"], cos_thr2d=th["cos_thr"], cos_thrN=th["cos_nl"],
+                             confidence=0.99)
+            assert np.array_equal(ctx.get_votes(3 * H), ref["votes"]), rep
+            assert got["winner"] == ref["winner"] and got["iter_final"] == ref["iter_final"]
+            assert np.array_equal(got["mask"], ref["mask"])
+        assert got["n_borderline"] > 50000
+        assert got["flags"] == 0  # by now the worklist holds them all
