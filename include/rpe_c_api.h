@@ -123,10 +123,12 @@ int rpe_num_correspondences(const rpe_ctx* ctx);
 /* ---- robust estimation ------------------------------------------------------------------
  * samples: int32 [H x 4] (host, page-locked host, or device memory) rows of correspondence indices (3 used by RPE_SHINJI), exactly the
  *          draws RandomElements::run / ProsacSampler::sample would produce (see rpe_sample_table).
- * H      : the caller's `Iter` on entry. All H iterations are generated and scored on the GPU;
- *          the reference's sequential rule (strict `votes > max`, Iter = RANSACUpdateNumIters(..))
- *          is then replayed on the device, so winner / max_votes / iter_final / mask are exactly
- *          what the early-stopping CPU loop returns.
+ * H      : the caller's `Iter` on entry. Up to 1024 iterations are generated and scored on the GPU
+ *          in one go; the reference's sequential rule (strict `votes > max`, Iter =
+ *          RANSACUpdateNumIters(..)) is then replayed on the device, so winner / max_votes /
+ *          iter_final / mask are exactly what the early-stopping CPU loop returns. A longer Iter is
+ *          scored progressively (1024, 2048, 4096, then 8192 iterations per pass) and the host looks
+ *          at the replayed bound between passes — those calls synchronise even when `_async`.
  * thr3d  : dist_thre_3d_ (metres). cos_thr2d: cos(atan(thre_2d_/focal)) (P3P.hpp:323).
  * cos_thrN: cos(nl_thre) (AbsoluteOrientationNormal.hpp:223). Unused ones are ignored.
  * mask   : host int16 [n x cols] column-major, cols = 1 (KNEIP*), 2 (SHINJI, SHINJI_KNEIP), 3 (NL_*);

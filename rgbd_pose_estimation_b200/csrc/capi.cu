@@ -448,7 +448,9 @@ int do_finish(rpe_ctx* ctx, int method, Thresh th, rpe_result* out, int16_t* mas
   return RPE_OK;
 }
 
-constexpr int kMaxPassIters = 8192;  // iterations generated + scored per device pass
+constexpr int kMaxPassIters = 8192;  // iterations generated + scored per device pass, at most
+constexpr int kFirstPassIters = 1024;  // a longer Iter is scored progressively: 1024, 2048, 4096, 8192, 8192, ... iterations,
+                                       // looking at the adaptive bound in between (the reference rarely gets past a few hundred)
 
 int do_ransac(rpe_ctx* ctx, int method, const int32_t* samples, int H, float thr3d, float cos_thr2d, float cos_thrN,
               float confidence, rpe_result* out, int16_t* mask, bool blocking) {
@@ -461,8 +463,8 @@ int do_ransac(rpe_ctx* ctx, int method, const int32_t* samples, int H, float thr
   const Thresh th = {thr3d, cos_thr2d, cos_thrN};
   if (!ctx->upload_stamped) stamp(ctx, ST_UPLOAD);
   ctx->upload_stamped = false;
-  const int pass = H < kMaxPassIters ? H : kMaxPassIters;
-  rc = ensure_hyp_capacity(ctx, pass, pass * S);
+  const int pass_cap = H < kMaxPassIters ? H : kMaxPassIters;
+  rc = ensure_hyp_capacity(ctx, pass_cap, pass_cap * S);
   if (rc) return rc;
   // sample table: device pointers are used in place; host memory is copied on the stream (pageable memory is
   // staged by the driver before the call returns, page-locked memory must stay alive until rpe_sync)
@@ -483,8 +485,9 @@ int do_ransac(rpe_ctx* ctx, int method, const int32_t* samples, int H, float thr
     rc = ensure_packed(ctx, kind_for_method(method));
     if (rc) return rc;
   }
-  const bool single = H <= pass;
-  for (int base = 0; base < H; base += pass) {
+  const bool single = H <= kFirstPassIters;
+  int pass = single ? H : kFirstPassIters;
+  for (int base = 0; base < H; base += pass, pass = (2 * pass < kMaxPassIters ? 2 * pass : kMaxPassIters)) {
     const int hc = (H - base) < pass ? (H - base) : pass;
     const int32_t* chunk = samples + (size_t)base * 4;
     const int32_t* samples_dev = chunk;

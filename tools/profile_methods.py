@@ -29,7 +29,8 @@ for name, m in rpe.METHODS.items():
     st = {k: float(np.median([x[k] for x in ms[1:]])) for k in ms[0]}
     slots = r["n_slots"]
     evals = slots * N
-    out[name] = {"slots": slots, "score_ms": st["score"], "score_fast_ms": st["score_fast"], "total_ms": st["total"],
+    out[name] = {"slots": slots, "stages_ms": {k: round(v, 4) for k, v in st.items()},
+                 "score_ms": st["score"], "score_fast_ms": st["score_fast"], "total_ms": st["total"],
                  "G_evals_per_s": evals / (st["score_fast"] * 1e-3) / 1e9 if st["score_fast"] > 0 else None,
                  "n_borderline": r["n_borderline"], "flags": r["flags"], "max_votes": r["max_votes"]}
     print(name, json.dumps(out[name]))
