@@ -76,25 +76,22 @@ rpe::SE3<Tp> shinji(const M& X_w_, const M& X_c_, int K) {
 
 template <typename Tp>
 void shinji_ransac(AOPoseAdapter<Tp>& adapter, const Tp dist_thre_3d_, int& Iter, Tp confidence = 0.99) {
-  std::vector<int32_t> table;
-  rpe::detail::draw_ransac_table(adapter.getNumberCorrespondences(), 3, Iter, &table);
-  rpe::detail::run_ransac<Tp>(adapter, RPE_SHINJI, table, dist_thre_3d_, Tp(0), Tp(0), Iter, confidence);
+  rpe::detail::RansacRows rows(adapter.getNumberCorrespondences(), 3);
+  rpe::detail::run_ransac<Tp>(adapter, RPE_SHINJI, rows, nullptr, dist_thre_3d_, Tp(0), Tp(0), Iter, confidence);
   adapter.cvtInlier();  // [reference :153]
 }
 
 template <typename Tp>
 void shinji_ransac2(AOOnlyPoseAdapter<Tp>& adapter, const Tp dist_thre_3d_, int& Iter, Tp confidence = 0.99) {
-  std::vector<int32_t> table;
-  rpe::detail::draw_ransac_table(adapter.getNumberCorrespondences(), 3, Iter, &table);
-  rpe::detail::run_ransac<Tp>(adapter, RPE_SHINJI, table, dist_thre_3d_, Tp(0), Tp(0), Iter, confidence);
+  rpe::detail::RansacRows rows(adapter.getNumberCorrespondences(), 3);
+  rpe::detail::run_ransac<Tp>(adapter, RPE_SHINJI, rows, nullptr, dist_thre_3d_, Tp(0), Tp(0), Iter, confidence);
   adapter.cvtInlier();  // [reference :210]
 }
 
 template <typename Tp>
 void shinji_prosac(AOOnlyPoseAdapter<Tp>& adapter, const Tp dist_thre_3d_, int& Iter, Tp confidence = 0.99) {
-  std::vector<int32_t> table;
-  rpe::detail::draw_prosac_table<Tp>(adapter, 3, Iter, &table);
-  rpe::detail::run_ransac<Tp>(adapter, RPE_SHINJI, table, dist_thre_3d_, Tp(0), Tp(0), Iter, confidence);
+  rpe::detail::ProsacRows<Tp, AOOnlyPoseAdapter<Tp> > rows(adapter, 3);
+  rpe::detail::run_ransac<Tp>(adapter, RPE_SHINJI, rows, nullptr, dist_thre_3d_, Tp(0), Tp(0), Iter, confidence);
   adapter.cvtInlier();  // [reference :268]
 }
 
@@ -115,9 +112,8 @@ template <typename Tp>
 void shinji_kneip_ransac(AOPoseAdapter<Tp>& adapter, const Tp dist_thre_3d_, const Tp thre_2d_, int& Iter,
                          Tp confidence = 0.99) {
   const Tp cos_thr = std::cos(std::atan(thre_2d_ / adapter.getFocal()));  // [reference :373]
-  std::vector<int32_t> table;
-  rpe::detail::draw_ransac_table(adapter.getNumberCorrespondences(), 4, Iter, &table);
-  rpe::detail::run_ransac<Tp>(adapter, RPE_SHINJI_KNEIP, table, dist_thre_3d_, cos_thr, Tp(0), Iter, confidence);
+  rpe::detail::RansacRows rows(adapter.getNumberCorrespondences(), 4);
+  rpe::detail::run_ransac<Tp>(adapter, RPE_SHINJI_KNEIP, rows, nullptr, dist_thre_3d_, cos_thr, Tp(0), Iter, confidence);
   PnPPoseAdapter<Tp>* pAdapter = &adapter;  // [reference :433-435]
   pAdapter->cvtInlier();
   adapter.cvtInlier();
@@ -127,9 +123,8 @@ template <typename Tp>
 void shinji_kneip_prosac(AOPoseAdapter<Tp>& adapter, const Tp dist_thre_3d_, const Tp thre_2d_, int& Iter,
                          Tp confidence = 0.99) {
   const Tp cos_thr = std::cos(std::atan(thre_2d_ / adapter.getFocal()));  // [reference :446]
-  std::vector<int32_t> table;
-  rpe::detail::draw_prosac_table<Tp>(adapter, 4, Iter, &table);
-  rpe::detail::run_ransac<Tp>(adapter, RPE_SHINJI_KNEIP, table, dist_thre_3d_, cos_thr, Tp(0), Iter, confidence);
+  rpe::detail::ProsacRows<Tp, AOPoseAdapter<Tp> > rows(adapter, 4);
+  rpe::detail::run_ransac<Tp>(adapter, RPE_SHINJI_KNEIP, rows, nullptr, dist_thre_3d_, cos_thr, Tp(0), Iter, confidence);
   PnPPoseAdapter<Tp>* pAdapter = &adapter;
   pAdapter->cvtInlier();
   adapter.cvtInlier();

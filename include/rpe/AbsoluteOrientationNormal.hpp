@@ -40,18 +40,16 @@ template <typename Tp>
 void nl_kneip_ransac(NormalAOPoseAdapter<Tp>& adapter, const Tp thre_2d_, const Tp nl_thre, int& Iter, Tp confidence = 0.99) {
   const Tp cos_thr = std::cos(std::atan(thre_2d_ / adapter.getFocal()));  // [reference :222]
   const Tp cos_nl_thre = std::cos(nl_thre);                          // [reference :223]
-  std::vector<int32_t> table;
-  rpe::detail::draw_ransac_table(adapter.getNumberCorrespondences(), 4, Iter, &table);
-  rpe::detail::run_ransac<Tp>(adapter, RPE_NL_KNEIP, table, Tp(0), cos_thr, cos_nl_thre, Iter, confidence);
+  rpe::detail::RansacRows rows(adapter.getNumberCorrespondences(), 4);
+  rpe::detail::run_ransac<Tp>(adapter, RPE_NL_KNEIP, rows, nullptr, Tp(0), cos_thr, cos_nl_thre, Iter, confidence);
   rpe::detail::nl_cvt_all(adapter, true, false);  // [reference :279-281]
 }
 
 template <typename Tp>
 void nl_shinji_ransac(NormalAOPoseAdapter<Tp>& adapter, const Tp thre_3d_, const Tp nl_thre, int& Iter, Tp confidence = 0.99) {
   const Tp cos_nl_thre = std::cos(nl_thre);  // [reference :294]
-  std::vector<int32_t> table;
-  rpe::detail::draw_ransac_table(adapter.getNumberCorrespondences(), 4, Iter, &table);
-  rpe::detail::run_ransac<Tp>(adapter, RPE_NL_SHINJI, table, thre_3d_, Tp(0), cos_nl_thre, Iter, confidence);
+  rpe::detail::RansacRows rows(adapter.getNumberCorrespondences(), 4);
+  rpe::detail::run_ransac<Tp>(adapter, RPE_NL_SHINJI, rows, nullptr, thre_3d_, Tp(0), cos_nl_thre, Iter, confidence);
   rpe::detail::nl_cvt_all(adapter, false, true);  // [reference :350-352]
 }
 
@@ -60,9 +58,8 @@ void nl_shinji_kneip_ransac(NormalAOPoseAdapter<Tp>& adapter, const Tp thre_3d_,
                             int& Iter, Tp confidence = 0.99) {
   const Tp cos_thr = std::cos(std::atan(thre_2d_ / adapter.getFocal()));  // [reference :363]
   const Tp cos_nl_thre = std::cos(nl_thre);                          // [reference :364]
-  std::vector<int32_t> table;
-  rpe::detail::draw_ransac_table(adapter.getNumberCorrespondences(), 4, Iter, &table);
-  rpe::detail::run_ransac<Tp>(adapter, RPE_NL_SHINJI_KNEIP, table, thre_3d_, cos_thr, cos_nl_thre, Iter, confidence);
+  rpe::detail::RansacRows rows(adapter.getNumberCorrespondences(), 4);
+  rpe::detail::run_ransac<Tp>(adapter, RPE_NL_SHINJI_KNEIP, rows, nullptr, thre_3d_, cos_thr, cos_nl_thre, Iter, confidence);
   rpe::detail::nl_cvt_all(adapter, true, true);  // [reference :439-443]
 }
 

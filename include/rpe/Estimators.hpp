@@ -53,6 +53,52 @@ inline void draw_prosac_table(Adapter& adapter, int m, int H, std::vector<int32_
   }
 }
 
+// ---- row producers: one sample row per RANSAC iteration, drawn in order on demand -------------------------------
+// (the GPU asks for the rows of one pass at a time — rpe_ransac_stream — so a caller whose Iter is 100 000 does not pay
+// for 100 000 draws when the adaptive bound stops the loop after a few hundred iterations)
+class RansacRows {  // `RandomElements<int> re(n); re.run(m, &sel)` per iteration (e.g. AbsoluteOrientation.hpp:111,124)
+ public:
+  RansacRows(int n, int m, RandSource* src = nullptr) : m_(m), re_(n, src) {}
+  void restart() {}  // RandomElements leaves the identity permutation behind after every run
+  void row(int32_t* out) {
+    re_.run(m_, &sel_);
+    for (int k = 0; k < 4; ++k) out[k] = k < (int)sel_.size() ? sel_[k] : -1;
+  }
+
+ private:
+  int m_;
+  RandomElements<int> re_;
+  std::vector<int> sel_;
+};
+// ProsacSampler draws mapped through adapter.getSortedIdx (e.g. AbsoluteOrientation.hpp:221-229); index n == N is clamped
+template <class Tp, class Adapter>
+class ProsacRows {
+ public:
+  ProsacRows(Adapter& adapter, int m, RandSource* src = nullptr)
+      : adapter_(adapter), m_(m), n_(adapter.getNumberCorrespondences()), src_(src), ps_(m, n_, src) {
+    adapter_.sortIdx();
+  }
+  void restart() { ps_ = ProsacSampler<Tp>(m_, n_, src_); }
+  void row(int32_t* out) {
+    std::vector<int> sel;
+    ps_.sample(&sel);
+    adapter_.getSortedIdx(sel);
+    for (int k = 0; k < 4; ++k) out[k] = k < m_ ? (sel[k] < n_ ? sel[k] : n_ - 1) : -1;
+  }
+
+ private:
+  Adapter& adapter_;
+  int m_, n_;
+  RandSource* src_;
+  ProsacSampler<Tp> ps_;
+};
+template <class Rows>
+inline int rows_callback(void* user, int /*first_iteration*/, int count, int32_t* out) {
+  Rows* rows = static_cast<Rows*>(user);
+  for (int i = 0; i < count; ++i) rows->row(out + 4 * (size_t)i);
+  return 0;
+}
+
 template <class Tp>
 inline void upload(Session& s, const PoseAdapterBase<Tp>& adapter) {
   const Tp *bv, *xc, *nc, *xw, *nw;
@@ -67,10 +113,18 @@ inline void pose_from_result(const rpe_result& r, SO3<Tp>* R, Vec3<Tp>* t) {
   *t = Vec3<Tp>((Tp)r.t[0], (Tp)r.t[1], (Tp)r.t[2]);
 }
 
+inline int method_slots(int method) {
+  return (method == RPE_SHINJI_KNEIP || method == RPE_NL_SHINJI) ? 2 : (method == RPE_NL_SHINJI_KNEIP ? 3 : 1);
+}
+
 // The common body of every *_ransac / *_prosac template.
-template <class Tp, class Adapter>
-inline rpe_result run_ransac(Adapter& adapter, int method, const std::vector<int32_t>& table, Tp thr3d, Tp cos_thr2d,
-                             Tp cos_thrN, int& Iter, Tp confidence) {
+// Random stream: the reference draws inside its loop and stops drawing when the loop ends, i.e. after
+// max(Iter_final, i_winner + 1) iterations (all of them when nothing was accepted). Here whole passes are drawn ahead,
+// so the generator is snapshotted first and, once the result is known, rewound and advanced by exactly the rows the
+// reference would have drawn. (A custom RandSource without save/load keeps the extra draws.)
+template <class Tp, class Adapter, class Rows>
+inline rpe_result run_ransac(Adapter& adapter, int method, Rows& rows, RandSource* src, Tp thr3d, Tp cos_thr2d, Tp cos_thrN,
+                             int& Iter, Tp confidence) {
   Session& s = Session::local();
   upload<Tp>(s, adapter);
   const int n = adapter.getNumberCorrespondences();
@@ -78,9 +132,23 @@ inline rpe_result run_ransac(Adapter& adapter, int method, const std::vector<int
   std::vector<int16_t> mask((size_t)n * cols);
   rpe_result res;
   adapter.setMaxVotes(-1);
-  s.check(rpe_ransac(s.ctx(), method, table.data(), Iter, (float)thr3d, (float)cos_thr2d, (float)cos_thrN,
-                     (float)confidence, &res, mask.data()),
-          "rpe_ransac");
+  const int iter0 = Iter;
+  RandState snapshot;
+  const bool saved = rand_save(src, &snapshot);
+  s.check(rpe_ransac_stream(s.ctx(), method, &rows_callback<Rows>, &rows, Iter, (float)thr3d, (float)cos_thr2d,
+                            (float)cos_thrN, (float)confidence, &res, mask.data()),
+          "rpe_ransac_stream");
+  if (saved && rand_load(src, snapshot)) {
+    int executed = iter0;
+    if (res.winner >= 0) {
+      executed = res.winner / method_slots(method) + 1;
+      if (res.iter_final > executed) executed = res.iter_final;
+      if (executed > iter0) executed = iter0;
+    }
+    rows.restart();
+    int32_t scratch[4];
+    for (int i = 0; i < executed; ++i) rows.row(scratch);
+  }
   if (res.winner >= 0) {
     adapter.setMaxVotes(res.max_votes);
     SO3<Tp> R;

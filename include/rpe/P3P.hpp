@@ -58,18 +58,16 @@ bool kneip(const M& X_w_, const M& bv_, rpe::SE3<Tp>* p_sol_) {
 template <typename Tp>
 void kneip_ransac(PnPPoseAdapter<Tp>& adapter, const Tp thre_2d_, int& Iter, Tp confidence = 0.99) {
   const Tp cos_thr = std::cos(std::atan(thre_2d_ / adapter.getFocal()));  // [reference :323]
-  std::vector<int32_t> table;
-  rpe::detail::draw_ransac_table(adapter.getNumberCorrespondences(), 4, Iter, &table);
-  rpe::detail::run_ransac<Tp>(adapter, RPE_KNEIP, table, Tp(0), cos_thr, Tp(0), Iter, confidence);
+  rpe::detail::RansacRows rows(adapter.getNumberCorrespondences(), 4);
+  rpe::detail::run_ransac<Tp>(adapter, RPE_KNEIP, rows, nullptr, Tp(0), cos_thr, Tp(0), Iter, confidence);
   adapter.cvtInlier();  // [reference :389]
 }
 
 template <typename Tp>
 void kneip_prosac(PnPPoseAdapter<Tp>& adapter, const Tp thre_2d_, int& Iter, Tp confidence = 0.99) {
   const Tp cos_thr = std::cos(std::atan(thre_2d_ / adapter.getFocal()));  // [reference :398]
-  std::vector<int32_t> table;
-  rpe::detail::draw_prosac_table<Tp>(adapter, 4, Iter, &table);
-  rpe::detail::run_ransac<Tp>(adapter, RPE_KNEIP_QUAT, table, Tp(0), cos_thr, Tp(0), Iter, confidence);
+  rpe::detail::ProsacRows<Tp, PnPPoseAdapter<Tp> > rows(adapter, 4);
+  rpe::detail::run_ransac<Tp>(adapter, RPE_KNEIP_QUAT, rows, nullptr, Tp(0), cos_thr, Tp(0), Iter, confidence);
   adapter.cvtInlier();  // [reference :466]
 }
 

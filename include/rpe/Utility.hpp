@@ -21,6 +21,7 @@
 
 #include <stdint.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include <algorithm>
 #include <cmath>
@@ -29,14 +30,75 @@
 
 namespace rpe {
 
+// Snapshot of a generator. The GPU path draws sample rows ahead of the iterations the reference's early-stopping loop
+// would actually run; afterwards the generator is put back and advanced by exactly the draws of the iterations the
+// reference executes, so that whatever the program draws next (the next estimator, the Simulator) is unchanged.
+struct RandState {
+  uint32_t w[68];
+  int words;
+  void* where;
+  RandState() : words(0), where(nullptr) {}
+};
+
 struct RandSource {
   virtual ~RandSource() {}
   virtual int next() = 0;  // same contract as ::rand(): uniform in [0, 2^31)
+  virtual bool save(RandState*) { return false; }
+  virtual bool load(const RandState&) { return false; }
 };
 
+// libc's hidden rand()/random() state. glibc keeps it in a user-replaceable array (initstate/setstate, POSIX): switching
+// to a scratch array makes libc write the current rear index into the header word of the array it leaves, after which
+// header + ring can be copied; copying them back and switching to that array again rewinds the generator.
 struct LibcRandom : RandSource {
   int next() override { return ::rand(); }
+  static char* scratch() {
+    static char buf[128];
+    return buf;
+  }
+  bool save(RandState* st) override {
+#if defined(__GLIBC__)
+    char* prev = ::initstate(1u, scratch(), 128);
+    if (!prev) return false;
+    uint32_t header;
+    memcpy(&header, prev, sizeof(header));
+    static const int kDegree[5] = {0, 7, 15, 31, 63};
+    const int type = (int)(header % 5u);
+    st->words = kDegree[type] + 1;
+    st->where = prev;
+    memcpy(st->w, prev, (size_t)st->words * 4);
+    ::setstate(prev);
+    return true;
+#else
+    (void)st;
+    return false;
+#endif
+  }
+  bool load(const RandState& st) override {
+#if defined(__GLIBC__)
+    if (!st.where || st.words <= 0) return false;
+    char* cur = ::initstate(1u, scratch(), 128);  // leave the live array (libc rewrites its header, restored below)
+    if (cur != st.where) {                        // the program installed another state array meanwhile
+      if (cur) ::setstate(cur);
+      return false;
+    }
+    memcpy(st.where, st.w, (size_t)st.words * 4);
+    ::setstate((char*)st.where);
+    return true;
+#else
+    (void)st;
+    return false;
+#endif
+  }
 };
+inline bool rand_save(RandSource* src, RandState* st) {
+  LibcRandom libc;
+  return src ? src->save(st) : libc.save(st);
+}
+inline bool rand_load(RandSource* src, const RandState& st) {
+  LibcRandom libc;
+  return src ? src->load(st) : libc.load(st);
+}
 
 // glibc random_r TYPE_3: 31-word additive feedback, taps 3 and 31, 310 outputs discarded after seeding.
 class GlibcRandom : public RandSource {
@@ -63,6 +125,21 @@ class GlibcRandom : public RandSource {
     if (++front_ == kDeg) front_ = 0;
     if (++rear_ == kDeg) rear_ = 0;
     return out;
+  }
+  bool save(RandState* st) override {
+    for (int i = 0; i < kDeg; ++i) st->w[i] = ring_[i];
+    st->w[kDeg] = (uint32_t)front_;
+    st->w[kDeg + 1] = (uint32_t)rear_;
+    st->words = kDeg + 2;
+    st->where = this;
+    return true;
+  }
+  bool load(const RandState& st) override {
+    if (st.where != this || st.words != kDeg + 2) return false;
+    for (int i = 0; i < kDeg; ++i) ring_[i] = st.w[i];
+    front_ = (int)st.w[kDeg];
+    rear_ = (int)st.w[kDeg + 1];
+    return true;
   }
 
  private:

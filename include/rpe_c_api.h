@@ -141,6 +141,16 @@ int rpe_ransac(rpe_ctx* ctx, int method, const int32_t* samples, int H, float th
 int rpe_ransac_async(rpe_ctx* ctx, int method, const int32_t* samples, int H, float thr3d, float cos_thr2d,
                      float cos_thrN, float confidence, rpe_result* out_pinned, int16_t* mask_pinned);
 
+/* Same as rpe_ransac, with the sample rows produced on demand: `fn(user, first_iteration, count, rows)` must write
+ * rows [first_iteration, first_iteration + count) of the table (count x 4 int32) and return 0. It is called once per
+ * device pass (1024, 2048, 4096, 8192, ... iterations) in increasing order, so a caller whose Iter is 100 000 — the
+ * reference's SimpleMain.cpp:45 — only draws the rows of the passes that run before the adaptive bound stops the loop.
+ * The reference draws inside its loop (AbsoluteOrientation.hpp:124, Utility.hpp:139-152): the iterations it executes
+ * are max(iter_final, winner / slots + 1) (all H when winner < 0), see rpe/Estimators.hpp. Blocking. */
+typedef int (*rpe_sample_fn)(void* user, int first_iteration, int count, int32_t* rows);
+int rpe_ransac_stream(rpe_ctx* ctx, int method, rpe_sample_fn fn, void* user, int H, float thr3d, float cos_thr2d,
+                      float cos_thrN, float confidence, rpe_result* out, int16_t* mask);
+
 /* Refit / refinement starting from the pose and inlier mask of the last rpe_ransac on ctx.
  * weights: modality weights {w2d, w3d, wN} for RPE_REFIT_GN (NULL = {1,1,1}); per-correspondence
  * n x 3 column-major weights for RPE_REFIT_NL_SK_LS (NULL = the adapters' default 1).

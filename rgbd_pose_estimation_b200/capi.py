@@ -102,6 +102,9 @@ _sig("rpe_ransac", C.c_int, [_vp, C.c_int, _vp, C.c_int, C.c_float, C.c_float, C
                              C.POINTER(_Result), _vp])
 _sig("rpe_ransac_async", C.c_int, [_vp, C.c_int, _vp, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float,
                                    C.POINTER(_Result), _vp])
+SAMPLE_FN = C.CFUNCTYPE(C.c_int, _vp, C.c_int, C.c_int, C.POINTER(C.c_int32))
+_sig("rpe_ransac_stream", C.c_int, [_vp, C.c_int, SAMPLE_FN, _vp, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float,
+                                    C.POINTER(_Result), _vp])
 _sig("rpe_refit", C.c_int, [_vp, C.c_int, _vp, C.c_int, C.POINTER(_Result)])
 _sig("rpe_refit_async", C.c_int, [_vp, C.c_int, _vp, C.c_int, C.POINTER(_Result)])
 _sig("rpe_set_pose", C.c_int, [_vp, _vp, _vp, C.c_int])
@@ -137,7 +140,7 @@ _sig("rpe_debug_set_packed", C.c_int, [C.c_int])
 DECLARED_SYMBOLS = [
     "rpe_version", "rpe_status_string", "rpe_device_count", "rpe_create", "rpe_create_on_stream", "rpe_destroy",
     "rpe_last_error", "rpe_stream", "rpe_sync", "rpe_launch_count", "rpe_host_alloc", "rpe_host_free", "rpe_upload",
-    "rpe_upload_device", "rpe_num_correspondences", "rpe_ransac", "rpe_ransac_async", "rpe_refit", "rpe_refit_async",
+    "rpe_upload_device", "rpe_num_correspondences", "rpe_ransac", "rpe_ransac_async", "rpe_ransac_stream", "rpe_refit", "rpe_refit_async",
     "rpe_set_pose", "rpe_set_mask", "rpe_generate", "rpe_get_hypotheses", "rpe_set_hypotheses", "rpe_score",
     "rpe_get_votes", "rpe_set_votes", "rpe_votes_device_ptr", "rpe_finish", "rpe_update_num_iters", "rpe_sample_table",
     "rpe_prosac_table", "rpe_sim_pose", "rpe_sim_3d_3d", "rpe_sim_2d_3d", "rpe_sim_2d_3d_nl", "rpe_sim_3d_3d_device",
@@ -323,6 +326,27 @@ class Context:
         out = {k: (np.empty((self.n, 3), np.float32) if k in names else None) for k in order}
         _check(lib.rpe_download(self._h, *[_ptr(out[k]) for k in order]), self._h)
         return {k: v for k, v in out.items() if v is not None}
+
+    def ransac_stream(self, method, row_fn, H, thr3d=0.0, cos_thr2d=0.0, cos_thrN=0.0, confidence=0.99, want_mask=True):
+        """rpe_ransac_stream: `row_fn(first_iteration, count)` returns the (count, 4) int32 rows of one device pass."""
+        m = METHODS[method] if isinstance(method, str) else method
+        calls = []
+
+        def thunk(_user, first, count, out):
+            rows = np.ascontiguousarray(row_fn(first, count), dtype=np.int32).reshape(count, 4)
+            C.memmove(out, rows.ctypes.data, rows.nbytes)
+            calls.append((first, count))
+            return 0
+
+        cb = SAMPLE_FN(thunk)
+        res = _Result()
+        mask = np.empty((method_mask_cols(m), self.n), np.int16) if want_mask else None
+        _check(lib.rpe_ransac_stream(self._h, m, cb, None, H, thr3d, cos_thr2d, cos_thrN, confidence, C.byref(res),
+                                     _ptr(mask)), self._h)
+        d = res.to_dict()
+        d["mask"] = mask
+        d["passes"] = calls
+        return d
 
     def ransac_async(self, method, samples, H=None, thr3d=0.0, cos_thr2d=0.0, cos_thrN=0.0, confidence=0.99, mask=None):
         """Enqueue only. `samples` may be a numpy int32 array (kept alive until sync) or a device pointer (int)

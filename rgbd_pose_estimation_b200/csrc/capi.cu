@@ -81,6 +81,8 @@ struct rpe_ctx {
   ReplayOut* h_pose = nullptr;    // pinned, kNumStaging slots; [0] doubles as scratch for set_pose
   bool kabsch_valid = false;
   bool suff_valid = false;  // rb.suff matches the inlier columns in d_mask
+  int32_t* h_samples = nullptr;  // pinned staging for rpe_ransac_stream
+  int h_samples_cap = 0;
   Worklist wl = {nullptr, nullptr, 0};
   unsigned int wl_allocated = 0;  // entries allocated (wl.capacity may be lowered by the test hook)
   unsigned int wl_want = 0;       // grow to this many entries before the next scoring call (set after an overflow)
@@ -452,10 +454,11 @@ constexpr int kMaxPassIters = 8192;  // iterations generated + scored per device
 constexpr int kFirstPassIters = 1024;  // a longer Iter is scored progressively: 1024, 2048, 4096, 8192, 8192, ... iterations,
                                        // looking at the adaptive bound in between (the reference rarely gets past a few hundred)
 
-int do_ransac(rpe_ctx* ctx, int method, const int32_t* samples, int H, float thr3d, float cos_thr2d, float cos_thrN,
-              float confidence, rpe_result* out, int16_t* mask, bool blocking) {
+int do_ransac(rpe_ctx* ctx, int method, const int32_t* samples, rpe_sample_fn fn, void* fn_user, int H, float thr3d,
+              float cos_thr2d, float cos_thrN, float confidence, rpe_result* out, int16_t* mask, bool blocking) {
   if (!ctx) return RPE_ERR_ARG;
-  if (!method_ok(method) || !samples || H <= 0 || !out) return fail(ctx, RPE_ERR_ARG, "bad argument to rpe_ransac");
+  if (!method_ok(method) || (!samples && !fn) || H <= 0 || !out)
+    return fail(ctx, RPE_ERR_ARG, "bad argument to rpe_ransac");
   int rc = check_arrays(ctx, method);
   if (rc) return rc;
   CK(cudaSetDevice(ctx->device));
@@ -469,7 +472,14 @@ int do_ransac(rpe_ctx* ctx, int method, const int32_t* samples, int H, float thr
   // sample table: device pointers are used in place; host memory is copied on the stream (pageable memory is
   // staged by the driver before the call returns, page-locked memory must stay alive until rpe_sync)
   bool samples_on_device = false;
-  {
+  if (fn) {  // rows are produced pass by pass into a page-locked staging buffer
+    if (ctx->h_samples_cap < pass_cap) {
+      if (ctx->h_samples) cudaFreeHost(ctx->h_samples);
+      ctx->h_samples = nullptr;
+      CK(cudaMallocHost(&ctx->h_samples, (size_t)pass_cap * 4 * sizeof(int32_t)));
+      ctx->h_samples_cap = pass_cap;
+    }
+  } else {
     cudaPointerAttributes attr;
     const cudaError_t pe = cudaPointerGetAttributes(&attr, samples);
     if (pe != cudaSuccess) (void)cudaGetLastError();
@@ -489,7 +499,11 @@ int do_ransac(rpe_ctx* ctx, int method, const int32_t* samples, int H, float thr
   int pass = single ? H : kFirstPassIters;
   for (int base = 0; base < H; base += pass, pass = (2 * pass < kMaxPassIters ? 2 * pass : kMaxPassIters)) {
     const int hc = (H - base) < pass ? (H - base) : pass;
-    const int32_t* chunk = samples + (size_t)base * 4;
+    const int32_t* chunk = samples ? samples + (size_t)base * 4 : nullptr;
+    if (fn) {
+      if (fn(fn_user, base, hc, ctx->h_samples) != 0) return fail(ctx, RPE_ERR_ARG, "the sample callback failed");
+      chunk = ctx->h_samples;
+    }
     const int32_t* samples_dev = chunk;
     if (!samples_on_device) {
       CK(cudaMemcpyAsync(ctx->d_samples, chunk, (size_t)hc * 4 * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
@@ -662,6 +676,7 @@ int rpe_destroy(rpe_ctx* ctx) {
   cudaFree(ctx->d_weights3);
   cudaFree(ctx->d_gn_cost);
   cudaFree(ctx->d_gn_evals);
+  if (ctx->h_samples) cudaFreeHost(ctx->h_samples);
   if (ctx->h_gn_cost) cudaFreeHost(ctx->h_gn_cost);
   if (ctx->h_gn_evals) cudaFreeHost(ctx->h_gn_evals);
   for (int k = 0; k <= ST_COUNT; ++k)
@@ -745,11 +760,16 @@ int rpe_num_correspondences(const rpe_ctx* ctx) { return ctx ? ctx->n : 0; }
 
 int rpe_ransac(rpe_ctx* ctx, int method, const int32_t* samples, int H, float thr3d, float cos_thr2d, float cos_thrN,
                float confidence, rpe_result* out, int16_t* mask) {
-  return do_ransac(ctx, method, samples, H, thr3d, cos_thr2d, cos_thrN, confidence, out, mask, true);
+  return do_ransac(ctx, method, samples, nullptr, nullptr, H, thr3d, cos_thr2d, cos_thrN, confidence, out, mask, true);
 }
 int rpe_ransac_async(rpe_ctx* ctx, int method, const int32_t* samples, int H, float thr3d, float cos_thr2d,
                      float cos_thrN, float confidence, rpe_result* out, int16_t* mask) {
-  return do_ransac(ctx, method, samples, H, thr3d, cos_thr2d, cos_thrN, confidence, out, mask, false);
+  return do_ransac(ctx, method, samples, nullptr, nullptr, H, thr3d, cos_thr2d, cos_thrN, confidence, out, mask, false);
+}
+int rpe_ransac_stream(rpe_ctx* ctx, int method, rpe_sample_fn fn, void* user, int H, float thr3d, float cos_thr2d,
+                      float cos_thrN, float confidence, rpe_result* out, int16_t* mask) {
+  if (!fn) return RPE_ERR_ARG;
+  return do_ransac(ctx, method, nullptr, fn, user, H, thr3d, cos_thr2d, cos_thrN, confidence, out, mask, true);
 }
 
 static int do_refit(rpe_ctx* ctx, int kind, const float* weights, int max_iters, rpe_result* out, bool blocking) {

@@ -247,3 +247,31 @@ def test_async_queue_longer_than_the_staging_ring(rpe, orc, gpu_ctx):
         else:
             assert r.refit_ok == 1
     gpu_ctx._keep = []
+
+
+def test_ransac_stream_draws_rows_pass_by_pass(rpe, orc, gpu_ctx):
+    """rpe_ransac_stream asks for the rows of one pass at a time (1024, 2048, ...) and stops asking once the
+    replayed adaptive bound ends the loop; same result as the whole-table call."""
+    orc.set_math_mode(orc.DET)
+    n, H = 1500, 100000
+    q, t, Q, P = _frame(rpe, 61, n)
+    S = rpe.sample_table(5, n, 3, H)
+    gpu_ctx.upload(xc=P, xw=Q)
+    want = gpu_ctx.ransac(SHINJI, S, thr3d=0.25, confidence=0.9999)
+    got = gpu_ctx.ransac_stream(SHINJI, lambda first, count: S[first:first + count], H, thr3d=0.25, confidence=0.9999)
+    for k in ("winner", "max_votes", "iter_final", "n_slots"):
+        assert got[k] == want[k], k
+    assert np.array_equal(got["mask"], want["mask"])
+    assert got["passes"] == [(0, 1024)]  # the bound (a few hundred iterations) is reached inside the first pass
+    ref = orc.ransac(SHINJI, S, thr3d=0.25, confidence=0.9999, full=False, xc=P, xw=Q, want_arrays=False)
+    assert (got["winner"], got["iter_final"]) == (ref["winner"], ref["iter_final"])
+    # iterations the reference's loop executes, as the drop-in headers reconstruct them from the result
+    assert ref["iters_run"] == max(got["iter_final"], got["winner"] + 1)
+    # 92 % outliers: the bound stays in the thousands, several passes are requested in order
+    q, t, Q, P = _frame(rpe, 62, n, 0.92)
+    gpu_ctx.upload(xc=P, xw=Q)
+    got = gpu_ctx.ransac_stream(SHINJI, lambda first, count: S[first:first + count], H, thr3d=0.25, confidence=0.9999)
+    ref = orc.ransac(SHINJI, S, thr3d=0.25, confidence=0.9999, full=False, xc=P, xw=Q, want_arrays=False)
+    assert (got["winner"], got["max_votes"], got["iter_final"]) == (ref["winner"], ref["max_votes"], ref["iter_final"])
+    assert got["passes"][:3] == [(0, 1024), (1024, 2048), (3072, 4096)]
+    assert ref["iters_run"] == max(got["iter_final"], got["winner"] + 1)

@@ -66,3 +66,14 @@ def test_host_solvers_bit_exact_vs_oracle(orc, rpe, tmp_path):
         assert tag == "nl_2p" and [int(v) for v in vals] == pose_bits(qn, tn)
     orc.set_math_mode(orc.LIBM)
     assert n_kneip > cases // 2
+
+
+def test_random_source_snapshot_and_rewind(tmp_path):
+    """The drop-in headers draw whole passes of sample rows ahead and then put ::rand() back to where the reference's
+    early-stopping loop would have left it (include/rpe/Utility.hpp RandState)."""
+    exe = str(tmp_path / "test_rand_state")
+    subprocess.run(["g++", "-std=c++11", "-O2", "-I", os.path.join(ROOT, "include"), "-o", exe,
+                    os.path.join(ROOT, "tests", "cpp", "test_rand_state.cpp")], check=True)
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0 and "FAIL" not in out.stdout, out.stdout
+    assert out.stdout.count("ok ") >= 11
