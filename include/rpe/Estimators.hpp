@@ -103,15 +103,32 @@ template <class Tp>
 inline void upload(Session& s, const PoseAdapterBase<Tp>& adapter) {
   const Tp *bv, *xc, *nc, *xw, *nw;
   adapter.rpeArrays(&bv, &xc, &nc, &xw, &nw);
-  s.upload<Tp>(bv, xc, nc, xw, nw, adapter.getNumberCorrespondences());
+  s.upload(bv, xc, nc, xw, nw, adapter.getNumberCorrespondences());  // double: binary64 path, see Session::upload
 }
 
+// qd / td carry the accepted hypothesis in binary64 on the binary64 path and the widened float pose otherwise
 template <class Tp>
 inline void pose_from_result(const rpe_result& r, SO3<Tp>* R, Vec3<Tp>* t) {
-  const Tp q[4] = {(Tp)r.q[0], (Tp)r.q[1], (Tp)r.q[2], (Tp)r.q[3]};
+  const Tp q[4] = {(Tp)r.qd[0], (Tp)r.qd[1], (Tp)r.qd[2], (Tp)r.qd[3]};
   *R = SO3<Tp>::fromRawQuaternion(q);
-  *t = Vec3<Tp>((Tp)r.t[0], (Tp)r.t[1], (Tp)r.t[2]);
+  *t = Vec3<Tp>((Tp)r.td[0], (Tp)r.td[1], (Tp)r.td[2]);
 }
+
+// the RANSAC call itself: binary64 thresholds for Tp = double, the float entry point otherwise
+template <class Tp>
+struct RansacCall {
+  static int run(rpe_ctx* ctx, int method, rpe_sample_fn fn, void* user, int H, Tp thr3d, Tp cos2, Tp cosn, Tp conf,
+                 rpe_result* out, int16_t* mask) {
+    return rpe_ransac_stream(ctx, method, fn, user, H, (float)thr3d, (float)cos2, (float)cosn, (float)conf, out, mask);
+  }
+};
+template <>
+struct RansacCall<double> {
+  static int run(rpe_ctx* ctx, int method, rpe_sample_fn fn, void* user, int H, double thr3d, double cos2, double cosn,
+                 double conf, rpe_result* out, int16_t* mask) {
+    return rpe_ransac_f64(ctx, method, nullptr, fn, user, H, thr3d, cos2, cosn, conf, out, mask);
+  }
+};
 
 inline int method_slots(int method) {
   return (method == RPE_SHINJI_KNEIP || method == RPE_NL_SHINJI) ? 2 : (method == RPE_NL_SHINJI_KNEIP ? 3 : 1);
@@ -135,9 +152,9 @@ inline rpe_result run_ransac(Adapter& adapter, int method, Rows& rows, RandSourc
   const int iter0 = Iter;
   RandState snapshot;
   const bool saved = rand_save(src, &snapshot);
-  s.check(rpe_ransac_stream(s.ctx(), method, &rows_callback<Rows>, &rows, Iter, (float)thr3d, (float)cos_thr2d,
-                            (float)cos_thrN, (float)confidence, &res, mask.data()),
-          "rpe_ransac_stream");
+  s.check(RansacCall<Tp>::run(s.ctx(), method, &rows_callback<Rows>, &rows, Iter, thr3d, cos_thr2d, cos_thrN, confidence, &res,
+                              mask.data()),
+          "rpe_ransac");
   if (saved && rand_load(src, snapshot)) {
     int executed = iter0;
     if (res.winner >= 0) {

@@ -84,6 +84,58 @@ RPE_HD int update_num_iters(float p, float ep, const int model_points, const int
   return rule_finish(rule_log_numerator(p), rule_denominator(ep, model_points), max_iters);
 }
 
+// ---- Tp = double: RANSACUpdateNumIters<double> (every operation in binary64; `+ 0.5f` promotes to double) --------
+RPE_HD double rule_ddiv(double a, double b) {
+#if defined(__CUDA_ARCH__)
+  return __ddiv_rn(a, b);
+#else
+  return a / b;
+#endif
+}
+struct RuleDenominatorD {
+  int state;
+  double log_denom;
+};
+RPE_HD double rule_log_numerator_d(double p) {
+  const double deps = 2.220446049250313e-16;  // std::numeric_limits<double>::epsilon()
+  p = p > 0.0 ? p : 0.0;
+  p = p < 1.0 ? p : 1.0;
+  double num = det::dsub(1.0, p);
+  num = num > deps ? num : deps;
+  return det::log_d(num);
+}
+RPE_HD RuleDenominatorD rule_denominator_d(double ep, const int model_points) {
+  const double deps = 2.220446049250313e-16;
+  ep = ep > 0.0 ? ep : 0.0;
+  ep = ep < 1.0 ? ep : 1.0;
+  const double base = det::dsub(1.0, ep);
+  double pw = 1.0;
+  for (int i = 0; i < model_points; ++i) pw = det::dmul(pw, base);
+  const double denom = det::dsub(1.0, pw);
+  RuleDenominatorD r;
+  if (denom < deps) {
+    r.state = 0;
+    r.log_denom = 0.0;
+  } else {
+    r.state = 1;
+    r.log_denom = det::log_d(denom);
+  }
+  return r;
+}
+RPE_HD int rule_finish_d(double log_num, RuleDenominatorD d, const int max_iters) {
+  if (d.state == 0) return 0;
+  const double num = log_num, denom = d.log_denom;
+  if (denom >= 0.0 || -num >= det::dmul((double)max_iters, -denom)) return max_iters;
+  return (int)det::dadd(rule_ddiv(num, denom), 0.5);
+}
+RPE_HD int update_num_iters_d(double p, double ep, const int model_points, const int max_iters) {
+  return rule_finish_d(rule_log_numerator_d(p), rule_denominator_d(ep, model_points), max_iters);
+}
+RPE_HD double outlier_ratio_d(int modalities, int n, int votes) {
+  if (modalities == 1) return rule_ddiv((double)(n - votes), (double)n);
+  return rule_ddiv(rule_ddiv((double)(n * modalities - votes), (double)n), (double)modalities);
+}
+
 RPE_HD float outlier_ratio(int modalities, int n, int votes) {
   if (modalities == 1) return rule_fdiv((float)(n - votes), (float)n);
   return rule_fdiv(rule_fdiv((float)(n * modalities - votes), (float)n), (float)modalities);

@@ -54,7 +54,12 @@ class Session {
     if (rc != RPE_OK) throw Failure(rc, std::string(what) + ": " + rpe_status_string(rc) + " (" + rpe_last_error(ctx_) + ")");
   }
 
-  // Upload column-major 3 x n arrays of any scalar type (converted to the float the kernels compute in).
+  // Tp = double: the arrays go up in binary64 and the next RANSAC decides in binary64 (rpe_upload_f64).
+  void upload(const double* bv, const double* xc, const double* nc, const double* xw, const double* nw, int n) {
+    check(rpe_upload_f64(ctx_, bv, xc, nc, xw, nw, n), "rpe_upload_f64");
+    ++token_;
+  }
+  // Upload column-major 3 x n arrays of any other scalar type (converted to the float the kernels compute in).
   template <class Tp>
   void upload(const Tp* bv, const Tp* xc, const Tp* nc, const Tp* xw, const Tp* nw, int n) {
     const Tp* src[5] = {bv, xc, nc, xw, nw};

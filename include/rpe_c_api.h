@@ -71,6 +71,8 @@ extern "C" {
 #define RPE_REFIT_NL_SK_LS 3       /* nl_shinji_kneip_ls (3 weighted Kabsch + ray-intersection passes)     */
 
 typedef struct rpe_ctx rpe_ctx; /* opaque: one per (host thread, GPU, stream) */
+/* sample-row producer of rpe_ransac_stream / rpe_ransac_f64 (documented there) */
+typedef int (*rpe_sample_fn)(void* user, int first_iteration, int count, int32_t* rows);
 
 typedef struct rpe_result {
   float R[9];       /* R_cw, row-major (same convention Library.cpp:66-69 writes out) */
@@ -81,12 +83,14 @@ typedef struct rpe_result {
   int32_t winner;      /* iteration*slots + slot of the accepted hypothesis, -1 none  */
   int32_t n_slots;     /* hypothesis slots generated and scored (H * slots)           */
   int32_t n_borderline;/* evaluations resolved by the exact-order path                */
-  int32_t flags;       /* bit0: worklist overflow -> whole frame rescored exactly     */
+  int32_t flags;       /* bit0: worklist overflow -> whole frame rescored exactly; bit1: binary64 path */
   int32_t n_inliers[3];/* per modality column (2-D, 3-D, normal) of the winner        */
   int32_t refit_ok;    /* 1 if the last rpe_refit produced a valid rotation           */
   double  refit_cost;  /* GN: final weighted sum of squared residuals                  */
   int32_t refit_evals; /* GN: cost/Jacobian evaluations executed                      */
   int32_t reserved;
+  double  qd[4];       /* binary64 path (rpe_upload_f64): the accepted hypothesis exactly as the double CPU path */
+  double  td[3];       /* holds it; q/t/R above are its float roundings. Zero on the float path.              */
 } rpe_result;
 
 /* ---- library / device ---------------------------------------------------------------- */
@@ -118,6 +122,18 @@ int rpe_host_free(void* ptr);
 int rpe_upload(rpe_ctx* ctx, const float* bv, const float* xc, const float* nc, const float* xw, const float* nw, int n);
 int rpe_upload_device(rpe_ctx* ctx, const float* bv, const float* xc, const float* nc, const float* xw, const float* nw,
                       int n);
+/* Tp = double adapters (the reference's TestMain.cpp runs its estimators as <double>): host arrays in binary64. The
+ * next rpe_ransac on this context generates, scores, replays and masks in binary64 in the reference's operation order
+ * (no binary32 fast path), so winner / votes / Iter / masks equal the double CPU path's; the accepted hypothesis comes
+ * back in rpe_result.qd / td. Refits run on float copies of the arrays with binary64 accumulation. */
+int rpe_upload_f64(rpe_ctx* ctx, const double* bv, const double* xc, const double* nc, const double* xw, const double* nw,
+                   int n);
+/* rpe_ransac / rpe_ransac_stream with binary64 thresholds, for a context in binary64 mode. Exactly one of `samples`
+ * (whole table) and `fn` (rows on demand) is non-NULL. Blocking. */
+int rpe_ransac_f64(rpe_ctx* ctx, int method, const int32_t* samples, rpe_sample_fn fn, void* user, int H, double thr3d,
+                   double cos_thr2d, double cos_thrN, double confidence, rpe_result* out, int16_t* mask);
+/* binary64 path: the hypotheses of the last pass, (q.x q.y q.z q.w t.x t.y t.z) per slot + valid flags */
+int rpe_get_hypotheses_f64(rpe_ctx* ctx, int n_slots, double* hyps7, int32_t* valid);
 int rpe_num_correspondences(const rpe_ctx* ctx);
 
 /* ---- robust estimation ------------------------------------------------------------------
@@ -147,7 +163,6 @@ int rpe_ransac_async(rpe_ctx* ctx, int method, const int32_t* samples, int H, fl
  * reference's SimpleMain.cpp:45 — only draws the rows of the passes that run before the adaptive bound stops the loop.
  * The reference draws inside its loop (AbsoluteOrientation.hpp:124, Utility.hpp:139-152): the iterations it executes
  * are max(iter_final, winner / slots + 1) (all H when winner < 0), see rpe/Estimators.hpp. Blocking. */
-typedef int (*rpe_sample_fn)(void* user, int first_iteration, int count, int32_t* rows);
 int rpe_ransac_stream(rpe_ctx* ctx, int method, rpe_sample_fn fn, void* user, int H, float thr3d, float cos_thr2d,
                       float cos_thrN, float confidence, rpe_result* out, int16_t* mask);
 

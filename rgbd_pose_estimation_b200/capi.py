@@ -47,6 +47,7 @@ class _Result(C.Structure):
         ("max_votes", C.c_int32), ("iter_final", C.c_int32), ("winner", C.c_int32), ("n_slots", C.c_int32),
         ("n_borderline", C.c_int32), ("flags", C.c_int32), ("n_inliers", C.c_int32 * 3), ("refit_ok", C.c_int32),
         ("refit_cost", C.c_double), ("refit_evals", C.c_int32), ("reserved", C.c_int32),
+        ("qd", C.c_double * 4), ("td", C.c_double * 3),
     ]
 
     def to_dict(self):
@@ -57,6 +58,7 @@ class _Result(C.Structure):
             "n_borderline": int(self.n_borderline), "flags": int(self.flags),
             "n_inliers": [int(v) for v in self.n_inliers], "refit_ok": int(self.refit_ok),
             "refit_cost": float(self.refit_cost), "refit_evals": int(self.refit_evals),
+            "qd": np.array(self.qd, dtype=np.float64), "td": np.array(self.td, dtype=np.float64),
         }
 
 
@@ -105,6 +107,10 @@ _sig("rpe_ransac_async", C.c_int, [_vp, C.c_int, _vp, C.c_int, C.c_float, C.c_fl
 SAMPLE_FN = C.CFUNCTYPE(C.c_int, _vp, C.c_int, C.c_int, C.POINTER(C.c_int32))
 _sig("rpe_ransac_stream", C.c_int, [_vp, C.c_int, SAMPLE_FN, _vp, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float,
                                     C.POINTER(_Result), _vp])
+_sig("rpe_upload_f64", C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, C.c_int])
+_sig("rpe_ransac_f64", C.c_int, [_vp, C.c_int, _vp, SAMPLE_FN, _vp, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double,
+                                 C.POINTER(_Result), _vp])
+_sig("rpe_get_hypotheses_f64", C.c_int, [_vp, C.c_int, _vp, _vp])
 _sig("rpe_refit", C.c_int, [_vp, C.c_int, _vp, C.c_int, C.POINTER(_Result)])
 _sig("rpe_refit_async", C.c_int, [_vp, C.c_int, _vp, C.c_int, C.POINTER(_Result)])
 _sig("rpe_set_pose", C.c_int, [_vp, _vp, _vp, C.c_int])
@@ -140,7 +146,7 @@ _sig("rpe_debug_set_packed", C.c_int, [C.c_int])
 DECLARED_SYMBOLS = [
     "rpe_version", "rpe_status_string", "rpe_device_count", "rpe_create", "rpe_create_on_stream", "rpe_destroy",
     "rpe_last_error", "rpe_stream", "rpe_sync", "rpe_launch_count", "rpe_host_alloc", "rpe_host_free", "rpe_upload",
-    "rpe_upload_device", "rpe_num_correspondences", "rpe_ransac", "rpe_ransac_async", "rpe_ransac_stream", "rpe_refit", "rpe_refit_async",
+    "rpe_upload_device", "rpe_num_correspondences", "rpe_ransac", "rpe_ransac_async", "rpe_ransac_stream", "rpe_upload_f64", "rpe_ransac_f64", "rpe_get_hypotheses_f64", "rpe_refit", "rpe_refit_async",
     "rpe_set_pose", "rpe_set_mask", "rpe_generate", "rpe_get_hypotheses", "rpe_set_hypotheses", "rpe_score",
     "rpe_get_votes", "rpe_set_votes", "rpe_votes_device_ptr", "rpe_finish", "rpe_update_num_iters", "rpe_sample_table",
     "rpe_prosac_table", "rpe_sim_pose", "rpe_sim_3d_3d", "rpe_sim_2d_3d", "rpe_sim_2d_3d_nl", "rpe_sim_3d_3d_device",
@@ -326,6 +332,31 @@ class Context:
         out = {k: (np.empty((self.n, 3), np.float32) if k in names else None) for k in order}
         _check(lib.rpe_download(self._h, *[_ptr(out[k]) for k in order]), self._h)
         return {k: v for k, v in out.items() if v is not None}
+
+    def upload_f64(self, bv=None, xc=None, nc=None, xw=None, nw=None):
+        """Binary64 arrays (n, 3): the next ransac_f64 decides everything in binary64 like a Tp = double adapter."""
+        arrs = [None if a is None else np.ascontiguousarray(a, dtype=np.float64) for a in (bv, xc, nc, xw, nw)]
+        n = next(a.shape[0] for a in arrs if a is not None)
+        self.n = n
+        self._arrays = arrs
+        _check(lib.rpe_upload_f64(self._h, *[_ptr(a) for a in arrs], n), self._h)
+
+    def ransac_f64(self, method, samples, thr3d=0.0, cos_thr2d=0.0, cos_thrN=0.0, confidence=0.99, want_mask=True):
+        m = METHODS[method] if isinstance(method, str) else method
+        samples = np.ascontiguousarray(samples, dtype=np.int32)
+        res = _Result()
+        mask = np.empty((method_mask_cols(m), self.n), np.int16) if want_mask else None
+        _check(lib.rpe_ransac_f64(self._h, m, _ptr(samples), C.cast(None, SAMPLE_FN), None, samples.shape[0], thr3d, cos_thr2d,
+                                  cos_thrN, confidence, C.byref(res), _ptr(mask)), self._h)
+        d = res.to_dict()
+        d["mask"] = mask
+        return d
+
+    def get_hypotheses_f64(self, n_slots):
+        hyps = np.empty((n_slots, 7), np.float64)
+        valid = np.empty(n_slots, np.int32)
+        _check(lib.rpe_get_hypotheses_f64(self._h, n_slots, _ptr(hyps), _ptr(valid)), self._h)
+        return hyps, valid
 
     def ransac_stream(self, method, row_fn, H, thr3d=0.0, cos_thr2d=0.0, cos_thrN=0.0, confidence=0.99, want_mask=True):
         """rpe_ransac_stream: `row_fn(first_iteration, count)` returns the (count, 4) int32 rows of one device pass."""

@@ -81,6 +81,17 @@ struct rpe_ctx {
   ReplayOut* h_pose = nullptr;    // pinned, kNumStaging slots; [0] doubles as scratch for set_pose
   bool kabsch_valid = false;
   bool suff_valid = false;  // rb.suff matches the inlier columns in d_mask
+  // binary64 path (rpe_upload_f64)
+  bool f64 = false;
+  double* d_raw64[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  const double* view64[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  size_t cap_n64 = 0;
+  HypGen64* d_gen64 = nullptr;
+  int cap_slots64 = 0;
+  ReplayState64* d_rs64 = nullptr;
+  ReplayState64* h_rs64 = nullptr;  // pinned
+  Pose64* d_pose64 = nullptr;
+  Pose64* h_pose64 = nullptr;       // pinned, kNumStaging slots
   int32_t* h_samples = nullptr;  // pinned staging for rpe_ransac_stream
   int h_samples_cap = 0;
   Worklist wl = {nullptr, nullptr, 0};
@@ -279,6 +290,13 @@ void fill_result(const rpe_ctx* ctx, rpe_result* out, int slot, bool is_refit, b
   out->flags = p.flags;
   for (int k = 0; k < 3; ++k) out->n_inliers[k] = p.n_inliers[k];
   out->refit_ok = is_refit ? p.refit_ok : 0;
+  if (!is_refit && (p.flags & 2)) {  // binary64 path: the accepted hypothesis as the double CPU path holds it
+    for (int k = 0; k < 4; ++k) out->qd[k] = ctx->h_pose64[slot].q[k];
+    for (int k = 0; k < 3; ++k) out->td[k] = ctx->h_pose64[slot].t[k];
+  } else {
+    for (int k = 0; k < 4; ++k) out->qd[k] = (double)p.q[k];
+    for (int k = 0; k < 3; ++k) out->td[k] = (double)p.t[k];
+  }
   if (gn) {
     out->refit_cost = ctx->h_gn_cost[slot];
     out->refit_evals = ctx->h_gn_evals[slot];
@@ -454,11 +472,114 @@ constexpr int kMaxPassIters = 8192;  // iterations generated + scored per device
 constexpr int kFirstPassIters = 1024;  // a longer Iter is scored progressively: 1024, 2048, 4096, 8192, 8192, ... iterations,
                                        // looking at the adaptive bound in between (the reference rarely gets past a few hundred)
 
+// ---- binary64 path ---------------------------------------------------------------------------------------
+FrameView64 make_view64(const rpe_ctx* c) {
+  FrameView64 f;
+  f.bv = c->view64[A_BV];
+  f.xc = c->view64[A_XC];
+  f.nc = c->view64[A_NC];
+  f.xw = c->view64[A_XW];
+  f.nw = c->view64[A_NW];
+  f.n = c->n;
+  return f;
+}
+
+int do_ransac64(rpe_ctx* ctx, int method, const int32_t* samples, rpe_sample_fn fn, void* fn_user, int H, double thr3d,
+                double cos_thr2d, double cos_thrN, double confidence, rpe_result* out, int16_t* mask) {
+  if (!method_ok(method) || (!samples && !fn) || H <= 0 || !out)
+    return fail(ctx, RPE_ERR_ARG, "bad argument to rpe_ransac");
+  int rc = check_arrays(ctx, method);
+  if (rc) return rc;
+  CK(cudaSetDevice(ctx->device));
+  const int S = method_slots(method);
+  const Thresh64 th = {thr3d, cos_thr2d, cos_thrN};
+  const int pass_cap = H < kMaxPassIters ? H : kMaxPassIters;
+  rc = ensure_hyp_capacity(ctx, pass_cap, pass_cap * S);
+  if (rc) return rc;
+  if (pass_cap * S > ctx->cap_slots64) {
+    if (ctx->d_gen64) cudaFree(ctx->d_gen64);
+    ctx->d_gen64 = nullptr;
+    const int cap = pass_cap * S + 256;
+    CK(cudaMalloc(&ctx->d_gen64, (size_t)cap * sizeof(HypGen64)));
+    ctx->cap_slots64 = cap;
+  }
+  bool samples_on_device = false;
+  if (fn) {
+    if (ctx->h_samples_cap < pass_cap) {
+      if (ctx->h_samples) cudaFreeHost(ctx->h_samples);
+      ctx->h_samples = nullptr;
+      CK(cudaMallocHost(&ctx->h_samples, (size_t)pass_cap * 4 * sizeof(int32_t)));
+      ctx->h_samples_cap = pass_cap;
+    }
+  } else {
+    cudaPointerAttributes attr;
+    const cudaError_t pe = cudaPointerGetAttributes(&attr, samples);
+    if (pe != cudaSuccess) (void)cudaGetLastError();
+    samples_on_device = pe == cudaSuccess && (attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged);
+  }
+  const FrameView64 f = make_view64(ctx);
+  launch_replay64_begin(ctx->d_rs64, H, ctx->stream);
+  ctx->launches++;
+  const bool single = H <= kFirstPassIters;
+  int pass = single ? H : kFirstPassIters;
+  for (int base = 0; base < H; base += pass, pass = (2 * pass < kMaxPassIters ? 2 * pass : kMaxPassIters)) {
+    const int hc = (H - base) < pass ? (H - base) : pass;
+    const int32_t* chunk = samples ? samples + (size_t)base * 4 : nullptr;
+    if (fn) {
+      if (fn(fn_user, base, hc, ctx->h_samples) != 0) return fail(ctx, RPE_ERR_ARG, "the sample callback failed");
+      chunk = ctx->h_samples;
+    }
+    const int32_t* samples_dev = chunk;
+    if (!samples_on_device) {
+      CK(cudaMemcpyAsync(ctx->d_samples, chunk, (size_t)hc * 4 * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+      samples_dev = ctx->d_samples;
+    }
+    launch_hypgen64(method, f, samples_dev, hc, ctx->d_gen64, ctx->d_votes, ctx->stream);
+    launch_score64(method, f, ctx->d_gen64, hc * S, th, ctx->d_votes, ctx->num_sms, ctx->stream);
+    launch_replay64(method, ctx->d_gen64, ctx->d_votes, hc, base, ctx->n, confidence, ctx->d_rs64, ctx->d_pose,
+                    ctx->d_pose64, single, ctx->stream);
+    ctx->launches += 3;
+    ctx->n_slots = hc * S;
+    ctx->cur_method = method;
+    if (!single) {
+      CK(cudaMemcpyAsync(ctx->h_rs64, ctx->d_rs64, sizeof(ReplayState64), cudaMemcpyDeviceToHost, ctx->stream));
+      CK(cudaStreamSynchronize(ctx->stream));
+      if (ctx->h_rs64->stop != 0 || base + hc >= H) {
+        launch_replay64(method, ctx->d_gen64, ctx->d_votes, 0, base + hc, ctx->n, confidence, ctx->d_rs64, ctx->d_pose,
+                        ctx->d_pose64, true, ctx->stream);
+        ctx->launches++;
+        break;
+      }
+    }
+  }
+  ctx->mask_cols = method_mask_cols(method);
+  launch_mask64(method, f, ctx->d_pose, ctx->d_pose64, th, ctx->d_mask, ctx->num_sms, ctx->stream);
+  ctx->launches++;
+  ctx->kabsch_valid = false;  // refits gather their statistics from the float copies when asked
+  ctx->suff_valid = false;
+  ctx->stats_clean = false;
+  int slot = 0;
+  rc = claim_slot(ctx, &slot);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(&ctx->h_pose[slot], ctx->d_pose, sizeof(ReplayOut), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(&ctx->h_pose64[slot], ctx->d_pose64, sizeof(Pose64), cudaMemcpyDeviceToHost, ctx->stream));
+  if (mask)
+    CK(cudaMemcpyAsync(mask, ctx->d_mask, (size_t)ctx->n * ctx->mask_cols * sizeof(int16_t), cudaMemcpyDeviceToHost,
+                       ctx->stream));
+  if (int rcp = push_pending(ctx, out, slot, false, false)) return rcp;
+  CK(cudaStreamSynchronize(ctx->stream));
+  finish_pending(ctx);
+  return RPE_OK;
+}
+
 int do_ransac(rpe_ctx* ctx, int method, const int32_t* samples, rpe_sample_fn fn, void* fn_user, int H, float thr3d,
               float cos_thr2d, float cos_thrN, float confidence, rpe_result* out, int16_t* mask, bool blocking) {
   if (!ctx) return RPE_ERR_ARG;
   if (!method_ok(method) || (!samples && !fn) || H <= 0 || !out)
     return fail(ctx, RPE_ERR_ARG, "bad argument to rpe_ransac");
+  if (ctx->f64)  // arrays uploaded in binary64: thresholds given as float are widened (use rpe_ransac_f64 for exact ones)
+    return do_ransac64(ctx, method, samples, fn, fn_user, H, (double)thr3d, (double)cos_thr2d, (double)cos_thrN,
+                       (double)confidence, out, mask);
   int rc = check_arrays(ctx, method);
   if (rc) return rc;
   CK(cudaSetDevice(ctx->device));
@@ -609,6 +730,10 @@ static int create_common(int device, void* stream, bool own, rpe_ctx** out) {
   ok = ok && cudaMalloc(&ctx->rb.moments, kMomentCount * sizeof(double)) == cudaSuccess;
   ok = ok && cudaMalloc(&ctx->rb.suff, kMomentCount * sizeof(double)) == cudaSuccess;
   ok = ok && cudaMalloc(&ctx->d_gn, sizeof(GnState)) == cudaSuccess;
+  ok = ok && cudaMalloc(&ctx->d_rs64, sizeof(ReplayState64)) == cudaSuccess;
+  ok = ok && cudaMallocHost(&ctx->h_rs64, sizeof(ReplayState64)) == cudaSuccess;
+  ok = ok && cudaMalloc(&ctx->d_pose64, sizeof(Pose64)) == cudaSuccess;
+  ok = ok && cudaMallocHost(&ctx->h_pose64, kNumStaging * sizeof(Pose64)) == cudaSuccess;
   ok = ok && cudaMalloc(&ctx->d_nlsk, sizeof(NlskState)) == cudaSuccess;
   ok = ok && cudaMalloc(&ctx->d_gn_cost, sizeof(double)) == cudaSuccess;
   ok = ok && cudaMalloc(&ctx->d_gn_evals, sizeof(int32_t)) == cudaSuccess;
@@ -677,6 +802,13 @@ int rpe_destroy(rpe_ctx* ctx) {
   cudaFree(ctx->d_gn_cost);
   cudaFree(ctx->d_gn_evals);
   if (ctx->h_samples) cudaFreeHost(ctx->h_samples);
+  for (int k = 0; k < 5; ++k)
+    if (ctx->d_raw64[k]) cudaFree(ctx->d_raw64[k]);
+  if (ctx->d_gen64) cudaFree(ctx->d_gen64);
+  if (ctx->d_rs64) cudaFree(ctx->d_rs64);
+  if (ctx->h_rs64) cudaFreeHost(ctx->h_rs64);
+  if (ctx->d_pose64) cudaFree(ctx->d_pose64);
+  if (ctx->h_pose64) cudaFreeHost(ctx->h_pose64);
   if (ctx->h_gn_cost) cudaFreeHost(ctx->h_gn_cost);
   if (ctx->h_gn_evals) cudaFreeHost(ctx->h_gn_evals);
   for (int k = 0; k <= ST_COUNT; ++k)
@@ -740,6 +872,7 @@ static int upload_common(rpe_ctx* ctx, const float* const src[5], int n, bool fr
   ctx->kabsch_valid = false;
   ctx->suff_valid = false;
   ctx->n_slots = 0;
+  ctx->f64 = false;
   return RPE_OK;
 }
 
@@ -770,6 +903,62 @@ int rpe_ransac_stream(rpe_ctx* ctx, int method, rpe_sample_fn fn, void* user, in
                       float cos_thrN, float confidence, rpe_result* out, int16_t* mask) {
   if (!fn) return RPE_ERR_ARG;
   return do_ransac(ctx, method, nullptr, fn, user, H, thr3d, cos_thr2d, cos_thrN, confidence, out, mask, true);
+}
+int rpe_ransac_f64(rpe_ctx* ctx, int method, const int32_t* samples, rpe_sample_fn fn, void* user, int H, double thr3d,
+                   double cos_thr2d, double cos_thrN, double confidence, rpe_result* out, int16_t* mask) {
+  if (!ctx) return RPE_ERR_ARG;
+  if (!ctx->f64) return fail(ctx, RPE_ERR_STATE, "rpe_ransac_f64 needs arrays uploaded with rpe_upload_f64");
+  return do_ransac64(ctx, method, samples, fn, user, H, thr3d, cos_thr2d, cos_thrN, confidence, out, mask);
+}
+int rpe_upload_f64(rpe_ctx* ctx, const double* bv, const double* xc, const double* nc, const double* xw, const double* nw,
+                   int n) {
+  if (!ctx || n <= 0 || !xw) return RPE_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  int rc = ensure_corr_capacity(ctx, n, true);
+  if (rc) return rc;
+  if ((size_t)n > ctx->cap_n64) {
+    for (int k = 0; k < 5; ++k) {
+      if (ctx->d_raw64[k]) cudaFree(ctx->d_raw64[k]);
+      ctx->d_raw64[k] = nullptr;
+    }
+    const size_t cap = (size_t)n + (size_t)n / 8 + 64;
+    for (int k = 0; k < 5; ++k) CK(cudaMalloc(&ctx->d_raw64[k], cap * 3 * sizeof(double)));
+    ctx->cap_n64 = cap;
+  }
+  const double* src[5] = {bv, xc, nc, xw, nw};
+  ctx->n = n;
+  for (int k = 0; k < 5; ++k) {
+    if (!src[k]) {
+      ctx->view[k] = nullptr;
+      ctx->view64[k] = nullptr;
+      continue;
+    }
+    CK(cudaMemcpyAsync(ctx->d_raw64[k], src[k], (size_t)n * 3 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    launch_f64_to_f32(ctx->d_raw64[k], ctx->d_raw[k], (size_t)n * 3, ctx->stream);
+    ctx->launches++;
+    ctx->view64[k] = ctx->d_raw64[k];
+    ctx->view[k] = ctx->d_raw[k];
+  }
+  ctx->pk_kind = -1;
+  ctx->kabsch_valid = false;
+  ctx->suff_valid = false;
+  ctx->n_slots = 0;
+  ctx->f64 = true;
+  return RPE_OK;
+}
+int rpe_get_hypotheses_f64(rpe_ctx* ctx, int n_slots, double* hyps7, int32_t* valid) {
+  if (!ctx || !hyps7 || n_slots <= 0) return RPE_ERR_ARG;
+  if (!ctx->f64 || n_slots > ctx->n_slots) return fail(ctx, RPE_ERR_STATE, "no binary64 hypotheses of that many slots");
+  CK(cudaSetDevice(ctx->device));
+  std::vector<HypGen64> h((size_t)n_slots);
+  CK(cudaMemcpyAsync(h.data(), ctx->d_gen64, (size_t)n_slots * sizeof(HypGen64), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  for (int i = 0; i < n_slots; ++i) {
+    for (int k = 0; k < 4; ++k) hyps7[7 * (size_t)i + k] = h[i].q[k];
+    for (int k = 0; k < 3; ++k) hyps7[7 * (size_t)i + 4 + k] = h[i].t[k];
+    if (valid) valid[i] = h[i].valid;
+  }
+  return RPE_OK;
 }
 
 static int do_refit(rpe_ctx* ctx, int kind, const float* weights, int max_iters, rpe_result* out, bool blocking) {
@@ -894,6 +1083,7 @@ int rpe_set_mask(rpe_ctx* ctx, const int16_t* mask, int cols) {
 
 // ---- stage access ----------------------------------------------------------------------------------
 int rpe_generate(rpe_ctx* ctx, int method, const int32_t* samples, int H) {
+  if (ctx && ctx->f64) return fail(ctx, RPE_ERR_STATE, "the stage API is binary32 only (arrays were uploaded with rpe_upload_f64)");
   if (!ctx) return RPE_ERR_ARG;
   if (!method_ok(method) || !samples || H <= 0) return fail(ctx, RPE_ERR_ARG, "bad argument to rpe_generate");
   int rc = check_arrays(ctx, method);
@@ -914,6 +1104,7 @@ int rpe_generate(rpe_ctx* ctx, int method, const int32_t* samples, int H) {
 }
 
 int rpe_get_hypotheses(rpe_ctx* ctx, float* hyps, int32_t* valid, int n_slots) {
+  if (ctx && ctx->f64) return fail(ctx, RPE_ERR_STATE, "the stage API is binary32 only (arrays were uploaded with rpe_upload_f64)");
   if (!ctx || n_slots <= 0 || n_slots > ctx->n_slots) return ctx ? fail(ctx, RPE_ERR_ARG, "bad slot count") : RPE_ERR_ARG;
   CK(cudaSetDevice(ctx->device));
   std::vector<HypGen> h(n_slots);
@@ -953,6 +1144,7 @@ int rpe_set_hypotheses(rpe_ctx* ctx, int method, const float* hyps, const int32_
 }
 
 int rpe_score(rpe_ctx* ctx, int method, int slot_begin, int slot_end, float thr3d, float cos_thr2d, float cos_thrN) {
+  if (ctx && ctx->f64) return fail(ctx, RPE_ERR_STATE, "the stage API is binary32 only (arrays were uploaded with rpe_upload_f64)");
   if (!ctx) return RPE_ERR_ARG;
   if (!method_ok(method) || slot_begin < 0 || slot_end > ctx->n_slots || slot_begin > slot_end)
     return fail(ctx, RPE_ERR_ARG, "bad slot range");

@@ -112,6 +112,44 @@ void launch_gn_iteration(const FrameView& f, const int16_t* mask, int mask_cols,
 void launch_gn_from_stats(RefitBuffers rb, int blocks_used, float w3d, float wnl, int max_iters, ReplayOut* pose_io,
                           GnState* gs, double* cost_out, int32_t* evals_out, cudaStream_t s);
 
+// -- binary64 RANSAC path (f64.cu) ------------------------------------------------------------------
+struct FrameView64 {
+  const double* bv;
+  const double* xc;
+  const double* nc;
+  const double* xw;
+  const double* nw;
+  int n;
+};
+struct Thresh64 {
+  double thr3d, cos_thr, cos_nl;
+};
+struct HypGen64 {
+  double q[4];
+  double t[3];
+  int32_t valid;
+  int32_t pad;
+};
+struct Pose64 {
+  double q[4];
+  double t[3];
+};
+struct ReplayState64 {
+  int32_t best, iter, win, cur_iter, stop, slots_done;
+  double q[4];
+  double t[3];
+};
+void launch_f64_to_f32(const double* src, float* dst, size_t count, cudaStream_t s);
+void launch_hypgen64(int method, const FrameView64& f, const int32_t* samples_dev, int H, HypGen64* gen, int32_t* votes,
+                     cudaStream_t s);
+void launch_score64(int method, const FrameView64& f, const HypGen64* gen, int n_slots, Thresh64 th, int32_t* votes,
+                    int num_sms, cudaStream_t s);
+void launch_replay64_begin(ReplayState64* rs, int iter_max, cudaStream_t s);
+void launch_replay64(int method, const HypGen64* gen, const int32_t* votes, int H, int iter_base, int n, double confidence,
+                     ReplayState64* rs, ReplayOut* out, Pose64* out64, bool finalize, cudaStream_t s);
+void launch_mask64(int method, const FrameView64& f, ReplayOut* pose_rw, const Pose64* pose64, Thresh64 th, int16_t* mask,
+                   int num_sms, cudaStream_t s);
+
 // nl_shinji_kneip_ls (AbsoluteOrientationNormal.hpp:447-552) as one pose-independent reduction pass plus three
 // passes for the only sum that depends on the running camera centre (M23); the 3x3 SVDs, find_opt_cc's
 // ray-intersection solve and the blending run in the last CTA of each pass, in binary64.

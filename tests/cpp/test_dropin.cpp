@@ -80,5 +80,32 @@ int main(int argc, char** argv) {
     nl_shinji_kneip_ls<data_type>(adapter);
     report("nl_shinji_kneip_ls_dw", adapter, updated_iter, (int)adapter.getInlierIdx().size());
   }
+  // ---- Tp = double (TestMain.cpp instantiates its estimators as <double>): binary64 arrays read from a file written
+  // by the Python test (five 3 x n blocks: bv, xc, nc, xw, nw), decided in binary64 on the device
+  if (argc > 3) {
+    FILE* fp = fopen(argv[3], "rb");
+    if (!fp) return 2;
+    rpe::MatrixX<double> Ud(3, total), Pd(3, total), Nd(3, total), Qd(3, total), Md(3, total);
+    rpe::MatrixX<double>* arrs[5] = {&Ud, &Pd, &Nd, &Qd, &Md};
+    for (int a = 0; a < 5; ++a)
+      if (fread(arrs[a]->data(), sizeof(double), (size_t)3 * total, fp) != (size_t)3 * total) return 3;
+    fclose(fp);
+    NormalAOPoseAdapter<double> adapter(Ud, Pd, Nd, Qd, Md);
+    adapter.setFocal(585., 585.);
+    int updated_iter = 300;
+    nl_shinji_kneip_ransac<double>(adapter, 0.2, 8., 0.1, updated_iter, 0.99);
+    const rpe::Quaternion<double> q = adapter.getRcw().unit_quaternion();
+    const rpe::Vec3<double> t = adapter.gettw();
+    printf("{\"case\": \"nl_shinji_kneip_ransac_f64\", \"max_votes\": %d, \"iter\": %d, \"n_inliers\": %d, \"q\": [%.17g, %.17g, %.17g, %.17g], \"t\": [%.17g, %.17g, %.17g]}\n",
+           adapter.getMaxVotes(), updated_iter, (int)adapter.getInlierIdx().size(), q.x(), q.y(), q.z(), q.w(), t[0], t[1], t[2]);
+    PnPPoseAdapter<double> pnp(Ud, Qd);
+    pnp.setFocal(585., 585.);
+    updated_iter = 500;
+    kneip_ransac<double>(pnp, 8., updated_iter, 0.99);
+    const rpe::Quaternion<double> q2 = pnp.getRcw().unit_quaternion();
+    const rpe::Vec3<double> t2 = pnp.gettw();
+    printf("{\"case\": \"kneip_ransac_f64\", \"max_votes\": %d, \"iter\": %d, \"n_inliers\": %d, \"q\": [%.17g, %.17g, %.17g, %.17g], \"t\": [%.17g, %.17g, %.17g]}\n",
+           pnp.getMaxVotes(), updated_iter, (int)pnp.getInlierIdx().size(), q2.x(), q2.y(), q2.z(), q2.w(), t2[0], t2[1], t2[2]);
+  }
   return 0;
 }

@@ -39,8 +39,28 @@ def dropin_output(tmp_path_factory, rpe):
     subprocess.run(["g++", "-std=c++11", "-O2", "-I", os.path.join(ROOT, "include"), "-o", exe,
                     os.path.join(ROOT, "tests", "cpp", "test_dropin.cpp"), "-L", libdir, "-lrpe_b200",
                     "-Wl,-rpath," + libdir], check=True)
-    out = subprocess.run([exe, "1000", "100000"], capture_output=True, text=True, check=True).stdout
+    f64_file = os.path.join(str(d), "arrays_f64.bin")
+    with open(f64_file, "wb") as fh:
+        for a in _arrays_f64(rpe, 1000):
+            fh.write(np.ascontiguousarray(a, np.float64).tobytes())
+    out = subprocess.run([exe, "1000", "100000", f64_file], capture_output=True, text=True, check=True).stdout
     return {j["case"]: j for j in (json.loads(l) for l in out.splitlines() if l.startswith("{"))}
+
+
+def _arrays_f64(rpe, total):
+    """bv, xc, nc, xw, nw in binary64 for the Tp = double section of the drop-in program: the simulator's frame widened,
+    perturbed below float resolution and with directions renormalised in binary64."""
+    q, t = rpe.sim_pose(11)
+    d = rpe.sim_2d_3d_nl(15, q, t, total, n2d=1.0, or2d=0.3, n3d=0.05, or3d=0.3, nnl=float(np.float32(2.0 * np.pi / 180.)),
+                         ornl=0.3)
+    rng = np.random.default_rng(15)
+    out = []
+    for k in ("bv", "xc", "nc", "xw", "nw"):
+        a = d[k].astype(np.float64) * (1.0 + 1e-9 * rng.standard_normal(d[k].shape))
+        if k in ("bv", "nc", "nw"):
+            a = a / np.linalg.norm(a, axis=1, keepdims=True)
+        out.append(np.ascontiguousarray(a))
+    return out
 
 
 def test_cpp_dropin_matches_oracle(dropin_output, rpe, orc):
@@ -99,6 +119,26 @@ def test_cpp_dropin_matches_oracle(dropin_output, rpe, orc):
     got2 = res["nl_shinji_kneip_ls_dw"]
     assert _angle(got2["q"], q2) < 2e-6 and np.abs(np.array(got2["t"]) - t2).max() < 2e-5
     assert _angle(got2["q"], q) < 5e-3  # and it is a good pose
+    # ---- Tp = double adapters: decided in binary64 on the device, compared with the oracle instantiated for double;
+    # the sample stream continues where the float estimators left ::rand()
+    bv, xc, nc, xw, nw = _arrays_f64(rpe, total)
+    _libm.cos.restype = _libm.atan.restype = ctypes.c_double
+    _libm.cos.argtypes = _libm.atan.argtypes = [ctypes.c_double]
+    cos_thr64 = _libm.cos(_libm.atan(8.0 / 585.0))
+    cos_nl64 = _libm.cos(0.1)
+    S = orc.sample_table_skip(1, skip, total, 4, 300)
+    ref = orc.ransac(5, S, thr3d=0.2, cos_thr=cos_thr64, cos_nl=cos_nl64, confidence=0.99, full=False, want_arrays=False,
+                     dt=np.float64, bv=bv, xc=xc, nc=nc, xw=xw, nw=nw)
+    skip += ref["iters_run"] * 4
+    got = res["nl_shinji_kneip_ransac_f64"]
+    assert (got["max_votes"], got["iter"]) == (ref["max_votes"], ref["iter_final"])
+    assert np.array_equal(np.float64(got["q"]).view(np.uint64), ref["q"].view(np.uint64))
+    assert np.array_equal(np.float64(got["t"]).view(np.uint64), ref["t"].view(np.uint64))
+    S = orc.sample_table_skip(1, skip, total, 4, 500)
+    ref = orc.ransac(1, S, cos_thr=cos_thr64, confidence=0.99, full=False, want_arrays=False, dt=np.float64, bv=bv, xw=xw)
+    got = res["kneip_ransac_f64"]
+    assert (got["max_votes"], got["iter"], got["n_inliers"]) == (ref["max_votes"], ref["iter_final"], int(ref["mask"][0].sum()))
+    assert np.array_equal(np.float64(got["q"]).view(np.uint64), ref["q"].view(np.uint64))
     orc.set_math_mode(orc.LIBM)
 
 
