@@ -56,3 +56,40 @@ def test_partial_range_scoring_single_gpu(rpe, orc, gpu_ctx):
     out = gpu_ctx.finish("shinji", H, thr3d=0.25, confidence=0.9999)
     assert (out["winner"], out["iter_final"]) == (ref["winner"], ref["iter_final"])
     assert np.array_equal(out["mask"], ref["mask"])
+
+
+def test_contexts_sharing_the_scorer_lane_do_not_interfere(rpe, orc):
+    """Several contexts (streams) of one device run frames asynchronously; their tiled scorers are serialised through the
+    per-device scorer lane while everything else overlaps. Every result equals the one a lone blocking context gives."""
+    n, H, NCTX, FRAMES = 30000, 512, 4, 5
+    frames = []
+    for i in range(NCTX * FRAMES):
+        q, t = rpe.sim_pose(900 + i)
+        Q, P, _ = rpe.sim_3d_3d(1900 + i, q, t, n, noise=0.1, outlier_ratio=0.5)
+        frames.append((Q, P, rpe.sample_table(2900 + i, n, 3, H)))
+    with rpe.Context(0) as solo:
+        want = []
+        for Q, P, S in frames:
+            solo.upload(xc=P, xw=Q)
+            r = solo.ransac("shinji", S, thr3d=0.25, confidence=0.9999, want_mask=False)
+            k = solo.refit("kabsch_inliers")
+            g = solo.refit("gn", max_iters=3)
+            want.append((r, k, g))
+    ctxs = [rpe.Context(0) for _ in range(NCTX)]
+    try:
+        got = []
+        for i, (Q, P, S) in enumerate(frames):
+            c = ctxs[i % NCTX]
+            c.upload(xc=P, xw=Q)  # pageable host arrays: the copies are staged before the call returns
+            got.append((c.ransac_async("shinji", S, thr3d=0.25, confidence=0.9999), c.refit_async("kabsch_inliers"),
+                        c.refit_async("gn", max_iters=3)))
+        for c in ctxs:
+            c.sync()
+        for (r, k, g), (wr, wk, wg) in zip(got, want):
+            assert (r.winner, r.max_votes, r.iter_final) == (wr["winner"], wr["max_votes"], wr["iter_final"])
+            assert np.array_equal(np.array(k.q, np.float32).view(np.uint32), wk["q"].view(np.uint32))
+            assert np.array_equal(np.array(g.q, np.float32).view(np.uint32), wg["q"].view(np.uint32))
+            assert np.array_equal(np.array(g.t, np.float32).view(np.uint32), wg["t"].view(np.uint32))
+    finally:
+        for c in ctxs:
+            c.close()
