@@ -488,7 +488,8 @@ def run_single_frame_sharded(args, torch, dist, rpe, ctx, stream, frames, tables
         xw = torch.from_numpy(f0["xw"]).to(dev)
         xc = torch.from_numpy(f0["xc"]).to(dev)
         ctx.upload_device(N_CORR, xc=xc.data_ptr(), xw=xw.data_ptr())
-        ctx.generate(METHOD_SHINJI, tab)
+        tab_dev = torch.from_numpy(tab).to(dev)
+        ctx.generate(METHOD_SHINJI, tab_dev.data_ptr(), H=N_HYP)
         votes = torch.as_tensor(_DevArray(ctx.votes_device_ptr(), N_HYP), device=dev)
         times = []
         res = None
@@ -498,7 +499,7 @@ def run_single_frame_sharded(args, torch, dist, rpe, ctx, stream, frames, tables
             e0 = torch.cuda.Event(enable_timing=True)
             e1 = torch.cuda.Event(enable_timing=True)
             e0.record(stream)
-            ctx.generate(METHOD_SHINJI, tab)  # resets the vote table; generation is replicated (cheap)
+            ctx.generate(METHOD_SHINJI, tab_dev.data_ptr(), H=N_HYP)  # resets the votes; generation is replicated (cheap)
             ctx.score(METHOD_SHINJI, sb, se, thr3d=THR3D)
             dist.all_gather_into_tensor(votes, votes[sb:se].clone())
             res = ctx.finish(METHOD_SHINJI, N_HYP, thr3d=THR3D, confidence=CONF, want_mask=False)

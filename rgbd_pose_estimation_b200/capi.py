@@ -427,8 +427,12 @@ class Context:
         mask = np.ascontiguousarray(mask, dtype=np.int16)
         _check(lib.rpe_set_mask(self._h, _ptr(mask), mask.shape[0]), self._h)
 
-    def generate(self, method, samples):
+    def generate(self, method, samples, H=None):
+        """`samples`: (H, 4) int32 array, or a device pointer (int) with H given."""
         m = METHODS[method] if isinstance(method, str) else method
+        if isinstance(samples, int):
+            _check(lib.rpe_generate(self._h, m, C.c_void_p(samples), H), self._h)
+            return H * method_slots(m)
         samples = np.ascontiguousarray(samples, dtype=np.int32)
         _check(lib.rpe_generate(self._h, m, _ptr(samples), samples.shape[0]), self._h)
         return samples.shape[0] * method_slots(m)

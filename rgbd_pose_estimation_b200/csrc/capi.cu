@@ -1092,7 +1092,8 @@ int rpe_generate(rpe_ctx* ctx, int method, const int32_t* samples, int H) {
   const int S = method_slots(method);
   rc = ensure_hyp_capacity(ctx, H, H * S);
   if (rc) return rc;
-  CK(cudaMemcpyAsync(ctx->d_samples, samples, (size_t)H * 4 * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+  // host (pageable or page-locked) or device memory: the unified address space tells them apart
+  CK(cudaMemcpyAsync(ctx->d_samples, samples, (size_t)H * 4 * sizeof(int32_t), cudaMemcpyDefault, ctx->stream));
   launch_reset_stats(ctx->d_stats, ctx->stream);
   FrameView f = make_view(ctx);
   launch_hypgen(method, f, ctx->d_samples, H, ctx->d_gen, ctx->d_fast, ctx->d_votes, ctx->d_stats, ctx->stream);
