@@ -205,6 +205,30 @@ def workload_config(args, world):
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
+def bind_near_gpu(torch, local_rank):
+    """Pin this rank's host threads (and with them the first-touch placement of its page-locked buffers) to the CPUs
+    of the GPU's NUMA node, so that the e2e leg's H2D/D2H copies do not cross the socket interconnect."""
+    try:
+        p = torch.cuda.get_device_properties(local_rank)
+        bdf = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bdf}/local_cpulist") as fh:
+            spec = fh.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return {"pci": bdf, "cpus": len(cpus)}
+    except Exception as e:  # no sysfs entry / no permission: leave the affinity alone
+        return {"skipped": repr(e)[:80]}
+    return {"skipped": "no local cpus"}
+
+
 def run_gpu(args, rank, world, local_rank):
     import torch
     import rgbd_pose_estimation_b200 as rpe
@@ -212,6 +236,7 @@ def run_gpu(args, rank, world, local_rank):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product has no CPU fallback (use --impl reference for the CPU path)")
     torch.cuda.set_device(local_rank)
+    binding = bind_near_gpu(torch, local_rank) if world > 1 else {"skipped": "single GPU"}
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -448,7 +473,7 @@ def run_gpu(args, rank, world, local_rank):
             "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "frames_per_s": frames_total / (ms_e2e * 1e-3), "ms_per_step": ms_e2e / args.steps,
                     "single_frame_latency_ms": {"median": float(np.median(lat)), "min": float(min(lat))},
-                    "host_issue_ms_per_frame": issue_e2e,
+                    "host_issue_ms_per_frame": issue_e2e, "numa_binding_rank0": binding,
                     "clocks": clocks_e2e,
                     "path": "rpe_upload(host pinned) + rpe_ransac_async + rpe_refit_async x2 + mask/pose D2H, "
                             f"{args.contexts} contexts round-robin"},
