@@ -473,6 +473,7 @@ constexpr int kFirstPassIters = 1024;  // a longer Iter is scored progressively:
                                        // looking at the adaptive bound in between (the reference rarely gets past a few hundred)
 
 // ---- binary64 path ---------------------------------------------------------------------------------------
+bool g_f64_exact_only = false;  // test hook: score every evaluation in binary64 (no binary32 prefilter)
 FrameView64 make_view64(const rpe_ctx* c) {
   FrameView64 f;
   f.bv = c->view64[A_BV];
@@ -518,6 +519,14 @@ int do_ransac64(rpe_ctx* ctx, int method, const int32_t* samples, rpe_sample_fn 
     samples_on_device = pe == cudaSuccess && (attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged);
   }
   const FrameView64 f = make_view64(ctx);
+  if (!ctx->stats_clean) {
+    launch_reset_stats(ctx->d_stats, ctx->stream);
+    ctx->launches++;
+  }
+  if (!g_f64_exact_only) {
+    rc = ensure_packed(ctx, kind_for_method(method));  // pair records from the float copies
+    if (rc) return rc;
+  }
   launch_replay64_begin(ctx->d_rs64, H, ctx->stream);
   ctx->launches++;
   const bool single = H <= kFirstPassIters;
@@ -535,18 +544,45 @@ int do_ransac64(rpe_ctx* ctx, int method, const int32_t* samples, rpe_sample_fn 
       samples_dev = ctx->d_samples;
     }
     launch_hypgen64(method, f, samples_dev, hc, ctx->d_gen64, ctx->d_votes, ctx->stream);
-    launch_score64(method, f, ctx->d_gen64, hc * S, th, ctx->d_votes, ctx->num_sms, ctx->stream);
-    launch_replay64(method, ctx->d_gen64, ctx->d_votes, hc, base, ctx->n, confidence, ctx->d_rs64, ctx->d_pose,
+    ctx->launches++;
+    if (g_f64_exact_only) {
+      launch_score64(method, f, ctx->d_gen64, hc * S, th, ctx->d_votes, ctx->num_sms, nullptr, ctx->stream);
+      ctx->launches++;
+    } else {
+      // binary32 prefilter on the float copies + binary64 evaluation of what falls inside the guard bands
+      const FrameView f32 = make_view(ctx);
+      const Thresh thf = {(float)thr3d, (float)cos_thr2d, (float)cos_thrN};
+      launch_derive_fast64(ctx->d_gen64, ctx->d_gen, ctx->d_fast, hc * S, ctx->stream);
+      if (int rcw = grow_worklist(ctx)) return rcw;
+      int nseg = 0;
+      ScorerLane* lane = lane_for(ctx);
+      if (lane) {
+        CK(cudaEventRecord(ctx->ev_lane[0], ctx->stream));
+        std::lock_guard<std::mutex> g(lane->mu);
+        CK(cudaStreamWaitEvent(lane->stream, ctx->ev_lane[0], 0));
+        nseg = launch_score_fast(method, f32, ctx->d_gen, ctx->d_fast, 0, hc * S, thf, ctx->d_votes, ctx->d_stats, ctx->wl,
+                                 ctx->num_sms, lane->stream);
+        CK(cudaEventRecord(ctx->ev_lane[1], lane->stream));
+        CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_lane[1], 0));
+      } else {
+        nseg = launch_score_fast(method, f32, ctx->d_gen, ctx->d_fast, 0, hc * S, thf, ctx->d_votes, ctx->d_stats, ctx->wl,
+                                 ctx->num_sms, ctx->stream);
+      }
+      launch_fixup64(method, f, ctx->d_gen64, th, ctx->d_votes, ctx->d_stats, ctx->wl, nseg, ctx->stream);
+      launch_score64(method, f, ctx->d_gen64, hc * S, th, ctx->d_votes, ctx->num_sms, ctx->d_stats, ctx->stream);
+      ctx->launches += 5;
+    }
+    launch_replay64(method, ctx->d_gen64, ctx->d_votes, hc, base, ctx->n, confidence, ctx->d_stats, ctx->d_rs64, ctx->d_pose,
                     ctx->d_pose64, single, ctx->stream);
-    ctx->launches += 3;
+    ctx->launches++;
     ctx->n_slots = hc * S;
     ctx->cur_method = method;
     if (!single) {
       CK(cudaMemcpyAsync(ctx->h_rs64, ctx->d_rs64, sizeof(ReplayState64), cudaMemcpyDeviceToHost, ctx->stream));
       CK(cudaStreamSynchronize(ctx->stream));
       if (ctx->h_rs64->stop != 0 || base + hc >= H) {
-        launch_replay64(method, ctx->d_gen64, ctx->d_votes, 0, base + hc, ctx->n, confidence, ctx->d_rs64, ctx->d_pose,
-                        ctx->d_pose64, true, ctx->stream);
+        launch_replay64(method, ctx->d_gen64, ctx->d_votes, 0, base + hc, ctx->n, confidence, ctx->d_stats, ctx->d_rs64,
+                        ctx->d_pose, ctx->d_pose64, true, ctx->stream);
         ctx->launches++;
         break;
       }
@@ -557,7 +593,7 @@ int do_ransac64(rpe_ctx* ctx, int method, const int32_t* samples, rpe_sample_fn 
   ctx->launches++;
   ctx->kabsch_valid = false;  // refits gather their statistics from the float copies when asked
   ctx->suff_valid = false;
-  ctx->stats_clean = false;
+  ctx->stats_clean = true;  // replay64 leaves the per-pass counters clean
   int slot = 0;
   rc = claim_slot(ctx, &slot);
   if (rc) return rc;
@@ -1389,6 +1425,10 @@ int rpe_debug_set_worklist_capacity(rpe_ctx* ctx, unsigned int cap) {
   if (!ctx) return RPE_ERR_ARG;
   ctx->wl.capacity = cap < ctx->wl_allocated ? cap : ctx->wl_allocated;
   ctx->wl_fixed = cap < ctx->wl_allocated;
+  return RPE_OK;
+}
+int rpe_debug_f64_exact_only(int v) {
+  g_f64_exact_only = v != 0;
   return RPE_OK;
 }
 int rpe_debug_force_exact_multi(int v) {

@@ -4,7 +4,9 @@
 // A double adapter must see the inlier masks of that double CPU path, which a binary32 scorer cannot guarantee, so the
 // whole decision chain is evaluated in binary64 here, in the reference's operation order:
 //   generation   the same solver templates as the float path (include/rpe/solvers*.h) instantiated for double
-//   scoring      quaternion sandwich / matrix form, unfused, IEEE sqrt and division (no fast path, no guard band)
+//   scoring      binary32 tiled prefilter (the float path's kernels on float copies of the arrays, same guard bands —
+//                they budget the extra input roundings) + binary64 exact-order evaluation of every
+//                borderline evaluation: quaternion sandwich / matrix form, unfused, IEEE sqrt and division
 //   replay       strict `votes > max`, Iter = RANSACUpdateNumIters<double>(..) (include/rpe/ransac_rule.h)
 //   mask         the winner's flags, same exact tests
 // Refits keep using the float copies of the arrays with binary64 accumulation (pose tolerance 1e-6).
@@ -180,11 +182,90 @@ void launch_hypgen64(int method, const FrameView64& f, const int32_t* samples_de
 }
 
 // ================================================================================================
+// operands of the binary32 prefilter, derived from the binary64 hypotheses
+// ================================================================================================
+__global__ void derive_fast64_kernel(const HypGen64* __restrict__ g64, HypGen* __restrict__ gen, HypFast* __restrict__ fast,
+                                     int n_slots) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_slots) return;
+  const HypGen64 g = g64[i];
+  HypGen gf;
+  for (int k = 0; k < 4; ++k) gf.q[k] = (float)g.q[k];
+  for (int k = 0; k < 3; ++k) gf.t[k] = (float)g.t[k];
+  gf.valid = g.valid;
+  gen[i] = gf;
+  const double x = g.q[0], y = g.q[1], z = g.q[2], w = g.q[3];
+  const double tx = 2.0 * x, ty = 2.0 * y, tz = 2.0 * z;
+  const double twx = tx * w, twy = ty * w, twz = tz * w;
+  const double txx = tx * x, txy = ty * x, txz = tz * x;
+  const double tyy = ty * y, tyz = tz * y, tzz = tz * z;
+  HypFast f;
+  f.nR[0] = -(float)(1.0 - (tyy + tzz));
+  f.nR[1] = -(float)(txy - twz);
+  f.nR[2] = -(float)(txz + twy);
+  f.nR[3] = -(float)(txy + twz);
+  f.nR[4] = -(float)(1.0 - (txx + tzz));
+  f.nR[5] = -(float)(tyz - twx);
+  f.nR[6] = -(float)(txz - twy);
+  f.nR[7] = -(float)(tyz + twx);
+  f.nR[8] = -(float)(1.0 - (txx + tyy));
+  for (int k = 0; k < 3; ++k) f.nt[k] = -(float)g.t[k];
+  fast[i] = f;
+}
+void launch_derive_fast64(const HypGen64* g64, HypGen* gen, HypFast* fast, int n_slots, cudaStream_t s) {
+  if (n_slots <= 0) return;
+  derive_fast64_kernel<<<(n_slots + 127) / 128, 128, 0, s>>>(g64, gen, fast, n_slots);
+}
+
+// binary64 re-evaluation of the prefilter's borderline evaluations (twin of fixup_kernel in score.cu)
+__global__ void __launch_bounds__(256)
+fixup64_kernel(int method, FrameView64 f, const HypGen64* __restrict__ gen, Thresh64 th, int32_t* __restrict__ votes,
+               const FrameStats* __restrict__ st, Worklist wl, int nseg) {
+  if (st->wl_overflow) return;  // the whole frame is rescored in binary64 instead
+  const unsigned int cap = wl.capacity / (unsigned int)nseg;
+  const unsigned int count = min(wl.counts[blockIdx.x], cap);
+  const uint2* seg = wl.entries + (size_t)blockIdx.x * cap;
+  for (unsigned int i = blockIdx.y * blockDim.x + threadIdx.x; i < count; i += gridDim.y * blockDim.x) {
+    const uint2 e = seg[i];
+    const int slot = (int)e.x;
+    const int modality = (int)(e.y >> 30);
+    const int c = (int)(e.y & 0x3fffffffu);
+    double q[4], t[3];
+    for (int k = 0; k < 4; ++k) q[k] = gen[slot].q[k];
+    for (int k = 0; k < 3; ++k) t[k] = gen[slot].t[k];
+    bool in = false;
+    if (modality == 1) {
+      const D3 xc = load_col64(f.xc, c);
+      in = dx_is_valid(xc) && dx_test_3d(q, t, load_col64(f.xw, c), xc, th.thr3d);
+    } else if (modality == 2) {
+      in = dx_is_valid(load_col64(f.xc, c)) && dx_test_nl(q, load_col64(f.nw, c), load_col64(f.nc, c), th.cos_nl);
+    } else {
+      double Rm[9];
+      if (method == RPE_KNEIP) dx_quat_to_matrix(q, Rm);
+      in = dx_test_2d(q, t, method == RPE_KNEIP ? Rm : nullptr, load_col64(f.xw, c), load_col64(f.bv, c), th.cos_thr);
+    }
+    if (in) atomicAdd(&votes[slot], 1);
+  }
+}
+void launch_fixup64(int method, const FrameView64& f, const HypGen64* gen, Thresh64 th, int32_t* votes, FrameStats* st,
+                    Worklist wl, int nseg, cudaStream_t s) {
+  if (nseg <= 0) return;
+  fixup64_kernel<<<dim3(nseg, 4), 256, 0, s>>>(method, f, gen, th, votes, st, wl, nseg);
+}
+__global__ void zero_votes64_kernel(const HypGen64* __restrict__ gen, int n_slots, int32_t* __restrict__ votes,
+                                    const FrameStats* __restrict__ st) {
+  if (!st->wl_overflow) return;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_slots; i += gridDim.x * blockDim.x)
+    votes[i] = gen[i].valid ? 0 : -1;
+}
+
+// ================================================================================================
 // scoring: thread <-> slot, CTA column <-> correspondence slice (every lane reads the same correspondence)
 // ================================================================================================
 __global__ void __launch_bounds__(128)
 score64_kernel(int method, FrameView64 f, const HypGen64* __restrict__ gen, int n_slots, Thresh64 th,
-               int32_t* __restrict__ votes, int corr_per_cta) {
+               int32_t* __restrict__ votes, int corr_per_cta, const FrameStats* __restrict__ st /*null: unconditional*/) {
+  if (st && !st->wl_overflow) return;
   const int slot = blockIdx.y * blockDim.x + threadIdx.x;
   const bool live = slot < n_slots && gen[slot].valid != 0;
   double q[4], t[3];
@@ -211,9 +292,11 @@ score64_kernel(int method, FrameView64 f, const HypGen64* __restrict__ gen, int 
   }
   if (live && cnt) atomicAdd(&votes[slot], cnt);
 }
+// only_if_overflow != null: the fallback after a prefilter whose worklist overflowed (votes are reset first)
 void launch_score64(int method, const FrameView64& f, const HypGen64* gen, int n_slots, Thresh64 th, int32_t* votes,
-                    int num_sms, cudaStream_t s) {
+                    int num_sms, const FrameStats* only_if_overflow, cudaStream_t s) {
   if (n_slots <= 0 || f.n <= 0) return;
+  if (only_if_overflow) zero_votes64_kernel<<<4, 256, 0, s>>>(gen, n_slots, votes, only_if_overflow);
   const int threads = 128;
   const int gy = (n_slots + threads - 1) / threads;
   int gx = (8 * num_sms) / gy;
@@ -221,7 +304,7 @@ void launch_score64(int method, const FrameView64& f, const HypGen64* gen, int n
   if (gx > f.n) gx = f.n;
   const int corr_per_cta = (f.n + gx - 1) / gx;
   gx = (f.n + corr_per_cta - 1) / corr_per_cta;
-  score64_kernel<<<dim3(gx, gy), threads, 0, s>>>(method, f, gen, n_slots, th, votes, corr_per_cta);
+  score64_kernel<<<dim3(gx, gy), threads, 0, s>>>(method, f, gen, n_slots, th, votes, corr_per_cta, only_if_overflow);
 }
 
 // ================================================================================================
@@ -235,6 +318,8 @@ __global__ void replay64_begin_kernel(ReplayState64* rs, int iter_max) {
   rs->cur_iter = -1;
   rs->stop = 0;
   rs->slots_done = 0;
+  rs->borderline = 0;
+  rs->overflow = 0;
   for (int k = 0; k < 4; ++k) rs->q[k] = k == 3 ? 1.0 : 0.0;
   for (int k = 0; k < 3; ++k) rs->t[k] = 0.0;
 }
@@ -243,8 +328,8 @@ void launch_replay64_begin(ReplayState64* rs, int iter_max, cudaStream_t s) { re
 constexpr int kReplay64Chunk = 4096;
 __global__ void __launch_bounds__(256)
 replay64_kernel(int method, const HypGen64* __restrict__ gen, const int32_t* __restrict__ votes, int H, int iter_base, int n,
-                double confidence, ReplayState64* __restrict__ rs, ReplayOut* __restrict__ out, Pose64* __restrict__ out64,
-                int finalize) {
+                double confidence, FrameStats* __restrict__ st, ReplayState64* __restrict__ rs, ReplayOut* __restrict__ out,
+                Pose64* __restrict__ out64, int finalize) {
   __shared__ int32_t sv[kReplay64Chunk];
   __shared__ int s_state[5];  // best, Iter, win, cur_iter, stop
   const int lane = threadIdx.x & 31;
@@ -332,6 +417,14 @@ replay64_kernel(int method, const HypGen64* __restrict__ gen, const int32_t* __r
     rs->cur_iter = s_state[3];
     rs->stop = s_state[4] || ((long long)(slot_base + E) >= (long long)s_state[1] * S) ? 1 : 0;
     rs->slots_done += E;
+    rs->borderline += (int)st->wl_count;
+    rs->overflow |= st->wl_overflow ? 1 : 0;
+    st->t_max_bits = 0;  // per-pass counters are consumed (as in replay_kernel)
+    st->wl_count = 0;
+    st->wl_consumed = 0;
+    st->wl_overflow = 0;
+    st->ticket = 0;
+    st->ticket2 = 0;
     if (finalize) {
       ReplayOut o;
       for (int k = 0; k < 4; ++k) o.q[k] = (float)rs->q[k];
@@ -340,8 +433,8 @@ replay64_kernel(int method, const HypGen64* __restrict__ gen, const int32_t* __r
       o.iter_final = rs->iter;
       o.winner = rs->win;
       o.n_slots = rs->slots_done;
-      o.n_borderline = 0;
-      o.flags = 2;  // bit 1: binary64 path
+      o.n_borderline = rs->borderline;
+      o.flags = 2 | (rs->overflow ? 1 : 0);  // bit 1: binary64 path
       o.n_inliers[0] = o.n_inliers[1] = o.n_inliers[2] = 0;
       o.refit_ok = 0;
       *out = o;
@@ -353,8 +446,8 @@ replay64_kernel(int method, const HypGen64* __restrict__ gen, const int32_t* __r
   }
 }
 void launch_replay64(int method, const HypGen64* gen, const int32_t* votes, int H, int iter_base, int n, double confidence,
-                     ReplayState64* rs, ReplayOut* out, Pose64* out64, bool finalize, cudaStream_t s) {
-  replay64_kernel<<<1, 256, 0, s>>>(method, gen, votes, H, iter_base, n, confidence, rs, out, out64, finalize ? 1 : 0);
+                     FrameStats* st, ReplayState64* rs, ReplayOut* out, Pose64* out64, bool finalize, cudaStream_t s) {
+  replay64_kernel<<<1, 256, 0, s>>>(method, gen, votes, H, iter_base, n, confidence, st, rs, out, out64, finalize ? 1 : 0);
 }
 
 // ================================================================================================

@@ -135,7 +135,7 @@ struct Pose64 {
   double t[3];
 };
 struct ReplayState64 {
-  int32_t best, iter, win, cur_iter, stop, slots_done;
+  int32_t best, iter, win, cur_iter, stop, slots_done, borderline, overflow;
   double q[4];
   double t[3];
 };
@@ -143,10 +143,13 @@ void launch_f64_to_f32(const double* src, float* dst, size_t count, cudaStream_t
 void launch_hypgen64(int method, const FrameView64& f, const int32_t* samples_dev, int H, HypGen64* gen, int32_t* votes,
                      cudaStream_t s);
 void launch_score64(int method, const FrameView64& f, const HypGen64* gen, int n_slots, Thresh64 th, int32_t* votes,
-                    int num_sms, cudaStream_t s);
+                    int num_sms, const FrameStats* only_if_overflow, cudaStream_t s);
+void launch_derive_fast64(const HypGen64* g64, HypGen* gen, HypFast* fast, int n_slots, cudaStream_t s);
+void launch_fixup64(int method, const FrameView64& f, const HypGen64* gen, Thresh64 th, int32_t* votes, FrameStats* st,
+                    Worklist wl, int nseg, cudaStream_t s);
 void launch_replay64_begin(ReplayState64* rs, int iter_max, cudaStream_t s);
 void launch_replay64(int method, const HypGen64* gen, const int32_t* votes, int H, int iter_base, int n, double confidence,
-                     ReplayState64* rs, ReplayOut* out, Pose64* out64, bool finalize, cudaStream_t s);
+                     FrameStats* st, ReplayState64* rs, ReplayOut* out, Pose64* out64, bool finalize, cudaStream_t s);
 void launch_mask64(int method, const FrameView64& f, ReplayOut* pose_rw, const Pose64* pose64, Thresh64 th, int16_t* mask,
                    int num_sms, cudaStream_t s);
 
