@@ -121,4 +121,32 @@ void simulate_2d_3d_nl_correspondences(const rpe::SO3<T>& R_cw_, const rpe::Vec3
   if (p_all_weights_) *p_all_weights_ = w;
 }
 
+template <typename T>
+T lateral_noise_kinect(T theta_, T z_, T f_) {  // [reference :368-377]
+  return rpe::sim::kinect_lateral_sigma<T>(theta_, z_, f_);
+}
+template <typename T>
+T axial_noise_kinect(T theta_, T z_) {  // [reference :379-387]
+  return rpe::sim::kinect_axial_sigma<T>(theta_, z_);
+}
+
+template <typename T>
+void simulate_kinect_2d_3d_nl_correspondences(const rpe::SO3<T>& R_cw_, const rpe::Vec3<T>& t_w_, int number_, T noise_2d_,
+                                              T outlier_ratio_2d_, T outlier_ratio_3d_, T noise_nl_, T outlier_ratio_nl_,
+                                              T min_depth_, T max_depth_, T f_, rpe::MatrixX<T>* p_pt_w_,
+                                              rpe::MatrixX<T>* p_nl_w_, rpe::MatrixX<T>* p_pt_c_, rpe::MatrixX<T>* p_nl_c_,
+                                              rpe::MatrixX<T>* p_bv_, rpe::MatrixX<T>* p_weights_ = NULL) {  // [reference :389-436]
+  p_pt_w_->resize(3, number_);
+  p_nl_w_->resize(3, number_);
+  p_pt_c_->resize(3, number_);
+  p_nl_c_->resize(3, number_);
+  p_bv_->resize(3, number_);
+  rpe::MatrixX<T> w(number_, 3);
+  rpe::sim::simulate_kinect_2d_3d_nl<T>(rpe::sim::global_rng(), rpe::sim::make_pose(R_cw_, t_w_), number_, noise_2d_,
+                                        outlier_ratio_2d_, outlier_ratio_3d_, noise_nl_, outlier_ratio_nl_, min_depth_,
+                                        max_depth_, f_, p_pt_w_->data(), p_nl_w_->data(), p_pt_c_->data(), p_nl_c_->data(),
+                                        p_bv_->data(), w.data());
+  if (p_weights_) *p_weights_ = w;
+}
+
 #endif  // RPE_SIMULATOR_HPP_

@@ -337,6 +337,59 @@ inline void simulate_2d_3d_nl(Rng& rng, const Pose<T>& pose, int n, T n2d, T or2
     for (int r = 0; r < 3; ++r) P[3 * idx[i] + r] = outp[3 * i + r];
 }
 
+// Kinect depth-noise model of Nguyen, Izadi & Lovell (3DIMPVT 2012), the functions the reference keeps at
+// Simulator.hpp:368-386: lateral sigma in metres for a surface seen under angle theta at depth z with focal length f,
+// and axial sigma (quadratic in depth, with the grazing-angle term beyond 60 degrees).
+template <class T>
+inline T kinect_lateral_sigma(T theta, T z, T f) {
+  const T half_pi = T(3.14159265358979323846 / 2.);
+  const T px = T(.8) + T(.035) * theta / (half_pi - theta);  // pixels
+  return px * z / f;
+}
+template <class T>
+inline T kinect_axial_sigma(T theta, T z) {
+  const T half_pi = T(3.14159265358979323846 / 2.);
+  const T dz = z - T(0.4);
+  T s = T(.0012) + T(.0019) * dz * dz;
+  if (std::fabs(theta) > T(3.14159265358979323846 / 3.)) {
+    const T g = half_pi - theta;
+    s += T(.0001) * theta * theta / std::sqrt(z) / g / g;
+  }
+  return s;
+}
+
+// simulate_kinect_2d_3d_nl_correspondences (:389-436): 2-D and normal channels as in simulate_2d_3d_nl, camera points
+// perturbed by the Kinect model (lateral on x, y; axial on z; theta = angle between the true normal and the optical
+// axis towards the camera), weight column 1 = sigma_axial(0, min_depth) / sigma_axial, 3-D outliers from the frustum.
+template <class T>
+inline void simulate_kinect_2d_3d_nl(Rng& rng, const Pose<T>& pose, int n, T n2d, T or2d, T or3d, T nnl, T ornl, T min_depth,
+                                     T max_depth, T f, T* Q, T* M, T* P, T* N, T* U, T* weights3) {
+  std::vector<T> P_gt((size_t)3 * n), N_gt((size_t)3 * n);
+  simulate_2d_3d(rng, pose, n, n2d, or2d, min_depth, max_depth, f, true, Q, U, P_gt.data(), weights3);
+  simulate_nl_nl(rng, pose, n, nnl, ornl, true, M, N, N_gt.data(), weights3);
+  const T sigma_min = kinect_axial_sigma<T>(T(0), min_depth);
+  for (int i = 0; i < n; ++i) {
+    T c = -N_gt[3 * i + 2];  // n . (0, 0, -1)
+    c = c > T(1) ? T(1) : (c < T(-1) ? T(-1) : c);
+    const T theta = std::acos(c);
+    const T z = P_gt[3 * i + 2];
+    const T sl = kinect_lateral_sigma<T>(theta, z, f), sa = kinect_axial_sigma<T>(theta, z);
+    T rv[3];
+    noise_vec(rng, true, 3, rv);
+    P[3 * i] = P_gt[3 * i] + sl * rv[0];
+    P[3 * i + 1] = P_gt[3 * i + 1] + sl * rv[1];
+    P[3 * i + 2] = P_gt[3 * i + 2] + sa * rv[2];
+    if (weights3) weights3[n + i] = sigma_min / sa;
+  }
+  const int out = (int)(or3d * n + .5);
+  std::vector<int> idx;
+  pick_distinct(rng, n, out, &idx);
+  std::vector<T> outp((size_t)3 * (out > 0 ? out : 1));
+  frustum_cloud(rng, out, f, min_depth, max_depth, outp.data());
+  for (int i = 0; i < out; ++i)
+    for (int r = 0; r < 3; ++r) P[3 * idx[i] + r] = outp[3 * i + r];
+}
+
 }  // namespace sim
 }  // namespace rpe
 

@@ -219,6 +219,12 @@ int rpe_sim_2d_3d_nl(uint64_t seed, const float q_xyzw[4], const float t[3], int
                      float or3d, float nnl, float ornl, float min_depth, float max_depth, float f, int use_gaussian,
                      float* Q_xw, float* M_nw, float* P_xc, float* N_nc, float* U_bv, float* weights3);
 
+/* simulate_kinect_2d_3d_nl_correspondences (:389-436): camera points perturbed by the Kinect lateral / axial noise model
+ * of Nguyen, Izadi & Lovell (:368-387); weights3 column 1 = sigma_axial(0, min_depth) / sigma_axial. */
+int rpe_sim_kinect_2d_3d_nl(uint64_t seed, const float q_xyzw[4], const float t[3], int n, float n2d, float or2d, float or3d,
+                            float nnl, float ornl, float min_depth, float max_depth, float f, float* Q_xw, float* M_nw,
+                            float* P_xc, float* N_nc, float* U_bv, float* weights3);
+
 /* Device-side generators: the same distributions produced straight into the context's device arrays (no PCIe
  * traffic; counter-based random stream, so the values differ from the host generators for the same seed).
  * After the call the context holds n correspondences exactly as after rpe_upload. */

@@ -20,6 +20,7 @@ from .capi import (  # noqa: F401
     sim_3d_3d,
     sim_2d_3d,
     sim_2d_3d_nl,
+    sim_kinect_2d_3d_nl,
     method_slots,
     method_mask_cols,
     method_sample_size,
@@ -28,6 +29,6 @@ from .capi import (  # noqa: F401
 
 __all__ = [
     "Context", "RpeError", "lib", "lib_path", "METHODS", "REFITS", "sample_table", "prosac_table",
-    "update_num_iters", "sim_pose", "sim_3d_3d", "sim_2d_3d", "sim_2d_3d_nl", "method_slots",
+    "update_num_iters", "sim_pose", "sim_3d_3d", "sim_2d_3d", "sim_2d_3d_nl", "sim_kinect_2d_3d_nl", "method_slots",
     "method_mask_cols", "method_sample_size", "pinned_empty",
 ]

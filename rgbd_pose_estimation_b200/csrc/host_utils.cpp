@@ -95,4 +95,14 @@ int rpe_sim_2d_3d_nl(uint64_t seed, const float q_xyzw[4], const float t[3], int
   return RPE_OK;
 }
 
+int rpe_sim_kinect_2d_3d_nl(uint64_t seed, const float q_xyzw[4], const float t[3], int n, float n2d, float or2d, float or3d,
+                            float nnl, float ornl, float min_depth, float max_depth, float f, float* Q_xw, float* M_nw,
+                            float* P_xc, float* N_nc, float* U_bv, float* weights3) {
+  if (!q_xyzw || !t || n <= 0 || !Q_xw || !M_nw || !P_xc || !N_nc || !U_bv) return RPE_ERR_ARG;
+  rpe::sim::Rng rng(seed);
+  rpe::sim::simulate_kinect_2d_3d_nl<float>(rng, make_pose(q_xyzw, t), n, n2d, or2d, or3d, nnl, ornl, min_depth, max_depth, f,
+                                            Q_xw, M_nw, P_xc, N_nc, U_bv, weights3);
+  return RPE_OK;
+}
+
 }  // extern "C"
