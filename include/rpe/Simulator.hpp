@@ -40,6 +40,27 @@ rpe::SO3<T> generate_random_rotation(T max_angle_radian_, bool use_guassian_ = t
   return rpe::SO3<T>::fromRawQuaternion(q);
 }
 
+// a candidate point of the box around the frustum: x, y uniform in +-tan_fov * max_depth, z uniform in [min, max]
+template <typename T>
+rpe::Vec3<T> generate_a_random_point(T min_depth_, T max_depth_, T tan_fov_x, T tan_fov_y) {  // [reference :135-145]
+  rpe::sim::Rng& rng = rpe::sim::global_rng();
+  const T x = (T)rng.uniform_pm1() * tan_fov_x * max_depth_;
+  const T y = (T)rng.uniform_pm1() * tan_fov_y * max_depth_;
+  const T z = ((T)rng.uniform_pm1() + T(1)) / T(2) * (max_depth_ - min_depth_) + min_depth_;
+  return rpe::Vec3<T>(x, y, z);
+}
+
+// pinhole projection with focal length f_ and the principal point at the origin: 2 x n pixel coordinates
+template <typename T>
+rpe::MatrixX<T> project_point_cloud(const rpe::MatrixX<T>& pt_c, T f_) {  // [reference :148-156]
+  rpe::MatrixX<T> uv(2, pt_c.cols());
+  for (int i = 0; i < pt_c.cols(); ++i) {
+    uv(2 * i) = f_ * pt_c(3 * i) / pt_c(3 * i + 2);
+    uv(2 * i + 1) = f_ * pt_c(3 * i + 1) / pt_c(3 * i + 2);
+  }
+  return uv;
+}
+
 template <typename T>
 rpe::MatrixX<T> simulate_rand_point_cloud_in_frustum(int number_, T f_, T min_depth_, T max_depth_) {  // [:158-173]
   rpe::MatrixX<T> P(3, number_);

@@ -62,6 +62,9 @@ int main() {
   rpe::Vec3<double> t = generate_random_translation_uniform<double>(5.0);
   rpe::MatrixX<double> Q, M, P, N, U, W;
   simulate_kinect_2d_3d_nl_correspondences<double>(R, t, 500, 1.0, 0.1, 0.1, 0.03, 0.1, 0.4, 8.0, 585.0, &Q, &M, &P, &N, &U, &W);
+  rpe::MatrixX<double> uv = project_point_cloud<double>(P, 585.0);
+  rpe::Vec3<double> c = generate_a_random_point<double>(0.4, 8.0, 320. / 585., 240. / 585.);
+  if (uv.rows() != 2 || uv.cols() != 500 || !(c[2] >= 0.4 && c[2] <= 8.0)) return 2;
   const double sa = axial_noise_kinect<double>(0.0, 0.4), sl = lateral_noise_kinect<double>(0.0, 2.0, 585.0);
   printf("%d %d %.6f %.6f\\n", (int)P.cols(), (int)W.rows(), sa, sl);
   return (P.cols() == 500 && W.rows() == 500 && W.cols() == 3) ? 0 : 1;
