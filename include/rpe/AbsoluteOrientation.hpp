@@ -108,6 +108,28 @@ void shinji_ls2(AOOnlyPoseAdapter<Tp>& adapter) {  // all correspondences [refer
   rpe::detail::run_refit<Tp>(adapter, RPE_REFIT_KABSCH_ALL, nullptr, 0);
 }
 
+// assign_sample [reference :344-365]: gather the K = size-1 sample columns (+ the 4th point used to pick the P3P root)
+// out of the adapter; true iff all K camera points are valid, i.e. the 3-D--3-D solver can run for this sample.
+// (On the device the same gather happens inside the generator kernel; this host form serves callers of the header.)
+template <typename Tp>
+bool assign_sample(const AOPoseAdapter<Tp>& adapter, const std::vector<int>& selected_cols_, rpe::MatrixX<Tp>* p_X_w_,
+                   rpe::MatrixX<Tp>* p_X_c_, rpe::MatrixX<Tp>* p_bv_) {
+  const int K = (int)selected_cols_.size() - 1;
+  int n_valid = 0;
+  for (int k = 0; k < K; ++k) {
+    const int c = selected_cols_[k];
+    p_X_w_->setCol(k, adapter.getPointGlob(c));
+    p_bv_->setCol(k, adapter.getBearingVector(c));
+    if (adapter.isValid(c)) {
+      p_X_c_->setCol(k, adapter.getPointCurr(c));
+      ++n_valid;
+    }
+  }
+  p_X_w_->setCol(3, adapter.getPointGlob(selected_cols_[3]));
+  p_bv_->setCol(3, adapter.getBearingVector(selected_cols_[3]));
+  return n_valid == K;
+}
+
 template <typename Tp>
 void shinji_kneip_ransac(AOPoseAdapter<Tp>& adapter, const Tp dist_thre_3d_, const Tp thre_2d_, int& Iter,
                          Tp confidence = 0.99) {

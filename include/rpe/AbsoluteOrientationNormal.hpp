@@ -36,6 +36,30 @@ inline void nl_cvt_all(NormalAOPoseAdapter<Tp>& adapter, bool pnp, bool ao) {
 }  // namespace detail
 }  // namespace rpe
 
+// assign_sample [reference :48-75]: as the AOPoseAdapter form, with the normals of both frames.
+template <typename Tp>
+bool assign_sample(const NormalAOPoseAdapter<Tp>& adapter, const std::vector<int>& selected_cols_, rpe::MatrixX<Tp>* p_X_w_,
+                   rpe::MatrixX<Tp>* p_N_w_, rpe::MatrixX<Tp>* p_X_c_, rpe::MatrixX<Tp>* p_N_c_, rpe::MatrixX<Tp>* p_bv_) {
+  const int K = (int)selected_cols_.size() - 1;
+  int n_valid = 0;
+  for (int k = 0; k < K; ++k) {
+    const int c = selected_cols_[k];
+    p_X_w_->setCol(k, adapter.getPointGlob(c));
+    p_N_w_->setCol(k, adapter.getNormalGlob(c));
+    p_bv_->setCol(k, adapter.getBearingVector(c));
+    if (adapter.isValid(c)) {
+      p_X_c_->setCol(k, adapter.getPointCurr(c));
+      p_N_c_->setCol(k, adapter.getNormalCurr(c));
+      ++n_valid;
+    }
+  }
+  const int c3 = selected_cols_[3];
+  p_X_w_->setCol(3, adapter.getPointGlob(c3));
+  p_N_w_->setCol(3, adapter.getNormalGlob(c3));
+  p_bv_->setCol(3, adapter.getBearingVector(c3));
+  return n_valid == K;
+}
+
 template <typename Tp>
 void nl_kneip_ransac(NormalAOPoseAdapter<Tp>& adapter, const Tp thre_2d_, const Tp nl_thre, int& Iter, Tp confidence = 0.99) {
   const Tp cos_thr = std::cos(std::atan(thre_2d_ / adapter.getFocal()));  // [reference :222]
