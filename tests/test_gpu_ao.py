@@ -275,3 +275,32 @@ def test_ransac_stream_draws_rows_pass_by_pass(rpe, orc, gpu_ctx):
     assert (got["winner"], got["max_votes"], got["iter_final"]) == (ref["winner"], ref["max_votes"], ref["iter_final"])
     assert got["passes"][:3] == [(0, 1024), (1024, 2048), (3072, 4096)]
     assert ref["iters_run"] == max(got["iter_final"], got["winner"] + 1)
+
+
+def test_c_abi_error_behaviour(rpe):
+    """The reference asserts / aborts; the C-ABI returns a status, keeps a message and leaves the context usable."""
+    import ctypes as C
+    with rpe.Context(0) as ctx:
+        S = rpe.sample_table(1, 100, 3, 8)
+        res = rpe.capi._Result()
+        # nothing uploaded yet
+        assert rpe.lib.rpe_ransac(ctx.handle, 0, S.ctypes.data, 8, 0.25, 0.0, 0.0, 0.99, C.byref(res), None) != 0
+        assert b"" != rpe.lib.rpe_last_error(ctx.handle)
+        assert rpe.lib.rpe_refit(ctx.handle, 0, None, 0, C.byref(res)) != 0
+        q, t, Q, P = _frame(rpe, 5, 100)
+        ctx.upload(xc=P, xw=Q)
+        for bad in [dict(method=99), dict(H=0), dict(samples=None)]:
+            m = bad.get("method", 0)
+            H = bad.get("H", 8)
+            sp = None if "samples" in bad else S.ctypes.data
+            assert rpe.lib.rpe_ransac(ctx.handle, m, sp, H, 0.25, 0.0, 0.0, 0.99, C.byref(res), None) != 0
+        # a 2-D method without bearing vectors is a state error, not a crash
+        with pytest.raises(rpe.RpeError):
+            ctx.ransac("kneip", rpe.sample_table(1, 100, 4, 8), cos_thr2d=0.999)
+        # GN before any mask exists
+        with pytest.raises(rpe.RpeError):
+            ctx.refit("gn")
+        # and the context still works
+        r = ctx.ransac("shinji", S, thr3d=0.25, confidence=0.99)
+        assert r["winner"] >= 0 and r["max_votes"] > 10
+    assert rpe.lib.rpe_ransac(None, 0, None, 0, 0.0, 0.0, 0.0, 0.0, None, None) != 0
