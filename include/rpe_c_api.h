@@ -233,6 +233,9 @@ int rpe_sim_3d_3d_device(rpe_ctx* ctx, uint64_t seed, const float q_xyzw[4], con
 int rpe_sim_2d_3d_nl_device(rpe_ctx* ctx, uint64_t seed, const float q_xyzw[4], const float t[3], int n, float n2d,
                             float or2d, float n3d, float or3d, float nnl, float ornl, float min_depth, float max_depth,
                             float f, int use_gaussian);
+/* simulate_kinect_2d_3d_nl_correspondences on the device (Kinect lateral / axial noise on the camera points). */
+int rpe_sim_kinect_2d_3d_nl_device(rpe_ctx* ctx, uint64_t seed, const float q_xyzw[4], const float t[3], int n, float n2d,
+                                   float or2d, float or3d, float nnl, float ornl, float min_depth, float max_depth, float f);
 /* Copy the context's current correspondence arrays back to host memory (NULL = skip). */
 int rpe_download(rpe_ctx* ctx, float* bv, float* xc, float* nc, float* xw, float* nw);
 

@@ -111,6 +111,7 @@ _sig("rpe_upload_f64", C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, C.c_int])
 _sig("rpe_ransac_f64", C.c_int, [_vp, C.c_int, _vp, SAMPLE_FN, _vp, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double,
                                  C.POINTER(_Result), _vp])
 _sig("rpe_get_hypotheses_f64", C.c_int, [_vp, C.c_int, _vp, _vp])
+_sig("rpe_sim_kinect_2d_3d_nl_device", C.c_int, [_vp, C.c_uint64, _vp, _vp, C.c_int] + [C.c_float] * 8)
 _sig("rpe_sim_kinect_2d_3d_nl", C.c_int, [C.c_uint64, _vp, _vp, C.c_int] + [C.c_float] * 8 + [_vp] * 6)
 _sig("rpe_refit", C.c_int, [_vp, C.c_int, _vp, C.c_int, C.POINTER(_Result)])
 _sig("rpe_refit_async", C.c_int, [_vp, C.c_int, _vp, C.c_int, C.POINTER(_Result)])
@@ -150,7 +151,7 @@ DECLARED_SYMBOLS = [
     "rpe_upload_device", "rpe_num_correspondences", "rpe_ransac", "rpe_ransac_async", "rpe_ransac_stream", "rpe_upload_f64", "rpe_ransac_f64", "rpe_get_hypotheses_f64", "rpe_refit", "rpe_refit_async",
     "rpe_set_pose", "rpe_set_mask", "rpe_generate", "rpe_get_hypotheses", "rpe_set_hypotheses", "rpe_score",
     "rpe_get_votes", "rpe_set_votes", "rpe_votes_device_ptr", "rpe_finish", "rpe_update_num_iters", "rpe_sample_table",
-    "rpe_prosac_table", "rpe_sim_pose", "rpe_sim_3d_3d", "rpe_sim_2d_3d", "rpe_sim_2d_3d_nl", "rpe_sim_kinect_2d_3d_nl", "rpe_sim_3d_3d_device",
+    "rpe_prosac_table", "rpe_sim_pose", "rpe_sim_3d_3d", "rpe_sim_2d_3d", "rpe_sim_2d_3d_nl", "rpe_sim_kinect_2d_3d_nl", "rpe_sim_kinect_2d_3d_nl_device", "rpe_sim_3d_3d_device",
     "rpe_sim_2d_3d_nl_device", "rpe_download", "rpe_ao", "rpe_ao_ransac",
     "rpe_measure_ffma_tflops", "rpe_last_stage_ms", "rpe_enable_stage_timing",
 ]
@@ -333,6 +334,12 @@ class Context:
         self.n = n
         _check(lib.rpe_sim_3d_3d_device(self._h, seed, _ptr(_f32(q)), _ptr(_f32(t)), n, noise, outlier_ratio, min_depth,
                                         max_depth, f, 1 if gaussian else 0), self._h)
+
+    def sim_kinect_2d_3d_nl_device(self, seed, q, t, n, n2d=1.0, or2d=0.3, or3d=0.3, nnl=np.deg2rad(2.0), ornl=0.3,
+                                   min_depth=0.4, max_depth=8.0, f=585.0):
+        self.n = n
+        _check(lib.rpe_sim_kinect_2d_3d_nl_device(self._h, seed, _ptr(_f32(q)), _ptr(_f32(t)), n, n2d, or2d, or3d, nnl, ornl,
+                                                  min_depth, max_depth, f), self._h)
 
     def sim_2d_3d_nl_device(self, seed, q, t, n, n2d=1.0, or2d=0.3, n3d=0.05, or3d=0.3, nnl=np.deg2rad(2.0), ornl=0.3,
                             min_depth=0.4, max_depth=8.0, f=585.0, gaussian=True):

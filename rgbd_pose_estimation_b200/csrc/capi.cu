@@ -17,18 +17,6 @@
 #include "kernels.cuh"
 
 namespace rpe {
-struct SimParams {
-  float R[9];
-  float t[3];
-  int n;
-  float noise2d, noise3d, noise_nl;
-  int out2d, out3d, outnl;
-  unsigned int ainv[3], b[3];
-  float min_depth, max_depth, f;
-  int gaussian;
-  unsigned long long seed;
-};
-void launch_simulate(const SimParams& p, float* xw, float* xc, float* bv, float* nw, float* nc, int mode_3d3d, cudaStream_t s);
 void set_use_packed(bool v);
 void set_score_variant(int v);
 void set_nosync(int v);
@@ -1265,7 +1253,7 @@ static unsigned int modinv_u(unsigned int a, unsigned int n) {  // a^-1 mod n, g
 
 static int sim_device_common(rpe_ctx* ctx, uint64_t seed, const float q[4], const float t[3], int n, float n2d, float or2d,
                              float n3d, float or3d, float nnl, float ornl, float min_depth, float max_depth, float f,
-                             int use_gaussian, int mode_3d3d) {
+                             int use_gaussian, int mode_3d3d, int kinect = 0) {
   if (!ctx || !q || !t || n <= 0) return RPE_ERR_ARG;
   CK(cudaSetDevice(ctx->device));
   int rc = ensure_corr_capacity(ctx, n, true);
@@ -1293,6 +1281,7 @@ static int sim_device_common(rpe_ctx* ctx, uint64_t seed, const float q[4], cons
   p.max_depth = max_depth;
   p.f = f;
   p.gaussian = use_gaussian;
+  p.kinect = kinect;
   p.seed = seed;
   ctx->n = n;
   for (int k = 0; k < 5; ++k) ctx->view[k] = nullptr;
@@ -1322,6 +1311,10 @@ int rpe_sim_2d_3d_nl_device(rpe_ctx* ctx, uint64_t seed, const float q_xyzw[4], 
                             float or2d, float n3d, float or3d, float nnl, float ornl, float min_depth, float max_depth,
                             float f, int use_gaussian) {
   return sim_device_common(ctx, seed, q_xyzw, t, n, n2d, or2d, n3d, or3d, nnl, ornl, min_depth, max_depth, f, use_gaussian, 0);
+}
+int rpe_sim_kinect_2d_3d_nl_device(rpe_ctx* ctx, uint64_t seed, const float q_xyzw[4], const float t[3], int n, float n2d,
+                                   float or2d, float or3d, float nnl, float ornl, float min_depth, float max_depth, float f) {
+  return sim_device_common(ctx, seed, q_xyzw, t, n, n2d, or2d, 0.f, or3d, nnl, ornl, min_depth, max_depth, f, 1, 0, 1);
 }
 // Copy the context's current correspondence arrays back to the host (NULL = skip). For tests / inspection.
 int rpe_download(rpe_ctx* ctx, float* bv, float* xc, float* nc, float* xw, float* nw) {

@@ -112,6 +112,22 @@ void launch_gn_iteration(const FrameView& f, const int16_t* mask, int mask_cols,
 void launch_gn_from_stats(RefitBuffers rb, int blocks_used, float w3d, float wnl, int max_iters, ReplayOut* pose_io,
                           GnState* gs, double* cost_out, int32_t* evals_out, cudaStream_t s);
 
+// -- device-side Simulator (simulate.cu) ------------------------------------------------------------
+struct SimParams {
+  float R[9];  // R_cw row-major
+  float t[3];
+  int n;
+  float noise2d, noise3d, noise_nl;
+  int out2d, out3d, outnl;  // number of outliers per modality
+  // affine permutations i -> (a*j + b) mod n ; membership: j = ainv*(i - b) mod n < out
+  unsigned int ainv[3], b[3];
+  float min_depth, max_depth, f;
+  int gaussian;
+  int kinect;  // camera points perturbed by the Kinect lateral / axial model instead of isotropic noise3d
+  unsigned long long seed;
+};
+void launch_simulate(const SimParams& p, float* xw, float* xc, float* bv, float* nw, float* nc, int mode_3d3d, cudaStream_t s);
+
 // -- binary64 RANSAC path (f64.cu) ------------------------------------------------------------------
 struct FrameView64 {
   const double* bv;

@@ -39,18 +39,6 @@ struct CRng {  // counter-based: (seed, stream, index) fixed, `draw` advances
   }
 };
 
-struct SimParams {
-  float R[9];  // R_cw row-major
-  float t[3];
-  int n;
-  float noise2d, noise3d, noise_nl;
-  int out2d, out3d, outnl;  // number of outliers per modality
-  // affine permutations i -> (a*j + b) mod n ; membership: j = ainv*(i - b) mod n < out
-  unsigned int ainv[3], b[3];
-  float min_depth, max_depth, f;
-  int gaussian;
-  unsigned long long seed;
-};
 
 __device__ __forceinline__ void frustum_point(CRng& g, float f, float dmin, float dmax, float* P) {
   const float tx = 320.f / f, ty = 240.f / f;
@@ -142,10 +130,11 @@ __global__ void sim_kernel(SimParams p, float* __restrict__ xw, float* __restric
     bv[3 * (size_t)i + 1] = ky / nn;
     bv[3 * (size_t)i + 2] = p.f / nn;
   }
+  float ngt[3] = {0.f, 0.f, -1.f};  // true camera-frame normal (frontal when the normal channel is absent)
   if (nw && nc) {
     CRng gn(p.seed, 3, (unsigned int)i);
     const float back[3] = {0.f, 0.f, -1.f};
-    float ngt[3], m[3], nn[3];
+    float m[3], nn[3];
     for (int k = 0; k < 64; ++k) {
       facing_normal(gn, 1.57079632679f, false, back, ngt);
       for (int r = 0; r < 3; ++r) m[r] = p.R[r] * ngt[0] + p.R[3 + r] * ngt[1] + p.R[6 + r] * ngt[2];
@@ -168,7 +157,21 @@ __global__ void sim_kernel(SimParams p, float* __restrict__ xw, float* __restric
   if (xc) {
     float C[3] = {P[0], P[1], P[2]};
     CRng gc(p.seed, 5, (unsigned int)i);
-    for (int r = 0; r < 3; ++r) C[r] += p.noise3d * (p.gaussian ? gc.normal() : gc.pm1());
+    if (p.kinect) {
+      // Nguyen, Izadi & Lovell (3DIMPVT 2012), as used at Simulator.hpp:368-423: lateral sigma (pixels -> metres) on x, y,
+      // axial sigma on z; theta = angle between the true normal and the optical axis towards the camera
+      const float half_pi = 1.57079632679f;
+      const float theta = acosf(fminf(fmaxf(-ngt[2], -1.f), 1.f));
+      const float z = P[2];
+      const float sl = (0.8f + 0.035f * theta / (half_pi - theta)) * z / p.f;
+      float sa = 0.0012f + 0.0019f * (z - 0.4f) * (z - 0.4f);
+      if (fabsf(theta) > 1.0471975512f) sa += 0.0001f * theta * theta / sqrtf(z) / ((half_pi - theta) * (half_pi - theta));
+      C[0] += sl * gc.normal();
+      C[1] += sl * gc.normal();
+      C[2] += sa * gc.normal();
+    } else {
+      for (int r = 0; r < 3; ++r) C[r] += p.noise3d * (p.gaussian ? gc.normal() : gc.pm1());
+    }
     if (is_outlier(p, 1, (unsigned int)i)) {
       CRng go(p.seed, 6, (unsigned int)i);
       frustum_point(go, p.f, p.min_depth, p.max_depth, C);

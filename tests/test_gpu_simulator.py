@@ -62,3 +62,34 @@ def test_device_multimodal_statistics(rpe, gpu_ctx):
     Re = _R(r["q"])
     ang = np.arccos(np.clip((np.trace(Re @ R.T) - 1) / 2, -1, 1))
     assert ang < 0.05 and r["max_votes"] > 1.8 * n
+
+
+def test_device_kinect_noise_model(rpe, gpu_ctx):
+    """rpe_sim_kinect_2d_3d_nl_device: camera points carry the Kinect axial (quadratic in depth) and lateral noise."""
+    n, f = 200000, 585.0
+    q, t = rpe.sim_pose(31)
+    gpu_ctx.sim_kinect_2d_3d_nl_device(32, q, t, n, n2d=1.0, or2d=0.0, or3d=0.2, nnl=float(np.deg2rad(2.0)), ornl=0.0)
+    d = gpu_ctx.download(("xc", "xw", "nc", "nw"))
+    P = d["xc"].astype(np.float64)
+    Pgt = d["xw"].astype(np.float64) @ _R(q).T + np.asarray(t, np.float64)
+    e = P - Pgt
+    inl = np.abs(e).max(axis=1) < 0.5
+    assert abs((~inl).mean() - 0.2) < 0.01
+    z = Pgt[:, 2]
+    ngt = d["nw"].astype(np.float64) @ _R(q).T            # true camera-frame normals (noise-free up to 2 deg)
+    theta = np.arccos(np.clip(-ngt[:, 2], -1, 1))
+    frontal = inl & (theta < np.deg2rad(55.0))
+    base = 0.0012 + 0.0019 * (z - 0.4) ** 2
+
+    def robust_sigma(v):
+        return 1.4826 * np.median(np.abs(v))
+
+    for lo, hi, tol in [(3.0, 4.0, 0.06), (6.5, 7.5, 0.04)]:
+        sel = frontal & (z > lo) & (z < hi)
+        assert abs(robust_sigma(e[sel, 2] / base[sel]) - 1) < tol
+    sel = frontal & (z > 3.0) & (z < 4.0)
+    lat = (0.8 + 0.035 * theta / (np.pi / 2 - theta)) * z / f
+    assert abs(robust_sigma(e[sel, 0] / lat[sel]) - 1) < 0.06 and abs(robust_sigma(e[sel, 1] / lat[sel]) - 1) < 0.06
+    # grazing surfaces are noisier in depth than the quadratic term alone
+    graz = inl & (theta > np.deg2rad(75.0)) & (z > 3.0) & (z < 4.0)
+    assert robust_sigma(e[graz, 2] / base[graz]) > 1.05
