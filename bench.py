@@ -547,7 +547,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--frames-per-step", type=int, default=96)
     ap.add_argument("--ring", type=int, default=24, help="distinct frames resident per GPU (>L2 in total)")
-    ap.add_argument("--contexts", type=int, default=8, help="rpe contexts (streams) per GPU, frames round-robin")
+    ap.add_argument("--contexts", type=int, default=12, help="rpe contexts (streams) per GPU, frames round-robin")
     ap.add_argument("--gn-iters", type=int, default=3)
     ap.add_argument("--ref-hyp", type=int, default=128, help="hypotheses per step of the CPU arm (bounded sample)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
