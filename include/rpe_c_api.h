@@ -190,6 +190,25 @@ int rpe_get_votes(rpe_ctx* ctx, int32_t* votes, int n_slots);
 int rpe_set_votes(rpe_ctx* ctx, const int32_t* votes, int n_slots);
 /* Device pointer of the votes array (for NCCL all-gather by the caller in sharded mode). */
 int32_t* rpe_votes_device_ptr(rpe_ctx* ctx);
+/* The exchange step of the hypothesis-sharded mode over peer memory instead of a collective library: every rank
+ * (one process per GPU of a node) exports one small block (rpe_peer_export -> 64-byte CUDA IPC handle), the handles
+ * are gathered by any host-side means (MPI, torch.distributed, a file) and imported (rpe_peer_import, `handles` =
+ * world x 64 bytes in rank order). rpe_exchange_votes then enqueues one kernel that writes this rank's slots
+ * [slot_begin, slot_end) of the vote table into every rank's table over NVLink, publishes a flag, waits (at most 2 s)
+ * for all ranks, and leaves the complete table in the context — asynchronous, no host round trip; every rank must call
+ * it once per frame. rpe_peer_status synchronises and reports a time-out. */
+int rpe_peer_export(rpe_ctx* ctx, unsigned char handle[64]);
+int rpe_peer_import(rpe_ctx* ctx, int rank, int world, const unsigned char* handles);
+int rpe_exchange_votes(rpe_ctx* ctx, int slot_begin, int slot_end);
+int rpe_peer_status(rpe_ctx* ctx);
+/* rpe_ransac for one frame whose hypotheses are sharded over the ranks set up with rpe_peer_import: every rank holds the
+ * same correspondences and sample table (H <= 8192), generates all hypotheses, scores its own contiguous slice of
+ * slots, exchanges the slices through peer memory and replays the rule — all ranks return the same result. One
+ * asynchronous stream of work per frame; every rank must make the same sequence of calls. */
+int rpe_ransac_sharded(rpe_ctx* ctx, int method, const int32_t* samples, int H, float thr3d, float cos_thr2d, float cos_thrN,
+                       float confidence, rpe_result* out, int16_t* mask);
+int rpe_ransac_sharded_async(rpe_ctx* ctx, int method, const int32_t* samples, int H, float thr3d, float cos_thr2d,
+                             float cos_thrN, float confidence, rpe_result* out, int16_t* mask);
 /* Replay the adaptive rule over the current votes, build the winner's mask. */
 int rpe_finish(rpe_ctx* ctx, int method, int H, float thr3d, float cos_thr2d, float cos_thrN, float confidence,
                rpe_result* out, int16_t* mask);

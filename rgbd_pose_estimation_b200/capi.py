@@ -113,6 +113,14 @@ _sig("rpe_ransac_f64", C.c_int, [_vp, C.c_int, _vp, SAMPLE_FN, _vp, C.c_int, C.c
 _sig("rpe_get_hypotheses_f64", C.c_int, [_vp, C.c_int, _vp, _vp])
 _sig("rpe_sim_kinect_2d_3d_nl_device", C.c_int, [_vp, C.c_uint64, _vp, _vp, C.c_int] + [C.c_float] * 8)
 _sig("rpe_sim_kinect_2d_3d_nl", C.c_int, [C.c_uint64, _vp, _vp, C.c_int] + [C.c_float] * 8 + [_vp] * 6)
+_sig("rpe_peer_export", C.c_int, [_vp, _vp])
+_sig("rpe_peer_import", C.c_int, [_vp, C.c_int, C.c_int, _vp])
+_sig("rpe_exchange_votes", C.c_int, [_vp, C.c_int, C.c_int])
+_sig("rpe_peer_status", C.c_int, [_vp])
+_sig("rpe_ransac_sharded", C.c_int, [_vp, C.c_int, _vp, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float,
+                                     C.POINTER(_Result), _vp])
+_sig("rpe_ransac_sharded_async", C.c_int, [_vp, C.c_int, _vp, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float,
+                                           C.POINTER(_Result), _vp])
 _sig("rpe_refit", C.c_int, [_vp, C.c_int, _vp, C.c_int, C.POINTER(_Result)])
 _sig("rpe_refit_async", C.c_int, [_vp, C.c_int, _vp, C.c_int, C.POINTER(_Result)])
 _sig("rpe_set_pose", C.c_int, [_vp, _vp, _vp, C.c_int])
@@ -150,7 +158,7 @@ DECLARED_SYMBOLS = [
     "rpe_last_error", "rpe_stream", "rpe_sync", "rpe_launch_count", "rpe_host_alloc", "rpe_host_free", "rpe_upload",
     "rpe_upload_device", "rpe_num_correspondences", "rpe_ransac", "rpe_ransac_async", "rpe_ransac_stream", "rpe_upload_f64", "rpe_ransac_f64", "rpe_get_hypotheses_f64", "rpe_refit", "rpe_refit_async",
     "rpe_set_pose", "rpe_set_mask", "rpe_generate", "rpe_get_hypotheses", "rpe_set_hypotheses", "rpe_score",
-    "rpe_get_votes", "rpe_set_votes", "rpe_votes_device_ptr", "rpe_finish", "rpe_update_num_iters", "rpe_sample_table",
+    "rpe_get_votes", "rpe_set_votes", "rpe_votes_device_ptr", "rpe_peer_export", "rpe_peer_import", "rpe_exchange_votes", "rpe_peer_status", "rpe_ransac_sharded", "rpe_ransac_sharded_async", "rpe_finish", "rpe_update_num_iters", "rpe_sample_table",
     "rpe_prosac_table", "rpe_sim_pose", "rpe_sim_3d_3d", "rpe_sim_2d_3d", "rpe_sim_2d_3d_nl", "rpe_sim_kinect_2d_3d_nl", "rpe_sim_kinect_2d_3d_nl_device", "rpe_sim_3d_3d_device",
     "rpe_sim_2d_3d_nl_device", "rpe_download", "rpe_ao", "rpe_ao_ransac",
     "rpe_measure_ffma_tflops", "rpe_last_stage_ms", "rpe_enable_stage_timing",
@@ -472,6 +480,42 @@ class Context:
     def score(self, method, slot_begin, slot_end, thr3d=0.0, cos_thr2d=0.0, cos_thrN=0.0):
         m = METHODS[method] if isinstance(method, str) else method
         _check(lib.rpe_score(self._h, m, slot_begin, slot_end, thr3d, cos_thr2d, cos_thrN), self._h)
+
+    def peer_export(self):
+        """64-byte CUDA IPC handle of this context's exchange block (hypothesis-sharded single-frame mode)."""
+        h = np.zeros(64, np.uint8)
+        _check(lib.rpe_peer_export(self._h, _ptr(h)), self._h)
+        return h
+
+    def peer_import(self, rank, world, handles):
+        handles = np.ascontiguousarray(handles, dtype=np.uint8).reshape(world, 64)
+        _check(lib.rpe_peer_import(self._h, rank, world, _ptr(handles)), self._h)
+
+    def exchange_votes(self, slot_begin, slot_end):
+        _check(lib.rpe_exchange_votes(self._h, slot_begin, slot_end), self._h)
+
+    def ransac_sharded(self, method, samples, H=None, thr3d=0.0, cos_thr2d=0.0, cos_thrN=0.0, confidence=0.99, blocking=True):
+        """One hypothesis-sharded frame (see rpe_ransac_sharded). `samples`: (H, 4) int32 array or a device pointer + H.
+        blocking=False returns the ctypes result struct, valid after sync()."""
+        m = METHODS[method] if isinstance(method, str) else method
+        if isinstance(samples, int):
+            sp = C.c_void_p(samples)
+        else:
+            samples = np.ascontiguousarray(samples, dtype=np.int32)
+            H = samples.shape[0]
+            self._keep.append(samples)
+            sp = _ptr(samples)
+        res = _Result()
+        if blocking:
+            _check(lib.rpe_ransac_sharded(self._h, m, sp, H, thr3d, cos_thr2d, cos_thrN, confidence, C.byref(res), None), self._h)
+            return res.to_dict()
+        self._keep.append(res)
+        _check(lib.rpe_ransac_sharded_async(self._h, m, sp, H, thr3d, cos_thr2d, cos_thrN, confidence, C.byref(res), None),
+               self._h)
+        return res
+
+    def peer_status(self):
+        _check(lib.rpe_peer_status(self._h), self._h)
 
     def get_votes(self, n_slots):
         v = np.empty(n_slots, np.int32)

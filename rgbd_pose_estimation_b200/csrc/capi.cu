@@ -69,6 +69,12 @@ struct rpe_ctx {
   ReplayOut* h_pose = nullptr;    // pinned, kNumStaging slots; [0] doubles as scratch for set_pose
   bool kabsch_valid = false;
   bool suff_valid = false;  // rb.suff matches the inlier columns in d_mask
+  // peer-memory vote exchange (hypothesis-sharded single frame)
+  unsigned char* d_peer_block = nullptr;  // own block (exported)
+  PeerTable peers = {};
+  bool peer_opened[kMaxPeers] = {};
+  int peer_rank = -1, peer_world = 0;
+  unsigned int peer_epoch = 0;
   // binary64 path (rpe_upload_f64)
   bool f64 = false;
   double* d_raw64[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -825,6 +831,9 @@ int rpe_destroy(rpe_ctx* ctx) {
   cudaFree(ctx->d_weights3);
   cudaFree(ctx->d_gn_cost);
   cudaFree(ctx->d_gn_evals);
+  for (int r = 0; r < kMaxPeers; ++r)
+    if (ctx->peer_opened[r]) cudaIpcCloseMemHandle(ctx->peers.block[r]);
+  if (ctx->d_peer_block) cudaFree(ctx->d_peer_block);
   if (ctx->h_samples) cudaFreeHost(ctx->h_samples);
   for (int k = 0; k < 5; ++k)
     if (ctx->d_raw64[k]) cudaFree(ctx->d_raw64[k]);
@@ -1205,6 +1214,114 @@ int rpe_set_votes(rpe_ctx* ctx, const int32_t* votes, int n_slots) {
   return RPE_OK;
 }
 int32_t* rpe_votes_device_ptr(rpe_ctx* ctx) { return ctx ? ctx->d_votes : nullptr; }
+
+// ---- peer-memory exchange of the vote table (one process per GPU, CUDA IPC over NVLink) ----------------------
+int rpe_peer_export(rpe_ctx* ctx, unsigned char handle[64]) {
+  if (!ctx || !handle) return RPE_ERR_ARG;
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
+  CK(cudaSetDevice(ctx->device));
+  if (!ctx->d_peer_block) {
+    CK(cudaMalloc(&ctx->d_peer_block, kPeerBlockBytes));
+    CK(cudaMemset(ctx->d_peer_block, 0, kPeerBlockBytes));
+  }
+  cudaIpcMemHandle_t h;
+  CK(cudaIpcGetMemHandle(&h, ctx->d_peer_block));
+  memcpy(handle, &h, 64);
+  return RPE_OK;
+}
+int rpe_peer_import(rpe_ctx* ctx, int rank, int world, const unsigned char* handles) {
+  if (!ctx || !handles || world < 1 || world > kMaxPeers || rank < 0 || rank >= world) return RPE_ERR_ARG;
+  if (!ctx->d_peer_block) return fail(ctx, RPE_ERR_STATE, "call rpe_peer_export first");
+  CK(cudaSetDevice(ctx->device));
+  for (int r = 0; r < world; ++r) {
+    if (r == rank) {
+      ctx->peers.block[r] = ctx->d_peer_block;
+      continue;
+    }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handles + 64 * (size_t)r, 64);
+    void* p = nullptr;
+    CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    ctx->peers.block[r] = (unsigned char*)p;
+    ctx->peer_opened[r] = true;
+  }
+  ctx->peer_rank = rank;
+  ctx->peer_world = world;
+  ctx->peer_epoch = 0;
+  return RPE_OK;
+}
+int rpe_exchange_votes(rpe_ctx* ctx, int slot_begin, int slot_end) {
+  if (!ctx) return RPE_ERR_ARG;
+  if (ctx->peer_world < 1) return fail(ctx, RPE_ERR_STATE, "call rpe_peer_import first");
+  if (slot_begin < 0 || slot_end < slot_begin || slot_end > ctx->n_slots || ctx->n_slots > kPeerSlots)
+    return fail(ctx, RPE_ERR_ARG, "bad slot range for rpe_exchange_votes");
+  CK(cudaSetDevice(ctx->device));
+  ctx->peer_epoch += 1;
+  launch_exchange_votes(ctx->peers, ctx->peer_rank, ctx->peer_world, ctx->peer_epoch, slot_begin, slot_end, ctx->n_slots,
+                        ctx->d_votes, ctx->stream);
+  ctx->launches++;
+  return RPE_OK;
+}
+// One frame of the hypothesis-sharded mode as a single asynchronous stream of work: generate all H (replicated,
+// cheap), score this rank's slots, exchange through peer memory, replay + mask on every rank (identical result).
+static int do_ransac_sharded(rpe_ctx* ctx, int method, const int32_t* samples, int H, float thr3d, float cos_thr2d,
+                             float cos_thrN, float confidence, rpe_result* out, int16_t* mask, bool blocking) {
+  if (!ctx) return RPE_ERR_ARG;
+  if (!method_ok(method) || !samples || H <= 0 || !out) return fail(ctx, RPE_ERR_ARG, "bad argument to rpe_ransac_sharded");
+  if (ctx->f64) return fail(ctx, RPE_ERR_STATE, "the sharded mode is binary32 only");
+  if (ctx->peer_world < 1) return fail(ctx, RPE_ERR_STATE, "call rpe_peer_import first");
+  const int S = method_slots(method);
+  if (H > kMaxPassIters || H * S > kPeerSlots) return fail(ctx, RPE_ERR_ARG, "rpe_ransac_sharded: at most 8192 iterations");
+  int rc = check_arrays(ctx, method);
+  if (rc) return rc;
+  CK(cudaSetDevice(ctx->device));
+  const Thresh th = {thr3d, cos_thr2d, cos_thrN};
+  rc = ensure_hyp_capacity(ctx, H, H * S);
+  if (rc) return rc;
+  if (!ctx->stats_clean) {
+    launch_reset_stats(ctx->d_stats, ctx->stream);
+    ctx->launches++;
+  }
+  launch_replay_begin(ctx->d_rs, H, ctx->stream);
+  ctx->launches++;
+  rc = ensure_packed(ctx, kind_for_method(method));
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(ctx->d_samples, samples, (size_t)H * 4 * sizeof(int32_t), cudaMemcpyDefault, ctx->stream));
+  FrameView f = make_view(ctx);
+  launch_hypgen(method, f, ctx->d_samples, H, ctx->d_gen, ctx->d_fast, ctx->d_votes, ctx->d_stats, ctx->stream);
+  ctx->launches++;
+  ctx->n_slots = H * S;
+  ctx->cur_method = method;
+  // balanced contiguous slot ranges, the same split on every rank
+  const int n_slots = H * S, G = ctx->peer_world, r = ctx->peer_rank;
+  const int base = n_slots / G, rem = n_slots % G;
+  const int sb = r * base + (r < rem ? r : rem), se = sb + base + (r < rem ? 1 : 0);
+  rc = score_range(ctx, method, sb, se, th);
+  if (rc) return rc;
+  ctx->peer_epoch += 1;
+  launch_exchange_votes(ctx->peers, r, G, ctx->peer_epoch, sb, se, n_slots, ctx->d_votes, ctx->stream);
+  launch_replay(method, ctx->d_gen, ctx->d_votes, H, 0, ctx->n, confidence, ctx->d_stats, ctx->d_rs, ctx->d_pose, true,
+                ctx->stream);
+  ctx->launches += 2;
+  ctx->stats_clean = true;
+  return do_finish(ctx, method, th, out, mask, blocking);
+}
+int rpe_ransac_sharded(rpe_ctx* ctx, int method, const int32_t* samples, int H, float thr3d, float cos_thr2d, float cos_thrN,
+                       float confidence, rpe_result* out, int16_t* mask) {
+  return do_ransac_sharded(ctx, method, samples, H, thr3d, cos_thr2d, cos_thrN, confidence, out, mask, true);
+}
+int rpe_ransac_sharded_async(rpe_ctx* ctx, int method, const int32_t* samples, int H, float thr3d, float cos_thr2d,
+                             float cos_thrN, float confidence, rpe_result* out, int16_t* mask) {
+  return do_ransac_sharded(ctx, method, samples, H, thr3d, cos_thr2d, cos_thrN, confidence, out, mask, false);
+}
+int rpe_peer_status(rpe_ctx* ctx) {
+  if (!ctx || !ctx->d_peer_block) return RPE_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  unsigned int err = 0;
+  CK(cudaMemcpy(&err, peer_flags(ctx->d_peer_block) + kPeerErrSlot, sizeof(err), cudaMemcpyDeviceToHost));
+  return err ? fail(ctx, RPE_ERR_STATE, "a peer did not publish its votes within the time-out") : RPE_OK;
+}
 
 int rpe_finish(rpe_ctx* ctx, int method, int H, float thr3d, float cos_thr2d, float cos_thrN, float confidence,
                rpe_result* out, int16_t* mask) {

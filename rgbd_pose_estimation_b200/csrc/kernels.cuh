@@ -112,6 +112,21 @@ void launch_gn_iteration(const FrameView& f, const int16_t* mask, int mask_cols,
 void launch_gn_from_stats(RefitBuffers rb, int blocks_used, float w3d, float wnl, int max_iters, ReplayOut* pose_io,
                           GnState* gs, double* cost_out, int32_t* evals_out, cudaStream_t s);
 
+// -- peer-memory vote exchange (peer.cu) --------------------------------------------------------------
+// One block per rank, exported through CUDA IPC: 64 flag words (slot r = the epoch rank r has published here, slot
+// kPeerErrSlot = latched time-out) followed by two vote tables of kPeerSlots int32.
+constexpr int kMaxPeers = 16, kPeerErrSlot = 63, kPeerFlagWords = 64, kPeerSlots = 8192 * 3;
+constexpr size_t kPeerBlockBytes = kPeerFlagWords * sizeof(unsigned int) + 2 * (size_t)kPeerSlots * sizeof(int32_t);
+struct PeerTable {
+  unsigned char* block[kMaxPeers];  // this process' mappings of every rank's block (own block included)
+};
+__host__ __device__ inline unsigned int* peer_flags(unsigned char* block) { return reinterpret_cast<unsigned int*>(block); }
+__host__ __device__ inline int32_t* peer_table(unsigned char* block, int parity) {
+  return reinterpret_cast<int32_t*>(block + kPeerFlagWords * sizeof(unsigned int)) + (size_t)parity * kPeerSlots;
+}
+void launch_exchange_votes(const PeerTable& peers, int rank, int world, unsigned int epoch, int slot_begin, int slot_end,
+                           int n_slots, int32_t* votes, cudaStream_t s);
+
 // -- device-side Simulator (simulate.cu) ------------------------------------------------------------
 struct SimParams {
   float R[9];  // R_cw row-major

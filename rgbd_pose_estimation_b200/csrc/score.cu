@@ -695,11 +695,13 @@ static int launch_multi(const FrameView& f, const HypGen* gen, const HypFast* fa
   // kinds with the 2-D test queue borderline evaluations on the spot (pixel-level thresholds put a percent of a good
   // hypothesis' evaluations inside the band); without it the group flag + rare re-walk is cheaper
   static const bool direct = getenv("RPE_MULTI_DIRECT") ? getenv("RPE_MULTI_DIRECT")[0] != '0' : KindTraits<KIND>::k2;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {};  // the attribute is per device
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64 && !attr_set[dev]) {
     cudaFuncSetAttribute(score_multi_fast_kernel<KIND, TILE, THREADS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaFuncSetAttribute(score_multi_fast_kernel<KIND, TILE, THREADS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attr_set = true;
+    attr_set[dev] = true;
   }
   if (direct)
     score_multi_fast_kernel<KIND, TILE, THREADS, true><<<dim3(gx, gy), THREADS, smem, s>>>(
@@ -740,10 +742,12 @@ static int launch_variant(const FrameView& f, const HypGen* gen, const HypFast* 
   // twice the latency per launch); the small kernels of other frames still co-run in the remaining space.
   if (MINB == 1 && g_exclusive_sm && smem < (size_t)116 * 1024) smem = (size_t)116 * 1024;
   auto kern = score3d_fast_kernel<PACKED, HPT, TILE, THREADS, MINB, SUB>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {};  // the attribute is per device
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64 && !attr_set[dev]) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem > (size_t)116 * 1024 ? smem : (size_t)116 * 1024));
-    attr_set = true;
+    attr_set[dev] = true;
   }
   kern<<<dim3(gx, gy), THREADS, smem, s>>>(f.pk, f.npairs_pad, pairs_per_cta, fast, gen, slot_begin, slot_end, th.thr3d,
                                             votes, st, wl, g_nosync);
@@ -768,7 +772,16 @@ int launch_score_fast(int method, const FrameView& f, const HypGen* gen, const H
   if (!g_use_packed) {
     RPE_V(false, 2, 256, 256, 2, 8);
   }
-  switch (g_variant) {
+  // A slot range narrower than one 1024-hypothesis CTA column (hypothesis-sharded frames, short passes): use narrower
+  // CTAs and more of them per SM, so that the work shrinks with the range instead of idling half-empty threads.
+  int variant = g_variant;
+  if (variant == 14) {
+    const int nslots = slot_end - slot_begin;
+    if (nslots <= 128) variant = 16;
+    else if (nslots <= 256) variant = 7;
+    else if (nslots <= 512) variant = 1;
+  }
+  switch (variant) {
     default:
     case 0: RPE_V(true, 2, 256, 256, 2, 8); 
     case 1: RPE_V(true, 2, 512, 256, 2, 8); 
@@ -785,7 +798,8 @@ int launch_score_fast(int method, const FrameView& f, const HypGen* gen, const H
     case 12: RPE_V(true, 4, 512, 256, 2, 8); 
     case 13: RPE_V(true, 1, 512, 1024, 1, 8); 
     case 14: RPE_V(true, 2, 1024, 512, 1, 8); 
-    case 15: RPE_V(true, 2, 512, 512, 1, 16); break;
+    case 15: RPE_V(true, 2, 512, 512, 1, 16); 
+    case 16: RPE_V(true, 2, 256, 64, 8, 8); break;
   }
 #undef RPE_V
 }

@@ -65,3 +65,19 @@ def replay(votes: np.ndarray, method: int, n_corr: int, confidence: float, iter_
                 it = capi.update_num_iters(float(np.float32(confidence)), float(ep), K, it)
         ii += 1
     return win, best, it
+
+
+def peer_setup(dist, ctx, rank: int, world: int) -> None:
+    """Exchange the CUDA IPC handles of the contexts' vote-exchange blocks over any torch.distributed backend and map
+    every peer's block (one process per GPU of a node). Afterwards ``ctx.exchange_votes(b, e)`` moves vote slices
+    straight through peer memory."""
+    import torch
+    mine = torch.from_numpy(ctx.peer_export().copy())
+    if dist is None or world == 1:
+        ctx.peer_import(0, 1, mine.numpy())
+        return
+    backend = dist.get_backend()
+    dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+    parts = [torch.empty(64, dtype=torch.uint8, device=dev) for _ in range(world)]
+    dist.all_gather(parts, mine.to(dev))
+    ctx.peer_import(rank, world, torch.stack(parts).cpu().numpy())

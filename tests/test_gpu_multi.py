@@ -93,3 +93,26 @@ def test_contexts_sharing_the_scorer_lane_do_not_interfere(rpe, orc):
     finally:
         for c in ctxs:
             c.close()
+
+
+def test_peer_memory_exchange_two_processes(rpe):
+    """rpe_ransac_sharded with one process per GPU: CUDA IPC mappings of every rank's exchange block, vote slices written
+    straight into the peers' tables over NVLink by the exchange kernel. All ranks get the oracle's result."""
+    import json
+    import os
+    import subprocess
+    import sys
+    if _ngpu(rpe) < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29631", os.path.join(root, "tests", "_peer_worker.py")]
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
+    line = [l for l in p.stdout.splitlines() if l.startswith("PEER_RESULT ")]
+    assert p.returncode == 0 and line, p.stdout[-2000:] + p.stderr[-2000:]
+    ranks = json.loads(line[0][len("PEER_RESULT "):])
+    assert len(ranks) == 2
+    for a, b in zip(ranks[0]["results"], ranks[1]["results"]):
+        assert a["oracle_ok"]
+        for k in ("winner", "max_votes", "iter_final", "votes_crc"):
+            assert a[k] == b[k], k
