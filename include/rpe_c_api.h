@@ -199,6 +199,8 @@ int32_t* rpe_votes_device_ptr(rpe_ctx* ctx);
  * it once per frame. rpe_peer_status synchronises and reports a time-out. */
 int rpe_peer_export(rpe_ctx* ctx, unsigned char handle[64]);
 int rpe_peer_import(rpe_ctx* ctx, int rank, int world, const unsigned char* handles);
+/* contexts of one process (one per GPU): direct peer pointers instead of IPC; ctxs[rank] must be ctx itself */
+int rpe_peer_import_local(rpe_ctx* ctx, int rank, int world, rpe_ctx* const* ctxs);
 int rpe_exchange_votes(rpe_ctx* ctx, int slot_begin, int slot_end);
 int rpe_peer_status(rpe_ctx* ctx);
 /* rpe_ransac for one frame whose hypotheses are sharded over the ranks set up with rpe_peer_import: every rank holds the

@@ -115,6 +115,7 @@ _sig("rpe_sim_kinect_2d_3d_nl_device", C.c_int, [_vp, C.c_uint64, _vp, _vp, C.c_
 _sig("rpe_sim_kinect_2d_3d_nl", C.c_int, [C.c_uint64, _vp, _vp, C.c_int] + [C.c_float] * 8 + [_vp] * 6)
 _sig("rpe_peer_export", C.c_int, [_vp, _vp])
 _sig("rpe_peer_import", C.c_int, [_vp, C.c_int, C.c_int, _vp])
+_sig("rpe_peer_import_local", C.c_int, [_vp, C.c_int, C.c_int, _vp])
 _sig("rpe_exchange_votes", C.c_int, [_vp, C.c_int, C.c_int])
 _sig("rpe_peer_status", C.c_int, [_vp])
 _sig("rpe_ransac_sharded", C.c_int, [_vp, C.c_int, _vp, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float,
@@ -158,7 +159,7 @@ DECLARED_SYMBOLS = [
     "rpe_last_error", "rpe_stream", "rpe_sync", "rpe_launch_count", "rpe_host_alloc", "rpe_host_free", "rpe_upload",
     "rpe_upload_device", "rpe_num_correspondences", "rpe_ransac", "rpe_ransac_async", "rpe_ransac_stream", "rpe_upload_f64", "rpe_ransac_f64", "rpe_get_hypotheses_f64", "rpe_refit", "rpe_refit_async",
     "rpe_set_pose", "rpe_set_mask", "rpe_generate", "rpe_get_hypotheses", "rpe_set_hypotheses", "rpe_score",
-    "rpe_get_votes", "rpe_set_votes", "rpe_votes_device_ptr", "rpe_peer_export", "rpe_peer_import", "rpe_exchange_votes", "rpe_peer_status", "rpe_ransac_sharded", "rpe_ransac_sharded_async", "rpe_finish", "rpe_update_num_iters", "rpe_sample_table",
+    "rpe_get_votes", "rpe_set_votes", "rpe_votes_device_ptr", "rpe_peer_export", "rpe_peer_import", "rpe_peer_import_local", "rpe_exchange_votes", "rpe_peer_status", "rpe_ransac_sharded", "rpe_ransac_sharded_async", "rpe_finish", "rpe_update_num_iters", "rpe_sample_table",
     "rpe_prosac_table", "rpe_sim_pose", "rpe_sim_3d_3d", "rpe_sim_2d_3d", "rpe_sim_2d_3d_nl", "rpe_sim_kinect_2d_3d_nl", "rpe_sim_kinect_2d_3d_nl_device", "rpe_sim_3d_3d_device",
     "rpe_sim_2d_3d_nl_device", "rpe_download", "rpe_ao", "rpe_ao_ransac",
     "rpe_measure_ffma_tflops", "rpe_last_stage_ms", "rpe_enable_stage_timing",
@@ -490,6 +491,13 @@ class Context:
     def peer_import(self, rank, world, handles):
         handles = np.ascontiguousarray(handles, dtype=np.uint8).reshape(world, 64)
         _check(lib.rpe_peer_import(self._h, rank, world, _ptr(handles)), self._h)
+
+    @staticmethod
+    def peer_link_local(ctxs):
+        """Contexts of this process, one per GPU: link them for the hypothesis-sharded mode (no IPC)."""
+        arr = (C.c_void_p * len(ctxs))(*[c._h for c in ctxs])
+        for r, c in enumerate(ctxs):
+            _check(lib.rpe_peer_import_local(c._h, r, len(ctxs), arr), c._h)
 
     def exchange_votes(self, slot_begin, slot_end):
         _check(lib.rpe_exchange_votes(self._h, slot_begin, slot_end), self._h)

@@ -1250,6 +1250,36 @@ int rpe_peer_import(rpe_ctx* ctx, int rank, int world, const unsigned char* hand
   ctx->peer_epoch = 0;
   return RPE_OK;
 }
+// Same for contexts that live in ONE process (one per GPU): no IPC, the peers' blocks are addressed directly after
+// enabling peer access. With blocking calls a single host thread would wait for itself: use the _async entry points
+// (or one host thread per context).
+int rpe_peer_import_local(rpe_ctx* ctx, int rank, int world, rpe_ctx* const* ctxs) {
+  if (!ctx || !ctxs || world < 1 || world > kMaxPeers || rank < 0 || rank >= world || ctxs[rank] != ctx) return RPE_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  for (int r = 0; r < world; ++r) {
+    rpe_ctx* p = ctxs[r];
+    if (!p) return RPE_ERR_ARG;
+    if (!p->d_peer_block) {
+      unsigned char h[64];
+      const int rc = rpe_peer_export(p, h);
+      if (rc) return rc;
+      CK(cudaSetDevice(ctx->device));
+    }
+    if (p->device != ctx->device) {
+      int can = 0;
+      CK(cudaDeviceCanAccessPeer(&can, ctx->device, p->device));
+      if (!can) return fail(ctx, RPE_ERR_STATE, "no peer access between the two devices");
+      const cudaError_t e = cudaDeviceEnablePeerAccess(p->device, 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(ctx, RPE_ERR_CUDA, "cudaDeviceEnablePeerAccess", e);
+      (void)cudaGetLastError();
+    }
+    ctx->peers.block[r] = p->d_peer_block;
+  }
+  ctx->peer_rank = rank;
+  ctx->peer_world = world;
+  ctx->peer_epoch = 0;
+  return RPE_OK;
+}
 int rpe_exchange_votes(rpe_ctx* ctx, int slot_begin, int slot_end) {
   if (!ctx) return RPE_ERR_ARG;
   if (ctx->peer_world < 1) return fail(ctx, RPE_ERR_STATE, "call rpe_peer_import first");

@@ -95,6 +95,36 @@ def test_contexts_sharing_the_scorer_lane_do_not_interfere(rpe, orc):
             c.close()
 
 
+def test_peer_memory_exchange_one_process_two_gpus(rpe, orc):
+    """Two contexts of one process on two GPUs, linked with rpe_peer_import_local; frames enqueued asynchronously on
+    both before the host waits (a blocking call on one context would wait for a peer nobody has started)."""
+    if _ngpu(rpe) < 2:
+        pytest.skip("needs 2 GPUs")
+    orc.set_math_mode(orc.DET)
+    n, H = 20000, 1024
+    q, t = rpe.sim_pose(3)
+    Q, P, _ = rpe.sim_3d_3d(4, q, t, n)
+    S = rpe.sample_table(1, n, 3, H)
+    ref = orc.ransac(0, S, thr3d=0.25, confidence=0.9999, full=True, xc=P, xw=Q)
+    ctxs = [rpe.Context(0), rpe.Context(1)]
+    try:
+        rpe.Context.peer_link_local(ctxs)
+        for c in ctxs:
+            c.upload(xc=P, xw=Q)
+        for rep in range(3):
+            res = [c.ransac_sharded("shinji", S, thr3d=0.25, confidence=0.9999, blocking=False) for c in ctxs]
+            for c in ctxs:
+                c.sync()
+            for c, r in zip(ctxs, res):
+                assert (r.winner, r.max_votes, r.iter_final) == (ref["winner"], ref["max_votes"], ref["iter_final"])
+                assert np.array_equal(c.get_votes(H), ref["votes"])
+        for c in ctxs:
+            c.peer_status()
+    finally:
+        for c in ctxs:
+            c.close()
+
+
 def test_peer_memory_exchange_two_processes(rpe):
     """rpe_ransac_sharded with one process per GPU: CUDA IPC mappings of every rank's exchange block, vote slices written
     straight into the peers' tables over NVLink by the exchange kernel. All ranks get the oracle's result."""
