@@ -639,34 +639,52 @@ __device__ __forceinline__ void gn_point_rows(const double y[3], double J[3][6])
 }
 
 __device__ bool gn_solve(const double* Hu, const double* g, double mu, double* delta) {
+  // fully unrolled so that A and L stay in registers (the single-thread tail of the refinement is latency-bound)
   double A[6][6], L[6][6];
-  int k = 0;
-  for (int i = 0; i < 6; ++i)
-    for (int j = i; j < 6; ++j) {
-      A[i][j] = A[j][i] = Hu[k++];
-    }
+  {
+    int k = 0;
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+#pragma unroll
+      for (int j = i; j < 6; ++j) {
+        A[i][j] = A[j][i] = Hu[k++];
+      }
+  }
+#pragma unroll
   for (int i = 0; i < 6; ++i) A[i][i] += mu * A[i][i];
+#pragma unroll
   for (int i = 0; i < 6; ++i)
+#pragma unroll
     for (int j = 0; j < 6; ++j) L[i][j] = 0.0;
+  bool ok = true;
+#pragma unroll
   for (int j = 0; j < 6; ++j) {
     double s = A[j][j];
+#pragma unroll
     for (int p = 0; p < j; ++p) s -= L[j][p] * L[j][p];
-    if (!(s > 0.0)) return false;
+    if (!(s > 0.0)) ok = false;
     L[j][j] = sqrt(s);
+#pragma unroll
     for (int i = j + 1; i < 6; ++i) {
       double v = A[i][j];
+#pragma unroll
       for (int p = 0; p < j; ++p) v -= L[i][p] * L[j][p];
       L[i][j] = v / L[j][j];
     }
   }
+  if (!ok) return false;
   double z[6];
+#pragma unroll
   for (int i = 0; i < 6; ++i) {
     double v = -g[i];
+#pragma unroll
     for (int p = 0; p < i; ++p) v -= L[i][p] * z[p];
     z[i] = v / L[i][i];
   }
+#pragma unroll
   for (int i = 5; i >= 0; --i) {
     double v = z[i];
+#pragma unroll
     for (int p = i + 1; p < 6; ++p) v -= L[p][i] * delta[p];
     delta[i] = v / L[i][i];
   }

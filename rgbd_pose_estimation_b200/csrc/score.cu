@@ -781,25 +781,12 @@ int launch_score_fast(int method, const FrameView& f, const HypGen* gen, const H
     else if (nslots <= 256) variant = 7;
     else if (nslots <= 512) variant = 1;
   }
-  switch (variant) {
+  switch (variant) {  // (packed, hypotheses per thread, pairs per stage, threads, CTAs per SM, rescan group)
+    case 1: RPE_V(true, 2, 512, 256, 2, 8);   // <= 512 slots
+    case 7: RPE_V(true, 2, 256, 128, 4, 8);   // <= 256 slots
+    case 16: RPE_V(true, 2, 256, 64, 8, 8);   // <= 128 slots
     default:
-    case 0: RPE_V(true, 2, 256, 256, 2, 8); 
-    case 1: RPE_V(true, 2, 512, 256, 2, 8); 
-    case 2: RPE_V(true, 2, 256, 256, 3, 8); 
-    case 3: RPE_V(true, 4, 256, 128, 3, 8); 
-    case 4: RPE_V(true, 1, 256, 256, 4, 8); 
-    case 5: RPE_V(true, 2, 512, 512, 1, 8); 
-    case 6: RPE_V(true, 4, 256, 256, 1, 8); 
-    case 7: RPE_V(true, 2, 256, 128, 4, 8); 
-    case 8: RPE_V(true, 2, 256, 256, 2, 4); 
-    case 9: RPE_V(true, 4, 256, 128, 4, 8); 
-    case 10: RPE_V(true, 4, 256, 256, 2, 8); 
-    case 11: RPE_V(true, 3, 256, 128, 4, 8); 
-    case 12: RPE_V(true, 4, 512, 256, 2, 8); 
-    case 13: RPE_V(true, 1, 512, 1024, 1, 8); 
-    case 14: RPE_V(true, 2, 1024, 512, 1, 8); 
-    case 15: RPE_V(true, 2, 512, 512, 1, 16); 
-    case 16: RPE_V(true, 2, 256, 64, 8, 8); break;
+    case 14: RPE_V(true, 2, 1024, 512, 1, 8);  // the full 1024-hypothesis column (profiles/r01_variant_sweep.md)
   }
 #undef RPE_V
 }
