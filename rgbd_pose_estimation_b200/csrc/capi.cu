@@ -18,6 +18,7 @@
 
 namespace rpe {
 void set_use_packed(bool v);
+bool use_packed();
 void set_score_variant(int v);
 void set_nosync(int v);
 }
@@ -167,6 +168,13 @@ int check_arrays(rpe_ctx* ctx, int method) {
   return RPE_OK;
 }
 
+// The 3-D / 3-D scorer can stream x_w / x_c themselves when they are 16-byte aligned (bulk TMA); see score3d_raw_kernel.
+bool g_raw_tiles = true;  // test hook: false = always pack
+bool raw_tiles_ok(const rpe_ctx* c) {
+  return g_raw_tiles && use_packed() && c->view[A_XW] && c->view[A_XC] && (reinterpret_cast<uintptr_t>(c->view[A_XW]) & 15) == 0 &&
+         (reinterpret_cast<uintptr_t>(c->view[A_XC]) & 15) == 0;
+}
+
 FrameView make_view(const rpe_ctx* c) {
   FrameView f;
   f.bv = c->view[A_BV];
@@ -179,6 +187,11 @@ FrameView make_view(const rpe_ctx* c) {
   f.pk = c->d_pk;
   f.pk_kind = c->pk_kind;
   f.pk_f4_per_pair = c->pk_kind >= 0 ? f4_per_pair(c->pk_kind) : 0;
+  f.raw_ok = raw_tiles_ok(c);
+  if (c->pk_kind < 0) {  // nothing packed (raw-array scorer): the pair count still rounds up to whole rescan groups
+    const int npairs = (c->n + 1) / 2;
+    f.npairs_pad = ((npairs + kSubPairs - 1) / kSubPairs) * kSubPairs;
+  }
   return f;
 }
 
@@ -229,6 +242,7 @@ int ensure_hyp_capacity(rpe_ctx* ctx, int H, int slots) {
 
 int ensure_packed(rpe_ctx* ctx, int kind) {
   if (ctx->pk_kind == kind) return RPE_OK;
+  if (kind == kind_for_method(RPE_SHINJI) && raw_tiles_ok(ctx)) return RPE_OK;  // scored straight from the arrays
   const int npairs = (ctx->n + 1) / 2;
   const int npad = ((npairs + kSubPairs - 1) / kSubPairs) * kSubPairs;
   const size_t bytes = (size_t)npad * f4_per_pair(kind) * sizeof(float4);
@@ -1565,6 +1579,10 @@ int rpe_debug_set_worklist_capacity(rpe_ctx* ctx, unsigned int cap) {
   if (!ctx) return RPE_ERR_ARG;
   ctx->wl.capacity = cap < ctx->wl_allocated ? cap : ctx->wl_allocated;
   ctx->wl_fixed = cap < ctx->wl_allocated;
+  return RPE_OK;
+}
+int rpe_debug_set_raw_tiles(int v) {
+  g_raw_tiles = v != 0;
   return RPE_OK;
 }
 int rpe_debug_f64_exact_only(int v) {

@@ -20,6 +20,7 @@ struct FrameView {
   const float4* pk;    // packed pair records, `pk_f4_per_pair` float4 per pair
   int pk_f4_per_pair;  // 3 (AO) ...
   int pk_kind;         // which modalities are packed (bit0 2-D, bit1 3-D, bit2 normal)
+  bool raw_ok;         // 3-D / 3-D only: the tiled scorer streams xw / xc themselves (16-byte aligned), nothing is packed
 };
 
 struct Thresh {

@@ -431,6 +431,193 @@ score3d_fast_kernel(const float4* __restrict__ pk, int npairs_pad, int pairs_per
 }
 
 // ================================================================================================
+// the same scorer fed from the caller's arrays (no packed copy of the frame)
+// ================================================================================================
+// The 3-D / 3-D frame is two column-major 3 x n arrays, i.e. n contiguous xyz triples each. A stage is TILE pairs =
+// 2 TILE correspondences: two 1-D bulk TMA copies (24 TILE bytes each) land the raw triples in shared memory, the CTA
+// transposes them once into the pair-interleaved records the FFMA2 loop wants (x0 x1 y0 y1 | z0 z1 px0 px1 | py0 py1
+// pz0 pz1; 6 LDS.128 + 6 STS.128 per thread against ~40 000 instructions of scoring per stage) and takes the stage's
+// own magnitude bound max(|x_w| + |x_c|) on the way — the guard band then uses the bound of the correspondences it is
+// applied to instead of the frame maximum. No pack kernel, no second copy of the frame in HBM.
+// TMA needs 16-byte aligned addresses and sizes: stages start at multiples of 4 correspondences and copy a multiple
+// of 4; the last 0..3 correspondences of the frame are read from global memory by the transposing threads.
+template <int HPT, int TILE, int THREADS, int MINB, int SUB>
+__global__ void __launch_bounds__(THREADS, MINB)
+score3d_raw_kernel(const float* __restrict__ xw, const float* __restrict__ xc, int n, int npairs_pad, int pairs_per_cta,
+                   const HypFast* __restrict__ fast, const HypGen* __restrict__ gen, int slot_begin, int slot_end, float thr,
+                   int32_t* __restrict__ votes, FrameStats* __restrict__ st, Worklist wl) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  constexpr int kStageFloats = TILE * 2 * 3;  // floats of one array in one stage
+  float4* packed = reinterpret_cast<float4*>(smem_raw);                                  // [TILE * 3]
+  float* raw = reinterpret_cast<float*>(smem_raw + (size_t)TILE * 3 * sizeof(float4));    // [2 stages][xw | xc][kStageFloats]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(raw + 4 * kStageFloats);
+  unsigned int* mtile = reinterpret_cast<unsigned int*>(bars + 2);
+
+  const int tid = threadIdx.x;
+  const int p_begin = blockIdx.x * pairs_per_cta;
+  const int p_end = min(p_begin + pairs_per_cta, npairs_pad);
+  const int npairs = p_end - p_begin;
+  const int ntiles = (npairs + TILE - 1) / TILE;
+  WlSegment seg(wl);
+
+  HypRegs<true> hyp[HPT];
+  int slot[HPT];
+  int cnt[HPT];
+  float tnorm[HPT];
+#pragma unroll
+  for (int k = 0; k < HPT; ++k) {
+    slot[k] = slot_begin + (blockIdx.y * HPT + k) * THREADS + tid;
+    const bool live = slot[k] < slot_end && gen[slot[k]].valid != 0;
+    hyp[k].load(&fast[live ? slot[k] : slot_begin], live);
+    if (!live) slot[k] = -1;
+    cnt[k] = 0;
+    tnorm[k] = sqrtf(hyp[k].nt[0].x * hyp[k].nt[0].x + hyp[k].nt[1].x * hyp[k].nt[1].x + hyp[k].nt[2].x * hyp[k].nt[2].x);
+  }
+  const float thr2 = __fmul_rn(thr, thr);
+  const float2 nlo = make_float2(-thr2, -thr2);
+
+  // correspondences [c0, c0 + cnt4) of stage t go through TMA (cnt4 a multiple of 4, possibly 0)
+  auto stage_range = [&](int t, int& c0, int& cnt4) {
+    c0 = 2 * (p_begin + t * TILE);
+    const int tp = min(TILE, npairs - t * TILE);
+    int c = min(2 * tp, n - c0);
+    if (c < 0) c = 0;
+    cnt4 = c & ~3;
+  };
+  auto issue = [&](int t, int buf) {
+    int c0, cnt4;
+    stage_range(t, c0, cnt4);
+    const uint32_t bytes = (uint32_t)cnt4 * 12u;
+    mbar_expect_tx(&bars[buf], 2u * bytes);  // 0 bytes: the phase completes on this arrival alone
+    if (bytes) {
+      tma_load_1d(raw + (size_t)(2 * buf) * kStageFloats, xw + (size_t)c0 * 3, bytes, &bars[buf]);
+      tma_load_1d(raw + (size_t)(2 * buf + 1) * kStageFloats, xc + (size_t)c0 * 3, bytes, &bars[buf]);
+    }
+  };
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    mbar_fence_init();
+    mtile[0] = mtile[1] = 0u;
+  }
+  __syncthreads();
+  if (tid == 0)
+    for (int t = 0; t < 2 && t < ntiles; ++t) issue(t, t);
+
+  for (int t = 0; t < ntiles; ++t) {
+    const int buf = t & 1;
+    mbar_wait(&bars[buf], (uint32_t)((t >> 1) & 1));
+    const int tp = min(TILE, npairs - t * TILE);
+    int c0, cnt4;
+    stage_range(t, c0, cnt4);
+    // ---- transpose the stage: thread <-> 4 correspondences = 2 pair records; stage magnitude bound
+    const float* rw = raw + (size_t)(2 * buf) * kStageFloats;
+    const float* rc = raw + (size_t)(2 * buf + 1) * kStageFloats;
+    float mloc = 0.f;
+    for (int qd = tid; qd < (tp + 1) / 2; qd += THREADS) {
+      float w[12], c[12];
+      if (4 * qd + 4 <= cnt4) {
+        const float4* w4 = reinterpret_cast<const float4*>(rw + 12 * qd);
+        const float4* c4 = reinterpret_cast<const float4*>(rc + 12 * qd);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          const float4 a = w4[i], b = c4[i];
+          w[4 * i] = a.x; w[4 * i + 1] = a.y; w[4 * i + 2] = a.z; w[4 * i + 3] = a.w;
+          c[4 * i] = b.x; c[4 * i + 1] = b.y; c[4 * i + 2] = b.z; c[4 * i + 3] = b.w;
+        }
+      } else {  // frame tail (or padding): element-wise, from global memory, NaN beyond the last correspondence
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int ci = c0 + 4 * qd + j;
+#pragma unroll
+          for (int r = 0; r < 3; ++r) {
+            w[3 * j + r] = ci < n ? xw[(size_t)ci * 3 + r] : CUDART_NAN_F;
+            c[3 * j + r] = ci < n ? xc[(size_t)ci * 3 + r] : CUDART_NAN_F;
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float m = sqrtf(w[3 * j] * w[3 * j] + w[3 * j + 1] * w[3 * j + 1] + w[3 * j + 2] * w[3 * j + 2]);
+        const float mc = sqrtf(c[3 * j] * c[3 * j] + c[3 * j + 1] * c[3 * j + 1] + c[3 * j + 2] * c[3 * j + 2]);
+        if (mc == mc && mc < CUDART_INF_F) m += mc;
+        if (m == m && m < CUDART_INF_F) mloc = fmaxf(mloc, m);
+      }
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {  // pair 2 qd + h = correspondences 4 qd + 2h, 4 qd + 2h + 1
+        const int pr = 2 * qd + h;
+        if (pr < tp) {
+          const float* a = w + 6 * h;
+          const float* b = c + 6 * h;
+          packed[pr * 3 + 0] = make_float4(a[0], a[3], a[1], a[4]);
+          packed[pr * 3 + 1] = make_float4(a[2], a[5], b[0], b[3]);
+          packed[pr * 3 + 2] = make_float4(b[1], b[4], b[2], b[5]);
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mloc = fmaxf(mloc, __shfl_xor_sync(0xffffffffu, mloc, o));
+    if ((tid & 31) == 0 && mloc > 0.f) atomicMax(&mtile[buf], __float_as_uint(mloc));
+    __syncthreads();  // records + bound complete; raw[buf] is free
+    if (tid == 0) {
+      if (t + 2 < ntiles) issue(t + 2, buf);
+      mtile[buf ^ 1] = 0u;  // the next stage's slot: untouched until everybody has passed the barrier below
+    }
+    const float mcorr = __uint_as_float(mtile[buf]);
+    float band[HPT];
+#pragma unroll
+    for (int k = 0; k < HPT; ++k) band[k] = guard_band_3d((mcorr + tnorm[k]) * 1.0001f, thr);  // NaN for a dead slot
+
+    const float4* sp = packed;
+    for (int sub = 0; sub < tp; sub += SUB) {
+      float smin[HPT];
+#pragma unroll
+      for (int k = 0; k < HPT; ++k) smin[k] = CUDART_INF_F;
+#pragma unroll
+      for (int pp = 0; pp < SUB; ++pp) {
+        const float4 a = sp[(sub + pp) * 3 + 0];
+        const float4 b = sp[(sub + pp) * 3 + 1];
+        const float4 c = sp[(sub + pp) * 3 + 2];
+#pragma unroll
+        for (int k = 0; k < HPT; ++k) {
+          const float2 s = hyp[k].eval(a, b, c, nlo);
+          cnt[k] += (int)(__float_as_uint(s.x) >> 31) + (int)(__float_as_uint(s.y) >> 31);
+          smin[k] = fminf(fminf(smin[k], fabsf(s.x)), fabsf(s.y));
+        }
+      }
+      bool any = false;
+#pragma unroll
+      for (int k = 0; k < HPT; ++k) any = any || (smin[k] <= band[k]);
+      if (any) {
+        for (int pp = 0; pp < SUB; ++pp) {
+          const float4 a = sp[(sub + pp) * 3 + 0];
+          const float4 b = sp[(sub + pp) * 3 + 1];
+          const float4 c = sp[(sub + pp) * 3 + 2];
+#pragma unroll
+          for (int k = 0; k < HPT; ++k) {
+            const float2 s = hyp[k].eval(a, b, c, nlo);
+            const float sv[2] = {s.x, s.y};
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              if (fabsf(sv[u]) <= band[k]) {
+                cnt[k] -= (int)(__float_as_uint(sv[u]) >> 31);
+                const unsigned int corr = (unsigned int)(2 * (p_begin + t * TILE + sub + pp) + u);
+                seg.push(make_uint2((unsigned int)slot[k], corr | (1u << 30)), st);
+              }
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();  // everybody is done with the records (and has read the bound) before the next transpose
+  }
+#pragma unroll
+  for (int k = 0; k < HPT; ++k)
+    if (slot[k] >= 0 && cnt[k] != 0) atomicAdd(&votes[slot[k]], cnt[k]);
+  seg.publish(wl, st);
+}
+
+// ================================================================================================
 // fast tiled scorer — 2-D, 3-D and normal modalities in any combination (all other estimator families)
 // ================================================================================================
 // Shared per (pair, hypothesis): ny = -(R x_w + t) = nR x_w + nt (9 FFMA2). Then
@@ -717,6 +904,7 @@ static int g_nosync = 0;
 void set_nosync(int v) { g_nosync = v; }
 static int g_variant = 14;  // HPT=2, 1024-pair stages, 512 threads, 1 CTA per SM (best of the sweep in profiles/r01_variant_sweep.md)
 void set_use_packed(bool v) { g_use_packed = v; }
+bool use_packed() { return g_use_packed; }
 void set_score_variant(int v) { g_variant = v; }
 
 // RPE_SCORER_SHARED_SM=1 in the environment lets two scorer CTAs share an SM (measurement aid)
@@ -741,10 +929,24 @@ static int launch_variant(const FrameView& f, const HypGen* gen, const HypFast* 
   // second context's scorer queues behind this one instead of time-slicing the same FMA pipe (same throughput,
   // twice the latency per launch); the small kernels of other frames still co-run in the remaining space.
   if (MINB == 1 && g_exclusive_sm && smem < (size_t)116 * 1024) smem = (size_t)116 * 1024;
-  auto kern = score3d_fast_kernel<PACKED, HPT, TILE, THREADS, MINB, SUB>;
-  static bool attr_set[64] = {};  // the attribute is per device
   int dev = 0;
   cudaGetDevice(&dev);
+  if (PACKED && f.raw_ok) {  // stream the caller's arrays: no packed copy
+    constexpr int RT = (TILE > 1024 / MINB ? 1024 / MINB : TILE);  // 144 bytes of shared memory per pair and CTA
+    auto rk = score3d_raw_kernel<HPT, RT, THREADS, MINB, SUB>;
+    size_t rsmem = (size_t)RT * 3 * sizeof(float4) + 4 * (size_t)RT * 6 * sizeof(float) + 2 * sizeof(uint64_t) + 16;
+    if (MINB == 1 && g_exclusive_sm && rsmem < (size_t)116 * 1024) rsmem = (size_t)116 * 1024;
+    static bool rattr_set[64] = {};
+    if (dev >= 0 && dev < 64 && !rattr_set[dev]) {
+      cudaFuncSetAttribute(rk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem);
+      rattr_set[dev] = true;
+    }
+    rk<<<dim3(gx, gy), THREADS, rsmem, s>>>(f.xw, f.xc, f.n, f.npairs_pad, pairs_per_cta, fast, gen, slot_begin, slot_end,
+                                            th.thr3d, votes, st, wl);
+    return gx * gy;
+  }
+  auto kern = score3d_fast_kernel<PACKED, HPT, TILE, THREADS, MINB, SUB>;
+  static bool attr_set[64] = {};  // the attribute is per device
   if (dev >= 0 && dev < 64 && !attr_set[dev]) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem > (size_t)116 * 1024 ? smem : (size_t)116 * 1024));
     attr_set[dev] = true;

@@ -304,3 +304,52 @@ def test_c_abi_error_behaviour(rpe):
         r = ctx.ransac("shinji", S, thr3d=0.25, confidence=0.99)
         assert r["winner"] >= 0 and r["max_votes"] > 10
     assert rpe.lib.rpe_ransac(None, 0, None, 0, 0.0, 0.0, 0.0, 0.0, None, None) != 0
+
+
+@pytest.mark.parametrize("n", [2, 3, 5, 37, 1001, 4098, 20003])
+def test_raw_array_scorer_matches_packed_and_oracle(rpe, orc, gpu_ctx, n):
+    """The 3-D / 3-D scorer streams the caller's arrays through bulk TMA (no packed copy) when they are 16-byte
+    aligned; ragged sizes exercise the 0..3-correspondence tail that bypasses TMA. Same votes as the packed path."""
+    orc.set_math_mode(orc.DET)
+    H = 200
+    q, t, Q, P = _frame(rpe, 300 + n, max(n, 3))
+    Q, P = Q[:n].copy(), P[:n].copy()
+    if n > 10:
+        P[n // 2] = np.nan            # an invalid camera point
+        Q[n // 3, 1] = np.float32(3e4)  # a far-away world point widens that stage's guard band only
+    rng = np.random.default_rng(n)
+    S = np.stack([rng.choice(n, 3, replace=n < 3) if n >= 3 else rng.integers(0, n, 3) for _ in range(H)]).astype(np.int32)
+    S = np.concatenate([S, -np.ones((H, 1), np.int32)], axis=1)
+    ref = orc.ransac(SHINJI, S, thr3d=0.25, confidence=0.9999, full=True, xc=P, xw=Q)
+    out = {}
+    for raw in (1, 0):
+        rpe.lib.rpe_debug_set_raw_tiles(raw)
+        gpu_ctx.upload(xc=P, xw=Q)
+        got = gpu_ctx.ransac(SHINJI, S, thr3d=0.25, confidence=0.9999)
+        out[raw] = (gpu_ctx.get_votes(H).copy(), got)
+    rpe.lib.rpe_debug_set_raw_tiles(1)
+    for raw in (1, 0):
+        votes, got = out[raw]
+        assert np.array_equal(votes, ref["votes"]), raw
+        assert (got["winner"], got["max_votes"], got["iter_final"]) == (ref["winner"], ref["max_votes"], ref["iter_final"])
+        assert np.array_equal(got["mask"], ref["mask"])
+
+
+def test_misaligned_device_arrays_fall_back_to_the_packed_path(rpe, orc):
+    import torch
+    orc.set_math_mode(orc.DET)
+    n, H = 5000, 128
+    q, t, Q, P = _frame(rpe, 55, n)
+    S = rpe.sample_table(55, n, 3, H)
+    ref = orc.ransac(SHINJI, S, thr3d=0.25, confidence=0.9999, full=True, xc=P, xw=Q)
+    dev = torch.device("cuda", 0)
+    buf_w = torch.zeros(3 * n + 1, dtype=torch.float32, device=dev)
+    buf_c = torch.zeros(3 * n + 1, dtype=torch.float32, device=dev)
+    buf_w[1:] = torch.from_numpy(Q.reshape(-1)).to(dev)   # 4-byte offset: not 16-byte aligned
+    buf_c[1:] = torch.from_numpy(P.reshape(-1)).to(dev)
+    torch.cuda.synchronize()
+    with rpe.Context(0) as ctx:
+        ctx.upload_device(n, xc=buf_c.data_ptr() + 4, xw=buf_w.data_ptr() + 4)
+        got = ctx.ransac(SHINJI, S, thr3d=0.25, confidence=0.9999)
+        assert np.array_equal(ctx.get_votes(H), ref["votes"])
+        assert np.array_equal(got["mask"], ref["mask"])
