@@ -197,7 +197,7 @@ def workload_config(args, world):
         "n_correspondences": N_CORR, "n_hypotheses": N_HYP, "outlier_ratio": OUTLIER, "noise_m": NOISE,
         "thr3d_m": THR3D, "confidence": CONF, "frames_per_step_per_gpu": args.frames_per_step,
         "distinct_frames_per_gpu": args.ring, "contexts_per_gpu": args.contexts, "gn_max_iters": args.gn_iters,
-        "l2_policy": f"inputs larger than L2: ring of {args.ring} distinct frames x 7.4 MB raw (+7.4 MB packed) per GPU",
+        "l2_policy": f"inputs larger than L2: ring of {args.ring} distinct frames x 7.4 MB per GPU (scored straight from these arrays)",
         "parallelism": f"frames sharded over {world} GPU(s), no data-path collective",
     }
 
