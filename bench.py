@@ -407,7 +407,7 @@ def run_gpu(args, rank, world, local_rank):
         hbm_peak = peaks["hbm_gbs"] if peaks else 6650.0
         alg_bytes = BYTES_PER_CORR * N_CORR  # compulsory: every correspondence read once
         roofline = {
-            "bound": "fp32", "kernel": "score3d_fast_kernel", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+            "bound": "fp32", "kernel": "score3d_raw_kernel", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
             "frac": achieved / peak if peak > 0 else None,
             "peak_source": "FFMA/FFMA2 microbenchmark measured in this run (MEASURED_PEAKS.json has no FP32 CUDA-core figure)",
             "frac_of_nominal": achieved / NOMINAL_FP32_TFLOPS, "nominal_peak": NOMINAL_FP32_TFLOPS,
