@@ -438,10 +438,10 @@ int score_range(rpe_ctx* ctx, int method, int slot_begin, int slot_end, Thresh t
       if (tm) cudaEventRecord(ctx->ev_fast[1], ctx->stream);
     }
     if (tm) ctx->ev_fast_recorded = true;
-    launch_fixup(method, f, ctx->d_gen, th, ctx->d_votes, ctx->d_stats, ctx->wl, nseg, ctx->num_sms, ctx->stream);
+    launch_fixup(method, f, ctx->d_gen, th, ctx->d_votes, ctx->d_stats, ctx->wl, nseg, slot_begin, slot_end, ctx->stream);
     launch_score_exact(method, f, ctx->d_gen, slot_begin, slot_end, th, ctx->d_votes, ctx->d_stats, true, ctx->num_sms,
                        ctx->stream);
-    ctx->launches += 4;
+    ctx->launches += 3;
   } else {
     launch_score_exact(method, f, ctx->d_gen, slot_begin, slot_end, th, ctx->d_votes, ctx->d_stats, false, ctx->num_sms,
                        ctx->stream);
@@ -654,8 +654,6 @@ int do_ransac(rpe_ctx* ctx, int method, const int32_t* samples, rpe_sample_fn fn
     launch_reset_stats(ctx->d_stats, ctx->stream);
     ctx->launches++;
   }
-  launch_replay_begin(ctx->d_rs, H, ctx->stream);
-  ctx->launches++;
   if (method == RPE_SHINJI || !g_force_exact_multi) {
     rc = ensure_packed(ctx, kind_for_method(method));
     if (rc) return rc;
@@ -685,7 +683,7 @@ int do_ransac(rpe_ctx* ctx, int method, const int32_t* samples, rpe_sample_fn fn
     if (rc) return rc;
     if (base == 0) stamp(ctx, ST_REPLAY);
     launch_replay(method, ctx->d_gen, ctx->d_votes, hc, base, ctx->n, confidence, ctx->d_stats, ctx->d_rs, ctx->d_pose,
-                  single, ctx->stream);
+                  single, base == 0 ? H : -1, ctx->stream);
     ctx->launches++;
     ctx->stats_clean = true;
     if (!single) {
@@ -695,7 +693,7 @@ int do_ransac(rpe_ctx* ctx, int method, const int32_t* samples, rpe_sample_fn fn
       const bool last = ctx->h_rs->stop != 0 || base + hc >= H;
       if (last) {
         launch_replay(method, ctx->d_gen, ctx->d_votes, 0, base + hc, ctx->n, confidence, ctx->d_stats, ctx->d_rs,
-                      ctx->d_pose, true, ctx->stream);
+                      ctx->d_pose, true, -1, ctx->stream);
         ctx->launches++;
         break;
       }
@@ -1326,8 +1324,6 @@ static int do_ransac_sharded(rpe_ctx* ctx, int method, const int32_t* samples, i
     launch_reset_stats(ctx->d_stats, ctx->stream);
     ctx->launches++;
   }
-  launch_replay_begin(ctx->d_rs, H, ctx->stream);
-  ctx->launches++;
   rc = ensure_packed(ctx, kind_for_method(method));
   if (rc) return rc;
   CK(cudaMemcpyAsync(ctx->d_samples, samples, (size_t)H * 4 * sizeof(int32_t), cudaMemcpyDefault, ctx->stream));
@@ -1344,7 +1340,7 @@ static int do_ransac_sharded(rpe_ctx* ctx, int method, const int32_t* samples, i
   if (rc) return rc;
   ctx->peer_epoch += 1;
   launch_exchange_votes(ctx->peers, r, G, ctx->peer_epoch, sb, se, n_slots, ctx->d_votes, ctx->stream);
-  launch_replay(method, ctx->d_gen, ctx->d_votes, H, 0, ctx->n, confidence, ctx->d_stats, ctx->d_rs, ctx->d_pose, true,
+  launch_replay(method, ctx->d_gen, ctx->d_votes, H, 0, ctx->n, confidence, ctx->d_stats, ctx->d_rs, ctx->d_pose, true, H,
                 ctx->stream);
   ctx->launches += 2;
   ctx->stats_clean = true;
@@ -1374,10 +1370,9 @@ int rpe_finish(rpe_ctx* ctx, int method, int H, float thr3d, float cos_thr2d, fl
     return fail(ctx, RPE_ERR_ARG, "bad argument to rpe_finish");
   CK(cudaSetDevice(ctx->device));
   const Thresh th = {thr3d, cos_thr2d, cos_thrN};
-  launch_replay_begin(ctx->d_rs, H, ctx->stream);
-  launch_replay(method, ctx->d_gen, ctx->d_votes, H, 0, ctx->n, confidence, ctx->d_stats, ctx->d_rs, ctx->d_pose, true,
+  launch_replay(method, ctx->d_gen, ctx->d_votes, H, 0, ctx->n, confidence, ctx->d_stats, ctx->d_rs, ctx->d_pose, true, H,
                 ctx->stream);
-  ctx->launches += 2;
+  ctx->launches += 1;
   ctx->stats_clean = true;
   return do_finish(ctx, method, th, out, mask, true);
 }

@@ -55,7 +55,7 @@ void launch_derive_fast(const HypGen* gen, HypFast* fast, int32_t* votes, int n_
 int launch_score_fast(int method, const FrameView& f, const HypGen* gen, const HypFast* fast, int slot_begin,
                        int slot_end, Thresh th, int32_t* votes, FrameStats* st, Worklist wl, int num_sms, cudaStream_t s);
 void launch_fixup(int method, const FrameView& f, const HypGen* gen, Thresh th, int32_t* votes, FrameStats* st,
-                  Worklist wl, int nseg, int num_sms, cudaStream_t s);
+                  Worklist wl, int nseg, int slot_begin, int slot_end, cudaStream_t s);
 void launch_consume_worklist(FrameStats* st, cudaStream_t s);
 // exact-order scoring of every (slot, correspondence); `only_if_overflow` makes it a no-op unless
 // the fast pass overflowed its worklist.
@@ -64,10 +64,10 @@ void launch_score_exact(int method, const FrameView& f, const HypGen* gen, int s
 
 // -- replay / mask / refit --------------------------------------------------------------------------
 // Replay of the sequential rule over the iterations [iter_base, iter_base+H) held in gen/votes; the state is
-// carried in `rs` (launch_replay_begin resets it). The kernel also clears the per-pass FrameStats counters.
-void launch_replay_begin(ReplayState* rs, int iter_max, cudaStream_t s);
+// carried in `rs`; begin_iter_max >= 0 (the frame's first pass) resets it to the loop's initial state with Iter =
+// begin_iter_max. The kernel also clears the per-pass FrameStats counters.
 void launch_replay(int method, const HypGen* gen, const int32_t* votes, int H, int iter_base, int n, float confidence,
-                   FrameStats* st, ReplayState* rs, ReplayOut* out, bool finalize, cudaStream_t s);
+                   FrameStats* st, ReplayState* rs, ReplayOut* out, bool finalize, int begin_iter_max, cudaStream_t s);
 
 struct RefitBuffers {
   double* partials = nullptr;   // [blocks x kMomentCount]

@@ -161,7 +161,7 @@ constexpr int kReplayChunk = 4096;  // vote-table entries staged in shared memor
 __global__ void __launch_bounds__(256)
 replay_kernel(int method, const HypGen* __restrict__ gen, const int32_t* __restrict__ votes, int H, int iter_base, int n,
               float confidence, FrameStats* __restrict__ st, ReplayState* __restrict__ rs, ReplayOut* __restrict__ out,
-              int finalize) {
+              int finalize, int begin_iter_max) {
   __shared__ int32_t sv[kReplayChunk];
   __shared__ int s_state[5];  // best, Iter, win, cur_iter, stop
   const int lane = threadIdx.x & 31;
@@ -171,6 +171,19 @@ replay_kernel(int method, const HypGen* __restrict__ gen, const int32_t* __restr
   const int E = H * S;
   const int slot_base = iter_base * S;
   if (threadIdx.x == 0) {
+    if (begin_iter_max >= 0) {  // first pass of a frame: the state the reference's loop starts from
+      rs->best = -1;  // setMaxVotes(-1)
+      rs->iter = begin_iter_max;
+      rs->win = -1;
+      rs->cur_iter = -1;
+      rs->stop = 0;
+      rs->slots_done = 0;
+      rs->borderline = 0;
+      rs->overflow = 0;
+      rs->q[0] = rs->q[1] = rs->q[2] = 0.f;
+      rs->q[3] = 1.f;
+      rs->t[0] = rs->t[1] = rs->t[2] = 0.f;
+    }
     s_state[0] = rs->best;
     s_state[1] = rs->iter;
     s_state[2] = rs->win;
@@ -281,25 +294,10 @@ replay_kernel(int method, const HypGen* __restrict__ gen, const int32_t* __restr
   }
 }
 
-__global__ void replay_begin_kernel(ReplayState* rs, int iter_max) {
-  if (threadIdx.x != 0) return;
-  rs->best = -1;  // setMaxVotes(-1)
-  rs->iter = iter_max;
-  rs->win = -1;
-  rs->cur_iter = -1;
-  rs->stop = 0;
-  rs->slots_done = 0;
-  rs->borderline = 0;
-  rs->overflow = 0;
-  rs->q[0] = rs->q[1] = rs->q[2] = 0.f;
-  rs->q[3] = 1.f;
-  rs->t[0] = rs->t[1] = rs->t[2] = 0.f;
-}
-void launch_replay_begin(ReplayState* rs, int iter_max, cudaStream_t s) { replay_begin_kernel<<<1, 32, 0, s>>>(rs, iter_max); }
-
 void launch_replay(int method, const HypGen* gen, const int32_t* votes, int H, int iter_base, int n, float confidence,
-                   FrameStats* st, ReplayState* rs, ReplayOut* out, bool finalize, cudaStream_t s) {
-  replay_kernel<<<1, 256, 0, s>>>(method, gen, votes, H, iter_base, n, confidence, st, rs, out, finalize ? 1 : 0);
+                   FrameStats* st, ReplayState* rs, ReplayOut* out, bool finalize, int begin_iter_max, cudaStream_t s) {
+  replay_kernel<<<1, 256, 0, s>>>(method, gen, votes, H, iter_base, n, confidence, st, rs, out, finalize ? 1 : 0,
+                                  begin_iter_max);
 }
 
 // ================================================================================================

@@ -1014,8 +1014,14 @@ __device__ __forceinline__ bool exact_eval(int method, int modality, const Frame
 constexpr int kFixupChunks = 4;  // CTAs per worklist segment
 __global__ void __launch_bounds__(256)
 fixup_kernel(int method, FrameView f, const HypGen* __restrict__ gen, Thresh th, int32_t* __restrict__ votes,
-             const FrameStats* __restrict__ st, Worklist wl, int nseg) {
-  if (st->wl_overflow) return;  // the whole frame is rescored exactly instead
+             const FrameStats* __restrict__ st, Worklist wl, int nseg, int slot_begin, int slot_end) {
+  if (st->wl_overflow) {
+    // the slot range is rescored exactly by the kernel that follows: hand it a clean vote table
+    const int nthreads = gridDim.x * gridDim.y * blockDim.x;
+    const int me = (blockIdx.y * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x;
+    for (int sidx = slot_begin + me; sidx < slot_end; sidx += nthreads) votes[sidx] = gen[sidx].valid ? 0 : -1;
+    return;
+  }
   const unsigned int cap = wl.capacity / (unsigned int)nseg;
   const unsigned int count = min(wl.counts[blockIdx.x], cap);
   const uint2* seg = wl.entries + (size_t)blockIdx.x * cap;
@@ -1042,10 +1048,9 @@ __global__ void consume_worklist_kernel(FrameStats* st) {
 void launch_consume_worklist(FrameStats* st, cudaStream_t s) { consume_worklist_kernel<<<1, 32, 0, s>>>(st); }
 
 void launch_fixup(int method, const FrameView& f, const HypGen* gen, Thresh th, int32_t* votes, FrameStats* st,
-                  Worklist wl, int nseg, int num_sms, cudaStream_t s) {
-  (void)num_sms;
+                  Worklist wl, int nseg, int slot_begin, int slot_end, cudaStream_t s) {
   if (nseg <= 0) return;
-  fixup_kernel<<<dim3(nseg, kFixupChunks), 256, 0, s>>>(method, f, gen, th, votes, st, wl, nseg);
+  fixup_kernel<<<dim3(nseg, kFixupChunks), 256, 0, s>>>(method, f, gen, th, votes, st, wl, nseg, slot_begin, slot_end);
 }
 
 // Whole-frame exact scoring. Thread <-> slot, CTA column <-> correspondence slice; every lane reads the
@@ -1088,7 +1093,8 @@ void launch_score_exact(int method, const FrameView& f, const HypGen* gen, int s
                         int32_t* votes, FrameStats* st, bool only_if_overflow, int num_sms, cudaStream_t s) {
   const int nslots = slot_end - slot_begin;
   if (nslots <= 0 || f.n <= 0) return;
-  zero_votes_if_overflow_kernel<<<4, 256, 0, s>>>(gen, slot_begin, slot_end, votes, st, only_if_overflow ? 1 : 0);
+  // after a fast pass the fix-up kernel has already cleaned the vote table when the worklist overflowed
+  if (!only_if_overflow) zero_votes_if_overflow_kernel<<<4, 256, 0, s>>>(gen, slot_begin, slot_end, votes, st, 0);
   const int threads = 128;
   const int gy = (nslots + threads - 1) / threads;
   int gx = (4 * num_sms + gy - 1) / gy;
