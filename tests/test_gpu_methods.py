@@ -267,3 +267,37 @@ def test_many_borderline_2d_evaluations_stay_exact(rpe, orc):
             assert np.array_equal(got["mask"], ref["mask"])
         assert got["n_borderline"] > 50000
         assert got["flags"] == 0  # by now the worklist holds them all
+
+
+def test_gpu_against_committed_golden_vectors(rpe, gpu_ctx):
+    """The CUDA path against tests/golden/oracle_golden.json directly (no oracle at run time): all seven families in
+    binary32, two families in binary64."""
+    import json
+    import os
+    g = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "oracle_golden.json")))
+    for case in g["ransac"]:
+        q, t = rpe.sim_pose(case["pose_seed"])
+        d = rpe.sim_2d_3d_nl(case["data_seed"], q, t, case["n"])
+        arrs = {k: d[k] for k in ("bv", "xc", "nc", "xw", "nw")}
+        S = rpe.sample_table(case["sample_seed"], case["n"], 3 if case["method"] == 0 else 4, case["H"])
+        gpu_ctx.upload(**arrs)
+        r = gpu_ctx.ransac(case["method"], S, thr3d=case["thr3d"], cos_thr2d=case["cos_thr"], cos_thrN=case["cos_nl"],
+                           confidence=case["confidence"])
+        slots = case["H"] * rpe.method_slots(case["method"])
+        assert [r["winner"], r["max_votes"], r["iter_final"]] == case["expect"][:3], case["method"]
+        assert int(gpu_ctx.get_votes(slots).astype(np.int64).sum()) == case["expect"][3]
+        assert [int(v) for v in r["mask"].sum(axis=1)] == case["expect_mask_sums"]
+        assert r["q"].view(np.uint32).tolist() == case["q_bits"]
+    for case in g["ransac_f64"]:
+        q, t = rpe.sim_pose(case["pose_seed"])
+        d = rpe.sim_2d_3d_nl(case["data_seed"], q, t, case["n"])
+        arrs = {k: d[k].astype(np.float64) for k in ("bv", "xc", "nc", "xw", "nw")}
+        S = rpe.sample_table(case["sample_seed"], case["n"], 3 if case["method"] == 0 else 4, case["H"])
+        gpu_ctx.upload_f64(**arrs)
+        r = gpu_ctx.ransac_f64(case["method"], S, thr3d=case["thr3d"], cos_thr2d=case["cos_thr"], cos_thrN=case["cos_nl"],
+                               confidence=case["confidence"])
+        slots = case["H"] * rpe.method_slots(case["method"])
+        assert [r["winner"], r["max_votes"], r["iter_final"]] == case["expect"][:3], case["method"]
+        assert int(gpu_ctx.get_votes(slots).astype(np.int64).sum()) == case["expect"][3]
+        assert [int(v) for v in r["mask"].sum(axis=1)] == case["expect_mask_sums"]
+        assert [str(v) for v in r["qd"].view(np.uint64).tolist()] == case["q_bits"]
