@@ -353,3 +353,53 @@ def test_misaligned_device_arrays_fall_back_to_the_packed_path(rpe, orc):
         got = ctx.ransac(SHINJI, S, thr3d=0.25, confidence=0.9999)
         assert np.array_equal(ctx.get_votes(H), ref["votes"])
         assert np.array_equal(got["mask"], ref["mask"])
+
+
+def test_full_size_frame_properties(rpe, orc, gpu_ctx):
+    """BASELINE config #4 at full size (307 200 correspondences x 1 024 hypotheses), checked through properties that do
+    not need the CPU oracle to run 3e8 evaluations:
+      * the tiled scorer's vote table equals the exact-order kernel's (same device, independent code path: the
+        worklist is shrunk to nothing, every borderline evaluation overflows it, the frame is rescored exactly);
+      * vote counts are invariant under a permutation of the correspondences (with the sample indices remapped);
+      * the winner's vote count equals the number of set flags in its mask; the replayed Iter matches the host rule;
+      * the oracle agrees on a sample of 24 hypotheses."""
+    import ctypes
+    from rgbd_pose_estimation_b200 import sharding
+    orc.set_math_mode(orc.DET)
+    n, H = 307200, 1024
+    q, t, Q, P = _frame(rpe, 4242, n)
+    S = rpe.sample_table(4242, n, 3, H)
+    gpu_ctx.upload(xc=P, xw=Q)
+    got = gpu_ctx.ransac(SHINJI, S, thr3d=0.25, confidence=0.9999)
+    votes = gpu_ctx.get_votes(H).copy()
+    assert got["flags"] == 0 and got["n_slots"] == H
+    assert got["max_votes"] == int(votes.max()) == int(got["mask"][1].sum()) == got["n_inliers"][1]
+    win, best, it = sharding.replay(votes, 0, n, 0.9999)
+    assert (win, best, it) == (got["winner"], got["max_votes"], got["iter_final"])
+    # exact-order kernel on the same frame
+    gpu_ctx.generate(SHINJI, S)
+    hyps, valid = gpu_ctx.get_hypotheses(H)
+    for k in range(0, H, 43):  # 24 hypotheses through the oracle, one at a time
+        if valid[k]:
+            v, _ = orc.score(SHINJI, hyps[k, :4], hyps[k, 4:], thr3d=0.25, xc=P, xw=Q)
+            assert int(v) == int(votes[k]), k
+    # the exact-order kernel scores the whole frame (worklist capacity 0 forces the overflow -> exact path)
+    rpe.lib.rpe_debug_set_worklist_capacity.argtypes = [ctypes.c_void_p, ctypes.c_uint]
+    rpe.lib.rpe_debug_set_worklist_capacity(gpu_ctx.handle, 0)
+    got_exact = gpu_ctx.ransac(SHINJI, S, thr3d=0.25, confidence=0.9999)
+    rpe.lib.rpe_debug_set_worklist_capacity(gpu_ctx.handle, 1 << 30)
+    assert got_exact["flags"] & 1
+    assert np.array_equal(gpu_ctx.get_votes(H), votes)
+    assert np.array_equal(got_exact["mask"], got["mask"])
+    # permutation invariance
+    rng = np.random.default_rng(7)
+    perm = rng.permutation(n)
+    inv = np.empty(n, np.int64)
+    inv[perm] = np.arange(n)
+    S2 = S.copy()
+    S2[:, :3] = inv[S[:, :3]]
+    gpu_ctx.upload(xc=np.ascontiguousarray(P[perm]), xw=np.ascontiguousarray(Q[perm]))
+    got2 = gpu_ctx.ransac(SHINJI, S2, thr3d=0.25, confidence=0.9999)
+    assert np.array_equal(gpu_ctx.get_votes(H), votes)
+    assert (got2["winner"], got2["max_votes"], got2["iter_final"]) == (got["winner"], got["max_votes"], got["iter_final"])
+    assert np.array_equal(got2["mask"][1][inv], got["mask"][1])
