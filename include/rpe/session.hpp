@@ -25,6 +25,9 @@ class Session {
   explicit Session(int device = 0) : ctx_(nullptr), device_(device), token_(0) {
     const int rc = rpe_create(device, &ctx_);
     if (rc != RPE_OK) throw Failure(rc, std::string("rpe_create: ") + rpe_status_string(rc));
+    // the header API is blocking and the reference's loops usually stop after a few dozen to a few hundred iterations:
+    // start with a short pass (256, 512, 1024, ... iterations), the result does not depend on it
+    rpe_set_first_pass_iters(ctx_, 256);
   }
   ~Session() {
     if (ctx_) rpe_destroy(ctx_);

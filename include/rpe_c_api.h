@@ -157,6 +157,11 @@ int rpe_ransac(rpe_ctx* ctx, int method, const int32_t* samples, int H, float th
 int rpe_ransac_async(rpe_ctx* ctx, int method, const int32_t* samples, int H, float thr3d, float cos_thr2d,
                      float cos_thrN, float confidence, rpe_result* out_pinned, int16_t* mask_pinned);
 
+/* Iterations of the first device pass (default 1024; later passes double up to 8192). An `Iter` that fits the first
+ * pass is scored in one go with no host round trip — what a pipeline of asynchronous frames wants; a latency-bound
+ * blocking caller whose loops usually stop after a few dozen iterations (low outlier ratios) can start smaller. The
+ * result does not depend on it. */
+int rpe_set_first_pass_iters(rpe_ctx* ctx, int iters);
 /* Same as rpe_ransac, with the sample rows produced on demand: `fn(user, first_iteration, count, rows)` must write
  * rows [first_iteration, first_iteration + count) of the table (count x 4 int32) and return 0. It is called once per
  * device pass (1024, 2048, 4096, 8192, ... iterations) in increasing order, so a caller whose Iter is 100 000 — the

@@ -70,6 +70,7 @@ struct rpe_ctx {
   ReplayOut* h_pose = nullptr;    // pinned, kNumStaging slots; [0] doubles as scratch for set_pose
   bool kabsch_valid = false;
   bool suff_valid = false;  // rb.suff matches the inlier columns in d_mask
+  int first_pass = 1024;  // iterations of the first device pass (kFirstPassIters; rpe_set_first_pass_iters)
   // peer-memory vote exchange (hypothesis-sharded single frame)
   unsigned char* d_peer_block = nullptr;  // own block (exported)
   PeerTable peers = {};
@@ -537,8 +538,8 @@ int do_ransac64(rpe_ctx* ctx, int method, const int32_t* samples, rpe_sample_fn 
   }
   launch_replay64_begin(ctx->d_rs64, H, ctx->stream);
   ctx->launches++;
-  const bool single = H <= kFirstPassIters;
-  int pass = single ? H : kFirstPassIters;
+  const bool single = H <= ctx->first_pass;
+  int pass = single ? H : ctx->first_pass;
   for (int base = 0; base < H; base += pass, pass = (2 * pass < kMaxPassIters ? 2 * pass : kMaxPassIters)) {
     const int hc = (H - base) < pass ? (H - base) : pass;
     const int32_t* chunk = samples ? samples + (size_t)base * 4 : nullptr;
@@ -658,8 +659,8 @@ int do_ransac(rpe_ctx* ctx, int method, const int32_t* samples, rpe_sample_fn fn
     rc = ensure_packed(ctx, kind_for_method(method));
     if (rc) return rc;
   }
-  const bool single = H <= kFirstPassIters;
-  int pass = single ? H : kFirstPassIters;
+  const bool single = H <= ctx->first_pass;
+  int pass = single ? H : ctx->first_pass;
   for (int base = 0; base < H; base += pass, pass = (2 * pass < kMaxPassIters ? 2 * pass : kMaxPassIters)) {
     const int hc = (H - base) < pass ? (H - base) : pass;
     const int32_t* chunk = samples ? samples + (size_t)base * 4 : nullptr;
@@ -943,6 +944,11 @@ int rpe_ransac(rpe_ctx* ctx, int method, const int32_t* samples, int H, float th
 int rpe_ransac_async(rpe_ctx* ctx, int method, const int32_t* samples, int H, float thr3d, float cos_thr2d,
                      float cos_thrN, float confidence, rpe_result* out, int16_t* mask) {
   return do_ransac(ctx, method, samples, nullptr, nullptr, H, thr3d, cos_thr2d, cos_thrN, confidence, out, mask, false);
+}
+int rpe_set_first_pass_iters(rpe_ctx* ctx, int iters) {
+  if (!ctx || iters < 1) return RPE_ERR_ARG;
+  ctx->first_pass = iters < kMaxPassIters ? iters : kMaxPassIters;
+  return RPE_OK;
 }
 int rpe_ransac_stream(rpe_ctx* ctx, int method, rpe_sample_fn fn, void* user, int H, float thr3d, float cos_thr2d,
                       float cos_thrN, float confidence, rpe_result* out, int16_t* mask) {

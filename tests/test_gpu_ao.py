@@ -275,6 +275,13 @@ def test_ransac_stream_draws_rows_pass_by_pass(rpe, orc, gpu_ctx):
     assert (got["winner"], got["max_votes"], got["iter_final"]) == (ref["winner"], ref["max_votes"], ref["iter_final"])
     assert got["passes"][:3] == [(0, 1024), (1024, 2048), (3072, 4096)]
     assert ref["iters_run"] == max(got["iter_final"], got["winner"] + 1)
+    # a shorter first pass changes the schedule, not the result
+    gpu_ctx.set_first_pass_iters(128)
+    got2 = gpu_ctx.ransac_stream(SHINJI, lambda first, count: S[first:first + count], H, thr3d=0.25, confidence=0.9999)
+    gpu_ctx.set_first_pass_iters(1024)
+    assert got2["passes"][:4] == [(0, 128), (128, 256), (384, 512), (896, 1024)]
+    assert (got2["winner"], got2["max_votes"], got2["iter_final"]) == (got["winner"], got["max_votes"], got["iter_final"])
+    assert np.array_equal(got2["mask"], got["mask"])
 
 
 def test_c_abi_error_behaviour(rpe):
