@@ -488,7 +488,9 @@ mask64_kernel(int method, FrameView64 f, ReplayOut* pose_rw, const Pose64* __res
     } else {
       f2 = f3d = fn = true;  // adapters start with setOnes() and setInlier is never called
     }
-    mask[c] = (int16_t)((cols == 1 || u2) ? (f2 ? 1 : 0) : 0);
+    // column 0 of a family without the 2-D test is never set by the reference's loop: 0 once a hypothesis has been
+    // accepted (the per-iteration matrix starts from zero), still the initial 1 when nothing was accepted
+    mask[c] = (int16_t)(!have ? 1 : ((cols == 1 || u2) ? (f2 ? 1 : 0) : 0));
     if (cols >= 2) mask[n + c] = (int16_t)(u3 ? (f3d ? 1 : 0) : (have ? 0 : 1));
     if (cols >= 3) mask[2 * n + c] = (int16_t)(fn ? 1 : 0);
   }
