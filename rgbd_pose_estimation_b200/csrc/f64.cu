@@ -392,7 +392,8 @@ replay64_kernel(int method, const HypGen64* __restrict__ gen, const int32_t* __r
           rb_.log_denom = __shfl_sync(0xffffffffu, rd.log_denom, b);
           Iter = rule_finish_d(log_num, rb_, Iter);
         }
-        if ((long long)(slot_base + cbase + base + 32) >= (long long)Iter * S) stop = true;
+        // nothing below the loop bound is left in (or after) this pass; a pass may end inside this 32-slot group
+        if ((long long)(slot_base + cbase + min(base + 32, cn)) >= (long long)Iter * S) stop = true;
       }
       if (lane == 0) {
         s_state[0] = best;
