@@ -831,11 +831,15 @@ __device__ void gn_publish(const GnState* gs, ReplayOut* pose_out, double* cost_
   }
 }
 
+// One LM evaluation over the correspondences (needed when 2-D rows take part: they are not polynomial in the pose).
+// Rows are formed in binary64 from the binary32 inputs with the twin's expressions (oracle/refine.hpp::gn_evaluate),
+// so a row has the same bits on both sides and only the summation order differs.
 template <bool GENERIC>
 __global__ void __launch_bounds__(256)
 gn_iteration_kernel(FrameView f, const int16_t* __restrict__ mask, int mask_cols, float w2d, float w3d, float wnl,
                     RefitBuffers rb, GnState* __restrict__ gs, FrameStats* __restrict__ st, ReplayOut* __restrict__ pose_out,
                     double* __restrict__ cost_out, int32_t* __restrict__ evals_out) {
+  static_assert(GENERIC, "3-D / normal rows alone are handled by gn_from_stats_kernel");
   if (gs->done) return;
   __shared__ double red[8 * kGnAcc];
   __shared__ bool is_last;
@@ -843,118 +847,70 @@ gn_iteration_kernel(FrameView f, const int16_t* __restrict__ mask, int mask_cols
   double acc[kGnAcc];
 #pragma unroll
   for (int k = 0; k < kGnAcc; ++k) acc[k] = 0.0;
-  // FP32 residuals / Jacobian entries from the FP32 copy of the current proposal, FP64 accumulation
-  float R[9], t[3];
+  double R[9], t[3];
 #pragma unroll
-  for (int k = 0; k < 9; ++k) R[k] = (float)gs->Rp[k];
+  for (int k = 0; k < 9; ++k) R[k] = gs->Rp[k];
 #pragma unroll
-  for (int k = 0; k < 3; ++k) t[k] = (float)gs->tp[k];
+  for (int k = 0; k < 3; ++k) t[k] = gs->tp[k];
   const bool m2 = mask_cols >= 1 && f.bv && w2d > 0.f;
   const bool m3 = mask_cols >= 2 && f.xc && w3d > 0.f;
   const bool mn = mask_cols >= 3 && f.nc && wnl > 0.f;
   for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < n; c += gridDim.x * blockDim.x) {
-    const bool u2 = GENERIC && m2 && mask[c] == 1;
+    const bool u2 = m2 && mask[c] == 1;
     const bool u3 = m3 && mask[n + c] == 1;
     const bool un = mn && mask[2 * n + c] == 1;
     if (!(u2 || u3 || un)) continue;
-    const F3 x = load_col(f.xw, c);
-    float yf[3];
+    const F3 xf = load_col(f.xw, c);
+    const double x[3] = {(double)xf.x, (double)xf.y, (double)xf.z};
+    double y[3];
 #pragma unroll
-    for (int r = 0; r < 3; ++r) yf[r] = fmaf(R[3 * r], x.x, fmaf(R[3 * r + 1], x.y, fmaf(R[3 * r + 2], x.z, t[r])));
-    const double y[3] = {yf[0], yf[1], yf[2]};
-    if (GENERIC) {
-      double Jy[3][6];
-      gn_point_rows(y, Jy);
-      if (u3) {
-        const F3 p = load_col(f.xc, c);
-        const float rf[3] = {yf[0] - p.x, yf[1] - p.y, yf[2] - p.z};
+    for (int r = 0; r < 3; ++r) y[r] = R[3 * r] * x[0] + R[3 * r + 1] * x[1] + R[3 * r + 2] * x[2] + t[r];
+    double Jy[3][6];
+    gn_point_rows(y, Jy);
+    if (u3) {
+      const F3 p = load_col(f.xc, c);
+      const double pd[3] = {(double)p.x, (double)p.y, (double)p.z};
 #pragma unroll
-        for (int r = 0; r < 3; ++r) gn_add_row(acc, Jy[r], (double)rf[r], (double)w3d);
+      for (int r = 0; r < 3; ++r) gn_add_row(acc, Jy[r], y[r] - pd[r], (double)w3d);
+    }
+    if (u2) {
+      const F3 bf = load_col(f.bv, c);
+      const double b[3] = {(double)bf.x, (double)bf.y, (double)bf.z};
+      const double ny = sqrt(y[0] * y[0] + y[1] * y[1] + y[2] * y[2]);
+      const double u[3] = {y[0] / ny, y[1] / ny, y[2] / ny};
+      double P[3][3];
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) P[r][k] = ((r == k ? 1.0 : 0.0) - u[r] * u[k]) / ny;
+      double Ju[3][6];
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int cc = 0; cc < 6; ++cc) Ju[r][cc] = P[r][0] * Jy[0][cc] + P[r][1] * Jy[1][cc] + P[r][2] * Jy[2][cc];
+      const double res[3] = {b[1] * u[2] - b[2] * u[1], b[2] * u[0] - b[0] * u[2], b[0] * u[1] - b[1] * u[0]};
+      double Jr[3][6];
+#pragma unroll
+      for (int cc = 0; cc < 6; ++cc) {
+        Jr[0][cc] = b[1] * Ju[2][cc] - b[2] * Ju[1][cc];
+        Jr[1][cc] = b[2] * Ju[0][cc] - b[0] * Ju[2][cc];
+        Jr[2][cc] = b[0] * Ju[1][cc] - b[1] * Ju[0][cc];
       }
-      if (u2) {
-        const F3 b = load_col(f.bv, c);
-        const float nyf = sqrtf(yf[0] * yf[0] + yf[1] * yf[1] + yf[2] * yf[2]);
-        const float uf[3] = {yf[0] / nyf, yf[1] / nyf, yf[2] / nyf};
-        const float resf[3] = {b.y * uf[2] - b.z * uf[1], b.z * uf[0] - b.x * uf[2], b.x * uf[1] - b.y * uf[0]};
-        const double u[3] = {uf[0], uf[1], uf[2]}, ny = nyf, bd[3] = {b.x, b.y, b.z};
-        double Ju[3][6];
 #pragma unroll
-        for (int r = 0; r < 3; ++r)
+      for (int r = 0; r < 3; ++r) gn_add_row(acc, Jr[r], res[r], (double)w2d);
+    }
+    if (un) {
+      const F3 nwf = load_col(f.nw, c), ncf = load_col(f.nc, c);
+      const double nw[3] = {(double)nwf.x, (double)nwf.y, (double)nwf.z}, nc[3] = {(double)ncf.x, (double)ncf.y, (double)ncf.z};
+      double m[3];
 #pragma unroll
-          for (int cc = 0; cc < 6; ++cc) {
-            double sacc = 0.0;
+      for (int r = 0; r < 3; ++r) m[r] = R[3 * r] * nw[0] + R[3 * r + 1] * nw[1] + R[3 * r + 2] * nw[2];
+      double Jn[3][6];
+      gn_point_rows(m, Jn);
 #pragma unroll
-            for (int k = 0; k < 3; ++k) sacc += (((r == k) ? 1.0 : 0.0) - u[r] * u[k]) / ny * Jy[k][cc];
-            Ju[r][cc] = sacc;
-          }
-        double Jr[3][6];
-#pragma unroll
-        for (int cc = 0; cc < 6; ++cc) {
-          Jr[0][cc] = bd[1] * Ju[2][cc] - bd[2] * Ju[1][cc];
-          Jr[1][cc] = bd[2] * Ju[0][cc] - bd[0] * Ju[2][cc];
-          Jr[2][cc] = bd[0] * Ju[1][cc] - bd[1] * Ju[0][cc];
-        }
-#pragma unroll
-        for (int r = 0; r < 3; ++r) gn_add_row(acc, Jr[r], (double)resf[r], (double)w2d);
-      }
-      if (un) {
-        const F3 nw = load_col(f.nw, c), nc = load_col(f.nc, c);
-        float mf[3];
-#pragma unroll
-        for (int r = 0; r < 3; ++r) mf[r] = fmaf(R[3 * r], nw.x, fmaf(R[3 * r + 1], nw.y, R[3 * r + 2] * nw.z));
-        const double m[3] = {mf[0], mf[1], mf[2]};
-        double Jn[3][6];
-        gn_point_rows(m, Jn);
-        const float rf[3] = {mf[0] - nc.x, mf[1] - nc.y, mf[2] - nc.z};
-#pragma unroll
-        for (int r = 0; r < 3; ++r) {
-          Jn[r][0] = Jn[r][1] = Jn[r][2] = 0.0;
-          gn_add_row(acc, Jn[r], (double)rf[r], (double)wnl);
-        }
-      }
-    } else {
-      if (u3) {
-        const F3 p = load_col(f.xc, c);
-        const double w = (double)w3d;
-        const double r[3] = {(double)(yf[0] - p.x), (double)(yf[1] - p.y), (double)(yf[2] - p.z)};
-        acc[0] += w;
-        acc[1] += w * y[0];
-        acc[2] += w * y[1];
-        acc[3] += w * y[2];
-        acc[4] += w * y[0] * y[0];
-        acc[5] += w * y[0] * y[1];
-        acc[6] += w * y[0] * y[2];
-        acc[7] += w * y[1] * y[1];
-        acc[8] += w * y[1] * y[2];
-        acc[9] += w * y[2] * y[2];
-        acc[10] += w * r[0];
-        acc[11] += w * r[1];
-        acc[12] += w * r[2];
-        acc[13] += w * (y[1] * r[2] - y[2] * r[1]);
-        acc[14] += w * (y[2] * r[0] - y[0] * r[2]);
-        acc[15] += w * (y[0] * r[1] - y[1] * r[0]);
-        acc[25] += w * (r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
-        acc[26] += 3.0;
-      }
-      if (un) {
-        const F3 nw = load_col(f.nw, c), nc = load_col(f.nc, c);
-        float mf[3];
-#pragma unroll
-        for (int r = 0; r < 3; ++r) mf[r] = fmaf(R[3 * r], nw.x, fmaf(R[3 * r + 1], nw.y, R[3 * r + 2] * nw.z));
-        const double m[3] = {mf[0], mf[1], mf[2]};
-        const double w = (double)wnl;
-        const double r[3] = {(double)(mf[0] - nc.x), (double)(mf[1] - nc.y), (double)(mf[2] - nc.z)};
-        acc[16] += w * m[0] * m[0];
-        acc[17] += w * m[0] * m[1];
-        acc[18] += w * m[0] * m[2];
-        acc[19] += w * m[1] * m[1];
-        acc[20] += w * m[1] * m[2];
-        acc[21] += w * m[2] * m[2];
-        acc[22] += w * (m[1] * r[2] - m[2] * r[1]);
-        acc[23] += w * (m[2] * r[0] - m[0] * r[2]);
-        acc[24] += w * (m[0] * r[1] - m[1] * r[0]);
-        acc[25] += w * (r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
-        acc[26] += 3.0;
+      for (int r = 0; r < 3; ++r) {
+        Jn[r][0] = Jn[r][1] = Jn[r][2] = 0.0;  // normals do not translate
+        gn_add_row(acc, Jn[r], m[r] - nc[r], (double)wnl);
       }
     }
   }
@@ -1101,12 +1057,9 @@ void launch_gn_iteration(const FrameView& f, const int16_t* mask, int mask_cols,
                          int32_t* evals_out, cudaStream_t s) {
   const int blocks = refit_grid(f.n, rb.num_sms);
   const bool generic = mask_cols >= 1 && f.bv != nullptr && w2d > 0.f;
-  if (generic)
-    gn_iteration_kernel<true><<<blocks, 256, 0, s>>>(f, mask, mask_cols, w2d, w3d, wnl, rb, gs, st, pose_out, cost_out,
-                                                     evals_out);
-  else
-    gn_iteration_kernel<false><<<blocks, 256, 0, s>>>(f, mask, mask_cols, w2d, w3d, wnl, rb, gs, st, pose_out, cost_out,
-                                                      evals_out);
+  (void)generic;  // 3-D / normal rows alone never come here (launch_gn_from_stats)
+  gn_iteration_kernel<true><<<blocks, 256, 0, s>>>(f, mask, mask_cols, w2d, w3d, wnl, rb, gs, st, pose_out, cost_out,
+                                                   evals_out);
 }
 
 // ================================================================================================
