@@ -16,6 +16,7 @@ cases = int(sys.argv[1]) if len(sys.argv) > 1 else 100
 seed0 = int(sys.argv[2]) if len(sys.argv) > 2 else 0
 orc.set_math_mode(orc.DET)
 ctx = rpe.Context(0)
+ctx.peer_import(0, 1, ctx.peer_export())  # a world of one rank: rpe_ransac_sharded must equal rpe_ransac
 names = {v: k for k, v in rpe.METHODS.items()}
 bad = 0
 for i in range(cases):
@@ -75,7 +76,22 @@ for i in range(cases):
     else:
         ref = orc.ransac(method, S, **kw, **arrs)
         ctx.upload(**arrs)
-        got = ctx.ransac(names[method], S, thr3d=thr3d, cos_thr2d=cos_thr, cos_thrN=cos_nl, confidence=conf)
+        gk = dict(thr3d=thr3d, cos_thr2d=cos_thr, cos_thrN=cos_nl, confidence=conf)
+        mode = int(rng.integers(0, 4))
+        if mode == 1:    # rows on demand, pass by pass
+            got = ctx.ransac_stream(names[method], lambda first, count: S[first:first + count], H, **gk)
+        elif mode == 2 and H <= first_pass:  # the one-call sharded frame (one rank), mask through the stage API afterwards
+            r = ctx.ransac_sharded(names[method], S, **gk)
+            got = ctx.finish(names[method], H, **gk)
+            assert (r["winner"], r["max_votes"], r["iter_final"]) == (got["winner"], got["max_votes"], got["iter_final"])
+        elif mode == 3 and H <= first_pass:  # stage API, the slot range scored in random pieces
+            ns = ctx.generate(names[method], S)
+            cuts = sorted(set([0, ns] + [int(c) for c in rng.integers(0, ns + 1, int(rng.integers(0, 4)))]))
+            for b, e in zip(cuts[:-1], cuts[1:]):
+                ctx.score(names[method], b, e, thr3d=thr3d, cos_thr2d=cos_thr, cos_thrN=cos_nl)
+            got = ctx.finish(names[method], H, **gk)
+        else:
+            got = ctx.ransac(names[method], S, **gk)
         pose_ok = np.array_equal(got["q"].view(np.uint32), ref["q"].view(np.uint32)) or got["winner"] < 0 or (
             np.isnan(got["q"]).all() and np.isnan(ref["q"]).all())
     # several device passes: the vote table on the device holds the last pass only
