@@ -8,6 +8,7 @@
 #ifndef RPE_ESTIMATORS_HPP_
 #define RPE_ESTIMATORS_HPP_
 
+#include <limits>
 #include <stdint.h>
 
 #include <cmath>
@@ -218,8 +219,8 @@ inline rpe_result run_refit(Adapter& adapter, int kind, const float* weights, in
 }  // namespace detail
 }  // namespace rpe
 
-// RANSACUpdateNumIters — /root/reference/pose/P3P.hpp:296-318 (same name, same arguments). For float it is the
-// bit-reproducible rule the device replays (rpe/ransac_rule.h); other scalar types use libm like the reference.
+// RANSACUpdateNumIters — /root/reference/pose/P3P.hpp:296-318 (same name, same arguments). For float and double it
+// is the bit-reproducible rule the device replays (rpe/ransac_rule.h); other scalar types use libm like the reference.
 #include "ransac_rule.h"
 template <typename T>
 int RANSACUpdateNumIters(T p, T ep, const int modelPoints, const int maxIters) {
@@ -237,6 +238,10 @@ int RANSACUpdateNumIters(T p, T ep, const int modelPoints, const int maxIters) {
 template <>
 inline int RANSACUpdateNumIters<float>(float p, float ep, const int modelPoints, const int maxIters) {
   return rpe::update_num_iters(p, ep, modelPoints, maxIters);
+}
+template <>
+inline int RANSACUpdateNumIters<double>(double p, double ep, const int modelPoints, const int maxIters) {
+  return rpe::update_num_iters_d(p, ep, modelPoints, maxIters);
 }
 
 #endif  // RPE_ESTIMATORS_HPP_

@@ -8,6 +8,7 @@
 #ifndef RPE_P3P_HPP_
 #define RPE_P3P_HPP_
 
+#include <limits>
 #include <iostream>
 #include <vector>
 

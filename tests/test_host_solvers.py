@@ -77,3 +77,37 @@ def test_random_source_snapshot_and_rewind(tmp_path):
     out = subprocess.run([exe], capture_output=True, text=True)
     assert out.returncode == 0 and "FAIL" not in out.stdout, out.stdout
     assert out.stdout.count("ok ") >= 11
+
+
+def test_every_public_header_is_self_contained(tmp_path):
+    """Each header of include/ compiles on its own as C++11 with -Wall -Werror (a caller may include just one)."""
+    import glob
+    heads = sorted(glob.glob(os.path.join(ROOT, "include", "rpe", "*.h*"))) + [os.path.join(ROOT, "include", "rpe_c_api.h")]
+    assert len(heads) >= 20
+    for h in heads:
+        src = tmp_path / "one.cpp"
+        src.write_text(f'#include "{h}"\nint main() {{ return 0; }}\n')
+        subprocess.run(["g++", "-std=c++11", "-O0", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), "-c", "-o",
+                        str(tmp_path / "one.o"), str(src)], check=True)
+
+
+def test_host_stopping_rule_equals_oracle_for_float_and_double(orc, tmp_path):
+    """RANSACUpdateNumIters<float> / <double> of the header API (what a caller can evaluate on the host) are the rules the
+    device replays; both equal the DET-mode oracle over a sweep of vote counts."""
+    src = tmp_path / "rule.cpp"
+    src.write_text('#include <cstdio>\n#include "rpe/P3P.hpp"\nint main() { for (int v = 1; v < 1000; ++v) { double ep = (1000.0 - v) / 1000.0; '
+                   'printf("%d %d\\n", RANSACUpdateNumIters<double>(0.99, ep, 3, 100000), '
+                   'RANSACUpdateNumIters<float>(0.99f, (float)ep, 4, 100000)); } return 0; }\n')
+    exe = str(tmp_path / "rule")
+    libdir = os.path.join(ROOT, "rgbd_pose_estimation_b200")
+    subprocess.run(["g++", "-std=c++11", "-O2", "-ffp-contract=off", "-I", os.path.join(ROOT, "include"), "-o", exe, str(src), "-L", libdir,
+                    "-lrpe_b200", "-Wl,-rpath," + libdir], check=True)
+    out = subprocess.run([exe], capture_output=True, text=True, check=True).stdout.split()
+    orc.set_math_mode(orc.DET)
+    k = 0
+    for v in range(1, 1000):
+        ep = (1000.0 - v) / 1000.0
+        assert int(out[k]) == orc.update_num_iters(0.99, ep, 3, 100000, dt=np.float64), v
+        assert int(out[k + 1]) == orc.update_num_iters(np.float32(0.99), np.float32(ep), 4, 100000, dt=np.float32), v
+        k += 2
+    orc.set_math_mode(orc.LIBM)
