@@ -8,10 +8,10 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _build(tmp_path):
-    exe = os.path.join(tmp_path, "test_host_solvers")
-    subprocess.run(["g++", "-std=c++11", "-O2", "-ffp-contract=off", "-I", os.path.join(ROOT, "include"), "-o", exe,
-                    os.path.join(ROOT, "tests", "cpp", "test_host_solvers.cpp")], check=True)
+def _build(tmp_path, real="float"):
+    exe = os.path.join(tmp_path, "test_host_solvers_" + real)
+    subprocess.run(["g++", "-std=c++11", "-O2", "-ffp-contract=off", "-DREAL=" + real, "-I", os.path.join(ROOT, "include"), "-o",
+                    exe, os.path.join(ROOT, "tests", "cpp", "test_host_solvers.cpp")], check=True)
     return exe
 
 
@@ -22,47 +22,57 @@ def test_header_api_compiles_cxx11(tmp_path):
                     os.path.join(ROOT, "tests", "cpp", "test_dropin.cpp")], check=True)
 
 
-def test_host_solvers_bit_exact_vs_oracle(orc, rpe, tmp_path):
-    exe = _build(str(tmp_path))
+import pytest
+
+
+@pytest.mark.parametrize("real", ["float", "double"])
+def test_host_solvers_bit_exact_vs_oracle(orc, rpe, tmp_path, real):
+    """float: what the device's binary32 generators run; double: the instantiation of the binary64 path."""
+    exe = _build(str(tmp_path), real)
+    npdt, npbits = (np.float32, np.uint32) if real == "float" else (np.float64, np.uint64)
     orc.set_math_mode(orc.DET)
-    cases = 60
+    cases = 300
     rng = np.random.default_rng(3)
     q, t = rpe.sim_pose(5)
     d = rpe.sim_2d_3d_nl(6, q, t, 400, or2d=0.1, or3d=0.1, ornl=0.1)
+    if real == "double":  # directions that are unit vectors to double precision, as a double Simulator produces them
+        d = {k: v.astype(np.float64) for k, v in d.items()}
+        for k in ("bv", "nw", "nc"):
+            d[k] = d[k] / np.linalg.norm(d[k], axis=1, keepdims=True)
     lines = [str(cases)]
     picks = []
     for _ in range(cases):
         idx = rng.choice(400, 4, replace=False)
         picks.append(idx)
         for name in ("xw", "xc", "bv", "nw", "nc"):
-            lines.append(" ".join(str(int(v)) for v in np.ascontiguousarray(d[name][idx]).view(np.uint32).ravel()))
+            lines.append(" ".join(str(int(v)) for v in np.ascontiguousarray(d[name][idx]).view(npbits).ravel()))
     out = subprocess.run([exe], input="\n".join(lines), capture_output=True, text=True, check=True).stdout.split("\n")
     it = iter([l for l in out if l])
 
     def pose_bits(q_, t_):
-        return list(np.asarray(q_, np.float32).view(np.uint32)) + list(np.asarray(t_, np.float32).view(np.uint32))
+        return list(np.asarray(q_, npdt).view(npbits)) + list(np.asarray(t_, npdt).view(npbits))
 
     n_kneip = 0
     for idx in picks:
         Xw, Xc, bv, Nw, Nc = (d[k][idx] for k in ("xw", "xc", "bv", "nw", "nc"))
         tag, *vals = next(it).split()
-        qs, ts, ok = orc.shinji(Xw[:3], Xc[:3], K=3, cols=4)
+        qs, ts, ok = orc.shinji(Xw[:3], Xc[:3], K=3, cols=4, dt=npdt)
         assert tag == "shinji" and [int(v) for v in vals] == pose_bits(qs, ts)
         tag, cnt = next(it).split()
-        qk, tk = orc.kneip_main(Xw, bv)
+        qk, tk = orc.kneip_main(Xw, bv, dt=npdt)
         assert tag == "kneip_main_count" and int(cnt) == len(qk)
         for i in range(int(cnt)):
             tag, *vals = next(it).split()
             assert [int(v) for v in vals] == pose_bits(qk[i], tk[i])
         tag, okv = next(it).split()
-        q4, t4, ok4 = orc.kneip4(Xw, bv)
+        q4, t4, ok4 = orc.kneip4(Xw, bv, dt=npdt)
         assert tag == "kneip4_ok" and int(okv) == int(ok4)
         if ok4:
             tag, *vals = next(it).split()
             assert [int(v) for v in vals] == pose_bits(q4, t4)
             n_kneip += 1
         tag, *vals = next(it).split()
-        qn, tn = orc.nl_2p(Xc[0], Nc[0], Xc[1], Xw[0], Nw[0], Xw[1])
+        qn, tn = orc.nl_2p(Xc[0], Nc[0], Xc[1], Xw[0], Nw[0], Xw[1], dt=npdt)
         assert tag == "nl_2p" and [int(v) for v in vals] == pose_bits(qn, tn)
     orc.set_math_mode(orc.LIBM)
     assert n_kneip > cases // 2
