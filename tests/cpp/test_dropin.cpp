@@ -98,6 +98,13 @@ int main(int argc, char** argv) {
     const rpe::Vec3<double> t = adapter.gettw();
     printf("{\"case\": \"nl_shinji_kneip_ransac_f64\", \"max_votes\": %d, \"iter\": %d, \"n_inliers\": %d, \"q\": [%.17g, %.17g, %.17g, %.17g], \"t\": [%.17g, %.17g, %.17g]}\n",
            adapter.getMaxVotes(), updated_iter, (int)adapter.getInlierIdx().size(), q.x(), q.y(), q.z(), q.w(), t[0], t[1], t[2]);
+    nl_shinji_kneip_ls<double>(adapter);  // refits of a double adapter: float copies on the device, binary64 accumulation
+    {
+      const rpe::Quaternion<double> ql = adapter.getRcw().unit_quaternion();
+      const rpe::Vec3<double> tl = adapter.gettw();
+      printf("{\"case\": \"nl_shinji_kneip_ls_f64\", \"max_votes\": %d, \"iter\": %d, \"n_inliers\": 0, \"q\": [%.17g, %.17g, %.17g, %.17g], \"t\": [%.17g, %.17g, %.17g]}\n",
+             adapter.getMaxVotes(), updated_iter, ql.x(), ql.y(), ql.z(), ql.w(), tl[0], tl[1], tl[2]);
+    }
     PnPPoseAdapter<double> pnp(Ud, Qd);
     pnp.setFocal(585., 585.);
     updated_iter = 500;

@@ -134,6 +134,10 @@ def test_cpp_dropin_matches_oracle(dropin_output, rpe, orc):
     assert (got["max_votes"], got["iter"]) == (ref["max_votes"], ref["iter_final"])
     assert np.array_equal(np.float64(got["q"]).view(np.uint64), ref["q"].view(np.uint64))
     assert np.array_equal(np.float64(got["t"]).view(np.uint64), ref["t"].view(np.uint64))
+    rq, rt = orc.nl_shinji_kneip_ls(ref["q"], ref["t"], ref["mask"], ref["max_votes"], dt=np.float64, bv=bv, xc=xc, nc=nc, xw=xw,
+                                    nw=nw)
+    got = res["nl_shinji_kneip_ls_f64"]
+    assert _angle(got["q"], rq) < 4e-6 and np.abs(np.array(got["t"]) - rt).max() < 4e-5
     S = orc.sample_table_skip(1, skip, total, 4, 500)
     ref = orc.ransac(1, S, cos_thr=cos_thr64, confidence=0.99, full=False, want_arrays=False, dt=np.float64, bv=bv, xw=xw)
     got = res["kneip_ransac_f64"]
