@@ -138,7 +138,8 @@ int rpe_num_correspondences(const rpe_ctx* ctx);
 
 /* ---- robust estimation ------------------------------------------------------------------
  * samples: int32 [H x 4] (host, page-locked host, or device memory) rows of correspondence indices (3 used by RPE_SHINJI), exactly the
- *          draws RandomElements::run / ProsacSampler::sample would produce (see rpe_sample_table).
+ *          draws RandomElements::run / ProsacSampler::sample would produce (see rpe_sample_table). A row with an
+ *          index outside [0, n) makes that iteration an empty slot (the reference's samplers cannot produce one).
  * H      : the caller's `Iter` on entry. Up to 1024 iterations are generated and scored on the GPU
  *          in one go; the reference's sequential rule (strict `votes > max`, Iter =
  *          RANSACUpdateNumIters(..)) is then replayed on the device, so winner / max_votes /

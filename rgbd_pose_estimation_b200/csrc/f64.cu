@@ -127,6 +127,13 @@ hypgen64_kernel(int method, FrameView64 f, const int32_t* __restrict__ samples, 
   g.t[0] = g.t[1] = g.t[2] = 0.0;
   g.valid = 0;
   g.pad = 0;
+  bool in_range = true;  // see hypgen_kernel
+  for (int k = 0; k < method_sample_size(method); ++k) in_range = in_range && sel[k] >= 0 && sel[k] < f.n;
+  if (!in_range) {
+    gen[ii * S + s] = g;
+    votes[ii * S + s] = -1;
+    return;
+  }
   if (solver == SOLVER_AO) {
     double Xw[9], Xc[9];
     bool all_valid = true;

@@ -73,6 +73,13 @@ hypgen_kernel(int method, FrameView f, const int32_t* __restrict__ samples, int 
   g.q[3] = 1.f;
   g.t[0] = g.t[1] = g.t[2] = 0.f;
   g.valid = 0;
+  // a row that points outside the frame (caller's table; the reference's samplers cannot produce one) yields an empty slot
+  bool in_range = true;
+  for (int k = 0; k < method_sample_size(method); ++k) in_range = in_range && sel[k] >= 0 && sel[k] < f.n;
+  if (!in_range) {
+    publish_hypothesis(g, ii * S + s, gen, fast, votes, st);
+    return;
+  }
   if (solver == SOLVER_AO) {
     float Xw[9], Xc[9];
     bool all_valid = true;

@@ -410,3 +410,25 @@ def test_full_size_frame_properties(rpe, orc, gpu_ctx):
     assert np.array_equal(gpu_ctx.get_votes(H), votes)
     assert (got2["winner"], got2["max_votes"], got2["iter_final"]) == (got["winner"], got["max_votes"], got["iter_final"])
     assert np.array_equal(got2["mask"][1][inv], got["mask"][1])
+
+
+def test_sample_rows_outside_the_frame_give_empty_slots(rpe, orc, gpu_ctx):
+    """A caller-made table with an index < 0 or >= n (the reference's samplers cannot produce one): that iteration is an
+    empty slot (votes -1) instead of an out-of-bounds read; the other iterations are unaffected."""
+    orc.set_math_mode(orc.DET)
+    n, H = 500, 64
+    q, t, Q, P = _frame(rpe, 66, n)
+    S = rpe.sample_table(66, n, 3, H)
+    ref = orc.ransac(SHINJI, S, thr3d=0.25, confidence=0.9999, full=True, xc=P, xw=Q)
+    bad = S.copy()
+    bad[5, 1] = n
+    bad[17, 0] = -3
+    bad[40, 2] = 2 ** 30
+    gpu_ctx.upload(xc=P, xw=Q)
+    got = gpu_ctx.ransac(SHINJI, bad, thr3d=0.25, confidence=0.9999)
+    votes = gpu_ctx.get_votes(H)
+    assert list(votes[[5, 17, 40]]) == [-1, -1, -1]
+    keep = np.ones(H, bool)
+    keep[[5, 17, 40]] = False
+    assert np.array_equal(votes[keep], ref["votes"][keep])
+    assert got["winner"] >= 0
