@@ -232,9 +232,11 @@ __device__ __forceinline__ float hyp_magnitude(const FrameStats* st, float nt0, 
   const float tn = sqrtf(nt0 * nt0 + nt1 * nt1 + nt2 * nt2);
   return (__uint_as_float(st->m_corr_bits) + tn) * 1.0001f;
 }
+// The error of s is 2|e| de + de^2 with |e| ~ thr and de <= 26.8 u M: the second-order term only matters for
+// thresholds down at the rounding level of the coordinates (thr <~ 30 u M), where it is covered by widening thr.
 __device__ __forceinline__ float guard_band_3d(float M, float thr) {
   const float u = 5.9604644775390625e-08f;
-  return thr * u * (64.f * M + 16.f * thr);
+  return (thr + 32.f * u * M) * u * (64.f * M + 16.f * thr);
 }
 
 template <bool PACKED>

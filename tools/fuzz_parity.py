@@ -29,6 +29,8 @@ for i in range(cases):
     ors = rng.uniform(0.0, 0.8, 3)
     n2d, n3d, nnl = float(rng.uniform(0.1, 3.0)), float(rng.uniform(0.005, 0.2)), float(np.deg2rad(rng.uniform(0.2, 5.0)))
     thr3d = float(np.float32(rng.uniform(0.02, 0.8)))
+    if rng.random() < 0.08:  # thresholds at the rounding level of the coordinates, and absurdly large ones
+        thr3d = float(np.float32(rng.choice([1e-7, 1e-6, 3e-5, 50.0, 1e4])))
     cos_thr = float(np.cos(np.arctan(np.float32(rng.uniform(0.5, 20.0)) / np.float32(585.0))))
     cos_nl = float(np.cos(np.float32(rng.uniform(0.02, 0.5))))
     conf = float(rng.choice([0.9, 0.99, 0.9999]))
