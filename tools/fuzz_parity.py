@@ -33,6 +33,10 @@ for i in range(cases):
         thr3d = float(np.float32(rng.choice([1e-7, 1e-6, 3e-5, 50.0, 1e4])))
     cos_thr = float(np.cos(np.arctan(np.float32(rng.uniform(0.5, 20.0)) / np.float32(585.0))))
     cos_nl = float(np.cos(np.float32(rng.uniform(0.02, 0.5))))
+    if rng.random() < 0.08:
+        cos_thr = float(np.cos(np.arctan(np.float32(rng.choice([0.01, 300.0, 1e5])) / np.float32(585.0))))
+    if rng.random() < 0.08:
+        cos_nl = float(np.cos(np.float32(rng.choice([1e-4, 1.2, 1.5707]))))
     conf = float(rng.choice([0.9, 0.99, 0.9999]))
     q, t = rpe.sim_pose(1000 + seed0 + i)
     d = rpe.sim_2d_3d_nl(5000 + seed0 + i, q, t, n, n2d=n2d, or2d=float(ors[0]), n3d=n3d, or3d=float(ors[1]), nnl=nnl,
