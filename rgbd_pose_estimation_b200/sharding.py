@@ -67,17 +67,38 @@ def replay(votes: np.ndarray, method: int, n_corr: int, confidence: float, iter_
     return win, best, it
 
 
-def peer_setup(dist, ctx, rank: int, world: int) -> None:
+def peer_setup(dist, ctx, rank: int, world: int) -> bool:
     """Exchange the CUDA IPC handles of the contexts' vote-exchange blocks over any torch.distributed backend and map
-    every peer's block (one process per GPU of a node). Afterwards ``ctx.exchange_votes(b, e)`` moves vote slices
-    straight through peer memory."""
+    every peer's block (one process per GPU of a node). Afterwards ``ctx.exchange_votes(b, e)`` /
+    ``ctx.ransac_sharded(...)`` move vote slices straight through peer memory.
+
+    Collective-safe: every rank takes part in every collective of this function whatever fails locally, and the return
+    value (all ranks succeeded) is the same on all ranks — so a rank that cannot export or map a block never leaves
+    the others waiting in a barrier."""
     import torch
-    mine = torch.from_numpy(ctx.peer_export().copy())
+    try:
+        mine = torch.from_numpy(ctx.peer_export().copy())
+        ok = 1
+    except Exception:
+        mine = torch.zeros(64, dtype=torch.uint8)
+        ok = 0
     if dist is None or world == 1:
-        ctx.peer_import(0, 1, mine.numpy())
-        return
+        if ok:
+            ctx.peer_import(0, 1, mine.numpy())
+        return bool(ok)
     backend = dist.get_backend()
     dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
     parts = [torch.empty(64, dtype=torch.uint8, device=dev) for _ in range(world)]
     dist.all_gather(parts, mine.to(dev))
-    ctx.peer_import(rank, world, torch.stack(parts).cpu().numpy())
+    flag = torch.tensor([ok], dtype=torch.int32, device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if int(flag.item()) == 1:
+        try:
+            ctx.peer_import(rank, world, torch.stack(parts).cpu().numpy())
+        except Exception:
+            ok = 0
+    else:
+        ok = 0
+    flag = torch.tensor([ok], dtype=torch.int32, device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    return int(flag.item()) == 1

@@ -21,7 +21,7 @@ def main():
     dist.init_process_group("gloo")
     out = {"rank": rank}
     with rpe.Context(local) as ctx:
-        sharding.peer_setup(dist, ctx, rank, world)
+        assert sharding.peer_setup(dist, ctx, rank, world)
         results = []
         for trial, (n, H, method, m) in enumerate([(20000, 1024, "shinji", 3), (5000, 300, "shinji", 3), (6000, 256, "nl_shinji_kneip", 4)]):
             q, t = rpe.sim_pose(3 + trial)
