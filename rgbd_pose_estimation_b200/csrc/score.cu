@@ -211,6 +211,14 @@ struct WlSegment {
     else
       st->wl_overflow = 1u;
   }
+  // several entries of one thread with a single shared-memory atomic: reserve(k), then put(i), put(i + 1), ...
+  __device__ __forceinline__ unsigned int reserve(unsigned int k) { return atomicAdd(n, k); }
+  __device__ __forceinline__ void put(unsigned int i, uint2 e, FrameStats* st) {
+    if (i < cap)
+      base[i] = e;
+    else
+      st->wl_overflow = 1u;
+  }
   // every thread of the CTA calls this once, after its last push
   __device__ __forceinline__ void publish(const Worklist& wl, FrameStats* st) {
     __syncthreads();
@@ -789,18 +797,50 @@ score_multi_fast_kernel(const float4* __restrict__ pk, int npairs_pad, int pairs
       val[2][1] = g.y;
       bnd[2][0] = bnd[2][1] = bc[k].band_n;
     }
+    if (DIRECT) {
+      // Straight-line common case: every sign bit is counted and the band tests are folded into one predicate;
+      // only a unit that holds a borderline value branches, takes that value out of the count and queues it.
+      bool any = false;
+#pragma unroll
+      for (int mod = 0; mod < 3; ++mod) {
+        if ((mod == 0 && !KT::k2) || (mod == 1 && !KT::k3) || (mod == 2 && !KT::kn)) continue;
+#pragma unroll
+        for (int uu = 0; uu < 2; ++uu) {
+          cnt[k] += (int)(__float_as_uint(val[mod][uu]) >> 31);
+          any = any || (fabsf(val[mod][uu]) <= bnd[mod][uu]);
+        }
+      }
+      if (any) {  // one reservation for all borderline values of this thread's unit
+        unsigned int nb = 0;
+#pragma unroll
+        for (int mod = 0; mod < 3; ++mod) {
+          if ((mod == 0 && !KT::k2) || (mod == 1 && !KT::k3) || (mod == 2 && !KT::kn)) continue;
+#pragma unroll
+          for (int uu = 0; uu < 2; ++uu) nb += (fabsf(val[mod][uu]) <= bnd[mod][uu]) ? 1u : 0u;
+        }
+        unsigned int wi = seg.reserve(nb);
+#pragma unroll
+        for (int mod = 0; mod < 3; ++mod) {
+          if ((mod == 0 && !KT::k2) || (mod == 1 && !KT::k3) || (mod == 2 && !KT::kn)) continue;
+#pragma unroll
+          for (int uu = 0; uu < 2; ++uu) {
+            const float v = val[mod][uu];
+            if (fabsf(v) <= bnd[mod][uu]) {
+              cnt[k] -= (int)(__float_as_uint(v) >> 31);
+              seg.put(wi++, make_uint2((unsigned int)slot[k], (unsigned int)(corr0 + uu) | ((unsigned int)mod << 30)), st);
+            }
+          }
+        }
+      }
+      return;
+    }
 #pragma unroll
     for (int mod = 0; mod < 3; ++mod) {
       if ((mod == 0 && !KT::k2) || (mod == 1 && !KT::k3) || (mod == 2 && !KT::kn)) continue;
 #pragma unroll
       for (int uu = 0; uu < 2; ++uu) {
         const float v = val[mod][uu];
-        if (DIRECT) {
-          if (fabsf(v) <= bnd[mod][uu])
-            seg.push(make_uint2((unsigned int)slot[k], (unsigned int)(corr0 + uu) | ((unsigned int)mod << 30)), st);
-          else
-            cnt[k] += (int)(__float_as_uint(v) >> 31);
-        } else if (!rescan) {
+        if (!rescan) {
           cnt[k] += (int)(__float_as_uint(v) >> 31);
           flag = flag || (fabsf(v) <= bnd[mod][uu]);
         } else if (fabsf(v) <= bnd[mod][uu]) {
@@ -1014,6 +1054,7 @@ __device__ __forceinline__ bool exact_eval(int method, int modality, const Frame
 }
 
 constexpr int kFixupChunks = 4;  // CTAs per worklist segment
+constexpr unsigned int kFixupWindow = 1024;  // slots per histogram: the widest scorer column (512 threads x 2 hypotheses)
 __global__ void __launch_bounds__(256)
 fixup_kernel(int method, FrameView f, const HypGen* __restrict__ gen, Thresh th, int32_t* __restrict__ votes,
              const FrameStats* __restrict__ st, Worklist wl, int nseg, int slot_begin, int slot_end) {
@@ -1026,7 +1067,15 @@ fixup_kernel(int method, FrameView f, const HypGen* __restrict__ gen, Thresh th,
   }
   const unsigned int cap = wl.capacity / (unsigned int)nseg;
   const unsigned int count = min(wl.counts[blockIdx.x], cap);
+  if (count <= blockIdx.y * blockDim.x) return;  // nothing for this CTA (uniform)
   const uint2* seg = wl.entries + (size_t)blockIdx.x * cap;
+  // A segment was filled by one scorer CTA, i.e. by one column of at most 1024 consecutive slots, and the good
+  // hypotheses collect most of the borderline evaluations: votes are gathered in a shared-memory histogram of that
+  // window and flushed with one global atomic per touched slot (a slot outside the window goes to memory directly).
+  __shared__ int hist[kFixupWindow];
+  const unsigned int window = ((unsigned int)seg[0].x - (unsigned int)slot_begin) / kFixupWindow;
+  for (int i = threadIdx.x; i < kFixupWindow; i += blockDim.x) hist[i] = 0;
+  __syncthreads();
   for (unsigned int i = blockIdx.y * blockDim.x + threadIdx.x; i < count; i += gridDim.y * blockDim.x) {
     const uint2 e = seg[i];
     const int slot = (int)e.x;
@@ -1035,8 +1084,17 @@ fixup_kernel(int method, FrameView f, const HypGen* __restrict__ gen, Thresh th,
     const HypGen h = gen[slot];
     float Rm[9];
     if (method == RPE_KNEIP) ex_quat_to_matrix(h.q, Rm);
-    if (exact_eval(method, modality, f, h, Rm, c, th)) atomicAdd(&votes[slot], 1);
+    if (exact_eval(method, modality, f, h, Rm, c, th)) {
+      const unsigned int rel = (unsigned int)slot - (unsigned int)slot_begin;
+      if (rel / kFixupWindow == window)
+        atomicAdd(&hist[rel % kFixupWindow], 1);
+      else
+        atomicAdd(&votes[slot], 1);
+    }
   }
+  __syncthreads();
+  for (int i = threadIdx.x; i < kFixupWindow; i += blockDim.x)
+    if (hist[i]) atomicAdd(&votes[slot_begin + (int)(window * kFixupWindow) + i], hist[i]);
 }
 
 // Stage API (rpe_score called several times per frame): mark the queued evaluations as resolved so that the next
