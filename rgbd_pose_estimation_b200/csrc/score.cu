@@ -904,17 +904,18 @@ score_multi_fast_kernel(const float4* __restrict__ pk, int npairs_pad, int pairs
   seg.publish(wl, st);
 }
 
-template <int KIND>
-static int launch_multi(const FrameView& f, const HypGen* gen, const HypFast* fast, int slot_begin, int slot_end, Thresh th,
-                         int32_t* votes, FrameStats* st, Worklist wl, int num_sms, cudaStream_t s) {
-  constexpr int THREADS = 256, HPT = 2;
+template <int KIND, int THREADS>
+static int launch_multi_t(const FrameView& f, const HypGen* gen, const HypFast* fast, int slot_begin, int slot_end, Thresh th,
+                           int32_t* votes, FrameStats* st, Worklist wl, int num_sms, cudaStream_t s) {
+  constexpr int HPT = 2;
+  constexpr int CTAS_PER_SM = 512 / THREADS;  // 16 warps per SM either way
   constexpr int F4 = KindTraits<KIND>::f4pp;
-  // two stages of TILE pairs; sized so that at least two 256-thread CTAs (16 warps) fit on an SM for every kind
-  constexpr int TILE = F4 <= 3 ? 1024 : (F4 <= 6 ? 512 : 256);
+  // two stages of TILE pairs; sized so that CTAS_PER_SM CTAs fit on an SM for every kind (<= 98 KB per 256 threads)
+  constexpr int TILE = (F4 <= 3 ? 1024 : (F4 <= 6 ? 512 : 256)) * (THREADS == 512 && F4 > 3 ? 2 : 1);
   const int nslots = slot_end - slot_begin;
   const int gy = (nslots + THREADS * HPT - 1) / (THREADS * HPT);
   const int groups = f.npairs_pad / kSubPairs;
-  int gx = (2 * num_sms) / gy;  // never more CTAs than the 2-per-SM resident slots: a partial second wave doubles the time
+  int gx = (CTAS_PER_SM * num_sms) / gy;  // never more CTAs than the resident slots: a partial second wave doubles the time
   if (gx < 1) gx = 1;
   if (gx > groups) gx = groups;
   const int groups_per_cta = (groups + gx - 1) / gx;
@@ -939,6 +940,17 @@ static int launch_multi(const FrameView& f, const HypGen* gen, const HypFast* fa
     score_multi_fast_kernel<KIND, TILE, THREADS, false><<<dim3(gx, gy), THREADS, smem, s>>>(
         f.pk, f.npairs_pad, pairs_per_cta, fast, gen, slot_begin, slot_end, th, votes, st, wl);
   return gx * gy;
+}
+
+// CTA width: 512 threads (one CTA per SM, a column of 1024 slots) for wide slot ranges, 256 threads (two CTAs per SM,
+// 512 slots) for narrow ones (short passes, hypothesis-sharded frames). RPE_MULTI_THREADS=256|512 forces one.
+template <int KIND>
+static int launch_multi(const FrameView& f, const HypGen* gen, const HypFast* fast, int slot_begin, int slot_end, Thresh th,
+                         int32_t* votes, FrameStats* st, Worklist wl, int num_sms, cudaStream_t s) {
+  static const int forced = getenv("RPE_MULTI_THREADS") ? atoi(getenv("RPE_MULTI_THREADS")) : 0;
+  const bool wide = forced ? forced == 512 : (slot_end - slot_begin) > 512;
+  if (wide) return launch_multi_t<KIND, 512>(f, gen, fast, slot_begin, slot_end, th, votes, st, wl, num_sms, s);
+  return launch_multi_t<KIND, 256>(f, gen, fast, slot_begin, slot_end, th, votes, st, wl, num_sms, s);
 }
 
 static bool g_use_packed = true;

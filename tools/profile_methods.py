@@ -19,7 +19,10 @@ FLOP = {"shinji": 26, "kneip": 30, "shinji_kneip": 38, "nl_kneip": 50, "nl_shinj
 ctx = rpe.Context(0)
 ctx.enable_stage_timing(1)
 out = {}
+ONLY = [x for x in os.environ.get("METHODS", "").split(",") if x]   # e.g. METHODS=kneip,nl_shinji_kneip
 for name, m in rpe.METHODS.items():
+    if ONLY and name not in ONLY:
+        continue
     S = rpe.sample_table(1, N, rpe.method_sample_size(m), H)
     ms = []
     for i in range(5):
