@@ -157,6 +157,27 @@ def cpu_run(frame, samples, nthreads, full=True):
                       xc=frame["xc"], xw=frame["xw"], want_arrays=False)
 
 
+def time_reference_sources(frame, iters=16):
+    """Informational: the reference's OWN shinji_ransac2 loop (oracle/_ref/libref_shim.so: /root/reference/pose/*.hpp
+    compiled unmodified against the Eigen / Sophus API stand-in of oracle/ref_shim/), single thread like the
+    reference, `iters` iterations with the adaptive stop disabled (confidence 1). Slower than the oracle port, which is
+    why the port — multi-threaded — stays the reported baseline. None when the library is not there."""
+    try:
+        from tests import refshim
+        if not os.path.exists(refshim.SO):
+            return None
+        refshim.ransac(0, 1, 2, thr3d=THR3D, confidence=1.0, xc=frame["xc"], xw=frame["xw"])  # warm-up
+        t0 = time.perf_counter()
+        r = refshim.ransac(0, 1, iters, thr3d=THR3D, confidence=1.0, xc=frame["xc"], xw=frame["xw"])
+        dt = time.perf_counter() - t0
+        if r["iter_final"] != iters:
+            return None
+        return {"value": iters * N_CORR / dt, "unit": "evals/s", "cores": 1,
+                "sample": f"{iters} iterations x {N_CORR} correspondences of shinji_ransac2 as written in the reference"}
+    except Exception as e:  # never let the informational leg break the line
+        return {"unavailable": str(e)[:200]}
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
@@ -187,6 +208,7 @@ def run_reference(args, rank):
         "gpu_launches": 0,
         "note": "reference cannot be compiled here (needs Eigen); this is the oracle port of its CPU path (oracle/README.md)",
     }
+    line["cpu_baseline"]["reference_sources_single_thread"] = time_reference_sources(frame)
     print(json.dumps(line))
 
 
