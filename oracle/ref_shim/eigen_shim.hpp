@@ -279,6 +279,23 @@ class Matrix : public MatrixBase<Matrix<T, R, C, Opt, MR, MC> >, public ShimStor
   Block<T, 1, C> row(int i) { return Block<T, 1, C>(data() + i, 1, cols_(), rows_()); }
   const Block<T, 1, C> row(int i) const { return Block<T, 1, C>(const_cast<T*>(data()) + i, 1, cols_(), rows_()); }
   static Matrix Zero() { return Matrix(); }
+  static Matrix Ones(int r, int c) {
+    Matrix m;
+    m.resize(r, c);
+    m.setOnes();
+    return m;
+  }
+  // DenseBase::Random: every coefficient is internal::random<Scalar>() = x + (y - x) * Scalar(std::rand()) / Scalar(RAND_MAX)
+  // with (x, y) = (-1, 1) for a signed scalar (Eigen 3.3 MathFunctions.h, random_default_impl), assigned in storage
+  // (column-major) order. Used by the reference's Simulator only (Simulator.hpp:19,33,140).
+  static Matrix Random(int r, int c) {
+    Matrix m;
+    m.resize(r, c);
+    for (int j = 0; j < c; ++j)
+      for (int i = 0; i < r; ++i) m.ref(i, j) = T(-1) + (T(1) - T(-1)) * T(std::rand()) / T(RAND_MAX);
+    return m;
+  }
+  static Matrix Random() { return Random(R, C); }
   static Matrix Identity() {
     Matrix m;
     for (int i = 0; i < m.rows_() && i < m.cols_(); ++i) m.ref(i, i) = T(1);

@@ -208,3 +208,62 @@ REF_DEFINE(f, float)
 REF_DEFINE(d, double)
 
 }  // extern "C"
+
+// ---- the reference's own Simulator (Simulator.hpp), for inputs made exactly the way SimpleMain / TestMain make them ----
+#include <Simulator.hpp>
+
+namespace {
+template <class T>
+void copy3(const Eigen::Matrix<T, Eigen::Dynamic, Eigen::Dynamic>& m, T* out) {
+  if (out) memcpy(out, m.data(), sizeof(T) * (size_t)m.rows() * m.cols());
+}
+// kind 0: simulate_3d_3d_correspondences, 1: simulate_2d_3d_correspondences, 2: simulate_2d_3d_nl_correspondences.
+// Pose drawn as SimpleMain.cpp:22-23 does; ::rand() seeded with `seed`, the global normal generator re-seeded with it too.
+template <class T>
+int run_sim(int kind, unsigned seed, int n, T n2d, T or2d, T n3d, T or3d, T nnl, T ornl, T min_depth, T max_depth, T f,
+            int gaussian, T* q4, T* t3, T* xw, T* nw, T* xc, T* nc, T* bv, T* weights3) {
+  typedef Eigen::Matrix<T, Eigen::Dynamic, Eigen::Dynamic> MX;
+  srand(seed);
+  generator.seed(seed);
+  distribution.reset();
+  Sophus::shim_ensure_failures() = 0;
+  const Eigen::Matrix<T, 3, 1> t = generate_random_translation_uniform<T>(T(5.0));
+  const Sophus::SO3<T> R = generate_random_rotation<T>(T(M_PI / 2), false);
+  put_pose<T>(R, t, q4, t3);
+  MX Q, M, P, N, U, W(n, 3);
+  if (kind == 0) {
+    simulate_3d_3d_correspondences<T>(R, t, n, n3d, or3d, min_depth, max_depth, f, gaussian != 0, &Q, &P, &W);
+  } else if (kind == 1) {
+    simulate_2d_3d_correspondences<T>(R, t, n, n2d, or2d, min_depth, max_depth, f, gaussian != 0, &Q, &U, &P, &W);
+  } else if (kind == 2) {
+    simulate_2d_3d_nl_correspondences<T>(R, t, n, n2d, or2d, n3d, or3d, nnl, ornl, min_depth, max_depth, f, gaussian != 0, &Q,
+                                         &M, &P, &N, &U, &W);
+  } else {
+    return -1;
+  }
+  copy3(Q, xw);
+  copy3(P, xc);
+  if (kind != 0) copy3(U, bv);
+  if (kind == 2) {
+    copy3(M, nw);
+    copy3(N, nc);
+  }
+  copy3(W, weights3);
+  return Sophus::shim_ensure_failures() == 0 ? 0 : 1;
+}
+}  // namespace
+
+extern "C" {
+int ref_sim_f(int kind, unsigned seed, int n, float n2d, float or2d, float n3d, float or3d, float nnl, float ornl,
+              float min_depth, float max_depth, float f, int gaussian, float* q4, float* t3, float* xw, float* nw, float* xc,
+              float* nc, float* bv, float* weights3) {
+  return run_sim<float>(kind, seed, n, n2d, or2d, n3d, or3d, nnl, ornl, min_depth, max_depth, f, gaussian, q4, t3, xw, nw, xc,
+                        nc, bv, weights3);
+}
+int ref_sim_d(int kind, unsigned seed, int n, double n2d, double or2d, double n3d, double or3d, double nnl, double ornl,
+              double min_depth, double max_depth, double f, int gaussian, double* q4, double* t3, double* xw, double* nw,
+              double* xc, double* nc, double* bv, double* weights3) {
+  return run_sim<double>(kind, seed, n, n2d, or2d, n3d, or3d, nnl, ornl, min_depth, max_depth, f, gaussian, q4, t3, xw, nw,
+                         xc, nc, bv, weights3);
+}
+}

@@ -134,3 +134,21 @@ def update_num_iters(p, ep, model_points, max_iters, dt=np.float32):
     fn.restype = C.c_int
     fn.argtypes = [ct, ct, C.c_int, C.c_int]
     return fn(p, ep, model_points, max_iters)
+
+
+def sim(kind, seed, n, n2d=1.0, or2d=0.3, n3d=0.05, or3d=0.3, nnl=float(np.deg2rad(2.0)), ornl=0.3, min_depth=0.4,
+        max_depth=8.0, f=585.0, gaussian=True, dt=np.float32):
+    """The reference's own Simulator.hpp (kind 0: simulate_3d_3d, 1: simulate_2d_3d, 2: simulate_2d_3d_nl) with the
+    pose drawn as SimpleMain.cpp does, ::rand() and the normal generator seeded with `seed`."""
+    s, npdt, ct = _suf(dt)
+    q, t = np.zeros(4, npdt), np.zeros(3, npdt)
+    out = {k: np.full((n, 3), np.nan, npdt) for k in ("xw", "nw", "xc", "nc", "bv")}
+    w = np.zeros((3, n), npdt)
+    fn = getattr(lib(), f"ref_sim_{s}")
+    fn.restype = C.c_int
+    fn.argtypes = [C.c_int, C.c_uint, C.c_int] + [ct] * 9 + [C.c_int] + [_vp] * 8
+    rc = fn(kind, seed, n, n2d, or2d, n3d, or3d, nnl, ornl, min_depth, max_depth, f, 1 if gaussian else 0, _p(q), _p(t),
+            _p(out["xw"]), _p(out["nw"]), _p(out["xc"]), _p(out["nc"]), _p(out["bv"]), _p(w))
+    assert rc == 0, rc
+    out.update({"q": q, "t": t, "weights": w})
+    return out

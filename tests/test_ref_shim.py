@@ -141,3 +141,79 @@ def test_refits_bit_identical(orc, rpe, dt):
             q, t = orc.nl_shinji_kneip_ls(a["q"], a["t"], a["mask"], a["max_votes"], weights3=w, dt=dt, **d)
             assert _same(q, b["q_refit"]) and _same(t, b["t_refit"]), (seed, use_w)
             assert not _same(q, a["q"])  # the refit did move the pose
+
+
+def _Rq(q):
+    x, y, z, w = [float(v) for v in q]
+    return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                     [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                     [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+
+
+def _stats(d, q, t):
+    R = _Rq(q)
+    y = d["xw"].astype(np.float64) @ R.T + np.asarray(t, np.float64)
+    e3 = np.linalg.norm(d["xc"] - y, axis=1)
+    yn = y / np.linalg.norm(y, axis=1, keepdims=True)
+    c2 = (yn * d["bv"]).sum(1)
+    cn = (d["nc"] * (d["nw"].astype(np.float64) @ R.T)).sum(1)
+    return {"in3": float((e3 < 0.2).mean()), "med3": float(np.median(e3)), "in2": float((c2 > np.cos(np.arctan(8 / F))).mean()),
+            "inn": float((cn > np.cos(0.1)).mean()), "w": d["weights"].mean(axis=1), "zmin": float(d["xc"][:, 2].min()),
+            "zmax": float(d["xc"][:, 2].max()), "facing": float((d["nc"][:, 2] < 0).mean())}
+
+
+def test_reference_simulator_and_ours_draw_from_the_same_distributions(rpe):
+    """Simulator.hpp:158-173,175-233,316-367 run as written (Matrix::Random on ::rand(), std::normal_distribution,
+    RandomElements for the outlier positions) next to the library's seeded restatement: same inlier fractions per
+    modality, noise level, PROSAC weights, depth range and camera-facing normals (the generators differ, so the
+    comparison is statistical)."""
+    n = 20000
+    ref = refshim.sim(2, 11, n, or2d=0.3, or3d=0.4, ornl=0.2)
+    q, t = rpe.sim_pose(11)
+    ours = rpe.sim_2d_3d_nl(12, q, t, n, or2d=0.3, or3d=0.4, ornl=0.2)
+    a, b = _stats(ref, ref["q"], ref["t"]), _stats(ours, q, t)
+    for k, tol in (("in3", 0.015), ("in2", 0.015), ("inn", 0.015), ("med3", 0.01), ("zmin", 0.3), ("zmax", 0.3), ("facing", 0.0)):
+        assert abs(a[k] - b[k]) <= tol, (k, a[k], b[k])
+    assert abs(a["in3"] - 0.6) < 0.02 and abs(a["in2"] - 0.7) < 0.02 and abs(a["inn"] - 0.8) < 0.03
+    assert np.allclose(a["w"], b["w"], rtol=0.06), (a["w"], b["w"])
+    assert np.abs(np.linalg.norm(ref["bv"], axis=1) - 1).max() < 1e-6
+
+
+@pytest.mark.parametrize("config", [1, 2, 3])
+def test_baseline_configs_on_reference_simulated_inputs(orc, config):
+    """BASELINE.json configs #1-#3 end to end the way SimpleMain / TestMain run them: inputs from the reference's own
+    Simulator, pose drawn as SimpleMain.cpp:22-23, the reference's estimator and refit on ::rand() — against the oracle
+    on the same arrays. (#3 with 30 000 correspondences: the reference's `short` index lists end at 32 767.)"""
+    dt = np.float32
+    if config == 1:   # SimpleMain.cpp:30-45,76-83: shinji_ransac2 + shinji_ls1, Iter0 = 100 000, confidence 0.9999
+        d = refshim.sim(0, 101, 1000, n3d=0.1, or3d=0.5, dt=dt)
+        method, n, iters, thr, conf, refit = 0, 1000, 100000, (0.25, 0.0, 0.0), 0.9999, 1
+    elif config == 2:  # kneip_ransac on 10 000 2-D / 3-D correspondences with 70 % outliers
+        d = refshim.sim(1, 102, 10000, n2d=1.0, or2d=0.7, dt=dt)
+        method, n, iters, thr, conf, refit = 1, 10000, 2000, (0.0, 8.0, 0.0), 0.99, 0
+    else:              # nl_shinji_kneip_ransac + nl_shinji_kneip_ls, three modalities (Parameters.yml:15-19 thresholds)
+        d = refshim.sim(2, 103, 30000, n2d=1.0, or2d=0.3, n3d=0.05, or3d=0.4, ornl=0.2, dt=dt)
+        method, n, iters, thr, conf, refit = 5, 30000, 1024, (0.2, 8.0, 0.1), 0.99, 2
+    arrs = {k: d[k] for k in ("bv", "xc", "nc", "xw", "nw")}
+    seed = 7 + config
+    ct, cn = refshim.cos_thr(thr[1], F, dt) if thr[1] else 0.0, refshim.cos_nl(thr[2], dt) if thr[2] else 0.0
+    S = orc.sample_table(seed, n, 3 if method == 0 else 4, min(iters, 4096))  # the loop stops long before 4 096 draws
+    a = orc.ransac(method, S, thr3d=thr[0], cos_thr=ct, cos_nl=cn, confidence=conf, full=False, dt=dt, **arrs)
+    b = refshim.ransac(method, seed, iters, thr3d=thr[0], thr2d=thr[1], focal=F, thrN=thr[2], confidence=conf, refit=refit,
+                       dt=dt, **arrs)
+    assert a["iters_run"] < S.shape[0]
+    # (config #1: the oracle starts from the table length instead of 100 000; the adaptive bound is far below both)
+    assert b["iter_final"] < S.shape[0]
+    _assert_same_run(a, b, ("config", method, config, seed))
+    assert a["max_votes"] == b["max_votes"] and _same(a["q"], b["q"]) and _same(a["t"], b["t"])
+    assert np.array_equal(a["mask"], b["mask"][:a["mask"].shape[0]])
+    # the accepted pose is the simulated one
+    Rg, Re = _Rq(d["q"]), _Rq(b["q_refit"])
+    ang = np.arccos(np.clip((np.trace(Rg @ Re.T) - 1) / 2, -1, 1))
+    assert ang < 0.02 and np.linalg.norm(b["t_refit"] - d["t"]) < 0.1, (ang, b["t_refit"], d["t"])
+    if refit == 1:
+        q, t, ok = orc.shinji_ls(arrs["xc"], arrs["xw"], a["mask"][1], dt=dt)
+        assert ok and _same(q, b["q_refit"]) and _same(t, b["t_refit"])
+    if refit == 2:
+        q, t = orc.nl_shinji_kneip_ls(a["q"], a["t"], a["mask"], a["max_votes"], dt=dt, **arrs)
+        assert _same(q, b["q_refit"]) and _same(t, b["t_refit"])
