@@ -217,7 +217,8 @@ template <class T>
 void copy3(const Eigen::Matrix<T, Eigen::Dynamic, Eigen::Dynamic>& m, T* out) {
   if (out) memcpy(out, m.data(), sizeof(T) * (size_t)m.rows() * m.cols());
 }
-// kind 0: simulate_3d_3d_correspondences, 1: simulate_2d_3d_correspondences, 2: simulate_2d_3d_nl_correspondences.
+// kind 0: simulate_3d_3d_correspondences, 1: simulate_2d_3d_correspondences, 2: simulate_2d_3d_nl_correspondences,
+// 3: simulate_kinect_2d_3d_nl_correspondences.
 // Pose drawn as SimpleMain.cpp:22-23 does; ::rand() seeded with `seed`, the global normal generator re-seeded with it too.
 template <class T>
 int run_sim(int kind, unsigned seed, int n, T n2d, T or2d, T n3d, T or3d, T nnl, T ornl, T min_depth, T max_depth, T f,
@@ -238,13 +239,16 @@ int run_sim(int kind, unsigned seed, int n, T n2d, T or2d, T n3d, T or3d, T nnl,
   } else if (kind == 2) {
     simulate_2d_3d_nl_correspondences<T>(R, t, n, n2d, or2d, n3d, or3d, nnl, ornl, min_depth, max_depth, f, gaussian != 0, &Q,
                                          &M, &P, &N, &U, &W);
+  } else if (kind == 3) {  // Kinect lateral / axial noise model (Simulator.hpp:368-436); n3d is not used
+    simulate_kinect_2d_3d_nl_correspondences<T>(R, t, n, n2d, or2d, or3d, nnl, ornl, min_depth, max_depth, f, &Q, &M, &P, &N, &U,
+                                                &W);
   } else {
     return -1;
   }
   copy3(Q, xw);
   copy3(P, xc);
   if (kind != 0) copy3(U, bv);
-  if (kind == 2) {
+  if (kind >= 2) {
     copy3(M, nw);
     copy3(N, nc);
   }

@@ -217,3 +217,34 @@ def test_baseline_configs_on_reference_simulated_inputs(orc, config):
     if refit == 2:
         q, t = orc.nl_shinji_kneip_ls(a["q"], a["t"], a["mask"], a["max_votes"], dt=dt, **arrs)
         assert _same(q, b["q_refit"]) and _same(t, b["t_refit"])
+
+
+def test_reference_kinect_simulator_and_ours_agree_statistically(rpe):
+    """simulate_kinect_2d_3d_nl_correspondences (Simulator.hpp:368-436) as written in the reference next to
+    rpe_sim_kinect_2d_3d_nl: the axial weights sigma_a(0, min_depth) / sigma_a follow the same law of depth, the axial and
+    lateral residuals have the same robust spread per depth band, 3-D outliers come in the same proportion."""
+    n = 60000
+    ref = refshim.sim(3, 31, n, n2d=1.0, or2d=0.0, or3d=0.2, ornl=0.0)
+    q, t = rpe.sim_pose(31)
+    ours = rpe.sim_kinect_2d_3d_nl(32, q, t, n, n2d=1.0, or2d=0.0, or3d=0.2, nnl=float(np.deg2rad(2.0)), ornl=0.0)
+
+    def summary(d, q, t):
+        R = _Rq(q)
+        Pgt = d["xw"].astype(np.float64) @ R.T + np.asarray(t, np.float64)
+        e = d["xc"].astype(np.float64) - Pgt
+        inl = np.abs(e).max(axis=1) < 0.5
+        z, w = Pgt[:, 2], d["weights"][1].astype(np.float64)
+        out = {"outliers": float((~inl).mean()), "w_med": float(np.median(w)), "w_max": float(w.max())}
+        for lo, hi in ((0.5, 2.0), (3.0, 5.0), (6.0, 8.0)):
+            sel = inl & (z > lo) & (z < hi)
+            out[f"ax_{lo}"] = 1.4826 * float(np.median(np.abs(e[sel, 2])))
+            out[f"lat_{lo}"] = 1.4826 * float(np.median(np.abs(e[sel, 0])))
+            out[f"w_{lo}"] = float(np.median(w[sel]))
+        return out
+
+    a, b = summary(ref, ref["q"], ref["t"]), summary(ours, q, t)
+    assert abs(a["outliers"] - b["outliers"]) < 0.01 and abs(a["outliers"] - 0.2) < 0.01
+    assert a["w_max"] <= 1.0 + 1e-6 and b["w_max"] <= 1.0 + 1e-6
+    for k in a:
+        if k[:3] in ("ax_", "lat", "w_0", "w_3", "w_6", "w_m"):
+            assert abs(a[k] / b[k] - 1) < 0.08, (k, a[k], b[k])
