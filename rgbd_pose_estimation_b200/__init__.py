@@ -14,6 +14,7 @@ from .capi import (  # noqa: F401
     METHODS,
     REFITS,
     sample_table,
+    Sampler,
     prosac_table,
     update_num_iters,
     sim_pose,
@@ -28,7 +29,7 @@ from .capi import (  # noqa: F401
 )
 
 __all__ = [
-    "Context", "RpeError", "lib", "lib_path", "METHODS", "REFITS", "sample_table", "prosac_table",
+    "Context", "RpeError", "lib", "lib_path", "METHODS", "REFITS", "sample_table", "prosac_table", "Sampler",
     "update_num_iters", "sim_pose", "sim_3d_3d", "sim_2d_3d", "sim_2d_3d_nl", "sim_kinect_2d_3d_nl", "method_slots",
     "method_mask_cols", "method_sample_size", "pinned_empty",
 ]

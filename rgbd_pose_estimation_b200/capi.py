@@ -138,6 +138,9 @@ _sig("rpe_finish", C.c_int, [_vp, C.c_int, C.c_int, C.c_float, C.c_float, C.c_fl
 _sig("rpe_update_num_iters", C.c_int, [C.c_float, C.c_float, C.c_int, C.c_int])
 _sig("rpe_sample_table", C.c_int, [C.c_uint32, C.c_int, C.c_int, C.c_int, _vp])
 _sig("rpe_prosac_table", C.c_int, [C.c_uint32, C.c_int, C.c_int, C.c_int, _vp, _vp])
+_sig("rpe_sampler_create", C.c_int, [C.c_uint32, C.c_int, C.POINTER(_vp)])
+_sig("rpe_sampler_rows", C.c_int, [_vp, C.c_int, C.c_int, _vp])
+_sig("rpe_sampler_destroy", None, [_vp])
 _sig("rpe_sim_pose", C.c_int, [C.c_uint64, C.c_float, C.c_float, _vp, _vp])
 _sig("rpe_sim_3d_3d", C.c_int, [C.c_uint64, _vp, _vp, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
                                 C.c_int, _vp, _vp, _vp])
@@ -161,7 +164,7 @@ DECLARED_SYMBOLS = [
     "rpe_upload_device", "rpe_num_correspondences", "rpe_ransac", "rpe_ransac_async", "rpe_ransac_stream", "rpe_set_first_pass_iters", "rpe_upload_f64", "rpe_ransac_f64", "rpe_get_hypotheses_f64", "rpe_refit", "rpe_refit_async",
     "rpe_set_pose", "rpe_set_mask", "rpe_generate", "rpe_get_hypotheses", "rpe_set_hypotheses", "rpe_score",
     "rpe_get_votes", "rpe_set_votes", "rpe_votes_device_ptr", "rpe_peer_export", "rpe_peer_import", "rpe_peer_import_local", "rpe_exchange_votes", "rpe_peer_status", "rpe_ransac_sharded", "rpe_ransac_sharded_async", "rpe_finish", "rpe_update_num_iters", "rpe_sample_table",
-    "rpe_prosac_table", "rpe_sim_pose", "rpe_sim_3d_3d", "rpe_sim_2d_3d", "rpe_sim_2d_3d_nl", "rpe_sim_kinect_2d_3d_nl", "rpe_sim_kinect_2d_3d_nl_device", "rpe_sim_3d_3d_device",
+    "rpe_prosac_table", "rpe_sampler_create", "rpe_sampler_rows", "rpe_sampler_destroy", "rpe_sim_pose", "rpe_sim_3d_3d", "rpe_sim_2d_3d", "rpe_sim_2d_3d_nl", "rpe_sim_kinect_2d_3d_nl", "rpe_sim_kinect_2d_3d_nl_device", "rpe_sim_3d_3d_device",
     "rpe_sim_2d_3d_nl_device", "rpe_download", "rpe_ao", "rpe_ao_ransac",
     "rpe_measure_ffma_tflops", "rpe_last_stage_ms", "rpe_enable_stage_timing",
 ]
@@ -204,6 +207,31 @@ def prosac_table(seed: int, n: int, m: int, H: int, weights=None) -> np.ndarray:
     w = _f32(weights)
     _check(lib.rpe_prosac_table(seed, n, m, H, _ptr(w), _ptr(out)))
     return out
+
+
+class Sampler:
+    """RandomElements<int> that lives across calls (rpe_sampler_*): per-frame sample tables at O(H m) each."""
+
+    def __init__(self, seed: int, n: int):
+        self._h = _vp()
+        _check(lib.rpe_sampler_create(seed, n, C.byref(self._h)))
+
+    def rows(self, m: int, H: int, out: np.ndarray | None = None) -> np.ndarray:
+        if out is None:
+            out = np.empty((H, 4), dtype=np.int32)
+        _check(lib.rpe_sampler_rows(self._h, m, H, _ptr(out)))
+        return out
+
+    def close(self):
+        if self._h:
+            lib.rpe_sampler_destroy(self._h)
+            self._h = _vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def update_num_iters(p: float, ep: float, model_points: int, max_iters: int) -> int:

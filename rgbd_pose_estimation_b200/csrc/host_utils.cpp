@@ -10,6 +10,14 @@
 #include "../../include/rpe/sim_core.hpp"
 #include "../../include/rpe_c_api.h"
 
+struct rpe_sampler {
+  rpe::GlibcRandom src;
+  RandomElements<int> re;
+  std::vector<int> sel;
+  int n;
+  rpe_sampler(uint32_t seed, int n_) : src(seed), re(n_, &src), n(n_) {}
+};
+
 extern "C" {
 
 int rpe_update_num_iters(float p, float ep, int model_points, int max_iters) {
@@ -27,6 +35,21 @@ int rpe_sample_table(uint32_t seed, int n, int m, int H, int32_t* samples) {
   }
   return RPE_OK;
 }
+
+int rpe_sampler_create(uint32_t seed, int n, rpe_sampler** out) {
+  if (!out || n <= 0) return RPE_ERR_ARG;
+  *out = new rpe_sampler(seed, n);
+  return RPE_OK;
+}
+int rpe_sampler_rows(rpe_sampler* s, int m, int H, int32_t* samples) {
+  if (!s || !samples || m <= 0 || m > 4 || m > s->n || H < 0) return RPE_ERR_ARG;
+  for (int h = 0; h < H; ++h) {
+    s->re.run(m, &s->sel);
+    for (int k = 0; k < 4; ++k) samples[4 * h + k] = k < m ? s->sel[k] : -1;
+  }
+  return RPE_OK;
+}
+void rpe_sampler_destroy(rpe_sampler* s) { delete s; }
 
 int rpe_prosac_table(uint32_t seed, int n, int m, int H, const float* weights, int32_t* samples) {
   if (!samples || n <= 0 || m <= 1 || m > 4 || m > n || H < 0) return RPE_ERR_ARG;

@@ -96,3 +96,25 @@ def test_update_num_iters_host(rpe):
     assert rpe.update_num_iters(0.9999, 0.5, 3, 100000) == 69
     assert rpe.update_num_iters(0.99, 0.0, 3, 100) == 0
     assert rpe.update_num_iters(0.99, 1.0, 3, 100) == 100
+
+
+def test_persistent_sampler_continues_the_rand_stream(rpe):
+    """rpe_sampler_*: a RandomElements that lives across calls gives the rows rpe_sample_table gives, split over calls."""
+    import time
+    n, H = 5000, 300
+    ref = rpe.sample_table(7, n, 3, H)
+    s = rpe.Sampler(7, n)
+    got = np.vstack([s.rows(3, 100), s.rows(3, 150), s.rows(3, 50)])
+    assert np.array_equal(ref, got)
+    ref4 = rpe.sample_table(9, n, 4, 64)
+    s4 = rpe.Sampler(9, n)
+    assert np.array_equal(ref4, s4.rows(4, 64))
+    big = rpe.Sampler(1, 307200)
+    big.rows(3, 1024)
+    t0 = time.perf_counter()
+    for _ in range(20):
+        big.rows(3, 1024)
+    per_frame = (time.perf_counter() - t0) / 20
+    assert per_frame < 0.5e-3  # the dense-frame table in well under a frame time of host work (27 us measured)
+    for x in (s, s4, big):
+        x.close()
