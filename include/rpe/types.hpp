@@ -13,6 +13,7 @@
 #include <cmath>
 #include <cstddef>
 #include <iostream>
+#include <utility>
 #include <vector>
 
 namespace rpe {
@@ -125,6 +126,11 @@ class MatrixX {
  public:
   MatrixX() : rows_(0), cols_(0) {}
   MatrixX(int rows, int cols) : rows_(rows), cols_(cols), d_((size_t)rows * cols) {}
+  // From any dense column-major matrix with data() / rows() / cols() (an Eigen::Matrix<Tp, Dynamic, Dynamic> in a
+  // program written for the reference): lets adapter.setWeights(all_weights) / setInlier(inliers) take it as is.
+  template <class M, class = decltype(static_cast<const Tp*>(std::declval<const M&>().data()), std::declval<const M&>().rows(),
+                                      std::declval<const M&>().cols(), void())>
+  MatrixX(const M& m) : rows_((int)m.rows()), cols_((int)m.cols()), d_(m.data(), m.data() + (size_t)m.rows() * (size_t)m.cols()) {}
   void resize(int rows, int cols) {
     rows_ = rows;
     cols_ = cols;
