@@ -539,6 +539,24 @@ class Quaternion {
   T& z() { return q.z; }
 };
 
+// Map<MatrixXf>(ptr, rows, cols) as Library.cpp:20-23 uses it: read once into a matrix (the reference copies it into
+// a MatrixXf right away).
+template <class M>
+class Map : public M {
+ public:
+  Map(const typename M::Scalar* p, int r, int c) {
+    this->resize(r, c);
+    memcpy(this->data(), p, sizeof(typename M::Scalar) * (size_t)r * c);
+  }
+};
+
+typedef Matrix<float, Dynamic, Dynamic> MatrixXf;
+typedef Matrix<double, Dynamic, Dynamic> MatrixXd;
+typedef Matrix<float, 3, 3> Matrix3f;
+typedef Matrix<double, 3, 3> Matrix3d;
+typedef Matrix<float, 3, 1> Vector3f;
+typedef Matrix<double, 3, 1> Vector3d;
+
 }  // namespace Eigen
 
 #endif  // ORACLE_REF_SHIM_EIGEN_SHIM_HPP_

@@ -248,3 +248,41 @@ def test_reference_kinect_simulator_and_ours_agree_statistically(rpe):
     for k in a:
         if k[:3] in ("ax_", "lat", "w_0", "w_3", "w_6", "w_m"):
             assert abs(a[k] / b[k] - 1) < 0.08, (k, a[k], b[k])
+
+
+def test_reference_ffi_library_ao_and_ao_ransac(orc, rpe):
+    """/root/reference/Library.cpp built unmodified (oracle/_ref/libref_library.so): extern "C" ao() = shinji_ls2 over all
+    points, ao_ransac() = shinji_ransac2(thr 0.1, 1000 iterations, confidence 0.99999, ::rand()) + shinji_ls1, R_cw written
+    row-major. The oracle's flow for them — the one rpe_ao / rpe_ao_ransac are tested against on the GPU
+    (tests/test_gpu_cpp_api.py) — gives the same bits."""
+    import ctypes
+    import os
+    so = os.path.join(refshim.ROOT, "oracle", "_ref", "libref_library.so")
+    if not os.path.exists(so):
+        pytest.skip("libref_library.so not built")
+    lib = ctypes.CDLL(so)
+    libc = ctypes.CDLL("libc.so.6")
+    n = 3000
+    q, t = rpe.sim_pose(21)
+    Q, P, _ = rpe.sim_3d_3d(22, q, t, n, noise=0.02, outlier_ratio=0.3)
+    R, tt = np.empty(9, np.float32), np.empty(3, np.float32)
+    devnull, saved = os.open(os.devnull, os.O_WRONLY), os.dup(1)  # the reference prints "ao()" etc. on stdout
+    try:
+        os.dup2(devnull, 1)
+        libc.srand(ctypes.c_uint(1))
+        lib.ao_ransac(Q.ctypes.data_as(ctypes.c_void_p), P.ctypes.data_as(ctypes.c_void_p), n, R.ctypes.data_as(ctypes.c_void_p),
+                      tt.ctypes.data_as(ctypes.c_void_p))
+        R1, t1 = R.copy(), tt.copy()
+        lib.ao(Q.ctypes.data_as(ctypes.c_void_p), P.ctypes.data_as(ctypes.c_void_p), n, R.ctypes.data_as(ctypes.c_void_p),
+               tt.ctypes.data_as(ctypes.c_void_p))
+        libc.fflush(None)
+    finally:
+        os.dup2(saved, 1)
+        os.close(devnull)
+        os.close(saved)
+    S = orc.sample_table(1, n, 3, 1000)
+    ref = orc.ransac(0, S, thr3d=np.float32(0.1), confidence=np.float32(0.99999), full=False, xc=P, xw=Q, want_arrays=False)
+    ls_q, ls_t, ok = orc.shinji_ls(P, Q, ref["mask"][1])
+    assert ok and np.array_equal(R1.reshape(3, 3), orc.quat_to_matrix(ls_q)) and np.array_equal(t1, ls_t)
+    ls_q, ls_t, ok = orc.shinji_ls(P, Q, None)
+    assert ok and np.array_equal(R.reshape(3, 3), orc.quat_to_matrix(ls_q)) and np.array_equal(tt, ls_t)
