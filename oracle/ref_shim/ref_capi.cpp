@@ -30,17 +30,6 @@ void put_pose(const Sophus::SO3<T>& R, const Eigen::Matrix<T, 3, 1>& t, T* q4, T
   q4[3] = q.w();
   for (int i = 0; i < 3; ++i) t3[i] = t(i);
 }
-template <class T>
-Sophus::SE3<T> get_pose(const T* q4, const T* t3) {
-  // the stored quaternion is a unit quaternion produced by the same code: go through the raw-coefficient path
-  Sophus::SE3<T> s;
-  Eigen::Quaternion<T> q(q4[3], q4[0], q4[1], q4[2]);
-  const orc::SO3<T>& m = s.so3().model();
-  const_cast<orc::SO3<T>&>(m).q = q.q;
-  s.translation() = Eigen::Matrix<T, 3, 1>(t3[0], t3[1], t3[2]);
-  return s;
-}
-
 struct RefOut {
   int max_votes;
   int iter_final;
