@@ -63,6 +63,20 @@ template <class T>
 inline T sum4(T a, T b, T c, T d) {
   return (a + b) + (c + d);
 }
+// Sensitivity builds (oracle/README.md, "version-dependent forks"; never used by the parity tests): -DORC_EIG_VARIANT=
+//   bit 0: dot / squaredNorm of a 3-vector as (a0 + a1) + a2 — what Eigen >= 3.3 does for double with one Packet2d;
+//   bit 1: the coefficient of a small matrix product accumulated in index order — Eigen 3.2.
+#ifndef ORC_EIG_VARIANT
+#define ORC_EIG_VARIANT 0
+#endif
+template <class T>
+inline T vsum3(T a, T b, T c) {  // 3-vector redux
+  return (ORC_EIG_VARIANT & 1) ? (a + b) + c : sum3(a, b, c);
+}
+template <class T>
+inline T psum3(T a, T b, T c) {  // product coefficient
+  return (ORC_EIG_VARIANT & 2) ? (a + b) + c : sum3(a, b, c);
+}
 
 template <class T>
 inline V3<T> operator+(const V3<T>& a, const V3<T>& b) {
@@ -91,11 +105,11 @@ inline V3<T> operator/(const V3<T>& a, T s) {
 }
 template <class T>
 inline T dot(const V3<T>& a, const V3<T>& b) {
-  return sum3(a[0] * b[0], a[1] * b[1], a[2] * b[2]);
+  return vsum3(a[0] * b[0], a[1] * b[1], a[2] * b[2]);
 }
 template <class T>
 inline T squared_norm(const V3<T>& a) {
-  return sum3(a[0] * a[0], a[1] * a[1], a[2] * a[2]);
+  return vsum3(a[0] * a[0], a[1] * a[1], a[2] * a[2]);
 }
 template <class T>
 inline T norm(const V3<T>& a) {
@@ -125,14 +139,14 @@ template <class T>
 inline M3<T> operator*(const M3<T>& a, const M3<T>& b) {
   M3<T> r;
   for (int i = 0; i < 3; ++i)
-    for (int j = 0; j < 3; ++j) r(i, j) = sum3(a(i, 0) * b(0, j), a(i, 1) * b(1, j), a(i, 2) * b(2, j));
+    for (int j = 0; j < 3; ++j) r(i, j) = psum3(a(i, 0) * b(0, j), a(i, 1) * b(1, j), a(i, 2) * b(2, j));
   return r;
 }
 template <class T>
 inline V3<T> operator*(const M3<T>& a, const V3<T>& x) {
-  return V3<T>(sum3(a(0, 0) * x[0], a(0, 1) * x[1], a(0, 2) * x[2]),
-               sum3(a(1, 0) * x[0], a(1, 1) * x[1], a(1, 2) * x[2]),
-               sum3(a(2, 0) * x[0], a(2, 1) * x[1], a(2, 2) * x[2]));
+  return V3<T>(psum3(a(0, 0) * x[0], a(0, 1) * x[1], a(0, 2) * x[2]),
+               psum3(a(1, 0) * x[0], a(1, 1) * x[1], a(1, 2) * x[2]),
+               psum3(a(2, 0) * x[0], a(2, 1) * x[1], a(2, 2) * x[2]));
 }
 template <class T>
 inline M3<T> operator-(const M3<T>& a, const M3<T>& b) {
