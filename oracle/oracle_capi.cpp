@@ -15,6 +15,7 @@
 
 namespace orc {
 int g_math_mode = 0;
+int g_stale_sample_buffers = 0;
 }
 
 using namespace orc;
@@ -128,6 +129,8 @@ extern "C" {
 
 void orc_set_math_mode(int m) { g_math_mode = m ? 1 : 0; }
 int orc_get_math_mode() { return g_math_mode; }
+// the reference's stale sample columns (ransac.hpp, StaleCols): only for the comparison with the reference's own sources
+void orc_set_stale_sample_buffers(int on) { g_stale_sample_buffers = on ? 1 : 0; }
 
 // ---- samplers ----------------------------------------------------------------------------
 void orc_rand_seq(unsigned seed, int n, int* out) {

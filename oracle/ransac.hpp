@@ -144,8 +144,21 @@ inline int score_hypothesis(int method, const Corr<T>& d, const SE3<T>& s, const
 // Generate the (up to 3) hypotheses of one RANSAC iteration from its 4 (or 3) sampled columns.
 // Order of slots = order of v_solutions.push_back in the reference. has[s] = false when the
 // reference pushes nothing for that slot (invalid sample, P3P without solution, aborted SO3).
+// The reference hoists its sample buffers out of the loop and assign_sample leaves the camera-side columns of an
+// INVALID (all-NaN) sample point untouched (AbsoluteOrientationNormal.hpp:48-75, :299-300): nl_2p, which is called in
+// every iteration (:315, :389), then pairs the current world point / normal with the camera point / normal of an
+// EARLIER sample. The product and this oracle deliberately do not (header of this file): NaN goes into nl_2p and the
+// hypothesis scores nothing. `StaleCols` is the reference's behaviour, for the comparison with its own sources only
+// (orc_set_stale_sample_buffers; columns start at zero, the reference's are uninitialised memory).
 template <class T>
-inline void generate_iteration(int method, const Corr<T>& d, const int* sel, SE3<T> hyp[3], bool has[3]) {
+struct StaleCols {
+  V3<T> xc[3], nc[3];
+};
+extern int g_stale_sample_buffers;
+
+template <class T>
+inline void generate_iteration(int method, const Corr<T>& d, const int* sel, SE3<T> hyp[3], bool has[3],
+                               StaleCols<T>* stale = nullptr) {
   has[0] = has[1] = has[2] = false;
   T Xw[12], Xc[12], bv[12], Nw[12], Nc[12];
   for (int i = 0; i < 12; ++i) Xw[i] = Xc[i] = bv[i] = Nw[i] = Nc[i] = std::numeric_limits<T>::quiet_NaN();
@@ -215,6 +228,14 @@ inline void generate_iteration(int method, const Corr<T>& d, const int* sel, SE3
   }
   if (want_nl2p) {
     // AbsoluteOrientationNormal.hpp:315 / :389
+    if (stale) {
+      for (int k = 0; k < 3; ++k)
+        if (d.valid(sel[k])) {
+          stale->xc[k] = col3(Xc, k);
+          stale->nc[k] = col3(Nc, k);
+        }
+      hyp[slot] = nl_2p(stale->xc[0], stale->nc[0], stale->xc[1], col3(Xw, 0), col3(Nw, 0), col3(Xw, 1));
+    } else
     hyp[slot] = nl_2p(col3(Xc, 0), col3(Nc, 0), col3(Xc, 1), col3(Xw, 0), col3(Nw, 0), col3(Xw, 1));
     has[slot] = true;
     ++slot;
@@ -268,10 +289,11 @@ inline RansacResult<T> ransac(int method, const Corr<T>& d, const int32_t* sampl
     hyps_all.resize((size_t)iter_in * S);
   }
   const int upper = full ? iter_in : 0;
+  StaleCols<T> stale_cols;
   for (int ii = 0; ii < (full ? upper : Iter); ++ii) {
     SE3<T> hyp[3];
     bool has[3];
-    generate_iteration(method, d, samples + 4 * ii, hyp, has);
+    generate_iteration(method, d, samples + 4 * ii, hyp, has, g_stale_sample_buffers ? &stale_cols : (StaleCols<T>*)0);
     for (int s = 0; s < S; ++s) {
       int v = -1;
       if (has[s]) {

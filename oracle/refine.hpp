@@ -365,7 +365,7 @@ inline int refine_gn(const Corr<T>& d, const short* mask, int mask_cols, T w2d, 
   for (int r = 0; r < 3; ++r)
     for (int c = 0; c < 3; ++c) Rp[3 * r + c] = R0(r, c);
   for (int r = 0; r < 3; ++r) tp[r] = (double)pose->t[r];
-  double Ra[9], ta[3];  // accepted
+  double Ra[9] = {0}, ta[3] = {0};  // accepted (read only once `have` is set)
   GnAccum acc_a;
   double mu = 1e-4;
   int evals = 0, accepted = 0;

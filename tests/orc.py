@@ -40,6 +40,11 @@ def set_math_mode(m):
     lib.orc_set_math_mode(int(m))
 
 
+def set_stale_sample_buffers(on):
+    """The reference's hoisted sample buffers (oracle/ransac.hpp, StaleCols) — comparison with its own sources only."""
+    lib.orc_set_stale_sample_buffers(1 if on else 0)
+
+
 def rand_seq(seed, n):
     out = np.empty(n, np.int32)
     lib.orc_rand_seq(C.c_uint(seed), n, _p(out))
