@@ -480,6 +480,8 @@ def run_gpu(args, rank, world, local_rank):
             "cpu_gpu_agree": bool(gpu_first["winner"] == r_mt["winner"] and gpu_first["max_votes"] == r_mt["max_votes"]
                                   and gpu_first["iter_final"] == r_mt["iter_final"]),
         }
+        # informational: the reference's own loop (its sources on the Eigen stand-in), single thread; never raises
+        cpu_baseline["reference_sources_single_thread"] = time_reference_sources(frames[0])
 
     if rank == 0:
         h2d = args.frames_per_step * (2 * N_CORR * 12 + N_HYP * 16)
