@@ -209,6 +209,11 @@ int rpe_peer_import(rpe_ctx* ctx, int rank, int world, const unsigned char* hand
 int rpe_peer_import_local(rpe_ctx* ctx, int rank, int world, rpe_ctx* const* ctxs);
 int rpe_exchange_votes(rpe_ctx* ctx, int slot_begin, int slot_end);
 int rpe_peer_status(rpe_ctx* ctx);
+/* How long the exchange kernel waits for a peer (default 2000 ms). The wait also absorbs host-side skew between the
+ * per-GPU processes (first-frame allocations), so callers that do not barrier before their first sharded frame may want
+ * more. On a time-out the frame has no winner (votes -1) and the blocking call / the next rpe_sync returns RPE_ERR_COMM
+ * (the latch is cleared by that report). */
+int rpe_peer_set_timeout_ms(rpe_ctx* ctx, int ms);
 /* rpe_ransac for one frame whose hypotheses are sharded over the ranks set up with rpe_peer_import: every rank holds the
  * same correspondences and sample table (H <= 8192), generates all hypotheses, scores its own contiguous slice of
  * slots, exchanges the slices through peer memory and replays the rule — all ranks return the same result. One
@@ -220,6 +225,44 @@ int rpe_ransac_sharded_async(rpe_ctx* ctx, int method, const int32_t* samples, i
 /* Replay the adaptive rule over the current votes, build the winner's mask. */
 int rpe_finish(rpe_ctx* ctx, int method, int H, float thr3d, float cos_thr2d, float cos_thrN, float confidence,
                rpe_result* out, int16_t* mask);
+
+/* ---- batched sequences of frames (BASELINE config #5) -----------------------------------------
+ * The reference runs one estimator call per frame from a single thread (SimpleMain.cpp:30-49). rpe_seq_* issues the
+ * same per-frame sequence — draw the sample table (Utility.hpp:138-155), rpe_upload, rpe_ransac_async, refits — from
+ * `n_threads` native host threads over `n_contexts` contexts (streams) of one device, so that frame k+1 is enqueued and
+ * uploaded while frame k is scored. Frames shard across GPUs by giving every process/GPU its own rpe_seq and its own
+ * frame range; there is no data-path collective.
+ * Frame i (global index first_frame + i) reads ring[(first_frame + i) % ring_len] and, when the frame carries no
+ * sample table, draws rpe_sample_table(sample_seed + first_frame + i, n, m, H) inside the call — results do not depend
+ * on n_threads / n_contexts. Host arrays and masks must be page-locked (rpe_host_alloc) for the copies to overlap. */
+#define RPE_SEQ_REFIT_KABSCH 1   /* shinji_ls / shinji_ls1 after the RANSAC                      */
+#define RPE_SEQ_REFIT_GN 2       /* LM on SE3 over the inliers (after the Kabsch refit if both)   */
+#define RPE_SEQ_REFIT_NL_SK_LS 4 /* nl_shinji_kneip_ls                                             */
+typedef struct rpe_seq rpe_seq;
+typedef struct rpe_seq_params {
+  int device, n_contexts, n_threads;
+  int method, H;
+  float thr3d, cos_thr2d, cos_thrN, confidence;
+  int refit;    /* RPE_SEQ_REFIT_* bits */
+  int gn_iters; /* <= 0 -> 6 */
+  uint32_t sample_seed;
+} rpe_seq_params;
+typedef struct rpe_seq_frame {
+  const float *bv, *xc, *nc, *xw, *nw; /* as rpe_upload / rpe_upload_device */
+  int n;
+  int on_device;          /* 0: host arrays (copied, PCIe inside the call), 1: device pointers */
+  const int32_t* samples; /* H x 4 table (host page-locked or device), NULL = draw inside      */
+  int16_t* mask;          /* host page-locked n x cols, or NULL                                */
+} rpe_seq_frame;
+int rpe_seq_create(const rpe_seq_params* params, rpe_seq** out);
+/* Blocking: returns when all n_frames results are on the host. ransac_out / final_out: n_frames entries each (the
+ * RANSAC result and the result of the last refit of the frame) or NULL. */
+int rpe_seq_run(rpe_seq* seq, const rpe_seq_frame* ring, int ring_len, long long first_frame, int n_frames,
+                rpe_result* ransac_out, rpe_result* final_out);
+rpe_ctx* rpe_seq_context(rpe_seq* seq, int index); /* for rpe_enable_stage_timing / rpe_launch_count */
+int rpe_seq_num_contexts(const rpe_seq* seq);
+const char* rpe_seq_last_error(const rpe_seq* seq);
+int rpe_seq_destroy(rpe_seq* seq);
 
 /* ---- host-side helpers that the reference computes on the CPU too ------------------------- */
 /* RANSACUpdateNumIters<float> with the bit-reproducible log of include/rpe/det_math.h. */
@@ -239,6 +282,9 @@ typedef struct rpe_sampler rpe_sampler;
 int rpe_sampler_create(uint32_t seed, int n, rpe_sampler** out);
 int rpe_sampler_rows(rpe_sampler* s, int m, int H, int32_t* samples);
 void rpe_sampler_destroy(rpe_sampler* s);
+/* Restart the sampler's generator from `seed` (what srand(seed) does to ::rand()); the permutation is untouched, so
+ * the next rows are exactly rpe_sample_table(seed, ...)'s at O(1) cost — per-frame tables of a sequence. */
+int rpe_sampler_reseed(rpe_sampler* s, uint32_t seed);
 
 /* ---- synthetic correspondences (Simulator.hpp) -------------------------------------------- */
 /* pose: R = Rz*Ry*Rx from uniform angles (Simulator.hpp:23-83, use_gaussian=false), t = size*U(-1,1)^3 (:16-21) */

@@ -7,6 +7,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import weakref
 
 import numpy as np
 
@@ -119,6 +120,7 @@ _sig("rpe_peer_import", C.c_int, [_vp, C.c_int, C.c_int, _vp])
 _sig("rpe_peer_import_local", C.c_int, [_vp, C.c_int, C.c_int, _vp])
 _sig("rpe_exchange_votes", C.c_int, [_vp, C.c_int, C.c_int])
 _sig("rpe_peer_status", C.c_int, [_vp])
+_sig("rpe_peer_set_timeout_ms", C.c_int, [_vp, C.c_int])
 _sig("rpe_ransac_sharded", C.c_int, [_vp, C.c_int, _vp, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float,
                                      C.POINTER(_Result), _vp])
 _sig("rpe_ransac_sharded_async", C.c_int, [_vp, C.c_int, _vp, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float,
@@ -156,6 +158,7 @@ _sig("rpe_measure_ffma_tflops", C.c_int, [_vp, C.c_int, C.POINTER(C.c_double), C
 _sig("rpe_last_stage_ms", C.c_int, [_vp, _vp])
 _sig("rpe_enable_stage_timing", C.c_int, [_vp, C.c_int])
 _sig("rpe_debug_set_packed", C.c_int, [C.c_int])
+_sig("rpe_debug_reset", C.c_int, [_vp])
 
 # every symbol include/rpe_c_api.h declares (tests check the header against this list and the .so)
 DECLARED_SYMBOLS = [
@@ -163,7 +166,7 @@ DECLARED_SYMBOLS = [
     "rpe_last_error", "rpe_stream", "rpe_sync", "rpe_launch_count", "rpe_host_alloc", "rpe_host_free", "rpe_upload",
     "rpe_upload_device", "rpe_num_correspondences", "rpe_ransac", "rpe_ransac_async", "rpe_ransac_stream", "rpe_set_first_pass_iters", "rpe_upload_f64", "rpe_ransac_f64", "rpe_get_hypotheses_f64", "rpe_refit", "rpe_refit_async",
     "rpe_set_pose", "rpe_set_mask", "rpe_generate", "rpe_get_hypotheses", "rpe_set_hypotheses", "rpe_score",
-    "rpe_get_votes", "rpe_set_votes", "rpe_votes_device_ptr", "rpe_peer_export", "rpe_peer_import", "rpe_peer_import_local", "rpe_exchange_votes", "rpe_peer_status", "rpe_ransac_sharded", "rpe_ransac_sharded_async", "rpe_finish", "rpe_update_num_iters", "rpe_sample_table",
+    "rpe_get_votes", "rpe_set_votes", "rpe_votes_device_ptr", "rpe_peer_export", "rpe_peer_import", "rpe_peer_import_local", "rpe_exchange_votes", "rpe_peer_status", "rpe_peer_set_timeout_ms", "rpe_ransac_sharded", "rpe_ransac_sharded_async", "rpe_finish", "rpe_update_num_iters", "rpe_sample_table",
     "rpe_prosac_table", "rpe_sampler_create", "rpe_sampler_rows", "rpe_sampler_destroy", "rpe_sim_pose", "rpe_sim_3d_3d", "rpe_sim_2d_3d", "rpe_sim_2d_3d_nl", "rpe_sim_kinect_2d_3d_nl", "rpe_sim_kinect_2d_3d_nl_device", "rpe_sim_3d_3d_device",
     "rpe_sim_2d_3d_nl_device", "rpe_download", "rpe_ao", "rpe_ao_ransac",
     "rpe_measure_ffma_tflops", "rpe_last_stage_ms", "rpe_enable_stage_timing",
@@ -291,19 +294,29 @@ def sim_kinect_2d_3d_nl(seed, q, t, n, n2d=1.0, or2d=0.3, or3d=0.3, nnl=np.deg2r
     return out
 
 
+class _PinnedBlock:
+    """Owner of one rpe_host_alloc block; arrays made by pinned_empty keep it alive through their `.base` chain and
+    the block is returned with rpe_host_free when the last of them is collected."""
+
+    def __init__(self, nbytes: int):
+        self.ptr = C.c_void_p()
+        _check(lib.rpe_host_alloc(max(nbytes, 1), C.byref(self.ptr)))
+        self.buf = (C.c_byte * max(nbytes, 1)).from_address(self.ptr.value)
+        weakref.finalize(self, lib.rpe_host_free, C.c_void_p(self.ptr.value))
+
+    @property
+    def __array_interface__(self):
+        return {"shape": (len(self.buf),), "typestr": "|u1", "data": (self.ptr.value, False), "version": 3}
+
+
 def pinned_empty(shape, dtype=np.float32) -> np.ndarray:
-    """numpy array backed by page-locked host memory from rpe_host_alloc (freed with the array's base)."""
+    """numpy array backed by page-locked host memory from rpe_host_alloc; the memory is freed (rpe_host_free) when
+    the array and every view of it are gone. Keep it alive until the asynchronous calls that use it are synchronised."""
     dtype = np.dtype(dtype)
-    nbytes = int(np.prod(shape)) * dtype.itemsize
-    p = C.c_void_p()
-    _check(lib.rpe_host_alloc(max(nbytes, 1), C.byref(p)))
-    buf = (C.c_byte * max(nbytes, 1)).from_address(p.value)
-    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
-    _PINNED.append((p, buf))
-    return arr
-
-
-_PINNED = []
+    count = int(np.prod(shape))
+    block = _PinnedBlock(count * dtype.itemsize)
+    raw = np.asarray(block)  # base = block
+    return raw[:count * dtype.itemsize].view(dtype).reshape(shape)
 
 
 # ---- device context ---------------------------------------------------------------------------
@@ -316,7 +329,8 @@ class Context:
             _check(lib.rpe_create(device, C.byref(self._h)))
         else:
             _check(lib.rpe_create_on_stream(device, C.c_void_p(stream), C.byref(self._h)))
-        self._keep = []
+        self._keep = []     # host arrays of the last upload (the copy is asynchronous)
+        self._pending = []  # result structs / sample tables of enqueued calls: the library writes them at sync time
         self.n = 0
 
     def close(self):
@@ -446,10 +460,10 @@ class Context:
         else:
             samples = np.ascontiguousarray(samples, dtype=np.int32)
             H = samples.shape[0]
-            self._keep.append(samples)
+            self._pending.append(samples)
             sp = _ptr(samples)
         res = _Result()
-        self._keep.append(res)  # the library writes into it at sync time
+        self._pending.append(res)  # the library writes into it at sync time
         _check(lib.rpe_ransac_async(self._h, m, sp, H, thr3d, cos_thr2d, cos_thrN, confidence, C.byref(res),
                                     _ptr(mask)), self._h)
         return res
@@ -459,8 +473,8 @@ class Context:
         res = _Result()
         w = _f32(weights)
         if w is not None:
-            self._keep.append(w)
-        self._keep.append(res)
+            self._pending.append(w)
+        self._pending.append(res)
         _check(lib.rpe_refit_async(self._h, k, _ptr(w), max_iters, C.byref(res)), self._h)
         return res
 
@@ -543,13 +557,13 @@ class Context:
         else:
             samples = np.ascontiguousarray(samples, dtype=np.int32)
             H = samples.shape[0]
-            self._keep.append(samples)
+            self._pending.append(samples)
             sp = _ptr(samples)
         res = _Result()
         if blocking:
             _check(lib.rpe_ransac_sharded(self._h, m, sp, H, thr3d, cos_thr2d, cos_thrN, confidence, C.byref(res), None), self._h)
             return res.to_dict()
-        self._keep.append(res)
+        self._pending.append(res)
         _check(lib.rpe_ransac_sharded_async(self._h, m, sp, H, thr3d, cos_thr2d, cos_thrN, confidence, C.byref(res), None),
                self._h)
         return res
@@ -579,8 +593,18 @@ class Context:
         return d
 
     def sync(self):
-        _check(lib.rpe_sync(self._h), self._h)
-        self._keep = []
+        try:
+            _check(lib.rpe_sync(self._h), self._h)
+        finally:
+            self._keep = []
+            self._pending = []
+
+    def debug_reset(self):
+        """Every test hook (process-global and of this context) back to the shipped configuration."""
+        _check(lib.rpe_debug_reset(self._h), self._h)
+
+    def peer_set_timeout_ms(self, ms):
+        _check(lib.rpe_peer_set_timeout_ms(self._h, int(ms)), self._h)
 
     def launch_count(self):
         return int(lib.rpe_launch_count(self._h))

@@ -21,6 +21,7 @@ void set_use_packed(bool v);
 bool use_packed();
 void set_score_variant(int v);
 void set_nosync(int v);
+constexpr int kDefaultScoreVariant = 14;  // must match g_variant's initial value in score.cu
 }
 
 using namespace rpe;
@@ -77,6 +78,8 @@ struct rpe_ctx {
   bool peer_opened[kMaxPeers] = {};
   int peer_rank = -1, peer_world = 0;
   unsigned int peer_epoch = 0;
+  unsigned int* h_peer_err = nullptr;   // pinned word the exchange kernel sets when a peer timed out (read after a sync)
+  unsigned long long peer_timeout_ns = 2000000000ull;
   // binary64 path (rpe_upload_f64)
   bool f64 = false;
   double* d_raw64[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -148,6 +151,13 @@ int fail(rpe_ctx* c, int code, const char* what, cudaError_t e = cudaSuccess) {
     cudaError_t e__ = (call);                                           \
     if (e__ != cudaSuccess) return fail(ctx, RPE_ERR_CUDA, #call, e__); \
   } while (0)
+
+// Every entry point that replaces the frame with binary32 arrays calls this: a context that was in binary64 mode
+// (rpe_upload_f64) must not route the next rpe_ransac to the binary64 arrays of an earlier, possibly smaller frame.
+void leave_f64_mode(rpe_ctx* c) {
+  c->f64 = false;
+  for (int k = 0; k < 5; ++k) c->view64[k] = nullptr;
+}
 
 int kind_for_method(int method) {
   return (method_uses_2d(method) ? 1 : 0) | (method_uses_3d(method) ? 2 : 0) | (method_uses_nl(method) ? 4 : 0);
@@ -343,6 +353,18 @@ int finish_pending(rpe_ctx* ctx) {
   return RPE_OK;
 }
 
+// After a synchronisation: did an exchange kernel of the sharded mode give up on a peer? The latch (host word + the
+// flag in the own block) is cleared so that the next frame starts clean.
+int check_comm(rpe_ctx* ctx) {
+  if (!ctx->h_peer_err || !*(volatile unsigned int*)ctx->h_peer_err) return RPE_OK;
+  *ctx->h_peer_err = 0;
+  if (ctx->d_peer_block) {
+    cudaMemsetAsync(peer_flags(ctx->d_peer_block) + kPeerErrSlot, 0, sizeof(unsigned int), ctx->stream);
+    cudaStreamSynchronize(ctx->stream);
+  }
+  return fail(ctx, RPE_ERR_COMM, "a peer did not publish its votes within the time-out (the frame has no winner)");
+}
+
 // claim a pinned staging slot for an enqueued result; when all are in flight, wait for the OLDEST result only
 // (its event) and deliver it, so that a long asynchronous stream of frames never drains the GPU queue
 int claim_slot(rpe_ctx* ctx, int* slot) {
@@ -473,6 +495,7 @@ int do_finish(rpe_ctx* ctx, int method, Thresh th, rpe_result* out, int16_t* mas
   if (blocking) {
     CK(cudaStreamSynchronize(ctx->stream));
     finish_pending(ctx);
+    return check_comm(ctx);
   }
   return RPE_OK;
 }
@@ -500,6 +523,9 @@ int do_ransac64(rpe_ctx* ctx, int method, const int32_t* samples, rpe_sample_fn 
     return fail(ctx, RPE_ERR_ARG, "bad argument to rpe_ransac");
   int rc = check_arrays(ctx, method);
   if (rc) return rc;
+  if (!ctx->f64 || (size_t)ctx->n > ctx->cap_n64) return fail(ctx, RPE_ERR_STATE, "no binary64 arrays of this frame on the device");
+  for (int k = 0; k < 5; ++k)
+    if (ctx->view[k] && !ctx->view64[k]) return fail(ctx, RPE_ERR_STATE, "binary64 copy of an array is missing");
   CK(cudaSetDevice(ctx->device));
   const int S = method_slots(method);
   const Thresh64 th = {thr3d, cos_thr2d, cos_thrN};
@@ -748,7 +774,12 @@ static int create_common(int device, void* stream, bool own, rpe_ctx** out) {
   rpe_ctx* ctx = new rpe_ctx();
   ctx->device = device;
   cudaDeviceProp prop;
-  if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->num_sms = prop.multiProcessorCount;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) {
+    (void)cudaGetLastError();
+    delete ctx;
+    return RPE_ERR_CUDA;
+  }
+  ctx->num_sms = prop.multiProcessorCount;
   ctx->rb.num_sms = ctx->num_sms;
   if (prop.major < 10) {
     delete ctx;
@@ -847,6 +878,7 @@ int rpe_destroy(rpe_ctx* ctx) {
   for (int r = 0; r < kMaxPeers; ++r)
     if (ctx->peer_opened[r]) cudaIpcCloseMemHandle(ctx->peers.block[r]);
   if (ctx->d_peer_block) cudaFree(ctx->d_peer_block);
+  if (ctx->h_peer_err) cudaFreeHost(ctx->h_peer_err);
   if (ctx->h_samples) cudaFreeHost(ctx->h_samples);
   for (int k = 0; k < 5; ++k)
     if (ctx->d_raw64[k]) cudaFree(ctx->d_raw64[k]);
@@ -878,7 +910,8 @@ long long rpe_launch_count(const rpe_ctx* ctx) { return ctx ? ctx->launches : 0;
 int rpe_sync(rpe_ctx* ctx) {
   if (!ctx) return RPE_ERR_ARG;
   CK(cudaStreamSynchronize(ctx->stream));
-  return finish_pending(ctx);
+  finish_pending(ctx);
+  return check_comm(ctx);
 }
 
 int rpe_host_alloc(size_t bytes, void** ptr) {
@@ -918,7 +951,7 @@ static int upload_common(rpe_ctx* ctx, const float* const src[5], int n, bool fr
   ctx->kabsch_valid = false;
   ctx->suff_valid = false;
   ctx->n_slots = 0;
-  ctx->f64 = false;
+  leave_f64_mode(ctx);
   return RPE_OK;
 }
 
@@ -1016,26 +1049,35 @@ static int do_refit(rpe_ctx* ctx, int kind, const float* weights, int max_iters,
   if (!ctx || !out) return RPE_ERR_ARG;
   if (ctx->n <= 0) return fail(ctx, RPE_ERR_STATE, "no correspondences uploaded");
   CK(cudaSetDevice(ctx->device));
+  FrameView f = make_view(ctx);
+  // every state / argument check comes before a staging slot is claimed: a failed call must not advance the ring
+  if (kind == RPE_REFIT_KABSCH_INLIERS || kind == RPE_REFIT_KABSCH_ALL) {
+    if (!f.xc) return fail(ctx, RPE_ERR_STATE, "Kabsch refit needs camera points");
+    if (kind == RPE_REFIT_KABSCH_INLIERS && !ctx->kabsch_valid && ctx->mask_cols < 2)
+      return fail(ctx, RPE_ERR_STATE, "no 3-D inlier column available");
+  } else if (kind == RPE_REFIT_GN) {
+    if (ctx->mask_cols <= 0) return fail(ctx, RPE_ERR_STATE, "no inlier mask: run rpe_ransac or rpe_set_mask first");
+  } else if (kind == RPE_REFIT_NL_SK_LS) {
+    if (!f.bv || !f.xc || !f.nc || !f.nw) return fail(ctx, RPE_ERR_STATE, "nl_shinji_kneip_ls needs all five arrays");
+    if (ctx->mask_cols < 3) return fail(ctx, RPE_ERR_STATE, "nl_shinji_kneip_ls needs the three inlier columns");
+  } else {
+    return fail(ctx, RPE_ERR_ARG, "unknown refit kind");
+  }
   int slot = 0;
   int rcs = claim_slot(ctx, &slot);
   if (rcs) return rcs;
-  FrameView f = make_view(ctx);
   bool gn = false;
   if (kind == RPE_REFIT_KABSCH_INLIERS || kind == RPE_REFIT_KABSCH_ALL) {
-    if (!f.xc) return fail(ctx, RPE_ERR_STATE, "Kabsch refit needs camera points");
     if (kind == RPE_REFIT_KABSCH_INLIERS && ctx->kabsch_valid) {
       // already computed by the mask kernel's last CTA; adopt it as the current pose
       CK(cudaMemcpyAsync(ctx->d_pose, ctx->d_kabsch, sizeof(ReplayOut), cudaMemcpyDeviceToDevice, ctx->stream));
     } else {
-      if (kind == RPE_REFIT_KABSCH_INLIERS && ctx->mask_cols < 2)
-        return fail(ctx, RPE_ERR_STATE, "no 3-D inlier column available");
       const int16_t* flags = kind == RPE_REFIT_KABSCH_INLIERS ? ctx->d_mask + ctx->n : nullptr;
       const int used = launch_kabsch_moments(f, flags, ctx->rb, ctx->d_stats, ctx->stream);
       launch_kabsch_solve(ctx->rb, used, ctx->d_pose, nullptr, ctx->stream);
       ctx->launches += 2;
     }
   } else if (kind == RPE_REFIT_GN) {
-    if (ctx->mask_cols <= 0) return fail(ctx, RPE_ERR_STATE, "no inlier mask: run rpe_ransac or rpe_set_mask first");
     const float w2 = weights ? weights[0] : 1.f, w3 = weights ? weights[1] : 1.f, wn = weights ? weights[2] : 1.f;
     const int iters = max_iters > 0 ? max_iters : 6;
     stamp(ctx, ST_GN);
@@ -1064,9 +1106,7 @@ static int do_refit(rpe_ctx* ctx, int kind, const float* weights, int max_iters,
     CK(cudaMemcpyAsync(&ctx->h_gn_evals[slot], ctx->d_gn_evals, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
     stamp(ctx, ST_TOTAL);
     gn = true;
-  } else if (kind == RPE_REFIT_NL_SK_LS) {
-    if (!f.bv || !f.xc || !f.nc || !f.nw) return fail(ctx, RPE_ERR_STATE, "nl_shinji_kneip_ls needs all five arrays");
-    if (ctx->mask_cols < 3) return fail(ctx, RPE_ERR_STATE, "nl_shinji_kneip_ls needs the three inlier columns");
+  } else {  // RPE_REFIT_NL_SK_LS
     const float* w3 = nullptr;
     if (weights) {
       const size_t need = (size_t)ctx->n * 3;
@@ -1082,8 +1122,6 @@ static int do_refit(rpe_ctx* ctx, int kind, const float* weights, int max_iters,
     for (int it = 0; it < 3; ++it)
       launch_nlsk_iteration(f, ctx->d_mask, w3, ctx->rb, ctx->d_nlsk, ctx->d_stats, ctx->d_pose, ctx->stream);
     ctx->launches += 4;
-  } else {
-    return fail(ctx, RPE_ERR_ARG, "unknown refit kind");
   }
   ctx->kabsch_valid = false;
   CK(cudaMemcpyAsync(&ctx->h_pose[slot], ctx->d_pose, sizeof(ReplayOut), cudaMemcpyDeviceToHost, ctx->stream));
@@ -1234,14 +1272,38 @@ int rpe_set_votes(rpe_ctx* ctx, const int32_t* votes, int n_slots) {
 int32_t* rpe_votes_device_ptr(rpe_ctx* ctx) { return ctx ? ctx->d_votes : nullptr; }
 
 // ---- peer-memory exchange of the vote table (one process per GPU, CUDA IPC over NVLink) ----------------------
+// (Re-)arming the own block: flags, error latch and epoch start from zero. Export is the right place: a peer can only
+// write into this block for the new group after it has imported the handle, i.e. after this call returned (the handles
+// are gathered in between). All ranks must have synchronised their contexts before a group is set up again.
+static int peer_arm(rpe_ctx* ctx) {
+  if (!ctx->d_peer_block) {
+    CK(cudaMalloc(&ctx->d_peer_block, kPeerBlockBytes));
+    CK(cudaMemset(ctx->d_peer_block, 0, kPeerBlockBytes));
+  } else {
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaMemset(ctx->d_peer_block, 0, kPeerFlagWords * sizeof(unsigned int)));
+  }
+  if (!ctx->h_peer_err) CK(cudaMallocHost(&ctx->h_peer_err, sizeof(unsigned int)));
+  *ctx->h_peer_err = 0;
+  ctx->peer_epoch = 0;
+  return RPE_OK;
+}
+static void peer_close(rpe_ctx* ctx) {
+  for (int r = 0; r < kMaxPeers; ++r) {
+    if (ctx->peer_opened[r]) cudaIpcCloseMemHandle(ctx->peers.block[r]);
+    ctx->peer_opened[r] = false;
+    ctx->peers.block[r] = nullptr;
+  }
+  (void)cudaGetLastError();
+  ctx->peer_world = 0;
+  ctx->peer_rank = -1;
+}
 int rpe_peer_export(rpe_ctx* ctx, unsigned char handle[64]) {
   if (!ctx || !handle) return RPE_ERR_ARG;
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
   CK(cudaSetDevice(ctx->device));
-  if (!ctx->d_peer_block) {
-    CK(cudaMalloc(&ctx->d_peer_block, kPeerBlockBytes));
-    CK(cudaMemset(ctx->d_peer_block, 0, kPeerBlockBytes));
-  }
+  peer_close(ctx);  // mappings of an earlier group
+  if (int rc = peer_arm(ctx)) return rc;
   cudaIpcMemHandle_t h;
   CK(cudaIpcGetMemHandle(&h, ctx->d_peer_block));
   memcpy(handle, &h, 64);
@@ -1251,6 +1313,7 @@ int rpe_peer_import(rpe_ctx* ctx, int rank, int world, const unsigned char* hand
   if (!ctx || !handles || world < 1 || world > kMaxPeers || rank < 0 || rank >= world) return RPE_ERR_ARG;
   if (!ctx->d_peer_block) return fail(ctx, RPE_ERR_STATE, "call rpe_peer_export first");
   CK(cudaSetDevice(ctx->device));
+  peer_close(ctx);
   for (int r = 0; r < world; ++r) {
     if (r == rank) {
       ctx->peers.block[r] = ctx->d_peer_block;
@@ -1265,7 +1328,11 @@ int rpe_peer_import(rpe_ctx* ctx, int rank, int world, const unsigned char* hand
   }
   ctx->peer_rank = rank;
   ctx->peer_world = world;
-  ctx->peer_epoch = 0;
+  return RPE_OK;  // the epoch was reset by rpe_peer_export, together with the flags it is compared with
+}
+int rpe_peer_set_timeout_ms(rpe_ctx* ctx, int ms) {
+  if (!ctx || ms < 1) return RPE_ERR_ARG;
+  ctx->peer_timeout_ns = (unsigned long long)ms * 1000000ull;
   return RPE_OK;
 }
 // Same for contexts that live in ONE process (one per GPU): no IPC, the peers' blocks are addressed directly after
@@ -1274,13 +1341,17 @@ int rpe_peer_import(rpe_ctx* ctx, int rank, int world, const unsigned char* hand
 int rpe_peer_import_local(rpe_ctx* ctx, int rank, int world, rpe_ctx* const* ctxs) {
   if (!ctx || !ctxs || world < 1 || world > kMaxPeers || rank < 0 || rank >= world || ctxs[rank] != ctx) return RPE_ERR_ARG;
   CK(cudaSetDevice(ctx->device));
+  peer_close(ctx);
+  // own block: (re-)armed here; the caller imports on every context before the first frame, so nobody writes into it
+  // yet. Peers' blocks that do not exist yet are created (armed) now and left alone when their own import runs.
+  if (int rc = peer_arm(ctx)) return rc;
   for (int r = 0; r < world; ++r) {
     rpe_ctx* p = ctxs[r];
     if (!p) return RPE_ERR_ARG;
     if (!p->d_peer_block) {
-      unsigned char h[64];
-      const int rc = rpe_peer_export(p, h);
-      if (rc) return rc;
+      CK(cudaSetDevice(p->device));
+      CK(cudaMalloc(&p->d_peer_block, kPeerBlockBytes));
+      CK(cudaMemset(p->d_peer_block, 0, kPeerBlockBytes));
       CK(cudaSetDevice(ctx->device));
     }
     if (p->device != ctx->device) {
@@ -1295,7 +1366,6 @@ int rpe_peer_import_local(rpe_ctx* ctx, int rank, int world, rpe_ctx* const* ctx
   }
   ctx->peer_rank = rank;
   ctx->peer_world = world;
-  ctx->peer_epoch = 0;
   return RPE_OK;
 }
 int rpe_exchange_votes(rpe_ctx* ctx, int slot_begin, int slot_end) {
@@ -1306,7 +1376,7 @@ int rpe_exchange_votes(rpe_ctx* ctx, int slot_begin, int slot_end) {
   CK(cudaSetDevice(ctx->device));
   ctx->peer_epoch += 1;
   launch_exchange_votes(ctx->peers, ctx->peer_rank, ctx->peer_world, ctx->peer_epoch, slot_begin, slot_end, ctx->n_slots,
-                        ctx->d_votes, ctx->stream);
+                        ctx->d_votes, ctx->h_peer_err, ctx->peer_timeout_ns, ctx->stream);
   ctx->launches++;
   return RPE_OK;
 }
@@ -1345,7 +1415,8 @@ static int do_ransac_sharded(rpe_ctx* ctx, int method, const int32_t* samples, i
   rc = score_range(ctx, method, sb, se, th);
   if (rc) return rc;
   ctx->peer_epoch += 1;
-  launch_exchange_votes(ctx->peers, r, G, ctx->peer_epoch, sb, se, n_slots, ctx->d_votes, ctx->stream);
+  launch_exchange_votes(ctx->peers, r, G, ctx->peer_epoch, sb, se, n_slots, ctx->d_votes, ctx->h_peer_err,
+                        ctx->peer_timeout_ns, ctx->stream);
   launch_replay(method, ctx->d_gen, ctx->d_votes, H, 0, ctx->n, confidence, ctx->d_stats, ctx->d_rs, ctx->d_pose, true, H,
                 ctx->stream);
   ctx->launches += 2;
@@ -1364,9 +1435,7 @@ int rpe_peer_status(rpe_ctx* ctx) {
   if (!ctx || !ctx->d_peer_block) return RPE_ERR_ARG;
   CK(cudaSetDevice(ctx->device));
   CK(cudaStreamSynchronize(ctx->stream));
-  unsigned int err = 0;
-  CK(cudaMemcpy(&err, peer_flags(ctx->d_peer_block) + kPeerErrSlot, sizeof(err), cudaMemcpyDeviceToHost));
-  return err ? fail(ctx, RPE_ERR_STATE, "a peer did not publish its votes within the time-out") : RPE_OK;
+  return check_comm(ctx);
 }
 
 int rpe_finish(rpe_ctx* ctx, int method, int H, float thr3d, float cos_thr2d, float cos_thrN, float confidence,
@@ -1447,6 +1516,7 @@ static int sim_device_common(rpe_ctx* ctx, uint64_t seed, const float q[4], cons
   p.seed = seed;
   ctx->n = n;
   for (int k = 0; k < 5; ++k) ctx->view[k] = nullptr;
+  leave_f64_mode(ctx);  // the frame replaces whatever rpe_upload_f64 left behind
   ctx->view[A_XW] = ctx->d_raw[A_XW];
   ctx->view[A_XC] = ctx->d_raw[A_XC];
   if (!mode_3d3d) {
@@ -1493,13 +1563,23 @@ int rpe_download(rpe_ctx* ctx, float* bv, float* xc, float* nc, float* xw, float
 }
 
 // ---- Library.cpp shim -----------------------------------------------------------------------------
+// One context, created on first use and kept for the life of the process (a context owns a 32 MiB worklist, a ring of
+// pinned staging slots and ~270 events: too much to build and tear down per call). Calls are serialised.
+static std::mutex g_ao_mu;
+static rpe_ctx* g_ao_ctx = nullptr;
 static int ao_common(const float* x_w, const float* x_c, int n, float* R_cw, float* t, bool ransac) {
   if (!x_w || !x_c || n < 3 || !R_cw || !t) return RPE_ERR_ARG;
-  rpe_ctx* ctx = nullptr;
-  int rc = rpe_create(0, &ctx);
-  if (rc) return rc;
+  std::lock_guard<std::mutex> g(g_ao_mu);
+  if (!g_ao_ctx) {
+    const int rcc = rpe_create(0, &g_ao_ctx);
+    if (rcc) {
+      g_ao_ctx = nullptr;
+      return rcc;
+    }
+  }
+  rpe_ctx* ctx = g_ao_ctx;
   rpe_result res;
-  rc = rpe_upload(ctx, nullptr, x_c, nullptr, x_w, nullptr, n);
+  int rc = rpe_upload(ctx, nullptr, x_c, nullptr, x_w, nullptr, n);
   if (!rc && ransac) {
     // Library.cpp:54-64: thr 0.1, 1000 iterations, confidence 0.99999, unseeded rand() (seed 1)
     const int H = 1000;
@@ -1514,7 +1594,6 @@ static int ao_common(const float* x_w, const float* x_c, int n, float* R_cw, flo
     for (int i = 0; i < 9; ++i) R_cw[i] = res.R[i];
     for (int i = 0; i < 3; ++i) t[i] = res.t[i];
   }
-  rpe_destroy(ctx);
   return rc;
 }
 int rpe_ao(const float* x_w, const float* x_c, int n, float* R_cw, float* t) { return ao_common(x_w, x_c, n, R_cw, t, false); }
@@ -1600,6 +1679,22 @@ int rpe_debug_set_nosync(int v) {
 }
 int rpe_debug_set_score_variant(int v) {
   rpe::set_score_variant(v);
+  return RPE_OK;
+}
+// Back to the shipped configuration: every process-global test hook, and (ctx may be NULL) the per-context ones.
+int rpe_debug_reset(rpe_ctx* ctx) {
+  rpe::set_use_packed(true);
+  rpe::set_score_variant(rpe::kDefaultScoreVariant);
+  rpe::set_nosync(0);
+  g_raw_tiles = true;
+  g_f64_exact_only = false;
+  g_force_exact_multi = false;
+  if (ctx) {
+    ctx->wl.capacity = ctx->wl_allocated;
+    ctx->wl_fixed = false;
+    ctx->first_pass = kFirstPassIters;
+    ctx->timing = ctx->timing_fast = false;
+  }
   return RPE_OK;
 }
 

@@ -50,6 +50,11 @@ int rpe_sampler_rows(rpe_sampler* s, int m, int H, int32_t* samples) {
   return RPE_OK;
 }
 void rpe_sampler_destroy(rpe_sampler* s) { delete s; }
+int rpe_sampler_reseed(rpe_sampler* s, uint32_t seed) {
+  if (!s) return RPE_ERR_ARG;
+  s->src.seed_with(seed);  // RandomElements::run leaves the identity permutation behind: nothing else to reset
+  return RPE_OK;
+}
 
 int rpe_prosac_table(uint32_t seed, int n, int m, int H, const float* weights, int32_t* samples) {
   if (!samples || n <= 0 || m <= 1 || m > 4 || m > n || H < 0) return RPE_ERR_ARG;
@@ -65,8 +70,10 @@ int rpe_prosac_table(uint32_t seed, int n, int m, int H, const float* weights, i
     ps.sample(&sel);
     for (int k = 0; k < 4; ++k) {
       int j = k < m ? sel[k] : -1;
-      // getSortedIdx (PnPPoseAdapter.hpp:246-255): indices beyond the table are left untouched
+      // getSortedIdx (PnPPoseAdapter.hpp:246-255) leaves indices beyond the table untouched; the sampler's out-of-range
+      // index n == N (Utility.hpp:238) is clamped to N-1, the same policy as the header path (rpe/Estimators.hpp)
       if (j >= 0 && weights && j < (int)order.size()) j = order[j];
+      if (j >= n) j = n - 1;
       samples[4 * h + k] = j;
     }
   }

@@ -126,7 +126,7 @@ __host__ __device__ inline int32_t* peer_table(unsigned char* block, int parity)
   return reinterpret_cast<int32_t*>(block + kPeerFlagWords * sizeof(unsigned int)) + (size_t)parity * kPeerSlots;
 }
 void launch_exchange_votes(const PeerTable& peers, int rank, int world, unsigned int epoch, int slot_begin, int slot_end,
-                           int n_slots, int32_t* votes, cudaStream_t s);
+                           int n_slots, int32_t* votes, unsigned int* host_err, unsigned long long timeout_ns, cudaStream_t s);
 
 // -- device-side Simulator (simulate.cu) ------------------------------------------------------------
 struct SimParams {

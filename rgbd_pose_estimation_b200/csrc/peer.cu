@@ -23,7 +23,7 @@ __device__ __forceinline__ unsigned long long global_ns() {
 
 __global__ void __launch_bounds__(256)
 exchange_votes_kernel(PeerTable peers, int rank, int world, unsigned int epoch, int slot_begin, int slot_end, int n_slots,
-                      int32_t* __restrict__ votes, unsigned long long timeout_ns) {
+                      int32_t* __restrict__ votes, unsigned int* __restrict__ host_err, unsigned long long timeout_ns) {
   const int par = (int)(epoch & 1u);
   // 1. my slice -> every rank's table
   for (int r = 0; r < world; ++r) {
@@ -58,13 +58,19 @@ exchange_votes_kernel(PeerTable peers, int rank, int world, unsigned int epoch, 
   // 4. the complete table -> the context's vote table (all empty on a timeout: no winner, and the error is latched)
   const int32_t* src = peer_table(peers.block[rank], par);
   for (int i = threadIdx.x; i < n_slots; i += blockDim.x) votes[i] = ok ? ((volatile const int32_t*)src)[i] : -1;
-  if (!ok && threadIdx.x == 0) peer_flags(peers.block[rank])[kPeerErrSlot] = 1u;
+  if (!ok && threadIdx.x == 0) {
+    peer_flags(peers.block[rank])[kPeerErrSlot] = 1u;
+    if (host_err) {  // page-locked host word: what rpe_sync / the blocking calls look at (RPE_ERR_COMM)
+      *(volatile unsigned int*)host_err = 1u;
+      __threadfence_system();
+    }
+  }
 }
 
 void launch_exchange_votes(const PeerTable& peers, int rank, int world, unsigned int epoch, int slot_begin, int slot_end,
-                           int n_slots, int32_t* votes, cudaStream_t s) {
-  exchange_votes_kernel<<<1, 256, 0, s>>>(peers, rank, world, epoch, slot_begin, slot_end, n_slots, votes,
-                                          2000000000ull /* 2 s */);
+                           int n_slots, int32_t* votes, unsigned int* host_err, unsigned long long timeout_ns, cudaStream_t s) {
+  exchange_votes_kernel<<<1, 256, 0, s>>>(peers, rank, world, epoch, slot_begin, slot_end, n_slots, votes, host_err,
+                                          timeout_ns);
 }
 
 }  // namespace rpe

@@ -18,6 +18,7 @@
 // evaluations are removed from the fast count and appended to a worklist which fixup_kernel
 // re-evaluates in the reference's exact operation order. Inlier counts are therefore identical to the
 // CPU path's, evaluation by evaluation.
+#include <atomic>
 #include <cstdlib>
 #include <cuda_runtime.h>
 #include <math_constants.h>
@@ -925,13 +926,13 @@ static int launch_multi_t(const FrameView& f, const HypGen* gen, const HypFast* 
   // kinds with the 2-D test queue borderline evaluations on the spot (pixel-level thresholds put a percent of a good
   // hypothesis' evaluations inside the band); without it the group flag + rare re-walk is cheaper
   static const bool direct = getenv("RPE_MULTI_DIRECT") ? getenv("RPE_MULTI_DIRECT")[0] != '0' : KindTraits<KIND>::k2;
-  static bool attr_set[64] = {};  // the attribute is per device
+  static std::atomic<bool> attr_set[64];  // the attribute is per device; setting it twice from two host threads is harmless
   int dev = 0;
   cudaGetDevice(&dev);
-  if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+  if (dev >= 0 && dev < 64 && !attr_set[dev].load(std::memory_order_acquire)) {
     cudaFuncSetAttribute(score_multi_fast_kernel<KIND, TILE, THREADS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaFuncSetAttribute(score_multi_fast_kernel<KIND, TILE, THREADS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attr_set[dev] = true;
+    attr_set[dev].store(true, std::memory_order_release);
   }
   if (direct)
     score_multi_fast_kernel<KIND, TILE, THREADS, true><<<dim3(gx, gy), THREADS, smem, s>>>(
@@ -990,20 +991,20 @@ static int launch_variant(const FrameView& f, const HypGen* gen, const HypFast* 
     auto rk = score3d_raw_kernel<HPT, RT, THREADS, MINB, SUB>;
     size_t rsmem = (size_t)RT * 3 * sizeof(float4) + 4 * (size_t)RT * 6 * sizeof(float) + 2 * sizeof(uint64_t) + 16;
     if (MINB == 1 && g_exclusive_sm && rsmem < (size_t)116 * 1024) rsmem = (size_t)116 * 1024;
-    static bool rattr_set[64] = {};
-    if (dev >= 0 && dev < 64 && !rattr_set[dev]) {
+    static std::atomic<bool> rattr_set[64];
+    if (dev >= 0 && dev < 64 && !rattr_set[dev].load(std::memory_order_acquire)) {
       cudaFuncSetAttribute(rk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem);
-      rattr_set[dev] = true;
+      rattr_set[dev].store(true, std::memory_order_release);
     }
     rk<<<dim3(gx, gy), THREADS, rsmem, s>>>(f.xw, f.xc, f.n, f.npairs_pad, pairs_per_cta, fast, gen, slot_begin, slot_end,
                                             th.thr3d, votes, st, wl);
     return gx * gy;
   }
   auto kern = score3d_fast_kernel<PACKED, HPT, TILE, THREADS, MINB, SUB>;
-  static bool attr_set[64] = {};  // the attribute is per device
-  if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+  static std::atomic<bool> attr_set[64];  // the attribute is per device
+  if (dev >= 0 && dev < 64 && !attr_set[dev].load(std::memory_order_acquire)) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem > (size_t)116 * 1024 ? smem : (size_t)116 * 1024));
-    attr_set[dev] = true;
+    attr_set[dev].store(true, std::memory_order_release);
   }
   kern<<<dim3(gx, gy), THREADS, smem, s>>>(f.pk, f.npairs_pad, pairs_per_cta, fast, gen, slot_begin, slot_end, th.thr3d,
                                             votes, st, wl, g_nosync);

@@ -24,8 +24,29 @@ def rpe():
     return r
 
 
-@pytest.fixture(scope="session")
+@pytest.fixture(scope="module")
 def gpu_ctx(rpe):
+    """One context per test MODULE (not per session): what a module leaves in it cannot reach another module."""
     ctx = rpe.Context(0)
     yield ctx
     ctx.close()
+
+
+@pytest.fixture(autouse=True)
+def _reset_debug_hooks(request):
+    """GPU tests: the process-global test hooks (packed / raw tiles / exact-only / score variant) and the per-context
+    ones (worklist capacity, first-pass length, stage timing) go back to the shipped configuration after EVERY test,
+    so the suite does not depend on file or test order."""
+    yield
+    if request.node.get_closest_marker("gpu") is None:
+        return
+    import rgbd_pose_estimation_b200 as r
+    ctx = request.node.funcargs.get("gpu_ctx") if hasattr(request.node, "funcargs") else None
+    if ctx is not None and ctx.handle:
+        try:
+            ctx.sync()
+        except r.RpeError:
+            pass
+        ctx.debug_reset()
+    else:
+        r.lib.rpe_debug_reset(None)

@@ -93,3 +93,39 @@ def test_device_kinect_noise_model(rpe, gpu_ctx):
     # grazing surfaces are noisier in depth than the quadratic term alone
     graz = inl & (theta > np.deg2rad(75.0)) & (z > 3.0) & (z < 4.0)
     assert robust_sigma(e[graz, 2] / base[graz]) > 1.05
+
+
+def test_frame_replacement_leaves_binary64_mode(rpe, orc):
+    """Regression (round-1 driver run): a context that was in binary64 mode (rpe_upload_f64, small n) must score the NEW
+    frame after rpe_sim_3d_3d_device / rpe_upload / rpe_upload_device — not the stale binary64 arrays, and never read
+    past them."""
+    rng = np.random.default_rng(5)
+    with rpe.Context(0) as ctx:
+        n_small = 2600
+        q, t = rpe.sim_pose(3)
+        Q, P, _ = rpe.sim_3d_3d(4, q, t, n_small)
+        ctx.upload_f64(xc=P.astype(np.float64), xw=Q.astype(np.float64))
+        r64 = ctx.ransac_f64("shinji", rpe.sample_table(1, n_small, 3, 64), thr3d=0.25, confidence=0.99)
+        assert r64["flags"] & 2
+        # 1. device-side simulator
+        n = 100000
+        ctx.sim_3d_3d_device(11, q, t, n, noise=0.1, outlier_ratio=0.5)
+        S = rpe.sample_table(1, n, 3, 256)
+        r = ctx.ransac("shinji", S, thr3d=0.25, confidence=0.9999)
+        assert not (r["flags"] & 2) and 0.4 * n < r["max_votes"] < 0.5 * n
+        d = ctx.download(("xc", "xw"))
+        ref = orc.ransac(0, S, thr3d=0.25, confidence=0.9999, full=True, xc=d["xc"], xw=d["xw"])
+        assert r["winner"] == ref["winner"] and r["max_votes"] == ref["max_votes"]
+        assert np.array_equal(r["mask"], ref["mask"])
+        # 2. float upload after a binary64 one
+        ctx.upload_f64(xc=P.astype(np.float64), xw=Q.astype(np.float64))
+        Q2, P2, _ = rpe.sim_3d_3d(6, q, t, 30000)
+        ctx.upload(xc=P2, xw=Q2)
+        S2 = rpe.sample_table(2, 30000, 3, 128)
+        r2 = ctx.ransac("shinji", S2, thr3d=0.25, confidence=0.99)
+        ref2 = orc.ransac(0, S2, thr3d=0.25, confidence=0.99, full=True, xc=P2, xw=Q2)
+        assert not (r2["flags"] & 2) and r2["winner"] == ref2["winner"] and np.array_equal(r2["mask"], ref2["mask"])
+        # 3. rpe_ransac_f64 on a context that left binary64 mode is refused, not served from stale arrays
+        with pytest.raises(rpe.RpeError):
+            ctx.ransac_f64("shinji", S2, thr3d=0.25, confidence=0.99)
+        del rng
