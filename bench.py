@@ -150,11 +150,11 @@ def load_profile_traffic():
 # ------------------------------------------------------------------------------------------------
 # CPU path (oracle port of the reference), used by --impl reference and by the cpu_baseline leg
 # ------------------------------------------------------------------------------------------------
-def cpu_run(frame, samples, nthreads, full=True):
+def cpu_run(frame, samples, nthreads, full=True, want_arrays=False):
     from tests import orc  # the CPU oracle: the thing being timed here
     orc.set_math_mode(orc.DET)
     return orc.ransac(METHOD_SHINJI, samples, thr3d=THR3D, confidence=CONF, full=full, nthreads=nthreads,
-                      xc=frame["xc"], xw=frame["xw"], want_arrays=False)
+                      xc=frame["xc"], xw=frame["xw"], want_arrays=want_arrays)
 
 
 def time_reference_sources(frame, iters=16):
@@ -214,12 +214,20 @@ def run_reference(args, rank):
 
 def workload_config(args, world):
     return {
-        "workload": "config4/5: dense 640x480 RGB-D frame, 307200 3-D/3-D correspondences x 1024 hypotheses, "
-                    "shinji_ransac2 + shinji_ls1 + LM refinement; frames sharded across GPUs",
+        "workload": "config5 (config4-sized frames): batched sequence of dense 640x480 RGB-D frames, 307200 3-D/3-D "
+                    "correspondences x 1024 hypotheses each, shinji_ransac2 + shinji_ls1 + LM refinement; frames sharded "
+                    "across GPUs",
         "n_correspondences": N_CORR, "n_hypotheses": N_HYP, "outlier_ratio": OUTLIER, "noise_m": NOISE,
         "thr3d_m": THR3D, "confidence": CONF, "frames_per_step_per_gpu": args.frames_per_step,
-        "distinct_frames_per_gpu": args.ring, "contexts_per_gpu": args.contexts, "gn_max_iters": args.gn_iters,
-        "l2_policy": f"inputs larger than L2: ring of {args.ring} distinct frames x 7.4 MB per GPU (scored straight from these arrays)",
+        "distinct_frames_per_gpu": args.distinct, "contexts_per_gpu": args.contexts, "issue_threads_per_gpu": args.threads,
+        "gn_max_iters": args.gn_iters,
+        "inputs": f"{args.distinct} distinct frames per GPU generated ON THE DEVICE before the timed region "
+                  f"(rpe_sim_3d_3d_device_to, counter-based RNG; {args.distinct} x 7.4 MB resident in HBM); the e2e leg "
+                  f"streams a ring of {args.ring} of them from page-locked host memory",
+        "sample_tables": "drawn INSIDE the timed regions by the issuing threads (rpe_sampler_reseed + rpe_sampler_rows: "
+                         "frame i uses rpe_sample_table(seed + i)), 16 KB H2D per frame",
+        "l2_policy": f"inputs larger than L2: {args.distinct} distinct frames x 7.4 MB per GPU (e2e: ring of {args.ring}), "
+                     "scored straight from these arrays",
         "parallelism": f"frames sharded over {world} GPU(s), no data-path collective",
     }
 
@@ -227,88 +235,89 @@ def workload_config(args, world):
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
-def bind_near_gpu(torch, local_rank):
-    """Pin this rank's host threads (and with them the first-touch placement of its page-locked buffers) to the CPUs
-    of the GPU's NUMA node, so that the e2e leg's H2D/D2H copies do not cross the socket interconnect."""
+def _parse_cpulist(spec):
+    cpus = set()
+    for part in spec.strip().split(","):
+        if "-" in part:
+            a, b = part.split("-")
+            cpus.update(range(int(a), int(b) + 1))
+        elif part:
+            cpus.add(int(part))
+    return cpus
+
+
+def bind_near_gpu(torch, local_rank, world):
+    """Pin this rank's host threads (and with them the first-touch placement of its page-locked buffers) to a slice of
+    the CPUs local to its GPU that NO other rank uses: ranks whose GPUs share a CPU list split it evenly."""
     try:
-        p = torch.cuda.get_device_properties(local_rank)
-        bdf = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
-        with open(f"/sys/bus/pci/devices/{bdf}/local_cpulist") as fh:
-            spec = fh.read().strip()
-        cpus = set()
-        for part in spec.split(","):
-            if "-" in part:
-                a, b = part.split("-")
-                cpus.update(range(int(a), int(b) + 1))
-            elif part:
-                cpus.add(int(part))
-        cpus &= os.sched_getaffinity(0)
-        if cpus:
-            os.sched_setaffinity(0, cpus)
-            return {"pci": bdf, "cpus": len(cpus)}
+        lists = []
+        for i in range(world):
+            p = torch.cuda.get_device_properties(i)
+            bdf = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+            with open(f"/sys/bus/pci/devices/{bdf}/local_cpulist") as fh:
+                lists.append(fh.read().strip())
+        mine = lists[local_rank]
+        sharers = [i for i in range(world) if lists[i] == mine]
+        cpus = sorted(_parse_cpulist(mine) & os.sched_getaffinity(0))
+        if not cpus:
+            return {"skipped": "no local cpus"}
+        j, g = sharers.index(local_rank), len(sharers)
+        part = cpus[j * len(cpus) // g:(j + 1) * len(cpus) // g]
+        if len(part) < 2:
+            part = cpus
+        os.sched_setaffinity(0, set(part))
+        return {"cpus": len(part), "first_cpu": part[0], "last_cpu": part[-1], "ranks_sharing_the_list": g,
+                "local_cpulist": mine}
     except Exception as e:  # no sysfs entry / no permission: leave the affinity alone
         return {"skipped": repr(e)[:80]}
-    return {"skipped": "no local cpus"}
 
 
 def run_gpu(args, rank, world, local_rank):
+    import ctypes as C
     import torch
     import rgbd_pose_estimation_b200 as rpe
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product has no CPU fallback (use --impl reference for the CPU path)")
     torch.cuda.set_device(local_rank)
-    binding = bind_near_gpu(torch, local_rank) if world > 1 else {"skipped": "single GPU"}
+    binding = bind_near_gpu(torch, local_rank, world) if world > 1 else {"skipped": "single GPU"}
     dist = None
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     dev = torch.device("cuda", local_rank)
-    # --- data: ring of distinct frames, device-resident for `value`, page-locked host copies for `e2e`
-    frames = make_frames(rpe, args.ring, N_CORR, seed0=1000 + 7919 * rank)
-    d_xw = [torch.from_numpy(f["xw"]).to(dev) for f in frames]
-    d_xc = [torch.from_numpy(f["xc"]).to(dev) for f in frames]
-    tables = [rpe.sample_table(1 + i + 100 * rank, N_CORR, 3, N_HYP) for i in range(args.ring)]
-    d_tab = [torch.from_numpy(t).to(dev) for t in tables]
-    h_xw, h_xc, h_tab = [], [], []
-    for f, t in zip(frames, tables):
+    frame_bytes = N_CORR * 12
+    # --- the sequence runner: native issue threads over `contexts` streams (the public API for batched sequences)
+    seq = rpe.Sequence(local_rank, "shinji", N_HYP, thr3d=THR3D, confidence=CONF, refit=("kabsch", "gn"),
+                       gn_iters=args.gn_iters, sample_seed=1 + 100003 * rank, contexts=args.contexts, threads=args.threads)
+    seq_ctx = seq.contexts()
+    for h in seq_ctx:
+        rpe.lib.rpe_enable_stage_timing(h, 2)  # two events around every tiled-scorer launch (roofline), nothing else
+
+    # --- data: `distinct` frames generated on the device (config #5: no PCIe traffic for the resident leg)
+    c0 = rpe.Context(local_rank)
+    xw_all = torch.empty((args.distinct, N_CORR, 3), dtype=torch.float32, device=dev)
+    xc_all = torch.empty((args.distinct, N_CORR, 3), dtype=torch.float32, device=dev)
+    poses = []
+    for i in range(args.distinct):
+        q, t = rpe.sim_pose(1000 + 7919 * rank + 2 * i)
+        poses.append((q, t))
+        c0.sim_3d_3d_device_to(5000 + 104729 * rank + i, q, t, N_CORR, xw_all[i].data_ptr(), xc_all[i].data_ptr(),
+                               noise=NOISE, outlier_ratio=OUTLIER)
+    c0.sync()
+    dev_frames = [{"xw": xw_all[i].data_ptr(), "xc": xc_all[i].data_ptr(), "n": N_CORR} for i in range(args.distinct)]
+    # page-locked host copies of the first `ring` frames (+ one page-locked mask each) for the e2e leg
+    h_xw, h_xc, h_mask = [], [], []
+    for i in range(args.ring):
         a = rpe.pinned_empty((N_CORR, 3), np.float32)
-        a[:] = f["xw"]
         b = rpe.pinned_empty((N_CORR, 3), np.float32)
-        b[:] = f["xc"]
-        c = rpe.pinned_empty((N_HYP, 4), np.int32)
-        c[:] = t
+        a[:] = xw_all[i].cpu().numpy()
+        b[:] = xc_all[i].cpu().numpy()
         h_xw.append(a)
         h_xc.append(b)
-        h_tab.append(c)
-
-    streams = [torch.cuda.Stream(device=dev) for _ in range(args.contexts)]
-    ctxs = [rpe.Context(local_rank, stream=s.cuda_stream) for s in streams]
-    h_mask = [rpe.pinned_empty((2, N_CORR), np.int16) for _ in ctxs]
-    for c in ctxs:
-        c.enable_stage_timing(2)  # timed legs: only the two events around the tiled scoring kernel (roofline)
-
-    def frame_device(ci, fi):
-        c = ctxs[ci]
-        c.upload_device(N_CORR, xc=d_xc[fi].data_ptr(), xw=d_xw[fi].data_ptr())
-        r0 = c.ransac_async(METHOD_SHINJI, d_tab[fi].data_ptr(), H=N_HYP, thr3d=THR3D, confidence=CONF)
-        r1 = c.refit_async("kabsch_inliers")
-        r2 = c.refit_async("gn", max_iters=args.gn_iters)
-        return r0, r1, r2
-
-    def frame_host(ci, fi):
-        c = ctxs[ci]
-        c.upload_async(xc=h_xc[fi], xw=h_xw[fi])
-        r0 = c.ransac_async(METHOD_SHINJI, h_tab[fi], thr3d=THR3D, confidence=CONF, mask=h_mask[ci])
-        r1 = c.refit_async("kabsch_inliers")
-        r2 = c.refit_async("gn", max_iters=args.gn_iters)
-        return r0, r1, r2
-
-    def sync_all():
-        for c in ctxs:
-            c.sync()
-            c._keep = []
+        h_mask.append(rpe.pinned_empty((2, N_CORR), np.int16))
+    host_frames = [{"xw": h_xw[i], "xc": h_xc[i], "mask": h_mask[i]} for i in range(args.ring)]
 
     def barrier():
         torch.cuda.synchronize()
@@ -316,99 +325,103 @@ def run_gpu(args, rank, world, local_rank):
             dist.barrier()
             torch.cuda.synchronize()
 
-    def run_steps(step_fn, steps):
-        k = 0
-        last = None
-        for _ in range(steps):
-            for _f in range(args.frames_per_step):
-                last = step_fn(k % args.contexts, k % args.ring)
-                k += 1
-        return last
+    def scorer_stats(reset):
+        tot, cnt = 0.0, 0
+        sm, ct = C.c_double(0), C.c_longlong(0)
+        for h in seq_ctx:
+            rpe.lib.rpe_scorer_time_stats(h, C.byref(sm), C.byref(ct), 1 if reset else 0)
+            tot += sm.value
+            cnt += ct.value
+        return tot, cnt
 
-    host_issue_ms = [0.0]  # wall time the host spends enqueueing one frame (no GPU wait unless a queue fills up)
+    def launches_now():
+        return sum(int(rpe.lib.rpe_launch_count(h)) for h in seq_ctx)
 
-    def timed(step_fn, steps, stage_acc=None):
+    def timed(n_frames, first):
+        """ONE rpe_seq_run over the whole region; device time by CUDA events on a stream that waits for nothing else:
+        the call is blocking and returns after every context has been synchronised, so the events bracket it."""
         barrier()
         e0 = torch.cuda.Event(enable_timing=True)
         e1 = torch.cuda.Event(enable_timing=True)
         e0.record()
-        k = 0
-        last = None
-        t_issue = time.perf_counter()
-        for _s in range(steps):
-            for _f in range(args.frames_per_step):
-                last = step_fn(k % args.contexts, k % args.ring)
-                k += 1
-            if stage_acc is not None and (_s % 4 == 3 or _s == steps - 1):
-                sync_all()
-                for c in ctxs:
-                    stage_acc.append(c.last_stage_ms())
-        host_issue_ms[0] = (time.perf_counter() - t_issue) * 1e3 / max(1, steps * args.frames_per_step)
-        sync_all()
+        t0 = time.perf_counter()
+        r0, r1 = seq.run(first, n_frames)
+        wall_ms = (time.perf_counter() - t0) * 1e3
         e1.record()
         torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1)
+        ms = max(e0.elapsed_time(e1), 0.0)
         if dist is not None:
             tt = torch.tensor([ms], device=dev, dtype=torch.float64)
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             ms = float(tt.item())
         barrier()
-        return ms, last
+        return ms, wall_ms, r0, r1
 
     sampler = ClockSampler(local_rank)
     sampler.start()
     # --- FFMA peak of this device, same process/run (roofline denominator)
-    ffma_scalar, ffma_packed = ctxs[0].measure_ffma_tflops(100)
+    ffma_scalar, ffma_packed = c0.measure_ffma_tflops(100)
 
-    # --- warm-up
-    run_steps(frame_device, args.warmup)
-    sync_all()
-    run_steps(frame_host, max(1, args.warmup // 2))
-    sync_all()
+    fps = args.frames_per_step
+    # --- warm-up (W >= 3 steps on the resident leg, half of that on the host leg)
+    seq.set_frames(dev_frames)
+    seq.run(0, args.warmup * fps, want_results=False)
+    seq.set_frames(host_frames)
+    seq.run(0, max(1, args.warmup // 2) * fps, want_results=False)
 
     # --- `value`: inputs resident in HBM
-    launches0 = sum(c.launch_count() for c in ctxs)
-    stage_acc = []
+    seq.set_frames(dev_frames)
+    scorer_stats(True)
+    launches0 = launches_now()
     w0 = time.time()
-    ms_dev, last_dev = timed(frame_device, args.steps, stage_acc)
-    issue_dev = host_issue_ms[0]
+    ms_dev, wall_dev, r0_dev, r1_dev = timed(args.steps * fps, 0)
     w1 = time.time()
-    launches = sum(c.launch_count() for c in ctxs) - launches0
-    # --- `e2e`: host buffers, H2D + D2H inside the timed region
+    launches = launches_now() - launches0
+    fast_sum, fast_cnt = scorer_stats(True)
+    # --- `e2e`: host buffers, H2D + D2H inside the timed region, through the same public call
+    seq.set_frames(host_frames)
     w2 = time.time()
-    ms_e2e, last_e2e = timed(frame_host, args.steps)
-    issue_e2e = host_issue_ms[0]
+    ms_e2e, wall_e2e, r0_e2e, r1_e2e = timed(args.steps * fps, 0)
     w3 = time.time()
+    fast_sum_e2e, fast_cnt_e2e = scorer_stats(True)
     sampler.stop()
     clocks = sampler.summarise(w0, w1)
     clocks_e2e = sampler.summarise(w2, w3)
     sampler.cleanup()
 
+    # --- the box's concurrent host-to-device ceiling: every rank copies the same page-locked frames, no compute
+    h2d = measure_h2d_ceiling(rpe, torch, dist, dev, local_rank, h_xw, h_xc, barrier)
+
     # --- per-stage device times of one frame running alone (all stage events on, one context, inputs in HBM)
-    ctxs[0].enable_stage_timing(1)
+    tab0 = rpe.sample_table(1 + 100003 * rank, N_CORR, 3, N_HYP)  # = the table frame 0 drew inside the runner
+    c0.enable_stage_timing(1)
     stage_alone = []
     for i in range(6):
-        frame_device(0, i % args.ring)
-        ctxs[0].sync()
-        ctxs[0]._keep = []
+        c0.upload_device(N_CORR, xc=dev_frames[i]["xc"], xw=dev_frames[i]["xw"])
+        c0.ransac_async(METHOD_SHINJI, tab0, thr3d=THR3D, confidence=CONF)
+        c0.refit_async("kabsch_inliers")
+        c0.refit_async("gn", max_iters=args.gn_iters)
+        c0.sync()
         if i > 0:
-            stage_alone.append(ctxs[0].last_stage_ms())
-    ctxs[0].enable_stage_timing(2)
+            stage_alone.append(c0.last_stage_ms())
+    c0.enable_stage_timing(0)
 
     # --- single blocking frame latency through the C-ABI with host buffers (one context)
+    h_tab = rpe.pinned_empty((N_HYP, 4), np.int32)
+    h_tab[:] = tab0
     lat = []
-    for i in range(5):
+    for i in range(7):
         t0 = time.perf_counter()
-        c = ctxs[0]
-        c.upload_async(xc=h_xc[i % args.ring], xw=h_xw[i % args.ring])
-        c.ransac_async(METHOD_SHINJI, h_tab[i % args.ring], thr3d=THR3D, confidence=CONF, mask=h_mask[0])
-        c.refit_async("kabsch_inliers")
-        c.refit_async("gn", max_iters=args.gn_iters)
-        c.sync()
-        lat.append((time.perf_counter() - t0) * 1e3)
-        c._keep = []
+        c0.upload_async(xc=h_xc[i % args.ring], xw=h_xw[i % args.ring])
+        c0.ransac_async(METHOD_SHINJI, h_tab, thr3d=THR3D, confidence=CONF, mask=h_mask[0])
+        c0.refit_async("kabsch_inliers")
+        c0.refit_async("gn", max_iters=args.gn_iters)
+        c0.sync()
+        if i >= 2:
+            lat.append((time.perf_counter() - t0) * 1e3)
 
-    frames_total = args.steps * args.frames_per_step * world
+    frames_rank = args.steps * fps
+    frames_total = frames_rank * world
     evals_total = frames_total * N_CORR * N_HYP
     value = evals_total / (ms_dev * 1e-3)
     e2e_value = evals_total / (ms_e2e * 1e-3)
@@ -417,12 +430,11 @@ def run_gpu(args, rank, world, local_rank):
         dist.all_reduce(lt)
         launches = int(lt.item())
 
-    # --- roofline of the dominant kernel (tiled scorer), live CUDA-event timing of that kernel alone
-    fast_ms = [s["score_fast"] for s in stage_acc if s["score_fast"] > 0]
+    # --- roofline of the dominant kernel (tiled scorer): mean CUDA-event duration of EVERY launch in the timed region
     stage_mean = {k: float(np.mean([s[k] for s in stage_alone])) for k in stage_alone[0]} if stage_alone else {}
     roofline = None
-    if fast_ms:
-        k_ms = float(np.mean(fast_ms))
+    if fast_cnt > 0:
+        k_ms = fast_sum / fast_cnt
         achieved = FLOP_PER_EVAL * N_CORR * N_HYP / (k_ms * 1e-3) / 1e12
         peak = max(ffma_scalar, ffma_packed)
         peaks = load_measured_peaks()
@@ -431,16 +443,22 @@ def run_gpu(args, rank, world, local_rank):
         roofline = {
             "bound": "fp32", "kernel": "score3d_raw_kernel", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
             "frac": achieved / peak if peak > 0 else None,
-            "peak_source": "FFMA/FFMA2 microbenchmark measured in this run (MEASURED_PEAKS.json has no FP32 CUDA-core figure)",
             "frac_of_nominal": achieved / NOMINAL_FP32_TFLOPS, "nominal_peak": NOMINAL_FP32_TFLOPS,
+            "peak_source": "FFMA/FFMA2 microbenchmark measured in this run (MEASURED_PEAKS.json has no FP32 CUDA-core "
+                           "figure); frac_of_nominal is against 148 SM x 128 lanes x 2 x 1.965 GHz",
             "ffma_scalar_tflops": ffma_scalar, "ffma2_packed_tflops": ffma_packed,
-            "kernel_ms": k_ms, "flop_per_eval": FLOP_PER_EVAL, "evals_per_launch": N_CORR * N_HYP,
-            "kernel_ms_note": f"mean over the timed region while {args.contexts} contexts share the GPU (the kernel "
-                              "co-runs with other frames' small kernels); kernel_alone_ms is the same kernel with one "
-                              "context",
+            "kernel_ms": k_ms, "launches_timed": fast_cnt, "flop_per_eval": FLOP_PER_EVAL,
+            "evals_per_launch": N_CORR * N_HYP,
+            "kernel_ms_note": f"mean over all {fast_cnt} scorer launches of the timed region (own CUDA-event pair per launch "
+                              f"on the stream it runs on) while {args.contexts} contexts share the GPU; kernel_alone_ms is "
+                              "the same kernel with one context",
+            "kernel_ms_e2e": fast_sum_e2e / fast_cnt_e2e if fast_cnt_e2e else None,
+            "share_of_step": fast_sum / ms_dev if ms_dev > 0 else None,
             "kernel_alone_ms": stage_mean.get("score_fast"),
             "frac_alone": (FLOP_PER_EVAL * N_CORR * N_HYP / (stage_mean["score_fast"] * 1e-3) / 1e12 / peak
                            if stage_mean.get("score_fast") and peak > 0 else None),
+            "frac_alone_of_nominal": (FLOP_PER_EVAL * N_CORR * N_HYP / (stage_mean["score_fast"] * 1e-3) / 1e12
+                                      / NOMINAL_FP32_TFLOPS if stage_mean.get("score_fast") else None),
             "traffic": load_profile_traffic(),
             "hbm": {"algorithmic_bytes_per_launch": alg_bytes, "achieved_gbs": alg_bytes / (k_ms * 1e-3) / 1e9,
                     "peak_gbs": hbm_peak, "peak_source": "MEASURED_PEAKS.json (of measured)" if peaks else "fallback 6.65 TB/s",
@@ -451,23 +469,37 @@ def run_gpu(args, rank, world, local_rank):
     sharded = None
     if dist is not None:
         try:
-            sharded = run_single_frame_sharded(args, torch, dist, rpe, ctxs[0], streams[0], frames, tables, rank, world, dev)
+            f0 = {"xw": None, "xc": None}
+            stream0 = torch.cuda.Stream(device=dev)
+            cs = rpe.Context(local_rank, stream=stream0.cuda_stream)
+            sharded = run_single_frame_sharded(args, torch, dist, rpe, cs, stream0, None, None, rank, world, dev)
+            cs.close()
+            del f0
         except Exception as e:  # never lose the headline line over the auxiliary measurement
             sharded = {"error": repr(e)}
 
-    # --- CPU baseline (rank 0, N=1 only): the oracle port of the reference CPU path on the host cores
+    # --- CPU baseline (rank 0, N=1 only): the oracle port of the reference CPU path on the host cores,
+    #     and the parity check of the GPU result of the same frame against it (full vote table + mask)
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cores = os.cpu_count() or 1
-        r_mt = cpu_run(frames[0], tables[0], cores)  # 1 frame, all 1024 hypotheses scored
+        f_host = {"xw": np.ascontiguousarray(h_xw[0]), "xc": np.ascontiguousarray(h_xc[0])}
+        r_mt = cpu_run(f_host, tab0, cores, want_arrays=True)  # 1 frame, all 1024 hypotheses scored
         h1 = 96
-        r_1t = cpu_run(frames[0], tables[0][:h1], 1)
-        r_es = cpu_run(frames[0], tables[0], 1, full=False)  # the reference's own early-stopping loop
-        gpu_first = None
-        c = ctxs[0]
-        c.upload_device(N_CORR, xc=d_xc[0].data_ptr(), xw=d_xw[0].data_ptr())
-        g = c.ransac(METHOD_SHINJI, tables[0], thr3d=THR3D, confidence=CONF, want_mask=False)
-        gpu_first = {"winner": g["winner"], "max_votes": g["max_votes"], "iter_final": g["iter_final"]}
+        r_1t = cpu_run(f_host, tab0[:h1], 1)
+        r_es = cpu_run(f_host, tab0, 1, full=False)  # the reference's own early-stopping loop
+        c0.upload_device(N_CORR, xc=dev_frames[0]["xc"], xw=dev_frames[0]["xw"])
+        g = c0.ransac(METHOD_SHINJI, tab0, thr3d=THR3D, confidence=CONF, want_mask=True)
+        g_votes = c0.get_votes(N_HYP)
+        seq0 = r0_dev[0]  # frame 0 of the timed resident region went through the sequence runner with the same table
+        agree = {
+            "winner_votes_iter": bool(g["winner"] == r_mt["winner"] and g["max_votes"] == r_mt["max_votes"]
+                                      and g["iter_final"] == r_mt["iter_final"]),
+            "vote_table_1024": bool(np.array_equal(g_votes, r_mt["votes"])),
+            "mask": bool(np.array_equal(g["mask"], r_mt["mask"])),
+            "sequence_runner_frame0": bool(seq0.winner == r_mt["winner"] and seq0.max_votes == r_mt["max_votes"]
+                                           and seq0.iter_final == r_mt["iter_final"]),
+        }
         cpu_baseline = {
             "value": r_mt["evals"] / r_mt["seconds"], "unit": "evals/s", "cores": cores, "kind": "port",
             "sample": f"1 frame x {N_HYP} hypotheses x {N_CORR} correspondences, every hypothesis scored, "
@@ -477,43 +509,99 @@ def run_gpu(args, rank, world, local_rank):
                               "sample": f"{h1} hypotheses x {N_CORR} correspondences"},
             "early_stop_loop": {"seconds_per_frame": r_es["seconds"], "iterations_run": r_es["iters_run"],
                                 "note": "the reference's literal loop stops at the adaptive Iter; same winner"},
-            "cpu_gpu_agree": bool(gpu_first["winner"] == r_mt["winner"] and gpu_first["max_votes"] == r_mt["max_votes"]
-                                  and gpu_first["iter_final"] == r_mt["iter_final"]),
+            "cpu_gpu_agree": all(agree.values()), "cpu_gpu_agree_detail": agree,
         }
         # informational: the reference's own loop (its sources on the Eigen stand-in), single thread; never raises
-        cpu_baseline["reference_sources_single_thread"] = time_reference_sources(frames[0])
+        cpu_baseline["reference_sources_single_thread"] = time_reference_sources(f_host)
 
     if rank == 0:
-        h2d = args.frames_per_step * (2 * N_CORR * 12 + N_HYP * 16)
-        d2h = args.frames_per_step * (2 * N_CORR * 2 + 3 * 72 + 12)
+        h2d_step = fps * (2 * frame_bytes + N_HYP * 16)
+        d2h_step = fps * (2 * N_CORR * 2 + 3 * 72 + 12)
+        e2e_frames_s_gpu = frames_rank / (ms_e2e * 1e-3)
+        e2e_h2d_gbs = e2e_frames_s_gpu * (2 * frame_bytes + N_HYP * 16) / 1e9
         line = {
             "metric": "hyp-corr evals/s", "value": value, "unit": "evals/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, world),
             "frames_per_s": frames_total / (ms_dev * 1e-3),
-            "ms_per_frame_per_gpu": ms_dev / (args.steps * args.frames_per_step),
-            "host_issue_ms_per_frame": issue_dev,
+            "ms_per_frame_per_gpu": ms_dev / frames_rank,
             "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+            "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": h2d_step, "d2h_bytes_per_step": d2h_step,
                     "frames_per_s": frames_total / (ms_e2e * 1e-3), "ms_per_step": ms_e2e / args.steps,
+                    "ms_per_frame_per_gpu": ms_e2e / frames_rank,
                     "single_frame_latency_ms": {"median": float(np.median(lat)), "min": float(min(lat))},
-                    "host_issue_ms_per_frame": issue_e2e, "numa_binding_rank0": binding,
+                    "h2d_gbs_per_gpu": e2e_h2d_gbs,
+                    "h2d_ceiling": h2d,
+                    "h2d_frac_of_ceiling": (e2e_h2d_gbs / h2d["per_gpu_gbs"] if h2d and h2d.get("per_gpu_gbs") else None),
+                    "numa_binding_rank0": binding,
                     "clocks": clocks_e2e,
-                    "path": "rpe_upload(host pinned) + rpe_ransac_async + rpe_refit_async x2 + mask/pose D2H, "
-                            f"{args.contexts} contexts round-robin"},
+                    "path": f"rpe_seq_run: {args.threads} native issue threads x {args.contexts} contexts per GPU; per frame "
+                            "sample-table draw + rpe_upload(host page-locked) + rpe_ransac_async + rpe_refit_async x2 + "
+                            "mask/pose D2H"},
             "gpu_launches": launches,
             "roofline": roofline,
             "stage_ms_mean": stage_mean,
             "cpu_baseline": cpu_baseline,
             "single_frame_sharded": sharded,
-            "last_result": {"max_votes": int(last_dev[0].max_votes), "iter_final": int(last_dev[0].iter_final),
-                            "n_borderline": int(last_dev[0].n_borderline), "gn_evals": int(last_dev[2].refit_evals)},
+            "last_result": {"max_votes": int(r0_dev[frames_rank - 1].max_votes),
+                            "iter_final": int(r0_dev[frames_rank - 1].iter_final),
+                            "n_borderline": int(r0_dev[frames_rank - 1].n_borderline),
+                            "gn_evals": int(r1_dev[frames_rank - 1].refit_evals)},
         }
         print(json.dumps(line))
-    for c in ctxs:
-        c.close()
+    seq.close()
+    c0.close()
     if dist is not None:
         dist.destroy_process_group()
+
+
+def measure_h2d_ceiling(rpe, torch, dist, dev, local_rank, h_xw, h_xc, barrier, seconds=0.25):
+    """All ranks at once: rpe_upload of the e2e leg's own page-locked frames (2 x 3.7 MB per frame) on 4 contexts
+    (streams), no compute. Returns this box's concurrent H2D rate per GPU (min over ranks) and in aggregate."""
+    try:
+        cs = [rpe.Context(local_rank) for _ in range(4)]
+        nbytes = 2 * h_xw[0].nbytes
+
+        def burst(reps):
+            k = 0
+            for _ in range(reps):
+                for c in cs:
+                    c.upload_async(xc=h_xc[k % len(h_xc)], xw=h_xw[k % len(h_xw)])
+                    k += 1
+            return k
+        burst(2)
+        for c in cs:
+            c.sync()
+        barrier()
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        t0 = time.perf_counter()
+        copies = 0
+        while time.perf_counter() - t0 < seconds:
+            copies += burst(4)
+            for c in cs:
+                c.sync()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        gbs = copies * nbytes / (ms * 1e-3) / 1e9
+        lo, tot = gbs, gbs
+        if dist is not None:
+            t = torch.tensor([gbs], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            lo = float(t.item())
+            t = torch.tensor([gbs], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            tot = float(t.item())
+        barrier()
+        for c in cs:
+            c.close()
+        return {"per_gpu_gbs": lo, "aggregate_gbs": tot, "rank0_gbs": gbs,
+                "how": "all ranks concurrently: rpe_upload of 2 x 3.7 MB page-locked arrays per frame on 4 streams per GPU, "
+                       "no compute"}
+    except Exception as e:
+        return {"error": repr(e)[:120]}
 
 
 class _DevArray:
@@ -526,7 +614,7 @@ class _DevArray:
 def run_single_frame_sharded(args, torch, dist, rpe, ctx, stream, frames, tables, rank, world, dev, reps=50):
     """Config #4: correspondences replicated, every rank scores H/world hypotheses, one all-gather of the
     int32 vote table (4 KB) over NCCL, then every rank replays the adaptive rule redundantly."""
-    # identical frame on every rank: regenerate rank 0's frame 0
+    # identical frame on every rank (host generator, same seed everywhere)
     f0 = make_frames(rpe, 1, N_CORR, seed0=1000)[0]
     tab = rpe.sample_table(1, N_CORR, 3, N_HYP)
     from rgbd_pose_estimation_b200 import sharding
@@ -587,7 +675,6 @@ def run_single_frame_sharded(args, torch, dist, rpe, ctx, stream, frames, tables
             for i in range(reps):
                 ctx.ransac_sharded(METHOD_SHINJI, tab_dev.data_ptr(), H=N_HYP, thr3d=THR3D, confidence=CONF, blocking=False)
             ctx.sync()
-            ctx._keep = []
             eb.record(stream)
             torch.cuda.synchronize()
             try:
@@ -615,9 +702,11 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--frames-per-step", type=int, default=96)
-    ap.add_argument("--ring", type=int, default=24, help="distinct frames resident per GPU (>L2 in total)")
+    ap.add_argument("--frames-per-step", type=int, default=128)
+    ap.add_argument("--distinct", type=int, default=512, help="distinct frames generated on the device per GPU (4096 / 8)")
+    ap.add_argument("--ring", type=int, default=24, help="frames of the e2e leg's page-locked host ring (>L2 in total)")
     ap.add_argument("--contexts", type=int, default=12, help="rpe contexts (streams) per GPU, frames round-robin")
+    ap.add_argument("--threads", type=int, default=2, help="native issue threads per GPU (rpe_seq)")
     ap.add_argument("--gn-iters", type=int, default=3)
     ap.add_argument("--ref-hyp", type=int, default=128, help="hypotheses per step of the CPU arm (bounded sample)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")

@@ -315,6 +315,11 @@ int rpe_sim_3d_3d_device(rpe_ctx* ctx, uint64_t seed, const float q_xyzw[4], con
 int rpe_sim_2d_3d_nl_device(rpe_ctx* ctx, uint64_t seed, const float q_xyzw[4], const float t[3], int n, float n2d,
                             float or2d, float n3d, float or3d, float nnl, float ornl, float min_depth, float max_depth,
                             float f, int use_gaussian);
+/* rpe_sim_3d_3d_device into device buffers of the caller (3 x n floats each); the context's own frame is untouched.
+ * Asynchronous on the context's stream. For sequences of distinct frames resident in HBM (config #5). */
+int rpe_sim_3d_3d_device_to(rpe_ctx* ctx, uint64_t seed, const float q_xyzw[4], const float t[3], int n, float noise,
+                            float outlier_ratio, float min_depth, float max_depth, float f, int use_gaussian, float* d_xw,
+                            float* d_xc);
 /* simulate_kinect_2d_3d_nl_correspondences on the device (Kinect lateral / axial noise on the camera points). */
 int rpe_sim_kinect_2d_3d_nl_device(rpe_ctx* ctx, uint64_t seed, const float q_xyzw[4], const float t[3], int n, float n2d,
                                    float or2d, float or3d, float nnl, float ornl, float min_depth, float max_depth, float f);
@@ -337,6 +342,10 @@ int rpe_measure_ffma_tflops(rpe_ctx* ctx, int ms_target, double* tflops_scalar, 
  * rpe_enable_stage_timing: 0 = off, 1 = every stage (ten event records per frame; they cost a few percent of
  * throughput when several contexts overlap), 2 = only the two events around the tiled scoring kernel ([7]). */
 int rpe_last_stage_ms(rpe_ctx* ctx, float ms[8]);
+/* With stage timing on (1 or 2): sum and count of the tiled scoring kernel's CUDA-event durations over EVERY launch of
+ * this context since the last reset, complete after rpe_sync (each launch gets its own event pair on the stream the
+ * kernel runs on; nothing is synchronised to collect them). The roofline's `kernel_ms` over a timed region. */
+int rpe_scorer_time_stats(rpe_ctx* ctx, double* sum_ms, long long* count, int reset);
 int rpe_enable_stage_timing(rpe_ctx* ctx, int enable);
 
 #ifdef __cplusplus

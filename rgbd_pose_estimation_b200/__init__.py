@@ -8,6 +8,7 @@ has not been built (``python -c "import __graft_entry__ as g; g.build()"``).
 """
 from .capi import (  # noqa: F401
     Context,
+    Sequence,
     RpeError,
     lib,
     lib_path,
@@ -29,7 +30,7 @@ from .capi import (  # noqa: F401
 )
 
 __all__ = [
-    "Context", "RpeError", "lib", "lib_path", "METHODS", "REFITS", "sample_table", "prosac_table", "Sampler",
+    "Context", "Sequence", "RpeError", "lib", "lib_path", "METHODS", "REFITS", "sample_table", "prosac_table", "Sampler",
     "update_num_iters", "sim_pose", "sim_3d_3d", "sim_2d_3d", "sim_2d_3d_nl", "sim_kinect_2d_3d_nl", "method_slots",
     "method_mask_cols", "method_sample_size", "pinned_empty",
 ]

@@ -151,12 +151,34 @@ _sig("rpe_sim_2d_3d", C.c_int, [C.c_uint64, _vp, _vp, C.c_int, C.c_float, C.c_fl
 _sig("rpe_sim_2d_3d_nl", C.c_int, [C.c_uint64, _vp, _vp, C.c_int] + [C.c_float] * 9 + [C.c_int] + [_vp] * 6)
 _sig("rpe_sim_3d_3d_device", C.c_int, [_vp, C.c_uint64, _vp, _vp, C.c_int] + [C.c_float] * 5 + [C.c_int])
 _sig("rpe_sim_2d_3d_nl_device", C.c_int, [_vp, C.c_uint64, _vp, _vp, C.c_int] + [C.c_float] * 9 + [C.c_int])
+_sig("rpe_sim_3d_3d_device_to", C.c_int, [_vp, C.c_uint64, _vp, _vp, C.c_int] + [C.c_float] * 5 + [C.c_int, _vp, _vp])
 _sig("rpe_download", C.c_int, [_vp] * 6)
+_sig("rpe_sampler_reseed", C.c_int, [_vp, C.c_uint32])
+
+
+class SeqParams(C.Structure):
+    _fields_ = [("device", C.c_int), ("n_contexts", C.c_int), ("n_threads", C.c_int), ("method", C.c_int), ("H", C.c_int),
+                ("thr3d", C.c_float), ("cos_thr2d", C.c_float), ("cos_thrN", C.c_float), ("confidence", C.c_float),
+                ("refit", C.c_int), ("gn_iters", C.c_int), ("sample_seed", C.c_uint32)]
+
+
+class SeqFrame(C.Structure):
+    _fields_ = [("bv", _vp), ("xc", _vp), ("nc", _vp), ("xw", _vp), ("nw", _vp), ("n", C.c_int), ("on_device", C.c_int),
+                ("samples", _vp), ("mask", _vp)]
+
+
+_sig("rpe_seq_create", C.c_int, [C.POINTER(SeqParams), C.POINTER(_vp)])
+_sig("rpe_seq_run", C.c_int, [_vp, C.POINTER(SeqFrame), C.c_int, C.c_longlong, C.c_int, C.POINTER(_Result), C.POINTER(_Result)])
+_sig("rpe_seq_context", _vp, [_vp, C.c_int])
+_sig("rpe_seq_num_contexts", C.c_int, [_vp])
+_sig("rpe_seq_last_error", C.c_char_p, [_vp])
+_sig("rpe_seq_destroy", C.c_int, [_vp])
 _sig("rpe_ao", C.c_int, [_vp, _vp, C.c_int, _vp, _vp])
 _sig("rpe_ao_ransac", C.c_int, [_vp, _vp, C.c_int, _vp, _vp])
 _sig("rpe_measure_ffma_tflops", C.c_int, [_vp, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)])
 _sig("rpe_last_stage_ms", C.c_int, [_vp, _vp])
 _sig("rpe_enable_stage_timing", C.c_int, [_vp, C.c_int])
+_sig("rpe_scorer_time_stats", C.c_int, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_longlong), C.c_int])
 _sig("rpe_debug_set_packed", C.c_int, [C.c_int])
 _sig("rpe_debug_reset", C.c_int, [_vp])
 
@@ -168,8 +190,9 @@ DECLARED_SYMBOLS = [
     "rpe_set_pose", "rpe_set_mask", "rpe_generate", "rpe_get_hypotheses", "rpe_set_hypotheses", "rpe_score",
     "rpe_get_votes", "rpe_set_votes", "rpe_votes_device_ptr", "rpe_peer_export", "rpe_peer_import", "rpe_peer_import_local", "rpe_exchange_votes", "rpe_peer_status", "rpe_peer_set_timeout_ms", "rpe_ransac_sharded", "rpe_ransac_sharded_async", "rpe_finish", "rpe_update_num_iters", "rpe_sample_table",
     "rpe_prosac_table", "rpe_sampler_create", "rpe_sampler_rows", "rpe_sampler_destroy", "rpe_sim_pose", "rpe_sim_3d_3d", "rpe_sim_2d_3d", "rpe_sim_2d_3d_nl", "rpe_sim_kinect_2d_3d_nl", "rpe_sim_kinect_2d_3d_nl_device", "rpe_sim_3d_3d_device",
-    "rpe_sim_2d_3d_nl_device", "rpe_download", "rpe_ao", "rpe_ao_ransac",
-    "rpe_measure_ffma_tflops", "rpe_last_stage_ms", "rpe_enable_stage_timing",
+    "rpe_sim_2d_3d_nl_device", "rpe_sim_3d_3d_device_to", "rpe_sampler_reseed", "rpe_seq_create", "rpe_seq_run",
+    "rpe_seq_context", "rpe_seq_num_contexts", "rpe_seq_last_error", "rpe_seq_destroy", "rpe_download", "rpe_ao", "rpe_ao_ransac",
+    "rpe_measure_ffma_tflops", "rpe_last_stage_ms", "rpe_enable_stage_timing", "rpe_scorer_time_stats",
 ]
 
 
@@ -224,6 +247,9 @@ class Sampler:
             out = np.empty((H, 4), dtype=np.int32)
         _check(lib.rpe_sampler_rows(self._h, m, H, _ptr(out)))
         return out
+
+    def reseed(self, seed: int):
+        _check(lib.rpe_sampler_reseed(self._h, seed))
 
     def close(self):
         if self._h:
@@ -319,6 +345,94 @@ def pinned_empty(shape, dtype=np.float32) -> np.ndarray:
     return raw[:count * dtype.itemsize].view(dtype).reshape(shape)
 
 
+# ---- batched sequence (rpe_seq_*) ---------------------------------------------------------------
+REFIT_BITS = {"kabsch": 1, "gn": 2, "nl_sk_ls": 4}
+
+
+class Sequence:
+    """rpe_seq: frames of a sequence issued by native host threads over several contexts of one GPU (config #5).
+    `run(frames, first_frame, n_frames)` blocks until every result is on the host."""
+
+    def __init__(self, device=0, method="shinji", H=1024, thr3d=0.0, cos_thr2d=0.0, cos_thrN=0.0, confidence=0.99,
+                 refit=("kabsch", "gn"), gn_iters=3, sample_seed=1, contexts=12, threads=2):
+        m = METHODS[method] if isinstance(method, str) else method
+        bits = 0
+        for r in refit:
+            bits |= REFIT_BITS[r]
+        self.params = SeqParams(device, contexts, threads, m, H, thr3d, cos_thr2d, cos_thrN, confidence, bits, gn_iters,
+                                sample_seed)
+        self._h = _vp()
+        _check(lib.rpe_seq_create(C.byref(self.params), C.byref(self._h)))
+        self.method = m
+        self._ring = None
+        self._keep = None
+
+    def set_frames(self, frames):
+        """frames: list of dicts with keys among bv/xc/nc/xw/nw (numpy (n,3) float32 page-locked arrays, or ints =
+        device pointers with 'n' given), optional 'samples' ((H,4) int32 array or device pointer), optional 'mask'."""
+        ring = (SeqFrame * len(frames))()
+        keep = []
+        for i, f in enumerate(frames):
+            on_dev = any(isinstance(f.get(k), int) for k in ("bv", "xc", "nc", "xw", "nw"))
+            n = f.get("n")
+            for k in ("bv", "xc", "nc", "xw", "nw"):
+                a = f.get(k)
+                if a is None:
+                    continue
+                if isinstance(a, int):
+                    setattr(ring[i], k, a)
+                else:
+                    if a.dtype != np.float32 or not a.flags["C_CONTIGUOUS"]:
+                        raise ValueError("sequence frames must be C-contiguous float32 (n, 3) arrays")
+                    n = a.shape[0]
+                    keep.append(a)
+                    setattr(ring[i], k, a.ctypes.data)
+            ring[i].n = int(n)
+            ring[i].on_device = 1 if on_dev else 0
+            sm = f.get("samples")
+            if sm is not None:
+                if isinstance(sm, int):
+                    ring[i].samples = sm
+                else:
+                    keep.append(sm)
+                    ring[i].samples = sm.ctypes.data
+            mk = f.get("mask")
+            if mk is not None:
+                keep.append(mk)
+                ring[i].mask = mk.ctypes.data
+        self._ring, self._keep = ring, keep
+
+    def run(self, first_frame, n_frames, want_results=True):
+        if self._ring is None:
+            raise RpeError("Sequence.set_frames first")
+        r0 = (_Result * n_frames)() if want_results else None
+        r1 = (_Result * n_frames)() if want_results else None
+        rc = lib.rpe_seq_run(self._h, self._ring, len(self._ring), first_frame, n_frames, r0, r1)
+        if rc != 0:
+            raise RpeError(f"rpe error {rc}: {lib.rpe_status_string(rc).decode()}: {lib.rpe_seq_last_error(self._h).decode()}")
+        return r0, r1
+
+    def contexts(self):
+        return [C.c_void_p(lib.rpe_seq_context(self._h, i)) for i in range(lib.rpe_seq_num_contexts(self._h))]
+
+    def close(self):
+        if self._h:
+            lib.rpe_seq_destroy(self._h)
+            self._h = _vp()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 # ---- device context ---------------------------------------------------------------------------
 class Context:
     """One rpe_ctx (one GPU, one stream). Arrays are (n, 3) float32 == the reference's 3 x n column-major."""
@@ -398,6 +512,12 @@ class Context:
         self.n = n
         _check(lib.rpe_sim_2d_3d_nl_device(self._h, seed, _ptr(_f32(q)), _ptr(_f32(t)), n, n2d, or2d, n3d, or3d, nnl, ornl,
                                            min_depth, max_depth, f, 1 if gaussian else 0), self._h)
+
+    def sim_3d_3d_device_to(self, seed, q, t, n, d_xw, d_xc, noise=0.1, outlier_ratio=0.5, min_depth=0.4, max_depth=8.0,
+                            f=585.0, gaussian=True):
+        """The device-side generator into caller-owned device buffers (ints = device pointers)."""
+        _check(lib.rpe_sim_3d_3d_device_to(self._h, seed, _ptr(_f32(q)), _ptr(_f32(t)), n, noise, outlier_ratio, min_depth,
+                                           max_depth, f, 1 if gaussian else 0, C.c_void_p(d_xw), C.c_void_p(d_xc)), self._h)
 
     def download(self, names=("xc", "xw")):
         order = ("bv", "xc", "nc", "xw", "nw")

@@ -128,6 +128,14 @@ struct rpe_ctx {
   cudaEvent_t ev[ST_COUNT + 1] = {};
   cudaEvent_t ev_fast[2] = {};
   bool ev_fast_recorded = false;
+  // every scorer launch of an asynchronous stream of frames gets its own event pair out of a small ring; elapsed times
+  // are folded into (fast_sum_ms, fast_count) when a pair is reused or at the next synchronisation (rpe_scorer_time_stats)
+  static constexpr int kFastRing = 32;
+  cudaEvent_t ev_ring[2 * kFastRing] = {};
+  bool ev_ring_live[kFastRing] = {};
+  int ev_ring_next = 0;
+  double fast_sum_ms = 0.0;
+  long long fast_count = 0;
   bool upload_stamped = false;
   bool ev_ok = false;
   bool ev_recorded[ST_COUNT + 1] = {};
@@ -278,6 +286,29 @@ void stamp(rpe_ctx* ctx, int which) {
   }
 }
 
+// ---- per-launch timing of the tiled scorer over a whole asynchronous region ------------------------------------
+void fast_ring_fold(rpe_ctx* ctx, int k) {
+  if (!ctx->ev_ring_live[k]) return;
+  float ms = 0.f;
+  if (cudaEventElapsedTime(&ms, ctx->ev_ring[2 * k], ctx->ev_ring[2 * k + 1]) == cudaSuccess) {
+    ctx->fast_sum_ms += ms;
+    ctx->fast_count += 1;
+  } else {
+    (void)cudaGetLastError();  // not finished yet (cannot happen 32 frames later on the same stream) or never run
+  }
+  ctx->ev_ring_live[k] = false;
+}
+int fast_ring_claim(rpe_ctx* ctx) {
+  const int k = ctx->ev_ring_next;
+  ctx->ev_ring_next = (k + 1) % rpe_ctx::kFastRing;
+  fast_ring_fold(ctx, k);
+  ctx->ev_ring_live[k] = true;
+  return k;
+}
+void fast_ring_drain(rpe_ctx* ctx) {
+  for (int k = 0; k < rpe_ctx::kFastRing; ++k) fast_ring_fold(ctx, k);
+}
+
 void quat_to_R_rowmajor(const float q[4], float R[9]) {
   const float x = q[0], y = q[1], z = q[2], w = q[3];
   const float tx = 2.f * x, ty = 2.f * y, tz = 2.f * z;
@@ -336,6 +367,7 @@ int finish_pending(rpe_ctx* ctx) {
     note_overflow(ctx, p.slot);
   }
   ctx->pending.clear();
+  if (ctx->timing_fast && ctx->ev_ok) fast_ring_drain(ctx);
   if ((ctx->timing || ctx->timing_fast) && ctx->ev_ok) {
     for (int k = 0; k < ST_COUNT; ++k) ctx->stage_ms[k] = 0.f;
     for (int k = 0; k < ST_TOTAL; ++k)
@@ -444,23 +476,28 @@ int score_range(rpe_ctx* ctx, int method, int slot_begin, int slot_end, Thresh t
     ScorerLane* lane = lane_for(ctx);
     int nseg = 0;
     if (int rcw = grow_worklist(ctx)) return rcw;
+    const int rk = tm ? fast_ring_claim(ctx) : 0;
     if (lane) {
       CK(cudaEventRecord(ctx->ev_lane[0], ctx->stream));  // everything the scorer reads has been enqueued before this
       std::lock_guard<std::mutex> g(lane->mu);
       CK(cudaStreamWaitEvent(lane->stream, ctx->ev_lane[0], 0));
-      if (tm) cudaEventRecord(ctx->ev_fast[0], lane->stream);
+      if (tm) cudaEventRecord(ctx->ev_ring[2 * rk], lane->stream);
       nseg = launch_score_fast(method, f, ctx->d_gen, ctx->d_fast, slot_begin, slot_end, th, ctx->d_votes, ctx->d_stats,
                                ctx->wl, ctx->num_sms, lane->stream);
-      if (tm) cudaEventRecord(ctx->ev_fast[1], lane->stream);
+      if (tm) cudaEventRecord(ctx->ev_ring[2 * rk + 1], lane->stream);
       CK(cudaEventRecord(ctx->ev_lane[1], lane->stream));
       CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_lane[1], 0));
     } else {
-      if (tm) cudaEventRecord(ctx->ev_fast[0], ctx->stream);
+      if (tm) cudaEventRecord(ctx->ev_ring[2 * rk], ctx->stream);
       nseg = launch_score_fast(method, f, ctx->d_gen, ctx->d_fast, slot_begin, slot_end, th, ctx->d_votes, ctx->d_stats,
                                ctx->wl, ctx->num_sms, ctx->stream);
-      if (tm) cudaEventRecord(ctx->ev_fast[1], ctx->stream);
+      if (tm) cudaEventRecord(ctx->ev_ring[2 * rk + 1], ctx->stream);
     }
-    if (tm) ctx->ev_fast_recorded = true;
+    if (tm) {  // rpe_last_stage_ms[7] keeps reporting the LAST launch
+      ctx->ev_fast[0] = ctx->ev_ring[2 * rk];
+      ctx->ev_fast[1] = ctx->ev_ring[2 * rk + 1];
+      ctx->ev_fast_recorded = true;
+    }
     launch_fixup(method, f, ctx->d_gen, th, ctx->d_votes, ctx->d_stats, ctx->wl, nseg, slot_begin, slot_end, ctx->stream);
     launch_score_exact(method, f, ctx->d_gen, slot_begin, slot_end, th, ctx->d_votes, ctx->d_stats, true, ctx->num_sms,
                        ctx->stream);
@@ -822,7 +859,7 @@ static int create_common(int device, void* stream, bool own, rpe_ctx** out) {
     ok = ok && cudaMemsetAsync(ctx->d_kabsch, 0, sizeof(ReplayOut), ctx->stream) == cudaSuccess;
   }
   for (int k = 0; k <= ST_COUNT && ok; ++k) ok = ok && cudaEventCreate(&ctx->ev[k]) == cudaSuccess;
-  for (int k = 0; k < 2 && ok; ++k) ok = ok && cudaEventCreate(&ctx->ev_fast[k]) == cudaSuccess;
+  for (int k = 0; k < 2 * rpe_ctx::kFastRing && ok; ++k) ok = ok && cudaEventCreate(&ctx->ev_ring[k]) == cudaSuccess;
   for (int k = 0; k < kNumStaging && ok; ++k)
     ok = ok && cudaEventCreateWithFlags(&ctx->ev_slot[k], cudaEventDisableTiming) == cudaSuccess;
   for (int k = 0; k < 2 && ok; ++k)
@@ -891,8 +928,8 @@ int rpe_destroy(rpe_ctx* ctx) {
   if (ctx->h_gn_evals) cudaFreeHost(ctx->h_gn_evals);
   for (int k = 0; k <= ST_COUNT; ++k)
     if (ctx->ev[k]) cudaEventDestroy(ctx->ev[k]);
-  for (int k = 0; k < 2; ++k)
-    if (ctx->ev_fast[k]) cudaEventDestroy(ctx->ev_fast[k]);
+  for (int k = 0; k < 2 * rpe_ctx::kFastRing; ++k)
+    if (ctx->ev_ring[k]) cudaEventDestroy(ctx->ev_ring[k]);
   for (int k = 0; k < kNumStaging; ++k)
     if (ctx->ev_slot[k]) cudaEventDestroy(ctx->ev_slot[k]);
   for (int k = 0; k < 2; ++k)
@@ -1482,13 +1519,9 @@ static unsigned int modinv_u(unsigned int a, unsigned int n) {  // a^-1 mod n, g
   return (unsigned int)t;
 }
 
-static int sim_device_common(rpe_ctx* ctx, uint64_t seed, const float q[4], const float t[3], int n, float n2d, float or2d,
-                             float n3d, float or3d, float nnl, float ornl, float min_depth, float max_depth, float f,
-                             int use_gaussian, int mode_3d3d, int kinect = 0) {
-  if (!ctx || !q || !t || n <= 0) return RPE_ERR_ARG;
-  CK(cudaSetDevice(ctx->device));
-  int rc = ensure_corr_capacity(ctx, n, true);
-  if (rc) return rc;
+static SimParams make_sim_params(uint64_t seed, const float q[4], const float t[3], int n, float n2d, float or2d, float n3d,
+                                 float or3d, float nnl, float ornl, float min_depth, float max_depth, float f,
+                                 int use_gaussian, int kinect) {
   SimParams p;
   quat_to_R_rowmajor(q, p.R);
   for (int k = 0; k < 3; ++k) p.t[k] = t[k];
@@ -1514,6 +1547,17 @@ static int sim_device_common(rpe_ctx* ctx, uint64_t seed, const float q[4], cons
   p.gaussian = use_gaussian;
   p.kinect = kinect;
   p.seed = seed;
+  return p;
+}
+
+static int sim_device_common(rpe_ctx* ctx, uint64_t seed, const float q[4], const float t[3], int n, float n2d, float or2d,
+                             float n3d, float or3d, float nnl, float ornl, float min_depth, float max_depth, float f,
+                             int use_gaussian, int mode_3d3d, int kinect = 0) {
+  if (!ctx || !q || !t || n <= 0) return RPE_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  int rc = ensure_corr_capacity(ctx, n, true);
+  if (rc) return rc;
+  const SimParams p = make_sim_params(seed, q, t, n, n2d, or2d, n3d, or3d, nnl, ornl, min_depth, max_depth, f, use_gaussian, kinect);
   ctx->n = n;
   for (int k = 0; k < 5; ++k) ctx->view[k] = nullptr;
   leave_f64_mode(ctx);  // the frame replaces whatever rpe_upload_f64 left behind
@@ -1531,6 +1575,20 @@ static int sim_device_common(rpe_ctx* ctx, uint64_t seed, const float q[4], cons
   ctx->kabsch_valid = false;
   ctx->suff_valid = false;
   ctx->n_slots = 0;
+  return RPE_OK;
+}
+
+// The same generator into device buffers of the caller (a resident sequence of distinct frames: config #5). The context
+// only lends its stream; its own frame is untouched.
+int rpe_sim_3d_3d_device_to(rpe_ctx* ctx, uint64_t seed, const float q_xyzw[4], const float t[3], int n, float noise,
+                            float outlier_ratio, float min_depth, float max_depth, float f, int use_gaussian, float* d_xw,
+                            float* d_xc) {
+  if (!ctx || !q_xyzw || !t || n <= 0 || !d_xw || !d_xc) return RPE_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  const SimParams p = make_sim_params(seed, q_xyzw, t, n, 0.f, 0.f, noise, outlier_ratio, 0.f, 0.f, min_depth, max_depth, f,
+                                      use_gaussian, 0);
+  launch_simulate(p, d_xw, d_xc, nullptr, nullptr, nullptr, 1, ctx->stream);
+  ctx->launches++;
   return RPE_OK;
 }
 
@@ -1641,6 +1699,16 @@ int rpe_enable_stage_timing(rpe_ctx* ctx, int enable) {
   if (!ctx) return RPE_ERR_ARG;
   ctx->timing = enable == 1;
   ctx->timing_fast = enable != 0;
+  return RPE_OK;
+}
+int rpe_scorer_time_stats(rpe_ctx* ctx, double* sum_ms, long long* count, int reset) {
+  if (!ctx) return RPE_ERR_ARG;
+  if (sum_ms) *sum_ms = ctx->fast_sum_ms;
+  if (count) *count = ctx->fast_count;
+  if (reset) {
+    ctx->fast_sum_ms = 0.0;
+    ctx->fast_count = 0;
+  }
   return RPE_OK;
 }
 int rpe_last_stage_ms(rpe_ctx* ctx, float ms[8]) {

@@ -121,7 +121,7 @@ int issue_frame(rpe_seq* s, int worker, SeqContext& sc, const rpe_seq_frame& f, 
 
 void worker_main(rpe_seq* s, int worker) {
   cudaSetDevice(s->p.device);
-  const int T = (int)s->workers.size();
+  const int T = s->p.n_threads;  // NOT workers.size(): the vector is still being filled while the first threads start
   unsigned long long seen = 0;
   // contexts of this worker: worker, worker + T, ...
   std::vector<int> mine;
@@ -218,7 +218,7 @@ int rpe_seq_run(rpe_seq* s, const rpe_seq_frame* ring, int ring_len, long long f
     s->job.n_frames = n_frames;
     s->job.ransac_out = ransac_out;
     s->job.final_out = final_out;
-    s->running = (int)s->workers.size();
+    s->running = s->p.n_threads;
     ++s->generation;
     s->cv_go.notify_all();
     s->cv_done.wait(lk, [&] { return s->running == 0; });
