@@ -181,6 +181,7 @@ _sig("rpe_enable_stage_timing", C.c_int, [_vp, C.c_int])
 _sig("rpe_scorer_time_stats", C.c_int, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_longlong), C.c_int])
 _sig("rpe_debug_set_packed", C.c_int, [C.c_int])
 _sig("rpe_debug_reset", C.c_int, [_vp])
+_sig("rpe_debug_set_raw_tiles", C.c_int, [C.c_int])
 
 # every symbol include/rpe_c_api.h declares (tests check the header against this list and the .so)
 DECLARED_SYMBOLS = [

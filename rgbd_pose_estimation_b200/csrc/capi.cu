@@ -187,11 +187,15 @@ int check_arrays(rpe_ctx* ctx, int method) {
   return RPE_OK;
 }
 
-// The 3-D / 3-D scorer can stream x_w / x_c themselves when they are 16-byte aligned (bulk TMA); see score3d_raw_kernel.
+// The tiled scorers stream the caller's arrays themselves when they are 16-byte aligned (bulk TMA); see
+// score3d_raw_kernel / score_multi_fast_kernel<.., RAW>.
 bool g_raw_tiles = true;  // test hook: false = always pack
-bool raw_tiles_ok(const rpe_ctx* c) {
-  return g_raw_tiles && use_packed() && c->view[A_XW] && c->view[A_XC] && (reinterpret_cast<uintptr_t>(c->view[A_XW]) & 15) == 0 &&
-         (reinterpret_cast<uintptr_t>(c->view[A_XC]) & 15) == 0;
+unsigned raw_aligned_bits(const rpe_ctx* c) {
+  if (!g_raw_tiles || !use_packed()) return 0u;
+  unsigned bits = 0;
+  for (int k = 0; k < 5; ++k)
+    if (c->view[k] && (reinterpret_cast<uintptr_t>(c->view[k]) & 15) == 0) bits |= 1u << k;
+  return bits;
 }
 
 FrameView make_view(const rpe_ctx* c) {
@@ -206,7 +210,7 @@ FrameView make_view(const rpe_ctx* c) {
   f.pk = c->d_pk;
   f.pk_kind = c->pk_kind;
   f.pk_f4_per_pair = c->pk_kind >= 0 ? f4_per_pair(c->pk_kind) : 0;
-  f.raw_ok = raw_tiles_ok(c);
+  f.raw_aligned = raw_aligned_bits(c);
   if (c->pk_kind < 0) {  // nothing packed (raw-array scorer): the pair count still rounds up to whole rescan groups
     const int npairs = (c->n + 1) / 2;
     f.npairs_pad = ((npairs + kSubPairs - 1) / kSubPairs) * kSubPairs;
@@ -261,7 +265,10 @@ int ensure_hyp_capacity(rpe_ctx* ctx, int H, int slots) {
 
 int ensure_packed(rpe_ctx* ctx, int kind) {
   if (ctx->pk_kind == kind) return RPE_OK;
-  if (kind == kind_for_method(RPE_SHINJI) && raw_tiles_ok(ctx)) return RPE_OK;  // scored straight from the arrays
+  {
+    FrameView fv = make_view(ctx);
+    if (frame_raw_ok(fv, kind)) return RPE_OK;  // scored straight from the arrays
+  }
   const int npairs = (ctx->n + 1) / 2;
   const int npad = ((npairs + kSubPairs - 1) / kSubPairs) * kSubPairs;
   const size_t bytes = (size_t)npad * f4_per_pair(kind) * sizeof(float4);

@@ -20,8 +20,17 @@ struct FrameView {
   const float4* pk;    // packed pair records, `pk_f4_per_pair` float4 per pair
   int pk_f4_per_pair;  // 3 (AO) ...
   int pk_kind;         // which modalities are packed (bit0 2-D, bit1 3-D, bit2 normal)
-  bool raw_ok;         // 3-D / 3-D only: the tiled scorer streams xw / xc themselves (16-byte aligned), nothing is packed
+  unsigned raw_aligned;  // bit k: array k (bv, xc, nc, xw, nw) is present, 16-byte aligned and may be streamed by bulk TMA;
+                         // 0 when raw streaming is switched off (test hook): the tiled scorers then need the packed copy
 };
+// can the tiled scorer of modality set `kind` (bit0 2-D, bit1 3-D, bit2 normal) stream the caller's arrays themselves?
+inline bool frame_raw_ok(const FrameView& f, int kind) {
+  unsigned need = 1u << 3;                  // x_w
+  if (kind & 1) need |= 1u << 0;            // b
+  if (kind & 2) need |= 1u << 1;            // x_c
+  if (kind & 4) need |= (1u << 2) | (1u << 4) | (1u << 1);  // n_c, n_w and x_c (isValid gate)
+  return (f.raw_aligned & need) == need;
+}
 
 struct Thresh {
   float thr3d, cos_thr, cos_nl;

@@ -658,18 +658,37 @@ struct BandConsts {   // per hypothesis
   float band_n;           // on g'
 };
 
-template <int KIND, int TILE, int THREADS, bool DIRECT>
+// Where a scoring CTA gets its correspondences from: the packed pair records (pack_kernel) or the caller's own
+// arrays (RAW: bulk TMA of the raw xyz triples of a stage + transpose in shared memory, no packed copy in HBM).
+struct MultiSrc {
+  const float4* pk;   // packed records (RAW == false)
+  const float* a[5];  // RAW: the record's source arrays in record order: x_w, [x_c], [b], [n_w, n_c]
+  const float* xc;    // RAW: camera points for the isValid gate of the normal test (may equal a[1])
+  int n;
+};
+
+template <int KIND, int TILE, int THREADS, bool DIRECT, bool RAW>
 __global__ void __launch_bounds__(THREADS, 1)
-score_multi_fast_kernel(const float4* __restrict__ pk, int npairs_pad, int pairs_per_cta, const HypFast* __restrict__ fast,
+score_multi_fast_kernel(MultiSrc src, int npairs_pad, int pairs_per_cta, const HypFast* __restrict__ fast,
                         const HypGen* __restrict__ gen, int slot_begin, int slot_end, Thresh th,
                         int32_t* __restrict__ votes, FrameStats* __restrict__ st, Worklist wl) {
   typedef KindTraits<KIND> KT;
   constexpr int HPT = 2;
   constexpr int SUB = kSubPairs;
   constexpr int F4 = KT::f4pp;
+  // RAW: arrays staged per stage = the record's arrays, plus x_c when the kind has the normal test but not the 3-D one
+  constexpr int NREC = KT::arrays;
+  constexpr bool XC_EXTRA = KT::kn && !KT::k3;
+  constexpr int NRAW = NREC + (XC_EXTRA ? 1 : 0);
+  constexpr int kStageFloats = TILE * 2 * 3;  // floats of one array in one stage
   extern __shared__ __align__(128) unsigned char smem_raw[];
+  // packed: [2 stages][TILE * F4] float4 | bars.   RAW: [TILE * F4] float4 records | [2 stages][NRAW][kStageFloats] | bars | bounds
   float4(*tile)[TILE * F4] = reinterpret_cast<float4(*)[TILE * F4]>(smem_raw);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + 2 * TILE * F4 * sizeof(float4));
+  float* rawbuf = reinterpret_cast<float*>(smem_raw + (size_t)TILE * F4 * sizeof(float4));
+  uint64_t* bars = RAW ? reinterpret_cast<uint64_t*>(rawbuf + (size_t)2 * NRAW * kStageFloats)
+                       : reinterpret_cast<uint64_t*>(smem_raw + 2 * TILE * F4 * sizeof(float4));
+  unsigned int* mstage = reinterpret_cast<unsigned int*>(bars + 2);  // RAW: [2 stages][3] = max|x_w|, max(|x_w|+|x_c|), max normal
+  const float4* pk = src.pk;
 
   const int tid = threadIdx.x;
   const int p_begin = blockIdx.x * pairs_per_cta;
@@ -699,35 +718,75 @@ score_multi_fast_kernel(const float4* __restrict__ pk, int npairs_pad, int pairs
   //   * otherwise |y| < y0 = 375 u M / c (a point within ~1e-5 M of the camera centre) and beta <= beta(y0) =: c0.
   // band2 = k1 |d'| + k2 n2 + c0 therefore covers beta in both regimes.
   BandConsts bc[HPT];
+  float tnorm[HPT];
 #pragma unroll
-  for (int k = 0; k < HPT; ++k) {
-    const float u = 5.9604644775390625e-08f;
-    const float M = hyp_magnitude(st, nt[k][0], nt[k][1], nt[k][2]);  // NaN for a dead slot: never borderline
-    bc[k].band3 = guard_band_3d(M, th.thr3d);
-    bc[k].k1_2d = u * 1.1f * 71.2f * M;
-    bc[k].k2_2d = u * 1.1f * 26.f * th.cos_thr;
-    const float y0 = 375.f * u * M / th.cos_thr;
-    bc[k].c0_2d = th.cos_thr * u * 1.1f * (64.f * M * y0 + 26.f * y0 * y0);
-    const float nmax = __uint_as_float(st->m_bv_bits) * 1.0001f;
-    bc[k].band_n = u * 1.1f * (29.f * nmax * nmax + 2.f);
+  for (int k = 0; k < HPT; ++k) tnorm[k] = sqrtf(nt[k][0] * nt[k][0] + nt[k][1] * nt[k][1] + nt[k][2] * nt[k][2]);  // NaN for a dead slot
+  // mw >= |x_w|, mwc >= |x_w| + |x_c|, nmax >= max(|n_w|, |n_c|) over the correspondences the bands are applied to:
+  // the frame (packed records, bounds taken by the pack kernel) or the current stage (RAW, taken while transposing)
+  auto set_bands = [&](float mw, float mwc, float nmax) {
+#pragma unroll
+    for (int k = 0; k < HPT; ++k) {
+      const float u = 5.9604644775390625e-08f;
+      const float M3 = (mwc + tnorm[k]) * 1.0001f;  // NaN for a dead slot: never borderline
+      const float M2 = (mw + tnorm[k]) * 1.0001f;
+      bc[k].band3 = guard_band_3d(M3, th.thr3d);
+      bc[k].k1_2d = u * 1.1f * 71.2f * M2;
+      bc[k].k2_2d = u * 1.1f * 26.f * th.cos_thr;
+      const float y0 = 375.f * u * M2 / th.cos_thr;
+      bc[k].c0_2d = th.cos_thr * u * 1.1f * (64.f * M2 * y0 + 26.f * y0 * y0);
+      const float nm = nmax * 1.0001f;
+      bc[k].band_n = u * 1.1f * (29.f * nm * nm + 2.f);
+    }
+  };
+  if (!RAW) {
+    const float mc = __uint_as_float(st->m_corr_bits);  // the pack kernel's frame bound is |x_w| + |x_c| (or |x_w| alone)
+    set_bands(mc, mc, __uint_as_float(st->m_bv_bits));
   }
   const float thr2 = __fmul_rn(th.thr3d, th.thr3d);
   const float2 nlo = make_float2(-thr2, -thr2);
   const float c2 = (float)((double)th.cos_thr * (double)th.cos_thr);
   const float2 cnl2 = make_float2(th.cos_nl, th.cos_nl);
 
+  // RAW: correspondences [c0, c0 + cnt4) of stage t go through TMA (cnt4 a multiple of 4, possibly 0); the frame's last
+  // 0..3 correspondences are read from global memory by the transposing threads
+  const int n = src.n;
+  auto stage_range = [&](int t, int& c0, int& cnt4) {
+    c0 = 2 * (p_begin + t * TILE);
+    const int tp = min(TILE, npairs - t * TILE);
+    int c = min(2 * tp, n - c0);
+    if (c < 0) c = 0;
+    cnt4 = c & ~3;
+  };
+  auto issue_raw = [&](int t, int buf) {
+    int c0, cnt4;
+    stage_range(t, c0, cnt4);
+    const uint32_t bytes = (uint32_t)cnt4 * 12u;
+    mbar_expect_tx(&bars[buf], (uint32_t)NRAW * bytes);  // 0 bytes: the phase completes on this arrival alone
+    if (bytes) {
+#pragma unroll
+      for (int a = 0; a < NREC; ++a)
+        tma_load_1d(rawbuf + (size_t)(buf * NRAW + a) * kStageFloats, src.a[a] + (size_t)c0 * 3, bytes, &bars[buf]);
+      if (XC_EXTRA) tma_load_1d(rawbuf + (size_t)(buf * NRAW + NREC) * kStageFloats, src.xc + (size_t)c0 * 3, bytes, &bars[buf]);
+    }
+  };
   if (tid == 0) {
     mbar_init(&bars[0], 1);
     mbar_init(&bars[1], 1);
     mbar_fence_init();
+    if (RAW)
+      for (int i = 0; i < 6; ++i) mstage[i] = 0u;
   }
   __syncthreads();
   if (tid == 0) {
     for (int t = 0; t < 2 && t < ntiles; ++t) {
-      const int tp = min(TILE, npairs - t * TILE);
-      const uint32_t bytes = (uint32_t)tp * F4 * 16u;
-      mbar_expect_tx(&bars[t], bytes);
-      tma_load_1d(&tile[t][0], pk + (size_t)(p_begin + t * TILE) * F4, bytes, &bars[t]);
+      if (RAW) {
+        issue_raw(t, t);
+      } else {
+        const int tp = min(TILE, npairs - t * TILE);
+        const uint32_t bytes = (uint32_t)tp * F4 * 16u;
+        mbar_expect_tx(&bars[t], bytes);
+        tma_load_1d(&tile[t][0], pk + (size_t)(p_begin + t * TILE) * F4, bytes, &bars[t]);
+      }
     }
   }
 
@@ -856,7 +915,117 @@ score_multi_fast_kernel(const float4* __restrict__ pk, int npairs_pad, int pairs
     const int buf = t & 1;
     mbar_wait(&bars[buf], (uint32_t)((t >> 1) & 1));
     const int tp = min(TILE, npairs - t * TILE);
-    const float* sp = reinterpret_cast<const float*>(&tile[buf][0]);
+    if (RAW) {
+      // ---- transpose the stage into pair records: thread <-> 4 correspondences = 2 records; stage magnitude bounds
+      int c0, cnt4;
+      stage_range(t, c0, cnt4);
+      float* recs = reinterpret_cast<float*>(&tile[0][0]);
+      float m_w = 0.f, m_wc = 0.f, m_n = 0.f;
+      for (int qd = tid; qd < (tp + 1) / 2; qd += THREADS) {
+        const bool in_smem = 4 * qd + 4 <= cnt4;
+        float vxc[12];  // camera points of the 4 correspondences (validity gate / 3-D bound), when the kind needs them
+        float wn[4] = {0.f, 0.f, 0.f, 0.f};  // |x_w|
+#pragma unroll
+        for (int a = 0; a < NRAW; ++a) {
+          const bool is_extra = a >= NREC;
+          const float* g = is_extra ? src.xc : src.a[a];
+          float v[12];
+          if (in_smem) {
+            const float4* p4 = reinterpret_cast<const float4*>(rawbuf + (size_t)(buf * NRAW + a) * kStageFloats + 12 * qd);
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+              const float4 x = p4[i];
+              v[4 * i] = x.x; v[4 * i + 1] = x.y; v[4 * i + 2] = x.z; v[4 * i + 3] = x.w;
+            }
+          } else {  // frame tail (or padding): element-wise from global memory, NaN beyond the last correspondence
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int ci = c0 + 4 * qd + j;
+#pragma unroll
+              for (int r = 0; r < 3; ++r) v[3 * j + r] = ci < n ? g[(size_t)ci * 3 + r] : CUDART_NAN_F;
+            }
+          }
+          // what this array is: record order x_w, [x_c], [b], [n_w, n_c] (+ x_c staged on the side)
+          const bool is_xw = a == 0;
+          const bool is_xc = (KT::k3 && a == 1) || is_extra;
+          const bool is_nw = KT::kn && a == NREC - 2, is_nc = KT::kn && a == NREC - 1;
+          if (is_xc) {
+#pragma unroll
+            for (int i = 0; i < 12; ++i) vxc[i] = v[i];
+          }
+          if (is_xw || (is_xc && KT::k3) || is_nw || is_nc) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float m = sqrtf(v[3 * j] * v[3 * j] + v[3 * j + 1] * v[3 * j + 1] + v[3 * j + 2] * v[3 * j + 2]);
+              const bool fin = m == m && m < CUDART_INF_F;
+              if (is_xw) {
+                wn[j] = fin ? m : CUDART_NAN_F;
+                if (fin) m_w = fmaxf(m_w, m);
+                if (!KT::k3 && fin) m_wc = fmaxf(m_wc, m);
+              } else if (is_xc) {  // k3: bound of |x_w| + |x_c| like the pack kernel (a non-finite x_c contributes nothing)
+                const float wv = wn[j];
+                if (wv == wv) m_wc = fmaxf(m_wc, fin ? wv + m : wv);
+              } else if (fin) {
+                m_n = fmaxf(m_n, m);
+              }
+            }
+          }
+          if (is_nc) {
+            // the normal test sits inside `if (adapter.isValid(c))` (AbsoluteOrientationNormal.hpp:246,323,398): an
+            // all-NaN camera point must never cast a normal vote -> poison its camera normal (x_c precedes n_c in NRAW order
+            // only for k3; for the side-staged x_c the poison is applied below, after the loop)
+            if (KT::k3) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                if (!(vxc[3 * j] == vxc[3 * j] || vxc[3 * j + 1] == vxc[3 * j + 1] || vxc[3 * j + 2] == vxc[3 * j + 2]))
+                  v[3 * j] = v[3 * j + 1] = v[3 * j + 2] = CUDART_NAN_F;
+            }
+          }
+          if (!is_extra) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {  // record 2 qd + h = correspondences 4 qd + 2h, 4 qd + 2h + 1
+              const int pr = 2 * qd + h;
+              if (pr < tp) {
+                const float* e = v + 6 * h;
+                float2* dst = reinterpret_cast<float2*>(recs + (size_t)pr * (F4 * 4) + 6 * a);
+                dst[0] = make_float2(e[0], e[3]);
+                dst[1] = make_float2(e[1], e[4]);
+                dst[2] = make_float2(e[2], e[5]);
+              }
+            }
+          }
+        }
+        if (XC_EXTRA) {  // x_c arrived after n_c: poison the records just written
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (!(vxc[3 * j] == vxc[3 * j] || vxc[3 * j + 1] == vxc[3 * j + 1] || vxc[3 * j + 2] == vxc[3 * j + 2])) {
+              const int pr = 2 * qd + (j >> 1);
+              if (pr < tp) {
+                float* e = recs + (size_t)pr * (F4 * 4) + 6 * (NREC - 1) + (j & 1);
+                e[0] = e[2] = e[4] = CUDART_NAN_F;
+              }
+            }
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        m_w = fmaxf(m_w, __shfl_xor_sync(0xffffffffu, m_w, o));
+        m_wc = fmaxf(m_wc, __shfl_xor_sync(0xffffffffu, m_wc, o));
+        m_n = fmaxf(m_n, __shfl_xor_sync(0xffffffffu, m_n, o));
+      }
+      if ((tid & 31) == 0) {
+        if (m_w > 0.f) atomicMax(&mstage[3 * buf + 0], __float_as_uint(m_w));
+        if (m_wc > 0.f) atomicMax(&mstage[3 * buf + 1], __float_as_uint(m_wc));
+        if (m_n > 0.f) atomicMax(&mstage[3 * buf + 2], __float_as_uint(m_n));
+      }
+      __syncthreads();  // records + bounds complete; rawbuf[buf] is free
+      if (tid == 0) {
+        if (t + 2 < ntiles) issue_raw(t + 2, buf);
+        mstage[3 * (buf ^ 1) + 0] = mstage[3 * (buf ^ 1) + 1] = mstage[3 * (buf ^ 1) + 2] = 0u;  // next stage's slots
+      }
+      set_bands(__uint_as_float(mstage[3 * buf + 0]), __uint_as_float(mstage[3 * buf + 1]), __uint_as_float(mstage[3 * buf + 2]));
+    }
+    const float* sp = reinterpret_cast<const float*>(&tile[RAW ? 0 : buf][0]);
     for (int sub = 0; sub < tp; sub += SUB) {
       bool flag = false;
 #pragma unroll 2
@@ -890,8 +1059,8 @@ score_multi_fast_kernel(const float4* __restrict__ pk, int npairs_pad, int pairs
         }
       }
     }
-    __syncthreads();
-    if (tid == 0 && t + 2 < ntiles) {
+    __syncthreads();  // RAW: everybody is done with the records (and has read the bounds) before the next transpose
+    if (!RAW && tid == 0 && t + 2 < ntiles) {
       const int tn = t + 2;
       const int tpn = min(TILE, npairs - tn * TILE);
       const uint32_t bytes = (uint32_t)tpn * F4 * 16u;
@@ -908,11 +1077,15 @@ score_multi_fast_kernel(const float4* __restrict__ pk, int npairs_pad, int pairs
 template <int KIND, int THREADS>
 static int launch_multi_t(const FrameView& f, const HypGen* gen, const HypFast* fast, int slot_begin, int slot_end, Thresh th,
                            int32_t* votes, FrameStats* st, Worklist wl, int num_sms, cudaStream_t s) {
+  typedef KindTraits<KIND> KT;
   constexpr int HPT = 2;
   constexpr int CTAS_PER_SM = 512 / THREADS;  // 16 warps per SM either way
-  constexpr int F4 = KindTraits<KIND>::f4pp;
+  constexpr int F4 = KT::f4pp;
   // two stages of TILE pairs; sized so that CTAS_PER_SM CTAs fit on an SM for every kind (<= 98 KB per 256 threads)
   constexpr int TILE = (F4 <= 3 ? 1024 : (F4 <= 6 ? 512 : 256)) * (THREADS == 512 && F4 > 3 ? 2 : 1);
+  // RAW: records (single) + two stages of raw triples of every staged array: (16 F4 + 48 NRAW) bytes per pair
+  constexpr int NRAW = KT::arrays + ((KT::kn && !KT::k3) ? 1 : 0);
+  constexpr int RTILE = (F4 <= 3 ? 1024 : 512) / CTAS_PER_SM;
   const int nslots = slot_end - slot_begin;
   const int gy = (nslots + THREADS * HPT - 1) / (THREADS * HPT);
   const int groups = f.npairs_pad / kSubPairs;
@@ -922,24 +1095,55 @@ static int launch_multi_t(const FrameView& f, const HypGen* gen, const HypFast* 
   const int groups_per_cta = (groups + gx - 1) / gx;
   const int pairs_per_cta = groups_per_cta * kSubPairs;
   gx = (f.npairs_pad + pairs_per_cta - 1) / pairs_per_cta;
-  const size_t smem = 2 * (size_t)TILE * F4 * sizeof(float4) + 2 * sizeof(uint64_t);
   // kinds with the 2-D test queue borderline evaluations on the spot (pixel-level thresholds put a percent of a good
   // hypothesis' evaluations inside the band); without it the group flag + rare re-walk is cheaper
-  static const bool direct = getenv("RPE_MULTI_DIRECT") ? getenv("RPE_MULTI_DIRECT")[0] != '0' : KindTraits<KIND>::k2;
-  static std::atomic<bool> attr_set[64];  // the attribute is per device; setting it twice from two host threads is harmless
+  static const bool direct = getenv("RPE_MULTI_DIRECT") ? getenv("RPE_MULTI_DIRECT")[0] != '0' : KT::k2;
   int dev = 0;
   cudaGetDevice(&dev);
+  MultiSrc src;
+  src.pk = f.pk;
+  src.n = f.n;
+  src.xc = f.xc;
+  {
+    int c = 0;
+    src.a[c++] = f.xw;
+    if (KT::k3) src.a[c++] = f.xc;
+    if (KT::k2) src.a[c++] = f.bv;
+    if (KT::kn) {
+      src.a[c++] = f.nw;
+      src.a[c++] = f.nc;
+    }
+    for (; c < 5; ++c) src.a[c] = nullptr;
+  }
+  if (frame_raw_ok(f, KIND)) {  // stream the caller's arrays: no packed copy
+    const size_t rsmem = (size_t)RTILE * F4 * sizeof(float4) + 2 * (size_t)NRAW * RTILE * 6 * sizeof(float) + 2 * sizeof(uint64_t) + 32;
+    static std::atomic<bool> rattr_set[64];
+    if (dev >= 0 && dev < 64 && !rattr_set[dev].load(std::memory_order_acquire)) {
+      cudaFuncSetAttribute(score_multi_fast_kernel<KIND, RTILE, THREADS, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem);
+      cudaFuncSetAttribute(score_multi_fast_kernel<KIND, RTILE, THREADS, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem);
+      rattr_set[dev].store(true, std::memory_order_release);
+    }
+    if (direct)
+      score_multi_fast_kernel<KIND, RTILE, THREADS, true, true><<<dim3(gx, gy), THREADS, rsmem, s>>>(
+          src, f.npairs_pad, pairs_per_cta, fast, gen, slot_begin, slot_end, th, votes, st, wl);
+    else
+      score_multi_fast_kernel<KIND, RTILE, THREADS, false, true><<<dim3(gx, gy), THREADS, rsmem, s>>>(
+          src, f.npairs_pad, pairs_per_cta, fast, gen, slot_begin, slot_end, th, votes, st, wl);
+    return gx * gy;
+  }
+  const size_t smem = 2 * (size_t)TILE * F4 * sizeof(float4) + 2 * sizeof(uint64_t) + 32;
+  static std::atomic<bool> attr_set[64];  // the attribute is per device; setting it twice from two host threads is harmless
   if (dev >= 0 && dev < 64 && !attr_set[dev].load(std::memory_order_acquire)) {
-    cudaFuncSetAttribute(score_multi_fast_kernel<KIND, TILE, THREADS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaFuncSetAttribute(score_multi_fast_kernel<KIND, TILE, THREADS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(score_multi_fast_kernel<KIND, TILE, THREADS, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(score_multi_fast_kernel<KIND, TILE, THREADS, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     attr_set[dev].store(true, std::memory_order_release);
   }
   if (direct)
-    score_multi_fast_kernel<KIND, TILE, THREADS, true><<<dim3(gx, gy), THREADS, smem, s>>>(
-        f.pk, f.npairs_pad, pairs_per_cta, fast, gen, slot_begin, slot_end, th, votes, st, wl);
+    score_multi_fast_kernel<KIND, TILE, THREADS, true, false><<<dim3(gx, gy), THREADS, smem, s>>>(
+        src, f.npairs_pad, pairs_per_cta, fast, gen, slot_begin, slot_end, th, votes, st, wl);
   else
-    score_multi_fast_kernel<KIND, TILE, THREADS, false><<<dim3(gx, gy), THREADS, smem, s>>>(
-        f.pk, f.npairs_pad, pairs_per_cta, fast, gen, slot_begin, slot_end, th, votes, st, wl);
+    score_multi_fast_kernel<KIND, TILE, THREADS, false, false><<<dim3(gx, gy), THREADS, smem, s>>>(
+        src, f.npairs_pad, pairs_per_cta, fast, gen, slot_begin, slot_end, th, votes, st, wl);
   return gx * gy;
 }
 
@@ -986,7 +1190,7 @@ static int launch_variant(const FrameView& f, const HypGen* gen, const HypFast* 
   if (MINB == 1 && g_exclusive_sm && smem < (size_t)116 * 1024) smem = (size_t)116 * 1024;
   int dev = 0;
   cudaGetDevice(&dev);
-  if (PACKED && f.raw_ok) {  // stream the caller's arrays: no packed copy
+  if (PACKED && frame_raw_ok(f, 2)) {  // stream the caller's arrays: no packed copy
     constexpr int RT = (TILE > 1024 / MINB ? 1024 / MINB : TILE);  // 144 bytes of shared memory per pair and CTA
     auto rk = score3d_raw_kernel<HPT, RT, THREADS, MINB, SUB>;
     size_t rsmem = (size_t)RT * 3 * sizeof(float4) + 4 * (size_t)RT * 6 * sizeof(float) + 2 * sizeof(uint64_t) + 16;
@@ -1016,7 +1220,9 @@ int launch_score_fast(int method, const FrameView& f, const HypGen* gen, const H
                       cudaStream_t s) {
   if (slot_end - slot_begin <= 0 || f.n <= 0) return 0;
   if (method != RPE_SHINJI) {
-    switch (f.pk_kind) {
+    const int kind = (method_uses_2d(method) ? 1 : 0) | (method_uses_3d(method) ? 2 : 0) | (method_uses_nl(method) ? 4 : 0);
+    if (!frame_raw_ok(f, kind) && f.pk_kind != kind) return 0;  // nothing packed for this family (caller bug)
+    switch (kind) {
       case 1: return launch_multi<1>(f, gen, fast, slot_begin, slot_end, th, votes, st, wl, num_sms, s);
       case 3: return launch_multi<3>(f, gen, fast, slot_begin, slot_end, th, votes, st, wl, num_sms, s);
       case 5: return launch_multi<5>(f, gen, fast, slot_begin, slot_end, th, votes, st, wl, num_sms, s);

@@ -54,15 +54,26 @@ def test_generation_bit_exact(rpe, orc, gpu_ctx, method, n, H, seed):
     assert same.all(), f"{(~same.all(axis=1)).sum()} of {sel.sum()} hypotheses differ in some bit"
 
 
+@pytest.mark.parametrize("raw", [1, 0])  # 1: the scorer streams the caller's arrays (bulk TMA + transpose); 0: packed copy
 @pytest.mark.parametrize("method", [1, 2, 3, 4, 5, 6])
 @pytest.mark.parametrize("n,H,seed,kw", [
     (800, 512, 3, {}),
     (5001, 300, 5, dict(n2d=2.0, or2d=0.5, n3d=0.1, or3d=0.5, nnl=float(np.deg2rad(4.0)), ornl=0.5)),
     (64, 100, 7, dict(or2d=0.0, or3d=0.0, ornl=0.0)),
+    (40003, 200, 9, dict(or2d=0.3, or3d=0.3, ornl=0.3, nan_rows=True)),  # several stages per CTA, ragged tail, invalid depth
 ])
-def test_ransac_identical_to_oracle(rpe, orc, gpu_ctx, method, n, H, seed, kw):
+def test_ransac_identical_to_oracle(rpe, orc, gpu_ctx, method, n, H, seed, kw, raw):
     orc.set_math_mode(orc.DET)
+    kw = dict(kw)
+    nan_rows = kw.pop("nan_rows", False)
     q, t, arrs, _ = _data(rpe, seed + 10 * method, n, **kw)
+    if nan_rows:  # all-NaN camera points: no 3-D and no normal vote, the 2-D vote still counts (Appendix A of SURVEY.md)
+        bad = np.random.default_rng(seed).choice(n, n // 20, replace=False)
+        bad = bad[bad > 64]  # keep the first rows valid so that most samples stay usable
+        arrs["xc"] = arrs["xc"].copy()
+        arrs["xc"][bad] = np.nan
+        arrs["xc"][n - 1] = np.nan
+    rpe.lib.rpe_debug_set_raw_tiles(raw)
     S = rpe.sample_table(seed, n, 4, H)
     th = _thr()
     ref = orc.ransac(method, S, confidence=0.99, full=True, **th, **arrs)
