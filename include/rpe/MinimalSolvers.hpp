@@ -3,43 +3,25 @@
 // The reference file is never called and half-finished: `ms` stops after step 4 of a 2-point+normal solver and
 // mutates const references (:22-46); the eigenvector half of `ev` does not compile (:92). Built here is their
 // intent: `ev` = closed-form eigenvalues of a symmetric 3x3 (:49-83), `ms` = the working point+normal minimal
-// solver (nl_2p, AbsoluteOrientationNormal.hpp:77-142) applied to the first correspondence pair.
+// solver (nl_2p, AbsoluteOrientationNormal.hpp:77-142) applied to the first correspondence pair. Both are host +
+// device templates (rpe/solvers_min.h); batches run on the GPU one problem per thread through rpe_min_ev / rpe_min_ms.
 #ifndef RPE_MINIMAL_SOLVERS_HPP_
 #define RPE_MINIMAL_SOLVERS_HPP_
 
 #include <cmath>
 
 #include "so3.hpp"
-#include "solvers_p3p.h"
+#include "solvers_min.h"
 
+// eigenvalues, eig(0) >= eig(1) >= eig(2); the arithmetic lives in solvers_min.h and is the one the GPU runs
+// (rpe_min_ev), so host and device agree bit for bit
 template <class T>
 void ev(const rpe::Mat3<T>& M_, rpe::Vec3<T>* pE_) {
-  const T p1 = M_(0, 1) * M_(0, 1) + M_(0, 2) * M_(0, 2) + M_(1, 2) * M_(1, 2);
-  if (std::fabs(p1) < 0.00001) {  // diagonal
-    (*pE_)(0) = M_(0, 0);
-    (*pE_)(1) = M_(1, 1);
-    (*pE_)(2) = M_(2, 2);
-    return;
-  }
-  T q = M_(0, 0) + M_(1, 1) + M_(2, 2);
-  q /= 3;
-  const T t1 = M_(0, 0) - q, t2 = M_(1, 1) - q, t3 = M_(2, 2) - q;
-  const T p2 = t1 * t1 + t2 * t2 + t3 * t3 + 2 * p1;
-  const T p = std::sqrt(p2 / 6);
-  rpe::Mat3<T> B;
+  T m[9], e[3];
   for (int i = 0; i < 3; ++i)
-    for (int j = 0; j < 3; ++j) B(i, j) = (1 / p) * (M_(i, j) - q * (i == j ? T(1) : T(0)));
-  const T r = B.determinant() / 2;
-  T phi;
-  if (r <= -1)
-    phi = T(3.141592653589793238) / 3;
-  else if (r >= 1)
-    phi = 0;
-  else
-    phi = std::acos(r) / 3;
-  (*pE_)(0) = q + 2 * p * std::cos(phi);
-  (*pE_)(2) = q + 2 * p * std::cos(phi + (2 * T(3.141592653589793238) / 3));
-  (*pE_)(1) = 3 * q - (*pE_)(0) - (*pE_)(2);
+    for (int j = 0; j < 3; ++j) m[3 * i + j] = M_(i, j);
+  rpe::sym3_eigenvalues<T>(m, e);
+  for (int i = 0; i < 3; ++i) (*pE_)(i) = e[i];
 }
 
 // Two correspondences with positions (A, B) and normals (N, M) in both frames -> R_cw, t_w (uses A, N, B).

@@ -25,6 +25,8 @@
  *   rpe_prosac_table      ProsacSampler::sample + getSortedIdx           Utility.hpp:161-250, PnPPoseAdapter.hpp:239-255
  *   rpe_sim_*             Simulator.hpp generators                       Simulator.hpp:158-367
  *   rpe_ao / rpe_ao_ransac  extern "C" ao() / ao_ransac()                Library.cpp:17-75
+ *   rpe_min_ev / rpe_min_ms ev() / ms()                                    MinimalSolvers.hpp:49-104, 10-46
+ *   rpe_seq_*             the per-frame call sequence of SimpleMain.cpp:30-49 for a sequence of frames
  *
  * Error behaviour: the reference returns void, asserts in debug builds and std::abort()s inside
  * SOPHUS_ENSURE (sophus/common.hpp:115-132). Every function here returns an int status instead
@@ -325,6 +327,17 @@ int rpe_sim_kinect_2d_3d_nl_device(rpe_ctx* ctx, uint64_t seed, const float q_xy
                                    float or2d, float or3d, float nnl, float ornl, float min_depth, float max_depth, float f);
 /* Copy the context's current correspondence arrays back to host memory (NULL = skip). */
 int rpe_download(rpe_ctx* ctx, float* bv, float* xc, float* nc, float* xw, float* nw);
+
+/* ---- MinimalSolvers.hpp (ev: :49-83, ms: :10-46) ------------------------------------------------
+ * Batches on the device, one problem per thread; the *_host forms run the same templates (rpe/solvers_min.h) on the
+ * CPU and return identical bits. M9: count x 9 row-major symmetric 3x3 -> E3: count x 3 eigenvalues, descending.
+ * in24: count x (Aw Bw Nw Mw Ac Bc Nc Mc), the argument order of ms() -> q4 (x,y,z,w of R_cw), t3 (t_w).
+ * Pointers may be host or device memory. Blocking. */
+int rpe_min_ev(rpe_ctx* ctx, const float* M9, int count, float* E3);
+int rpe_min_ms(rpe_ctx* ctx, const float* in24, int count, float* q4, float* t3);
+int rpe_min_ev_host(const float* M9, int count, float* E3);
+int rpe_min_ev_host_f64(const double* M9, int count, double* E3);
+int rpe_min_ms_host(const float* in24, int count, float* q4, float* t3);
 
 /* ---- the reference's own C shim (Library.cpp:17-75), same argument meaning ------------------ */
 /* x_w, x_c: 3 x n column-major; R_cw out row-major 9; t out 3. ao = shinji_ls2; ao_ransac =

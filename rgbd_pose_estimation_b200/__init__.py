@@ -18,6 +18,8 @@ from .capi import (  # noqa: F401
     Sampler,
     prosac_table,
     update_num_iters,
+    min_ev_host,
+    min_ms_host,
     sim_pose,
     sim_3d_3d,
     sim_2d_3d,
@@ -31,6 +33,6 @@ from .capi import (  # noqa: F401
 
 __all__ = [
     "Context", "Sequence", "RpeError", "lib", "lib_path", "METHODS", "REFITS", "sample_table", "prosac_table", "Sampler",
-    "update_num_iters", "sim_pose", "sim_3d_3d", "sim_2d_3d", "sim_2d_3d_nl", "sim_kinect_2d_3d_nl", "method_slots",
+    "update_num_iters", "min_ev_host", "min_ms_host", "sim_pose", "sim_3d_3d", "sim_2d_3d", "sim_2d_3d_nl", "sim_kinect_2d_3d_nl", "method_slots",
     "method_mask_cols", "method_sample_size", "pinned_empty",
 ]

@@ -179,6 +179,11 @@ _sig("rpe_measure_ffma_tflops", C.c_int, [_vp, C.c_int, C.POINTER(C.c_double), C
 _sig("rpe_last_stage_ms", C.c_int, [_vp, _vp])
 _sig("rpe_enable_stage_timing", C.c_int, [_vp, C.c_int])
 _sig("rpe_scorer_time_stats", C.c_int, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_longlong), C.c_int])
+_sig("rpe_min_ev", C.c_int, [_vp, _vp, C.c_int, _vp])
+_sig("rpe_min_ms", C.c_int, [_vp, _vp, C.c_int, _vp, _vp])
+_sig("rpe_min_ev_host", C.c_int, [_vp, C.c_int, _vp])
+_sig("rpe_min_ev_host_f64", C.c_int, [_vp, C.c_int, _vp])
+_sig("rpe_min_ms_host", C.c_int, [_vp, C.c_int, _vp, _vp])
 _sig("rpe_debug_set_packed", C.c_int, [C.c_int])
 _sig("rpe_debug_reset", C.c_int, [_vp])
 _sig("rpe_debug_set_raw_tiles", C.c_int, [C.c_int])
@@ -191,7 +196,8 @@ DECLARED_SYMBOLS = [
     "rpe_set_pose", "rpe_set_mask", "rpe_generate", "rpe_get_hypotheses", "rpe_set_hypotheses", "rpe_score",
     "rpe_get_votes", "rpe_set_votes", "rpe_votes_device_ptr", "rpe_peer_export", "rpe_peer_import", "rpe_peer_import_local", "rpe_exchange_votes", "rpe_peer_status", "rpe_peer_set_timeout_ms", "rpe_ransac_sharded", "rpe_ransac_sharded_async", "rpe_finish", "rpe_update_num_iters", "rpe_sample_table",
     "rpe_prosac_table", "rpe_sampler_create", "rpe_sampler_rows", "rpe_sampler_destroy", "rpe_sim_pose", "rpe_sim_3d_3d", "rpe_sim_2d_3d", "rpe_sim_2d_3d_nl", "rpe_sim_kinect_2d_3d_nl", "rpe_sim_kinect_2d_3d_nl_device", "rpe_sim_3d_3d_device",
-    "rpe_sim_2d_3d_nl_device", "rpe_sim_3d_3d_device_to", "rpe_sampler_reseed", "rpe_seq_create", "rpe_seq_run",
+    "rpe_sim_2d_3d_nl_device", "rpe_min_ev", "rpe_min_ms", "rpe_min_ev_host", "rpe_min_ev_host_f64", "rpe_min_ms_host",
+    "rpe_sim_3d_3d_device_to", "rpe_sampler_reseed", "rpe_seq_create", "rpe_seq_run",
     "rpe_seq_context", "rpe_seq_num_contexts", "rpe_seq_last_error", "rpe_seq_destroy", "rpe_download", "rpe_ao", "rpe_ao_ransac",
     "rpe_measure_ffma_tflops", "rpe_last_stage_ms", "rpe_enable_stage_timing", "rpe_scorer_time_stats",
 ]
@@ -262,6 +268,24 @@ class Sampler:
             self.close()
         except Exception:
             pass
+
+
+def min_ev_host(M, dtype=np.float32):
+    """ev() of MinimalSolvers.hpp on the host: (count, 3, 3) symmetric matrices -> (count, 3) eigenvalues, descending."""
+    M = np.ascontiguousarray(M, dtype=dtype).reshape(-1, 9)
+    E = np.empty((M.shape[0], 3), dtype)
+    fn = lib.rpe_min_ev_host if dtype == np.float32 else lib.rpe_min_ev_host_f64
+    _check(fn(_ptr(M), M.shape[0], _ptr(E)))
+    return E
+
+
+def min_ms_host(in24):
+    """ms() of MinimalSolvers.hpp on the host: (count, 24) = Aw Bw Nw Mw Ac Bc Nc Mc -> q (count, 4), t (count, 3)."""
+    a = np.ascontiguousarray(in24, dtype=np.float32).reshape(-1, 24)
+    q = np.empty((a.shape[0], 4), np.float32)
+    t = np.empty((a.shape[0], 3), np.float32)
+    _check(lib.rpe_min_ms_host(_ptr(a), a.shape[0], _ptr(q), _ptr(t)))
+    return q, t
 
 
 def update_num_iters(p: float, ep: float, model_points: int, max_iters: int) -> int:
@@ -519,6 +543,21 @@ class Context:
         """The device-side generator into caller-owned device buffers (ints = device pointers)."""
         _check(lib.rpe_sim_3d_3d_device_to(self._h, seed, _ptr(_f32(q)), _ptr(_f32(t)), n, noise, outlier_ratio, min_depth,
                                            max_depth, f, 1 if gaussian else 0, C.c_void_p(d_xw), C.c_void_p(d_xc)), self._h)
+
+    def min_ev(self, M):
+        """ev() batches on the GPU, one matrix per thread (rpe_min_ev)."""
+        M = np.ascontiguousarray(M, dtype=np.float32).reshape(-1, 9)
+        E = np.empty((M.shape[0], 3), np.float32)
+        _check(lib.rpe_min_ev(self._h, _ptr(M), M.shape[0], _ptr(E)), self._h)
+        return E
+
+    def min_ms(self, in24):
+        """ms() batches on the GPU, one two-correspondence problem per thread (rpe_min_ms)."""
+        a = np.ascontiguousarray(in24, dtype=np.float32).reshape(-1, 24)
+        q = np.empty((a.shape[0], 4), np.float32)
+        t = np.empty((a.shape[0], 3), np.float32)
+        _check(lib.rpe_min_ms(self._h, _ptr(a), a.shape[0], _ptr(q), _ptr(t)), self._h)
+        return q, t
 
     def download(self, names=("xc", "xw")):
         order = ("bv", "xc", "nc", "xw", "nw")

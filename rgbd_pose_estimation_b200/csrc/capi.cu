@@ -1627,6 +1627,36 @@ int rpe_download(rpe_ctx* ctx, float* bv, float* xc, float* nc, float* xw, float
   return RPE_OK;
 }
 
+// ---- MinimalSolvers.hpp on the device: batches, one problem per thread ------------------------------------------
+static int minsolv_common(rpe_ctx* ctx, const float* in, int in_stride, int count, float* out_a, int a_stride, float* out_b,
+                          int b_stride, bool is_ms) {
+  if (!ctx || !in || count <= 0 || !out_a || (is_ms && !out_b)) return RPE_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  float *d_in = nullptr, *d_a = nullptr, *d_b = nullptr;
+  CK(cudaMallocAsync(&d_in, (size_t)count * in_stride * sizeof(float), ctx->stream));
+  CK(cudaMallocAsync(&d_a, (size_t)count * a_stride * sizeof(float), ctx->stream));
+  if (is_ms) CK(cudaMallocAsync(&d_b, (size_t)count * b_stride * sizeof(float), ctx->stream));
+  CK(cudaMemcpyAsync(d_in, in, (size_t)count * in_stride * sizeof(float), cudaMemcpyDefault, ctx->stream));
+  if (is_ms)
+    launch_minsolv_ms(d_in, count, d_a, d_b, ctx->stream);
+  else
+    launch_minsolv_ev(d_in, count, d_a, ctx->stream);
+  ctx->launches++;
+  CK(cudaMemcpyAsync(out_a, d_a, (size_t)count * a_stride * sizeof(float), cudaMemcpyDefault, ctx->stream));
+  if (is_ms) CK(cudaMemcpyAsync(out_b, d_b, (size_t)count * b_stride * sizeof(float), cudaMemcpyDefault, ctx->stream));
+  cudaFreeAsync(d_in, ctx->stream);
+  cudaFreeAsync(d_a, ctx->stream);
+  if (d_b) cudaFreeAsync(d_b, ctx->stream);
+  CK(cudaStreamSynchronize(ctx->stream));
+  return RPE_OK;
+}
+int rpe_min_ev(rpe_ctx* ctx, const float* M9, int count, float* E3) {
+  return minsolv_common(ctx, M9, 9, count, E3, 3, nullptr, 0, false);
+}
+int rpe_min_ms(rpe_ctx* ctx, const float* in24, int count, float* q4, float* t3) {
+  return minsolv_common(ctx, in24, 24, count, q4, 4, t3, 3, true);
+}
+
 // ---- Library.cpp shim -----------------------------------------------------------------------------
 // One context, created on first use and kept for the life of the process (a context owns a 32 MiB worklist, a ring of
 // pinned staging slots and ~270 events: too much to build and tear down per call). Calls are serialised.

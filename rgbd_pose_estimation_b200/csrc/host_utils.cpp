@@ -8,6 +8,7 @@
 #include "../../include/rpe/Utility.hpp"
 #include "../../include/rpe/ransac_rule.h"
 #include "../../include/rpe/sim_core.hpp"
+#include "../../include/rpe/solvers_min.h"
 #include "../../include/rpe_c_api.h"
 
 struct rpe_sampler {
@@ -22,6 +23,23 @@ extern "C" {
 
 int rpe_update_num_iters(float p, float ep, int model_points, int max_iters) {
   return rpe::update_num_iters(p, ep, model_points, max_iters);
+}
+
+// MinimalSolvers.hpp on the host: the same templates the device kernels instantiate (identical bits)
+int rpe_min_ev_host(const float* M9, int count, float* E3) {
+  if (!M9 || !E3 || count < 0) return RPE_ERR_ARG;
+  for (int i = 0; i < count; ++i) rpe::sym3_eigenvalues<float>(M9 + 9 * (size_t)i, E3 + 3 * (size_t)i);
+  return RPE_OK;
+}
+int rpe_min_ev_host_f64(const double* M9, int count, double* E3) {
+  if (!M9 || !E3 || count < 0) return RPE_ERR_ARG;
+  for (int i = 0; i < count; ++i) rpe::sym3_eigenvalues<double>(M9 + 9 * (size_t)i, E3 + 3 * (size_t)i);
+  return RPE_OK;
+}
+int rpe_min_ms_host(const float* in24, int count, float* q4, float* t3) {
+  if (!in24 || !q4 || !t3 || count < 0) return RPE_ERR_ARG;
+  for (int i = 0; i < count; ++i) rpe::min_solver_2pn<float>(in24 + 24 * (size_t)i, q4 + 4 * (size_t)i, t3 + 3 * (size_t)i);
+  return RPE_OK;
 }
 
 int rpe_sample_table(uint32_t seed, int n, int m, int H, int32_t* samples) {

@@ -60,6 +60,10 @@ void launch_hypgen(int method, const FrameView& f, const int32_t* samples_dev, i
                    int32_t* votes, FrameStats* st, cudaStream_t s);
 void launch_derive_fast(const HypGen* gen, HypFast* fast, int32_t* votes, int n_slots, FrameStats* st, cudaStream_t s);
 
+// MinimalSolvers.hpp batches (one problem per thread); device pointers
+void launch_minsolv_ev(const float* M9, int count, float* E3, cudaStream_t s);
+void launch_minsolv_ms(const float* in24, int count, float* q4, float* t3, cudaStream_t s);
+
 // -- scoring -------------------------------------------------------------------------------------
 int launch_score_fast(int method, const FrameView& f, const HypGen* gen, const HypFast* fast, int slot_begin,
                        int slot_end, Thresh th, int32_t* votes, FrameStats* st, Worklist wl, int num_sms, cudaStream_t s);

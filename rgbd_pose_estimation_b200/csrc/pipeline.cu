@@ -17,6 +17,7 @@
 #include "kernels.cuh"
 #include "../../include/rpe/solvers.h"
 #include "../../include/rpe/solvers_p3p.h"
+#include "../../include/rpe/solvers_min.h"
 
 namespace rpe {
 
@@ -131,6 +132,37 @@ hypgen_kernel(int method, FrameView f, const int32_t* __restrict__ samples, int 
     g.valid = 1;
   }
   publish_hypothesis(g, ii * S + s, gen, fast, votes, st);
+}
+
+// MinimalSolvers.hpp as batch kernels, one problem per thread (rpe_min_ev / rpe_min_ms)
+__global__ void __launch_bounds__(128) minsolv_ev_kernel(const float* __restrict__ M9, int count, float* __restrict__ E3) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  float m[9], e[3];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) m[k] = M9[9 * (size_t)i + k];
+  sym3_eigenvalues<float>(m, e);
+#pragma unroll
+  for (int k = 0; k < 3; ++k) E3[3 * (size_t)i + k] = e[k];
+}
+__global__ void __launch_bounds__(128) minsolv_ms_kernel(const float* __restrict__ in24, int count, float* __restrict__ q4,
+                                                         float* __restrict__ t3) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  float in[24], q[4], t[3];
+#pragma unroll
+  for (int k = 0; k < 24; ++k) in[k] = in24[24 * (size_t)i + k];
+  min_solver_2pn<float>(in, q, t);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) q4[4 * (size_t)i + k] = q[k];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) t3[3 * (size_t)i + k] = t[k];
+}
+void launch_minsolv_ev(const float* M9, int count, float* E3, cudaStream_t s) {
+  if (count > 0) minsolv_ev_kernel<<<(count + 127) / 128, 128, 0, s>>>(M9, count, E3);
+}
+void launch_minsolv_ms(const float* in24, int count, float* q4, float* t3, cudaStream_t s) {
+  if (count > 0) minsolv_ms_kernel<<<(count + 127) / 128, 128, 0, s>>>(in24, count, q4, t3);
 }
 
 void launch_hypgen(int method, const FrameView& f, const int32_t* samples_dev, int H, HypGen* gen, HypFast* fast,

@@ -17,11 +17,13 @@ from rgbd_pose_estimation_b200 import sharding  # noqa: E402
 
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    local = local % max(1, torch.cuda.device_count())  # one-GPU box: both ranks share device 0 (IPC works there too)
     torch.cuda.set_device(local)
     dist.init_process_group("gloo")
     out = {"rank": rank}
     with rpe.Context(local) as ctx:
         assert sharding.peer_setup(dist, ctx, rank, world)
+        ctx.peer_set_timeout_ms(20000)  # two processes time-slicing one GPU exchange slowly; never a false time-out
         results = []
         for trial, (n, H, method, m) in enumerate([(20000, 1024, "shinji", 3), (5000, 300, "shinji", 3), (6000, 256, "nl_shinji_kneip", 4)]):
             q, t = rpe.sim_pose(3 + trial)

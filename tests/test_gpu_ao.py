@@ -124,10 +124,10 @@ def test_gn_refinement_matches_twin_and_closed_form(rpe, orc, gpu_ctx):
     assert fit["refit_ok"] == 1 and fit["refit_evals"] >= 2
     scale = float(np.abs(P).max())
     assert _angle(fit["q"], twin_q) < 1e-6
-    assert np.abs(fit["t"].astype(np.float64) - twin_t.astype(np.float64)).max() < 1e-6 * scale * 4
+    assert np.abs(fit["t"].astype(np.float64) - twin_t.astype(np.float64)).max() < 1e-6 * scale
     # same least-squares objective as Kabsch on pure 3-D data: converges to the closed form
     ls_q, ls_t, _ = orc.shinji_ls(P, Q, got["mask"][1], dt=np.float64)
-    assert _angle(fit["q"], ls_q) < 2e-6
+    assert _angle(fit["q"], ls_q) < 1e-6
     assert np.abs(fit["t"].astype(np.float64) - ls_t).max() < 1e-5
 
 
@@ -363,13 +363,13 @@ def test_misaligned_device_arrays_fall_back_to_the_packed_path(rpe, orc):
 
 
 def test_full_size_frame_properties(rpe, orc, gpu_ctx):
-    """BASELINE config #4 at full size (307 200 correspondences x 1 024 hypotheses), checked through properties that do
-    not need the CPU oracle to run 3e8 evaluations:
+    """BASELINE config #4 at full size (307 200 correspondences x 1 024 hypotheses), against the oracle and through
+    size-independent properties:
       * the tiled scorer's vote table equals the exact-order kernel's (same device, independent code path: the
         worklist is shrunk to nothing, every borderline evaluation overflows it, the frame is rescored exactly);
       * vote counts are invariant under a permutation of the correspondences (with the sample indices remapped);
       * the winner's vote count equals the number of set flags in its mask; the replayed Iter matches the host rule;
-      * the oracle agrees on a sample of 24 hypotheses."""
+      * the CPU oracle agrees on the full vote table (all 1 024 hypotheses), the hypotheses, the winner and the mask."""
     import ctypes
     from rgbd_pose_estimation_b200 import sharding
     orc.set_math_mode(orc.DET)
@@ -383,13 +383,19 @@ def test_full_size_frame_properties(rpe, orc, gpu_ctx):
     assert got["max_votes"] == int(votes.max()) == int(got["mask"][1].sum()) == got["n_inliers"][1]
     win, best, it = sharding.replay(votes, 0, n, 0.9999)
     assert (win, best, it) == (got["winner"], got["max_votes"], got["iter_final"])
-    # exact-order kernel on the same frame
+    # the CPU oracle on the WHOLE frame: all 1 024 hypotheses x 307 200 correspondences (3.1e8 evaluations in the
+    # reference's operation order, hypotheses sharded over the host cores: about half a second on the GPU box)
+    import os
+    ref = orc.ransac(SHINJI, S, thr3d=0.25, confidence=0.9999, full=True, nthreads=os.cpu_count() or 1, xc=P, xw=Q)
+    assert np.array_equal(votes, ref["votes"]), f"votes differ at {np.nonzero(votes != ref['votes'])[0][:10]}"
+    assert (got["winner"], got["max_votes"], got["iter_final"]) == (ref["winner"], ref["max_votes"], ref["iter_final"])
+    assert np.array_equal(got["mask"], ref["mask"])
+    assert np.array_equal(got["q"].view(np.uint32), ref["q"].view(np.uint32))
+    assert np.array_equal(got["t"].view(np.uint32), ref["t"].view(np.uint32))
     gpu_ctx.generate(SHINJI, S)
     hyps, valid = gpu_ctx.get_hypotheses(H)
-    for k in range(0, H, 43):  # 24 hypotheses through the oracle, one at a time
-        if valid[k]:
-            v, _ = orc.score(SHINJI, hyps[k, :4], hyps[k, 4:], thr3d=0.25, xc=P, xw=Q)
-            assert int(v) == int(votes[k]), k
+    sel = valid == 1
+    assert np.array_equal(hyps[sel].view(np.uint32), ref["hyps"][sel].view(np.uint32))
     # the exact-order kernel scores the whole frame (worklist capacity 0 forces the overflow -> exact path)
     rpe.lib.rpe_debug_set_worklist_capacity.argtypes = [ctypes.c_void_p, ctypes.c_uint]
     rpe.lib.rpe_debug_set_worklist_capacity(gpu_ctx.handle, 0)

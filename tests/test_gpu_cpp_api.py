@@ -112,12 +112,12 @@ def test_cpp_dropin_matches_oracle(dropin_output, rpe, orc):
         last = ref
     q1, t1 = orc.nl_shinji_kneip_ls(last["q"], last["t"], last["mask"], last["max_votes"], dt=np.float64, **arrs)
     got = res["nl_shinji_kneip_ls"]
-    assert _angle(got["q"], q1) < 2e-6 and np.abs(np.array(got["t"]) - t1).max() < 2e-5
+    assert _angle(got["q"], q1) < 1e-6 and np.abs(np.array(got["t"]) - t1).max() < 1e-5
     # second call starts from the first refit's pose, now with the simulator's dynamic weights (TestMain.cpp:219-221)
     q2, t2 = orc.nl_shinji_kneip_ls(np.float32(got["q"]), np.float32(got["t"]), last["mask"], last["max_votes"],
                                     weights3=d["weights"].astype(np.float64), dt=np.float64, **arrs)
     got2 = res["nl_shinji_kneip_ls_dw"]
-    assert _angle(got2["q"], q2) < 2e-6 and np.abs(np.array(got2["t"]) - t2).max() < 2e-5
+    assert _angle(got2["q"], q2) < 1e-6 and np.abs(np.array(got2["t"]) - t2).max() < 1e-5
     assert _angle(got2["q"], q) < 5e-3  # and it is a good pose
     # ---- Tp = double adapters: decided in binary64 on the device, compared with the oracle instantiated for double;
     # the sample stream continues where the float estimators left ::rand()
@@ -137,7 +137,7 @@ def test_cpp_dropin_matches_oracle(dropin_output, rpe, orc):
     rq, rt = orc.nl_shinji_kneip_ls(ref["q"], ref["t"], ref["mask"], ref["max_votes"], dt=np.float64, bv=bv, xc=xc, nc=nc, xw=xw,
                                     nw=nw)
     got = res["nl_shinji_kneip_ls_f64"]
-    assert _angle(got["q"], rq) < 4e-6 and np.abs(np.array(got["t"]) - rt).max() < 4e-5
+    assert _angle(got["q"], rq) < 1e-6 and np.abs(np.array(got["t"]) - rt).max() < 1e-5
     S = orc.sample_table_skip(1, skip, total, 4, 500)
     ref = orc.ransac(1, S, cos_thr=cos_thr64, confidence=0.99, full=False, want_arrays=False, dt=np.float64, bv=bv, xw=xw)
     got = res["kneip_ransac_f64"]
@@ -179,9 +179,9 @@ def test_library_cpp_shim_ao_and_ao_ransac(rpe, orc):
     ref = orc.ransac(0, S, thr3d=np.float32(0.1), confidence=np.float32(0.99999), full=False, xc=P, xw=Q, want_arrays=False)
     ls_q, ls_t, _ = orc.shinji_ls(P, Q, ref["mask"][1], dt=np.float64)
     Rref = orc.quat_to_matrix(ls_q, np.float64)
-    assert np.abs(R.reshape(3, 3) - Rref).max() < 2e-6 and np.abs(tt - ls_t).max() < 2e-5
+    assert np.abs(R.reshape(3, 3) - Rref).max() < 1e-6 and np.abs(tt - ls_t).max() < 1e-5
     # ao(): least squares over all points, so the 30 % outliers bias it — compare with the oracle's shinji_ls2
     assert rpe.lib.rpe_ao(Q.ctypes.data, P.ctypes.data, n, R.ctypes.data, tt.ctypes.data) == 0
     ls_q, ls_t, _ = orc.shinji_ls(P, Q, None, dt=np.float64)
-    assert np.abs(R.reshape(3, 3) - orc.quat_to_matrix(ls_q, np.float64)).max() < 2e-6 and np.abs(tt - ls_t).max() < 2e-5
+    assert np.abs(R.reshape(3, 3) - orc.quat_to_matrix(ls_q, np.float64)).max() < 1e-6 and np.abs(tt - ls_t).max() < 1e-5
     orc.set_math_mode(orc.LIBM)
