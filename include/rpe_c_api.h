@@ -165,6 +165,15 @@ int rpe_ransac_async(rpe_ctx* ctx, int method, const int32_t* samples, int H, fl
  * blocking caller whose loops usually stop after a few dozen iterations (low outlier ratios) can start smaller. The
  * result does not depend on it. */
 int rpe_set_first_pass_iters(rpe_ctx* ctx, int iters);
+/* Opt-in: reproduce the reference's STALE SAMPLE COLUMNS on frames with invalid depth. Its nl_shinji_ransac /
+ * nl_shinji_kneip_ransac hoist the sample buffers out of the loop and assign_sample skips the camera-side columns of an
+ * invalid (all-NaN) sample point (AbsoluteOrientationNormal.hpp:48-75, 299-315), so nl_2p (:315, :389) pairs the
+ * current world point / normal with the camera point / normal an EARLIER iteration left in that column — and such a
+ * hypothesis can win. Off (default): the invalid point's NaN goes into nl_2p and the hypothesis scores nothing. On: the
+ * device reproduces the reference (columns never written read as zeros; the reference reads uninitialised memory
+ * there). Also switched on for every new context by RPE_STALE_SAMPLE_COLUMNS=1 in the environment. Frames without
+ * invalid camera points (all Simulator inputs) give identical results either way. */
+int rpe_set_stale_sample_columns(rpe_ctx* ctx, int on);
 /* Same as rpe_ransac, with the sample rows produced on demand: `fn(user, first_iteration, count, rows)` must write
  * rows [first_iteration, first_iteration + count) of the table (count x 4 int32) and return 0. It is called once per
  * device pass (1024, 2048, 4096, 8192, ... iterations) in increasing order, so a caller whose Iter is 100 000 — the

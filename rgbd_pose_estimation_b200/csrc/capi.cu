@@ -71,6 +71,10 @@ struct rpe_ctx {
   ReplayOut* h_pose = nullptr;    // pinned, kNumStaging slots; [0] doubles as scratch for set_pose
   bool kabsch_valid = false;
   bool suff_valid = false;  // rb.suff matches the inlier columns in d_mask
+  bool stale_cols = false;       // rpe_set_stale_sample_columns
+  int32_t* d_stale_eff = nullptr;  // [cap_stale x 2] effective camera-side sample indices of the current pass
+  int32_t* d_stale_carry = nullptr;
+  int cap_stale = 0;
   int first_pass = 1024;  // iterations of the first device pass (kFirstPassIters; rpe_set_first_pass_iters)
   // peer-memory vote exchange (hypothesis-sharded single frame)
   unsigned char* d_peer_block = nullptr;  // own block (exported)
@@ -260,6 +264,25 @@ int ensure_hyp_capacity(rpe_ctx* ctx, int H, int slots) {
     CK(cudaMalloc(&ctx->d_samples, (size_t)cap * 4 * sizeof(int32_t)));
     ctx->cap_H = cap;
   }
+  return RPE_OK;
+}
+
+// opt-in stale sample columns: run the prefix scan for this pass and return the table the generator should read
+// (nullptr when the option is off or the family has no nl_2p slot)
+int prepare_stale(rpe_ctx* ctx, int method, const int32_t* samples_dev, int hc, bool first_pass_of_frame, const int32_t** eff) {
+  *eff = nullptr;
+  if (!ctx->stale_cols || !(method == RPE_NL_SHINJI || method == RPE_NL_SHINJI_KNEIP)) return RPE_OK;
+  if (hc > ctx->cap_stale) {
+    if (ctx->d_stale_eff) cudaFree(ctx->d_stale_eff);
+    ctx->d_stale_eff = nullptr;
+    CK(cudaMalloc(&ctx->d_stale_eff, (size_t)(hc + 256) * 2 * sizeof(int32_t)));
+    ctx->cap_stale = hc + 256;
+  }
+  if (!ctx->d_stale_carry) CK(cudaMalloc(&ctx->d_stale_carry, 2 * sizeof(int32_t)));
+  launch_stale_cols(samples_dev, hc, ctx->view[A_XC], ctx->f64 ? ctx->view64[A_XC] : nullptr, ctx->n, ctx->d_stale_carry,
+                    first_pass_of_frame, ctx->d_stale_eff, ctx->stream);
+  ctx->launches++;
+  *eff = ctx->d_stale_eff;
   return RPE_OK;
 }
 
@@ -622,7 +645,9 @@ int do_ransac64(rpe_ctx* ctx, int method, const int32_t* samples, rpe_sample_fn 
       CK(cudaMemcpyAsync(ctx->d_samples, chunk, (size_t)hc * 4 * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
       samples_dev = ctx->d_samples;
     }
-    launch_hypgen64(method, f, samples_dev, hc, ctx->d_gen64, ctx->d_votes, ctx->stream);
+    const int32_t* stale_eff = nullptr;
+    if (int rcs = prepare_stale(ctx, method, samples_dev, hc, base == 0, &stale_eff)) return rcs;
+    launch_hypgen64(method, f, samples_dev, hc, ctx->d_gen64, ctx->d_votes, ctx->stream, stale_eff);
     ctx->launches++;
     if (g_f64_exact_only) {
       launch_score64(method, f, ctx->d_gen64, hc * S, th, ctx->d_votes, ctx->num_sms, nullptr, ctx->stream);
@@ -745,7 +770,9 @@ int do_ransac(rpe_ctx* ctx, int method, const int32_t* samples, rpe_sample_fn fn
     }
     if (base == 0) stamp(ctx, ST_GEN);
     FrameView f = make_view(ctx);
-    launch_hypgen(method, f, samples_dev, hc, ctx->d_gen, ctx->d_fast, ctx->d_votes, ctx->d_stats, ctx->stream);
+    const int32_t* stale_eff = nullptr;
+    if (int rcs = prepare_stale(ctx, method, samples_dev, hc, base == 0, &stale_eff)) return rcs;
+    launch_hypgen(method, f, samples_dev, hc, ctx->d_gen, ctx->d_fast, ctx->d_votes, ctx->d_stats, ctx->stream, stale_eff);
     ctx->launches++;
     ctx->n_slots = hc * S;
     ctx->cur_method = method;
@@ -838,6 +865,10 @@ static int create_common(int device, void* stream, bool own, rpe_ctx** out) {
     ctx->stream = (cudaStream_t)stream;
   }
   ctx->own_stream = own;
+  {
+    const char* e = getenv("RPE_STALE_SAMPLE_COLUMNS");  // the header-only adapters have no knob of their own for it
+    ctx->stale_cols = e && e[0] == '1';
+  }
   bool ok = true;
   ok = ok && cudaMalloc(&ctx->d_stats, sizeof(FrameStats)) == cudaSuccess;
   ok = ok && cudaMalloc(&ctx->d_pose, sizeof(ReplayOut)) == cudaSuccess;
@@ -902,6 +933,8 @@ int rpe_destroy(rpe_ctx* ctx) {
   cudaFree(ctx->d_fast);
   cudaFree(ctx->d_votes);
   cudaFree(ctx->d_samples);
+  cudaFree(ctx->d_stale_eff);
+  cudaFree(ctx->d_stale_carry);
   cudaFree(ctx->d_stats);
   cudaFree(ctx->d_pose);
   cudaFree(ctx->d_rs);
@@ -1021,6 +1054,11 @@ int rpe_ransac(rpe_ctx* ctx, int method, const int32_t* samples, int H, float th
 int rpe_ransac_async(rpe_ctx* ctx, int method, const int32_t* samples, int H, float thr3d, float cos_thr2d,
                      float cos_thrN, float confidence, rpe_result* out, int16_t* mask) {
   return do_ransac(ctx, method, samples, nullptr, nullptr, H, thr3d, cos_thr2d, cos_thrN, confidence, out, mask, false);
+}
+int rpe_set_stale_sample_columns(rpe_ctx* ctx, int on) {
+  if (!ctx) return RPE_ERR_ARG;
+  ctx->stale_cols = on != 0;
+  return RPE_OK;
 }
 int rpe_set_first_pass_iters(rpe_ctx* ctx, int iters) {
   if (!ctx || iters < 1) return RPE_ERR_ARG;
@@ -1229,7 +1267,9 @@ int rpe_generate(rpe_ctx* ctx, int method, const int32_t* samples, int H) {
   CK(cudaMemcpyAsync(ctx->d_samples, samples, (size_t)H * 4 * sizeof(int32_t), cudaMemcpyDefault, ctx->stream));
   launch_reset_stats(ctx->d_stats, ctx->stream);
   FrameView f = make_view(ctx);
-  launch_hypgen(method, f, ctx->d_samples, H, ctx->d_gen, ctx->d_fast, ctx->d_votes, ctx->d_stats, ctx->stream);
+  const int32_t* stale_eff = nullptr;
+  if (int rcs = prepare_stale(ctx, method, ctx->d_samples, H, true, &stale_eff)) return rcs;
+  launch_hypgen(method, f, ctx->d_samples, H, ctx->d_gen, ctx->d_fast, ctx->d_votes, ctx->d_stats, ctx->stream, stale_eff);
   ctx->launches += 2;
   ctx->n_slots = H * S;
   ctx->cur_method = method;
@@ -1448,7 +1488,9 @@ static int do_ransac_sharded(rpe_ctx* ctx, int method, const int32_t* samples, i
   if (rc) return rc;
   CK(cudaMemcpyAsync(ctx->d_samples, samples, (size_t)H * 4 * sizeof(int32_t), cudaMemcpyDefault, ctx->stream));
   FrameView f = make_view(ctx);
-  launch_hypgen(method, f, ctx->d_samples, H, ctx->d_gen, ctx->d_fast, ctx->d_votes, ctx->d_stats, ctx->stream);
+  const int32_t* stale_eff = nullptr;
+  if (int rcs = prepare_stale(ctx, method, ctx->d_samples, H, true, &stale_eff)) return rcs;
+  launch_hypgen(method, f, ctx->d_samples, H, ctx->d_gen, ctx->d_fast, ctx->d_votes, ctx->d_stats, ctx->stream, stale_eff);
   ctx->launches++;
   ctx->n_slots = H * S;
   ctx->cur_method = method;

@@ -114,7 +114,8 @@ void launch_f64_to_f32(const double* src, float* dst, size_t count, cudaStream_t
 // ================================================================================================
 __global__ void __launch_bounds__(128)
 hypgen64_kernel(int method, FrameView64 f, const int32_t* __restrict__ samples, int H, HypGen64* __restrict__ gen,
-                int32_t* __restrict__ votes) {
+                int32_t* __restrict__ votes,
+                const int32_t* __restrict__ stale_eff) {
   const int ii = blockIdx.x * blockDim.x + threadIdx.x;
   if (ii >= H) return;
   const int S = method_slots(method);
@@ -167,10 +168,11 @@ hypgen64_kernel(int method, FrameView64 f, const int32_t* __restrict__ samples, 
   } else {
     double pc0[3], nc0[3], pc1[3], pw0[3], nw0[3], pw1[3];
     const int c0 = sel[0], c1 = sel[1];
+    const int e0 = stale_eff ? stale_eff[2 * ii] : c0, e1 = stale_eff ? stale_eff[2 * ii + 1] : c1;  // see hypgen_kernel
     for (int r = 0; r < 3; ++r) {
-      pc0[r] = f.xc[3 * c0 + r];
-      nc0[r] = f.nc[3 * c0 + r];
-      pc1[r] = f.xc[3 * c1 + r];
+      pc0[r] = e0 >= 0 ? f.xc[3 * e0 + r] : 0.0;
+      nc0[r] = e0 >= 0 ? f.nc[3 * e0 + r] : 0.0;
+      pc1[r] = e1 >= 0 ? f.xc[3 * e1 + r] : 0.0;
       pw0[r] = f.xw[3 * c0 + r];
       nw0[r] = f.nw[3 * c0 + r];
       pw1[r] = f.xw[3 * c1 + r];
@@ -182,10 +184,10 @@ hypgen64_kernel(int method, FrameView64 f, const int32_t* __restrict__ samples, 
   votes[ii * S + s] = g.valid ? 0 : -1;
 }
 void launch_hypgen64(int method, const FrameView64& f, const int32_t* samples_dev, int H, HypGen64* gen, int32_t* votes,
-                     cudaStream_t s) {
+                     cudaStream_t s, const int32_t* stale_eff) {
   if (H <= 0) return;
   dim3 grid((H + 127) / 128, method_slots(method));
-  hypgen64_kernel<<<grid, 128, 0, s>>>(method, f, samples_dev, H, gen, votes);
+  hypgen64_kernel<<<grid, 128, 0, s>>>(method, f, samples_dev, H, gen, votes, stale_eff);
 }
 
 // ================================================================================================

@@ -57,7 +57,10 @@ void launch_pack(const FrameView& f, int kind, float4* pk_out, FrameStats* st, c
 
 // -- generation ----------------------------------------------------------------------------------
 void launch_hypgen(int method, const FrameView& f, const int32_t* samples_dev, int H, HypGen* gen, HypFast* fast,
-                   int32_t* votes, FrameStats* st, cudaStream_t s);
+                   int32_t* votes, FrameStats* st, cudaStream_t s, const int32_t* stale_eff = nullptr);
+// opt-in reproduction of the reference's stale sample columns (see hypgen_kernel): eff = [H x 2] int32
+void launch_stale_cols(const int32_t* samples_dev, int H, const float* xc, const double* xc64, int n, int32_t* carry,
+                       bool reset_carry, int32_t* eff, cudaStream_t s);
 void launch_derive_fast(const HypGen* gen, HypFast* fast, int32_t* votes, int n_slots, FrameStats* st, cudaStream_t s);
 
 // MinimalSolvers.hpp batches (one problem per thread); device pointers
@@ -186,7 +189,7 @@ struct ReplayState64 {
 };
 void launch_f64_to_f32(const double* src, float* dst, size_t count, cudaStream_t s);
 void launch_hypgen64(int method, const FrameView64& f, const int32_t* samples_dev, int H, HypGen64* gen, int32_t* votes,
-                     cudaStream_t s);
+                     cudaStream_t s, const int32_t* stale_eff = nullptr);
 void launch_score64(int method, const FrameView64& f, const HypGen64* gen, int n_slots, Thresh64 th, int32_t* votes,
                     int num_sms, const FrameStats* only_if_overflow, cudaStream_t s);
 void launch_derive_fast64(const HypGen64* g64, HypGen* gen, HypFast* fast, int n_slots, cudaStream_t s);

@@ -62,7 +62,8 @@ __device__ __forceinline__ void publish_hypothesis(const HypGen& g, int slot, Hy
 // grid.x over iterations, grid.y = slot within the iteration (so a CTA runs one solver only).
 __global__ void __launch_bounds__(128)
 hypgen_kernel(int method, FrameView f, const int32_t* __restrict__ samples, int H, HypGen* __restrict__ gen,
-              HypFast* __restrict__ fast, int32_t* __restrict__ votes, FrameStats* __restrict__ st) {
+              HypFast* __restrict__ fast, int32_t* __restrict__ votes, FrameStats* __restrict__ st,
+              const int32_t* __restrict__ stale_eff) {
   const int ii = blockIdx.x * blockDim.x + threadIdx.x;
   if (ii >= H) return;
   const int S = method_slots(method);
@@ -118,16 +119,20 @@ hypgen_kernel(int method, FrameView f, const int32_t* __restrict__ samples, int 
   } else {
     float pc0[3], nc0[3], pc1[3], pw0[3], nw0[3], pw1[3];
     const int c0 = sel[0], c1 = sel[1];
+    // Camera-side columns: by default the sample's own (an invalid, all-NaN camera point then simply propagates NaN into
+    // the translation). With rpe_set_stale_sample_columns the reference's hoisted buffers are reproduced
+    // (AbsoluteOrientationNormal.hpp:48-75, 299-315): an invalid sample point leaves column k of X_c / N_c as an EARLIER
+    // iteration wrote it; stale_eff[2 ii + k] is that earlier correspondence (-1: never written; the reference reads
+    // uninitialised memory there, zeros here and in the oracle's StaleCols model).
+    const int e0 = stale_eff ? stale_eff[2 * ii] : c0, e1 = stale_eff ? stale_eff[2 * ii + 1] : c1;
     for (int r = 0; r < 3; ++r) {
-      pc0[r] = f.xc[3 * c0 + r];
-      nc0[r] = f.nc[3 * c0 + r];
-      pc1[r] = f.xc[3 * c1 + r];
+      pc0[r] = e0 >= 0 ? f.xc[3 * e0 + r] : 0.f;
+      nc0[r] = e0 >= 0 ? f.nc[3 * e0 + r] : 0.f;
+      pc1[r] = e1 >= 0 ? f.xc[3 * e1 + r] : 0.f;
       pw0[r] = f.xw[3 * c0 + r];
       nw0[r] = f.nw[3 * c0 + r];
       pw1[r] = f.xw[3 * c1 + r];
     }
-    // An invalid (all-NaN) camera point simply propagates NaN into the translation (the reference
-    // would read a stale column of its hoisted sample buffer there: AbsoluteOrientationNormal.hpp:61-65).
     nl_2p<float>(pc0, nc0, pc1, pw0, nw0, pw1, g.q, g.t);
     g.valid = 1;
   }
@@ -166,10 +171,51 @@ void launch_minsolv_ms(const float* in24, int count, float* q4, float* t3, cudaS
 }
 
 void launch_hypgen(int method, const FrameView& f, const int32_t* samples_dev, int H, HypGen* gen, HypFast* fast,
-                   int32_t* votes, FrameStats* st, cudaStream_t s) {
+                   int32_t* votes, FrameStats* st, cudaStream_t s, const int32_t* stale_eff) {
   if (H <= 0) return;
   dim3 grid((H + 127) / 128, method_slots(method));
-  hypgen_kernel<<<grid, 128, 0, s>>>(method, f, samples_dev, H, gen, fast, votes, st);
+  hypgen_kernel<<<grid, 128, 0, s>>>(method, f, samples_dev, H, gen, fast, votes, st, stale_eff);
+}
+
+// The reference's stale sample columns as a prefix scan: eff[2 ii + k] = sel[j][k] of the latest iteration j <= ii whose
+// k-th sample point has a valid camera point (k = 0, 1: the columns nl_2p reads), carried across device passes in
+// carry[2] (reset_carry on the frame's first pass). One warp per column; 32 iterations per step.
+__device__ __forceinline__ bool corr_valid_f(const float* xc, int c) {
+  return xc[3 * c] == xc[3 * c] || xc[3 * c + 1] == xc[3 * c + 1] || xc[3 * c + 2] == xc[3 * c + 2];
+}
+__device__ __forceinline__ bool corr_valid_f(const double* xc, int c) {
+  return xc[3 * c] == xc[3 * c] || xc[3 * c + 1] == xc[3 * c + 1] || xc[3 * c + 2] == xc[3 * c + 2];
+}
+template <class T>
+__global__ void __launch_bounds__(64) stale_cols_kernel(const int32_t* __restrict__ samples, int H, const T* __restrict__ xc, int n,
+                                                        int32_t* __restrict__ carry, int reset_carry, int32_t* __restrict__ eff) {
+  const int k = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int last = reset_carry ? -1 : carry[k];
+  for (int base = 0; base < H; base += 32) {
+    const int ii = base + lane;
+    int v = -1;
+    if (ii < H) {
+      const int c = samples[4 * ii + k];
+      if (c >= 0 && c < n && corr_valid_f(xc, c)) v = c;
+    }
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {  // inclusive scan with "the later valid one wins"
+      const int up = __shfl_up_sync(0xffffffffu, v, o);
+      if (lane >= o && v < 0) v = up;
+    }
+    if (v < 0) v = last;
+    if (ii < H) eff[2 * ii + k] = v;
+    last = __shfl_sync(0xffffffffu, v, 31);
+  }
+  if (lane == 0) carry[k] = last;
+}
+void launch_stale_cols(const int32_t* samples_dev, int H, const float* xc, const double* xc64, int n, int32_t* carry,
+                       bool reset_carry, int32_t* eff, cudaStream_t s) {
+  if (H <= 0) return;
+  if (xc64)
+    stale_cols_kernel<double><<<1, 64, 0, s>>>(samples_dev, H, xc64, n, carry, reset_carry ? 1 : 0, eff);
+  else
+    stale_cols_kernel<float><<<1, 64, 0, s>>>(samples_dev, H, xc, n, carry, reset_carry ? 1 : 0, eff);
 }
 
 __global__ void derive_fast_kernel(const HypGen* __restrict__ gen, HypFast* __restrict__ fast, int32_t* __restrict__ votes,
