@@ -259,7 +259,7 @@ fixup64_kernel(int method, FrameView64 f, const HypGen64* __restrict__ gen, Thre
 void launch_fixup64(int method, const FrameView64& f, const HypGen64* gen, Thresh64 th, int32_t* votes, FrameStats* st,
                     Worklist wl, int nseg, cudaStream_t s) {
   if (nseg <= 0) return;
-  fixup64_kernel<<<dim3(nseg, 4), 256, 0, s>>>(method, f, gen, th, votes, st, wl, nseg);
+  fixup64_kernel<<<dim3(nseg, nseg > 1024 ? 1 : 4), 256, 0, s>>>(method, f, gen, th, votes, st, wl, nseg);
 }
 __global__ void zero_votes64_kernel(const HypGen64* __restrict__ gen, int n_slots, int32_t* __restrict__ votes,
                                     const FrameStats* __restrict__ st) {

@@ -452,7 +452,15 @@ score3d_fast_kernel(const float4* __restrict__ pk, int npairs_pad, int pairs_per
 // applied to instead of the frame maximum. No pack kernel, no second copy of the frame in HBM.
 // TMA needs 16-byte aligned addresses and sizes: stages start at multiples of 4 correspondences and copy a multiple
 // of 4; the last 0..3 correspondences of the frame are read from global memory by the transposing threads.
-template <int HPT, int TILE, int THREADS, int MINB, int SUB>
+// (s.y < 0 ? 0xffff0000 : 0) | (s.x < 0 ? 0x0000ffff : 0): PRMT in its generic mode replicates the sign of the selected byte
+// when bit 3 of the selector nibble is set (0xB = sign of byte 3 of a, 0xF = sign of byte 3 of b)
+__device__ __forceinline__ unsigned int sign_words(float2 s) {
+  unsigned int d;
+  asm("prmt.b32 %0, %1, %2, 0xFFBB;" : "=r"(d) : "r"(__float_as_uint(s.x)), "r"(__float_as_uint(s.y)));
+  return d;
+}
+
+template <int HPT, int TILE, int THREADS, int MINB, int SUB, bool PCOUNT>
 __global__ void __launch_bounds__(THREADS, MINB)
 score3d_raw_kernel(const float* __restrict__ xw, const float* __restrict__ xc, int n, int npairs_pad, int pairs_per_cta,
                    const HypFast* __restrict__ fast, const HypGen* __restrict__ gen, int slot_begin, int slot_end, float thr,
@@ -474,6 +482,7 @@ score3d_raw_kernel(const float* __restrict__ xw, const float* __restrict__ xc, i
   HypRegs<true> hyp[HPT];
   int slot[HPT];
   int cnt[HPT];
+  unsigned int pacc[HPT];
   float tnorm[HPT];
 #pragma unroll
   for (int k = 0; k < HPT; ++k) {
@@ -482,6 +491,7 @@ score3d_raw_kernel(const float* __restrict__ xw, const float* __restrict__ xc, i
     hyp[k].load(&fast[live ? slot[k] : slot_begin], live);
     if (!live) slot[k] = -1;
     cnt[k] = 0;
+    pacc[k] = 0u;
     tnorm[k] = sqrtf(hyp[k].nt[0].x * hyp[k].nt[0].x + hyp[k].nt[1].x * hyp[k].nt[1].x + hyp[k].nt[2].x * hyp[k].nt[2].x);
   }
   const float thr2 = __fmul_rn(thr, thr);
@@ -584,6 +594,29 @@ score3d_raw_kernel(const float* __restrict__ xw, const float* __restrict__ xc, i
       float smin[HPT];
 #pragma unroll
       for (int k = 0; k < HPT; ++k) smin[k] = CUDART_INF_F;
+      if (PCOUNT) {
+        // Packed sign count: one PRMT with sign replication turns the two decision values of a pair into
+        // (s.y < 0 ? 0xffff0000 : 0) | (s.x < 0 ? 0x0000ffff : 0), and one IADD3 subtracts the words of TWO pairs from a
+        // packed accumulator: 3 ALU-pipe instructions per 4 evaluations instead of 4 LEA.HI. acc = (ny - nx) 2^16 + nx.
+#pragma unroll
+        for (int pp = 0; pp < SUB; pp += 2) {
+          unsigned int tw[2][HPT];
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const float4 a = sp[(sub + pp + h) * 3 + 0];
+            const float4 b = sp[(sub + pp + h) * 3 + 1];
+            const float4 c = sp[(sub + pp + h) * 3 + 2];
+#pragma unroll
+            for (int k = 0; k < HPT; ++k) {
+              const float2 s = hyp[k].eval(a, b, c, nlo);
+              tw[h][k] = sign_words(s);
+              smin[k] = fminf(fminf(smin[k], fabsf(s.x)), fabsf(s.y));
+            }
+          }
+#pragma unroll
+          for (int k = 0; k < HPT; ++k) pacc[k] = pacc[k] - tw[0][k] - tw[1][k];
+        }
+      } else {
 #pragma unroll
       for (int pp = 0; pp < SUB; ++pp) {
         const float4 a = sp[(sub + pp) * 3 + 0];
@@ -595,6 +628,7 @@ score3d_raw_kernel(const float* __restrict__ xw, const float* __restrict__ xc, i
           cnt[k] += (int)(__float_as_uint(s.x) >> 31) + (int)(__float_as_uint(s.y) >> 31);
           smin[k] = fminf(fminf(smin[k], fabsf(s.x)), fabsf(s.y));
         }
+      }
       }
       bool any = false;
 #pragma unroll
@@ -611,13 +645,21 @@ score3d_raw_kernel(const float* __restrict__ xw, const float* __restrict__ xc, i
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
               if (fabsf(sv[u]) <= band[k]) {
-                cnt[k] -= (int)(__float_as_uint(sv[u]) >> 31);
+                cnt[k] -= (int)(__float_as_uint(sv[u]) >> 31);  // (the packed accumulator is folded into cnt per stage)
                 const unsigned int corr = (unsigned int)(2 * (p_begin + t * TILE + sub + pp) + u);
                 seg.push(make_uint2((unsigned int)slot[k], corr | (1u << 30)), st);
               }
             }
           }
         }
+      }
+    }
+    if (PCOUNT) {  // fold the packed fields (at most TILE <= 1024 pairs since the last fold: no field overflows)
+#pragma unroll
+      for (int k = 0; k < HPT; ++k) {
+        const unsigned int lo = pacc[k] & 0xffffu, hi = pacc[k] >> 16;
+        cnt[k] += (int)(lo + ((hi + lo) & 0xffffu));
+        pacc[k] = 0u;
       }
     }
     __syncthreads();  // everybody is done with the records (and has read the bound) before the next transpose
@@ -646,6 +688,9 @@ struct KindTraits {
   static constexpr bool k2 = (KIND & 1) != 0, k3 = (KIND & 2) != 0, kn = (KIND & 4) != 0;
   static constexpr int arrays = 1 + (k2 ? 1 : 0) + (k3 ? 1 : 0) + (kn ? 2 : 0);
   static constexpr int f4pp = (arrays * 6 + 3) / 4;
+  // RAW records carry, instead of n_w and n_c, the nine products n_c,i n_w,j of each correspondence (18 floats per pair,
+  // formed once per stage while transposing): the normal test is then 9 FFMA2 per (pair, hypothesis) instead of 12
+  static constexpr int f4raw = kn ? ((arrays - 2) * 6 + 18 + 3) / 4 : f4pp;
   static constexpr int off_xc = 6;                       // floats
   static constexpr int off_bv = 6 + (k3 ? 6 : 0);
   static constexpr int off_nw = 6 + (k3 ? 6 : 0) + (k2 ? 6 : 0);
@@ -654,7 +699,7 @@ struct KindTraits {
 
 struct BandConsts {   // per hypothesis
   float band3;            // on s3
-  float k1_2d, k2_2d, c0_2d;  // band2 = k1 |d'| + k2 n2 + c0
+  float k1_2d, k2_2d, c0_2d;  // band2 = -k1 d' + k2 n2 + c0 (k1_2d holds -k1)
   float band_n;           // on g'
 };
 
@@ -675,7 +720,8 @@ score_multi_fast_kernel(MultiSrc src, int npairs_pad, int pairs_per_cta, const H
   typedef KindTraits<KIND> KT;
   constexpr int HPT = 2;
   constexpr int SUB = kSubPairs;
-  constexpr int F4 = KT::f4pp;
+  constexpr int F4 = RAW ? KT::f4raw : KT::f4pp;
+  constexpr bool kBandAbs = KIND == 1;  // 2-D band from |d'| (2-D-only kind) or from -d' (hybrids), see set_bands
   // RAW: arrays staged per stage = the record's arrays, plus x_c when the kind has the normal test but not the 3-D one
   constexpr int NREC = KT::arrays;
   constexpr bool XC_EXTRA = KT::kn && !KT::k3;
@@ -730,12 +776,21 @@ score_multi_fast_kernel(MultiSrc src, int npairs_pad, int pairs_per_cta, const H
       const float M3 = (mwc + tnorm[k]) * 1.0001f;  // NaN for a dead slot: never borderline
       const float M2 = (mw + tnorm[k]) * 1.0001f;
       bc[k].band3 = guard_band_3d(M3, th.thr3d);
-      bc[k].k1_2d = u * 1.1f * 71.2f * M2;
+      // stored NEGATED: the band uses -d' instead of |d'| (one FFMA2, no absolute values). For d' < 0 that is the same
+      // number. For d' >= 0, F' = d'^2 + c^2 n2 >= c^2 n2, so |F'| <= beta(|y|) forces |y| <= y1 = 70.5 u M2 / c (< y0), and
+      // the band  c0 + k2 n2 - k1 d' >= c0 - k1 y1  must still cover beta(y1): c0 >= beta(y1) + k1 y1 =
+      // 1.1 u M2 y1 (64 c + 71.2) <= 1.1 * 9532 u^2 M2^2 / c, while beta(y0) = 1.1 * 24000 u^2 M2^2: (2 + 1/c) beta(y0) covers it
+      // for every cos_thr > 0.
+      // (the 2-D-only kind keeps |d'|: measured 3 % faster there, 4-7 % slower for the hybrids — round 2, r02d)
+      bc[k].k1_2d = kBandAbs ? u * 1.1f * 71.2f * M2 : -(u * 1.1f * 71.2f * M2);
       bc[k].k2_2d = u * 1.1f * 26.f * th.cos_thr;
       const float y0 = 375.f * u * M2 / th.cos_thr;
-      bc[k].c0_2d = th.cos_thr * u * 1.1f * (64.f * M2 * y0 + 26.f * y0 * y0);
+      bc[k].c0_2d = (kBandAbs ? 1.f : 2.f + 1.f / th.cos_thr) * th.cos_thr * u * 1.1f * (64.f * M2 * y0 + 26.f * y0 * y0);
       const float nm = nmax * 1.0001f;
-      bc[k].band_n = u * 1.1f * (29.f * nm * nm + 2.f);
+      // packed records: reference 19.1 u N^2, fast (3 FMUL2 + 9 FFMA2) 9.2 u N^2 + u.
+      // RAW records (products p_ij = fl(n_c,i n_w,j), then one 9-term FFMA chain from cos_nl): product and nR roundings
+      // 2 x 1.74 u N^2 (|| |R| ||_2 <= sqrt 3), chain 9 u (1 + 1.74 N^2)  ->  fast <= u (19.1 N^2 + 9)
+      bc[k].band_n = RAW ? u * 1.1f * (40.f * nm * nm + 12.f) : u * 1.1f * (29.f * nm * nm + 2.f);
     }
   };
   if (!RAW) {
@@ -746,7 +801,6 @@ score_multi_fast_kernel(MultiSrc src, int npairs_pad, int pairs_per_cta, const H
   const float2 nlo = make_float2(-thr2, -thr2);
   const float c2 = (float)((double)th.cos_thr * (double)th.cos_thr);
   const float2 cnl2 = make_float2(th.cos_nl, th.cos_nl);
-
   // RAW: correspondences [c0, c0 + cnt4) of stage t go through TMA (cnt4 a multiple of 4, possibly 0); the frame's last
   // 0..3 correspondences are read from global memory by the transposing threads
   const int n = src.n;
@@ -831,13 +885,23 @@ score_multi_fast_kernel(MultiSrc src, int npairs_pad, int pairs_per_cta, const H
       n2 = __ffma2_rn(ny1, ny1, n2);
       n2 = __ffma2_rn(ny2, ny2, n2);
       float2 band2 = __ffma2_rn(make_float2(bc[k].k2_2d, bc[k].k2_2d), n2, make_float2(bc[k].c0_2d, bc[k].c0_2d));
-      band2 = __ffma2_rn(make_float2(bc[k].k1_2d, bc[k].k1_2d), make_float2(fabsf(d.x), fabsf(d.y)), band2);
+      band2 = __ffma2_rn(make_float2(bc[k].k1_2d, bc[k].k1_2d), kBandAbs ? make_float2(fabsf(d.x), fabsf(d.y)) : d,
+                         band2);  // hybrids: k1 is stored negated, -k1 d' (see set_bands)
       val[0][0] = fmaf(c2, n2.x, d.x * fabsf(d.x));
       val[0][1] = fmaf(c2, n2.y, d.y * fabsf(d.y));
       bnd[0][0] = band2.x;
       bnd[0][1] = band2.y;
     }
-    if (KT::kn) {
+    if (KT::kn && RAW) {
+      const float* pr = rec + KT::off_nw;  // p_ij of both correspondences, (i, j) row-major, interleaved
+      float2 g = cnl2;
+#pragma unroll
+      for (int e = 0; e < 9; ++e) g = __ffma2_rn(make_float2(nR[k][e], nR[k][e]), make_float2(pr[2 * e], pr[2 * e + 1]), g);
+      val[2][0] = g.x;
+      val[2][1] = g.y;
+      bnd[2][0] = bnd[2][1] = bc[k].band_n;
+    }
+    if (KT::kn && !RAW) {
       const float* w = rec + KT::off_nw;
       const float* c = rec + KT::off_nc;
       const float2 W0 = make_float2(w[0], w[1]), W1 = make_float2(w[2], w[3]), W2 = make_float2(w[4], w[5]);
@@ -870,6 +934,9 @@ score_multi_fast_kernel(MultiSrc src, int npairs_pad, int pairs_per_cta, const H
           any = any || (fabsf(val[mod][uu]) <= bnd[mod][uu]);
         }
       }
+      // (Two warp-cooperative variants of this slow path — a warp-uniform vote + ballots into per-warp sub-segments, and
+      // ballot aggregation among the branching lanes with a shared-memory warp counter — were measured in round 2 and
+      // were slower for the 2-D kinds: the vote sits in the fast path, the counter adds two shared-memory round trips.)
       if (any) {  // one reservation for all borderline values of this thread's unit
         unsigned int nb = 0;
 #pragma unroll
@@ -925,6 +992,7 @@ score_multi_fast_kernel(MultiSrc src, int npairs_pad, int pairs_per_cta, const H
         const bool in_smem = 4 * qd + 4 <= cnt4;
         float vxc[12];  // camera points of the 4 correspondences (validity gate / 3-D bound), when the kind needs them
         float wn[4] = {0.f, 0.f, 0.f, 0.f};  // |x_w|
+        float vnw[12];                       // world normals of the 4 correspondences (kinds with the normal test)
 #pragma unroll
         for (int a = 0; a < NRAW; ++a) {
           const bool is_extra = a >= NREC;
@@ -970,6 +1038,10 @@ score_multi_fast_kernel(MultiSrc src, int npairs_pad, int pairs_per_cta, const H
               }
             }
           }
+          if (is_nw) {
+#pragma unroll
+            for (int i = 0; i < 12; ++i) vnw[i] = v[i];
+          }
           if (is_nc) {
             // the normal test sits inside `if (adapter.isValid(c))` (AbsoluteOrientationNormal.hpp:246,323,398): an
             // all-NaN camera point must never cast a normal vote -> poison its camera normal (x_c precedes n_c in NRAW order
@@ -980,8 +1052,22 @@ score_multi_fast_kernel(MultiSrc src, int npairs_pad, int pairs_per_cta, const H
                 if (!(vxc[3 * j] == vxc[3 * j] || vxc[3 * j + 1] == vxc[3 * j + 1] || vxc[3 * j + 2] == vxc[3 * j + 2]))
                   v[3 * j] = v[3 * j + 1] = v[3 * j + 2] = CUDART_NAN_F;
             }
+            // the nine products n_c,i n_w,j of every correspondence replace n_w and n_c in the record
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const int pr = 2 * qd + h;
+              if (pr < tp) {
+                float2* dst = reinterpret_cast<float2*>(recs + (size_t)pr * (F4 * 4) + KT::off_nw);
+                const float* c0p = v + 6 * h;      // n_c of correspondences 4 qd + 2h, + 1
+                const float* w0p = vnw + 6 * h;    // n_w of the same two
+#pragma unroll
+                for (int i = 0; i < 3; ++i)
+#pragma unroll
+                  for (int j = 0; j < 3; ++j) dst[3 * i + j] = make_float2(__fmul_rn(c0p[i], w0p[j]), __fmul_rn(c0p[3 + i], w0p[3 + j]));
+              }
+            }
           }
-          if (!is_extra) {
+          if (!is_extra && !is_nw && !is_nc) {
 #pragma unroll
             for (int h = 0; h < 2; ++h) {  // record 2 qd + h = correspondences 4 qd + 2h, 4 qd + 2h + 1
               const int pr = 2 * qd + h;
@@ -1001,8 +1087,9 @@ score_multi_fast_kernel(MultiSrc src, int npairs_pad, int pairs_per_cta, const H
             if (!(vxc[3 * j] == vxc[3 * j] || vxc[3 * j + 1] == vxc[3 * j + 1] || vxc[3 * j + 2] == vxc[3 * j + 2])) {
               const int pr = 2 * qd + (j >> 1);
               if (pr < tp) {
-                float* e = recs + (size_t)pr * (F4 * 4) + 6 * (NREC - 1) + (j & 1);
-                e[0] = e[2] = e[4] = CUDART_NAN_F;
+                float* e = recs + (size_t)pr * (F4 * 4) + KT::off_nw + (j & 1);
+#pragma unroll
+                for (int q9 = 0; q9 < 9; ++q9) e[2 * q9] = CUDART_NAN_F;
               }
             }
         }
@@ -1116,7 +1203,7 @@ static int launch_multi_t(const FrameView& f, const HypGen* gen, const HypFast* 
     for (; c < 5; ++c) src.a[c] = nullptr;
   }
   if (frame_raw_ok(f, KIND)) {  // stream the caller's arrays: no packed copy
-    const size_t rsmem = (size_t)RTILE * F4 * sizeof(float4) + 2 * (size_t)NRAW * RTILE * 6 * sizeof(float) + 2 * sizeof(uint64_t) + 32;
+    const size_t rsmem = (size_t)RTILE * KT::f4raw * sizeof(float4) + 2 * (size_t)NRAW * RTILE * 6 * sizeof(float) + 2 * sizeof(uint64_t) + 32;
     static std::atomic<bool> rattr_set[64];
     if (dev >= 0 && dev < 64 && !rattr_set[dev].load(std::memory_order_acquire)) {
       cudaFuncSetAttribute(score_multi_fast_kernel<KIND, RTILE, THREADS, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem);
@@ -1192,7 +1279,8 @@ static int launch_variant(const FrameView& f, const HypGen* gen, const HypFast* 
   cudaGetDevice(&dev);
   if (PACKED && frame_raw_ok(f, 2)) {  // stream the caller's arrays: no packed copy
     constexpr int RT = (TILE > 1024 / MINB ? 1024 / MINB : TILE);  // 144 bytes of shared memory per pair and CTA
-    auto rk = score3d_raw_kernel<HPT, RT, THREADS, MINB, SUB>;
+    static const bool pcount = getenv("RPE_PCOUNT") ? getenv("RPE_PCOUNT")[0] != '0' : true;  // packed sign count (1 % faster, r02d)
+    auto rk = pcount ? score3d_raw_kernel<HPT, RT, THREADS, MINB, SUB, true> : score3d_raw_kernel<HPT, RT, THREADS, MINB, SUB, false>;
     size_t rsmem = (size_t)RT * 3 * sizeof(float4) + 4 * (size_t)RT * 6 * sizeof(float) + 2 * sizeof(uint64_t) + 16;
     if (MINB == 1 && g_exclusive_sm && rsmem < (size_t)116 * 1024) rsmem = (size_t)116 * 1024;
     static std::atomic<bool> rattr_set[64];
@@ -1329,7 +1417,9 @@ void launch_consume_worklist(FrameStats* st, cudaStream_t s) { consume_worklist_
 void launch_fixup(int method, const FrameView& f, const HypGen* gen, Thresh th, int32_t* votes, FrameStats* st,
                   Worklist wl, int nseg, int slot_begin, int slot_end, cudaStream_t s) {
   if (nseg <= 0) return;
-  fixup_kernel<<<dim3(nseg, kFixupChunks), 256, 0, s>>>(method, f, gen, th, votes, st, wl, nseg, slot_begin, slot_end);
+  // per-warp segments (2-D kinds) are 8-16 times smaller than per-CTA ones: one CTA each is enough
+  fixup_kernel<<<dim3(nseg, nseg > 1024 ? 1 : kFixupChunks), 256, 0, s>>>(method, f, gen, th, votes, st, wl, nseg, slot_begin,
+                                                                          slot_end);
 }
 
 // Whole-frame exact scoring. Thread <-> slot, CTA column <-> correspondence slice; every lane reads the
