@@ -116,6 +116,7 @@ _sig("rpe_sim_kinect_2d_3d_nl_device", C.c_int, [_vp, C.c_uint64, _vp, _vp, C.c_
 _sig("rpe_sim_kinect_2d_3d_nl", C.c_int, [C.c_uint64, _vp, _vp, C.c_int] + [C.c_float] * 8 + [_vp] * 6)
 _sig("rpe_set_first_pass_iters", C.c_int, [_vp, C.c_int])
 _sig("rpe_set_stale_sample_columns", C.c_int, [_vp, C.c_int])
+_sig("rpe_set_upload_overlap", C.c_int, [_vp, C.c_int])
 _sig("rpe_peer_export", C.c_int, [_vp, _vp])
 _sig("rpe_peer_import", C.c_int, [_vp, C.c_int, C.c_int, _vp])
 _sig("rpe_peer_import_local", C.c_int, [_vp, C.c_int, C.c_int, _vp])
@@ -193,7 +194,7 @@ _sig("rpe_debug_set_raw_tiles", C.c_int, [C.c_int])
 DECLARED_SYMBOLS = [
     "rpe_version", "rpe_status_string", "rpe_device_count", "rpe_create", "rpe_create_on_stream", "rpe_destroy",
     "rpe_last_error", "rpe_stream", "rpe_sync", "rpe_launch_count", "rpe_host_alloc", "rpe_host_free", "rpe_upload",
-    "rpe_upload_device", "rpe_num_correspondences", "rpe_ransac", "rpe_ransac_async", "rpe_ransac_stream", "rpe_set_first_pass_iters", "rpe_set_stale_sample_columns", "rpe_upload_f64", "rpe_ransac_f64", "rpe_get_hypotheses_f64", "rpe_refit", "rpe_refit_async",
+    "rpe_upload_device", "rpe_num_correspondences", "rpe_ransac", "rpe_ransac_async", "rpe_ransac_stream", "rpe_set_first_pass_iters", "rpe_set_stale_sample_columns", "rpe_set_upload_overlap", "rpe_upload_f64", "rpe_ransac_f64", "rpe_get_hypotheses_f64", "rpe_refit", "rpe_refit_async",
     "rpe_set_pose", "rpe_set_mask", "rpe_generate", "rpe_get_hypotheses", "rpe_set_hypotheses", "rpe_score",
     "rpe_get_votes", "rpe_set_votes", "rpe_votes_device_ptr", "rpe_peer_export", "rpe_peer_import", "rpe_peer_import_local", "rpe_exchange_votes", "rpe_peer_status", "rpe_peer_set_timeout_ms", "rpe_ransac_sharded", "rpe_ransac_sharded_async", "rpe_finish", "rpe_update_num_iters", "rpe_sample_table",
     "rpe_prosac_table", "rpe_sampler_create", "rpe_sampler_rows", "rpe_sampler_destroy", "rpe_sim_pose", "rpe_sim_3d_3d", "rpe_sim_2d_3d", "rpe_sim_2d_3d_nl", "rpe_sim_kinect_2d_3d_nl", "rpe_sim_kinect_2d_3d_nl_device", "rpe_sim_3d_3d_device",
@@ -689,6 +690,10 @@ class Context:
     def set_stale_sample_columns(self, on=True):
         """Opt-in reproduction of the reference's stale sample columns (rpe_set_stale_sample_columns)."""
         _check(lib.rpe_set_stale_sample_columns(self._h, 1 if on else 0), self._h)
+
+    def set_upload_overlap(self, chunks=4):
+        """Overlap the upload of page-locked frames with generation + scoring (rpe_set_upload_overlap); 0 = off."""
+        _check(lib.rpe_set_upload_overlap(self._h, int(chunks)), self._h)
 
     def set_first_pass_iters(self, iters):
         _check(lib.rpe_set_first_pass_iters(self._h, iters), self._h)

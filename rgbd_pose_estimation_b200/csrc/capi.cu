@@ -17,6 +17,7 @@
 #include "kernels.cuh"
 
 namespace rpe {
+int score_variant();
 void set_use_packed(bool v);
 bool use_packed();
 void set_score_variant(int v);
@@ -71,6 +72,17 @@ struct rpe_ctx {
   ReplayOut* h_pose = nullptr;    // pinned, kNumStaging slots; [0] doubles as scratch for set_pose
   bool kabsch_valid = false;
   bool suff_valid = false;  // rb.suff matches the inlier columns in d_mask
+  // overlap of the host-to-device upload with generation and scoring (rpe_set_upload_overlap; 3-D / 3-D family,
+  // page-locked host arrays): the frame is copied in chunks on copy_stream, the generator reads its sample points
+  // straight from the page-locked host arrays, the scorer is launched once per chunk as the chunk lands
+  static constexpr int kMaxChunks = 8;
+  int overlap_chunks = 0;          // 0 = off
+  cudaStream_t copy_stream = nullptr, early_stream = nullptr;
+  cudaEvent_t ev_chunk[kMaxChunks] = {};
+  cudaEvent_t ev_prev = nullptr, ev_early = nullptr;
+  bool chunked = false;            // the current frame was uploaded in chunks and no estimator call has consumed it yet
+  int n_chunks = 0, chunk_corr = 0;
+  const float* host_view[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // device-visible addresses of the host arrays
   bool stale_cols = false;       // rpe_set_stale_sample_columns
   int32_t* d_stale_eff = nullptr;  // [cap_stale x 2] effective camera-side sample indices of the current pass
   int32_t* d_stale_carry = nullptr;
@@ -169,6 +181,7 @@ int fail(rpe_ctx* c, int code, const char* what, cudaError_t e = cudaSuccess) {
 void leave_f64_mode(rpe_ctx* c) {
   c->f64 = false;
   for (int k = 0; k < 5; ++k) c->view64[k] = nullptr;
+  c->chunked = false;  // (rpe_upload sets it again after this call when it copies in chunks)
 }
 
 int kind_for_method(int method) {
@@ -746,6 +759,70 @@ int do_ransac(rpe_ctx* ctx, int method, const int32_t* samples, rpe_sample_fn fn
     if (pe != cudaSuccess) (void)cudaGetLastError();
     samples_on_device = pe == cudaSuccess && (attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged);
   }
+  const bool single = H <= ctx->first_pass;
+  // ---- upload still in flight (rpe_set_upload_overlap): generate from the page-locked host arrays and score chunk by chunk
+  if (ctx->chunked) {
+    ctx->chunked = false;  // one estimator call per upload runs ahead of it (a second one would race the first one's tail)
+    ScorerLane* lane = lane_for(ctx);
+    FrameView fv = make_view(ctx);
+    if (method == RPE_SHINJI && single && !fn && H * S > 512 && lane && frame_raw_ok(fv, 2) && !ctx->timing && !ctx->timing_fast &&
+        !ctx->stale_cols && ctx->wl_want <= ctx->wl_allocated && rpe::score_variant() == rpe::kDefaultScoreVariant) {
+      cudaStream_t es = ctx->early_stream;
+      CK(cudaStreamWaitEvent(es, ctx->ev_prev, 0));  // after everything that was enqueued before the upload
+      if (!ctx->stats_clean) {  // (the context's own stream is already parked behind the upload)
+        launch_reset_stats(ctx->d_stats, es);
+        ctx->launches++;
+      }
+      const int32_t* samples_dev = samples;
+      if (!samples_on_device) {
+        CK(cudaMemcpyAsync(ctx->d_samples, samples, (size_t)H * 4 * sizeof(int32_t), cudaMemcpyHostToDevice, es));
+        samples_dev = ctx->d_samples;
+      }
+      const int C = ctx->n_chunks;
+      const unsigned int seg_cap = ctx->wl.capacity / (unsigned int)(C * ctx->num_sms);
+      CK(cudaMemsetAsync(ctx->wl.counts, 0, (size_t)C * ctx->num_sms * sizeof(unsigned int), es));
+      FrameView fh = fv;  // the generator reads its 3 H sample points over PCIe from the host arrays
+      fh.xw = ctx->host_view[A_XW];
+      fh.xc = ctx->host_view[A_XC];
+      launch_hypgen(method, fh, samples_dev, H, ctx->d_gen, ctx->d_fast, ctx->d_votes, ctx->d_stats, es);
+      ctx->launches++;
+      ctx->n_slots = H * S;
+      ctx->cur_method = method;
+      CK(cudaEventRecord(ctx->ev_early, es));
+      {
+        std::lock_guard<std::mutex> g(lane->mu);
+        CK(cudaStreamWaitEvent(lane->stream, ctx->ev_early, 0));
+        for (int c = 0; c < C; ++c) {
+          const int c0 = c * ctx->chunk_corr;
+          const int cnt = (ctx->n - c0) < ctx->chunk_corr ? (ctx->n - c0) : ctx->chunk_corr;
+          CK(cudaStreamWaitEvent(lane->stream, ctx->ev_chunk[c], 0));
+          FrameView fc = fv;
+          fc.xw = fv.xw + 3 * (size_t)c0;
+          fc.xc = fv.xc + 3 * (size_t)c0;
+          fc.n = cnt;
+          const int npairs = (cnt + 1) / 2;
+          fc.npairs_pad = ((npairs + kSubPairs - 1) / kSubPairs) * kSubPairs;
+          Worklist wc = ctx->wl;
+          wc.entries = ctx->wl.entries + (size_t)c * ctx->num_sms * seg_cap;
+          wc.counts = ctx->wl.counts + (size_t)c * ctx->num_sms;
+          launch_score_fast(method, fc, ctx->d_gen, ctx->d_fast, 0, H * S, th, ctx->d_votes, ctx->d_stats, wc, ctx->num_sms,
+                            lane->stream, c0, seg_cap);
+          ctx->launches++;
+        }
+        CK(cudaEventRecord(ctx->ev_lane[1], lane->stream));
+      }
+      CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_lane[1], 0));
+      Worklist wall = ctx->wl;
+      wall.capacity = seg_cap * (unsigned int)(C * ctx->num_sms);
+      launch_fixup(method, fv, ctx->d_gen, th, ctx->d_votes, ctx->d_stats, wall, C * ctx->num_sms, 0, H * S, ctx->stream);
+      launch_score_exact(method, fv, ctx->d_gen, 0, H * S, th, ctx->d_votes, ctx->d_stats, true, ctx->num_sms, ctx->stream);
+      launch_replay(method, ctx->d_gen, ctx->d_votes, H, 0, ctx->n, confidence, ctx->d_stats, ctx->d_rs, ctx->d_pose, true, H,
+                    ctx->stream);
+      ctx->launches += 3;
+      ctx->stats_clean = true;
+      return do_finish(ctx, method, th, out, mask, blocking);
+    }
+  }
   if (!ctx->stats_clean) {
     launch_reset_stats(ctx->d_stats, ctx->stream);
     ctx->launches++;
@@ -754,7 +831,6 @@ int do_ransac(rpe_ctx* ctx, int method, const int32_t* samples, rpe_sample_fn fn
     rc = ensure_packed(ctx, kind_for_method(method));
     if (rc) return rc;
   }
-  const bool single = H <= ctx->first_pass;
   int pass = single ? H : ctx->first_pass;
   for (int base = 0; base < H; base += pass, pass = (2 * pass < kMaxPassIters ? 2 * pass : kMaxPassIters)) {
     const int hc = (H - base) < pass ? (H - base) : pass;
@@ -902,6 +978,12 @@ static int create_common(int device, void* stream, bool own, rpe_ctx** out) {
     ok = ok && cudaEventCreateWithFlags(&ctx->ev_slot[k], cudaEventDisableTiming) == cudaSuccess;
   for (int k = 0; k < 2 && ok; ++k)
     ok = ok && cudaEventCreateWithFlags(&ctx->ev_lane[k], cudaEventDisableTiming) == cudaSuccess;
+  for (int k = 0; k < rpe_ctx::kMaxChunks && ok; ++k)
+    ok = ok && cudaEventCreateWithFlags(&ctx->ev_chunk[k], cudaEventDisableTiming) == cudaSuccess;
+  ok = ok && cudaEventCreateWithFlags(&ctx->ev_prev, cudaEventDisableTiming) == cudaSuccess;
+  ok = ok && cudaEventCreateWithFlags(&ctx->ev_early, cudaEventDisableTiming) == cudaSuccess;
+  ok = ok && cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
+  ok = ok && cudaStreamCreateWithFlags(&ctx->early_stream, cudaStreamNonBlocking) == cudaSuccess;
   ctx->ev_ok = ok;
   if (!ok) {
     rpe_destroy(ctx);
@@ -974,6 +1056,14 @@ int rpe_destroy(rpe_ctx* ctx) {
     if (ctx->ev_slot[k]) cudaEventDestroy(ctx->ev_slot[k]);
   for (int k = 0; k < 2; ++k)
     if (ctx->ev_lane[k]) cudaEventDestroy(ctx->ev_lane[k]);
+  if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+  if (ctx->early_stream) cudaStreamSynchronize(ctx->early_stream);
+  for (int k = 0; k < rpe_ctx::kMaxChunks; ++k)
+    if (ctx->ev_chunk[k]) cudaEventDestroy(ctx->ev_chunk[k]);
+  if (ctx->ev_prev) cudaEventDestroy(ctx->ev_prev);
+  if (ctx->ev_early) cudaEventDestroy(ctx->ev_early);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  if (ctx->early_stream) cudaStreamDestroy(ctx->early_stream);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
   (void)cudaGetLastError();
   delete ctx;
@@ -1012,16 +1102,55 @@ static int upload_common(rpe_ctx* ctx, const float* const src[5], int n, bool fr
   int rc = ensure_corr_capacity(ctx, n, !from_device);
   if (rc) return rc;
   ctx->n = n;
-  for (int k = 0; k < 5; ++k) {
-    if (!src[k]) {
-      ctx->view[k] = nullptr;
-      continue;
+  bool chunked = false;
+  if (!from_device && ctx->overlap_chunks >= 2 && n >= 65536 && src[A_XC] && !src[A_BV] && !src[A_NC] && !src[A_NW]) {
+    // page-locked (and device-visible) host arrays?
+    chunked = true;
+    for (int k = 0; k < 5 && chunked; ++k) {
+      if (!src[k]) continue;
+      cudaPointerAttributes attr;
+      if (cudaPointerGetAttributes(&attr, src[k]) != cudaSuccess) {
+        (void)cudaGetLastError();
+        chunked = false;
+      } else if (attr.type != cudaMemoryTypeHost || !attr.devicePointer) {
+        chunked = false;
+      } else {
+        ctx->host_view[k] = static_cast<const float*>(attr.devicePointer);
+      }
     }
-    if (from_device) {
-      ctx->view[k] = src[k];
-    } else {
-      CK(cudaMemcpyAsync(ctx->d_raw[k], src[k], (size_t)n * 3 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
-      ctx->view[k] = ctx->d_raw[k];
+  }
+  if (chunked) {
+    const int C = ctx->overlap_chunks;
+    const int cs = (((n + C - 1) / C) + 1023) & ~1023;  // whole scorer stages; 16-byte aligned chunk starts
+    ctx->chunk_corr = cs;
+    ctx->n_chunks = (n + cs - 1) / cs;
+    // the copies may overwrite the arrays only after everything enqueued so far has read them
+    CK(cudaEventRecord(ctx->ev_prev, ctx->stream));
+    CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_prev, 0));
+    for (int c = 0; c < ctx->n_chunks; ++c) {
+      const size_t c0 = (size_t)c * cs, cnt = (size_t)((n - (int)c0) < cs ? (n - (int)c0) : cs);
+      for (int k = 0; k < 5; ++k)
+        if (src[k])
+          CK(cudaMemcpyAsync(ctx->d_raw[k] + 3 * c0, src[k] + 3 * c0, cnt * 3 * sizeof(float), cudaMemcpyHostToDevice,
+                             ctx->copy_stream));
+      CK(cudaEventRecord(ctx->ev_chunk[c], ctx->copy_stream));
+    }
+    // everything on the context's stream sees the whole frame; only the early part of the next estimator call
+    // (generation + chunk-wise scoring, on early_stream / the scorer lane) runs ahead of it
+    CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_chunk[ctx->n_chunks - 1], 0));
+    for (int k = 0; k < 5; ++k) ctx->view[k] = src[k] ? ctx->d_raw[k] : nullptr;
+  } else {
+    for (int k = 0; k < 5; ++k) {
+      if (!src[k]) {
+        ctx->view[k] = nullptr;
+        continue;
+      }
+      if (from_device) {
+        ctx->view[k] = src[k];
+      } else {
+        CK(cudaMemcpyAsync(ctx->d_raw[k], src[k], (size_t)n * 3 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+        ctx->view[k] = ctx->d_raw[k];
+      }
     }
   }
   ctx->pk_kind = -1;
@@ -1029,6 +1158,7 @@ static int upload_common(rpe_ctx* ctx, const float* const src[5], int n, bool fr
   ctx->suff_valid = false;
   ctx->n_slots = 0;
   leave_f64_mode(ctx);
+  ctx->chunked = chunked;
   return RPE_OK;
 }
 
@@ -1054,6 +1184,11 @@ int rpe_ransac(rpe_ctx* ctx, int method, const int32_t* samples, int H, float th
 int rpe_ransac_async(rpe_ctx* ctx, int method, const int32_t* samples, int H, float thr3d, float cos_thr2d,
                      float cos_thrN, float confidence, rpe_result* out, int16_t* mask) {
   return do_ransac(ctx, method, samples, nullptr, nullptr, H, thr3d, cos_thr2d, cos_thrN, confidence, out, mask, false);
+}
+int rpe_set_upload_overlap(rpe_ctx* ctx, int chunks) {
+  if (!ctx || chunks < 0) return RPE_ERR_ARG;
+  ctx->overlap_chunks = chunks < 2 ? 0 : (chunks > rpe_ctx::kMaxChunks ? rpe_ctx::kMaxChunks : chunks);
+  return RPE_OK;
 }
 int rpe_set_stale_sample_columns(rpe_ctx* ctx, int on) {
   if (!ctx) return RPE_ERR_ARG;
@@ -1110,6 +1245,7 @@ int rpe_upload_f64(rpe_ctx* ctx, const double* bv, const double* xc, const doubl
   ctx->suff_valid = false;
   ctx->n_slots = 0;
   ctx->f64 = true;
+  ctx->chunked = false;
   return RPE_OK;
 }
 int rpe_get_hypotheses_f64(rpe_ctx* ctx, int n_slots, double* hyps7, int32_t* valid) {

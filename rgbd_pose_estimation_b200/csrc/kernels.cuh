@@ -68,8 +68,12 @@ void launch_minsolv_ev(const float* M9, int count, float* E3, cudaStream_t s);
 void launch_minsolv_ms(const float* in24, int count, float* q4, float* t3, cudaStream_t s);
 
 // -- scoring -------------------------------------------------------------------------------------
+// corr_base / seg_cap (3-D raw-array scorer only): a launch may score ONE CHUNK of a frame that is still being uploaded
+// — f then views the chunk, corr_base is the frame index of its first correspondence and seg_cap fixes the size of a
+// worklist segment so that the launches of all chunks fill consecutive parts of one list (wl points at this chunk's part).
 int launch_score_fast(int method, const FrameView& f, const HypGen* gen, const HypFast* fast, int slot_begin,
-                       int slot_end, Thresh th, int32_t* votes, FrameStats* st, Worklist wl, int num_sms, cudaStream_t s);
+                       int slot_end, Thresh th, int32_t* votes, FrameStats* st, Worklist wl, int num_sms, cudaStream_t s,
+                       int corr_base = 0, unsigned int seg_cap = 0);
 void launch_fixup(int method, const FrameView& f, const HypGen* gen, Thresh th, int32_t* votes, FrameStats* st,
                   Worklist wl, int nseg, int slot_begin, int slot_end, cudaStream_t s);
 void launch_consume_worklist(FrameStats* st, cudaStream_t s);

@@ -464,7 +464,8 @@ template <int HPT, int TILE, int THREADS, int MINB, int SUB, bool PCOUNT>
 __global__ void __launch_bounds__(THREADS, MINB)
 score3d_raw_kernel(const float* __restrict__ xw, const float* __restrict__ xc, int n, int npairs_pad, int pairs_per_cta,
                    const HypFast* __restrict__ fast, const HypGen* __restrict__ gen, int slot_begin, int slot_end, float thr,
-                   int32_t* __restrict__ votes, FrameStats* __restrict__ st, Worklist wl) {
+                   int32_t* __restrict__ votes, FrameStats* __restrict__ st, Worklist wl, int corr_base) {
+  // corr_base: index, in the whole frame, of the first correspondence of xw / xc (a launch may score one uploaded chunk)
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr int kStageFloats = TILE * 2 * 3;  // floats of one array in one stage
   float4* packed = reinterpret_cast<float4*>(smem_raw);                                  // [TILE * 3]
@@ -646,7 +647,7 @@ score3d_raw_kernel(const float* __restrict__ xw, const float* __restrict__ xc, i
             for (int u = 0; u < 2; ++u) {
               if (fabsf(sv[u]) <= band[k]) {
                 cnt[k] -= (int)(__float_as_uint(sv[u]) >> 31);  // (the packed accumulator is folded into cnt per stage)
-                const unsigned int corr = (unsigned int)(2 * (p_begin + t * TILE + sub + pp) + u);
+                const unsigned int corr = (unsigned int)(corr_base + 2 * (p_begin + t * TILE + sub + pp) + u);
                 seg.push(make_uint2((unsigned int)slot[k], corr | (1u << 30)), st);
               }
             }
@@ -1252,13 +1253,15 @@ static int g_variant = 14;  // HPT=2, 1024-pair stages, 512 threads, 1 CTA per S
 void set_use_packed(bool v) { g_use_packed = v; }
 bool use_packed() { return g_use_packed; }
 void set_score_variant(int v) { g_variant = v; }
+int score_variant() { return g_variant; }
 
 // RPE_SCORER_SHARED_SM=1 in the environment lets two scorer CTAs share an SM (measurement aid)
 static int g_exclusive_sm = getenv("RPE_SCORER_SHARED_SM") ? 0 : 1;
 
 template <bool PACKED, int HPT, int TILE, int THREADS, int MINB, int SUB>
 static int launch_variant(const FrameView& f, const HypGen* gen, const HypFast* fast, int slot_begin, int slot_end,
-                           Thresh th, int32_t* votes, FrameStats* st, Worklist wl, int num_sms, cudaStream_t s) {
+                           Thresh th, int32_t* votes, FrameStats* st, Worklist wl, int num_sms, cudaStream_t s,
+                           int corr_base, unsigned int seg_cap) {
   const int nslots = slot_end - slot_begin;
   const int hyp_per_cta = THREADS * HPT;
   const int gy = (nslots + hyp_per_cta - 1) / hyp_per_cta;
@@ -1288,8 +1291,10 @@ static int launch_variant(const FrameView& f, const HypGen* gen, const HypFast* 
       cudaFuncSetAttribute(rk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem);
       rattr_set[dev].store(true, std::memory_order_release);
     }
+    if (seg_cap) wl.capacity = seg_cap * (unsigned int)(gx * gy);  // fixed segment size (chunked frames share one list;
+                                                                   // the caller provides room for num_sms segments per chunk: gx * gy <= num_sms with MINB = 1)
     rk<<<dim3(gx, gy), THREADS, rsmem, s>>>(f.xw, f.xc, f.n, f.npairs_pad, pairs_per_cta, fast, gen, slot_begin, slot_end,
-                                            th.thr3d, votes, st, wl);
+                                            th.thr3d, votes, st, wl, corr_base);
     return gx * gy;
   }
   auto kern = score3d_fast_kernel<PACKED, HPT, TILE, THREADS, MINB, SUB>;
@@ -1305,7 +1310,7 @@ static int launch_variant(const FrameView& f, const HypGen* gen, const HypFast* 
 
 int launch_score_fast(int method, const FrameView& f, const HypGen* gen, const HypFast* fast, int slot_begin,
                       int slot_end, Thresh th, int32_t* votes, FrameStats* st, Worklist wl, int num_sms,
-                      cudaStream_t s) {
+                      cudaStream_t s, int corr_base, unsigned int seg_cap) {
   if (slot_end - slot_begin <= 0 || f.n <= 0) return 0;
   if (method != RPE_SHINJI) {
     const int kind = (method_uses_2d(method) ? 1 : 0) | (method_uses_3d(method) ? 2 : 0) | (method_uses_nl(method) ? 4 : 0);
@@ -1319,7 +1324,7 @@ int launch_score_fast(int method, const FrameView& f, const HypGen* gen, const H
       default: return 0;
     }
   }
-#define RPE_V(P, H, T, TH, MB, SB) return launch_variant<P, H, T, TH, MB, SB>(f, gen, fast, slot_begin, slot_end, th, votes, st, wl, num_sms, s)
+#define RPE_V(P, H, T, TH, MB, SB) return launch_variant<P, H, T, TH, MB, SB>(f, gen, fast, slot_begin, slot_end, th, votes, st, wl, num_sms, s, corr_base, seg_cap)
   if (!g_use_packed) {
     RPE_V(false, 2, 256, 256, 2, 8);
   }
