@@ -80,6 +80,11 @@ struct rpe_ctx {
   cudaStream_t copy_stream = nullptr, early_stream = nullptr;
   cudaEvent_t ev_chunk[kMaxChunks] = {};
   cudaEvent_t ev_prev = nullptr, ev_early = nullptr;
+  // the inlier mask (1.2 MB for a dense frame) goes back on its own stream so that the refits enqueued behind the RANSAC
+  // do not wait for it (own streams only; with a borrowed stream the caller synchronises that stream and nothing else)
+  cudaStream_t d2h_stream = nullptr;
+  cudaEvent_t ev_mask_ready = nullptr, ev_mask_copied = nullptr;
+  bool mask_copy_pending = false;
   bool chunked = false;            // the current frame was uploaded in chunks and no estimator call has consumed it yet
   int n_chunks = 0, chunk_corr = 0;
   const float* host_view[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // device-visible addresses of the host arrays
@@ -192,6 +197,20 @@ int f4_per_pair(int kind) {
   return (arrays * 6 + 3) / 4;
 }
 bool method_ok(int m) { return m >= RPE_SHINJI && m <= RPE_KNEIP_QUAT; }
+
+// host-side wait for everything the context has enqueued, including a mask copy on the side stream
+cudaError_t sync_stream(rpe_ctx* ctx) {
+  cudaError_t e = cudaStreamSynchronize(ctx->stream);
+  if (e == cudaSuccess && ctx->mask_copy_pending) {
+    e = cudaEventSynchronize(ctx->ev_mask_copied);
+    ctx->mask_copy_pending = false;
+  }
+  return e;
+}
+// stream-side: whoever overwrites d_mask next waits for the copy of the previous mask
+void order_after_mask_copy(rpe_ctx* ctx) {
+  if (ctx->mask_copy_pending) cudaStreamWaitEvent(ctx->stream, ctx->ev_mask_copied, 0);
+}
 
 int check_arrays(rpe_ctx* ctx, int method) {
   if (ctx->n <= 0) return fail(ctx, RPE_ERR_STATE, "no correspondences uploaded");
@@ -477,7 +496,7 @@ int alloc_worklist(rpe_ctx* ctx, unsigned int entries) {
 }
 int grow_worklist(rpe_ctx* ctx) {
   if (ctx->wl_fixed || ctx->wl_want <= ctx->wl_allocated) return RPE_OK;
-  CK(cudaStreamSynchronize(ctx->stream));  // kernels in flight may still read the old list
+  CK(sync_stream(ctx));  // kernels in flight may still read the old list
   finish_pending(ctx);
   return alloc_worklist(ctx, ctx->wl_want);
 }
@@ -558,6 +577,7 @@ int do_finish(rpe_ctx* ctx, int method, Thresh th, rpe_result* out, int16_t* mas
   FrameView f = make_view(ctx);
   stamp(ctx, ST_MASK);
   ctx->mask_cols = method_mask_cols(method);
+  order_after_mask_copy(ctx);
   launch_mask(method, f, ctx->d_pose, th, ctx->d_mask, ctx->d_kabsch, ctx->rb, ctx->d_stats, ctx->stream);
   ctx->launches += 1;
   ctx->kabsch_valid = method_uses_3d(method);
@@ -568,12 +588,23 @@ int do_finish(rpe_ctx* ctx, int method, Thresh th, rpe_result* out, int16_t* mas
   int rc = claim_slot(ctx, &slot);
   if (rc) return rc;
   CK(cudaMemcpyAsync(&ctx->h_pose[slot], ctx->d_pose, sizeof(ReplayOut), cudaMemcpyDeviceToHost, ctx->stream));
-  if (mask)
-    CK(cudaMemcpyAsync(mask, ctx->d_mask, (size_t)ctx->n * ctx->mask_cols * sizeof(int16_t), cudaMemcpyDeviceToHost,
-                       ctx->stream));
+  if (mask) {
+    const size_t bytes = (size_t)ctx->n * ctx->mask_cols * sizeof(int16_t);
+    if (ctx->d2h_stream && bytes >= (size_t)256 * 1024) {
+      CK(cudaEventRecord(ctx->ev_mask_ready, ctx->stream));
+      CK(cudaStreamWaitEvent(ctx->d2h_stream, ctx->ev_mask_ready, 0));
+      // (one transfer: cutting it into pieces so that the refits' small result copies can slip in between was measured
+      // slower — 0.438 against 0.412 ms per blocking frame, round 2)
+      CK(cudaMemcpyAsync(mask, ctx->d_mask, bytes, cudaMemcpyDeviceToHost, ctx->d2h_stream));
+      CK(cudaEventRecord(ctx->ev_mask_copied, ctx->d2h_stream));
+      ctx->mask_copy_pending = true;
+    } else {
+      CK(cudaMemcpyAsync(mask, ctx->d_mask, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+  }
   if (int rcp = push_pending(ctx, out, slot, false, false)) return rcp;
   if (blocking) {
-    CK(cudaStreamSynchronize(ctx->stream));
+    CK(sync_stream(ctx));
     finish_pending(ctx);
     return check_comm(ctx);
   }
@@ -696,7 +727,7 @@ int do_ransac64(rpe_ctx* ctx, int method, const int32_t* samples, rpe_sample_fn 
     ctx->cur_method = method;
     if (!single) {
       CK(cudaMemcpyAsync(ctx->h_rs64, ctx->d_rs64, sizeof(ReplayState64), cudaMemcpyDeviceToHost, ctx->stream));
-      CK(cudaStreamSynchronize(ctx->stream));
+      CK(sync_stream(ctx));
       if (ctx->h_rs64->stop != 0 || base + hc >= H) {
         launch_replay64(method, ctx->d_gen64, ctx->d_votes, 0, base + hc, ctx->n, confidence, ctx->d_stats, ctx->d_rs64,
                         ctx->d_pose, ctx->d_pose64, true, ctx->stream);
@@ -706,6 +737,7 @@ int do_ransac64(rpe_ctx* ctx, int method, const int32_t* samples, rpe_sample_fn 
     }
   }
   ctx->mask_cols = method_mask_cols(method);
+  order_after_mask_copy(ctx);
   launch_mask64(method, f, ctx->d_pose, ctx->d_pose64, th, ctx->d_mask, ctx->num_sms, ctx->stream);
   ctx->launches++;
   ctx->kabsch_valid = false;  // refits gather their statistics from the float copies when asked
@@ -720,7 +752,7 @@ int do_ransac64(rpe_ctx* ctx, int method, const int32_t* samples, rpe_sample_fn 
     CK(cudaMemcpyAsync(mask, ctx->d_mask, (size_t)ctx->n * ctx->mask_cols * sizeof(int16_t), cudaMemcpyDeviceToHost,
                        ctx->stream));
   if (int rcp = push_pending(ctx, out, slot, false, false)) return rcp;
-  CK(cudaStreamSynchronize(ctx->stream));
+  CK(sync_stream(ctx));
   finish_pending(ctx);
   return RPE_OK;
 }
@@ -863,7 +895,7 @@ int do_ransac(rpe_ctx* ctx, int method, const int32_t* samples, rpe_sample_fn fn
     if (!single) {
       // the caller's Iter exceeds one pass: look at the adaptive bound before generating more hypotheses
       CK(cudaMemcpyAsync(ctx->h_rs, ctx->d_rs, sizeof(ReplayState), cudaMemcpyDeviceToHost, ctx->stream));
-      CK(cudaStreamSynchronize(ctx->stream));
+      CK(sync_stream(ctx));
       const bool last = ctx->h_rs->stop != 0 || base + hc >= H;
       if (last) {
         launch_replay(method, ctx->d_gen, ctx->d_votes, 0, base + hc, ctx->n, confidence, ctx->d_stats, ctx->d_rs,
@@ -984,6 +1016,9 @@ static int create_common(int device, void* stream, bool own, rpe_ctx** out) {
   ok = ok && cudaEventCreateWithFlags(&ctx->ev_early, cudaEventDisableTiming) == cudaSuccess;
   ok = ok && cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
   ok = ok && cudaStreamCreateWithFlags(&ctx->early_stream, cudaStreamNonBlocking) == cudaSuccess;
+  ok = ok && cudaEventCreateWithFlags(&ctx->ev_mask_ready, cudaEventDisableTiming) == cudaSuccess;
+  ok = ok && cudaEventCreateWithFlags(&ctx->ev_mask_copied, cudaEventDisableTiming) == cudaSuccess;
+  if (own) ok = ok && cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking) == cudaSuccess;
   ctx->ev_ok = ok;
   if (!ok) {
     rpe_destroy(ctx);
@@ -1062,6 +1097,12 @@ int rpe_destroy(rpe_ctx* ctx) {
     if (ctx->ev_chunk[k]) cudaEventDestroy(ctx->ev_chunk[k]);
   if (ctx->ev_prev) cudaEventDestroy(ctx->ev_prev);
   if (ctx->ev_early) cudaEventDestroy(ctx->ev_early);
+  if (ctx->d2h_stream) {
+    cudaStreamSynchronize(ctx->d2h_stream);
+    cudaStreamDestroy(ctx->d2h_stream);
+  }
+  if (ctx->ev_mask_ready) cudaEventDestroy(ctx->ev_mask_ready);
+  if (ctx->ev_mask_copied) cudaEventDestroy(ctx->ev_mask_copied);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->early_stream) cudaStreamDestroy(ctx->early_stream);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -1076,7 +1117,7 @@ long long rpe_launch_count(const rpe_ctx* ctx) { return ctx ? ctx->launches : 0;
 
 int rpe_sync(rpe_ctx* ctx) {
   if (!ctx) return RPE_ERR_ARG;
-  CK(cudaStreamSynchronize(ctx->stream));
+  CK(sync_stream(ctx));
   finish_pending(ctx);
   return check_comm(ctx);
 }
@@ -1254,7 +1295,7 @@ int rpe_get_hypotheses_f64(rpe_ctx* ctx, int n_slots, double* hyps7, int32_t* va
   CK(cudaSetDevice(ctx->device));
   std::vector<HypGen64> h((size_t)n_slots);
   CK(cudaMemcpyAsync(h.data(), ctx->d_gen64, (size_t)n_slots * sizeof(HypGen64), cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaStreamSynchronize(ctx->stream));
+  CK(sync_stream(ctx));
   for (int i = 0; i < n_slots; ++i) {
     for (int k = 0; k < 4; ++k) hyps7[7 * (size_t)i + k] = h[i].q[k];
     for (int k = 0; k < 3; ++k) hyps7[7 * (size_t)i + 4 + k] = h[i].t[k];
@@ -1345,7 +1386,7 @@ static int do_refit(rpe_ctx* ctx, int kind, const float* weights, int max_iters,
   CK(cudaMemcpyAsync(&ctx->h_pose[slot], ctx->d_pose, sizeof(ReplayOut), cudaMemcpyDeviceToHost, ctx->stream));
   if (int rcp = push_pending(ctx, out, slot, true, gn)) return rcp;
   if (blocking) {
-    CK(cudaStreamSynchronize(ctx->stream));
+    CK(sync_stream(ctx));
     finish_pending(ctx);
   }
   return RPE_OK;
@@ -1361,7 +1402,7 @@ int rpe_refit_async(rpe_ctx* ctx, int kind, const float* weights, int max_iters,
 int rpe_set_pose(rpe_ctx* ctx, const float q_xyzw[4], const float t[3], int max_votes) {
   if (!ctx || !q_xyzw || !t) return RPE_ERR_ARG;
   CK(cudaSetDevice(ctx->device));
-  CK(cudaStreamSynchronize(ctx->stream));
+  CK(sync_stream(ctx));
   finish_pending(ctx);
   ReplayOut p;
   memset(&p, 0, sizeof(p));
@@ -1371,7 +1412,7 @@ int rpe_set_pose(rpe_ctx* ctx, const float q_xyzw[4], const float t[3], int max_
   p.winner = 0;
   *ctx->h_pose = p;
   CK(cudaMemcpyAsync(ctx->d_pose, ctx->h_pose, sizeof(ReplayOut), cudaMemcpyHostToDevice, ctx->stream));
-  CK(cudaStreamSynchronize(ctx->stream));
+  CK(sync_stream(ctx));
   ctx->kabsch_valid = false;
   return RPE_OK;
 }
@@ -1380,8 +1421,9 @@ int rpe_set_mask(rpe_ctx* ctx, const int16_t* mask, int cols) {
   if (!ctx || !mask || cols < 1 || cols > 3) return RPE_ERR_ARG;
   if (ctx->n <= 0) return fail(ctx, RPE_ERR_STATE, "no correspondences uploaded");
   CK(cudaSetDevice(ctx->device));
+  order_after_mask_copy(ctx);
   CK(cudaMemcpyAsync(ctx->d_mask, mask, (size_t)ctx->n * cols * sizeof(int16_t), cudaMemcpyHostToDevice, ctx->stream));
-  CK(cudaStreamSynchronize(ctx->stream));
+  CK(sync_stream(ctx));
   ctx->mask_cols = cols;
   ctx->kabsch_valid = false;
   ctx->suff_valid = false;
@@ -1419,7 +1461,7 @@ int rpe_get_hypotheses(rpe_ctx* ctx, float* hyps, int32_t* valid, int n_slots) {
   CK(cudaSetDevice(ctx->device));
   std::vector<HypGen> h(n_slots);
   CK(cudaMemcpyAsync(h.data(), ctx->d_gen, (size_t)n_slots * sizeof(HypGen), cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaStreamSynchronize(ctx->stream));
+  CK(sync_stream(ctx));
   for (int i = 0; i < n_slots; ++i) {
     if (hyps) {
       for (int k = 0; k < 4; ++k) hyps[7 * i + k] = h[i].q[k];
@@ -1446,7 +1488,7 @@ int rpe_set_hypotheses(rpe_ctx* ctx, int method, const float* hyps, const int32_
   launch_reset_stats(ctx->d_stats, ctx->stream);
   launch_derive_fast(ctx->d_gen, ctx->d_fast, ctx->d_votes, n_slots, ctx->d_stats, ctx->stream);
   ctx->launches += 2;
-  CK(cudaStreamSynchronize(ctx->stream));
+  CK(sync_stream(ctx));
   ctx->n_slots = n_slots;
   ctx->cur_method = method;
   ctx->stats_clean = false;
@@ -1479,14 +1521,14 @@ int rpe_get_votes(rpe_ctx* ctx, int32_t* votes, int n_slots) {
   if (!ctx || !votes || n_slots <= 0 || n_slots > ctx->n_slots) return RPE_ERR_ARG;
   CK(cudaSetDevice(ctx->device));
   CK(cudaMemcpyAsync(votes, ctx->d_votes, (size_t)n_slots * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaStreamSynchronize(ctx->stream));
+  CK(sync_stream(ctx));
   return RPE_OK;
 }
 int rpe_set_votes(rpe_ctx* ctx, const int32_t* votes, int n_slots) {
   if (!ctx || !votes || n_slots <= 0 || n_slots > ctx->n_slots) return RPE_ERR_ARG;
   CK(cudaSetDevice(ctx->device));
   CK(cudaMemcpyAsync(ctx->d_votes, votes, (size_t)n_slots * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
-  CK(cudaStreamSynchronize(ctx->stream));
+  CK(sync_stream(ctx));
   return RPE_OK;
 }
 int32_t* rpe_votes_device_ptr(rpe_ctx* ctx) { return ctx ? ctx->d_votes : nullptr; }
@@ -1500,7 +1542,7 @@ static int peer_arm(rpe_ctx* ctx) {
     CK(cudaMalloc(&ctx->d_peer_block, kPeerBlockBytes));
     CK(cudaMemset(ctx->d_peer_block, 0, kPeerBlockBytes));
   } else {
-    CK(cudaStreamSynchronize(ctx->stream));
+    CK(sync_stream(ctx));
     CK(cudaMemset(ctx->d_peer_block, 0, kPeerFlagWords * sizeof(unsigned int)));
   }
   if (!ctx->h_peer_err) CK(cudaMallocHost(&ctx->h_peer_err, sizeof(unsigned int)));
@@ -1656,7 +1698,7 @@ int rpe_ransac_sharded_async(rpe_ctx* ctx, int method, const int32_t* samples, i
 int rpe_peer_status(rpe_ctx* ctx) {
   if (!ctx || !ctx->d_peer_block) return RPE_ERR_ARG;
   CK(cudaSetDevice(ctx->device));
-  CK(cudaStreamSynchronize(ctx->stream));
+  CK(sync_stream(ctx));
   return check_comm(ctx);
 }
 
@@ -1801,7 +1843,7 @@ int rpe_download(rpe_ctx* ctx, float* bv, float* xc, float* nc, float* xw, float
       if (!ctx->view[k]) return fail(ctx, RPE_ERR_STATE, "array not present on the device");
       CK(cudaMemcpyAsync(dst[k], ctx->view[k], (size_t)ctx->n * 3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
     }
-  CK(cudaStreamSynchronize(ctx->stream));
+  CK(sync_stream(ctx));
   return RPE_OK;
 }
 
@@ -1825,7 +1867,7 @@ static int minsolv_common(rpe_ctx* ctx, const float* in, int in_stride, int coun
   cudaFreeAsync(d_in, ctx->stream);
   cudaFreeAsync(d_a, ctx->stream);
   if (d_b) cudaFreeAsync(d_b, ctx->stream);
-  CK(cudaStreamSynchronize(ctx->stream));
+  CK(sync_stream(ctx));
   return RPE_OK;
 }
 int rpe_min_ev(rpe_ctx* ctx, const float* M9, int count, float* E3) {
