@@ -85,7 +85,8 @@ struct rpe_ctx {
   cudaStream_t d2h_stream = nullptr;
   cudaEvent_t ev_mask_ready = nullptr, ev_mask_copied = nullptr;
   bool mask_copy_pending = false;
-  bool chunked = false;            // the current frame was uploaded in chunks and no estimator call has consumed it yet
+  bool deferred = false;           // rpe_upload has only taken note of the host arrays: nothing copied yet
+  const float* host_src[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // the caller's page-locked arrays (deferred)
   int n_chunks = 0, chunk_corr = 0;
   const float* host_view[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // device-visible addresses of the host arrays
   bool stale_cols = false;       // rpe_set_stale_sample_columns
@@ -186,7 +187,7 @@ int fail(rpe_ctx* c, int code, const char* what, cudaError_t e = cudaSuccess) {
 void leave_f64_mode(rpe_ctx* c) {
   c->f64 = false;
   for (int k = 0; k < 5; ++k) c->view64[k] = nullptr;
-  c->chunked = false;  // (rpe_upload sets it again after this call when it copies in chunks)
+  c->deferred = false;  // (rpe_upload sets it again after this call when it defers the copies)
 }
 
 int kind_for_method(int method) {
@@ -211,6 +212,23 @@ cudaError_t sync_stream(rpe_ctx* ctx) {
 void order_after_mask_copy(rpe_ctx* ctx) {
   if (ctx->mask_copy_pending) cudaStreamWaitEvent(ctx->stream, ctx->ev_mask_copied, 0);
 }
+
+// A deferred upload (rpe_set_upload_overlap) that the next call cannot overlap with anything is simply carried out now,
+// on the context's stream, the plain way.
+int flush_deferred(rpe_ctx* ctx) {
+  if (!ctx->deferred) return RPE_OK;
+  ctx->deferred = false;
+  for (int k = 0; k < 5; ++k)
+    if (ctx->host_src[k] && ctx->view[k])
+      CK(cudaMemcpyAsync(ctx->d_raw[k], ctx->host_src[k], (size_t)ctx->n * 3 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  return RPE_OK;
+}
+// first thing every entry point that works on the context's frame does
+#define ENTER(ctx)                                     \
+  do {                                                 \
+    CK(cudaSetDevice((ctx)->device));                  \
+    if (int rcf__ = flush_deferred(ctx)) return rcf__; \
+  } while (0)
 
 int check_arrays(rpe_ctx* ctx, int method) {
   if (ctx->n <= 0) return fail(ctx, RPE_ERR_STATE, "no correspondences uploaded");
@@ -637,7 +655,7 @@ int do_ransac64(rpe_ctx* ctx, int method, const int32_t* samples, rpe_sample_fn 
   if (!ctx->f64 || (size_t)ctx->n > ctx->cap_n64) return fail(ctx, RPE_ERR_STATE, "no binary64 arrays of this frame on the device");
   for (int k = 0; k < 5; ++k)
     if (ctx->view[k] && !ctx->view64[k]) return fail(ctx, RPE_ERR_STATE, "binary64 copy of an array is missing");
-  CK(cudaSetDevice(ctx->device));
+  ENTER(ctx);
   const int S = method_slots(method);
   const Thresh64 th = {thr3d, cos_thr2d, cos_thrN};
   const int pass_cap = H < kMaxPassIters ? H : kMaxPassIters;
@@ -792,16 +810,28 @@ int do_ransac(rpe_ctx* ctx, int method, const int32_t* samples, rpe_sample_fn fn
     samples_on_device = pe == cudaSuccess && (attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged);
   }
   const bool single = H <= ctx->first_pass;
-  // ---- upload still in flight (rpe_set_upload_overlap): generate from the page-locked host arrays and score chunk by chunk
-  if (ctx->chunked) {
-    ctx->chunked = false;  // one estimator call per upload runs ahead of it (a second one would race the first one's tail)
+  // ---- deferred upload (rpe_set_upload_overlap): generate from the page-locked host arrays, then copy and score chunk by chunk
+  if (ctx->deferred) {
     ScorerLane* lane = lane_for(ctx);
     FrameView fv = make_view(ctx);
-    if (method == RPE_SHINJI && single && !fn && H * S > 512 && lane && frame_raw_ok(fv, 2) && !ctx->timing && !ctx->timing_fast &&
-        !ctx->stale_cols && ctx->wl_want <= ctx->wl_allocated && rpe::score_variant() == rpe::kDefaultScoreVariant) {
+    if (!(method == RPE_SHINJI && single && !fn && H * S > 512 && lane && frame_raw_ok(fv, 2) && !ctx->timing && !ctx->timing_fast &&
+          !ctx->stale_cols && ctx->wl_want <= ctx->wl_allocated && rpe::score_variant() == rpe::kDefaultScoreVariant)) {
+      if (int rcf = flush_deferred(ctx)) return rcf;
+    } else {
+      ctx->deferred = false;
       cudaStream_t es = ctx->early_stream;
-      CK(cudaStreamWaitEvent(es, ctx->ev_prev, 0));  // after everything that was enqueued before the upload
-      if (!ctx->stats_clean) {  // (the context's own stream is already parked behind the upload)
+      static const bool trace = getenv("RPE_OVERLAP_TRACE") != nullptr;  // debugging aid: device timeline of this path on stderr
+      static thread_local cudaEvent_t tev[24] = {};
+      int ntev = 0;
+      if (trace && !tev[0])
+        for (int i = 0; i < 24; ++i) cudaEventCreate(&tev[i]);
+      auto mark = [&](cudaStream_t st) {
+        if (trace && ntev < 24) cudaEventRecord(tev[ntev++], st);
+      };
+      CK(cudaEventRecord(ctx->ev_prev, ctx->stream));  // everything enqueued so far (it may still read the arrays / the tables)
+      CK(cudaStreamWaitEvent(es, ctx->ev_prev, 0));
+      mark(es);
+      if (!ctx->stats_clean) {
         launch_reset_stats(ctx->d_stats, es);
         ctx->launches++;
       }
@@ -821,6 +851,20 @@ int do_ransac(rpe_ctx* ctx, int method, const int32_t* samples, rpe_sample_fn fn
       ctx->n_slots = H * S;
       ctx->cur_method = method;
       CK(cudaEventRecord(ctx->ev_early, es));
+      mark(es);  // 1: generator done
+      // now the frame: chunk by chunk on the copy stream, behind the generator's reads
+      CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_early, 0));
+      for (int c = 0; c < C; ++c) {
+        const size_t c0 = (size_t)c * ctx->chunk_corr;
+        const size_t cnt = (size_t)((ctx->n - (int)c0) < ctx->chunk_corr ? (ctx->n - (int)c0) : ctx->chunk_corr);
+        for (int k = 0; k < 5; ++k)
+          if (ctx->host_src[k] && ctx->view[k])
+            CK(cudaMemcpyAsync(ctx->d_raw[k] + 3 * c0, ctx->host_src[k] + 3 * c0, cnt * 3 * sizeof(float), cudaMemcpyHostToDevice,
+                               ctx->copy_stream));
+        CK(cudaEventRecord(ctx->ev_chunk[c], ctx->copy_stream));
+        mark(ctx->copy_stream);  // 2..: chunk c landed
+      }
+      CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_chunk[C - 1], 0));  // the context's own stream sees the whole frame
       {
         std::lock_guard<std::mutex> g(lane->mu);
         CK(cudaStreamWaitEvent(lane->stream, ctx->ev_early, 0));
@@ -840,6 +884,7 @@ int do_ransac(rpe_ctx* ctx, int method, const int32_t* samples, rpe_sample_fn fn
           launch_score_fast(method, fc, ctx->d_gen, ctx->d_fast, 0, H * S, th, ctx->d_votes, ctx->d_stats, wc, ctx->num_sms,
                             lane->stream, c0, seg_cap);
           ctx->launches++;
+          mark(lane->stream);  // chunk c scored
         }
         CK(cudaEventRecord(ctx->ev_lane[1], lane->stream));
       }
@@ -852,7 +897,20 @@ int do_ransac(rpe_ctx* ctx, int method, const int32_t* samples, rpe_sample_fn fn
                     ctx->stream);
       ctx->launches += 3;
       ctx->stats_clean = true;
-      return do_finish(ctx, method, th, out, mask, blocking);
+      mark(ctx->stream);  // fix-up + replay done
+      const int rcf = do_finish(ctx, method, th, out, mask, blocking);
+      if (trace) {
+        mark(ctx->stream);  // mask + result copies enqueued behind it
+        cudaStreamSynchronize(ctx->stream);
+        fprintf(stderr, "[rpe overlap trace] us after the call: generator %d chunks landed / scored, fix-up+replay, mask:", C);
+        for (int i = 1; i < ntev; ++i) {
+          float ms = 0.f;
+          cudaEventElapsedTime(&ms, tev[0], tev[i]);
+          fprintf(stderr, " %.1f", ms * 1e3f);
+        }
+        fprintf(stderr, "\n");
+      }
+      return rcf;
     }
   }
   if (!ctx->stats_clean) {
@@ -1117,6 +1175,7 @@ long long rpe_launch_count(const rpe_ctx* ctx) { return ctx ? ctx->launches : 0;
 
 int rpe_sync(rpe_ctx* ctx) {
   if (!ctx) return RPE_ERR_ARG;
+  ENTER(ctx);
   CK(sync_stream(ctx));
   finish_pending(ctx);
   return check_comm(ctx);
@@ -1143,43 +1202,36 @@ static int upload_common(rpe_ctx* ctx, const float* const src[5], int n, bool fr
   int rc = ensure_corr_capacity(ctx, n, !from_device);
   if (rc) return rc;
   ctx->n = n;
-  bool chunked = false;
+  bool defer = false;
   if (!from_device && ctx->overlap_chunks >= 2 && n >= 65536 && src[A_XC] && !src[A_BV] && !src[A_NC] && !src[A_NW]) {
     // page-locked (and device-visible) host arrays?
-    chunked = true;
-    for (int k = 0; k < 5 && chunked; ++k) {
+    defer = true;
+    for (int k = 0; k < 5 && defer; ++k) {
       if (!src[k]) continue;
       cudaPointerAttributes attr;
       if (cudaPointerGetAttributes(&attr, src[k]) != cudaSuccess) {
         (void)cudaGetLastError();
-        chunked = false;
+        defer = false;
       } else if (attr.type != cudaMemoryTypeHost || !attr.devicePointer) {
-        chunked = false;
+        defer = false;
       } else {
         ctx->host_view[k] = static_cast<const float*>(attr.devicePointer);
       }
     }
   }
-  if (chunked) {
+  if (defer) {
+    // Nothing is copied yet. If the next call is an rpe_ransac that can run ahead of the copy, it first generates its
+    // hypotheses from the host arrays (3 H points over an idle PCIe bus: a few microseconds; behind the frame's DMA
+    // traffic the same reads took longer than the whole upload), then starts the chunk copies and scores chunk by
+    // chunk. Any other call carries the upload out the plain way (flush_deferred).
     const int C = ctx->overlap_chunks;
     const int cs = (((n + C - 1) / C) + 1023) & ~1023;  // whole scorer stages; 16-byte aligned chunk starts
     ctx->chunk_corr = cs;
     ctx->n_chunks = (n + cs - 1) / cs;
-    // the copies may overwrite the arrays only after everything enqueued so far has read them
-    CK(cudaEventRecord(ctx->ev_prev, ctx->stream));
-    CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_prev, 0));
-    for (int c = 0; c < ctx->n_chunks; ++c) {
-      const size_t c0 = (size_t)c * cs, cnt = (size_t)((n - (int)c0) < cs ? (n - (int)c0) : cs);
-      for (int k = 0; k < 5; ++k)
-        if (src[k])
-          CK(cudaMemcpyAsync(ctx->d_raw[k] + 3 * c0, src[k] + 3 * c0, cnt * 3 * sizeof(float), cudaMemcpyHostToDevice,
-                             ctx->copy_stream));
-      CK(cudaEventRecord(ctx->ev_chunk[c], ctx->copy_stream));
+    for (int k = 0; k < 5; ++k) {
+      ctx->host_src[k] = src[k];
+      ctx->view[k] = src[k] ? ctx->d_raw[k] : nullptr;
     }
-    // everything on the context's stream sees the whole frame; only the early part of the next estimator call
-    // (generation + chunk-wise scoring, on early_stream / the scorer lane) runs ahead of it
-    CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_chunk[ctx->n_chunks - 1], 0));
-    for (int k = 0; k < 5; ++k) ctx->view[k] = src[k] ? ctx->d_raw[k] : nullptr;
   } else {
     for (int k = 0; k < 5; ++k) {
       if (!src[k]) {
@@ -1199,7 +1251,7 @@ static int upload_common(rpe_ctx* ctx, const float* const src[5], int n, bool fr
   ctx->suff_valid = false;
   ctx->n_slots = 0;
   leave_f64_mode(ctx);
-  ctx->chunked = chunked;
+  ctx->deferred = defer;
   return RPE_OK;
 }
 
@@ -1286,13 +1338,13 @@ int rpe_upload_f64(rpe_ctx* ctx, const double* bv, const double* xc, const doubl
   ctx->suff_valid = false;
   ctx->n_slots = 0;
   ctx->f64 = true;
-  ctx->chunked = false;
+  ctx->deferred = false;
   return RPE_OK;
 }
 int rpe_get_hypotheses_f64(rpe_ctx* ctx, int n_slots, double* hyps7, int32_t* valid) {
   if (!ctx || !hyps7 || n_slots <= 0) return RPE_ERR_ARG;
   if (!ctx->f64 || n_slots > ctx->n_slots) return fail(ctx, RPE_ERR_STATE, "no binary64 hypotheses of that many slots");
-  CK(cudaSetDevice(ctx->device));
+  ENTER(ctx);
   std::vector<HypGen64> h((size_t)n_slots);
   CK(cudaMemcpyAsync(h.data(), ctx->d_gen64, (size_t)n_slots * sizeof(HypGen64), cudaMemcpyDeviceToHost, ctx->stream));
   CK(sync_stream(ctx));
@@ -1307,7 +1359,7 @@ int rpe_get_hypotheses_f64(rpe_ctx* ctx, int n_slots, double* hyps7, int32_t* va
 static int do_refit(rpe_ctx* ctx, int kind, const float* weights, int max_iters, rpe_result* out, bool blocking) {
   if (!ctx || !out) return RPE_ERR_ARG;
   if (ctx->n <= 0) return fail(ctx, RPE_ERR_STATE, "no correspondences uploaded");
-  CK(cudaSetDevice(ctx->device));
+  ENTER(ctx);
   FrameView f = make_view(ctx);
   // every state / argument check comes before a staging slot is claimed: a failed call must not advance the ring
   if (kind == RPE_REFIT_KABSCH_INLIERS || kind == RPE_REFIT_KABSCH_ALL) {
@@ -1401,7 +1453,7 @@ int rpe_refit_async(rpe_ctx* ctx, int kind, const float* weights, int max_iters,
 
 int rpe_set_pose(rpe_ctx* ctx, const float q_xyzw[4], const float t[3], int max_votes) {
   if (!ctx || !q_xyzw || !t) return RPE_ERR_ARG;
-  CK(cudaSetDevice(ctx->device));
+  ENTER(ctx);
   CK(sync_stream(ctx));
   finish_pending(ctx);
   ReplayOut p;
@@ -1420,7 +1472,7 @@ int rpe_set_pose(rpe_ctx* ctx, const float q_xyzw[4], const float t[3], int max_
 int rpe_set_mask(rpe_ctx* ctx, const int16_t* mask, int cols) {
   if (!ctx || !mask || cols < 1 || cols > 3) return RPE_ERR_ARG;
   if (ctx->n <= 0) return fail(ctx, RPE_ERR_STATE, "no correspondences uploaded");
-  CK(cudaSetDevice(ctx->device));
+  ENTER(ctx);
   order_after_mask_copy(ctx);
   CK(cudaMemcpyAsync(ctx->d_mask, mask, (size_t)ctx->n * cols * sizeof(int16_t), cudaMemcpyHostToDevice, ctx->stream));
   CK(sync_stream(ctx));
@@ -1437,7 +1489,7 @@ int rpe_generate(rpe_ctx* ctx, int method, const int32_t* samples, int H) {
   if (!method_ok(method) || !samples || H <= 0) return fail(ctx, RPE_ERR_ARG, "bad argument to rpe_generate");
   int rc = check_arrays(ctx, method);
   if (rc) return rc;
-  CK(cudaSetDevice(ctx->device));
+  ENTER(ctx);
   const int S = method_slots(method);
   rc = ensure_hyp_capacity(ctx, H, H * S);
   if (rc) return rc;
@@ -1458,7 +1510,7 @@ int rpe_generate(rpe_ctx* ctx, int method, const int32_t* samples, int H) {
 int rpe_get_hypotheses(rpe_ctx* ctx, float* hyps, int32_t* valid, int n_slots) {
   if (ctx && ctx->f64) return fail(ctx, RPE_ERR_STATE, "the stage API is binary32 only (arrays were uploaded with rpe_upload_f64)");
   if (!ctx || n_slots <= 0 || n_slots > ctx->n_slots) return ctx ? fail(ctx, RPE_ERR_ARG, "bad slot count") : RPE_ERR_ARG;
-  CK(cudaSetDevice(ctx->device));
+  ENTER(ctx);
   std::vector<HypGen> h(n_slots);
   CK(cudaMemcpyAsync(h.data(), ctx->d_gen, (size_t)n_slots * sizeof(HypGen), cudaMemcpyDeviceToHost, ctx->stream));
   CK(sync_stream(ctx));
@@ -1475,7 +1527,7 @@ int rpe_get_hypotheses(rpe_ctx* ctx, float* hyps, int32_t* valid, int n_slots) {
 int rpe_set_hypotheses(rpe_ctx* ctx, int method, const float* hyps, const int32_t* valid, int n_slots) {
   if (!ctx) return RPE_ERR_ARG;
   if (!method_ok(method) || !hyps || n_slots <= 0) return fail(ctx, RPE_ERR_ARG, "bad argument to rpe_set_hypotheses");
-  CK(cudaSetDevice(ctx->device));
+  ENTER(ctx);
   int rc = ensure_hyp_capacity(ctx, 1, n_slots);
   if (rc) return rc;
   std::vector<HypGen> h(n_slots);
@@ -1502,7 +1554,7 @@ int rpe_score(rpe_ctx* ctx, int method, int slot_begin, int slot_end, float thr3
     return fail(ctx, RPE_ERR_ARG, "bad slot range");
   int rc = check_arrays(ctx, method);
   if (rc) return rc;
-  CK(cudaSetDevice(ctx->device));
+  ENTER(ctx);
   if (method == RPE_SHINJI || !g_force_exact_multi) {
     rc = ensure_packed(ctx, kind_for_method(method));
     if (rc) return rc;
@@ -1519,14 +1571,14 @@ int rpe_score(rpe_ctx* ctx, int method, int slot_begin, int slot_end, float thr3
 
 int rpe_get_votes(rpe_ctx* ctx, int32_t* votes, int n_slots) {
   if (!ctx || !votes || n_slots <= 0 || n_slots > ctx->n_slots) return RPE_ERR_ARG;
-  CK(cudaSetDevice(ctx->device));
+  ENTER(ctx);
   CK(cudaMemcpyAsync(votes, ctx->d_votes, (size_t)n_slots * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
   CK(sync_stream(ctx));
   return RPE_OK;
 }
 int rpe_set_votes(rpe_ctx* ctx, const int32_t* votes, int n_slots) {
   if (!ctx || !votes || n_slots <= 0 || n_slots > ctx->n_slots) return RPE_ERR_ARG;
-  CK(cudaSetDevice(ctx->device));
+  ENTER(ctx);
   CK(cudaMemcpyAsync(ctx->d_votes, votes, (size_t)n_slots * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
   CK(sync_stream(ctx));
   return RPE_OK;
@@ -1563,7 +1615,7 @@ static void peer_close(rpe_ctx* ctx) {
 int rpe_peer_export(rpe_ctx* ctx, unsigned char handle[64]) {
   if (!ctx || !handle) return RPE_ERR_ARG;
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
-  CK(cudaSetDevice(ctx->device));
+  ENTER(ctx);
   peer_close(ctx);  // mappings of an earlier group
   if (int rc = peer_arm(ctx)) return rc;
   cudaIpcMemHandle_t h;
@@ -1574,7 +1626,7 @@ int rpe_peer_export(rpe_ctx* ctx, unsigned char handle[64]) {
 int rpe_peer_import(rpe_ctx* ctx, int rank, int world, const unsigned char* handles) {
   if (!ctx || !handles || world < 1 || world > kMaxPeers || rank < 0 || rank >= world) return RPE_ERR_ARG;
   if (!ctx->d_peer_block) return fail(ctx, RPE_ERR_STATE, "call rpe_peer_export first");
-  CK(cudaSetDevice(ctx->device));
+  ENTER(ctx);
   peer_close(ctx);
   for (int r = 0; r < world; ++r) {
     if (r == rank) {
@@ -1602,7 +1654,7 @@ int rpe_peer_set_timeout_ms(rpe_ctx* ctx, int ms) {
 // (or one host thread per context).
 int rpe_peer_import_local(rpe_ctx* ctx, int rank, int world, rpe_ctx* const* ctxs) {
   if (!ctx || !ctxs || world < 1 || world > kMaxPeers || rank < 0 || rank >= world || ctxs[rank] != ctx) return RPE_ERR_ARG;
-  CK(cudaSetDevice(ctx->device));
+  ENTER(ctx);
   peer_close(ctx);
   // own block: (re-)armed here; the caller imports on every context before the first frame, so nobody writes into it
   // yet. Peers' blocks that do not exist yet are created (armed) now and left alone when their own import runs.
@@ -1614,7 +1666,7 @@ int rpe_peer_import_local(rpe_ctx* ctx, int rank, int world, rpe_ctx* const* ctx
       CK(cudaSetDevice(p->device));
       CK(cudaMalloc(&p->d_peer_block, kPeerBlockBytes));
       CK(cudaMemset(p->d_peer_block, 0, kPeerBlockBytes));
-      CK(cudaSetDevice(ctx->device));
+      ENTER(ctx);
     }
     if (p->device != ctx->device) {
       int can = 0;
@@ -1635,7 +1687,7 @@ int rpe_exchange_votes(rpe_ctx* ctx, int slot_begin, int slot_end) {
   if (ctx->peer_world < 1) return fail(ctx, RPE_ERR_STATE, "call rpe_peer_import first");
   if (slot_begin < 0 || slot_end < slot_begin || slot_end > ctx->n_slots || ctx->n_slots > kPeerSlots)
     return fail(ctx, RPE_ERR_ARG, "bad slot range for rpe_exchange_votes");
-  CK(cudaSetDevice(ctx->device));
+  ENTER(ctx);
   ctx->peer_epoch += 1;
   launch_exchange_votes(ctx->peers, ctx->peer_rank, ctx->peer_world, ctx->peer_epoch, slot_begin, slot_end, ctx->n_slots,
                         ctx->d_votes, ctx->h_peer_err, ctx->peer_timeout_ns, ctx->stream);
@@ -1654,7 +1706,7 @@ static int do_ransac_sharded(rpe_ctx* ctx, int method, const int32_t* samples, i
   if (H > kMaxPassIters || H * S > kPeerSlots) return fail(ctx, RPE_ERR_ARG, "rpe_ransac_sharded: at most 8192 iterations");
   int rc = check_arrays(ctx, method);
   if (rc) return rc;
-  CK(cudaSetDevice(ctx->device));
+  ENTER(ctx);
   const Thresh th = {thr3d, cos_thr2d, cos_thrN};
   rc = ensure_hyp_capacity(ctx, H, H * S);
   if (rc) return rc;
@@ -1697,7 +1749,7 @@ int rpe_ransac_sharded_async(rpe_ctx* ctx, int method, const int32_t* samples, i
 }
 int rpe_peer_status(rpe_ctx* ctx) {
   if (!ctx || !ctx->d_peer_block) return RPE_ERR_ARG;
-  CK(cudaSetDevice(ctx->device));
+  ENTER(ctx);
   CK(sync_stream(ctx));
   return check_comm(ctx);
 }
@@ -1707,7 +1759,7 @@ int rpe_finish(rpe_ctx* ctx, int method, int H, float thr3d, float cos_thr2d, fl
   if (!ctx) return RPE_ERR_ARG;
   if (!method_ok(method) || H <= 0 || H * method_slots(method) > ctx->n_slots || !out)
     return fail(ctx, RPE_ERR_ARG, "bad argument to rpe_finish");
-  CK(cudaSetDevice(ctx->device));
+  ENTER(ctx);
   const Thresh th = {thr3d, cos_thr2d, cos_thrN};
   launch_replay(method, ctx->d_gen, ctx->d_votes, H, 0, ctx->n, confidence, ctx->d_stats, ctx->d_rs, ctx->d_pose, true, H,
                 ctx->stream);
@@ -1836,7 +1888,7 @@ int rpe_sim_kinect_2d_3d_nl_device(rpe_ctx* ctx, uint64_t seed, const float q_xy
 // Copy the context's current correspondence arrays back to the host (NULL = skip). For tests / inspection.
 int rpe_download(rpe_ctx* ctx, float* bv, float* xc, float* nc, float* xw, float* nw) {
   if (!ctx || ctx->n <= 0) return RPE_ERR_ARG;
-  CK(cudaSetDevice(ctx->device));
+  ENTER(ctx);
   float* dst[5] = {bv, xc, nc, xw, nw};
   for (int k = 0; k < 5; ++k)
     if (dst[k]) {
@@ -1851,7 +1903,7 @@ int rpe_download(rpe_ctx* ctx, float* bv, float* xc, float* nc, float* xw, float
 static int minsolv_common(rpe_ctx* ctx, const float* in, int in_stride, int count, float* out_a, int a_stride, float* out_b,
                           int b_stride, bool is_ms) {
   if (!ctx || !in || count <= 0 || !out_a || (is_ms && !out_b)) return RPE_ERR_ARG;
-  CK(cudaSetDevice(ctx->device));
+  ENTER(ctx);
   float *d_in = nullptr, *d_a = nullptr, *d_b = nullptr;
   CK(cudaMallocAsync(&d_in, (size_t)count * in_stride * sizeof(float), ctx->stream));
   CK(cudaMallocAsync(&d_a, (size_t)count * a_stride * sizeof(float), ctx->stream));
@@ -1919,7 +1971,7 @@ int rpe_ao_ransac(const float* x_w, const float* x_c, int n, float* R_cw, float*
 // ---- microbenchmark / timing -------------------------------------------------------------------------
 int rpe_measure_ffma_tflops(rpe_ctx* ctx, int ms_target, double* tflops_scalar, double* tflops_packed) {
   if (!ctx) return RPE_ERR_ARG;
-  CK(cudaSetDevice(ctx->device));
+  ENTER(ctx);
   float* sink = nullptr;
   CK(cudaMalloc(&sink, 64));
   cudaEvent_t e0, e1;
