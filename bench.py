@@ -378,10 +378,18 @@ def run_gpu(args, rank, world, local_rank):
     w1 = time.time()
     launches = launches_now() - launches0
     fast_sum, fast_cnt = scorer_stats(True)
-    # --- `e2e`: host buffers, H2D + D2H inside the timed region, through the same public call
+    # --- `e2e`: host buffers, H2D + D2H inside the timed region, through the same public call. With several GPUs the
+    #     frames of the region are handed out by ONE counter in POSIX shared memory (rpe_seq_run_shared): the box's PCIe
+    #     paths are not equally fast when all GPUs upload at once, and a static split makes everybody wait for the slowest
     seq.set_frames(host_frames)
+    shared = None
+    frames_done_e2e = args.steps * fps
     w2 = time.time()
-    ms_e2e, wall_e2e, r0_e2e, r1_e2e = timed(args.steps * fps, 0)
+    if world > 1 and not args.static_e2e:
+        shared = SharedCounter(rank, tag=os.environ.get("MASTER_PORT", "0"))
+        ms_e2e, frames_done_e2e = timed_shared(seq, shared, args.steps * fps * world, torch, dist, dev, barrier)
+    else:
+        ms_e2e, wall_e2e, r0_e2e, r1_e2e = timed(args.steps * fps, 0)
     w3 = time.time()
     fast_sum_e2e, fast_cnt_e2e = scorer_stats(True)
     sampler.stop()
@@ -523,7 +531,7 @@ def run_gpu(args, rank, world, local_rank):
     if rank == 0:
         h2d_step = fps * (2 * frame_bytes + N_HYP * 16)
         d2h_step = fps * (2 * N_CORR * 2 + 3 * 72 + 12)
-        e2e_frames_s_gpu = frames_rank / (ms_e2e * 1e-3)
+        e2e_frames_s_gpu = frames_done_e2e / (ms_e2e * 1e-3)  # rank 0's share (dynamic hand-out at N > 1)
         e2e_h2d_gbs = e2e_frames_s_gpu * (2 * frame_bytes + N_HYP * 16) / 1e9
         line = {
             "metric": "hyp-corr evals/s", "value": value, "unit": "evals/s", "n_gpus": world, "steps": args.steps,
@@ -542,7 +550,14 @@ def run_gpu(args, rank, world, local_rank):
                                                 "without_overlap_min": float(min(lat_plain))},
                     "h2d_gbs_per_gpu": e2e_h2d_gbs,
                     "h2d_ceiling": h2d,
-                    "h2d_frac_of_ceiling": (e2e_h2d_gbs / h2d["per_gpu_gbs"] if h2d and h2d.get("per_gpu_gbs") else None),
+                    "h2d_gbs_aggregate": frames_total / (ms_e2e * 1e-3) * (2 * frame_bytes + N_HYP * 16) / 1e9,
+                    "h2d_frac_of_ceiling": (frames_total / (ms_e2e * 1e-3) * (2 * frame_bytes + N_HYP * 16) / 1e9 / h2d["aggregate_gbs"]
+                                            if h2d and h2d.get("aggregate_gbs") else None),
+                    "h2d_frac_of_ceiling_note": "aggregate e2e upload rate / aggregate concurrent-upload ceiling of the box "
+                                                "(all ranks copying, no compute), both measured in this run",
+                    "frame_distribution": ("one shared counter (rpe_seq_run_shared): a rank takes a frame when one of its "
+                                           "contexts has fewer than two unfinished frames; rank 0 took "
+                                           f"{frames_done_e2e} of {frames_total}" if shared is not None else "static: equal share per GPU"),
                     "numa_binding_rank0": binding,
                     "clocks": clocks_e2e,
                     "path": f"rpe_seq_run: {args.threads} native issue threads x {args.contexts} contexts per GPU; per frame "
@@ -563,6 +578,68 @@ def run_gpu(args, rank, world, local_rank):
     c0.close()
     if dist is not None:
         dist.destroy_process_group()
+
+
+class SharedCounter:
+    """One int64 in POSIX shared memory, created by rank 0 and attached by the others (after a barrier)."""
+
+    def __init__(self, rank, tag):
+        from multiprocessing import shared_memory
+        self.name = f"rpe_bench_counter_{tag}"
+        self.rank = rank
+        self.shm = None
+        self._sm = shared_memory
+        if rank == 0:
+            try:
+                old = shared_memory.SharedMemory(name=self.name)
+                old.close()
+                old.unlink()
+            except FileNotFoundError:
+                pass
+            self.shm = shared_memory.SharedMemory(name=self.name, create=True, size=64)
+            self.shm.buf[:64] = bytes(64)
+
+    def attach(self):
+        if self.shm is None:
+            self.shm = self._sm.SharedMemory(name=self.name)
+        self.arr = np.ndarray((1,), dtype=np.int64, buffer=self.shm.buf)
+        return self.arr
+
+    def close(self):
+        try:
+            self.arr = None
+            self.shm.close()
+            if self.rank == 0:
+                self.shm.unlink()
+        except Exception:
+            pass
+
+
+def timed_shared(seq, shared, total, torch, dist, dev, barrier):
+    """The e2e region with dynamic frame hand-out: every rank runs rpe_seq_run_shared on the same counter until `total`
+    frames are done. Returns (max-over-ranks device-clock ms, frames this rank processed)."""
+    barrier()                       # rank 0 has created the segment
+    counter = shared.attach()
+    barrier()
+    if shared.rank == 0:
+        counter[0] = 0
+    barrier()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    _, _, _, done = seq.run_shared(counter, total, total)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    tt = torch.tensor([ms], device=dev, dtype=torch.float64)
+    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ms = float(tt.item())
+    dn = torch.tensor([done], device=dev, dtype=torch.int64)
+    dist.all_reduce(dn)
+    assert int(dn.item()) == total, (int(dn.item()), total)
+    barrier()
+    shared.close()
+    return ms, done
 
 
 def measure_h2d_ceiling(rpe, torch, dist, dev, local_rank, h_xw, h_xc, barrier, seconds=0.25):
@@ -596,18 +673,17 @@ def measure_h2d_ceiling(rpe, torch, dist, dev, local_rank, h_xw, h_xc, barrier, 
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
         gbs = copies * nbytes / (ms * 1e-3) / 1e9
-        lo, tot = gbs, gbs
+        lo, tot, per_rank = gbs, gbs, [gbs]
         if dist is not None:
             t = torch.tensor([gbs], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MIN)
-            lo = float(t.item())
-            t = torch.tensor([gbs], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.SUM)
-            tot = float(t.item())
+            parts = [torch.zeros_like(t) for _ in range(dist.get_world_size())]
+            dist.all_gather(parts, t)
+            per_rank = [float(x.item()) for x in parts]
+            lo, tot = min(per_rank), sum(per_rank)
         barrier()
         for c in cs:
             c.close()
-        return {"per_gpu_gbs": lo, "aggregate_gbs": tot, "rank0_gbs": gbs,
+        return {"per_gpu_gbs": lo, "aggregate_gbs": tot, "rank0_gbs": gbs, "per_rank_gbs": [round(x, 2) for x in per_rank],
                 "how": "all ranks concurrently: rpe_upload of 2 x 3.7 MB page-locked arrays per frame on 4 streams per GPU, "
                        "no compute"}
     except Exception as e:
@@ -717,6 +793,7 @@ def main():
     ap.add_argument("--ring", type=int, default=24, help="frames of the e2e leg's page-locked host ring (>L2 in total)")
     ap.add_argument("--contexts", type=int, default=12, help="rpe contexts (streams) per GPU, frames round-robin")
     ap.add_argument("--threads", type=int, default=2, help="native issue threads per GPU (rpe_seq)")
+    ap.add_argument("--static-e2e", action="store_true", help="N > 1: equal static share per GPU in the e2e leg too")
     ap.add_argument("--overlap-chunks", type=int, default=4, help="rpe_set_upload_overlap of the single-frame latency leg")
     ap.add_argument("--gn-iters", type=int, default=3)
     ap.add_argument("--ref-hyp", type=int, default=128, help="hypotheses per step of the CPU arm (bounded sample)")

@@ -53,6 +53,12 @@ class Session {
   }
 
   rpe_ctx* ctx() { return ctx_; }
+  // Reproduce the reference's stale sample columns on frames with invalid depth (rpe_set_stale_sample_columns;
+  // /root/reference/pose/AbsoluteOrientationNormal.hpp:48-75, 299-315). Off by default; RPE_STALE_SAMPLE_COLUMNS=1 in the
+  // environment switches it on for every session.
+  void setReferenceStaleSampleColumns(bool on) { check(rpe_set_stale_sample_columns(ctx_, on ? 1 : 0), "rpe_set_stale_sample_columns"); }
+  // Overlap the upload of page-locked 3-D / 3-D frames with generation and scoring (rpe_set_upload_overlap); 0 = off.
+  void setUploadOverlap(int chunks) { check(rpe_set_upload_overlap(ctx_, chunks), "rpe_set_upload_overlap"); }
   void check(int rc, const char* what) {
     if (rc != RPE_OK) throw Failure(rc, std::string(what) + ": " + rpe_status_string(rc) + " (" + rpe_last_error(ctx_) + ")");
   }

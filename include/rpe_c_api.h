@@ -278,6 +278,14 @@ int rpe_seq_create(const rpe_seq_params* params, rpe_seq** out);
  * RANSAC result and the result of the last refit of the frame) or NULL. */
 int rpe_seq_run(rpe_seq* seq, const rpe_seq_frame* ring, int ring_len, long long first_frame, int n_frames,
                 rpe_result* ransac_out, rpe_result* final_out);
+/* The same with the frame indices taken from a COUNTER SHARED by several sequences (one per GPU; with one process per
+ * GPU the counter lives in shared memory): every issuing thread fetch-adds *shared_next and processes frame `index`
+ * (reading ring[index % ring_len], table seed sample_seed + index) until the counter reaches `total`, taking a new frame
+ * only when one of its contexts has fewer than two unfinished frames — so a GPU behind a slower PCIe path simply takes
+ * fewer frames. Still no data-path collective. frame_index_out[i] (may be NULL) = the frame whose results are in
+ * ransac_out[i] / final_out[i]; *n_done = frames this sequence processed; capacity = length of the three arrays. */
+int rpe_seq_run_shared(rpe_seq* seq, const rpe_seq_frame* ring, int ring_len, long long* shared_next, long long total,
+                       int capacity, rpe_result* ransac_out, rpe_result* final_out, long long* frame_index_out, int* n_done);
 rpe_ctx* rpe_seq_context(rpe_seq* seq, int index); /* for rpe_enable_stage_timing / rpe_launch_count */
 int rpe_seq_num_contexts(const rpe_seq* seq);
 const char* rpe_seq_last_error(const rpe_seq* seq);

@@ -171,6 +171,8 @@ class SeqFrame(C.Structure):
 
 _sig("rpe_seq_create", C.c_int, [C.POINTER(SeqParams), C.POINTER(_vp)])
 _sig("rpe_seq_run", C.c_int, [_vp, C.POINTER(SeqFrame), C.c_int, C.c_longlong, C.c_int, C.POINTER(_Result), C.POINTER(_Result)])
+_sig("rpe_seq_run_shared", C.c_int, [_vp, C.POINTER(SeqFrame), C.c_int, _vp, C.c_longlong, C.c_int, C.POINTER(_Result),
+                                     C.POINTER(_Result), _vp, C.POINTER(C.c_int)])
 _sig("rpe_seq_context", _vp, [_vp, C.c_int])
 _sig("rpe_seq_num_contexts", C.c_int, [_vp])
 _sig("rpe_seq_last_error", C.c_char_p, [_vp])
@@ -199,7 +201,7 @@ DECLARED_SYMBOLS = [
     "rpe_get_votes", "rpe_set_votes", "rpe_votes_device_ptr", "rpe_peer_export", "rpe_peer_import", "rpe_peer_import_local", "rpe_exchange_votes", "rpe_peer_status", "rpe_peer_set_timeout_ms", "rpe_ransac_sharded", "rpe_ransac_sharded_async", "rpe_finish", "rpe_update_num_iters", "rpe_sample_table",
     "rpe_prosac_table", "rpe_sampler_create", "rpe_sampler_rows", "rpe_sampler_destroy", "rpe_sim_pose", "rpe_sim_3d_3d", "rpe_sim_2d_3d", "rpe_sim_2d_3d_nl", "rpe_sim_kinect_2d_3d_nl", "rpe_sim_kinect_2d_3d_nl_device", "rpe_sim_3d_3d_device",
     "rpe_sim_2d_3d_nl_device", "rpe_min_ev", "rpe_min_ms", "rpe_min_ev_host", "rpe_min_ev_host_f64", "rpe_min_ms_host",
-    "rpe_sim_3d_3d_device_to", "rpe_sampler_reseed", "rpe_seq_create", "rpe_seq_run",
+    "rpe_sim_3d_3d_device_to", "rpe_sampler_reseed", "rpe_seq_create", "rpe_seq_run", "rpe_seq_run_shared",
     "rpe_seq_context", "rpe_seq_num_contexts", "rpe_seq_last_error", "rpe_seq_destroy", "rpe_download", "rpe_ao", "rpe_ao_ransac",
     "rpe_measure_ffma_tflops", "rpe_last_stage_ms", "rpe_enable_stage_timing", "rpe_scorer_time_stats",
 ]
@@ -438,6 +440,22 @@ class Sequence:
         if rc != 0:
             raise RpeError(f"rpe error {rc}: {lib.rpe_status_string(rc).decode()}: {lib.rpe_seq_last_error(self._h).decode()}")
         return r0, r1
+
+    def run_shared(self, counter, total, capacity):
+        """Frames handed out by a counter shared with other sequences (rpe_seq_run_shared). `counter`: a numpy int64 array
+        of one element (e.g. a view of multiprocessing.shared_memory). Returns (ransac results, final results, frame
+        indices, n_done)."""
+        if self._ring is None:
+            raise RpeError("Sequence.set_frames first")
+        r0 = (_Result * capacity)()
+        r1 = (_Result * capacity)()
+        idx = np.full(capacity, -1, np.int64)
+        nd = C.c_int(0)
+        rc = lib.rpe_seq_run_shared(self._h, self._ring, len(self._ring), counter.ctypes.data_as(C.c_void_p), total, capacity,
+                                    r0, r1, idx.ctypes.data_as(C.c_void_p), C.byref(nd))
+        if rc != 0:
+            raise RpeError(f"rpe error {rc}: {lib.rpe_status_string(rc).decode()}: {lib.rpe_seq_last_error(self._h).decode()}")
+        return r0, r1, idx, nd.value
 
     def contexts(self):
         return [C.c_void_p(lib.rpe_seq_context(self._h, i)) for i in range(lib.rpe_seq_num_contexts(self._h))]

@@ -33,15 +33,25 @@ struct SeqContext {
   cudaEvent_t ev[kTableSlots] = {};
   bool ev_used[kTableSlots] = {};
   int next = 0;
+  // shared mode: at most kInflight frames enqueued and unfinished per context, so that a sequence takes frames at the
+  // pace its GPU (and its PCIe path) works them off instead of at the pace its host thread can enqueue them
+  cudaEvent_t done[2] = {};
+  bool done_used[2] = {};
+  int done_next = 0;
 };
 
 struct Job {
   const rpe_seq_frame* ring = nullptr;
   int ring_len = 0;
   long long first = 0;
-  int n_frames = 0;
+  int n_frames = 0;  // static mode: frames of this call; shared mode: capacity of the result arrays
   rpe_result* ransac_out = nullptr;
   rpe_result* final_out = nullptr;
+  // shared mode (rpe_seq_run_shared): frame indices come from a counter that several sequences — one per GPU, usually
+  // one per process, the counter in shared memory — advance together
+  long long* shared_next = nullptr;
+  long long total = 0;
+  long long* frame_index_out = nullptr;
 };
 
 }  // namespace
@@ -55,6 +65,7 @@ struct rpe_seq {
   std::mutex mu;
   std::condition_variable cv_go, cv_done;
   Job job;
+  std::atomic<int> local_done{0};  // shared mode: frames this sequence has taken in the current run
   unsigned long long generation = 0;
   int running = 0;
   bool quit = false;
@@ -138,6 +149,38 @@ void worker_main(rpe_seq* s, int worker) {
     }
     int rc = RPE_OK;
     size_t k = 0;
+    if (job.shared_next) {
+      for (; rc == RPE_OK; ++k) {
+        const size_t ci = k % mine.size();
+        SeqContext& sc = s->ctxs[mine[ci]];
+        // backpressure first, THEN take a frame: a frame is claimed only when this context can start it
+        const int d = sc.done_next;
+        if (sc.done_used[d] && cudaEventSynchronize(sc.done[d]) != cudaSuccess) {
+          rc = RPE_ERR_CUDA;
+          break;
+        }
+        const long long fi = __atomic_fetch_add(job.shared_next, 1LL, __ATOMIC_RELAXED);
+        if (fi >= job.total) break;
+        const int i = s->local_done.fetch_add(1);
+        if (i >= job.n_frames) {  // result arrays full (cannot happen when the caller sized them for `total`)
+          rc = RPE_ERR_ARG;
+          s->errors[worker] = "rpe_seq_run_shared: result arrays too small";
+          break;
+        }
+        const rpe_seq_frame& f = job.ring[(size_t)(fi % job.ring_len)];
+        rpe_result* r_out = job.ransac_out ? &job.ransac_out[i] : &scratch[2 * ci];
+        rpe_result* f_out = job.final_out ? &job.final_out[i] : &scratch[2 * ci + 1];
+        if (job.frame_index_out) job.frame_index_out[i] = fi;
+        rc = issue_frame(s, worker, sc, f, fi, r_out, f_out);
+        if (rc) {
+          s->errors[worker] = rpe_last_error(sc.ctx);
+          break;
+        }
+        if (cudaEventRecord(sc.done[d], (cudaStream_t)rpe_stream(sc.ctx)) != cudaSuccess) rc = RPE_ERR_CUDA;
+        sc.done_used[d] = true;
+        sc.done_next = (d + 1) % 2;
+      }
+    } else
     for (int i = worker; i < job.n_frames && rc == RPE_OK; i += T, ++k) {
       const size_t ci = k % mine.size();
       SeqContext& sc = s->ctxs[mine[ci]];
@@ -190,6 +233,8 @@ int rpe_seq_create(const rpe_seq_params* params, rpe_seq** out) {
     }
     for (int k = 0; k < kTableSlots && !rc; ++k)
       if (cudaEventCreateWithFlags(&sc.ev[k], cudaEventDisableTiming) != cudaSuccess) rc = RPE_ERR_CUDA;
+    for (int k = 0; k < 2 && !rc; ++k)
+      if (cudaEventCreateWithFlags(&sc.done[k], cudaEventDisableTiming) != cudaSuccess) rc = RPE_ERR_CUDA;
     if (rc) break;
   }
   if (rc) {
@@ -206,18 +251,12 @@ int rpe_seq_create(const rpe_seq_params* params, rpe_seq** out) {
   return RPE_OK;
 }
 
-int rpe_seq_run(rpe_seq* s, const rpe_seq_frame* ring, int ring_len, long long first_frame, int n_frames,
-                rpe_result* ransac_out, rpe_result* final_out) {
-  if (!s || !ring || ring_len < 1 || n_frames < 0 || first_frame < 0) return RPE_ERR_ARG;
-  if (n_frames == 0) return RPE_OK;
+static int seq_run_job(rpe_seq* s, const Job& job) {
   {
     std::unique_lock<std::mutex> lk(s->mu);
-    s->job.ring = ring;
-    s->job.ring_len = ring_len;
-    s->job.first = first_frame;
-    s->job.n_frames = n_frames;
-    s->job.ransac_out = ransac_out;
-    s->job.final_out = final_out;
+    s->job = job;
+    s->local_done.store(0);
+    for (SeqContext& sc : s->ctxs) sc.done_used[0] = sc.done_used[1] = false;
     s->running = s->p.n_threads;
     ++s->generation;
     s->cv_go.notify_all();
@@ -229,6 +268,40 @@ int rpe_seq_run(rpe_seq* s, const rpe_seq_frame* ring, int ring_len, long long f
       return s->status[t];
     }
   return RPE_OK;
+}
+
+int rpe_seq_run(rpe_seq* s, const rpe_seq_frame* ring, int ring_len, long long first_frame, int n_frames,
+                rpe_result* ransac_out, rpe_result* final_out) {
+  if (!s || !ring || ring_len < 1 || n_frames < 0 || first_frame < 0) return RPE_ERR_ARG;
+  if (n_frames == 0) return RPE_OK;
+  Job job;
+  job.ring = ring;
+  job.ring_len = ring_len;
+  job.first = first_frame;
+  job.n_frames = n_frames;
+  job.ransac_out = ransac_out;
+  job.final_out = final_out;
+  return seq_run_job(s, job);
+}
+
+int rpe_seq_run_shared(rpe_seq* s, const rpe_seq_frame* ring, int ring_len, long long* shared_next, long long total,
+                       int capacity, rpe_result* ransac_out, rpe_result* final_out, long long* frame_index_out, int* n_done) {
+  if (!s || !ring || ring_len < 1 || !shared_next || total < 0 || capacity < 1) return RPE_ERR_ARG;
+  Job job;
+  job.ring = ring;
+  job.ring_len = ring_len;
+  job.n_frames = capacity;
+  job.ransac_out = ransac_out;
+  job.final_out = final_out;
+  job.shared_next = shared_next;
+  job.total = total;
+  job.frame_index_out = frame_index_out;
+  const int rc = seq_run_job(s, job);
+  if (n_done) {
+    const int d = s->local_done.load();
+    *n_done = d < capacity ? d : capacity;
+  }
+  return rc;
 }
 
 rpe_ctx* rpe_seq_context(rpe_seq* s, int index) {
@@ -252,6 +325,8 @@ int rpe_seq_destroy(rpe_seq* s) {
     if (sc.tables) cudaFreeHost(sc.tables);
     for (int k = 0; k < kTableSlots; ++k)
       if (sc.ev[k]) cudaEventDestroy(sc.ev[k]);
+    for (int k = 0; k < 2; ++k)
+      if (sc.done[k]) cudaEventDestroy(sc.done[k]);
   }
   for (rpe_sampler* sm : s->samplers)
     if (sm) rpe_sampler_destroy(sm);

@@ -104,3 +104,44 @@ def test_sequence_errors_are_reported(rpe):
         with pytest.raises(rpe.RpeError) as e:
             seq.run(0, 2)
         assert "bearing" in str(e.value)
+
+
+def test_shared_counter_hands_every_frame_out_once(rpe, orc):
+    """rpe_seq_run_shared: two sequences (here on one GPU, two host threads) advance one counter; together they process
+    every frame exactly once, and each frame's result is what the oracle gives for that frame's own sample table."""
+    import threading
+    orc.set_math_mode(orc.DET)
+    n, ring, total, seed = 8000, 5, 61, 300
+    frames = _frames(rpe, ring, n)
+    host = [{"xw": _pinned_copy(rpe, f["xw"]), "xc": _pinned_copy(rpe, f["xc"])} for f in frames]
+    counter = np.zeros(1, np.int64)
+    out = [None, None]
+    seqs = [rpe.Sequence(0, "shinji", H, thr3d=THR, confidence=CONF, refit=("kabsch",), sample_seed=seed, contexts=c, threads=t)
+            for c, t in ((3, 2), (2, 1))]
+    try:
+        for s in seqs:
+            s.set_frames(host)
+
+        def work(k):
+            out[k] = seqs[k].run_shared(counter, total, total)
+        th = [threading.Thread(target=work, args=(k,)) for k in range(2)]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        seen = {}
+        for k in range(2):
+            r0, r1, idx, nd = out[k]
+            assert nd >= 1  # both got some work
+            for i in range(nd):
+                fi = int(idx[i])
+                assert fi not in seen
+                seen[fi] = (r0[i].winner, r0[i].max_votes, r0[i].iter_final, r1[i].refit_ok)
+        assert sorted(seen) == list(range(total)) and int(counter[0]) >= total
+        for fi in (0, 7, 33, 60):
+            f = frames[fi % ring]
+            ref = orc.ransac(0, rpe.sample_table(seed + fi, n, 3, H), thr3d=THR, confidence=CONF, full=True, xc=f["xc"], xw=f["xw"])
+            assert seen[fi][:3] == (ref["winner"], ref["max_votes"], ref["iter_final"]) and seen[fi][3] == 1
+    finally:
+        for s in seqs:
+            s.close()
