@@ -643,51 +643,68 @@ def timed_shared(seq, shared, total, torch, dist, dev, barrier):
 
 
 def measure_h2d_ceiling(rpe, torch, dist, dev, local_rank, h_xw, h_xc, barrier, seconds=0.25):
-    """All ranks at once: rpe_upload of the e2e leg's own page-locked frames (2 x 3.7 MB per frame) on 4 contexts
-    (streams), no compute. Returns this box's concurrent H2D rate per GPU (min over ranks) and in aggregate."""
+    """All ranks at once, no compute: (a) rpe_upload of the e2e leg's own page-locked frames (2 x 3.7 MB per frame) on 4
+    contexts (streams); (b) the same with the e2e leg's device-to-host traffic beside it (one 1.2 MB mask per frame on a
+    side stream). Returns the box's concurrent rates per GPU and in aggregate for both patterns."""
     try:
         cs = [rpe.Context(local_rank) for _ in range(4)]
         nbytes = 2 * h_xw[0].nbytes
+        d_mask = torch.zeros(2 * N_CORR, dtype=torch.int16, device=dev)
+        h_masks = [torch.empty(2 * N_CORR, dtype=torch.int16, pin_memory=True) for _ in range(4)]
+        side = [torch.cuda.Stream(device=dev) for _ in range(4)]
 
-        def burst(reps):
+        def burst(reps, with_d2h):
             k = 0
             for _ in range(reps):
-                for c in cs:
+                for j, c in enumerate(cs):
                     c.upload_async(xc=h_xc[k % len(h_xc)], xw=h_xw[k % len(h_xw)])
+                    if with_d2h:
+                        with torch.cuda.stream(side[j]):
+                            h_masks[j].copy_(d_mask, non_blocking=True)
                     k += 1
             return k
-        burst(2)
-        for c in cs:
-            c.sync()
-        barrier()
-        e0 = torch.cuda.Event(enable_timing=True)
-        e1 = torch.cuda.Event(enable_timing=True)
-        e0.record()
-        t0 = time.perf_counter()
-        copies = 0
-        while time.perf_counter() - t0 < seconds:
-            copies += burst(4)
+
+        def run(with_d2h):
+            burst(2, with_d2h)
             for c in cs:
                 c.sync()
-        e1.record()
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1)
-        gbs = copies * nbytes / (ms * 1e-3) / 1e9
-        lo, tot, per_rank = gbs, gbs, [gbs]
-        if dist is not None:
-            t = torch.tensor([gbs], device=dev, dtype=torch.float64)
-            parts = [torch.zeros_like(t) for _ in range(dist.get_world_size())]
-            dist.all_gather(parts, t)
-            per_rank = [float(x.item()) for x in parts]
-            lo, tot = min(per_rank), sum(per_rank)
-        barrier()
+            torch.cuda.synchronize()
+            barrier()
+            e0 = torch.cuda.Event(enable_timing=True)
+            e1 = torch.cuda.Event(enable_timing=True)
+            e0.record()
+            t0 = time.perf_counter()
+            copies = 0
+            while time.perf_counter() - t0 < seconds:
+                copies += burst(4, with_d2h)
+                for c in cs:
+                    c.sync()
+                for st in side:
+                    st.synchronize()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1)
+            gbs = copies * nbytes / (ms * 1e-3) / 1e9
+            per_rank = [gbs]
+            if dist is not None:
+                t = torch.tensor([gbs], device=dev, dtype=torch.float64)
+                parts = [torch.zeros_like(t) for _ in range(dist.get_world_size())]
+                dist.all_gather(parts, t)
+                per_rank = [float(x.item()) for x in parts]
+            barrier()
+            return {"per_gpu_gbs": min(per_rank), "aggregate_gbs": sum(per_rank), "per_rank_gbs": [round(x, 2) for x in per_rank]}
+        up = run(False)
+        both = run(True)
         for c in cs:
             c.close()
-        return {"per_gpu_gbs": lo, "aggregate_gbs": tot, "rank0_gbs": gbs, "per_rank_gbs": [round(x, 2) for x in per_rank],
-                "how": "all ranks concurrently: rpe_upload of 2 x 3.7 MB page-locked arrays per frame on 4 streams per GPU, "
-                       "no compute"}
+        out = dict(both)
+        out["upload_only"] = up
+        out["how"] = ("all ranks concurrently, no compute: rpe_upload of 2 x 3.7 MB page-locked arrays per frame on 4 streams "
+                      "per GPU, with one 1.2 MB device-to-host copy per frame beside it (the e2e leg's own traffic pattern); "
+                      "upload_only = the same without the device-to-host copies; rates count the uploaded bytes")
+        return out
     except Exception as e:
-        return {"error": repr(e)[:120]}
+        return {"error": repr(e)[:160]}
 
 
 class _DevArray:

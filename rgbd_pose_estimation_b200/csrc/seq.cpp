@@ -12,6 +12,7 @@
 // can be checked against the CPU path on its own. (The reference continues one global rand() stream across calls; how
 // far a frame advances it depends on that frame's early stop, which no pipelined implementation can know in time.)
 #include <cuda_runtime.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
@@ -25,6 +26,7 @@
 
 namespace {
 
+constexpr int kMaxInflight = 4;  // shared mode: unfinished frames per context, at most (RPE_SEQ_INFLIGHT, default 2)
 constexpr int kTableSlots = 4;  // pinned sample tables per context; a slot is reused only after its frame's copy ran
 
 struct SeqContext {
@@ -35,8 +37,8 @@ struct SeqContext {
   int next = 0;
   // shared mode: at most kInflight frames enqueued and unfinished per context, so that a sequence takes frames at the
   // pace its GPU (and its PCIe path) works them off instead of at the pace its host thread can enqueue them
-  cudaEvent_t done[2] = {};
-  bool done_used[2] = {};
+  cudaEvent_t done[kMaxInflight] = {};
+  bool done_used[kMaxInflight] = {};
   int done_next = 0;
 };
 
@@ -65,6 +67,7 @@ struct rpe_seq {
   std::mutex mu;
   std::condition_variable cv_go, cv_done;
   Job job;
+  int inflight = 2;
   std::atomic<int> local_done{0};  // shared mode: frames this sequence has taken in the current run
   unsigned long long generation = 0;
   int running = 0;
@@ -178,7 +181,7 @@ void worker_main(rpe_seq* s, int worker) {
         }
         if (cudaEventRecord(sc.done[d], (cudaStream_t)rpe_stream(sc.ctx)) != cudaSuccess) rc = RPE_ERR_CUDA;
         sc.done_used[d] = true;
-        sc.done_next = (d + 1) % 2;
+        sc.done_next = (d + 1) % s->inflight;
       }
     } else
     for (int i = worker; i < job.n_frames && rc == RPE_OK; i += T, ++k) {
@@ -216,6 +219,10 @@ int rpe_seq_create(const rpe_seq_params* params, rpe_seq** out) {
   if (params->n_contexts < 1 || params->n_contexts > 64 || params->n_threads < 1 || params->H < 1) return RPE_ERR_ARG;
   rpe_seq* s = new rpe_seq();
   s->p = *params;
+  if (const char* e = getenv("RPE_SEQ_INFLIGHT")) {
+    const int v = atoi(e);
+    s->inflight = v < 1 ? 1 : (v > kMaxInflight ? kMaxInflight : v);
+  }
   if (s->p.n_threads > s->p.n_contexts) s->p.n_threads = s->p.n_contexts;
   if (cudaSetDevice(s->p.device) != cudaSuccess) {
     (void)cudaGetLastError();
@@ -233,7 +240,7 @@ int rpe_seq_create(const rpe_seq_params* params, rpe_seq** out) {
     }
     for (int k = 0; k < kTableSlots && !rc; ++k)
       if (cudaEventCreateWithFlags(&sc.ev[k], cudaEventDisableTiming) != cudaSuccess) rc = RPE_ERR_CUDA;
-    for (int k = 0; k < 2 && !rc; ++k)
+    for (int k = 0; k < kMaxInflight && !rc; ++k)
       if (cudaEventCreateWithFlags(&sc.done[k], cudaEventDisableTiming) != cudaSuccess) rc = RPE_ERR_CUDA;
     if (rc) break;
   }
@@ -256,7 +263,10 @@ static int seq_run_job(rpe_seq* s, const Job& job) {
     std::unique_lock<std::mutex> lk(s->mu);
     s->job = job;
     s->local_done.store(0);
-    for (SeqContext& sc : s->ctxs) sc.done_used[0] = sc.done_used[1] = false;
+    for (SeqContext& sc : s->ctxs) {
+      for (int k = 0; k < kMaxInflight; ++k) sc.done_used[k] = false;
+      sc.done_next = 0;
+    }
     s->running = s->p.n_threads;
     ++s->generation;
     s->cv_go.notify_all();
@@ -325,7 +335,7 @@ int rpe_seq_destroy(rpe_seq* s) {
     if (sc.tables) cudaFreeHost(sc.tables);
     for (int k = 0; k < kTableSlots; ++k)
       if (sc.ev[k]) cudaEventDestroy(sc.ev[k]);
-    for (int k = 0; k < 2; ++k)
+    for (int k = 0; k < kMaxInflight; ++k)
       if (sc.done[k]) cudaEventDestroy(sc.done[k]);
   }
   for (rpe_sampler* sm : s->samplers)
