@@ -460,7 +460,7 @@ __device__ __forceinline__ unsigned int sign_words(float2 s) {
   return d;
 }
 
-template <int HPT, int TILE, int THREADS, int MINB, int SUB, bool PCOUNT>
+template <int HPT, int TILE, int THREADS, int MINB, int SUB, int PCOUNT>
 __global__ void __launch_bounds__(THREADS, MINB)
 score3d_raw_kernel(const float* __restrict__ xw, const float* __restrict__ xc, int n, int npairs_pad, int pairs_per_cta,
                    const HypFast* __restrict__ fast, const HypGen* __restrict__ gen, int slot_begin, int slot_end, float thr,
@@ -1249,7 +1249,7 @@ static int launch_multi(const FrameView& f, const HypGen* gen, const HypFast* fa
 static bool g_use_packed = true;
 static int g_nosync = 0;
 void set_nosync(int v) { g_nosync = v; }
-static int g_variant = 14;  // HPT=2, 1024-pair stages, 512 threads, 1 CTA per SM (best of the sweep in profiles/r01_variant_sweep.md)
+static int g_variant = 14;  // HPT=2, 1024-pair stages, 512 threads, 1 CTA per SM, 4-pair groups (profiles/r01_variant_sweep.md, r02_variant_sweep.md)
 void set_use_packed(bool v) { g_use_packed = v; }
 bool use_packed() { return g_use_packed; }
 void set_score_variant(int v) { g_variant = v; }
@@ -1282,8 +1282,8 @@ static int launch_variant(const FrameView& f, const HypGen* gen, const HypFast* 
   cudaGetDevice(&dev);
   if (PACKED && frame_raw_ok(f, 2)) {  // stream the caller's arrays: no packed copy
     constexpr int RT = (TILE > 1024 / MINB ? 1024 / MINB : TILE);  // 144 bytes of shared memory per pair and CTA
-    static const bool pcount = getenv("RPE_PCOUNT") ? getenv("RPE_PCOUNT")[0] != '0' : true;  // packed sign count (1 % faster, r02d)
-    auto rk = pcount ? score3d_raw_kernel<HPT, RT, THREADS, MINB, SUB, true> : score3d_raw_kernel<HPT, RT, THREADS, MINB, SUB, false>;
+    static const int pcount = getenv("RPE_PCOUNT") ? getenv("RPE_PCOUNT")[0] - '0' : 1;  // 1: packed sign count (1 % faster, r02d)
+    auto rk = pcount ? score3d_raw_kernel<HPT, RT, THREADS, MINB, SUB, 1> : score3d_raw_kernel<HPT, RT, THREADS, MINB, SUB, 0>;
     size_t rsmem = (size_t)RT * 3 * sizeof(float4) + 4 * (size_t)RT * 6 * sizeof(float) + 2 * sizeof(uint64_t) + 16;
     if (MINB == 1 && g_exclusive_sm && rsmem < (size_t)116 * 1024) rsmem = (size_t)116 * 1024;
     static std::atomic<bool> rattr_set[64];
@@ -1341,8 +1341,12 @@ int launch_score_fast(int method, const FrameView& f, const HypGen* gen, const H
     case 1: RPE_V(true, 2, 512, 256, 2, 8);   // <= 512 slots
     case 7: RPE_V(true, 2, 256, 128, 4, 8);   // <= 256 slots
     case 16: RPE_V(true, 2, 256, 64, 8, 8);   // <= 128 slots
+    // round-2 sweep of the raw-array scorer (profiles/r02_variant_sweep.md)
+    case 24: RPE_V(true, 2, 1024, 512, 1, 8);   // the round-1 default (8-pair groups)
+    case 27: RPE_V(true, 4, 1024, 256, 1, 4);
     default:
-    case 14: RPE_V(true, 2, 1024, 512, 1, 8);  // the full 1024-hypothesis column (profiles/r01_variant_sweep.md)
+    case 14: RPE_V(true, 2, 1024, 512, 1, 4);  // the full 1024-hypothesis column; 4-pair groups keep the X0 / X1 / X2 runs of FFMA2
+               // on the operand-reuse cache more often than 8-pair groups do (3 % faster, profiles/r02_variant_sweep.md)
   }
 #undef RPE_V
 }
