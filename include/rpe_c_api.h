@@ -384,6 +384,12 @@ int rpe_last_stage_ms(rpe_ctx* ctx, float ms[8]);
  * this context since the last reset, complete after rpe_sync (each launch gets its own event pair on the stream the
  * kernel runs on; nothing is synchronised to collect them). The roofline's `kernel_ms` over a timed region. */
 int rpe_scorer_time_stats(rpe_ctx* ctx, double* sum_ms, long long* count, int reset);
+/* Device-wide companion (all contexts of `device`, launches timed with stage timing on): the scorers of consecutive
+ * frames are launched into two alternating "lane" streams, so the next launch takes over each SM the moment the previous
+ * launch's CTA leaves it and the event pairs of neighbouring launches overlap. This call returns the length of the UNION
+ * of the launches' [start, end] event intervals (start = inputs ready and lane free) and the number of launches: sum / count is the device time one launch costs inside a pipelined region. Complete after the contexts
+ * have been synchronised. */
+int rpe_scorer_busy_stats(int device, double* sum_ms, long long* count, int reset);
 int rpe_enable_stage_timing(rpe_ctx* ctx, int enable);
 
 #ifdef __cplusplus

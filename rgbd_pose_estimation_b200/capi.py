@@ -183,6 +183,7 @@ _sig("rpe_measure_ffma_tflops", C.c_int, [_vp, C.c_int, C.POINTER(C.c_double), C
 _sig("rpe_last_stage_ms", C.c_int, [_vp, _vp])
 _sig("rpe_enable_stage_timing", C.c_int, [_vp, C.c_int])
 _sig("rpe_scorer_time_stats", C.c_int, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_longlong), C.c_int])
+_sig("rpe_scorer_busy_stats", C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_longlong), C.c_int])
 _sig("rpe_min_ev", C.c_int, [_vp, _vp, C.c_int, _vp])
 _sig("rpe_min_ms", C.c_int, [_vp, _vp, C.c_int, _vp, _vp])
 _sig("rpe_min_ev_host", C.c_int, [_vp, C.c_int, _vp])
@@ -203,7 +204,7 @@ DECLARED_SYMBOLS = [
     "rpe_sim_2d_3d_nl_device", "rpe_min_ev", "rpe_min_ms", "rpe_min_ev_host", "rpe_min_ev_host_f64", "rpe_min_ms_host",
     "rpe_sim_3d_3d_device_to", "rpe_sampler_reseed", "rpe_seq_create", "rpe_seq_run", "rpe_seq_run_shared",
     "rpe_seq_context", "rpe_seq_num_contexts", "rpe_seq_last_error", "rpe_seq_destroy", "rpe_download", "rpe_ao", "rpe_ao_ransac",
-    "rpe_measure_ffma_tflops", "rpe_last_stage_ms", "rpe_enable_stage_timing", "rpe_scorer_time_stats",
+    "rpe_measure_ffma_tflops", "rpe_last_stage_ms", "rpe_enable_stage_timing", "rpe_scorer_time_stats", "rpe_scorer_busy_stats",
 ]
 
 

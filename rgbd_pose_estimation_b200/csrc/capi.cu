@@ -9,6 +9,8 @@
 #include <string.h>
 
 #include <string>
+#include <algorithm>
+#include <atomic>
 #include <cstdlib>
 #include <deque>
 #include <mutex>
@@ -531,12 +533,20 @@ struct ScorerLane {
   cudaStream_t stream = nullptr;
   bool tried = false;
 };
-ScorerLane g_lane[64];
+constexpr int kMaxLanes = 4;
+ScorerLane g_lane[64][kMaxLanes];
+std::atomic<unsigned int> g_lane_rr[64];
 const bool g_lane_enabled = !(getenv("RPE_SCORER_LANE") && getenv("RPE_SCORER_LANE")[0] == '0');
+// Scorers of consecutive calls alternate between TWO lane streams: the next scorer's CTAs take over an SM the moment the
+// previous scorer's CTA leaves it, which hides the launch gap and the spread of the CTAs' finishing times (resident
+// frames 0.1813 -> 0.1789 ms, host frames 0.208 -> 0.193 ms per frame, round 2: under host-to-device DMA traffic a
+// launch into a busy lane starts ~30 us late). RPE_SCORER_LANES=k overrides (1 = strictly back to back, up to 4).
+const int g_lane_count = getenv("RPE_SCORER_LANES") ? std::max(1, std::min(kMaxLanes, atoi(getenv("RPE_SCORER_LANES")))) : 2;
 
 ScorerLane* lane_for(rpe_ctx* ctx) {
   if (!g_lane_enabled || ctx->device < 0 || ctx->device >= 64 || !ctx->ev_ok) return nullptr;
-  ScorerLane* L = &g_lane[ctx->device];
+  const unsigned int which = g_lane_count > 1 ? g_lane_rr[ctx->device].fetch_add(1u, std::memory_order_relaxed) % (unsigned int)g_lane_count : 0u;
+  ScorerLane* L = &g_lane[ctx->device][which];
   std::lock_guard<std::mutex> g(L->mu);
   if (!L->tried) {
     L->tried = true;
@@ -546,6 +556,57 @@ ScorerLane* lane_for(rpe_ctx* ctx) {
     }
   }
   return L->stream ? L : nullptr;
+}
+
+// ---- time the device spends in scorer launches (two lanes overlap the head of one launch with the tail of the
+// previous one, so a launch's own event pair no longer is its cost): per device, every timed launch leaves its
+// [start, end] event interval (start = the moment the launch could begin: its inputs were ready and its lane free), and
+// rpe_scorer_busy_stats returns the length of the UNION of those intervals and their number. Idle time between
+// launches is not counted, time a launch spends queued behind another one is counted once. Events live in a
+// per-device ring and are turned into times (relative to one reference event) 64 launches later — far more than
+// can be in flight.
+struct LaneClock {
+  static constexpr int kRing = 128;
+  std::mutex mu;  // also orders the submissions of all lanes of the device
+  cudaEvent_t start[kRing] = {}, end[kRing] = {}, ref = nullptr;
+  bool live[kRing] = {};
+  bool ref_set = false;
+  int next = 0;
+  bool tried = false, ok = false;
+  std::vector<std::pair<float, float>> iv;  // ms since ref
+};
+LaneClock g_clock[64];
+
+void lane_clock_fold(LaneClock& c, int j) {
+  if (!c.live[j]) return;
+  float a = 0.f, b = 0.f;
+  if (cudaEventElapsedTime(&a, c.ref, c.start[j]) != cudaSuccess || cudaEventElapsedTime(&b, c.ref, c.end[j]) != cudaSuccess) {
+    (void)cudaGetLastError();  // not finished: leave it for the next drain
+    return;
+  }
+  if (c.iv.size() < ((size_t)1 << 22)) c.iv.emplace_back(a, b);
+  c.live[j] = false;
+}
+// caller holds c.mu; `stream` is the lane the launch goes to
+int lane_clock_claim(LaneClock& c, cudaStream_t stream) {
+  if (!c.tried) {
+    c.tried = true;
+    c.ok = cudaEventCreate(&c.ref) == cudaSuccess;
+    for (int k = 0; k < LaneClock::kRing && c.ok; ++k)
+      c.ok = cudaEventCreate(&c.start[k]) == cudaSuccess && cudaEventCreate(&c.end[k]) == cudaSuccess;
+    if (!c.ok) (void)cudaGetLastError();
+  }
+  if (!c.ok) return -1;
+  if (!c.ref_set) {
+    cudaEventRecord(c.ref, stream);
+    c.ref_set = true;
+  }
+  const int k = c.next;
+  c.next = (k + 1) % LaneClock::kRing;
+  lane_clock_fold(c, (k + LaneClock::kRing / 2) % LaneClock::kRing);
+  if (c.live[k]) lane_clock_fold(c, k);  // (only if the half-ring fold found it unfinished)
+  c.live[k] = true;
+  return k;
 }
 
 // score the slot range with the best available kernel, including the exact fix-up
@@ -559,11 +620,16 @@ int score_range(rpe_ctx* ctx, int method, int slot_begin, int slot_end, Thresh t
     const int rk = tm ? fast_ring_claim(ctx) : 0;
     if (lane) {
       CK(cudaEventRecord(ctx->ev_lane[0], ctx->stream));  // everything the scorer reads has been enqueued before this
+      LaneClock& clk = g_clock[ctx->device];
+      std::lock_guard<std::mutex> gd(clk.mu);
       std::lock_guard<std::mutex> g(lane->mu);
       CK(cudaStreamWaitEvent(lane->stream, ctx->ev_lane[0], 0));
+      const int ck = tm ? lane_clock_claim(clk, lane->stream) : -1;
       if (tm) cudaEventRecord(ctx->ev_ring[2 * rk], lane->stream);
+      if (ck >= 0) cudaEventRecord(clk.start[ck], lane->stream);
       nseg = launch_score_fast(method, f, ctx->d_gen, ctx->d_fast, slot_begin, slot_end, th, ctx->d_votes, ctx->d_stats,
                                ctx->wl, ctx->num_sms, lane->stream);
+      if (ck >= 0) cudaEventRecord(clk.end[ck], lane->stream);
       if (tm) cudaEventRecord(ctx->ev_ring[2 * rk + 1], lane->stream);
       CK(cudaEventRecord(ctx->ev_lane[1], lane->stream));
       CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_lane[1], 0));
@@ -1023,7 +1089,16 @@ static int create_common(int device, void* stream, bool own, rpe_ctx** out) {
     return RPE_ERR_NO_DEVICE;  // kernels are built for sm_100a only
   }
   if (own) {
-    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    // The context's own stream carries the small kernels of a frame (generation, fix-up, replay, mask, refits). It gets
+    // the highest priority, the scorer lanes the lowest: when a scorer CTA leaves an SM, the waiting CTAs of another
+    // frame's small kernels go first and the next scorer never waits for its inputs (RPE_STREAM_PRIORITY=0: all equal).
+    int prio_lo = 0, prio_hi = 0;
+    static const bool use_prio = !(getenv("RPE_STREAM_PRIORITY") && getenv("RPE_STREAM_PRIORITY")[0] == '0');
+    if (use_prio && cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi) != cudaSuccess) {
+      (void)cudaGetLastError();
+      prio_lo = prio_hi = 0;
+    }
+    if (cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, use_prio ? prio_hi : 0) != cudaSuccess) {
       delete ctx;
       return RPE_ERR_CUDA;
     }
@@ -2017,6 +2092,30 @@ int rpe_scorer_time_stats(rpe_ctx* ctx, double* sum_ms, long long* count, int re
   if (reset) {
     ctx->fast_sum_ms = 0.0;
     ctx->fast_count = 0;
+  }
+  return RPE_OK;
+}
+int rpe_scorer_busy_stats(int device, double* sum_ms, long long* count, int reset) {
+  if (device < 0 || device >= 64) return RPE_ERR_ARG;
+  LaneClock& c = g_clock[device];
+  std::lock_guard<std::mutex> g(c.mu);
+  if (c.ok)
+    for (int i = 0; i < LaneClock::kRing; ++i) lane_clock_fold(c, (c.next + i) % LaneClock::kRing);
+  std::vector<std::pair<float, float>> v = c.iv;
+  std::sort(v.begin(), v.end());
+  double sum = 0.0;
+  float covered = -1e30f;
+  for (const auto& e : v) {
+    const float lo = e.first > covered ? e.first : covered;
+    if (e.second > lo) sum += (double)(e.second - lo);
+    if (e.second > covered) covered = e.second;
+  }
+  if (sum_ms) *sum_ms = sum;
+  if (count) *count = (long long)v.size();
+  if (reset) {
+    c.iv.clear();
+    for (int i = 0; i < LaneClock::kRing; ++i) c.live[i] = false;  // (a launch still running is dropped)
+    c.ref_set = false;
   }
   return RPE_OK;
 }
