@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Summarise an `ncu --metrics gpu__time_duration.sum --csv` launch list: launches, mean duration and share of the
-serialised kernel time per kernel (the ffma_bench_kernel peak microbenchmark runs outside the timed region and is left out).
+serialised kernel time per kernel (the ffma_bench_kernel peak microbenchmark and the sim_kernel frame generator run outside the timed region and are left out).
 
     python tools/launch_list_summary.py gpurun_out/r01f_launches.csv "<command that was profiled>" > profiles/r01f_launch_list_summary.json
 """
@@ -23,8 +23,8 @@ def main():
         if len(r) <= iv or r[im] != "gpu__time_duration.sum":
             continue
         name = re.sub(r"\(.*", "", r[ik]).strip()
-        if "ffma_bench_kernel" in name:
-            continue
+        if "ffma_bench_kernel" in name or name.startswith("sim_kernel"):
+            continue  # peak microbenchmark / device-side frame generation: both run before the timed region
         v = float(r[iv].replace(",", ""))
         unit = r[iu]
         us = v / 1e3 if unit in ("ns", "nsecond") else (v * 1e3 if unit in ("ms", "msecond") else v)
@@ -34,7 +34,7 @@ def main():
     kernels = [{"kernel": k, "launches": cnt[k], "mean_us": round(tot[k] / cnt[k], 3), "share_pct": round(100 * tot[k] / total, 2)}
                for k in sorted(tot, key=lambda k: -tot[k])]
     print(json.dumps({"command": command,
-                      "note": "ffma_bench_kernel (peak microbenchmark, outside the timed region) excluded from shares; per-launch "
+                      "note": "ffma_bench_kernel (peak microbenchmark) and sim_kernel (device-side frame generation), both outside the timed region, excluded from shares; per-launch "
                               "times are cold-cache and serialised; in the live step the other kernels overlap the scorer from other streams",
                       "kernels": kernels}, indent=1))
 
