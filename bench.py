@@ -547,7 +547,7 @@ def run_gpu(args, rank, world, local_rank):
 
     if rank == 0:
         h2d_step = fps * (2 * frame_bytes + N_HYP * 16)
-        d2h_step = fps * (2 * N_CORR * 2 + 3 * 72 + 12)
+        d2h_step = fps * (mask_d2h_bytes() + 3 * 72 + 12)
         e2e_frames_s_gpu = frames_done_e2e / (ms_e2e * 1e-3)  # rank 0's share (dynamic hand-out at N > 1)
         e2e_h2d_gbs = e2e_frames_s_gpu * (2 * frame_bytes + N_HYP * 16) / 1e9
         line = {
@@ -579,7 +579,9 @@ def run_gpu(args, rank, world, local_rank):
                     "clocks": clocks_e2e,
                     "path": f"rpe_seq_run: {args.threads} native issue threads x {args.contexts} contexts per GPU; per frame "
                             "sample-table draw + rpe_upload(host page-locked) + rpe_ransac_async + rpe_refit_async x2 + "
-                            "mask/pose D2H"},
+                            "mask/pose D2H" + (" (inlier matrix sent as one bit per flag and expanded into the caller's "
+                                               "16-bit matrix by the issuing threads, rpe_set_mask_transfer(1))"
+                                               if mask_bits_on() else "")},
             "gpu_launches": launches,
             "roofline": roofline,
             "stage_ms_mean": stage_mean,
@@ -659,6 +661,15 @@ def timed_shared(seq, shared, total, torch, dist, dev, barrier):
     return ms, done
 
 
+def mask_bits_on():
+    """RPE_SEQ_MASK_BITS=1: the sequence runner sends the inlier matrix as bits (rpe_set_mask_transfer); off by default"""
+    return os.environ.get("RPE_SEQ_MASK_BITS", "0")[:1] == "1"
+
+
+def mask_d2h_bytes():
+    return 2 * ((N_CORR + 31) // 32) * 4 if mask_bits_on() else 2 * N_CORR * 2
+
+
 def measure_h2d_ceiling(rpe, torch, dist, dev, local_rank, h_xw, h_xc, barrier, seconds=0.25):
     """All ranks at once, no compute: (a) rpe_upload of the e2e leg's own page-locked frames (2 x 3.7 MB per frame) on 4
     contexts (streams); (b) the same with the e2e leg's device-to-host traffic beside it (one 1.2 MB mask per frame on a
@@ -666,8 +677,8 @@ def measure_h2d_ceiling(rpe, torch, dist, dev, local_rank, h_xw, h_xc, barrier, 
     try:
         cs = [rpe.Context(local_rank) for _ in range(4)]
         nbytes = 2 * h_xw[0].nbytes
-        d_mask = torch.zeros(2 * N_CORR, dtype=torch.int16, device=dev)
-        h_masks = [torch.empty(2 * N_CORR, dtype=torch.int16, pin_memory=True) for _ in range(4)]
+        d_mask = torch.zeros(mask_d2h_bytes() // 2, dtype=torch.int16, device=dev)
+        h_masks = [torch.empty(mask_d2h_bytes() // 2, dtype=torch.int16, pin_memory=True) for _ in range(4)]
         side = [torch.cuda.Stream(device=dev) for _ in range(4)]
 
         def burst(reps, with_d2h):
@@ -717,7 +728,8 @@ def measure_h2d_ceiling(rpe, torch, dist, dev, local_rank, h_xw, h_xc, barrier, 
         out = dict(both)
         out["upload_only"] = up
         out["how"] = ("all ranks concurrently, no compute: rpe_upload of 2 x 3.7 MB page-locked arrays per frame on 4 streams "
-                      "per GPU, with one 1.2 MB device-to-host copy per frame beside it (the e2e leg's own traffic pattern); "
+                      f"per GPU, with one {mask_d2h_bytes() / 1e6:.2f} MB device-to-host copy per frame beside it (the e2e leg's "
+                      "own traffic pattern: the inlier matrix " + ("as bits" if mask_bits_on() else "as 16-bit flags") + "); "
                       "upload_only = the same without the device-to-host copies; rates count the uploaded bytes")
         return out
     except Exception as e:

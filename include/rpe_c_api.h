@@ -106,6 +106,9 @@ int rpe_destroy(rpe_ctx* ctx);
 const char* rpe_last_error(const rpe_ctx* ctx);
 void* rpe_stream(rpe_ctx* ctx);
 int rpe_sync(rpe_ctx* ctx);
+/* Non-blocking companion of rpe_sync: hands over (fills the caller's rpe_result structs, expands bit-form masks) every
+ * result of the asynchronous calls whose device work has finished, oldest first, and returns without waiting for the rest. */
+int rpe_poll(rpe_ctx* ctx);
 /* Number of kernels this context has launched since creation (bench.py's gpu_launches). */
 long long rpe_launch_count(const rpe_ctx* ctx);
 
@@ -391,6 +394,16 @@ int rpe_scorer_time_stats(rpe_ctx* ctx, double* sum_ms, long long* count, int re
  * have been synchronised. */
 int rpe_scorer_busy_stats(int device, double* sum_ms, long long* count, int reset);
 int rpe_enable_stage_timing(rpe_ctx* ctx, int enable);
+/* How the inlier matrix of the ASYNCHRONOUS calls (rpe_ransac_async, rpe_ransac_sharded_async, the sequence runner) reaches
+ * the caller's `mask` buffer. 0 (default): the n x cols matrix of 16-bit flags is copied as it is (the reference's
+ * setInlier layout, PnPPoseAdapter.hpp:196-237: 2 bytes per flag, 1.2 MB for a dense 3-D / 3-D frame). 1: the device
+ * sends one BIT per flag (77 KB) into the tail of the same buffer and the thread that collects the result (rpe_sync, or
+ * the next call once 256 results are in flight) expands it in place — the buffer holds exactly the same matrix afterwards,
+ * with 1/16 of the device-to-host bytes on the bus, for 0.04-0.1 ms of host work per dense frame (measured, round 2: on
+ * the 8-GPU box the concurrent-upload ceiling rises from 190 to 226 GB/s, but with 4 host cores per GPU the expansion
+ * costs the issuing threads more than that — 21.1 k against 22.7 k frames/s — so this is an opt-in for hosts with
+ * cores to spare). Blocking calls always copy the matrix. */
+int rpe_set_mask_transfer(rpe_ctx* ctx, int mode);
 
 #ifdef __cplusplus
 }

@@ -182,6 +182,8 @@ _sig("rpe_ao_ransac", C.c_int, [_vp, _vp, C.c_int, _vp, _vp])
 _sig("rpe_measure_ffma_tflops", C.c_int, [_vp, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)])
 _sig("rpe_last_stage_ms", C.c_int, [_vp, _vp])
 _sig("rpe_enable_stage_timing", C.c_int, [_vp, C.c_int])
+_sig("rpe_set_mask_transfer", C.c_int, [_vp, C.c_int])
+_sig("rpe_poll", C.c_int, [_vp])
 _sig("rpe_scorer_time_stats", C.c_int, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_longlong), C.c_int])
 _sig("rpe_scorer_busy_stats", C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_longlong), C.c_int])
 _sig("rpe_min_ev", C.c_int, [_vp, _vp, C.c_int, _vp])
@@ -204,7 +206,7 @@ DECLARED_SYMBOLS = [
     "rpe_sim_2d_3d_nl_device", "rpe_min_ev", "rpe_min_ms", "rpe_min_ev_host", "rpe_min_ev_host_f64", "rpe_min_ms_host",
     "rpe_sim_3d_3d_device_to", "rpe_sampler_reseed", "rpe_seq_create", "rpe_seq_run", "rpe_seq_run_shared",
     "rpe_seq_context", "rpe_seq_num_contexts", "rpe_seq_last_error", "rpe_seq_destroy", "rpe_download", "rpe_ao", "rpe_ao_ransac",
-    "rpe_measure_ffma_tflops", "rpe_last_stage_ms", "rpe_enable_stage_timing", "rpe_scorer_time_stats", "rpe_scorer_busy_stats",
+    "rpe_measure_ffma_tflops", "rpe_last_stage_ms", "rpe_enable_stage_timing", "rpe_scorer_time_stats", "rpe_scorer_busy_stats", "rpe_set_mask_transfer", "rpe_poll",
 ]
 
 
@@ -800,6 +802,15 @@ class Context:
 
     def stream(self):
         return int(lib.rpe_stream(self._h) or 0)
+
+    def set_mask_transfer(self, mode):
+        """0: asynchronous calls copy the int16 inlier matrix as it is; 1: they send one bit per flag and the collecting
+        thread expands it in place (same matrix in the caller's buffer after sync / poll, 1/16 of the D2H bytes)."""
+        _check(lib.rpe_set_mask_transfer(self._h, int(mode)), self._h)
+
+    def poll(self):
+        """Hand over the results of asynchronous calls that have finished, without waiting for the others."""
+        _check(lib.rpe_poll(self._h), self._h)
 
     def enable_stage_timing(self, on=True):
         """False/0: off; True/1: every stage; 2: only the events around the tiled scoring kernel."""

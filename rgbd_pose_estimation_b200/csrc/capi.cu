@@ -122,6 +122,10 @@ struct rpe_ctx {
   unsigned int wl_want = 0;       // grow to this many entries before the next scoring call (set after an overflow)
   bool wl_fixed = false;          // test hook in force: no automatic growth
   int16_t* d_mask = nullptr;
+  uint32_t* d_maskbits = nullptr;  // the mask as one bit per flag (rpe_set_mask_transfer(1)), 3 x ceil(n / 32) words
+  size_t maskbits_cap = 0;
+  int mask_transfer = 0;           // 0: the int16 matrix goes to the host as it is, 1: bits + expansion on the host
+  std::vector<uint32_t> bits_scratch;
   size_t mask_cap = 0;
   int mask_cols = 0;
   RefitBuffers rb;
@@ -139,6 +143,8 @@ struct rpe_ctx {
     rpe_result* out;
     int slot;
     bool is_refit, gn;
+    int16_t* mask_expand = nullptr;  // bit form waiting in the tail of this host buffer (see expand_mask)
+    int mask_n = 0, mask_cols = 0;
   };
   std::deque<Pending> pending;
   int next_slot = 0;                      // staging slots are handed out round-robin
@@ -289,6 +295,13 @@ int ensure_corr_capacity(rpe_ctx* ctx, int n, bool own_copy) {
     if (ctx->d_mask) cudaFree(ctx->d_mask);
     CK(cudaMalloc(&ctx->d_mask, mask_need * sizeof(int16_t)));
     ctx->mask_cap = mask_need;
+  }
+  const size_t bits_need = 3 * (((size_t)n + 31) / 32);
+  if (bits_need > ctx->maskbits_cap) {
+    if (ctx->d_maskbits) cudaFree(ctx->d_maskbits);
+    ctx->d_maskbits = nullptr;
+    CK(cudaMalloc(&ctx->d_maskbits, bits_need * sizeof(uint32_t)));
+    ctx->maskbits_cap = bits_need;
   }
   const int blocks = (n + 255) / 256;
   if (blocks > ctx->rb.max_blocks) {
@@ -443,11 +456,38 @@ void note_overflow(rpe_ctx* ctx, int slot) {
   }
 }
 
-int finish_pending(rpe_ctx* ctx) {
-  for (const rpe_ctx::Pending& p : ctx->pending) {
-    fill_result(ctx, p.out, p.slot, p.is_refit, p.gn);
-    note_overflow(ctx, p.slot);
+// rpe_set_mask_transfer(1): the device sent cols x ceil(n / 32) words of flag bits into the TAIL of the caller's mask
+// buffer; turn them into the reference's n x cols matrix of 16-bit flags (setInlier layout) in place. The words are
+// moved to a scratch vector first (77 KB for a dense frame), so the expansion may overwrite where they were.
+struct ExpandLut {
+  alignas(16) int16_t v[256][8];
+  ExpandLut() {
+    for (int b = 0; b < 256; ++b)
+      for (int k = 0; k < 8; ++k) v[b][k] = (int16_t)((b >> k) & 1);
   }
+};
+void expand_mask(rpe_ctx* ctx, int16_t* mask, int n, int cols) {
+  static const ExpandLut lut;
+  const size_t wpc = ((size_t)n + 31) / 32, words = wpc * (size_t)cols;
+  const size_t bytes = (size_t)n * cols * sizeof(int16_t);
+  ctx->bits_scratch.resize(words);
+  memcpy(ctx->bits_scratch.data(), reinterpret_cast<const char*>(mask) + bytes - words * sizeof(uint32_t), words * sizeof(uint32_t));
+  for (int col = 0; col < cols; ++col) {
+    const unsigned char* src = reinterpret_cast<const unsigned char*>(ctx->bits_scratch.data() + (size_t)col * wpc);
+    int16_t* dst = mask + (size_t)col * n;
+    const int full = n / 8;
+    for (int i = 0; i < full; ++i) memcpy(dst + 8 * (size_t)i, lut.v[src[i]], 16);
+    for (int c = 8 * full; c < n; ++c) dst[c] = (int16_t)((src[c >> 3] >> (c & 7)) & 1);
+  }
+}
+void deliver(rpe_ctx* ctx, const rpe_ctx::Pending& p) {
+  fill_result(ctx, p.out, p.slot, p.is_refit, p.gn);
+  note_overflow(ctx, p.slot);
+  if (p.mask_expand) expand_mask(ctx, p.mask_expand, p.mask_n, p.mask_cols);
+}
+
+int finish_pending(rpe_ctx* ctx) {
+  for (const rpe_ctx::Pending& p : ctx->pending) deliver(ctx, p);
   ctx->pending.clear();
   if (ctx->timing_fast && ctx->ev_ok) fast_ring_drain(ctx);
   if ((ctx->timing || ctx->timing_fast) && ctx->ev_ok) {
@@ -485,8 +525,7 @@ int claim_slot(rpe_ctx* ctx, int* slot) {
   if ((int)ctx->pending.size() >= kNumStaging) {
     const rpe_ctx::Pending p = ctx->pending.front();
     CK(cudaEventSynchronize(ctx->ev_slot[p.slot]));
-    fill_result(ctx, p.out, p.slot, p.is_refit, p.gn);
-    note_overflow(ctx, p.slot);
+    deliver(ctx, p);
     ctx->pending.pop_front();
   }
   *slot = ctx->next_slot;
@@ -494,9 +533,14 @@ int claim_slot(rpe_ctx* ctx, int* slot) {
   return RPE_OK;
 }
 // the result whose copies were just enqueued becomes pending
-int push_pending(rpe_ctx* ctx, rpe_result* out, int slot, bool is_refit, bool gn) {
+int push_pending(rpe_ctx* ctx, rpe_result* out, int slot, bool is_refit, bool gn, int16_t* mask_expand = nullptr, int mask_n = 0,
+                 int mask_cols = 0) {
   CK(cudaEventRecord(ctx->ev_slot[slot], ctx->stream));
-  ctx->pending.push_back(rpe_ctx::Pending{out, slot, is_refit, gn});
+  rpe_ctx::Pending p{out, slot, is_refit, gn};
+  p.mask_expand = mask_expand;
+  p.mask_n = mask_n;
+  p.mask_cols = mask_cols;
+  ctx->pending.push_back(p);
   return RPE_OK;
 }
 
@@ -662,7 +706,12 @@ int do_finish(rpe_ctx* ctx, int method, Thresh th, rpe_result* out, int16_t* mas
   stamp(ctx, ST_MASK);
   ctx->mask_cols = method_mask_cols(method);
   order_after_mask_copy(ctx);
-  launch_mask(method, f, ctx->d_pose, th, ctx->d_mask, ctx->d_kabsch, ctx->rb, ctx->d_stats, ctx->stream);
+  const size_t mask_bytes = (size_t)ctx->n * ctx->mask_cols * sizeof(int16_t);
+  // bit form for the host (16 x fewer bytes on the bus, expanded by whoever collects the result): asynchronous calls only —
+  // a blocking caller would wait for the expansion, while the plain copy hides behind the refits on the side stream
+  const bool as_bits = mask && ctx->mask_transfer == 1 && !blocking && mask_bytes >= (size_t)256 * 1024 && ctx->d_maskbits;
+  launch_mask(method, f, ctx->d_pose, th, ctx->d_mask, ctx->d_kabsch, ctx->rb, ctx->d_stats, ctx->stream,
+              as_bits ? ctx->d_maskbits : nullptr);
   ctx->launches += 1;
   ctx->kabsch_valid = method_uses_3d(method);
   ctx->suff_valid = true;
@@ -672,8 +721,13 @@ int do_finish(rpe_ctx* ctx, int method, Thresh th, rpe_result* out, int16_t* mas
   int rc = claim_slot(ctx, &slot);
   if (rc) return rc;
   CK(cudaMemcpyAsync(&ctx->h_pose[slot], ctx->d_pose, sizeof(ReplayOut), cudaMemcpyDeviceToHost, ctx->stream));
+  if (as_bits) {
+    const size_t wbytes = (((size_t)ctx->n + 31) / 32) * ctx->mask_cols * sizeof(uint32_t);
+    CK(cudaMemcpyAsync(reinterpret_cast<char*>(mask) + mask_bytes - wbytes, ctx->d_maskbits, wbytes, cudaMemcpyDeviceToHost, ctx->stream));
+    return push_pending(ctx, out, slot, false, false, mask, ctx->n, ctx->mask_cols);
+  }
   if (mask) {
-    const size_t bytes = (size_t)ctx->n * ctx->mask_cols * sizeof(int16_t);
+    const size_t bytes = mask_bytes;
     if (ctx->d2h_stream && bytes >= (size_t)256 * 1024) {
       CK(cudaEventRecord(ctx->ev_mask_ready, ctx->stream));
       CK(cudaStreamWaitEvent(ctx->d2h_stream, ctx->ev_mask_ready, 0));
@@ -1194,6 +1248,7 @@ int rpe_destroy(rpe_ctx* ctx) {
   cudaFree(ctx->wl.entries);
   cudaFree(ctx->wl.counts);
   cudaFree(ctx->d_mask);
+  cudaFree(ctx->d_maskbits);
   cudaFree(ctx->rb.partials);
   cudaFree(ctx->rb.moments);
   cudaFree(ctx->rb.suff);
@@ -1254,6 +1309,23 @@ int rpe_sync(rpe_ctx* ctx) {
   CK(sync_stream(ctx));
   finish_pending(ctx);
   return check_comm(ctx);
+}
+
+int rpe_poll(rpe_ctx* ctx) {
+  if (!ctx) return RPE_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  while (!ctx->pending.empty()) {
+    const rpe_ctx::Pending p = ctx->pending.front();
+    const cudaError_t e = cudaEventQuery(ctx->ev_slot[p.slot]);
+    if (e == cudaErrorNotReady) {
+      (void)cudaGetLastError();
+      break;
+    }
+    CK(e);
+    deliver(ctx, p);
+    ctx->pending.pop_front();
+  }
+  return RPE_OK;
 }
 
 int rpe_host_alloc(size_t bytes, void** ptr) {
@@ -2079,6 +2151,11 @@ int rpe_measure_ffma_tflops(rpe_ctx* ctx, int ms_target, double* tflops_scalar, 
   return RPE_OK;
 }
 
+int rpe_set_mask_transfer(rpe_ctx* ctx, int mode) {
+  if (!ctx || mode < 0 || mode > 1) return RPE_ERR_ARG;
+  ctx->mask_transfer = mode;
+  return RPE_OK;
+}
 int rpe_enable_stage_timing(rpe_ctx* ctx, int enable) {
   if (!ctx) return RPE_ERR_ARG;
   ctx->timing = enable == 1;

@@ -101,7 +101,7 @@ constexpr int kMomentCount = 48;  // 16 Kabsch moments / 29 LM entries / 40 nl_s
 // pose_rw: the ReplayOut written by the replay kernel (read for the pose, per-column inlier counts are
 // added to it); kabsch_out receives pose_rw with (q,t) replaced by the Kabsch refit over the 3-D inliers.
 void launch_mask(int method, const FrameView& f, ReplayOut* pose_rw, Thresh th, int16_t* mask, ReplayOut* kabsch_out,
-                 RefitBuffers rb, FrameStats* st, cudaStream_t s);
+                 RefitBuffers rb, FrameStats* st, cudaStream_t s, uint32_t* bits = nullptr);
 void launch_reset_corr_bound(FrameStats* st, cudaStream_t s);
 // Kabsch from the moments left by launch_mask (or by launch_kabsch_moments); writes pose_out.
 // returns the number of CTAs launched (= rows of rb.partials to reduce)

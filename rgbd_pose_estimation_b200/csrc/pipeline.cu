@@ -497,7 +497,9 @@ __device__ __forceinline__ void suff_add_nl(double* m, const F3& nw, const F3& n
 template <bool UN>
 __global__ void __launch_bounds__(256, 2)
 mask_kernel(int method, FrameView f, ReplayOut* pose_rw, Thresh th, int16_t* __restrict__ mask, RefitBuffers rb,
-            ReplayOut* kabsch_out, FrameStats* st) {
+            ReplayOut* kabsch_out, FrameStats* st, uint32_t* __restrict__ bits) {
+  // bits (optional): the same flags as one bit per correspondence, cols x ceil(n / 32) words, column after column —
+  // what rpe_set_mask_transfer(1) sends to the host instead of the 16-bit matrix
   const ReplayOut* pose = pose_rw;
   constexpr int NV = UN ? kSuffAll : kSuff3;
   __shared__ double red[8 * NV];
@@ -518,9 +520,14 @@ mask_kernel(int method, FrameView f, ReplayOut* pose_rw, Thresh th, int16_t* __r
 #pragma unroll
   for (int k = 0; k < NV; ++k) mom[k] = 0.0;
   int c2 = 0, c3 = 0, cn = 0;
-  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < n; c += gridDim.x * blockDim.x) {
+  const int wpc = (n + 31) >> 5;  // words per column of the bit form
+  // (the loop condition is uniform over a warp: its 32 lanes hold 32 consecutive correspondences starting at a multiple of 32)
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c - (int)(threadIdx.x & 31) < n; c += gridDim.x * blockDim.x) {
+    const bool inb = c < n;
     bool f2 = false, f3d = false, fn = false;
-    if (have) {
+    if (!inb) {
+      // beyond the frame: contributes nothing
+    } else if (have) {
       const F3 xw = load_col(f.xw, c);
       bool valid = false;
       F3 xc = f3(0.f, 0.f, 0.f);
@@ -547,9 +554,25 @@ mask_kernel(int method, FrameView f, ReplayOut* pose_rw, Thresh th, int16_t* __r
     }
     // column 0 of a family without the 2-D test is never set by the reference's loop: 0 once a hypothesis has been
     // accepted (the per-iteration matrix starts from zero), still the initial 1 when nothing was accepted
-    mask[c] = (int16_t)(!have ? 1 : ((cols == 1 || u2) ? (f2 ? 1 : 0) : 0));
-    if (cols >= 2) mask[n + c] = (int16_t)(u3 ? (f3d ? 1 : 0) : (have ? 0 : 1));
-    if (cols >= 3) mask[2 * n + c] = (int16_t)(fn ? 1 : 0);
+    const bool v0 = !have ? true : ((cols == 1 || u2) ? f2 : false);
+    const bool v1 = u3 ? f3d : !have;
+    const bool v2 = fn;
+    if (inb) {
+      mask[c] = (int16_t)(v0 ? 1 : 0);
+      if (cols >= 2) mask[n + c] = (int16_t)(v1 ? 1 : 0);
+      if (cols >= 3) mask[2 * n + c] = (int16_t)(v2 ? 1 : 0);
+    }
+    if (bits) {
+      const unsigned int b0 = __ballot_sync(0xffffffffu, inb && v0);
+      const unsigned int b1 = __ballot_sync(0xffffffffu, inb && v1);
+      const unsigned int b2 = __ballot_sync(0xffffffffu, inb && v2);
+      if ((threadIdx.x & 31) == 0) {
+        const int w = c >> 5;
+        bits[w] = b0;
+        if (cols >= 2) bits[wpc + w] = b1;
+        if (cols >= 3) bits[2 * wpc + w] = b2;
+      }
+    }
   }
   // per-column counts
 #pragma unroll
@@ -604,11 +627,11 @@ static int refit_grid(int n, int num_sms_hint) {
   return full < cap ? full : cap;
 }
 void launch_mask(int method, const FrameView& f, ReplayOut* pose_rw, Thresh th, int16_t* mask, ReplayOut* kabsch_out,
-                 RefitBuffers rb, FrameStats* st, cudaStream_t s) {
+                 RefitBuffers rb, FrameStats* st, cudaStream_t s, uint32_t* bits) {
   if (method_uses_nl(method))
-    mask_kernel<true><<<refit_grid(f.n, rb.num_sms), 256, 0, s>>>(method, f, pose_rw, th, mask, rb, kabsch_out, st);
+    mask_kernel<true><<<refit_grid(f.n, rb.num_sms), 256, 0, s>>>(method, f, pose_rw, th, mask, rb, kabsch_out, st, bits);
   else
-    mask_kernel<false><<<refit_grid(f.n, rb.num_sms), 256, 0, s>>>(method, f, pose_rw, th, mask, rb, kabsch_out, st);
+    mask_kernel<false><<<refit_grid(f.n, rb.num_sms), 256, 0, s>>>(method, f, pose_rw, th, mask, rb, kabsch_out, st, bits);
 }
 
 // Stand-alone statistics over explicit flag columns (after rpe_set_mask) or over all points (shinji_ls2).
