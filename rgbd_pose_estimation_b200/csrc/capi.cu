@@ -149,6 +149,7 @@ struct rpe_ctx {
   std::deque<Pending> pending;
   int next_slot = 0;                      // staging slots are handed out round-robin
   cudaEvent_t ev_lane[2] = {};            // fences between this context's stream and the device's scorer lane
+  cudaEvent_t ev_lane_done[4] = {};       // chunked frames: one fence per lane used (kMaxLanes)
   cudaEvent_t ev_slot[kNumStaging] = {};  // recorded behind each result's device-to-host copies
   Thresh last_th = {0.f, 0.f, 0.f};
 
@@ -985,13 +986,21 @@ int do_ransac(rpe_ctx* ctx, int method, const int32_t* samples, rpe_sample_fn fn
         mark(ctx->copy_stream);  // 2..: chunk c landed
       }
       CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_chunk[C - 1], 0));  // the context's own stream sees the whole frame
-      {
-        std::lock_guard<std::mutex> g(lane->mu);
-        CK(cudaStreamWaitEvent(lane->stream, ctx->ev_early, 0));
-        for (int c = 0; c < C; ++c) {
+      // the chunk scorers alternate between the device's lanes like the scorers of consecutive frames do: the head of
+      // one chunk's launch overlaps the tail of the previous one (they add into the same vote table with atomics)
+      bool lane_used[kMaxLanes] = {};
+      for (int c = 0; c < C; ++c) {
+        ScorerLane* L = c == 0 ? lane : lane_for(ctx);
+        if (!L) L = lane;
+        const int li = (int)(L - &g_lane[ctx->device][0]);
+        std::lock_guard<std::mutex> g(L->mu);
+        if (!lane_used[li]) CK(cudaStreamWaitEvent(L->stream, ctx->ev_early, 0));
+        lane_used[li] = true;
+        {
+          cudaStream_t lane_stream = L->stream;
           const int c0 = c * ctx->chunk_corr;
           const int cnt = (ctx->n - c0) < ctx->chunk_corr ? (ctx->n - c0) : ctx->chunk_corr;
-          CK(cudaStreamWaitEvent(lane->stream, ctx->ev_chunk[c], 0));
+          CK(cudaStreamWaitEvent(lane_stream, ctx->ev_chunk[c], 0));
           FrameView fc = fv;
           fc.xw = fv.xw + 3 * (size_t)c0;
           fc.xc = fv.xc + 3 * (size_t)c0;
@@ -1002,13 +1011,14 @@ int do_ransac(rpe_ctx* ctx, int method, const int32_t* samples, rpe_sample_fn fn
           wc.entries = ctx->wl.entries + (size_t)c * ctx->num_sms * seg_cap;
           wc.counts = ctx->wl.counts + (size_t)c * ctx->num_sms;
           launch_score_fast(method, fc, ctx->d_gen, ctx->d_fast, 0, H * S, th, ctx->d_votes, ctx->d_stats, wc, ctx->num_sms,
-                            lane->stream, c0, seg_cap);
+                            lane_stream, c0, seg_cap);
           ctx->launches++;
-          mark(lane->stream);  // chunk c scored
+          mark(lane_stream);  // chunk c scored
+          CK(cudaEventRecord(ctx->ev_lane_done[li], lane_stream));  // (the last record of a lane is the one that counts)
         }
-        CK(cudaEventRecord(ctx->ev_lane[1], lane->stream));
       }
-      CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_lane[1], 0));
+      for (int li = 0; li < kMaxLanes; ++li)
+        if (lane_used[li]) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_lane_done[li], 0));
       Worklist wall = ctx->wl;
       wall.capacity = seg_cap * (unsigned int)(C * ctx->num_sms);
       launch_fixup(method, fv, ctx->d_gen, th, ctx->d_votes, ctx->d_stats, wall, C * ctx->num_sms, 0, H * S, ctx->stream);
@@ -1197,6 +1207,8 @@ static int create_common(int device, void* stream, bool own, rpe_ctx** out) {
     ok = ok && cudaEventCreateWithFlags(&ctx->ev_slot[k], cudaEventDisableTiming) == cudaSuccess;
   for (int k = 0; k < 2 && ok; ++k)
     ok = ok && cudaEventCreateWithFlags(&ctx->ev_lane[k], cudaEventDisableTiming) == cudaSuccess;
+  for (int k = 0; k < 4 && ok; ++k)
+    ok = ok && cudaEventCreateWithFlags(&ctx->ev_lane_done[k], cudaEventDisableTiming) == cudaSuccess;
   for (int k = 0; k < rpe_ctx::kMaxChunks && ok; ++k)
     ok = ok && cudaEventCreateWithFlags(&ctx->ev_chunk[k], cudaEventDisableTiming) == cudaSuccess;
   ok = ok && cudaEventCreateWithFlags(&ctx->ev_prev, cudaEventDisableTiming) == cudaSuccess;
@@ -1279,6 +1291,8 @@ int rpe_destroy(rpe_ctx* ctx) {
     if (ctx->ev_slot[k]) cudaEventDestroy(ctx->ev_slot[k]);
   for (int k = 0; k < 2; ++k)
     if (ctx->ev_lane[k]) cudaEventDestroy(ctx->ev_lane[k]);
+  for (int k = 0; k < 4; ++k)
+    if (ctx->ev_lane_done[k]) cudaEventDestroy(ctx->ev_lane_done[k]);
   if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
   if (ctx->early_stream) cudaStreamSynchronize(ctx->early_stream);
   for (int k = 0; k < rpe_ctx::kMaxChunks; ++k)
