@@ -936,11 +936,54 @@ int do_ransac(rpe_ctx* ctx, int method, const int32_t* samples, rpe_sample_fn fn
     ScorerLane* lane = lane_for(ctx);
     FrameView fv = make_view(ctx);
     if (!(method == RPE_SHINJI && single && !fn && H * S > 512 && lane && frame_raw_ok(fv, 2) && !ctx->timing && !ctx->timing_fast &&
-          !ctx->stale_cols && ctx->wl_want <= ctx->wl_allocated && rpe::score_variant() == rpe::kDefaultScoreVariant)) {
+          !ctx->stale_cols && ctx->wl_want <= ctx->wl_allocated && rpe::score_variant() == rpe::kDefaultScoreVariant &&
+          (ctx->overlap_chunks != 1 || H * S <= 1024))) {  // (stream mode: one hypothesis column, the frame crosses the bus once)
       if (int rcf = flush_deferred(ctx)) return rcf;
     } else {
       ctx->deferred = false;
       cudaStream_t es = ctx->early_stream;
+      if (ctx->n_chunks == 1 && ctx->overlap_chunks == 1) {
+        // ---- stream mode: nothing is copied by the copy engine. The generator reads its sample points from the host
+        // arrays, the scorer's bulk-TMA loads read the frame itself from the page-locked host arrays while it scores,
+        // and it leaves the device copy behind that the fix-up, mask and refit kernels use.
+        CK(cudaEventRecord(ctx->ev_prev, ctx->stream));
+        CK(cudaStreamWaitEvent(es, ctx->ev_prev, 0));
+        if (!ctx->stats_clean) {
+          launch_reset_stats(ctx->d_stats, es);
+          ctx->launches++;
+        }
+        const int32_t* sdev = samples;
+        if (!samples_on_device) {
+          CK(cudaMemcpyAsync(ctx->d_samples, samples, (size_t)H * 4 * sizeof(int32_t), cudaMemcpyHostToDevice, es));
+          sdev = ctx->d_samples;
+        }
+        FrameView fh = fv;
+        fh.xw = ctx->host_view[A_XW];
+        fh.xc = ctx->host_view[A_XC];
+        launch_hypgen(method, fh, sdev, H, ctx->d_gen, ctx->d_fast, ctx->d_votes, ctx->d_stats, es);
+        ctx->launches++;
+        ctx->n_slots = H * S;
+        ctx->cur_method = method;
+        CK(cudaEventRecord(ctx->ev_early, es));
+        int nseg = 0;
+        {
+          const int li = (int)(lane - &g_lane[ctx->device][0]);
+          std::lock_guard<std::mutex> g(lane->mu);
+          CK(cudaStreamWaitEvent(lane->stream, ctx->ev_early, 0));
+          nseg = launch_score3d_stream(fh, ctx->d_raw[A_XW], ctx->d_raw[A_XC], ctx->d_gen, ctx->d_fast, 0, H * S, th.thr3d,
+                                       ctx->d_votes, ctx->d_stats, ctx->wl, ctx->num_sms, lane->stream);
+          ctx->launches++;
+          CK(cudaEventRecord(ctx->ev_lane_done[li], lane->stream));
+          CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_lane_done[li], 0));
+        }
+        launch_fixup(method, fv, ctx->d_gen, th, ctx->d_votes, ctx->d_stats, ctx->wl, nseg, 0, H * S, ctx->stream);
+        launch_score_exact(method, fv, ctx->d_gen, 0, H * S, th, ctx->d_votes, ctx->d_stats, true, ctx->num_sms, ctx->stream);
+        launch_replay(method, ctx->d_gen, ctx->d_votes, H, 0, ctx->n, confidence, ctx->d_stats, ctx->d_rs, ctx->d_pose, true, H,
+                      ctx->stream);
+        ctx->launches += 3;
+        ctx->stats_clean = true;
+        return do_finish(ctx, method, th, out, mask, blocking);
+      }
       static const bool trace = getenv("RPE_OVERLAP_TRACE") != nullptr;  // debugging aid: device timeline of this path on stderr
       static thread_local cudaEvent_t tev[24] = {};
       int ntev = 0;
@@ -1364,7 +1407,7 @@ static int upload_common(rpe_ctx* ctx, const float* const src[5], int n, bool fr
   if (rc) return rc;
   ctx->n = n;
   bool defer = false;
-  if (!from_device && ctx->overlap_chunks >= 2 && n >= 65536 && src[A_XC] && !src[A_BV] && !src[A_NC] && !src[A_NW]) {
+  if (!from_device && ctx->overlap_chunks >= 1 && n >= 65536 && src[A_XC] && !src[A_BV] && !src[A_NC] && !src[A_NW]) {
     // page-locked (and device-visible) host arrays?
     defer = true;
     for (int k = 0; k < 5 && defer; ++k) {
@@ -1441,7 +1484,7 @@ int rpe_ransac_async(rpe_ctx* ctx, int method, const int32_t* samples, int H, fl
 }
 int rpe_set_upload_overlap(rpe_ctx* ctx, int chunks) {
   if (!ctx || chunks < 0) return RPE_ERR_ARG;
-  ctx->overlap_chunks = chunks < 2 ? 0 : (chunks > rpe_ctx::kMaxChunks ? rpe_ctx::kMaxChunks : chunks);
+  ctx->overlap_chunks = chunks > rpe_ctx::kMaxChunks ? rpe_ctx::kMaxChunks : chunks;  // 0 off, 1 stream from the host arrays, >= 2 chunked copy
   return RPE_OK;
 }
 int rpe_set_stale_sample_columns(rpe_ctx* ctx, int on) {

@@ -74,6 +74,11 @@ void launch_minsolv_ms(const float* in24, int count, float* q4, float* t3, cudaS
 int launch_score_fast(int method, const FrameView& f, const HypGen* gen, const HypFast* fast, int slot_begin,
                        int slot_end, Thresh th, int32_t* votes, FrameStats* st, Worklist wl, int num_sms, cudaStream_t s,
                        int corr_base = 0, unsigned int seg_cap = 0);
+// The 3-D / 3-D scorer fed straight from page-locked host arrays (fsrc.xw / fsrc.xc as the device sees them); the frame is
+// written to dxw / dxc on the way (may be null). Returns the number of worklist segments (= CTAs).
+int launch_score3d_stream(const FrameView& fsrc, float* dxw, float* dxc, const HypGen* gen, const HypFast* fast, int slot_begin,
+                          int slot_end, float thr3d, int32_t* votes, FrameStats* st, Worklist wl, int num_sms, cudaStream_t s);
+
 void launch_fixup(int method, const FrameView& f, const HypGen* gen, Thresh th, int32_t* votes, FrameStats* st,
                   Worklist wl, int nseg, int slot_begin, int slot_end, cudaStream_t s);
 void launch_consume_worklist(FrameStats* st, cudaStream_t s);

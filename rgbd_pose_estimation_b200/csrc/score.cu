@@ -672,6 +672,278 @@ score3d_raw_kernel(const float* __restrict__ xw, const float* __restrict__ xc, i
 }
 
 // ================================================================================================
+// 3-D / 3-D scorer that STREAMS the frame from page-locked host memory and leaves a device copy behind
+// ================================================================================================
+// Bulk TMA reads mapped host memory like any other global memory (measured: 53 GB/s, more than the copy engine gets
+// for the same arrays), so a frame that lives in page-locked host memory needs no upload before it is scored: the CTA
+// asks for its whole slice at once, in sub-stages of SUBT pairs with one mbarrier each, and transposes + scores a
+// sub-stage as soon as it has landed while the rest is still on the bus. Each landed sub-stage is also written to the
+// context's device arrays with a bulk store (shared -> global), so that the fix-up, mask and refit kernels find the
+// frame in HBM afterwards. Arithmetic, guard bands (per sub-stage bound) and vote counts are those of score3d_raw_kernel.
+__device__ __forceinline__ void tma_store_1d(void* dst_gmem, const void* src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+template <int TILE, int THREADS, int SUB, int SUBT>
+__global__ void __launch_bounds__(THREADS, 1)
+score3d_stream_kernel(const float* __restrict__ xw, const float* __restrict__ xc, float* __restrict__ dxw, float* __restrict__ dxc,
+                      int n, int npairs_pad, int pairs_per_cta, const HypFast* __restrict__ fast,
+                      const HypGen* __restrict__ gen, int slot_begin, int slot_end, float thr, int32_t* __restrict__ votes,
+                      FrameStats* __restrict__ st, Worklist wl) {
+  constexpr int HPT = 2;
+  constexpr int NSUB = TILE / SUBT;
+  static_assert(TILE % SUBT == 0 && SUBT % SUB == 0 && SUBT % 2 == 0, "sub-stages are whole groups");
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  constexpr int kStageFloats = TILE * 2 * 3;
+  float4* packed = reinterpret_cast<float4*>(smem_raw);                                  // [TILE * 3]
+  float* raw = reinterpret_cast<float*>(smem_raw + (size_t)TILE * 3 * sizeof(float4));    // [2 stages][xw | xc][kStageFloats]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(raw + 4 * kStageFloats);                  // [2 stages][NSUB]
+  unsigned int* mtile = reinterpret_cast<unsigned int*>(bars + 2 * NSUB);                // [2 stages][NSUB]
+
+  const int tid = threadIdx.x;
+  const int p_begin = blockIdx.x * pairs_per_cta;
+  const int p_end = min(p_begin + pairs_per_cta, npairs_pad);
+  const int npairs = p_end - p_begin;
+  const int ntiles = (npairs + TILE - 1) / TILE;
+  WlSegment seg(wl);
+
+  HypRegs<true> hyp[HPT];
+  int slot[HPT];
+  int cnt[HPT];
+  unsigned int pacc[HPT];
+  float tnorm[HPT];
+#pragma unroll
+  for (int k = 0; k < HPT; ++k) {
+    slot[k] = slot_begin + (blockIdx.y * HPT + k) * THREADS + tid;
+    const bool live = slot[k] < slot_end && gen[slot[k]].valid != 0;
+    hyp[k].load(&fast[live ? slot[k] : slot_begin], live);
+    if (!live) slot[k] = -1;
+    cnt[k] = 0;
+    pacc[k] = 0u;
+    tnorm[k] = sqrtf(hyp[k].nt[0].x * hyp[k].nt[0].x + hyp[k].nt[1].x * hyp[k].nt[1].x + hyp[k].nt[2].x * hyp[k].nt[2].x);
+  }
+  const float thr2 = __fmul_rn(thr, thr);
+  const float2 nlo = make_float2(-thr2, -thr2);
+
+  auto stage_range = [&](int t, int& c0, int& cnt4) {
+    c0 = 2 * (p_begin + t * TILE);
+    const int tp = min(TILE, npairs - t * TILE);
+    int c = min(2 * tp, n - c0);
+    if (c < 0) c = 0;
+    cnt4 = c & ~3;
+  };
+  // correspondences [c0 + 2 SUBT sub, ...) of sub-stage `sub`: how many go through TMA
+  auto sub_count = [&](int cnt4, int sub) {
+    int c = cnt4 - 2 * SUBT * sub;
+    return c < 0 ? 0 : (c > 2 * SUBT ? 2 * SUBT : c);
+  };
+  auto issue = [&](int t, int buf) {
+    int c0, cnt4;
+    stage_range(t, c0, cnt4);
+#pragma unroll 1
+    for (int sub = 0; sub < NSUB; ++sub) {
+      const uint32_t bytes = (uint32_t)sub_count(cnt4, sub) * 12u;
+      uint64_t* bar = &bars[buf * NSUB + sub];
+      mbar_expect_tx(bar, 2u * bytes);  // 0 bytes: the phase completes on this arrival alone
+      if (bytes) {
+        const size_t off = (size_t)sub * 2 * SUBT * 3;
+        tma_load_1d(raw + (size_t)(2 * buf) * kStageFloats + off, xw + (size_t)c0 * 3 + off, bytes, bar);
+        tma_load_1d(raw + (size_t)(2 * buf + 1) * kStageFloats + off, xc + (size_t)c0 * 3 + off, bytes, bar);
+      }
+    }
+  };
+  if (tid == 0) {
+    for (int i = 0; i < 2 * NSUB; ++i) {
+      mbar_init(&bars[i], 1);
+      mtile[i] = 0u;
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+  if (tid == 0)
+    for (int t = 0; t < 2 && t < ntiles; ++t) issue(t, t);
+
+  for (int t = 0; t < ntiles; ++t) {
+    const int buf = t & 1;
+    const uint32_t parity = (uint32_t)((t >> 1) & 1);
+    const int tp = min(TILE, npairs - t * TILE);
+    int c0, cnt4;
+    stage_range(t, c0, cnt4);
+    const float* rw = raw + (size_t)(2 * buf) * kStageFloats;
+    const float* rc = raw + (size_t)(2 * buf + 1) * kStageFloats;
+    const int nsub = (tp + SUBT - 1) / SUBT;
+    for (int sub = 0; sub < nsub; ++sub) {
+      mbar_wait(&bars[buf * NSUB + sub], parity);
+      if (tid == 0 && dxw) {  // the device copy of what has just landed
+        const uint32_t bytes = (uint32_t)sub_count(cnt4, sub) * 12u;
+        if (bytes) {
+          const size_t off = (size_t)sub * 2 * SUBT * 3;
+          tma_store_1d(dxw + (size_t)c0 * 3 + off, rw + off, bytes);
+          tma_store_1d(dxc + (size_t)c0 * 3 + off, rc + off, bytes);
+          tma_store_commit();
+        }
+      }
+      const int pr_lo = sub * SUBT, pr_hi = min(tp, pr_lo + SUBT);
+      // ---- transpose the sub-stage: thread <-> 4 correspondences = 2 pair records; its magnitude bound
+      float mloc = 0.f;
+      for (int qd = pr_lo / 2 + tid; qd < (pr_hi + 1) / 2; qd += THREADS) {
+        float w[12], c[12];
+        if (4 * qd + 4 <= cnt4) {
+          const float4* w4 = reinterpret_cast<const float4*>(rw + 12 * qd);
+          const float4* c4 = reinterpret_cast<const float4*>(rc + 12 * qd);
+#pragma unroll
+          for (int i = 0; i < 3; ++i) {
+            const float4 a = w4[i], b = c4[i];
+            w[4 * i] = a.x; w[4 * i + 1] = a.y; w[4 * i + 2] = a.z; w[4 * i + 3] = a.w;
+            c[4 * i] = b.x; c[4 * i + 1] = b.y; c[4 * i + 2] = b.z; c[4 * i + 3] = b.w;
+          }
+        } else {  // frame tail (or padding): element-wise from the source arrays, NaN beyond the last correspondence
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int ci = c0 + 4 * qd + j;
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+              w[3 * j + r] = ci < n ? xw[(size_t)ci * 3 + r] : CUDART_NAN_F;
+              c[3 * j + r] = ci < n ? xc[(size_t)ci * 3 + r] : CUDART_NAN_F;
+              if (dxw && ci < n) {
+                dxw[(size_t)ci * 3 + r] = w[3 * j + r];
+                dxc[(size_t)ci * 3 + r] = c[3 * j + r];
+              }
+            }
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float m = sqrtf(w[3 * j] * w[3 * j] + w[3 * j + 1] * w[3 * j + 1] + w[3 * j + 2] * w[3 * j + 2]);
+          const float mc = sqrtf(c[3 * j] * c[3 * j] + c[3 * j + 1] * c[3 * j + 1] + c[3 * j + 2] * c[3 * j + 2]);
+          if (mc == mc && mc < CUDART_INF_F) m += mc;
+          if (m == m && m < CUDART_INF_F) mloc = fmaxf(mloc, m);
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int pr = 2 * qd + h;
+          if (pr < tp) {
+            const float* a = w + 6 * h;
+            const float* b = c + 6 * h;
+            packed[pr * 3 + 0] = make_float4(a[0], a[3], a[1], a[4]);
+            packed[pr * 3 + 1] = make_float4(a[2], a[5], b[0], b[3]);
+            packed[pr * 3 + 2] = make_float4(b[1], b[4], b[2], b[5]);
+          }
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) mloc = fmaxf(mloc, __shfl_xor_sync(0xffffffffu, mloc, o));
+      if ((tid & 31) == 0 && mloc > 0.f) atomicMax(&mtile[buf * NSUB + sub], __float_as_uint(mloc));
+      __syncthreads();  // records + bound of this sub-stage complete
+      const float mcorr = __uint_as_float(mtile[buf * NSUB + sub]);
+      float band[HPT];
+#pragma unroll
+      for (int k = 0; k < HPT; ++k) band[k] = guard_band_3d((mcorr + tnorm[k]) * 1.0001f, thr);  // NaN for a dead slot
+
+      const float4* sp = packed;
+      for (int g0 = pr_lo; g0 < pr_hi; g0 += SUB) {
+        float smin[HPT];
+#pragma unroll
+        for (int k = 0; k < HPT; ++k) smin[k] = CUDART_INF_F;
+#pragma unroll
+        for (int pp = 0; pp < SUB; pp += 2) {
+          unsigned int tw[2][HPT];
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const float4 a = sp[(g0 + pp + h) * 3 + 0];
+            const float4 b = sp[(g0 + pp + h) * 3 + 1];
+            const float4 c = sp[(g0 + pp + h) * 3 + 2];
+#pragma unroll
+            for (int k = 0; k < HPT; ++k) {
+              const float2 s = hyp[k].eval(a, b, c, nlo);
+              tw[h][k] = sign_words(s);
+              smin[k] = fminf(fminf(smin[k], fabsf(s.x)), fabsf(s.y));
+            }
+          }
+#pragma unroll
+          for (int k = 0; k < HPT; ++k) pacc[k] = pacc[k] - tw[0][k] - tw[1][k];
+        }
+        bool any = false;
+#pragma unroll
+        for (int k = 0; k < HPT; ++k) any = any || (smin[k] <= band[k]);
+        if (any) {
+          for (int pp = 0; pp < SUB; ++pp) {
+            const float4 a = sp[(g0 + pp) * 3 + 0];
+            const float4 b = sp[(g0 + pp) * 3 + 1];
+            const float4 c = sp[(g0 + pp) * 3 + 2];
+#pragma unroll
+            for (int k = 0; k < HPT; ++k) {
+              const float2 s = hyp[k].eval(a, b, c, nlo);
+              const float sv[2] = {s.x, s.y};
+#pragma unroll
+              for (int u = 0; u < 2; ++u) {
+                if (fabsf(sv[u]) <= band[k]) {
+                  cnt[k] -= (int)(__float_as_uint(sv[u]) >> 31);
+                  const unsigned int corr = (unsigned int)(2 * (p_begin + t * TILE + g0 + pp) + u);
+                  seg.push(make_uint2((unsigned int)slot[k], corr | (1u << 30)), st);
+                }
+              }
+            }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < HPT; ++k) {  // fold the packed fields (at most TILE <= 1024 pairs since the last fold)
+      const unsigned int lo = pacc[k] & 0xffffu, hi = pacc[k] >> 16;
+      cnt[k] += (int)(lo + ((hi + lo) & 0xffffu));
+      pacc[k] = 0u;
+    }
+    __syncthreads();  // everybody is done with the records and the bounds of this stage
+    if (tid == 0) {
+      for (int i = 0; i < NSUB; ++i) mtile[buf * NSUB + i] = 0u;
+      if (t + 2 < ntiles) {
+        tma_store_wait_read();  // the bulk stores have read raw[buf]
+        issue(t + 2, buf);
+      }
+    }
+  }
+  if (tid == 0) tma_store_wait_all();
+#pragma unroll
+  for (int k = 0; k < HPT; ++k)
+    if (slot[k] >= 0 && cnt[k] != 0) atomicAdd(&votes[slot[k]], cnt[k]);
+  seg.publish(wl, st);
+}
+
+// host side of the streaming scorer: the full 1024-hypothesis column shape of the default variant
+int launch_score3d_stream(const FrameView& fsrc, float* dxw, float* dxc, const HypGen* gen, const HypFast* fast, int slot_begin,
+                          int slot_end, float thr3d, int32_t* votes, FrameStats* st, Worklist wl, int num_sms, cudaStream_t s) {
+  constexpr int TILE = 1024, THREADS = 512, SUB = 4, SUBT = 128, HPT = 2;
+  const int nslots = slot_end - slot_begin;
+  if (nslots <= 0 || fsrc.n <= 0) return 0;
+  const int gy = (nslots + THREADS * HPT - 1) / (THREADS * HPT);
+  const int groups = fsrc.npairs_pad / SUB;
+  int gx = num_sms / gy;
+  if (gx < 1) gx = 1;
+  if (gx > groups) gx = groups;
+  const int groups_per_cta = (groups + gx - 1) / gx;
+  const int pairs_per_cta = groups_per_cta * SUB;
+  gx = (fsrc.npairs_pad + pairs_per_cta - 1) / pairs_per_cta;
+  const size_t smem = (size_t)TILE * 3 * sizeof(float4) + 4 * (size_t)TILE * 6 * sizeof(float) + 2 * (TILE / SUBT) * (sizeof(uint64_t) + sizeof(unsigned int)) + 16;
+  auto k = score3d_stream_kernel<TILE, THREADS, SUB, SUBT>;
+  static std::atomic<bool> attr[64];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64 && !attr[dev].load(std::memory_order_acquire)) {
+    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr[dev].store(true, std::memory_order_release);
+  }
+  // (gy > 1 would stream the frame once per hypothesis column: the caller only uses this for H * S <= 1024)
+  k<<<dim3(gx, gy), THREADS, smem, s>>>(fsrc.xw, fsrc.xc, gy == 1 ? dxw : nullptr, gy == 1 ? dxc : nullptr, fsrc.n, fsrc.npairs_pad,
+                                       pairs_per_cta, fast, gen, slot_begin, slot_end, thr3d, votes, st, wl);
+  return gx * gy;
+}
+
+// ================================================================================================
 // fast tiled scorer — 2-D, 3-D and normal modalities in any combination (all other estimator families)
 // ================================================================================================
 // Shared per (pair, hypothesis): ny = -(R x_w + t) = nR x_w + nt (9 FFMA2). Then
@@ -1280,6 +1552,10 @@ static int launch_variant(const FrameView& f, const HypGen* gen, const HypFast* 
   if (MINB == 1 && g_exclusive_sm && smem < (size_t)116 * 1024) smem = (size_t)116 * 1024;
   int dev = 0;
   cudaGetDevice(&dev);
+  // measurement aid: RPE_FORCE_STREAM_SCORER=1 runs the sub-staged streaming scorer (no device copy) in place of the default one
+  static const bool force_stream = getenv("RPE_FORCE_STREAM_SCORER") != nullptr;
+  if (force_stream && PACKED && frame_raw_ok(f, 2) && MINB == 1 && THREADS == 512 && corr_base == 0 && seg_cap == 0 && gy == 1)
+    return launch_score3d_stream(f, nullptr, nullptr, gen, fast, slot_begin, slot_end, th.thr3d, votes, st, wl, num_sms, s);
   if (PACKED && frame_raw_ok(f, 2)) {  // stream the caller's arrays: no packed copy
     constexpr int RT = (TILE > 1024 / MINB ? 1024 / MINB : TILE);  // 144 bytes of shared memory per pair and CTA
     static const int pcount = getenv("RPE_PCOUNT") ? getenv("RPE_PCOUNT")[0] - '0' : 1;  // 1: packed sign count (1 % faster, r02d)

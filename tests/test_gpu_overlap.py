@@ -1,5 +1,7 @@
 """GPU: rpe_set_upload_overlap — the frame is uploaded in chunks from page-locked host memory while the generator reads
-its sample points from the host arrays and the scorer runs chunk by chunk. Results must be what the plain path and the
+its sample points from the host arrays and the scorer runs chunk by chunk; with chunks = 1 nothing is uploaded at all: the
+scorer streams the frame from the host arrays with bulk TMA and leaves the device copy behind (H = 2048 falls back to the
+plain upload: the frame would cross the bus once per hypothesis column). Results must be what the plain path and the
 CPU oracle give (reference loop: /root/reference/pose/AbsoluteOrientation.hpp:101-213)."""
 import numpy as np
 import pytest
@@ -13,7 +15,8 @@ def _pinned(rpe, a):
     return b
 
 
-@pytest.mark.parametrize("n,H,chunks", [(307200, 1024, 4), (100003, 600, 3), (70000, 1024, 8), (200000, 2048, 2)])
+@pytest.mark.parametrize("n,H,chunks", [(307200, 1024, 4), (100003, 600, 3), (70000, 1024, 8), (200000, 2048, 2),
+                                        (307200, 1024, 1), (100003, 600, 1), (70001, 1024, 1), (200000, 2048, 1)])
 def test_overlapped_upload_gives_identical_results(rpe, orc, n, H, chunks):
     import os
     orc.set_math_mode(orc.DET)

@@ -5,15 +5,19 @@
 // MODE 1: every FFMA2 of a run has its own pair operand (nothing to reuse)
 // MODE 2: like 1 with scalar FFMA (3 distinct registers)
 // MODE 3: like 0 with scalar FFMA (multiplicand shared by the run)
+// MODE 4: like 0, the scalar multiplicand in a UNIFORM register (FFMA2 R, R.F32x2, UR.F32, R.F32x2): pair shared by runs
+// MODE 5: like 1, the scalar multiplicand in a uniform register: four distinct registers per FFMA2, nothing to reuse
 #include <cstdio>
 #include <cuda_runtime.h>
 
 #define ITERS 2048
 
+__constant__ float cscal[32];
+
 template <int MODE>
 __global__ void __launch_bounds__(256) k(float* sink, const float* src, int iters) {
   float r[18];
-  for (int i = 0; i < 18; ++i) r[i] = src[i] + 1e-6f * threadIdx.x;
+  for (int i = 0; i < 18; ++i) r[i] = MODE >= 4 ? cscal[i] : src[i] + 1e-6f * threadIdx.x;
   float2 X[6];
   for (int i = 0; i < 6; ++i) X[i] = make_float2(src[20 + 2 * i] + 1e-7f * threadIdx.x, src[21 + 2 * i]);
   float2 acc[6];
@@ -23,6 +27,8 @@ __global__ void __launch_bounds__(256) k(float* sink, const float* src, int iter
     for (int j = 0; j < 3; ++j) {
 #pragma unroll
       for (int i = 0; i < 6; ++i) {
+        if (MODE == 4) acc[i] = __ffma2_rn(make_float2(r[6 * j + i], r[6 * j + i]), X[j], acc[i]);
+        if (MODE == 5) acc[i] = __ffma2_rn(make_float2(r[6 * j + i], r[6 * j + i]), X[i], acc[i]);
         if (MODE == 0) acc[i] = __ffma2_rn(make_float2(r[6 * j + i], r[6 * j + i]), X[j], acc[i]);
         if (MODE == 1) acc[i] = __ffma2_rn(make_float2(r[6 * j + i], r[6 * j + i]), X[i], acc[i]);
         if (MODE == 2) {
@@ -68,7 +74,10 @@ int main() {
   float h[64];
   for (int i = 0; i < 64; ++i) h[i] = 0.001f * (i + 1);
   cudaMemcpy(src, h, sizeof(h), cudaMemcpyHostToDevice);
-  for (int c : {2, 8}) {
+  cudaMemcpyToSymbol(cscal, h, 32 * sizeof(float));
+  for (int c : {2, 3, 4, 8}) {
+    run<4>("FFMA2 UNIFORM scalar x pair + acc, pair shared by runs", sink, src, c);
+    run<5>("FFMA2 UNIFORM scalar x pair + acc, 4 distinct registers", sink, src, c);
     run<0>("FFMA2 scalar x pair + acc, pair shared by runs of 6", sink, src, c);
     run<1>("FFMA2 scalar x pair + acc, 5 distinct registers", sink, src, c);
     run<2>("FFMA 3 distinct registers", sink, src, c);
