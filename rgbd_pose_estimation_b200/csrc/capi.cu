@@ -673,7 +673,7 @@ int score_range(rpe_ctx* ctx, int method, int slot_begin, int slot_end, Thresh t
       if (tm) cudaEventRecord(ctx->ev_ring[2 * rk], lane->stream);
       if (ck >= 0) cudaEventRecord(clk.start[ck], lane->stream);
       nseg = launch_score_fast(method, f, ctx->d_gen, ctx->d_fast, slot_begin, slot_end, th, ctx->d_votes, ctx->d_stats,
-                               ctx->wl, ctx->num_sms, lane->stream);
+                               ctx->wl, ctx->num_sms, lane->stream, 0, 0, (int)(lane - &g_lane[ctx->device][0]));
       if (ck >= 0) cudaEventRecord(clk.end[ck], lane->stream);
       if (tm) cudaEventRecord(ctx->ev_ring[2 * rk + 1], lane->stream);
       CK(cudaEventRecord(ctx->ev_lane[1], lane->stream));

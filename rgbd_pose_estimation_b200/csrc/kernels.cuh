@@ -73,7 +73,15 @@ void launch_minsolv_ms(const float* in24, int count, float* q4, float* t3, cudaS
 // worklist segment so that the launches of all chunks fill consecutive parts of one list (wl points at this chunk's part).
 int launch_score_fast(int method, const FrameView& f, const HypGen* gen, const HypFast* fast, int slot_begin,
                        int slot_end, Thresh th, int32_t* votes, FrameStats* st, Worklist wl, int num_sms, cudaStream_t s,
-                       int corr_base = 0, unsigned int seg_cap = 0);
+                       int corr_base = 0, unsigned int seg_cap = 0, int ur_lane = -1);
+// The correspondence-stationary 3-D / 3-D scorer (score_ur.cu: hypotheses in uniform registers, fed from a __constant__
+// buffer that belongs to scorer lane 0 / 1). ur_lane of launch_score_fast: the lane stream `s` is, -1 if `s` is no lane
+// (the buffer of a lane must not be rewritten while another launch that reads it may still run: stream order does that
+// for a lane's own stream only). Returns 0 if the frame / slot range is not for this kernel.
+int launch_score3d_ur_lane0(const FrameView& f, const HypGen* gen, const HypFast* fast, int slot_begin, int slot_end, float thr3d,
+                            int32_t* votes, FrameStats* st, Worklist wl, int num_sms, cudaStream_t s);
+int launch_score3d_ur_lane1(const FrameView& f, const HypGen* gen, const HypFast* fast, int slot_begin, int slot_end, float thr3d,
+                            int32_t* votes, FrameStats* st, Worklist wl, int num_sms, cudaStream_t s);
 // The 3-D / 3-D scorer fed straight from page-locked host arrays (fsrc.xw / fsrc.xc as the device sees them); the frame is
 // written to dxw / dxc on the way (may be null). Returns the number of worklist segments (= CTAs).
 int launch_score3d_stream(const FrameView& fsrc, float* dxw, float* dxc, const HypGen* gen, const HypFast* fast, int slot_begin,

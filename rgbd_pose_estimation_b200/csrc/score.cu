@@ -24,39 +24,9 @@
 #include <math_constants.h>
 
 #include "kernels.cuh"
+#include "score_common.cuh"
 
 namespace rpe {
-
-// ================================================================================================
-// small PTX helpers: mbarrier + 1-D bulk TMA
-// ================================================================================================
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_u32(dst_smem)),
-               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t ok = 0;
-  const uint32_t addr = smem_u32(bar);
-  while (!ok) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(addr), "r"(parity)
-        : "memory");
-  }
-}
 
 // ================================================================================================
 // reset / pack
@@ -191,47 +161,6 @@ void launch_pack(const FrameView& f, int kind, float4* pk_out, FrameStats* st, c
 }
 
 // ================================================================================================
-// this CTA's segment of the borderline worklist (see struct Worklist)
-// ================================================================================================
-struct WlSegment {
-  uint2* base;
-  unsigned int cap;
-  unsigned int* n;  // shared-memory counter
-  __device__ __forceinline__ explicit WlSegment(const Worklist& wl) {
-    __shared__ unsigned int counter;
-    n = &counter;
-    const unsigned int nseg = gridDim.x * gridDim.y, cta = blockIdx.y * gridDim.x + blockIdx.x;
-    cap = wl.capacity / nseg;
-    base = wl.entries + (size_t)cta * cap;
-    if (threadIdx.x == 0) counter = 0;  // ordered before the first push by the __syncthreads after the mbarrier init
-  }
-  __device__ __forceinline__ void push(uint2 e, FrameStats* st) {
-    const unsigned int i = atomicAdd(n, 1u);
-    if (i < cap)
-      base[i] = e;
-    else
-      st->wl_overflow = 1u;
-  }
-  // several entries of one thread with a single shared-memory atomic: reserve(k), then put(i), put(i + 1), ...
-  __device__ __forceinline__ unsigned int reserve(unsigned int k) { return atomicAdd(n, k); }
-  __device__ __forceinline__ void put(unsigned int i, uint2 e, FrameStats* st) {
-    if (i < cap)
-      base[i] = e;
-    else
-      st->wl_overflow = 1u;
-  }
-  // every thread of the CTA calls this once, after its last push
-  __device__ __forceinline__ void publish(const Worklist& wl, FrameStats* st) {
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      const unsigned int cnt = *n;
-      wl.counts[blockIdx.y * gridDim.x + blockIdx.x] = cnt < cap ? cnt : cap;
-      if (cnt) atomicAdd(&st->wl_count, cnt);
-    }
-  }
-};
-
-// ================================================================================================
 // fast tiled scorer — 3-D modality (RPE_SHINJI)
 // ================================================================================================
 // Guard band on s = r^2 - thr^2:  band = thr * u * (64 M + 16 thr),  u = 2^-24,
@@ -241,13 +170,6 @@ __device__ __forceinline__ float hyp_magnitude(const FrameStats* st, float nt0, 
   const float tn = sqrtf(nt0 * nt0 + nt1 * nt1 + nt2 * nt2);
   return (__uint_as_float(st->m_corr_bits) + tn) * 1.0001f;
 }
-// The error of s is 2|e| de + de^2 with |e| ~ thr and de <= 26.8 u M: the second-order term only matters for
-// thresholds down at the rounding level of the coordinates (thr <~ 30 u M), where it is covered by widening thr.
-__device__ __forceinline__ float guard_band_3d(float M, float thr) {
-  const float u = 5.9604644775390625e-08f;
-  return (thr + 32.f * u * M) * u * (64.f * M + 16.f * thr);
-}
-
 template <bool PACKED>
 struct HypRegs;
 
@@ -452,14 +374,6 @@ score3d_fast_kernel(const float4* __restrict__ pk, int npairs_pad, int pairs_per
 // applied to instead of the frame maximum. No pack kernel, no second copy of the frame in HBM.
 // TMA needs 16-byte aligned addresses and sizes: stages start at multiples of 4 correspondences and copy a multiple
 // of 4; the last 0..3 correspondences of the frame are read from global memory by the transposing threads.
-// (s.y < 0 ? 0xffff0000 : 0) | (s.x < 0 ? 0x0000ffff : 0): PRMT in its generic mode replicates the sign of the selected byte
-// when bit 3 of the selector nibble is set (0xB = sign of byte 3 of a, 0xF = sign of byte 3 of b)
-__device__ __forceinline__ unsigned int sign_words(float2 s) {
-  unsigned int d;
-  asm("prmt.b32 %0, %1, %2, 0xFFBB;" : "=r"(d) : "r"(__float_as_uint(s.x)), "r"(__float_as_uint(s.y)));
-  return d;
-}
-
 template <int HPT, int TILE, int THREADS, int MINB, int SUB, int PCOUNT>
 __global__ void __launch_bounds__(THREADS, MINB)
 score3d_raw_kernel(const float* __restrict__ xw, const float* __restrict__ xc, int n, int npairs_pad, int pairs_per_cta,
@@ -1586,7 +1500,7 @@ static int launch_variant(const FrameView& f, const HypGen* gen, const HypFast* 
 
 int launch_score_fast(int method, const FrameView& f, const HypGen* gen, const HypFast* fast, int slot_begin,
                       int slot_end, Thresh th, int32_t* votes, FrameStats* st, Worklist wl, int num_sms,
-                      cudaStream_t s, int corr_base, unsigned int seg_cap) {
+                      cudaStream_t s, int corr_base, unsigned int seg_cap, int ur_lane) {
   if (slot_end - slot_begin <= 0 || f.n <= 0) return 0;
   if (method != RPE_SHINJI) {
     const int kind = (method_uses_2d(method) ? 1 : 0) | (method_uses_3d(method) ? 2 : 0) | (method_uses_nl(method) ? 4 : 0);
@@ -1607,6 +1521,17 @@ int launch_score_fast(int method, const FrameView& f, const HypGen* gen, const H
   // A slot range narrower than one 1024-hypothesis CTA column (hypothesis-sharded frames, short passes): use narrower
   // CTAs and more of them per SM, so that the work shrinks with the range instead of idling half-empty threads.
   int variant = g_variant;
+  // The uniform-register scorer (score_ur.cu) is an opt-in: measured on config #4 it reaches 76 % of the FMA pipe against
+  // this file's 78 % (profiles/r02k_ur_kernel_ncu.md) — RPE_UR=1 lets it take whole dense frames against a full hypothesis
+  // column when the launch goes to a scorer lane, variant 30 forces it for every frame it can take (tests).
+  static const bool ur_on = getenv("RPE_UR") && getenv("RPE_UR")[0] == '1';
+  if ((variant == 30 || (variant == 14 && ur_on && slot_end - slot_begin > 512 && f.n >= 65536)) && (ur_lane == 0 || ur_lane == 1) &&
+      corr_base == 0 && seg_cap == 0 && slot_end - slot_begin <= 1024 && frame_raw_ok(f, 2)) {
+    const int nseg = ur_lane == 0 ? launch_score3d_ur_lane0(f, gen, fast, slot_begin, slot_end, th.thr3d, votes, st, wl, num_sms, s)
+                                  : launch_score3d_ur_lane1(f, gen, fast, slot_begin, slot_end, th.thr3d, votes, st, wl, num_sms, s);
+    if (nseg > 0) return nseg;
+  }
+  if (variant == 30) variant = 14;
   if (variant == 14) {
     const int nslots = slot_end - slot_begin;
     if (nslots <= 128) variant = 16;
