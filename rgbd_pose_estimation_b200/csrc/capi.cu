@@ -1016,50 +1016,48 @@ int do_ransac(rpe_ctx* ctx, int method, const int32_t* samples, rpe_sample_fn fn
       ctx->cur_method = method;
       CK(cudaEventRecord(ctx->ev_early, es));
       mark(es);  // 1: generator done
-      // now the frame: chunk by chunk on the copy stream, behind the generator's reads
-      CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_early, 0));
-      for (int c = 0; c < C; ++c) {
-        const size_t c0 = (size_t)c * ctx->chunk_corr;
-        const size_t cnt = (size_t)((ctx->n - (int)c0) < ctx->chunk_corr ? (ctx->n - (int)c0) : ctx->chunk_corr);
-        for (int k = 0; k < 5; ++k)
-          if (ctx->host_src[k] && ctx->view[k])
-            CK(cudaMemcpyAsync(ctx->d_raw[k] + 3 * c0, ctx->host_src[k] + 3 * c0, cnt * 3 * sizeof(float), cudaMemcpyHostToDevice,
-                               ctx->copy_stream));
-        CK(cudaEventRecord(ctx->ev_chunk[c], ctx->copy_stream));
-        mark(ctx->copy_stream);  // 2..: chunk c landed
-      }
-      CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_chunk[C - 1], 0));  // the context's own stream sees the whole frame
-      // the chunk scorers alternate between the device's lanes like the scorers of consecutive frames do: the head of
-      // one chunk's launch overlaps the tail of the previous one (they add into the same vote table with atomics)
+      // Now the frame, chunk by chunk on the copy stream. The copies start BESIDE the generator (its reads get slower,
+      // 40 -> 64 us, but the first chunk has landed when it ends; RPE_OVERLAP_EAGER=0: behind it), and every chunk's scorer is
+      // enqueued right after its copy, so that the host's issue order never holds a launch back (blocking frame 0.413 ->
+      // 0.396 ms, profiles/r02_latency_breakdown.md). The chunk scorers alternate between the device's lanes like the
+      // scorers of consecutive frames do: the head of one chunk's launch overlaps the tail of the previous one (they add
+      // into the same vote table with atomics).
+      static const bool eager = !(getenv("RPE_OVERLAP_EAGER") && getenv("RPE_OVERLAP_EAGER")[0] == '0');
+      CK(cudaStreamWaitEvent(ctx->copy_stream, eager ? ctx->ev_prev : ctx->ev_early, 0));
       bool lane_used[kMaxLanes] = {};
       for (int c = 0; c < C; ++c) {
+        const int c0 = c * ctx->chunk_corr;
+        const int cnt = (ctx->n - c0) < ctx->chunk_corr ? (ctx->n - c0) : ctx->chunk_corr;
+        for (int k = 0; k < 5; ++k)
+          if (ctx->host_src[k] && ctx->view[k])
+            CK(cudaMemcpyAsync(ctx->d_raw[k] + 3 * (size_t)c0, ctx->host_src[k] + 3 * (size_t)c0, (size_t)cnt * 3 * sizeof(float),
+                               cudaMemcpyHostToDevice, ctx->copy_stream));
+        CK(cudaEventRecord(ctx->ev_chunk[c], ctx->copy_stream));
+        mark(ctx->copy_stream);  // chunk c landed
         ScorerLane* L = c == 0 ? lane : lane_for(ctx);
         if (!L) L = lane;
         const int li = (int)(L - &g_lane[ctx->device][0]);
         std::lock_guard<std::mutex> g(L->mu);
         if (!lane_used[li]) CK(cudaStreamWaitEvent(L->stream, ctx->ev_early, 0));
         lane_used[li] = true;
-        {
-          cudaStream_t lane_stream = L->stream;
-          const int c0 = c * ctx->chunk_corr;
-          const int cnt = (ctx->n - c0) < ctx->chunk_corr ? (ctx->n - c0) : ctx->chunk_corr;
-          CK(cudaStreamWaitEvent(lane_stream, ctx->ev_chunk[c], 0));
-          FrameView fc = fv;
-          fc.xw = fv.xw + 3 * (size_t)c0;
-          fc.xc = fv.xc + 3 * (size_t)c0;
-          fc.n = cnt;
-          const int npairs = (cnt + 1) / 2;
-          fc.npairs_pad = ((npairs + kSubPairs - 1) / kSubPairs) * kSubPairs;
-          Worklist wc = ctx->wl;
-          wc.entries = ctx->wl.entries + (size_t)c * ctx->num_sms * seg_cap;
-          wc.counts = ctx->wl.counts + (size_t)c * ctx->num_sms;
-          launch_score_fast(method, fc, ctx->d_gen, ctx->d_fast, 0, H * S, th, ctx->d_votes, ctx->d_stats, wc, ctx->num_sms,
-                            lane_stream, c0, seg_cap);
-          ctx->launches++;
-          mark(lane_stream);  // chunk c scored
-          CK(cudaEventRecord(ctx->ev_lane_done[li], lane_stream));  // (the last record of a lane is the one that counts)
-        }
+        cudaStream_t lane_stream = L->stream;
+        CK(cudaStreamWaitEvent(lane_stream, ctx->ev_chunk[c], 0));
+        FrameView fc = fv;
+        fc.xw = fv.xw + 3 * (size_t)c0;
+        fc.xc = fv.xc + 3 * (size_t)c0;
+        fc.n = cnt;
+        const int npairs = (cnt + 1) / 2;
+        fc.npairs_pad = ((npairs + kSubPairs - 1) / kSubPairs) * kSubPairs;
+        Worklist wc = ctx->wl;
+        wc.entries = ctx->wl.entries + (size_t)c * ctx->num_sms * seg_cap;
+        wc.counts = ctx->wl.counts + (size_t)c * ctx->num_sms;
+        launch_score_fast(method, fc, ctx->d_gen, ctx->d_fast, 0, H * S, th, ctx->d_votes, ctx->d_stats, wc, ctx->num_sms,
+                          lane_stream, c0, seg_cap);
+        ctx->launches++;
+        mark(lane_stream);  // chunk c scored
+        CK(cudaEventRecord(ctx->ev_lane_done[li], lane_stream));  // (the last record of a lane is the one that counts)
       }
+      CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_chunk[C - 1], 0));  // the context's own stream sees the whole frame
       for (int li = 0; li < kMaxLanes; ++li)
         if (lane_used[li]) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_lane_done[li], 0));
       Worklist wall = ctx->wl;
@@ -1075,7 +1073,7 @@ int do_ransac(rpe_ctx* ctx, int method, const int32_t* samples, rpe_sample_fn fn
       if (trace) {
         mark(ctx->stream);  // mask + result copies enqueued behind it
         cudaStreamSynchronize(ctx->stream);
-        fprintf(stderr, "[rpe overlap trace] us after the call: generator %d chunks landed / scored, fix-up+replay, mask:", C);
+        fprintf(stderr, "[rpe overlap trace] us after the call: generator, %d x (chunk landed, chunk scored), fix-up+replay, mask:", C);
         for (int i = 1; i < ntev; ++i) {
           float ms = 0.f;
           cudaEventElapsedTime(&ms, tev[0], tev[i]);
