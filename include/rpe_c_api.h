@@ -130,10 +130,13 @@ int rpe_upload_device(rpe_ctx* ctx, const float* bv, const float* xc, const floa
 /* Latency knob for a caller that waits for every frame: with chunks >= 2 (at most 8), rpe_upload of PAGE-LOCKED host
  * arrays of the 3-D / 3-D family (x_c and x_w only, n >= 65 536) copies the frame in `chunks` pieces on a copy stream,
  * and the next rpe_ransac(_async) with RPE_SHINJI whose Iter fits one device pass starts before the copy has finished:
- * the generator reads its 3 H sample points straight from the host arrays over PCIe, the scorer runs once per chunk as
- * the chunk lands (votes accumulate). Results are identical. A dense frame's blocking latency drops by most of the
- * 0.15 ms its upload takes; a pipeline of asynchronous frames gains nothing (and pays three more scorer launches per
- * frame), hence off by default (chunks = 0). Pageable host memory is always copied the plain way. */
+ * the generator reads its 3 H sample points straight from the host arrays over PCIe while the first chunk is already
+ * on the bus, the scorer runs once per chunk as the chunk lands (votes accumulate). Results are identical. A dense
+ * frame's blocking latency drops by about half of the 0.15 ms its upload takes (0.47 -> 0.40 ms); a pipeline of
+ * asynchronous frames gains nothing (and pays three more scorer launches per frame), hence off by default (chunks = 0).
+ * chunks = 1 ("stream mode", H <= 1024): no copy at all — the scorer's bulk-TMA loads read the frame from the page-locked
+ * host arrays while it scores and leave the device copy behind for the fix-up, mask and refit kernels (same latency as
+ * 4 chunks, no copy-engine work). Pageable host memory is always copied the plain way. */
 int rpe_set_upload_overlap(rpe_ctx* ctx, int chunks);
 /* Tp = double adapters (the reference's TestMain.cpp runs its estimators as <double>): host arrays in binary64. The
  * next rpe_ransac on this context generates, scores, replays and masks in binary64 in the reference's operation order

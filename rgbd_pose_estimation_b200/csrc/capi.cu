@@ -1188,6 +1188,8 @@ static int create_common(int device, void* stream, bool own, rpe_ctx** out) {
     return RPE_ERR_CUDA;
   }
   ctx->num_sms = prop.multiProcessorCount;
+  if (const char* e = getenv("RPE_KABSCH_POLAR"))  // measurement aid: 0 = Jacobi SVD in every Kabsch refit of this device
+    rpe::set_kabsch_polar(e[0] != '0');
   ctx->rb.num_sms = ctx->num_sms;
   if (prop.major < 10) {
     delete ctx;
@@ -2288,6 +2290,12 @@ int rpe_debug_set_nosync(int v) {
 int rpe_debug_set_score_variant(int v) {
   rpe::set_score_variant(v);
   return RPE_OK;
+}
+// 0: the Kabsch refits of the CURRENT device always take the Jacobi SVD instead of the polar iteration (A/B in the tests)
+int rpe_debug_set_kabsch_polar(int on) {
+  cudaDeviceSynchronize();
+  rpe::set_kabsch_polar(on);
+  return cudaGetLastError() == cudaSuccess ? RPE_OK : RPE_ERR_CUDA;
 }
 // Back to the shipped configuration: every process-global test hook, and (ctx may be NULL) the per-context ones.
 int rpe_debug_reset(rpe_ctx* ctx) {

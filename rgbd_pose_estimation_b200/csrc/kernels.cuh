@@ -55,6 +55,8 @@ constexpr int kHypPerThread = 2;   // hypotheses held in registers by one thread
 void launch_reset_stats(FrameStats* st, cudaStream_t s);
 void launch_pack(const FrameView& f, int kind, float4* pk_out, FrameStats* st, cudaStream_t s);
 
+void set_kabsch_polar(int on);  // debug: 0 = the Kabsch refits always take the Jacobi SVD (per device, synchronous)
+
 // -- generation ----------------------------------------------------------------------------------
 void launch_hypgen(int method, const FrameView& f, const int32_t* samples_dev, int H, HypGen* gen, HypFast* fast,
                    int32_t* votes, FrameStats* st, cudaStream_t s, const int32_t* stale_eff = nullptr);

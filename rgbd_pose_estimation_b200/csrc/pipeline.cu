@@ -430,6 +430,68 @@ __device__ __forceinline__ void final_reduce_partials(const double* __restrict__
   }
 }
 
+// The rotation of a cross-covariance with three healthy singular values and a positive determinant is its orthogonal
+// polar factor U V^T. Scaled Newton iteration X <- (g X + X^-T / g) / 2, g^2 = |X^-1|_F / |X|_F (Higham): quadratic
+// convergence, ~6 steps of one 3x3 inverse each — about a sixth of the instructions of the two-sided Jacobi SVD a single
+// thread otherwise walks at the end of the mask kernel (profiles/r02m_small_kernels.md). Accepted only if the result is
+// orthogonal to 1e-13 with determinant +1; reflections (det M <= 0), rank-deficient and badly conditioned covariances
+// (the K = 3 samples of the generator never come here) return false and take the SVD path. Agreement with the SVD route:
+// < 1e-12 in R (tests/test_gpu_ao.py refits, tools/fuzz_refit.py), against a 1e-6 rad bar.
+__device__ int g_kabsch_polar = 1;  // 0: always the Jacobi SVD (rpe_debug_set_kabsch_polar, A/B in the tests)
+void set_kabsch_polar(int on) {
+  const int v = on ? 1 : 0;
+  cudaMemcpyToSymbol(g_kabsch_polar, &v, sizeof(int));
+}
+__device__ bool polar_rotation_newton(const double* M, double* R) {
+  double X[9], fro2 = 0.0;
+  for (int i = 0; i < 9; ++i) fro2 += M[i] * M[i];
+  if (!(fro2 > 0.0) || !(fro2 < 1e300)) return false;
+  const double inv_fro = 1.0 / sqrt(fro2);
+  for (int i = 0; i < 9; ++i) X[i] = M[i] * inv_fro;  // singular values now in (0, 1]
+  for (int it = 0; it < 16; ++it) {
+    double C[9];  // cofactors: X^-T = C / det
+    C[0] = X[4] * X[8] - X[5] * X[7];
+    C[1] = X[5] * X[6] - X[3] * X[8];
+    C[2] = X[3] * X[7] - X[4] * X[6];
+    C[3] = X[2] * X[7] - X[1] * X[8];
+    C[4] = X[0] * X[8] - X[2] * X[6];
+    C[5] = X[1] * X[6] - X[0] * X[7];
+    C[6] = X[1] * X[5] - X[2] * X[4];
+    C[7] = X[2] * X[3] - X[0] * X[5];
+    C[8] = X[0] * X[4] - X[1] * X[3];
+    const double det = X[0] * C[0] + X[1] * C[1] + X[2] * C[2];
+    if (it == 0 && !(det > 1e-7)) return false;  // sigma_1 sigma_2 sigma_3 / |M|_F^3: reflection, rank loss or cond >~ 1e6
+    if (!(det > 0.0)) return false;
+    double nx = 0.0, nc = 0.0;
+    for (int i = 0; i < 9; ++i) {
+      nx += X[i] * X[i];
+      nc += C[i] * C[i];
+    }
+    const double g2 = sqrt(nc / nx) / det;  // |X^-1|_F / |X|_F
+    const double g = sqrt(g2);
+    const double a = 0.5 * g, b = 0.5 / (g * det);
+    double change = 0.0;
+    for (int i = 0; i < 9; ++i) {
+      const double xn = a * X[i] + b * C[i];
+      const double d = xn - X[i];
+      change += d * d;
+      X[i] = xn;
+    }
+    if (change < 1e-30) break;
+  }
+  // orthogonality and orientation of what came out
+  double worst = 0.0;
+  for (int i = 0; i < 3; ++i)
+    for (int j = i; j < 3; ++j) {
+      const double d = X[i] * X[j] + X[3 + i] * X[3 + j] + X[6 + i] * X[6 + j] - (i == j ? 1.0 : 0.0);
+      worst = fmax(worst, fabs(d));
+    }
+  const double det = X[0] * (X[4] * X[8] - X[5] * X[7]) - X[1] * (X[3] * X[8] - X[5] * X[6]) + X[2] * (X[3] * X[7] - X[4] * X[6]);
+  if (!(worst < 1e-13) || !(fabs(det - 1.0) < 1e-12)) return false;
+  for (int i = 0; i < 9; ++i) R[i] = X[i];
+  return true;
+}
+
 // Kabsch from moments m[0]=K, m[1..3]=sum x_w, m[4..6]=sum x_c, m[7..15]=sum x_c x_w^T (row-major).
 // Same closed form as shinji (centroids, cross-covariance / K, SVD, det fix, t = c_c - R c_w), evaluated in binary64.
 __device__ bool kabsch_from_moments(const double* m, float* q_out, float* t_out) {
@@ -443,8 +505,8 @@ __device__ bool kabsch_from_moments(const double* m, float* q_out, float* t_out)
   double M[9];
   for (int i = 0; i < 3; ++i)
     for (int j = 0; j < 3; ++j) M[3 * i + j] = (m[7 + 3 * i + j] - K * cc[i] * cw[j]) / K;
-  double q[4];
-  const bool ok = rotation_from_covariance<double>(M, q);
+  double q[4], Rp[9];
+  const bool ok = (g_kabsch_polar && polar_rotation_newton(M, Rp)) ? so3_from_matrix<double>(Rp, q) : rotation_from_covariance<double>(M, q);
   double rc[3];
   quat_rotate<double>(q, cw, rc);
   for (int k = 0; k < 4; ++k) q_out[k] = (float)q[k];
