@@ -105,7 +105,10 @@ RPE_UNROLL
   while (!finished && sweeps < 64) {
     finished = true;
     ++sweeps;
+    // (both loops unrolled on the device: with constant p, q the three matrices stay in registers instead of local memory)
+RPE_UNROLL
     for (int p = 1; p < 3; ++p) {
+RPE_UNROLL
       for (int q = 0; q < p; ++q) {
         const T pm = precision * max_diag;
         const T threshold = tiny > pm ? tiny : pm;
@@ -176,28 +179,35 @@ RPE_UNROLL
   }
 RPE_UNROLL
   for (int i = 0; i < 3; ++i) s[i] *= scale;
+  // selection sort, largest first (the swap target is tested against constants so that no index is dynamic)
+  bool sorting = true;
+RPE_UNROLL
   for (int i = 0; i < 3; ++i) {
     int pos = i;
     T best = s[i];
+RPE_UNROLL
     for (int k = i + 1; k < 3; ++k)
-      if (s[k] > best) {
+      if (sorting && s[k] > best) {
         best = s[k];
         pos = k;
       }
-    if (best == T(0)) break;
-    if (pos != i) {
-      T tmp = s[i];
-      s[i] = s[pos];
-      s[pos] = tmp;
-      for (int r = 0; r < 3; ++r) {
-        tmp = U[3 * r + i];
-        U[3 * r + i] = U[3 * r + pos];
-        U[3 * r + pos] = tmp;
-        tmp = V[3 * r + i];
-        V[3 * r + i] = V[3 * r + pos];
-        V[3 * r + pos] = tmp;
+    if (best == T(0)) sorting = false;
+RPE_UNROLL
+    for (int k = i + 1; k < 3; ++k)
+      if (sorting && pos == k) {
+        T tmp = s[i];
+        s[i] = s[k];
+        s[k] = tmp;
+RPE_UNROLL
+        for (int r = 0; r < 3; ++r) {
+          tmp = U[3 * r + i];
+          U[3 * r + i] = U[3 * r + k];
+          U[3 * r + k] = tmp;
+          tmp = V[3 * r + i];
+          V[3 * r + i] = V[3 * r + k];
+          V[3 * r + k] = tmp;
+        }
       }
-    }
   }
 }
 
