@@ -2291,6 +2291,15 @@ int rpe_debug_set_score_variant(int v) {
   rpe::set_score_variant(v);
   return RPE_OK;
 }
+// Host logic of the opt-in uniform-register scorer's launcher, callable without a device (tests): CTA shape for a frame of
+// `n` correspondences against `nslots` hypothesis slots on `num_sms` SMs; out6 = {pairs per thread, threads, hypothesis
+// rows, correspondence columns, pairs per column, tail pairs}. Returns 1 if the kernel takes the frame.
+int rpe_debug_ur_shape(int n, int nslots, int num_sms, int* out6) {
+  if (!out6 || n <= 0) return 0;
+  const int npairs = (n + 1) / 2;
+  const int npairs_pad = ((npairs + rpe::kSubPairs - 1) / rpe::kSubPairs) * rpe::kSubPairs;
+  return rpe::ur_shape_for(npairs_pad, nslots, num_sms, out6);
+}
 // 0: the Kabsch refits of the CURRENT device always take the Jacobi SVD instead of the polar iteration (A/B in the tests)
 int rpe_debug_set_kabsch_polar(int on) {
   cudaDeviceSynchronize();

@@ -80,6 +80,7 @@ int launch_score_fast(int method, const FrameView& f, const HypGen* gen, const H
 // buffer that belongs to scorer lane 0 / 1). ur_lane of launch_score_fast: the lane stream `s` is, -1 if `s` is no lane
 // (the buffer of a lane must not be rewritten while another launch that reads it may still run: stream order does that
 // for a lane's own stream only). Returns 0 if the frame / slot range is not for this kernel.
+int ur_shape_for(int npairs_pad, int nslots, int num_sms, int* out6);  // host logic of the launcher (tests)
 int launch_score3d_ur_lane0(const FrameView& f, const HypGen* gen, const HypFast* fast, int slot_begin, int slot_end, float thr3d,
                             int32_t* votes, FrameStats* st, Worklist wl, int num_sms, cudaStream_t s);
 int launch_score3d_ur_lane1(const FrameView& f, const HypGen* gen, const HypFast* fast, int slot_begin, int slot_end, float thr3d,

@@ -336,6 +336,22 @@ static int ur_launch(const UrShape& sh, const FrameView& f, const HypGen* gen, c
   return sh.gx * sh.hsplit;
 }
 
+#if RPE_UR_LANE == 0
+// host logic only (no device needed): the shape the launcher would pick; out = {P, T, hsplit, columns, pairs per column, tail}
+int ur_shape_for(int npairs_pad, int nslots, int num_sms, int* out6) {
+  if (npairs_pad <= 0 || nslots <= 0 || nslots > kUrMaxHyp || num_sms <= 0) return 0;
+  const UrShape sh = ur_pick_shape(npairs_pad, nslots, num_sms);
+  if (sh.P == 0) return 0;
+  out6[0] = sh.P;
+  out6[1] = sh.T;
+  out6[2] = sh.hsplit;
+  out6[3] = sh.gx;
+  out6[4] = sh.pairs_per_cta;
+  out6[5] = sh.pairs_per_cta > sh.T * sh.P ? sh.pairs_per_cta - sh.T * sh.P : 0;
+  return 1;
+}
+#endif
+
 #define RPE_UR_CAT2(a, b) a##b
 #define RPE_UR_CAT(a, b) RPE_UR_CAT2(a, b)
 // Returns the number of worklist segments (= CTAs), 0 if the frame / slot range is not for this kernel.
