@@ -985,12 +985,12 @@ int do_ransac(rpe_ctx* ctx, int method, const int32_t* samples, rpe_sample_fn fn
         return do_finish(ctx, method, th, out, mask, blocking);
       }
       static const bool trace = getenv("RPE_OVERLAP_TRACE") != nullptr;  // debugging aid: device timeline of this path on stderr
-      static thread_local cudaEvent_t tev[24] = {};
+      static thread_local cudaEvent_t tev[40] = {};
       int ntev = 0;
       if (trace && !tev[0])
-        for (int i = 0; i < 24; ++i) cudaEventCreate(&tev[i]);
+        for (int i = 0; i < 40; ++i) cudaEventCreate(&tev[i]);
       auto mark = [&](cudaStream_t st) {
-        if (trace && ntev < 24) cudaEventRecord(tev[ntev++], st);
+        if (trace && ntev < 40) cudaEventRecord(tev[ntev++], st);
       };
       CK(cudaEventRecord(ctx->ev_prev, ctx->stream));  // everything enqueued so far (it may still read the arrays / the tables)
       CK(cudaStreamWaitEvent(es, ctx->ev_prev, 0));
@@ -1051,6 +1051,7 @@ int do_ransac(rpe_ctx* ctx, int method, const int32_t* samples, rpe_sample_fn fn
         Worklist wc = ctx->wl;
         wc.entries = ctx->wl.entries + (size_t)c * ctx->num_sms * seg_cap;
         wc.counts = ctx->wl.counts + (size_t)c * ctx->num_sms;
+        mark(lane_stream);  // chunk c: the lane has passed its waits
         launch_score_fast(method, fc, ctx->d_gen, ctx->d_fast, 0, H * S, th, ctx->d_votes, ctx->d_stats, wc, ctx->num_sms,
                           lane_stream, c0, seg_cap);
         ctx->launches++;
@@ -1073,7 +1074,7 @@ int do_ransac(rpe_ctx* ctx, int method, const int32_t* samples, rpe_sample_fn fn
       if (trace) {
         mark(ctx->stream);  // mask + result copies enqueued behind it
         cudaStreamSynchronize(ctx->stream);
-        fprintf(stderr, "[rpe overlap trace] us after the call: generator, %d x (chunk landed, chunk scored), fix-up+replay, mask:", C);
+        fprintf(stderr, "[rpe overlap trace] us after the call: generator, %d x (chunk landed, scorer may start, chunk scored), fix-up+replay, mask:", C);
         for (int i = 1; i < ntev; ++i) {
           float ms = 0.f;
           cudaEventElapsedTime(&ms, tev[0], tev[i]);
