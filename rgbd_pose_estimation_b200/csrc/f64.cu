@@ -237,23 +237,32 @@ fixup64_kernel(int method, FrameView64 f, const HypGen64* __restrict__ gen, Thre
   for (unsigned int i = blockIdx.y * blockDim.x + threadIdx.x; i < count; i += gridDim.y * blockDim.x) {
     const uint2 e = seg[i];
     const int slot = (int)e.x;
-    const int modality = (int)(e.y >> 30);
-    const int c = (int)(e.y & 0x3fffffffu);
     double q[4], t[3];
     for (int k = 0; k < 4; ++k) q[k] = gen[slot].q[k];
     for (int k = 0; k < 3; ++k) t[k] = gen[slot].t[k];
-    bool in = false;
-    if (modality == 1) {
-      const D3 xc = load_col64(f.xc, c);
-      in = dx_is_valid(xc) && dx_test_3d(q, t, load_col64(f.xw, c), xc, th.thr3d);
-    } else if (modality == 2) {
-      in = dx_is_valid(load_col64(f.xc, c)) && dx_test_nl(q, load_col64(f.nw, c), load_col64(f.nc, c), th.cos_nl);
-    } else {
+    auto one = [&](int modality, int c) -> bool {
+      if (modality == 1) {
+        const D3 xc = load_col64(f.xc, c);
+        return dx_is_valid(xc) && dx_test_3d(q, t, load_col64(f.xw, c), xc, th.thr3d);
+      }
+      if (modality == 2) return dx_is_valid(load_col64(f.xc, c)) && dx_test_nl(q, load_col64(f.nw, c), load_col64(f.nc, c), th.cos_nl);
       double Rm[9];
       if (method == RPE_KNEIP) dx_quat_to_matrix(q, Rm);
-      in = dx_test_2d(q, t, method == RPE_KNEIP ? Rm : nullptr, load_col64(f.xw, c), load_col64(f.bv, c), th.cos_thr);
+      return dx_test_2d(q, t, method == RPE_KNEIP ? Rm : nullptr, load_col64(f.xw, c), load_col64(f.bv, c), th.cos_thr);
+    };
+    int add = 0;
+    if ((e.y >> 30) == 3u) {  // unit entry of the multi-modality scorer: pair index, six borderline bits (see fixup_kernel)
+      const int c0 = 2 * (int)(e.y & 0xffffffu);
+      unsigned int bits = (e.y >> 24) & 0x3fu;
+      while (bits) {
+        const int b = __ffs(bits) - 1;
+        bits &= bits - 1u;
+        add += one(b >> 1, c0 + (b & 1)) ? 1 : 0;
+      }
+    } else {
+      add = one((int)(e.y >> 30), (int)(e.y & 0x3fffffffu)) ? 1 : 0;
     }
-    if (in) atomicAdd(&votes[slot], 1);
+    if (add) atomicAdd(&votes[slot], add);
   }
 }
 void launch_fixup64(int method, const FrameView64& f, const HypGen64* gen, Thresh64 th, int32_t* votes, FrameStats* st,

@@ -897,6 +897,7 @@ struct MultiSrc {
   const float* a[5];  // RAW: the record's source arrays in record order: x_w, [x_c], [b], [n_w, n_c]
   const float* xc;    // RAW: camera points for the isValid gate of the normal test (may equal a[1])
   int n;
+  int unit_entries;   // DIRECT: one worklist entry per borderline (pair, hypothesis) unit (needs n <= 2^25), else one per value
 };
 
 template <int KIND, int TILE, int THREADS, bool DIRECT, bool RAW>
@@ -924,6 +925,7 @@ score_multi_fast_kernel(MultiSrc src, int npairs_pad, int pairs_per_cta, const H
   const float4* pk = src.pk;
 
   const int tid = threadIdx.x;
+  const bool unit_entries = src.unit_entries != 0;
   const int p_begin = blockIdx.x * pairs_per_cta;
   const int p_end = min(p_begin + pairs_per_cta, npairs_pad);
   const int npairs = p_end - p_begin;
@@ -1031,6 +1033,7 @@ score_multi_fast_kernel(MultiSrc src, int npairs_pad, int pairs_per_cta, const H
     }
   }
 
+  int xtra = 0;  // borderline evaluations beyond one per queued entry (unit entries)
   // One (pair, hypothesis) unit.
   // DIRECT (default): a borderline evaluation is queued for the exact fix-up on the spot instead of being counted —
   //   frames with many near-threshold evaluations (dense frames, low outlier ratios, pixel-level 2-D thresholds) would
@@ -1124,6 +1127,27 @@ score_multi_fast_kernel(MultiSrc src, int npairs_pad, int pairs_per_cta, const H
       // (Two warp-cooperative variants of this slow path — a warp-uniform vote + ballots into per-warp sub-segments, and
       // ballot aggregation among the branching lanes with a shared-memory warp counter — were measured in round 2 and
       // were slower for the 2-D kinds: the vote sits in the fast path, the counter adds two shared-memory round trips.)
+      if (any && unit_entries) {
+        // ONE entry for the unit: (slot, pair index | six borderline bits << 24 | 3 << 30), bit 2 mod + uu. The fix-up kernel
+        // expands it. Half the instructions of the per-value form below, and the branch is taken by a quarter of the
+        // warp-iterations of a dense frame at 30 % outliers (a percent of a good hypothesis' 2-D evaluations is borderline).
+        unsigned int bits = 0u;
+#pragma unroll
+        for (int mod = 0; mod < 3; ++mod) {
+          if ((mod == 0 && !KT::k2) || (mod == 1 && !KT::k3) || (mod == 2 && !KT::kn)) continue;
+#pragma unroll
+          for (int uu = 0; uu < 2; ++uu) {
+            const float v = val[mod][uu];
+            if (fabsf(v) <= bnd[mod][uu]) {
+              bits |= 1u << (2 * mod + uu);
+              cnt[k] -= (int)(__float_as_uint(v) >> 31);
+            }
+          }
+        }
+        xtra += __popc(bits) - 1;
+        seg.push(make_uint2((unsigned int)slot[k], ((unsigned int)corr0 >> 1) | (bits << 24) | (3u << 30)), st);
+        return;
+      }
       if (any) {  // one reservation for all borderline values of this thread's unit
         unsigned int nb = 0;
 #pragma unroll
@@ -1345,7 +1369,16 @@ score_multi_fast_kernel(MultiSrc src, int npairs_pad, int pairs_per_cta, const H
 #pragma unroll
   for (int k = 0; k < HPT; ++k)
     if (slot[k] >= 0 && cnt[k] != 0) atomicAdd(&votes[slot[k]], cnt[k]);
-  seg.publish(wl, st);
+  __shared__ unsigned int xtra_cta;
+  if (DIRECT) {  // (uniform) evaluations behind the unit entries, for the n_borderline diagnostic
+    if (tid == 0) xtra_cta = 0u;
+    __syncthreads();
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) xtra += __shfl_xor_sync(0xffffffffu, xtra, o);
+    if ((tid & 31) == 0 && xtra) atomicAdd(&xtra_cta, (unsigned int)xtra);
+    __syncthreads();
+  }
+  seg.publish(wl, st, DIRECT ? xtra_cta : 0u);
 }
 
 template <int KIND, int THREADS>
@@ -1378,6 +1411,8 @@ static int launch_multi_t(const FrameView& f, const HypGen* gen, const HypFast* 
   src.pk = f.pk;
   src.n = f.n;
   src.xc = f.xc;
+  static const bool unit_off = getenv("RPE_UNIT_ENTRIES") && getenv("RPE_UNIT_ENTRIES")[0] == '0';  // measurement aid
+  src.unit_entries = (!unit_off && KIND != 1 && f.n <= (1 << 25)) ? 1 : 0;  // (2-D only: at most two values per unit, no gain)
   {
     int c = 0;
     src.a[c++] = f.xw;
@@ -1555,7 +1590,7 @@ int launch_score_fast(int method, const FrameView& f, const HypGen* gen, const H
 // ================================================================================================
 // exact-order evaluation: worklist fix-up and whole-frame fallback
 // ================================================================================================
-// modality codes carried in bits 30..31 of a worklist entry: 0 = 2-D, 1 = 3-D, 2 = normal
+// modality codes carried in bits 30..31 of a worklist entry: 0 = 2-D, 1 = 3-D, 2 = normal, 3 = a unit entry (see fixup_kernel)
 __device__ __forceinline__ bool exact_eval(int method, int modality, const FrameView& f, const HypGen& h, const float* Rm,
                                            int c, const Thresh& th) {
   if (modality == 1) {
@@ -1597,16 +1632,27 @@ fixup_kernel(int method, FrameView f, const HypGen* __restrict__ gen, Thresh th,
     const uint2 e = seg[i];
     const int slot = (int)e.x;
     const int modality = (int)(e.y >> 30);
-    const int c = (int)(e.y & 0x3fffffffu);
     const HypGen h = gen[slot];
     float Rm[9];
     if (method == RPE_KNEIP) ex_quat_to_matrix(h.q, Rm);
-    if (exact_eval(method, modality, f, h, Rm, c, th)) {
+    int add = 0;
+    if (modality == 3) {  // a unit entry of the multi-modality scorer: pair index, six borderline bits (2 modality + which of the pair)
+      const int c0 = 2 * (int)(e.y & 0xffffffu);
+      unsigned int bits = (e.y >> 24) & 0x3fu;
+      while (bits) {
+        const int b = __ffs(bits) - 1;
+        bits &= bits - 1u;
+        add += exact_eval(method, b >> 1, f, h, Rm, c0 + (b & 1), th) ? 1 : 0;
+      }
+    } else {
+      add = exact_eval(method, modality, f, h, Rm, (int)(e.y & 0x3fffffffu), th) ? 1 : 0;
+    }
+    if (add) {
       const unsigned int rel = (unsigned int)slot - (unsigned int)slot_begin;
       if (rel / kFixupWindow == window)
-        atomicAdd(&hist[rel % kFixupWindow], 1);
+        atomicAdd(&hist[rel % kFixupWindow], add);
       else
-        atomicAdd(&votes[slot], 1);
+        atomicAdd(&votes[slot], add);
     }
   }
   __syncthreads();

@@ -71,13 +71,14 @@ struct WlSegment {
     else
       st->wl_overflow = 1u;
   }
-  // every thread of the CTA calls this once, after its last push
-  __device__ __forceinline__ void publish(const Worklist& wl, FrameStats* st) {
+  // every thread of the CTA calls this once, after its last push. `extra`: evaluations the entries stand for beyond one
+  // each (a unit entry carries up to six), summed over the CTA by the caller — only the n_borderline diagnostic sees it.
+  __device__ __forceinline__ void publish(const Worklist& wl, FrameStats* st, unsigned int extra = 0u) {
     __syncthreads();
     if (threadIdx.x == 0) {
       const unsigned int cnt = *n;
       wl.counts[blockIdx.y * gridDim.x + blockIdx.x] = cnt < cap ? cnt : cap;
-      if (cnt) atomicAdd(&st->wl_count, cnt);
+      if (cnt + extra) atomicAdd(&st->wl_count, cnt + extra);
     }
   }
 };
