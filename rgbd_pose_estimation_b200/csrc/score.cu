@@ -1074,11 +1074,21 @@ score_multi_fast_kernel(MultiSrc src, int npairs_pad, int pairs_per_cta, const H
       float2 n2 = __fmul2_rn(ny0, ny0);
       n2 = __ffma2_rn(ny1, ny1, n2);
       n2 = __ffma2_rn(ny2, ny2, n2);
+      const float2 dabs = make_float2(fabsf(d.x), fabsf(d.y));  // two LOP3 on the ALU pipe, which has room
       float2 band2 = __ffma2_rn(make_float2(bc[k].k2_2d, bc[k].k2_2d), n2, make_float2(bc[k].c0_2d, bc[k].c0_2d));
-      band2 = __ffma2_rn(make_float2(bc[k].k1_2d, bc[k].k1_2d), kBandAbs ? make_float2(fabsf(d.x), fabsf(d.y)) : d,
+      band2 = __ffma2_rn(make_float2(bc[k].k1_2d, bc[k].k1_2d), kBandAbs ? dabs : d,
                          band2);  // hybrids: k1 is stored negated, -k1 d' (see set_bands)
-      val[0][0] = fmaf(c2, n2.x, d.x * fabsf(d.x));
-      val[0][1] = fmaf(c2, n2.y, d.y * fabsf(d.y));
+      // F' = d'|d'| + cos^2 |y|^2 of both correspondences as two packed instructions (same products, same single rounding
+      // of the sum as the scalar fmaf(c2, n2, d * |d|) they replace: four FMA-pipe cycles instead of eight)
+      // (measured: 1-2 % for shinji_kneip, nothing for the three-modality kind, 1 % slower for the 2-D-only kind, which keeps the scalar form)
+      if (KIND == 1) {
+        val[0][0] = fmaf(c2, n2.x, d.x * fabsf(d.x));
+        val[0][1] = fmaf(c2, n2.y, d.y * fabsf(d.y));
+      } else {
+        const float2 fv = __ffma2_rn(make_float2(c2, c2), n2, __fmul2_rn(d, dabs));
+        val[0][0] = fv.x;
+        val[0][1] = fv.y;
+      }
       bnd[0][0] = band2.x;
       bnd[0][1] = band2.y;
     }
