@@ -1137,7 +1137,7 @@ score_multi_fast_kernel(MultiSrc src, int npairs_pad, int pairs_per_cta, const H
       // (Two warp-cooperative variants of this slow path — a warp-uniform vote + ballots into per-warp sub-segments, and
       // ballot aggregation among the branching lanes with a shared-memory warp counter — were measured in round 2 and
       // were slower for the 2-D kinds: the vote sits in the fast path, the counter adds two shared-memory round trips.)
-      if (any && unit_entries) {
+      if (KIND != 1 && any && unit_entries) {  // (compiled out for the 2-D-only kind: at most two values per unit, no gain)
         // ONE entry for the unit: (slot, pair index | six borderline bits << 24 | 3 << 30), bit 2 mod + uu. The fix-up kernel
         // expands it. Half the instructions of the per-value form below, and the branch is taken by a quarter of the
         // warp-iterations of a dense frame at 30 % outliers (a percent of a good hypothesis' 2-D evaluations is borderline).
