@@ -12,8 +12,11 @@
 //                        from the operand-reuse cache (profiles/r02_ubench_ur.log)
 //
 // The price is the vote count: a hypothesis' votes are spread over the threads. Each thread packs the sign words of its
-// P pairs (PRMT + IADD3, as before), one REDUX adds the packed words of the warp and one lane adds the result to the CTA's
-// shared-memory counter of that hypothesis; the counters are decoded and flushed to the vote table when the CTA ends.
+// P pairs (PRMT + IADD3, as before), one REDUX adds the packed words of the warp and one lane parks the sum, together with
+// the ballot of the lanes that saw a borderline value, in the warp's own row of a shared-memory table (no atomics); flagged
+// hypotheses are re-walked per warp after the loop, and the rows are added, decoded and flushed to the vote table when the
+// CTA ends. Measured: the loop reaches 82.8 % of the FMA pipe, the launch 75.8 % (default kernel: 78.0 %) — an opt-in
+// (RPE_UR=1), see profiles/r02_ur_scorer.md.
 //
 // A slice rarely is a whole number of T x P pairs (307 200 correspondences over 148 SMs: 2 076 pairs per CTA column against
 // 512 x 4 = 2 048), and the FMA pipe wants the same number of warps on all four schedulers of the SM (704 threads = 6 6 5 5
