@@ -581,7 +581,9 @@ def run_gpu(args, rank, world, local_rank):
                             "sample-table draw + rpe_upload(host page-locked) + rpe_ransac_async + rpe_refit_async x2 + "
                             "mask/pose D2H" + (" (inlier matrix sent as one bit per flag and expanded into the caller's "
                                                "16-bit matrix by the issuing threads, rpe_set_mask_transfer(1))"
-                                               if mask_bits_on() else "")},
+                                               if mask_bits_on() else "")
+                            + (" (the constant 2-D column of the inlier matrix is written by the issuing threads, only the 3-D "
+                               "column crosses the bus: rpe_set_mask_transfer(2))" if mask_mode() == 2 else "")},
             "gpu_launches": launches,
             "roofline": roofline,
             "stage_ms_mean": stage_mean,
@@ -666,8 +668,14 @@ def mask_bits_on():
     return os.environ.get("RPE_SEQ_MASK_BITS", "0")[:1] == "1"
 
 
+def mask_mode():
+    """RPE_SEQ_MASK_BITS: 0 the 16-bit matrix as it is, 1 bits + host expansion, 2 the constant 2-D column of the 3-D / 3-D
+    family stays on the device and the collecting thread writes it (rpe_set_mask_transfer)."""
+    return int(os.environ.get("RPE_SEQ_MASK_BITS", "0")[:1] or 0)
+
+
 def mask_d2h_bytes():
-    return 2 * ((N_CORR + 31) // 32) * 4 if mask_bits_on() else 2 * N_CORR * 2
+    return {0: 2 * N_CORR * 2, 1: 2 * ((N_CORR + 31) // 32) * 4, 2: N_CORR * 2}[mask_mode()]
 
 
 def measure_h2d_ceiling(rpe, torch, dist, dev, local_rank, h_xw, h_xc, barrier, seconds=0.25):

@@ -405,7 +405,11 @@ int rpe_enable_stage_timing(rpe_ctx* ctx, int enable);
  * with 1/16 of the device-to-host bytes on the bus, for 0.04-0.1 ms of host work per dense frame (measured, round 2: on
  * the 8-GPU box the concurrent-upload ceiling rises from 190 to 226 GB/s, but with 4 host cores per GPU the expansion
  * costs the issuing threads more than that — 21.1 k against 22.7 k frames/s — so this is an opt-in for hosts with
- * cores to spare). Blocking calls always copy the matrix. */
+ * cores to spare). Blocking calls always copy the matrix.
+ * mode 2: column 0 of a family without the 2-D test (RPE_SHINJI, RPE_NL_SHINJI) is a constant — 0 once a hypothesis has
+ * been accepted, the adapters' initial 1 otherwise (AOPoseAdapter.hpp: setInlier is fed a matrix whose 2-D column the loop
+ * never touches) — so it stays on the device and the collecting thread writes it (one std::fill of n shorts): half the
+ * device-to-host bytes of a dense 3-D / 3-D frame, blocking and asynchronous calls alike; the buffer holds the same matrix. */
 int rpe_set_mask_transfer(rpe_ctx* ctx, int mode);
 
 #ifdef __cplusplus

@@ -124,7 +124,7 @@ struct rpe_ctx {
   int16_t* d_mask = nullptr;
   uint32_t* d_maskbits = nullptr;  // the mask as one bit per flag (rpe_set_mask_transfer(1)), 3 x ceil(n / 32) words
   size_t maskbits_cap = 0;
-  int mask_transfer = 0;           // 0: the int16 matrix goes to the host as it is, 1: bits + expansion on the host
+  int mask_transfer = 0;           // 0: the int16 matrix goes to the host as it is, 1: bits + expansion on the host, 2: constant column 0 stays behind
   std::vector<uint32_t> bits_scratch;
   size_t mask_cap = 0;
   int mask_cols = 0;
@@ -145,6 +145,7 @@ struct rpe_ctx {
     bool is_refit, gn;
     int16_t* mask_expand = nullptr;  // bit form waiting in the tail of this host buffer (see expand_mask)
     int mask_n = 0, mask_cols = 0;
+    int16_t* mask_fill0 = nullptr;   // rpe_set_mask_transfer(2): column 0 was not copied, the collector writes its constant
   };
   std::deque<Pending> pending;
   int next_slot = 0;                      // staging slots are handed out round-robin
@@ -485,6 +486,11 @@ void deliver(rpe_ctx* ctx, const rpe_ctx::Pending& p) {
   fill_result(ctx, p.out, p.slot, p.is_refit, p.gn);
   note_overflow(ctx, p.slot);
   if (p.mask_expand) expand_mask(ctx, p.mask_expand, p.mask_n, p.mask_cols);
+  if (p.mask_fill0) {
+    // column 0 of a family without the 2-D test: 0 once a hypothesis has been accepted, the adapters' initial 1 otherwise
+    // (mask_kernel writes exactly this constant; it did not have to cross the bus)
+    std::fill_n(p.mask_fill0, (size_t)p.mask_n, (int16_t)(ctx->h_pose[p.slot].winner >= 0 ? 0 : 1));
+  }
 }
 
 int finish_pending(rpe_ctx* ctx) {
@@ -535,12 +541,13 @@ int claim_slot(rpe_ctx* ctx, int* slot) {
 }
 // the result whose copies were just enqueued becomes pending
 int push_pending(rpe_ctx* ctx, rpe_result* out, int slot, bool is_refit, bool gn, int16_t* mask_expand = nullptr, int mask_n = 0,
-                 int mask_cols = 0) {
+                 int mask_cols = 0, int16_t* mask_fill0 = nullptr) {
   CK(cudaEventRecord(ctx->ev_slot[slot], ctx->stream));
   rpe_ctx::Pending p{out, slot, is_refit, gn};
   p.mask_expand = mask_expand;
   p.mask_n = mask_n;
   p.mask_cols = mask_cols;
+  p.mask_fill0 = mask_fill0;
   ctx->pending.push_back(p);
   return RPE_OK;
 }
@@ -727,21 +734,26 @@ int do_finish(rpe_ctx* ctx, int method, Thresh th, rpe_result* out, int16_t* mas
     CK(cudaMemcpyAsync(reinterpret_cast<char*>(mask) + mask_bytes - wbytes, ctx->d_maskbits, wbytes, cudaMemcpyDeviceToHost, ctx->stream));
     return push_pending(ctx, out, slot, false, false, mask, ctx->n, ctx->mask_cols);
   }
+  int16_t* fill0 = nullptr;
   if (mask) {
-    const size_t bytes = mask_bytes;
+    // rpe_set_mask_transfer(2): column 0 of a family without the 2-D test is a constant the collector can write itself
+    const bool skip0 = ctx->mask_transfer == 2 && ctx->mask_cols >= 2 && !method_uses_2d(method) && mask_bytes >= (size_t)256 * 1024;
+    const size_t off = skip0 ? (size_t)ctx->n : 0;
+    const size_t bytes = mask_bytes - off * sizeof(int16_t);
+    if (skip0) fill0 = mask;
     if (ctx->d2h_stream && bytes >= (size_t)256 * 1024) {
       CK(cudaEventRecord(ctx->ev_mask_ready, ctx->stream));
       CK(cudaStreamWaitEvent(ctx->d2h_stream, ctx->ev_mask_ready, 0));
       // (one transfer: cutting it into pieces so that the refits' small result copies can slip in between was measured
       // slower — 0.438 against 0.412 ms per blocking frame, round 2)
-      CK(cudaMemcpyAsync(mask, ctx->d_mask, bytes, cudaMemcpyDeviceToHost, ctx->d2h_stream));
+      CK(cudaMemcpyAsync(mask + off, ctx->d_mask + off, bytes, cudaMemcpyDeviceToHost, ctx->d2h_stream));
       CK(cudaEventRecord(ctx->ev_mask_copied, ctx->d2h_stream));
       ctx->mask_copy_pending = true;
     } else {
-      CK(cudaMemcpyAsync(mask, ctx->d_mask, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+      CK(cudaMemcpyAsync(mask + off, ctx->d_mask + off, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     }
   }
-  if (int rcp = push_pending(ctx, out, slot, false, false)) return rcp;
+  if (int rcp = push_pending(ctx, out, slot, false, false, nullptr, ctx->n, ctx->mask_cols, fill0)) return rcp;
   if (blocking) {
     CK(sync_stream(ctx));
     finish_pending(ctx);
@@ -2210,7 +2222,7 @@ int rpe_measure_ffma_tflops(rpe_ctx* ctx, int ms_target, double* tflops_scalar, 
 }
 
 int rpe_set_mask_transfer(rpe_ctx* ctx, int mode) {
-  if (!ctx || mode < 0 || mode > 1) return RPE_ERR_ARG;
+  if (!ctx || mode < 0 || mode > 2) return RPE_ERR_ARG;
   ctx->mask_transfer = mode;
   return RPE_OK;
 }

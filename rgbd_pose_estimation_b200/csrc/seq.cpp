@@ -238,8 +238,9 @@ int rpe_seq_create(const rpe_seq_params* params, rpe_seq** out) {
     // RPE_SEQ_MASK_BITS=1: masks travel as bits and are expanded by the issuing threads (rpe_set_mask_transfer). Off by
     // default: on the 8-GPU box (4 host cores per GPU) the expansion costs the issuing threads more than the bus gains —
     // 21.1 k against 22.7 k frames/s, although the concurrent-upload ceiling rises from 190 to 226 GB/s (round 2).
-    static const bool bits = getenv("RPE_SEQ_MASK_BITS") && getenv("RPE_SEQ_MASK_BITS")[0] == '1';
-    if (bits) rpe_set_mask_transfer(sc.ctx, 1);
+    // RPE_SEQ_MASK_BITS=2: the constant column 0 of the 3-D / 3-D family stays on the device (rpe_set_mask_transfer(2)).
+    static const int mask_mode = getenv("RPE_SEQ_MASK_BITS") ? getenv("RPE_SEQ_MASK_BITS")[0] - '0' : 0;
+    if (mask_mode == 1 || mask_mode == 2) rpe_set_mask_transfer(sc.ctx, mask_mode);
     if (cudaMallocHost(&sc.tables, (size_t)kTableSlots * s->p.H * 4 * sizeof(int32_t)) != cudaSuccess) {
       rc = RPE_ERR_NOMEM;
       break;

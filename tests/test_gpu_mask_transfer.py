@@ -78,3 +78,53 @@ def test_bit_form_mask_when_nothing_is_accepted(rpe):
             assert r.winner < 0
     assert np.array_equal(np.asarray(m0), np.asarray(m1))
     assert np.asarray(m1).min() == 1
+
+
+@pytest.mark.parametrize("method,n", [("shinji", 307200), ("shinji", 131077), ("nl_shinji", 150031), ("shinji_kneip", 140001)])
+def test_constant_column_stays_on_the_device(rpe, method, n):
+    """rpe_set_mask_transfer(2): column 0 of a family without the 2-D test is written by the collecting thread, the other
+    columns cross the bus; families with the 2-D test are copied whole. Same matrix as the plain copy, blocking and asynchronous."""
+    cols = {"shinji": 2, "nl_shinji": 3, "shinji_kneip": 2}[method]
+    H = 256
+    f = _frame(rpe, n, 700 + n % 89)
+    S = _pinned(rpe, rpe.sample_table(3, n, rpe.method_sample_size(rpe.METHODS[method]), H))
+    m_plain = rpe.pinned_empty((cols, n), np.int16)
+    m_skip = rpe.pinned_empty((cols, n), np.int16)
+    with rpe.Context(0) as a, rpe.Context(0) as b:
+        b.set_mask_transfer(2)
+        for ctx, m in ((a, m_plain), (b, m_skip)):
+            m[:] = -7
+            ctx.upload_async(**f)
+            r = ctx.ransac_async(method, S, confidence=0.99, mask=m, **TH)
+            ctx.refit_async("gn", max_iters=2)
+            ctx.sync()
+            assert r.winner >= 0
+        assert np.array_equal(np.asarray(m_plain), np.asarray(m_skip))
+        masks = [rpe.pinned_empty((cols, n), np.int16) for _ in range(3)]
+        for m in masks:
+            m[:] = -7
+            b.upload_async(**f)
+            b.ransac_async(method, S, confidence=0.99, mask=m, **TH)
+            b.poll()
+        b.sync()
+        for m in masks:
+            assert np.array_equal(np.asarray(m), np.asarray(m_plain))
+        b.upload(**{k: np.asarray(v) for k, v in f.items()})
+        w = b.ransac(method, np.asarray(S), confidence=0.99, **TH)   # blocking call
+        assert np.array_equal(w["mask"], np.asarray(m_plain))
+
+
+def test_constant_column_when_nothing_is_accepted(rpe):
+    n, H = 140003, 64
+    Q = np.full((n, 3), np.nan, np.float32)
+    P = np.full((n, 3), np.nan, np.float32)
+    S = rpe.sample_table(5, n, 3, H)
+    m = rpe.pinned_empty((2, n), np.int16)
+    with rpe.Context(0) as b:
+        b.set_mask_transfer(2)
+        m[:] = -7
+        b.upload(xc=P, xw=Q)
+        r = b.ransac_async("shinji", S, thr3d=0.25, confidence=0.99, mask=m)
+        b.sync()
+        assert r.winner < 0
+    assert np.asarray(m).min() == 1 and np.asarray(m).max() == 1
