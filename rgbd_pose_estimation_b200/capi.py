@@ -805,7 +805,8 @@ class Context:
 
     def set_mask_transfer(self, mode):
         """0: asynchronous calls copy the int16 inlier matrix as it is; 1: they send one bit per flag and the collecting
-        thread expands it in place (same matrix in the caller's buffer after sync / poll, 1/16 of the D2H bytes)."""
+        thread expands it in place (same matrix in the caller's buffer after sync / poll, 1/16 of the D2H bytes); 2: the
+        constant 2-D column of a family without the 2-D test stays on the device and the collecting thread writes it."""
         _check(lib.rpe_set_mask_transfer(self._h, int(mode)), self._h)
 
     def poll(self):
